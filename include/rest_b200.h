@@ -1,0 +1,221 @@
+/*
+ * rest_b200.h -- C ABI of librest_b200.so, the B200 (sm_100a) implementation of the rest_tensors RI hot path.
+ *
+ * Two families of entry points:
+ *
+ *  (1) COMPAT symbols -- exactly the symbols the reference's Rust FFI binds to its Fortran librestmatr
+ *      (reference src/external_libs/ffi_restmatr.rs:4-62; linked by name through build.rs:34
+ *      `cargo:rustc-link-lib=restmatr`).  gfortran ABI: every argument by pointer, 32-bit ints, no hidden
+ *      string-length argument (the Rust side passes none, src/external_libs/mod.rs:70,75).  All data
+ *      pointers are HOST pointers; the call uploads, runs the CUDA kernels and downloads before returning.
+ *      They return void like the Fortran; on a CUDA failure they print rb_last_error() and abort()
+ *      (the same contract as BLAS xerbla).
+ *
+ *  (2) rb_* API -- status-returning.  `rb_host_*` take HOST pointers and mirror the reference's safe Rust
+ *      wrappers around OpenBLAS (src/matrix/matrix_blas_lapack.rs) and its pure-Rust pack/unpack/transposes.
+ *      The remaining rb_* take DEVICE pointers (column-major FP64, 8-byte aligned; 16-byte alignment and even
+ *      leading dimensions enable the TMA fast path) and run asynchronously on the context's stream, so that
+ *      ri3ao can stay resident (and P-sharded) in HBM across SCF iterations.
+ *
+ * All matrices/tensors are column-major, exactly as in the reference (RIFull: x + y*s0 + z*s0*s1,
+ * src/ri.rs:18-40; MatrixFull: i + j*rows, src/matrix/mod.rs:472-480; MatrixUpper: j(j+1)/2+i,
+ * src/index.rs:209-226).
+ *
+ * There is no CPU fallback anywhere in this library: with no usable CUDA device every entry point fails
+ * (rb_* return RB_ERR_CUDA, compat symbols abort).
+ */
+#ifndef REST_B200_H
+#define REST_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RB_OK 0
+#define RB_ERR_INVALID 1     /* bad argument / shape mismatch (the Rust wrappers panic on these) */
+#define RB_ERR_CUDA 2        /* CUDA runtime / driver failure, or no device */
+#define RB_ERR_UNSUPPORTED 3 /* valid request this build does not implement */
+#define RB_ERR_NOMEM 4
+
+typedef struct rb_ctx rb_ctx;
+
+/* ---- library / context ------------------------------------------------------------------------------- */
+int rb_version(void);
+const char *rb_last_error(void); /* thread-local message of the last failing call on this thread */
+int rb_device_count(void);
+
+int rb_ctx_create(int device, rb_ctx **out);
+int rb_ctx_destroy(rb_ctx *ctx);
+/* Run subsequent calls on `cuda_stream` (a cudaStream_t, e.g. torch's current stream); NULL = the ctx's own. */
+int rb_ctx_set_stream(rb_ctx *ctx, void *cuda_stream);
+int rb_ctx_sync(rb_ctx *ctx);
+int rb_ctx_num_sms(rb_ctx *ctx);
+/* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
+int64_t rb_ctx_launch_count(rb_ctx *ctx);
+/* Select the GEMM implementation: 0 = auto (TMA+DMMA when alignment allows, else generic DMMA), 1 = force generic. */
+int rb_ctx_set_gemm_path(rb_ctx *ctx, int path);
+
+/* device memory helpers for hosts without their own allocator (Rust/C++ side) */
+int rb_dev_alloc(rb_ctx *ctx, int64_t bytes, void **out);
+int rb_dev_free(rb_ctx *ctx, void *p);
+int rb_host_alloc_pinned(int64_t bytes, void **out);
+int rb_host_free_pinned(void *p);
+int rb_memcpy_h2d(rb_ctx *ctx, void *dst, const void *src, int64_t bytes); /* async on the ctx stream */
+int rb_memcpy_d2h(rb_ctx *ctx, void *dst, const void *src, int64_t bytes);
+
+/* ---- (1) COMPAT: reference src/external_libs/ffi_restmatr.rs:4-62 == restmatr.f90 ---------------------- */
+
+/* ffi_restmatr.rs:5-11 / restmatr.f90:158-194:
+ * ri3mo[P + a*nx + b*nx*ns] = sum_mu C[mu,a] sum_nu ri3fn[mu,nu,P] C[nu,b];  ri3mo fully overwritten.
+ * The Fortran is only defined for num_states == num_basis (it passes ldc=num_basis for an ns x ns section);
+ * this implementation gives the same result there and the natural rectangular result otherwise. */
+void ri_ao2mo_f_(const double *eigenvector, const double *ri3fn, double *ri3mo, const int *num_states,
+                 const int *num_basis, const int *num_auxbas);
+
+/* ffi_restmatr.rs:13-24 / restmatr.f90:63-107: C[rc,cc] = alpha*op(A[ra,ca])*op(B[rb,cb]) + beta*C[rc,cc];
+ * starts are 0-based; elements of C outside the block are untouched; op chars 'N' | 'T'. */
+void general_dgemm_f_(const double *matr_a, const int *rows_a, const int *columns_a, const int *start_row_a,
+                      const int *len_row_a, const int *start_column_a, const int *len_column_a, const char *opa,
+                      const double *matr_b, const int *rows_b, const int *columns_b, const int *start_row_b,
+                      const int *len_row_b, const int *start_column_b, const int *len_column_b, const char *opb,
+                      double *matr_c, const int *rows_c, const int *columns_c, const int *start_row_c,
+                      const int *len_row_c, const int *start_column_c, const int *len_column_c, const double *alpha,
+                      const double *beta);
+
+/* ffi_restmatr.rs:25-33 / restmatr.f90:111-154: for every y, in place:
+ * T[xr, y, zr] <- alpha * T[xr, y, zr] * B[rb, cb] + beta * T[xr, y, zr]   (needs len_column_b == len_z_a). */
+void special_dgemm_f_01_(double *ten3_a, const int *x_a, const int *y_a, const int *z_a, const int *start_x_a,
+                         const int *len_x_a, const int *i_y, const int *start_z_a, const int *len_z_a,
+                         const double *matr_b, const int *rows_b, const int *columns_b, const int *start_row_b,
+                         const int *len_row_b, const int *start_column_b, const int *len_column_b,
+                         const double *alpha, const double *beta);
+
+/* ffi_restmatr.rs:35-39 / restmatr.f90:197-212 */
+void copy_mm_(const int *x_len, const int *y_len, const double *f_matr, const int *f_x_len, const int *f_y_len,
+              const int *f_x_start, const int *f_y_start, double *t_matr, const int *t_x_len, const int *t_y_len,
+              const int *t_x_start, const int *t_y_start);
+/* ffi_restmatr.rs:41-46 / restmatr.f90:215-238; mod 0: t(x1,x2,x3) 1: t(x1,x3,x2) 2: t(x3,x1,x2); else no-op */
+void copy_mr_(const int *x_len, const int *y_len, const double *f_matr, const int *f_x_len, const int *f_y_len,
+              const int *f_x_start, const int *f_y_start, double *t_ri, const int *t_x_len, const int *t_y_len,
+              const int *t_z_len, const int *t_x_start, const int *t_y_start, const int *t_x3, const int *t_mod);
+/* ffi_restmatr.rs:48-53 / restmatr.f90:241-264 */
+void copy_rm_(const int *x_len, const int *y_len, const double *f_ri, const int *f_x_len, const int *f_y_len,
+              const int *f_z_len, const int *f_x_start, const int *f_y_start, const int *f_x3, const int *f_mod,
+              double *t_matr, const int *t_x_len, const int *t_y_len, const int *t_x_start, const int *t_y_start);
+/* ffi_restmatr.rs:55-61 / restmatr.f90:266-285 */
+void copy_rr_(const int *x_len, const int *y_len, const int *z_len, const double *f_ri, const int *f_x_len,
+              const int *f_y_len, const int *f_z_len, const int *f_x_start, const int *f_y_start,
+              const int *f_z_start, double *t_ri, const int *t_x_len, const int *t_y_len, const int *t_z_len,
+              const int *t_x_start, const int *t_y_start, const int *t_z_start);
+
+/* ---- (2a) HOST-pointer wrappers of the reference's BLAS / layout calls --------------------------------- */
+/* These use a process-wide default context on device $REST_B200_DEVICE (default 0) and serialise on a mutex. */
+
+/* blas::dgemm as called from _dgemm_full / lapack_dgemm / ddot (matrix_blas_lapack.rs:180-252,714-774) */
+int rb_host_dgemm(char transa, char transb, int m, int n, int k, double alpha, const double *a, int lda,
+                  const double *b, int ldb, double beta, double *c, int ldc);
+/* blas::dsyrk as called from _dsyrk (matrix_blas_lapack.rs:392-413): only the uplo triangle of C is touched */
+int rb_host_dsyrk(char uplo, char trans, int n, int k, double alpha, const double *a, int lda, double beta,
+                  double *c, int ldc);
+/* blas::dgemv as called from _dgemv (matrix_blas_lapack.rs:38-70) */
+int rb_host_dgemv(char trans, int m, int n, double alpha, const double *a, int lda, const double *x, int incx,
+                  double beta, double *y, int incy);
+/* blas::dsymm as called from _dsymm (matrix_blas_lapack.rs:354-378) */
+int rb_host_dsymm(char side, char uplo, int m, int n, double alpha, const double *a, int lda, const double *b,
+                  int ldb, double beta, double *c, int ldc);
+/* MatrixFull::to_matrixupper (matrixfull.rs:638-646): packed[j(j+1)/2+i] = full[i+j*n], i<=j */
+int rb_host_to_matrixupper(const double *full, int64_t n, double *packed);
+/* MatrixUpper::to_matrixfull (matrixupper.rs:330-373): len must be triangular (else RB_ERR_INVALID == None) */
+int rb_host_to_matrixfull(const double *packed, int64_t len, double *full);
+/* RIFull::rifull_to_matfull_symm (ri.rs:297-341) */
+int rb_host_ri_pack_symm(const double *ri, int64_t nao, int64_t naux, double *out);
+/* RIFull::transpose_{jik,jki,kji,ikj} (ri.rs:227-294); which = 0,1,2,3 */
+int rb_host_ri_transpose(const double *in, int64_t i, int64_t j, int64_t k, int which, double *out);
+/* MatrixFull::transpose (matrixfull.rs:579-614) */
+int rb_host_matrix_transpose(const double *in, int64_t rows, int64_t cols, double *out);
+/* Rectangular ao2mo (north-star occ-vir form): out[P + a*nx + b*nx*nl] = sum C_L[mu,a] A[mu,nu,P] C_R[nu,b] */
+int rb_host_ri_ao2mo(const double *c_left, int nl, const double *c_right, int nr, const double *ri3ao, double *out,
+                     int nb, int nx);
+/* axpy family on host buffers (matrix/mod.rs:545-648, ri.rs:345-354, matrixupper.rs:395-420):
+ * op 0: c += p*b   1: c = c*a + p*b   2: c *= a   3: c += p   4: c -= p   (unfused mul-then-add, bit-exact) */
+int rb_host_axpy(int op, double *c, const double *p, double a, double b, int64_t n);
+/* d_P, J, K with host buffers (composed by REST from _dgemv/_dgemm/_dsyrk) */
+int rb_host_ri_dp(const double *ri3ao, const double *dm, double *d, int nb, int nx);
+int rb_host_ri_j(const double *ri3ao, const double *d, double *j, int nb, int nx);
+int rb_host_ri_k(const double *ri3ao, const double *ct, int no, double *k, int nb, int nx);
+
+/* ---- (2b) DEVICE-pointer API (async on the ctx stream) -------------------------------------------------- */
+
+/* BLAS-3/2 on device buffers; same argument meaning as the Fortran BLAS. */
+int rb_dgemm(rb_ctx *ctx, char transa, char transb, int m, int n, int k, double alpha, const double *a, int64_t lda,
+             const double *b, int64_t ldb, double beta, double *c, int64_t ldc);
+int rb_dgemm_strided_batched(rb_ctx *ctx, char transa, char transb, int m, int n, int k, double alpha,
+                             const double *a, int64_t lda, int64_t stride_a, const double *b, int64_t ldb,
+                             int64_t stride_b, double beta, double *c, int64_t ldc, int64_t stride_c, int batch);
+int rb_dsyrk(rb_ctx *ctx, char uplo, char trans, int n, int k, double alpha, const double *a, int64_t lda,
+             double beta, double *c, int64_t ldc);
+int rb_dgemv(rb_ctx *ctx, char trans, int m, int n, double alpha, const double *a, int64_t lda, const double *x,
+             int incx, double beta, double *y, int incy);
+int rb_dsymm(rb_ctx *ctx, char side, char uplo, int m, int n, double alpha, const double *a, int64_t lda,
+             const double *b, int64_t ldb, double beta, double *c, int64_t ldc);
+
+/* RI contractions over the local slabs ri3ao[nb, nb, nx] (one rank's P-shard).
+ * ao2mo: out[P + a*out_ldp + b*out_ldp*nl], P in [0,nx): out_ldp >= nx lets a rank write its rows of a larger
+ *        (e.g. global-naux) tensor.  c_left [nb,nl], c_right [nb,nr]; square reference semantics: both = C, nl=nr=ns. */
+int rb_ri_ao2mo(rb_ctx *ctx, const double *c_left, int nl, const double *c_right, int nr, const double *ri3ao,
+                double *out, int nb, int nx, int64_t out_ldp);
+/* d[P] = sum_{mu,nu} ri3ao[mu,nu,P]*dm[mu,nu] */
+int rb_ri_dp(rb_ctx *ctx, const double *ri3ao, const double *dm, double *d, int nb, int nx);
+/* j[mu,nu] = sum_P ri3ao[mu,nu,P]*d[P]  (this rank's partial sum; all-reduce across ranks) */
+int rb_ri_j(rb_ctx *ctx, const double *ri3ao, const double *d, double *j, int nb, int nx);
+/* k = sum_P (A_P ct)(A_P ct)^T, ct [nb,no]; full symmetric nb x nb (both triangles written); partial per rank */
+int rb_ri_k(rb_ctx *ctx, const double *ri3ao, const double *ct, int no, double *k, int nb, int nx);
+/* in-place slab x matrix of restmatr.f90:111-154 on device buffers */
+int rb_special_dgemm_01(rb_ctx *ctx, double *ten3, int x_a, int y_a, int z_a, int start_x, int len_x, int start_z,
+                        int len_z, const double *b, int64_t ldb, int len_col_b, double alpha, double beta);
+
+/* pack / unpack (bit-exact) */
+int rb_pack_upper(rb_ctx *ctx, const double *full, int64_t n, double *packed);
+int rb_unpack_upper(rb_ctx *ctx, const double *packed, int64_t n, double *full);
+int rb_ri_pack_symm(rb_ctx *ctx, const double *ri, int64_t nao, int64_t naux, double *out);
+
+/* strided sub-box copies (bit-exact); same argument order as copy_mm_/copy_mr_/copy_rm_/copy_rr_ but by value */
+int rb_copy_mm(rb_ctx *ctx, int x_len, int y_len, const double *f, int f_x_len, int f_y_len, int f_x_start,
+               int f_y_start, double *t, int t_x_len, int t_y_len, int t_x_start, int t_y_start);
+int rb_copy_mr(rb_ctx *ctx, int x_len, int y_len, const double *f, int f_x_len, int f_y_len, int f_x_start,
+               int f_y_start, double *t, int t_x_len, int t_y_len, int t_z_len, int t_x_start, int t_y_start,
+               int t_x3, int mod);
+int rb_copy_rm(rb_ctx *ctx, int x_len, int y_len, const double *f, int f_x_len, int f_y_len, int f_z_len,
+               int f_x_start, int f_y_start, int f_x3, int mod, double *t, int t_x_len, int t_y_len, int t_x_start,
+               int t_y_start);
+int rb_copy_rr(rb_ctx *ctx, int x_len, int y_len, int z_len, const double *f, int f_x_len, int f_y_len, int f_z_len,
+               int f_x_start, int f_y_start, int f_z_start, double *t, int t_x_len, int t_y_len, int t_z_len,
+               int t_x_start, int t_y_start, int t_z_start);
+
+/* transposes (bit-exact) */
+int rb_ri_transpose(rb_ctx *ctx, const double *in, int64_t i, int64_t j, int64_t k, int which, double *out);
+int rb_matrix_transpose(rb_ctx *ctx, const double *in, int64_t rows, int64_t cols, double *out);
+
+/* axpy family (matrix/mod.rs:545-648, ri.rs:345-354); unfused mul-then-add, bit-exact vs the Rust loops */
+int rb_self_scaled_add(rb_ctx *ctx, double *c, const double *p, double b, int64_t n);               /* c += p*b   */
+int rb_self_general_add(rb_ctx *ctx, double *c, const double *p, double a, double b, int64_t n);    /* c = c*a+p*b */
+int rb_self_multiple(rb_ctx *ctx, double *c, double a, int64_t n);                                  /* c *= a     */
+int rb_self_add(rb_ctx *ctx, double *c, const double *p, int64_t n);                                /* c += p     */
+int rb_self_sub(rb_ctx *ctx, double *c, const double *p, int64_t n);                                /* c -= p     */
+
+/* counter-based synthetic inputs generated in HBM; bit-identical to oracle/rest_oracle.c */
+int rb_fill_linear(rb_ctx *ctx, double *v, int64_t n, uint64_t seed, uint64_t idx0, double scale);
+int rb_fill_ri3ao_symm(rb_ctx *ctx, double *a, int64_t nb, int64_t p_lo, int64_t p_hi, uint64_t seed, double scale);
+
+/* FP64 pipe micro-benchmarks used by bench.py for the roofline denominator: returns achieved TFLOP/s of a
+ * register-resident DMMA (kind=0) or DFMA (kind=1) loop over the whole chip, timed with CUDA events. */
+int rb_fp64_peak_probe(rb_ctx *ctx, int kind, int iters, double *tflops_out, double *ms_out);
+/* Stream copy probe (read+write bytes / time) for the HBM denominator cross-check. */
+int rb_hbm_copy_probe(rb_ctx *ctx, int64_t bytes, int iters, double *gbs_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REST_B200_H */

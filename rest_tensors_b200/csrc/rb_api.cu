@@ -1,0 +1,267 @@
+// rb_api.cu -- context, error reporting, memory helpers, FP64/HBM probes.
+#include "rb_common.cuh"
+#include <cstring>
+
+static thread_local char g_err[1024] = "";
+
+void rb_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *rb_last_error(void) { return g_err; }
+extern "C" int rb_version(void) { return 100; }
+
+extern "C" int rb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int rb_ctx_create(int device, rb_ctx **out)
+{
+    RB_REQUIRE(out != nullptr, "rb_ctx_create: out is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        rb_set_error("rb_ctx_create: no CUDA device available (%s); librest_b200 has no CPU fallback",
+                     e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+        return RB_ERR_CUDA;
+    }
+    RB_REQUIRE(device >= 0 && device < n, "rb_ctx_create: device %d out of range [0,%d)", device, n);
+    RB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    RB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        rb_set_error("rb_ctx_create: device %d is sm_%d%d; this library contains sm_100a code only", device,
+                     prop.major, prop.minor);
+        return RB_ERR_CUDA;
+    }
+    rb_ctx *c = new rb_ctx();
+    c->device = device;
+    c->num_sms = prop.multiProcessorCount;
+    RB_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    RB_CUDA(cudaEventCreate(&c->ev0));
+    RB_CUDA(cudaEventCreate(&c->ev1));
+    // cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link against libcuda).
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) c->encode_tiled = (rb_encode_tiled_fn)fn;
+    else cudaGetLastError();
+    *out = c;
+    return RB_OK;
+}
+
+extern "C" int rb_ctx_destroy(rb_ctx *ctx)
+{
+    if (!ctx) return RB_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int s = 0; s < 4; ++s) if (ctx->ws[s]) cudaFree(ctx->ws[s]);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return RB_OK;
+}
+
+extern "C" int rb_ctx_set_stream(rb_ctx *ctx, void *cuda_stream)
+{
+    RB_REQUIRE(ctx, "rb_ctx_set_stream: ctx is NULL");
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return RB_OK;
+}
+
+extern "C" int rb_ctx_sync(rb_ctx *ctx)
+{
+    RB_REQUIRE(ctx, "rb_ctx_sync: ctx is NULL");
+    RB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return RB_OK;
+}
+
+extern "C" int rb_ctx_num_sms(rb_ctx *ctx) { return ctx ? ctx->num_sms : 0; }
+extern "C" int64_t rb_ctx_launch_count(rb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int rb_ctx_set_gemm_path(rb_ctx *ctx, int path)
+{
+    RB_REQUIRE(ctx, "rb_ctx_set_gemm_path: ctx is NULL");
+    ctx->gemm_path = path;
+    return RB_OK;
+}
+
+int rb_ws_reserve(rb_ctx *ctx, int slot, i64 bytes, void **out)
+{
+    if (bytes > ctx->ws_bytes[slot]) {
+        RB_CUDA(cudaSetDevice(ctx->device));
+        RB_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->ws[slot]) { RB_CUDA(cudaFree(ctx->ws[slot])); ctx->ws[slot] = nullptr; ctx->ws_bytes[slot] = 0; }
+        cudaError_t e = cudaMalloc(&ctx->ws[slot], (size_t)bytes);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            rb_set_error("workspace allocation of %lld bytes failed: %s", (long long)bytes, cudaGetErrorString(e));
+            return RB_ERR_NOMEM;
+        }
+        ctx->ws_bytes[slot] = bytes;
+    }
+    *out = ctx->ws[slot];
+    return RB_OK;
+}
+
+extern "C" int rb_dev_alloc(rb_ctx *ctx, int64_t bytes, void **out)
+{
+    RB_REQUIRE(ctx && out && bytes >= 0, "rb_dev_alloc: bad arguments");
+    RB_CUDA(cudaSetDevice(ctx->device));
+    *out = nullptr;
+    if (bytes == 0) return RB_OK;
+    cudaError_t e = cudaMalloc(out, (size_t)bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        rb_set_error("rb_dev_alloc(%lld) failed: %s", (long long)bytes, cudaGetErrorString(e));
+        return RB_ERR_NOMEM;
+    }
+    return RB_OK;
+}
+extern "C" int rb_dev_free(rb_ctx *ctx, void *p)
+{
+    RB_REQUIRE(ctx, "rb_dev_free: ctx is NULL");
+    if (p) RB_CUDA(cudaFree(p));
+    return RB_OK;
+}
+extern "C" int rb_host_alloc_pinned(int64_t bytes, void **out)
+{
+    RB_REQUIRE(out && bytes >= 0, "rb_host_alloc_pinned: bad arguments");
+    *out = nullptr;
+    if (bytes == 0) return RB_OK;
+    RB_CUDA(cudaMallocHost(out, (size_t)bytes));
+    return RB_OK;
+}
+extern "C" int rb_host_free_pinned(void *p)
+{
+    if (p) RB_CUDA(cudaFreeHost(p));
+    return RB_OK;
+}
+extern "C" int rb_memcpy_h2d(rb_ctx *ctx, void *dst, const void *src, int64_t bytes)
+{
+    RB_REQUIRE(ctx, "rb_memcpy_h2d: ctx is NULL");
+    if (bytes > 0) RB_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return RB_OK;
+}
+extern "C" int rb_memcpy_d2h(rb_ctx *ctx, void *dst, const void *src, int64_t bytes)
+{
+    RB_REQUIRE(ctx, "rb_memcpy_d2h: ctx is NULL");
+    if (bytes > 0) RB_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return RB_OK;
+}
+
+// ---- default context for host-pointer entry points -----------------------------------------------------
+static rb_ctx *g_default = nullptr;
+static std::mutex g_default_mutex;
+std::mutex &rb_default_mutex(void) { return g_default_mutex; }
+rb_ctx *rb_default_ctx(void)
+{
+    if (!g_default) {
+        int dev = 0;
+        const char *env = getenv("REST_B200_DEVICE");
+        if (env) dev = atoi(env);
+        rb_ctx *c = nullptr;
+        if (rb_ctx_create(dev, &c) != RB_OK) return nullptr;
+        g_default = c;
+    }
+    cudaSetDevice(g_default->device);
+    return g_default;
+}
+
+// ---- probes ------------------------------------------------------------------------------------------------
+// Register-resident FP64 pipe probes: the roofline denominator for the DMMA kernels is measured, not assumed.
+template <int KIND>
+__global__ void __launch_bounds__(256) rb_fp64_probe_kernel(double *sink, int iters, double seed)
+{
+    // 16 independent accumulator tiles per warp keep the pipe full regardless of its latency.
+    double c[16][2];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { c[i][0] = seed * i; c[i][1] = seed; }
+    double a = seed + threadIdx.x * 1e-9, b = seed - threadIdx.x * 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            if (KIND == 0) {
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(c[i][0]), "+d"(c[i][1])
+                             : "d"(a), "d"(b));
+            } else {
+                c[i][0] = fma(a, b, c[i][0]);
+                c[i][1] = fma(b, a, c[i][1]);
+            }
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += c[i][0] + c[i][1];
+    if (s == 123.456) sink[0] = s; // never true; keeps the loop alive
+}
+
+extern "C" int rb_fp64_peak_probe(rb_ctx *ctx, int kind, int iters, double *tflops_out, double *ms_out)
+{
+    RB_REQUIRE(ctx && tflops_out, "rb_fp64_peak_probe: bad arguments");
+    RB_REQUIRE(kind == 0 || kind == 1, "rb_fp64_peak_probe: kind must be 0 (DMMA) or 1 (DFMA)");
+    RB_CUDA(cudaSetDevice(ctx->device));
+    void *sink;
+    RB_TRY(rb_ws_reserve(ctx, 3, 256, &sink));
+    const int blocks = ctx->num_sms * 2, threads = 256;
+    for (int rep = 0; rep < 2; ++rep) { // rep 0 = warm-up
+        RB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+        if (kind == 0) rb_fp64_probe_kernel<0><<<blocks, threads, 0, ctx->stream>>>((double *)sink, iters, 1e-3);
+        else rb_fp64_probe_kernel<1><<<blocks, threads, 0, ctx->stream>>>((double *)sink, iters, 1e-3);
+        RB_LAUNCHED(ctx);
+        RB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+        RB_CUDA(cudaEventSynchronize(ctx->ev1));
+    }
+    float ms = 0;
+    RB_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    // DMMA m8n8k4: 8*8*4 FMA = 512 flop per warp-instruction; DFMA: 2 flop per thread-instruction, 2 per tile here.
+    double flop;
+    if (kind == 0) flop = (double)blocks * (threads / 32) * (double)iters * 16.0 * 512.0;
+    else flop = (double)blocks * threads * (double)iters * 16.0 * 2.0 * 2.0;
+    *tflops_out = flop / (ms * 1e-3) / 1e12;
+    if (ms_out) *ms_out = ms;
+    return RB_OK;
+}
+
+__global__ void __launch_bounds__(256) rb_copy_probe_kernel(const double2 *__restrict__ src, double2 *__restrict__ dst,
+                                                            i64 n2)
+{
+    i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) dst[i] = src[i];
+}
+
+extern "C" int rb_hbm_copy_probe(rb_ctx *ctx, int64_t bytes, int iters, double *gbs_out)
+{
+    RB_REQUIRE(ctx && gbs_out && bytes >= 32 && iters > 0, "rb_hbm_copy_probe: bad arguments");
+    RB_CUDA(cudaSetDevice(ctx->device));
+    void *buf;
+    i64 half = (bytes / 2) & ~(i64)15;
+    RB_TRY(rb_ws_reserve(ctx, 3, half * 2, &buf));
+    const double2 *src = (const double2 *)buf;
+    double2 *dst = (double2 *)((char *)buf + half);
+    i64 n2 = half / 16;
+    int blocks = ctx->num_sms * 8;
+    rb_copy_probe_kernel<<<blocks, 256, 0, ctx->stream>>>(src, dst, n2);
+    RB_LAUNCHED(ctx);
+    RB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    for (int i = 0; i < iters; ++i) {
+        rb_copy_probe_kernel<<<blocks, 256, 0, ctx->stream>>>(src, dst, n2);
+        RB_LAUNCHED(ctx);
+    }
+    RB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    RB_CUDA(cudaEventSynchronize(ctx->ev1));
+    float ms = 0;
+    RB_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    *gbs_out = (double)half * 2.0 * iters / (ms * 1e-3) / 1e9;
+    return RB_OK;
+}

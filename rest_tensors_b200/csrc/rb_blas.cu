@@ -1,0 +1,275 @@
+// rb_blas.cu -- device-pointer BLAS-3/2 entry points with the Fortran BLAS argument meaning the reference's
+// wrappers use (src/matrix/matrix_blas_lapack.rs:38-70 _dgemv, 180-252 _dgemm_full, 354-378 _dsymm, 392-413 _dsyrk).
+// Level-3 goes through the DMMA GEMM core; level-2 (GEMV) is HBM-bound and runs as coalesced, vectorised
+// kernels with warp-shuffle + fixed-order block reductions (deterministic: no FP64 atomics).
+#include "rb_common.cuh"
+
+extern "C" int rb_dgemm_strided_batched(rb_ctx *ctx, char transa, char transb, int m, int n, int k, double alpha,
+                                        const double *a, int64_t lda, int64_t stride_a, const double *b, int64_t ldb,
+                                        int64_t stride_b, double beta, double *c, int64_t ldc, int64_t stride_c,
+                                        int batch)
+{
+    RB_REQUIRE(ctx, "rb_dgemm: ctx is NULL");
+    RB_REQUIRE((rb_is_n(transa) || rb_is_t(transa)) && (rb_is_n(transb) || rb_is_t(transb)),
+               "rb_dgemm: trans must be 'N' or 'T' (got '%c','%c')", transa, transb);
+    RB_REQUIRE(m >= 0 && n >= 0 && k >= 0 && batch >= 0, "rb_dgemm: negative dimension");
+    RB_CUDA(cudaSetDevice(ctx->device));
+    return rb_gemm_core(ctx, rb_is_t(transa), rb_is_t(transb), m, n, k, alpha, a, lda, stride_a, b, ldb, stride_b, beta,
+                        c, ldc, stride_c, batch, 0);
+}
+
+extern "C" int rb_dgemm(rb_ctx *ctx, char transa, char transb, int m, int n, int k, double alpha, const double *a,
+                        int64_t lda, const double *b, int64_t ldb, double beta, double *c, int64_t ldc)
+{
+    return rb_dgemm_strided_batched(ctx, transa, transb, m, n, k, alpha, a, lda, 0, b, ldb, 0, beta, c, ldc, 0, 1);
+}
+
+// C := alpha*A*A^T + beta*C ('N', A n x k) or alpha*A^T*A + beta*C ('T', A k x n); only `uplo` triangle touched.
+extern "C" int rb_dsyrk(rb_ctx *ctx, char uplo, char trans, int n, int k, double alpha, const double *a, int64_t lda,
+                        double beta, double *c, int64_t ldc)
+{
+    RB_REQUIRE(ctx, "rb_dsyrk: ctx is NULL");
+    RB_REQUIRE(rb_is_u(uplo) || rb_is_l(uplo), "rb_dsyrk: uplo must be 'U' or 'L'");
+    RB_REQUIRE(rb_is_n(trans) || rb_is_t(trans), "rb_dsyrk: trans must be 'N' or 'T'");
+    RB_REQUIRE(n >= 0 && k >= 0, "rb_dsyrk: negative dimension");
+    RB_CUDA(cudaSetDevice(ctx->device));
+    const int tri = rb_is_u(uplo) ? 1 : 2;
+    if (rb_is_n(trans)) return rb_gemm_core(ctx, false, true, n, n, k, alpha, a, lda, 0, a, lda, 0, beta, c, ldc, 0, 1, tri);
+    return rb_gemm_core(ctx, true, false, n, n, k, alpha, a, lda, 0, a, lda, 0, beta, c, ldc, 0, 1, tri);
+}
+
+// ---- symmetric expand: S = full symmetric copy of the `uplo` triangle of A -----------------------------------
+__global__ void __launch_bounds__(256) rb_sym_expand_kernel(const double *__restrict__ a, i64 lda, double *__restrict__ s,
+                                                            i64 n, int upper)
+{
+    i64 total = n * n;
+    i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        i64 i = e % n, j = e / n;
+        bool in_tri = upper ? (i <= j) : (i >= j);
+        s[e] = in_tri ? a[i + j * lda] : a[j + i * lda];
+    }
+}
+
+extern "C" int rb_dsymm(rb_ctx *ctx, char side, char uplo, int m, int n, double alpha, const double *a, int64_t lda,
+                        const double *b, int64_t ldb, double beta, double *c, int64_t ldc)
+{
+    RB_REQUIRE(ctx, "rb_dsymm: ctx is NULL");
+    RB_REQUIRE(rb_is_l(side) || side == 'R' || side == 'r', "rb_dsymm: side must be 'L' or 'R'");
+    RB_REQUIRE(rb_is_u(uplo) || rb_is_l(uplo), "rb_dsymm: uplo must be 'U' or 'L'");
+    RB_REQUIRE(m >= 0 && n >= 0, "rb_dsymm: negative dimension");
+    if (m == 0 || n == 0) return RB_OK;
+    RB_CUDA(cudaSetDevice(ctx->device));
+    const i64 ka = rb_is_l(side) ? m : n;
+    RB_REQUIRE(lda >= ka, "rb_dsymm: lda too small");
+    void *ws;
+    RB_TRY(rb_ws_reserve(ctx, 0, ka * ka * 8, &ws));
+    double *s = (double *)ws;
+    i64 blocks = rb_cdiv(ka * ka, 256);
+    i64 cap = (i64)ctx->num_sms * 16;
+    if (blocks > cap) blocks = cap;
+    rb_sym_expand_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(a, lda, s, ka, rb_is_u(uplo) ? 1 : 0);
+    RB_LAUNCHED(ctx);
+    if (rb_is_l(side)) return rb_gemm_core(ctx, false, false, m, n, m, alpha, s, ka, 0, b, ldb, 0, beta, c, ldc, 0, 1, 0);
+    return rb_gemm_core(ctx, false, false, m, n, n, alpha, b, ldb, 0, s, ka, 0, beta, c, ldc, 0, 1, 0);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// GEMV.  'T': y[j] = alpha * dot(A[:,j], x) + beta*y[j]   -- column dots (this is d_P with A = [nb^2, nx])
+//        'N': y[i] = alpha * sum_j A[i,j] x[j] + beta*y[i] -- row sums   (this is J)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// grid (chunks, n): CTA reduces rows [chunk*rows_per_chunk, ...) of column j; partial[chunk + j*chunks]
+template <bool VEC>
+__global__ void __launch_bounds__(256) rb_gemv_t_kernel(const double *__restrict__ a, i64 lda, i64 m,
+                                                        const double *__restrict__ x, i64 incx, i64 rows_per_chunk,
+                                                        double *__restrict__ partial, i64 chunks)
+{
+    const i64 j = blockIdx.y, chunk = blockIdx.x;
+    const i64 r0 = chunk * rows_per_chunk;
+    i64 r1 = r0 + rows_per_chunk;
+    if (r1 > m) r1 = m;
+    const double *col = a + j * lda;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    if (VEC) { // incx == 1, 16-byte aligned columns and x, even r0
+        const double2 *c2 = reinterpret_cast<const double2 *>(col + r0);
+        const double2 *x2 = reinterpret_cast<const double2 *>(x + r0);
+        i64 n2 = (r1 - r0) >> 1;
+        i64 i = threadIdx.x;
+        for (; i + 768 < n2; i += 1024) {
+            double2 a0 = c2[i], a1 = c2[i + 256], a2 = c2[i + 512], a3 = c2[i + 768];
+            double2 x0 = x2[i], x1 = x2[i + 256], xx2 = x2[i + 512], x3 = x2[i + 768];
+            s0 += a0.x * x0.x + a0.y * x0.y;
+            s1 += a1.x * x1.x + a1.y * x1.y;
+            s2 += a2.x * xx2.x + a2.y * xx2.y;
+            s3 += a3.x * x3.x + a3.y * x3.y;
+        }
+        for (; i < n2; i += 256) { double2 a0 = c2[i], x0 = x2[i]; s0 += a0.x * x0.x + a0.y * x0.y; }
+        if (((r1 - r0) & 1) && threadIdx.x == 0) s1 += col[r1 - 1] * x[r1 - 1];
+    } else {
+        for (i64 i = r0 + threadIdx.x; i < r1; i += 256) s0 += col[i] * x[i * incx];
+    }
+    double s = (s0 + s1) + (s2 + s3);
+    s = warp_sum(s);
+    __shared__ double red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tsum = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) tsum += red[w];
+        partial[chunk + j * chunks] = tsum;
+    }
+}
+
+__global__ void __launch_bounds__(256) rb_gemv_t_finish_kernel(const double *__restrict__ partial, i64 chunks, i64 n,
+                                                               double alpha, double beta, double *__restrict__ y,
+                                                               i64 incy)
+{
+    i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    double s = 0.0;
+    for (i64 c = 0; c < chunks; ++c) s += partial[c + j * chunks];
+    double *yp = y + j * incy;
+    *yp = (beta == 0.0) ? alpha * s : alpha * s + beta * (*yp);
+}
+
+// grid (row blocks, splits): thread owns RPT consecutive rows, loops over its column range; partial[split][m]
+template <bool VEC>
+__global__ void __launch_bounds__(256) rb_gemv_n_kernel(const double *__restrict__ a, i64 lda, i64 m, i64 n,
+                                                        const double *__restrict__ x, i64 incx, i64 cols_per_split,
+                                                        double *__restrict__ partial, i64 pstride)
+{
+    const i64 split = blockIdx.y;
+    const i64 j0 = split * cols_per_split;
+    i64 j1 = j0 + cols_per_split;
+    if (j1 > n) j1 = n;
+    double *out = partial + split * pstride;
+    if (VEC) {
+        const i64 i = ((i64)blockIdx.x * 256 + threadIdx.x) * 2;
+        if (i >= m) return;
+        const bool pair = (i + 1 < m);
+        double ax = 0.0, ay = 0.0, bx = 0.0, by = 0.0, cx = 0.0, cy = 0.0, dx = 0.0, dy = 0.0;
+        const double *ap = a + i;
+        i64 j = j0;
+        if (pair) {
+            for (; j + 3 < j1; j += 4) {
+                double2 v0 = *reinterpret_cast<const double2 *>(ap + j * lda);
+                double2 v1 = *reinterpret_cast<const double2 *>(ap + (j + 1) * lda);
+                double2 v2 = *reinterpret_cast<const double2 *>(ap + (j + 2) * lda);
+                double2 v3 = *reinterpret_cast<const double2 *>(ap + (j + 3) * lda);
+                double x0 = __ldg(x + j), x1 = __ldg(x + j + 1), x2 = __ldg(x + j + 2), x3 = __ldg(x + j + 3);
+                ax += v0.x * x0; ay += v0.y * x0;
+                bx += v1.x * x1; by += v1.y * x1;
+                cx += v2.x * x2; cy += v2.y * x2;
+                dx += v3.x * x3; dy += v3.y * x3;
+            }
+            for (; j < j1; ++j) {
+                double2 v0 = *reinterpret_cast<const double2 *>(ap + j * lda);
+                double x0 = __ldg(x + j);
+                ax += v0.x * x0; ay += v0.y * x0;
+            }
+            double2 r;
+            r.x = (ax + bx) + (cx + dx);
+            r.y = (ay + by) + (cy + dy);
+            *reinterpret_cast<double2 *>(out + i) = r;
+        } else {
+            for (; j < j1; ++j) ax += ap[j * lda] * __ldg(x + j);
+            out[i] = ax;
+        }
+    } else {
+        const i64 i = (i64)blockIdx.x * 256 + threadIdx.x;
+        if (i >= m) return;
+        double s = 0.0;
+        for (i64 j = j0; j < j1; ++j) s += a[i + j * lda] * x[j * incx];
+        out[i] = s;
+    }
+}
+
+__global__ void __launch_bounds__(256) rb_gemv_n_finish_kernel(const double *__restrict__ partial, i64 pstride,
+                                                               i64 splits, i64 m, double alpha, double beta,
+                                                               double *__restrict__ y, i64 incy)
+{
+    i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
+        double s = 0.0;
+        for (i64 sp = 0; sp < splits; ++sp) s += partial[sp * pstride + i];
+        double *yp = y + i * incy;
+        *yp = (beta == 0.0) ? alpha * s : alpha * s + beta * (*yp);
+    }
+}
+
+extern "C" int rb_dgemv(rb_ctx *ctx, char trans, int m_, int n_, double alpha, const double *a, int64_t lda,
+                        const double *x, int incx_, double beta, double *y, int incy_)
+{
+    RB_REQUIRE(ctx, "rb_dgemv: ctx is NULL");
+    RB_REQUIRE(rb_is_n(trans) || rb_is_t(trans), "rb_dgemv: trans must be 'N' or 'T'");
+    RB_REQUIRE(m_ >= 0 && n_ >= 0, "rb_dgemv: negative dimension");
+    RB_REQUIRE(incx_ != 0 && incy_ != 0, "rb_dgemv: zero increment");
+    const i64 m = m_, n = n_;
+    if (m == 0 || n == 0) return RB_OK;
+    RB_REQUIRE(lda >= m, "rb_dgemv: lda too small");
+    RB_CUDA(cudaSetDevice(ctx->device));
+    const i64 lenx = rb_is_n(trans) ? n : m, leny = rb_is_n(trans) ? m : n;
+    // BLAS convention for negative increments: element i lives at (len-1-i)*|inc|
+    i64 incx = incx_, incy = incy_;
+    const double *xb = incx > 0 ? x : x + (1 - lenx) * incx;
+    double *yb = incy > 0 ? y : y + (1 - leny) * incy;
+    if (alpha == 0.0) return rb_scale_or_zero(ctx, yb, leny, incy, beta);
+
+    if (rb_is_t(trans)) {
+        // column dots; split long columns so that the grid covers the chip a few times over
+        i64 chunks = 1;
+        i64 want = (i64)ctx->num_sms * 4;
+        if (n < want) chunks = rb_cdiv(want, n);
+        i64 max_chunks = rb_cdiv(m, 8192);
+        if (chunks > max_chunks) chunks = max_chunks;
+        if (chunks < 1) chunks = 1;
+        i64 rows_per_chunk = (rb_cdiv(m, chunks) + 1) & ~(i64)1;
+        chunks = rb_cdiv(m, rows_per_chunk);
+        void *ws;
+        RB_TRY(rb_ws_reserve(ctx, 1, chunks * n * 8, &ws));
+        bool vec = incx == 1 && ((lda & 1) == 0) && ((((uintptr_t)a) & 15) == 0) && ((((uintptr_t)xb) & 15) == 0);
+        for (i64 j0 = 0; j0 < n; j0 += 65535) {
+            i64 nj = n - j0 < 65535 ? n - j0 : 65535;
+            dim3 grid((unsigned)chunks, (unsigned)nj);
+            if (vec) rb_gemv_t_kernel<true><<<grid, 256, 0, ctx->stream>>>(a + j0 * lda, lda, m, xb, incx, rows_per_chunk, (double *)ws + j0 * chunks, chunks);
+            else rb_gemv_t_kernel<false><<<grid, 256, 0, ctx->stream>>>(a + j0 * lda, lda, m, xb, incx, rows_per_chunk, (double *)ws + j0 * chunks, chunks);
+            RB_LAUNCHED(ctx);
+        }
+        rb_gemv_t_finish_kernel<<<(unsigned)rb_cdiv(n, 256), 256, 0, ctx->stream>>>((const double *)ws, chunks, n, alpha, beta, yb, incy);
+        RB_LAUNCHED(ctx);
+        return RB_OK;
+    }
+    // 'N'
+    bool vec = incx == 1 && ((lda & 1) == 0) && ((((uintptr_t)a) & 15) == 0);
+    i64 row_blocks = vec ? rb_cdiv(rb_cdiv(m, 2), 256) : rb_cdiv(m, 256);
+    i64 splits = 1;
+    i64 want = (i64)ctx->num_sms * 4;
+    if (row_blocks < want) splits = rb_cdiv(want, row_blocks);
+    i64 max_splits = rb_cdiv(n, 32);
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    if (splits > 65535) splits = 65535;
+    i64 cols_per_split = rb_cdiv(n, splits);
+    splits = rb_cdiv(n, cols_per_split);
+    void *ws;
+    const i64 pstride = (m + 1) & ~(i64)1;
+    RB_TRY(rb_ws_reserve(ctx, 1, splits * pstride * 8, &ws));
+    dim3 grid((unsigned)row_blocks, (unsigned)splits);
+    if (vec) rb_gemv_n_kernel<true><<<grid, 256, 0, ctx->stream>>>(a, lda, m, n, xb, incx, cols_per_split, (double *)ws, pstride);
+    else rb_gemv_n_kernel<false><<<grid, 256, 0, ctx->stream>>>(a, lda, m, n, xb, incx, cols_per_split, (double *)ws, pstride);
+    RB_LAUNCHED(ctx);
+    i64 blocks = rb_cdiv(m, 256);
+    i64 cap = (i64)ctx->num_sms * 16;
+    if (blocks > cap) blocks = cap;
+    rb_gemv_n_finish_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>((const double *)ws, pstride, splits, m, alpha, beta, yb, incy);
+    RB_LAUNCHED(ctx);
+    return RB_OK;
+}

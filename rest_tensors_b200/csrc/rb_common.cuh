@@ -1,0 +1,97 @@
+// rb_common.cuh -- context, error plumbing and small device helpers shared by all translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <cstdlib>
+#include <mutex>
+#include "../../include/rest_b200.h"
+
+typedef int64_t i64;
+
+// ---- error plumbing ---------------------------------------------------------------------------------
+void rb_set_error(const char *fmt, ...);
+
+#define RB_CUDA(call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t _e = (call);                                                                        \
+        if (_e != cudaSuccess) {                                                                        \
+            rb_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e));         \
+            return RB_ERR_CUDA;                                                                         \
+        }                                                                                               \
+    } while (0)
+
+#define RB_REQUIRE(cond, ...)                                                                           \
+    do {                                                                                                \
+        if (!(cond)) {                                                                                  \
+            rb_set_error(__VA_ARGS__);                                                                  \
+            return RB_ERR_INVALID;                                                                      \
+        }                                                                                               \
+    } while (0)
+
+#define RB_TRY(expr)                                                                                    \
+    do {                                                                                                \
+        int _s = (expr);                                                                                \
+        if (_s != RB_OK) return _s;                                                                     \
+    } while (0)
+
+// ---- context ----------------------------------------------------------------------------------------
+typedef CUresult (*rb_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                       const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                       CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                       CUtensorMapFloatOOBfill);
+
+struct rb_ctx {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr; // the stream calls run on (own_stream or the caller's)
+    void *ws[4] = {nullptr, nullptr, nullptr, nullptr}; // grow-only workspaces (slot 0: RI ops, 1: GEMM split-K, 2: host staging, 3: probes)
+    i64 ws_bytes[4] = {0, 0, 0, 0};
+    i64 launches = 0;
+    int gemm_path = 0;
+    rb_encode_tiled_fn encode_tiled = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+// Grow-only device workspace (synchronises the stream before freeing the old block).
+int rb_ws_reserve(rb_ctx *ctx, int slot, i64 bytes, void **out);
+
+// After every kernel launch: count it and surface launch-configuration errors.
+#define RB_LAUNCHED(ctx)                                                                                \
+    do {                                                                                                \
+        (ctx)->launches++;                                                                              \
+        cudaError_t _e = cudaGetLastError();                                                            \
+        if (_e != cudaSuccess) {                                                                        \
+            rb_set_error("%s:%d: kernel launch failed -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            return RB_ERR_CUDA;                                                                         \
+        }                                                                                               \
+    } while (0)
+
+static inline i64 rb_cdiv(i64 a, i64 b) { return (a + b - 1) / b; }
+static inline bool rb_is_n(char c) { return c == 'N' || c == 'n'; }
+static inline bool rb_is_t(char c) { return c == 'T' || c == 't'; }
+static inline bool rb_is_u(char c) { return c == 'U' || c == 'u'; }
+static inline bool rb_is_l(char c) { return c == 'L' || c == 'l'; }
+
+// ---- internal cross-TU entry points -------------------------------------------------------------------
+// Generic strided 3-D copy: dst[d0 + i*di + j*dj + k*dk] = src[s0 + i*si + j*sj + k*sk]
+int rb_copy3d(rb_ctx *ctx, const double *src, i64 s0, i64 si, i64 sj, i64 sk, double *dst, i64 d0, i64 di, i64 dj,
+              i64 dk, i64 ni, i64 nj, i64 nk);
+// Batched tiled 2-D transpose: out[c + r*ors + b*obs] = in[r + c*ics + b*ibs]
+int rb_transpose_batched(rb_ctx *ctx, const double *in, i64 ics, i64 ibs, double *out, i64 ors, i64 obs, i64 nr,
+                         i64 nc, i64 nbatch);
+// GEMM core (rb_gemm.cu). tri: 0 = full, 1 = only tiles/elements with row<=col (upper), 2 = row>=col (lower)
+int rb_gemm_core(rb_ctx *ctx, bool ta, bool tb, i64 m, i64 n, i64 k, double alpha, const double *a, i64 lda,
+                 i64 stride_a, const double *b, i64 ldb, i64 stride_b, double beta, double *c, i64 ldc,
+                 i64 stride_c, i64 batch, int tri);
+// Symmetrise: copy the `uplo` triangle of the n x n matrix c onto the other triangle.
+int rb_symmetrize(rb_ctx *ctx, double *c, i64 n, i64 ldc, bool from_upper);
+// y = beta-scaled / zero helper
+int rb_scale_or_zero(rb_ctx *ctx, double *y, i64 n, i64 inc, double beta);
+
+// Default (process-wide) context for the host-pointer entry points.
+rb_ctx *rb_default_ctx(void);
+std::mutex &rb_default_mutex(void);

@@ -1,0 +1,625 @@
+// rb_compat.cu -- HOST-pointer entry points.
+//   (1) the seven Fortran-ABI symbols the reference's Rust FFI binds (src/external_libs/ffi_restmatr.rs:4-62),
+//   (2) rb_host_* mirrors of the reference's BLAS / layout calls (src/matrix/matrix_blas_lapack.rs, matrixupper.rs,
+//       matrixfull.rs, ri.rs).
+// Every call stages its operands into HBM, runs the same CUDA kernels as the device API and copies the result back
+// before returning; nothing is retained.  There is no CPU arithmetic here: the only host work is cudaMemcpy.
+// ri_ao2mo_f_ / rb_host_ri_ao2mo stream P-chunks through a 3-stream pipeline (H2D | DMMA GEMMs | D2H) so that PCIe
+// transfers overlap the contraction; pass pinned buffers (rb_host_alloc_pinned) to make the copies truly async.
+#include "rb_common.cuh"
+#include <vector>
+
+namespace {
+
+struct HostOp {
+    rb_ctx *ctx;
+    std::unique_lock<std::mutex> lock;
+    std::vector<void *> bufs;
+    HostOp() : ctx(nullptr), lock(rb_default_mutex()) { ctx = rb_default_ctx(); }
+    ~HostOp()
+    {
+        if (ctx) cudaStreamSynchronize(ctx->stream);
+        for (void *p : bufs) cudaFree(p);
+    }
+    int alloc(i64 elems, double **out)
+    {
+        *out = nullptr;
+        if (elems <= 0) elems = 1;
+        void *p = nullptr;
+        cudaError_t e = cudaMalloc(&p, (size_t)elems * 8);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            rb_set_error("host wrapper: cudaMalloc(%lld doubles) failed: %s", (long long)elems, cudaGetErrorString(e));
+            return RB_ERR_NOMEM;
+        }
+        bufs.push_back(p);
+        *out = (double *)p;
+        return RB_OK;
+    }
+    // upload a host matrix block [rows x cols] with leading dimension ld into a dense device buffer
+    int up2d(double *dst, const double *src, i64 rows, i64 cols, i64 ld)
+    {
+        if (rows <= 0 || cols <= 0) return RB_OK;
+        RB_CUDA(cudaMemcpy2DAsync(dst, (size_t)rows * 8, src, (size_t)ld * 8, (size_t)rows * 8, (size_t)cols,
+                                  cudaMemcpyHostToDevice, ctx->stream));
+        return RB_OK;
+    }
+    int down2d(double *dst, i64 ld, const double *src, i64 rows, i64 cols)
+    {
+        if (rows <= 0 || cols <= 0) return RB_OK;
+        RB_CUDA(cudaMemcpy2DAsync(dst, (size_t)ld * 8, src, (size_t)rows * 8, (size_t)rows * 8, (size_t)cols,
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+        return RB_OK;
+    }
+    int up(double *dst, const double *src, i64 n)
+    {
+        if (n > 0) RB_CUDA(cudaMemcpyAsync(dst, src, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        return RB_OK;
+    }
+    int down(double *dst, const double *src, i64 n)
+    {
+        if (n > 0) RB_CUDA(cudaMemcpyAsync(dst, src, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        return RB_OK;
+    }
+    int sync()
+    {
+        RB_CUDA(cudaStreamSynchronize(ctx->stream));
+        return RB_OK;
+    }
+};
+
+#define HOST_CTX(op)                                                                                     \
+    HostOp op;                                                                                           \
+    if (!op.ctx) return RB_ERR_CUDA
+
+void die_if(int status, const char *who)
+{
+    if (status != RB_OK) {
+        fprintf(stderr, "librest_b200: %s failed: %s\n", who, rb_last_error());
+        abort();
+    }
+}
+
+// ---- pipelined host ao2mo ---------------------------------------------------------------------------------------
+struct Pipe {
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t in_done[2] = {nullptr, nullptr}, comp_done[2] = {nullptr, nullptr}, out_done[2] = {nullptr, nullptr};
+    ~Pipe()
+    {
+        for (int i = 0; i < 2; ++i) {
+            if (in_done[i]) cudaEventDestroy(in_done[i]);
+            if (comp_done[i]) cudaEventDestroy(comp_done[i]);
+            if (out_done[i]) cudaEventDestroy(out_done[i]);
+        }
+        if (s_in) cudaStreamDestroy(s_in);
+        if (s_out) cudaStreamDestroy(s_out);
+    }
+    int init()
+    {
+        RB_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+        RB_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            RB_CUDA(cudaEventCreateWithFlags(&in_done[i], cudaEventDisableTiming));
+            RB_CUDA(cudaEventCreateWithFlags(&comp_done[i], cudaEventDisableTiming));
+            RB_CUDA(cudaEventCreateWithFlags(&out_done[i], cudaEventDisableTiming));
+        }
+        return RB_OK;
+    }
+};
+
+int host_ao2mo(const double *cl, int nl, const double *cr, int nr, const double *ri3ao, double *out, int nb_, int nx_)
+{
+    RB_REQUIRE(nl >= 0 && nr >= 0 && nb_ >= 0 && nx_ >= 0, "ao2mo: negative dimension");
+    const i64 nb = nb_, nx = nx_;
+    if (nx == 0 || nl == 0 || nr == 0) return RB_OK;
+    HOST_CTX(op);
+    rb_ctx *ctx = op.ctx;
+    // chunk of P slabs staged per pipeline step: large enough for full 128-row MMA tiles along P, small enough
+    // to overlap the PCIe transfers with compute
+    i64 pc = 256;
+    const i64 slab_in = nb * nb, slab_out = (i64)nl * nr;
+    while (pc > 8 && pc * (slab_in + slab_out) * 8 * 2 > ((i64)6 << 30)) pc >>= 1;
+    if (pc > nx) pc = nx;
+    double *d_cl, *d_cr, *d_in[2], *d_out[2];
+    RB_TRY(op.alloc(nb * nl, &d_cl));
+    const bool same_c = (cl == cr && nl == nr);
+    if (same_c) d_cr = d_cl; else RB_TRY(op.alloc(nb * nr, &d_cr));
+    for (int i = 0; i < 2; ++i) {
+        RB_TRY(op.alloc(pc * slab_in, &d_in[i]));
+        RB_TRY(op.alloc(pc * slab_out, &d_out[i]));
+    }
+    Pipe pipe;
+    RB_TRY(pipe.init());
+    RB_TRY(op.up(d_cl, cl, nb * nl));
+    if (!same_c) RB_TRY(op.up(d_cr, cr, nb * nr));
+    int step = 0;
+    for (i64 p0 = 0; p0 < nx; p0 += pc, ++step) {
+        const int s = step & 1;
+        const i64 pn = (nx - p0 < pc) ? nx - p0 : pc;
+        // H2D of this chunk may start once the compute that last read d_in[s] is done
+        if (step >= 2) RB_CUDA(cudaStreamWaitEvent(pipe.s_in, pipe.comp_done[s], 0));
+        if (nb > 0)
+            RB_CUDA(cudaMemcpyAsync(d_in[s], ri3ao + p0 * slab_in, (size_t)(pn * slab_in) * 8, cudaMemcpyHostToDevice,
+                                    pipe.s_in));
+        RB_CUDA(cudaEventRecord(pipe.in_done[s], pipe.s_in));
+        // compute needs the chunk in HBM and the previous D2H out of d_out[s]
+        RB_CUDA(cudaStreamWaitEvent(ctx->stream, pipe.in_done[s], 0));
+        if (step >= 2) RB_CUDA(cudaStreamWaitEvent(ctx->stream, pipe.out_done[s], 0));
+        RB_TRY(rb_ri_ao2mo(ctx, d_cl, nl, d_cr, nr, d_in[s], d_out[s], nb_, (int)pn, pn));
+        RB_CUDA(cudaEventRecord(pipe.comp_done[s], ctx->stream));
+        // D2H: rows of pn doubles into the P-fastest host tensor (pitch nx)
+        RB_CUDA(cudaStreamWaitEvent(pipe.s_out, pipe.comp_done[s], 0));
+        RB_CUDA(cudaMemcpy2DAsync(out + p0, (size_t)nx * 8, d_out[s], (size_t)pn * 8, (size_t)pn * 8, (size_t)slab_out,
+                                  cudaMemcpyDeviceToHost, pipe.s_out));
+        RB_CUDA(cudaEventRecord(pipe.out_done[s], pipe.s_out));
+    }
+    RB_CUDA(cudaStreamSynchronize(pipe.s_out));
+    RB_CUDA(cudaStreamSynchronize(pipe.s_in));
+    RB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return RB_OK;
+}
+
+int host_gemm_block(const double *a, i64 rows_a, i64 sra, i64 lra, i64 sca, i64 lca, char opa, const double *b,
+                    i64 rows_b, i64 srb, i64 lrb, i64 scb, i64 lcb, char opb, double *c, i64 rows_c, i64 src, i64 lrc,
+                    i64 scc, i64 lcc, double alpha, double beta)
+{
+    RB_REQUIRE((opa == 'N' || opa == 'T') && (opb == 'N' || opb == 'T'), "general_dgemm_f: op must be 'N' or 'T'");
+    const i64 m = lrc, n = lcc, k = (opa == 'N') ? lca : lra;
+    RB_REQUIRE(m >= 0 && n >= 0 && k >= 0, "general_dgemm_f: negative block length");
+    RB_REQUIRE(((opa == 'N') ? lra : lca) == m, "general_dgemm_f: op(A) rows != rows of C block");
+    RB_REQUIRE(((opb == 'N') ? lrb : lcb) == k && ((opb == 'N') ? lcb : lrb) == n, "general_dgemm_f: op(B) shape mismatch");
+    if (m == 0 || n == 0) return RB_OK;
+    HOST_CTX(op);
+    double *da, *db, *dc;
+    RB_TRY(op.alloc(lra * lca, &da));
+    RB_TRY(op.alloc(lrb * lcb, &db));
+    RB_TRY(op.alloc(m * n, &dc));
+    RB_TRY(op.up2d(da, a + sra + sca * rows_a, lra, lca, rows_a));
+    RB_TRY(op.up2d(db, b + srb + scb * rows_b, lrb, lcb, rows_b));
+    if (beta != 0.0) RB_TRY(op.up2d(dc, c + src + scc * rows_c, m, n, rows_c));
+    RB_TRY(rb_dgemm(op.ctx, opa, opb, (int)m, (int)n, (int)k, alpha, da, lra > 0 ? lra : 1, db, lrb > 0 ? lrb : 1, beta,
+                    dc, m));
+    RB_TRY(op.down2d(c + src + scc * rows_c, rows_c, dc, m, n));
+    return op.sync();
+}
+
+} // namespace
+
+// =====================================================================================================================
+// (1) Fortran-ABI compat symbols
+// =====================================================================================================================
+extern "C" void ri_ao2mo_f_(const double *eigenvector, const double *ri3fn, double *ri3mo, const int *num_states,
+                            const int *num_basis, const int *num_auxbas)
+{
+    die_if(host_ao2mo(eigenvector, *num_states, eigenvector, *num_states, ri3fn, ri3mo, *num_basis, *num_auxbas),
+           "ri_ao2mo_f_");
+}
+
+extern "C" void general_dgemm_f_(const double *matr_a, const int *rows_a, const int *columns_a, const int *start_row_a,
+                                 const int *len_row_a, const int *start_column_a, const int *len_column_a,
+                                 const char *opa, const double *matr_b, const int *rows_b, const int *columns_b,
+                                 const int *start_row_b, const int *len_row_b, const int *start_column_b,
+                                 const int *len_column_b, const char *opb, double *matr_c, const int *rows_c,
+                                 const int *columns_c, const int *start_row_c, const int *len_row_c,
+                                 const int *start_column_c, const int *len_column_c, const double *alpha,
+                                 const double *beta)
+{
+    (void)columns_a; (void)columns_b; (void)columns_c;
+    die_if(host_gemm_block(matr_a, *rows_a, *start_row_a, *len_row_a, *start_column_a, *len_column_a, *opa, matr_b,
+                           *rows_b, *start_row_b, *len_row_b, *start_column_b, *len_column_b, *opb, matr_c, *rows_c,
+                           *start_row_c, *len_row_c, *start_column_c, *len_column_c, *alpha, *beta),
+           "general_dgemm_f_");
+}
+
+static int host_special_dgemm(double *t, int x_a, int y_a, int z_a, int sx, int lx, int sz, int lz, const double *b,
+                              int rows_b, int srb, int scb, int lcb, double alpha, double beta)
+{
+    RB_REQUIRE(x_a >= 0 && y_a >= 0 && z_a >= 0, "special_dgemm_f_01: negative dimension");
+    const i64 total = (i64)x_a * y_a * z_a;
+    if (total == 0 || lx == 0 || lz == 0) return RB_OK;
+    HOST_CTX(op);
+    double *dt, *db;
+    RB_TRY(op.alloc(total, &dt));
+    RB_TRY(op.alloc((i64)lz * lcb, &db));
+    RB_TRY(op.up(dt, t, total));
+    RB_TRY(op.up2d(db, b + srb + (i64)scb * rows_b, lz, lcb, rows_b));
+    RB_TRY(rb_special_dgemm_01(op.ctx, dt, x_a, y_a, z_a, sx, lx, sz, lz, db, lz, lcb, alpha, beta));
+    RB_TRY(op.down(t, dt, total));
+    return op.sync();
+}
+
+extern "C" void special_dgemm_f_01_(double *ten3_a, const int *x_a, const int *y_a, const int *z_a,
+                                    const int *start_x_a, const int *len_x_a, const int *i_y, const int *start_z_a,
+                                    const int *len_z_a, const double *matr_b, const int *rows_b, const int *columns_b,
+                                    const int *start_row_b, const int *len_row_b, const int *start_column_b,
+                                    const int *len_column_b, const double *alpha, const double *beta)
+{
+    (void)i_y; (void)columns_b; (void)len_row_b; // i_y_a is unused by the Fortran as well (restmatr.f90:111-154)
+    die_if(host_special_dgemm(ten3_a, *x_a, *y_a, *z_a, *start_x_a, *len_x_a, *start_z_a, *len_z_a, matr_b, *rows_b,
+                              *start_row_b, *start_column_b, *len_column_b, *alpha, *beta),
+           "special_dgemm_f_01_");
+}
+
+// copy_* : upload the source box, run the strided-copy kernel into a device image of the destination box,
+// download the box.  (Only the destination BOX is written back, so untouched elements keep their host values.)
+static int host_copy_box(const double *f, i64 f0, i64 fs1, i64 fs2, i64 fs3, double *t, i64 t0, i64 ts1, i64 ts2,
+                         i64 ts3, i64 n1, i64 n2, i64 n3)
+{
+    if (n1 <= 0 || n2 <= 0 || n3 <= 0) return RB_OK;
+    HOST_CTX(op);
+    // source box -> dense device buffer [n1,n2,n3]
+    double *ds, *dd;
+    RB_TRY(op.alloc(n1 * n2 * n3, &ds));
+    RB_TRY(op.alloc(n1 * n2 * n3, &dd));
+    // gather rows of the source box (unit stride along whichever axis has stride 1; generic fallback: element rows)
+    if (fs1 == 1) {
+        for (i64 k = 0; k < n3; ++k)
+            RB_CUDA(cudaMemcpy2DAsync(ds + k * n1 * n2, (size_t)n1 * 8, f + f0 + k * fs3, (size_t)fs2 * 8, (size_t)n1 * 8,
+                                      (size_t)n2, cudaMemcpyHostToDevice, op.ctx->stream));
+    } else {
+        // x3-fixed plane of an RI tensor (mode 2): elements are fs1 apart
+        for (i64 k = 0; k < n3; ++k)
+            for (i64 j = 0; j < n2; ++j)
+                RB_CUDA(cudaMemcpy2DAsync(ds + (j + k * n2) * n1, 8, f + f0 + j * fs2 + k * fs3, (size_t)fs1 * 8, 8,
+                                          (size_t)n1, cudaMemcpyHostToDevice, op.ctx->stream));
+    }
+    RB_TRY(rb_copy3d(op.ctx, ds, 0, 1, n1, n1 * n2, dd, 0, 1, n1, n1 * n2, n1, n2, n3));
+    if (ts1 == 1) {
+        for (i64 k = 0; k < n3; ++k)
+            RB_CUDA(cudaMemcpy2DAsync(t + t0 + k * ts3, (size_t)ts2 * 8, dd + k * n1 * n2, (size_t)n1 * 8, (size_t)n1 * 8,
+                                      (size_t)n2, cudaMemcpyDeviceToHost, op.ctx->stream));
+    } else {
+        for (i64 k = 0; k < n3; ++k)
+            for (i64 j = 0; j < n2; ++j)
+                RB_CUDA(cudaMemcpy2DAsync(t + t0 + j * ts2 + k * ts3, (size_t)ts1 * 8, dd + (j + k * n2) * n1, 8, 8,
+                                          (size_t)n1, cudaMemcpyDeviceToHost, op.ctx->stream));
+    }
+    return op.sync();
+}
+
+static bool in_box(i64 s, i64 l, i64 d) { return s >= 0 && l >= 0 && s + l <= d; }
+
+static int ri_plane(int mod, i64 X, i64 Y, i64 Z, i64 s1, i64 s2, i64 x3, i64 l1, i64 l2, i64 *off, i64 *st1, i64 *st2)
+{
+    if (mod == 0) {
+        RB_REQUIRE(in_box(s1, l1, X) && in_box(s2, l2, Y) && x3 >= 0 && x3 < Z, "copy: block outside tensor");
+        *off = s1 + s2 * X + x3 * X * Y; *st1 = 1; *st2 = X;
+    } else if (mod == 1) {
+        RB_REQUIRE(in_box(s1, l1, X) && in_box(s2, l2, Z) && x3 >= 0 && x3 < Y, "copy: block outside tensor");
+        *off = s1 + x3 * X + s2 * X * Y; *st1 = 1; *st2 = X * Y;
+    } else {
+        RB_REQUIRE(in_box(s1, l1, Y) && in_box(s2, l2, Z) && x3 >= 0 && x3 < X, "copy: block outside tensor");
+        *off = x3 + s1 * X + s2 * X * Y; *st1 = X; *st2 = X * Y;
+    }
+    return RB_OK;
+}
+
+extern "C" void copy_mm_(const int *x_len, const int *y_len, const double *f_matr, const int *f_x_len,
+                         const int *f_y_len, const int *f_x_start, const int *f_y_start, double *t_matr,
+                         const int *t_x_len, const int *t_y_len, const int *t_x_start, const int *t_y_start)
+{
+    int st = RB_OK;
+    if (!(in_box(*f_x_start, *x_len, *f_x_len) && in_box(*f_y_start, *y_len, *f_y_len) &&
+          in_box(*t_x_start, *x_len, *t_x_len) && in_box(*t_y_start, *y_len, *t_y_len))) {
+        rb_set_error("copy_mm_: block outside matrix");
+        st = RB_ERR_INVALID;
+    } else {
+        st = host_copy_box(f_matr, *f_x_start + (i64)*f_y_start * *f_x_len, 1, *f_x_len, 0, t_matr,
+                           *t_x_start + (i64)*t_y_start * *t_x_len, 1, *t_x_len, 0, *x_len, *y_len, 1);
+    }
+    die_if(st, "copy_mm_");
+}
+
+extern "C" void copy_mr_(const int *x_len, const int *y_len, const double *f_matr, const int *f_x_len,
+                         const int *f_y_len, const int *f_x_start, const int *f_y_start, double *t_ri,
+                         const int *t_x_len, const int *t_y_len, const int *t_z_len, const int *t_x_start,
+                         const int *t_y_start, const int *t_x3, const int *t_mod)
+{
+    if (*t_mod < 0 || *t_mod > 2) return; // restmatr.f90:227-237
+    int st;
+    i64 off, s1, s2;
+    if (!(in_box(*f_x_start, *x_len, *f_x_len) && in_box(*f_y_start, *y_len, *f_y_len))) {
+        rb_set_error("copy_mr_: block outside matrix");
+        st = RB_ERR_INVALID;
+    } else if ((st = ri_plane(*t_mod, *t_x_len, *t_y_len, *t_z_len, *t_x_start, *t_y_start, *t_x3, *x_len, *y_len, &off,
+                              &s1, &s2)) == RB_OK) {
+        st = host_copy_box(f_matr, *f_x_start + (i64)*f_y_start * *f_x_len, 1, *f_x_len, 0, t_ri, off, s1, s2, 0, *x_len,
+                           *y_len, 1);
+    }
+    die_if(st, "copy_mr_");
+}
+
+extern "C" void copy_rm_(const int *x_len, const int *y_len, const double *f_ri, const int *f_x_len, const int *f_y_len,
+                         const int *f_z_len, const int *f_x_start, const int *f_y_start, const int *f_x3,
+                         const int *f_mod, double *t_matr, const int *t_x_len, const int *t_y_len, const int *t_x_start,
+                         const int *t_y_start)
+{
+    if (*f_mod < 0 || *f_mod > 2) return;
+    int st;
+    i64 off, s1, s2;
+    if (!(in_box(*t_x_start, *x_len, *t_x_len) && in_box(*t_y_start, *y_len, *t_y_len))) {
+        rb_set_error("copy_rm_: block outside matrix");
+        st = RB_ERR_INVALID;
+    } else if ((st = ri_plane(*f_mod, *f_x_len, *f_y_len, *f_z_len, *f_x_start, *f_y_start, *f_x3, *x_len, *y_len, &off,
+                              &s1, &s2)) == RB_OK) {
+        st = host_copy_box(f_ri, off, s1, s2, 0, t_matr, *t_x_start + (i64)*t_y_start * *t_x_len, 1, *t_x_len, 0, *x_len,
+                           *y_len, 1);
+    }
+    die_if(st, "copy_rm_");
+}
+
+extern "C" void copy_rr_(const int *x_len, const int *y_len, const int *z_len, const double *f_ri, const int *f_x_len,
+                         const int *f_y_len, const int *f_z_len, const int *f_x_start, const int *f_y_start,
+                         const int *f_z_start, double *t_ri, const int *t_x_len, const int *t_y_len, const int *t_z_len,
+                         const int *t_x_start, const int *t_y_start, const int *t_z_start)
+{
+    int st;
+    if (!(in_box(*f_x_start, *x_len, *f_x_len) && in_box(*f_y_start, *y_len, *f_y_len) &&
+          in_box(*f_z_start, *z_len, *f_z_len) && in_box(*t_x_start, *x_len, *t_x_len) &&
+          in_box(*t_y_start, *y_len, *t_y_len) && in_box(*t_z_start, *z_len, *t_z_len))) {
+        rb_set_error("copy_rr_: box outside tensor");
+        st = RB_ERR_INVALID;
+    } else {
+        const i64 FX = *f_x_len, FY = *f_y_len, TX = *t_x_len, TY = *t_y_len;
+        st = host_copy_box(f_ri, *f_x_start + *f_y_start * FX + *f_z_start * FX * FY, 1, FX, FX * FY, t_ri,
+                           *t_x_start + *t_y_start * TX + *t_z_start * TX * TY, 1, TX, TX * TY, *x_len, *y_len, *z_len);
+    }
+    die_if(st, "copy_rr_");
+}
+
+// =====================================================================================================================
+// (2) rb_host_* wrappers
+// =====================================================================================================================
+extern "C" int rb_host_ri_ao2mo(const double *c_left, int nl, const double *c_right, int nr, const double *ri3ao,
+                                double *out, int nb, int nx)
+{
+    return host_ao2mo(c_left, nl, c_right, nr, ri3ao, out, nb, nx);
+}
+
+extern "C" int rb_host_dgemm(char ta, char tb, int m, int n, int k, double alpha, const double *a, int lda,
+                             const double *b, int ldb, double beta, double *c, int ldc)
+{
+    RB_REQUIRE((rb_is_n(ta) || rb_is_t(ta)) && (rb_is_n(tb) || rb_is_t(tb)), "rb_host_dgemm: trans must be 'N' or 'T'");
+    RB_REQUIRE(m >= 0 && n >= 0 && k >= 0, "rb_host_dgemm: negative dimension");
+    if (m == 0 || n == 0) return RB_OK;
+    const i64 ra = rb_is_n(ta) ? m : k, ca = rb_is_n(ta) ? k : m;
+    const i64 rb_ = rb_is_n(tb) ? k : n, cb = rb_is_n(tb) ? n : k;
+    RB_REQUIRE(lda >= (ra > 1 ? ra : 1) && ldb >= (rb_ > 1 ? rb_ : 1) && ldc >= m, "rb_host_dgemm: leading dimension too small");
+    HOST_CTX(op);
+    double *da, *db, *dc;
+    RB_TRY(op.alloc(ra * ca, &da));
+    RB_TRY(op.alloc(rb_ * cb, &db));
+    RB_TRY(op.alloc((i64)m * n, &dc));
+    RB_TRY(op.up2d(da, a, ra, ca, lda));
+    RB_TRY(op.up2d(db, b, rb_, cb, ldb));
+    if (beta != 0.0) RB_TRY(op.up2d(dc, c, m, n, ldc));
+    RB_TRY(rb_dgemm(op.ctx, ta, tb, m, n, k, alpha, da, ra > 0 ? ra : 1, db, rb_ > 0 ? rb_ : 1, beta, dc, m));
+    RB_TRY(op.down2d(c, ldc, dc, m, n));
+    return op.sync();
+}
+
+extern "C" int rb_host_dsyrk(char uplo, char trans, int n, int k, double alpha, const double *a, int lda, double beta,
+                             double *c, int ldc)
+{
+    RB_REQUIRE(rb_is_u(uplo) || rb_is_l(uplo), "rb_host_dsyrk: uplo must be 'U' or 'L'");
+    RB_REQUIRE(rb_is_n(trans) || rb_is_t(trans), "rb_host_dsyrk: trans must be 'N' or 'T'");
+    RB_REQUIRE(n >= 0 && k >= 0, "rb_host_dsyrk: negative dimension");
+    if (n == 0) return RB_OK;
+    const i64 ra = rb_is_n(trans) ? n : k, ca = rb_is_n(trans) ? k : n;
+    RB_REQUIRE(lda >= (ra > 1 ? ra : 1) && ldc >= n, "rb_host_dsyrk: leading dimension too small");
+    HOST_CTX(op);
+    double *da, *dc;
+    RB_TRY(op.alloc(ra * ca, &da));
+    RB_TRY(op.alloc((i64)n * n, &dc));
+    RB_TRY(op.up2d(da, a, ra, ca, lda));
+    // C travels both ways in full: the kernel touches only the `uplo` triangle, so the other one round-trips unchanged.
+    RB_TRY(op.up2d(dc, c, n, n, ldc));
+    RB_TRY(rb_dsyrk(op.ctx, uplo, trans, n, k, alpha, da, ra > 0 ? ra : 1, beta, dc, n));
+    RB_TRY(op.down2d(c, ldc, dc, n, n));
+    return op.sync();
+}
+
+extern "C" int rb_host_dgemv(char trans, int m, int n, double alpha, const double *a, int lda, const double *x,
+                             int incx, double beta, double *y, int incy)
+{
+    RB_REQUIRE(rb_is_n(trans) || rb_is_t(trans), "rb_host_dgemv: trans must be 'N' or 'T'");
+    RB_REQUIRE(m >= 0 && n >= 0 && incx != 0 && incy != 0, "rb_host_dgemv: bad dimension / increment");
+    if (m == 0 || n == 0) return RB_OK;
+    RB_REQUIRE(lda >= m, "rb_host_dgemv: lda too small");
+    const i64 lenx = rb_is_n(trans) ? n : m, leny = rb_is_n(trans) ? m : n;
+    const i64 ax = incx > 0 ? incx : -incx, ay = incy > 0 ? incy : -incy;
+    const i64 nxv = 1 + (lenx - 1) * ax, nyv = 1 + (leny - 1) * ay;
+    HOST_CTX(op);
+    double *da, *dx, *dy;
+    RB_TRY(op.alloc((i64)m * n, &da));
+    RB_TRY(op.alloc(nxv, &dx));
+    RB_TRY(op.alloc(nyv, &dy));
+    RB_TRY(op.up2d(da, a, m, n, lda));
+    RB_TRY(op.up(dx, x, nxv));
+    RB_TRY(op.up(dy, y, nyv));
+    RB_TRY(rb_dgemv(op.ctx, trans, m, n, alpha, da, m, dx, incx, beta, dy, incy));
+    RB_TRY(op.down(y, dy, nyv));
+    return op.sync();
+}
+
+extern "C" int rb_host_dsymm(char side, char uplo, int m, int n, double alpha, const double *a, int lda,
+                             const double *b, int ldb, double beta, double *c, int ldc)
+{
+    RB_REQUIRE(rb_is_l(side) || side == 'R' || side == 'r', "rb_host_dsymm: side must be 'L' or 'R'");
+    RB_REQUIRE(rb_is_u(uplo) || rb_is_l(uplo), "rb_host_dsymm: uplo must be 'U' or 'L'");
+    RB_REQUIRE(m >= 0 && n >= 0, "rb_host_dsymm: negative dimension");
+    if (m == 0 || n == 0) return RB_OK;
+    const i64 ka = rb_is_l(side) ? m : n;
+    RB_REQUIRE(lda >= ka && ldb >= m && ldc >= m, "rb_host_dsymm: leading dimension too small");
+    HOST_CTX(op);
+    double *da, *db, *dc;
+    RB_TRY(op.alloc(ka * ka, &da));
+    RB_TRY(op.alloc((i64)m * n, &db));
+    RB_TRY(op.alloc((i64)m * n, &dc));
+    RB_TRY(op.up2d(da, a, ka, ka, lda));
+    RB_TRY(op.up2d(db, b, m, n, ldb));
+    if (beta != 0.0) RB_TRY(op.up2d(dc, c, m, n, ldc));
+    RB_TRY(rb_dsymm(op.ctx, side, uplo, m, n, alpha, da, ka, db, m, beta, dc, m));
+    RB_TRY(op.down2d(c, ldc, dc, m, n));
+    return op.sync();
+}
+
+extern "C" int rb_host_to_matrixupper(const double *full, int64_t n, double *packed)
+{
+    RB_REQUIRE(n >= 0, "rb_host_to_matrixupper: negative n");
+    if (n == 0) return RB_OK;
+    HOST_CTX(op);
+    double *df, *dp;
+    const i64 np = n * (n + 1) / 2;
+    RB_TRY(op.alloc(n * n, &df));
+    RB_TRY(op.alloc(np, &dp));
+    RB_TRY(op.up(df, full, n * n));
+    RB_TRY(rb_pack_upper(op.ctx, df, n, dp));
+    RB_TRY(op.down(packed, dp, np));
+    return op.sync();
+}
+
+// exact integer inverse of len = n(n+1)/2 (the reference uses an f64 sqrt, matrixupper.rs:331-332; identical for
+// every representable triangular len)
+static i64 tri_dim(i64 len)
+{
+    if (len <= 0) return 0;
+    i64 n = (i64)((sqrt(1.0 + 8.0 * (double)len) - 1.0) * 0.5);
+    while (n * (n + 1) / 2 > len) --n;
+    while ((n + 1) * (n + 2) / 2 <= len) ++n;
+    return (n * (n + 1) / 2 == len) ? n : -1;
+}
+
+extern "C" int rb_host_to_matrixfull(const double *packed, int64_t len, double *full)
+{
+    RB_REQUIRE(len >= 0, "rb_host_to_matrixfull: negative length");
+    if (len == 0) return RB_OK; // MatrixFull::empty()
+    const i64 n = tri_dim(len);
+    RB_REQUIRE(n > 0, "rb_host_to_matrixfull: length %lld is not n(n+1)/2 (the reference returns None)", (long long)len);
+    HOST_CTX(op);
+    double *df, *dp;
+    RB_TRY(op.alloc(n * n, &df));
+    RB_TRY(op.alloc(len, &dp));
+    RB_TRY(op.up(dp, packed, len));
+    RB_TRY(rb_unpack_upper(op.ctx, dp, n, df));
+    RB_TRY(op.down(full, df, n * n));
+    return op.sync();
+}
+
+extern "C" int rb_host_ri_pack_symm(const double *ri, int64_t nao, int64_t naux, double *out)
+{
+    RB_REQUIRE(nao >= 0 && naux >= 0, "rb_host_ri_pack_symm: negative dimension");
+    if (nao == 0 || naux == 0) return RB_OK;
+    HOST_CTX(op);
+    double *di, *dout;
+    const i64 np = nao * (nao + 1) / 2;
+    RB_TRY(op.alloc(nao * nao * naux, &di));
+    RB_TRY(op.alloc(np * naux, &dout));
+    RB_TRY(op.up(di, ri, nao * nao * naux));
+    RB_TRY(rb_ri_pack_symm(op.ctx, di, nao, naux, dout));
+    RB_TRY(op.down(out, dout, np * naux));
+    return op.sync();
+}
+
+extern "C" int rb_host_ri_transpose(const double *in, int64_t i, int64_t j, int64_t k, int which, double *out)
+{
+    RB_REQUIRE(i >= 0 && j >= 0 && k >= 0, "rb_host_ri_transpose: negative dimension");
+    RB_REQUIRE(which >= 0 && which <= 3, "rb_host_ri_transpose: which must be 0..3");
+    const i64 n = i * j * k;
+    if (n == 0) return RB_OK;
+    HOST_CTX(op);
+    double *di, *dout;
+    RB_TRY(op.alloc(n, &di));
+    RB_TRY(op.alloc(n, &dout));
+    RB_TRY(op.up(di, in, n));
+    RB_TRY(rb_ri_transpose(op.ctx, di, i, j, k, which, dout));
+    RB_TRY(op.down(out, dout, n));
+    return op.sync();
+}
+
+extern "C" int rb_host_matrix_transpose(const double *in, int64_t rows, int64_t cols, double *out)
+{
+    RB_REQUIRE(rows >= 0 && cols >= 0, "rb_host_matrix_transpose: negative dimension");
+    const i64 n = rows * cols;
+    if (n == 0) return RB_OK;
+    HOST_CTX(op);
+    double *di, *dout;
+    RB_TRY(op.alloc(n, &di));
+    RB_TRY(op.alloc(n, &dout));
+    RB_TRY(op.up(di, in, n));
+    RB_TRY(rb_matrix_transpose(op.ctx, di, rows, cols, dout));
+    RB_TRY(op.down(out, dout, n));
+    return op.sync();
+}
+
+extern "C" int rb_host_axpy(int opc, double *c, const double *p, double a, double b, int64_t n)
+{
+    RB_REQUIRE(opc >= 0 && opc <= 4, "rb_host_axpy: op must be 0..4");
+    RB_REQUIRE(n >= 0, "rb_host_axpy: negative length");
+    if (n == 0) return RB_OK;
+    HOST_CTX(op);
+    double *dc, *dp = nullptr;
+    RB_TRY(op.alloc(n, &dc));
+    RB_TRY(op.up(dc, c, n));
+    if (opc != 2) { RB_TRY(op.alloc(n, &dp)); RB_TRY(op.up(dp, p, n)); }
+    switch (opc) {
+    case 0: RB_TRY(rb_self_scaled_add(op.ctx, dc, dp, b, n)); break;
+    case 1: RB_TRY(rb_self_general_add(op.ctx, dc, dp, a, b, n)); break;
+    case 2: RB_TRY(rb_self_multiple(op.ctx, dc, a, n)); break;
+    case 3: RB_TRY(rb_self_add(op.ctx, dc, dp, n)); break;
+    default: RB_TRY(rb_self_sub(op.ctx, dc, dp, n)); break;
+    }
+    RB_TRY(op.down(c, dc, n));
+    return op.sync();
+}
+
+extern "C" int rb_host_ri_dp(const double *ri3ao, const double *dm, double *d, int nb, int nx)
+{
+    RB_REQUIRE(nb >= 0 && nx >= 0, "rb_host_ri_dp: negative dimension");
+    if (nx == 0) return RB_OK;
+    HOST_CTX(op);
+    const i64 n2 = (i64)nb * nb;
+    double *da, *dd, *dout;
+    RB_TRY(op.alloc(n2 * nx, &da));
+    RB_TRY(op.alloc(n2, &dd));
+    RB_TRY(op.alloc(nx, &dout));
+    RB_TRY(op.up(da, ri3ao, n2 * nx));
+    RB_TRY(op.up(dd, dm, n2));
+    RB_TRY(rb_ri_dp(op.ctx, da, dd, dout, nb, nx));
+    RB_TRY(op.down(d, dout, nx));
+    return op.sync();
+}
+
+extern "C" int rb_host_ri_j(const double *ri3ao, const double *d, double *j, int nb, int nx)
+{
+    RB_REQUIRE(nb >= 0 && nx >= 0, "rb_host_ri_j: negative dimension");
+    const i64 n2 = (i64)nb * nb;
+    if (n2 == 0) return RB_OK;
+    HOST_CTX(op);
+    double *da, *dd, *dj;
+    RB_TRY(op.alloc(n2 * nx, &da));
+    RB_TRY(op.alloc(nx, &dd));
+    RB_TRY(op.alloc(n2, &dj));
+    RB_TRY(op.up(da, ri3ao, n2 * nx));
+    RB_TRY(op.up(dd, d, nx));
+    RB_TRY(rb_ri_j(op.ctx, da, dd, dj, nb, nx));
+    RB_TRY(op.down(j, dj, n2));
+    return op.sync();
+}
+
+extern "C" int rb_host_ri_k(const double *ri3ao, const double *ct, int no, double *k, int nb, int nx)
+{
+    RB_REQUIRE(nb >= 0 && nx >= 0 && no >= 0, "rb_host_ri_k: negative dimension");
+    const i64 n2 = (i64)nb * nb;
+    if (n2 == 0) return RB_OK;
+    HOST_CTX(op);
+    double *da, *dc, *dk;
+    RB_TRY(op.alloc(n2 * nx, &da));
+    RB_TRY(op.alloc((i64)nb * no, &dc));
+    RB_TRY(op.alloc(n2, &dk));
+    RB_TRY(op.up(da, ri3ao, n2 * nx));
+    RB_TRY(op.up(dc, ct, (i64)nb * no));
+    RB_TRY(rb_ri_k(op.ctx, da, dc, no, dk, nb, nx));
+    RB_TRY(op.down(k, dk, n2));
+    return op.sync();
+}

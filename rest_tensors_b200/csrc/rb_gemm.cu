@@ -1,0 +1,595 @@
+// rb_gemm.cu -- FP64 GEMM core for sm_100a.
+//
+// sm_100a has no tcgen05 FP64 MMA kind; the FP64 tensor path is warp-level mma.sync.m8n8k4.f64, which ptxas
+// lowers to DMMA.8x8x4.  The fast kernel here is a persistent, warp-specialised pipeline:
+//
+//   producer warp : one elected lane issues TMA (cp.async.bulk.tensor.3d) box loads of the A and B tiles into a
+//                   3-stage shared-memory ring, completion signalled on per-stage "full" mbarriers;
+//   8 consumer warps (2 x 4): each owns a 64 x 32 slice of the 128 x 128 CTA tile as 8 x 4 DMMA 8x8 tiles
+//                   (128 accumulator registers), reads fragments with conflict-free LDS.128, and releases the
+//                   stage on a per-stage "empty" mbarrier.
+//
+// Operand layouts in shared memory (chosen so that every fragment read is one LDS.128 with no bank conflicts):
+//   K-major operand (op='T' for A, 'N' for B; element (r,k) at k + r*ld):  TMA box {8 k, 128 rows}, no swizzle,
+//       smem [kb][row][8 doubles]; a quarter-warp reads two 64-byte rows that sit in opposite halves of a 128-byte
+//       bank window.  The 16 bytes a lane reads are k = 2t, 2t+1 -> the two DMMAs of a k8 block use the k-sets
+//       {0,2,4,6} and {1,3,5,7} (the summation index may be permuted freely as long as A and B agree).
+//   MN-major operand (op='N' for A, 'T' for B; element (r,k) at r + k*ld): TMA box {16 rows, 32 k}, SWIZZLE_128B,
+//       smem [rowblock][k][16 doubles ^ swizzle]; a lane reads rows (2g, 2g+1) of a 16-row block at k = 2t+j.
+//   The rows (2g, 2g+1) of every 16-row block end up in the same thread (one in each of the two 8-row DMMA
+//   tiles), so the epilogue stores 16 bytes per thread and 128 contiguous bytes per 8 lanes along M.
+//
+// Work decomposition: work item = (batch, tile_m, tile_n, k-split); grouped rasterisation (8 tile rows per group)
+// keeps the operands of concurrently running CTAs in L2; `tri` enumerates only the tiles of one triangle (SYRK);
+// split-K writes partials that a second kernel reduces in a fixed order (deterministic, no FP64 atomics).
+//
+// A second, generic kernel (plain loads, any alignment / leading dimension) covers operands TMA cannot describe.
+#include "rb_common.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 32;
+constexpr int STAGES = 3;
+constexpr int A_TILE_BYTES = BM * BK * 8;
+constexpr int B_TILE_BYTES = BN * BK * 8;
+constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 64 /*barriers*/;
+constexpr int NUM_CONSUMER_WARPS = 8;
+constexpr int NUM_THREADS = (NUM_CONSUMER_WARPS + 4) * 32; // 2 consumer warpgroups + 1 producer warpgroup
+constexpr int GROUP_M = 8;
+
+struct GemmParams {
+    i64 m, n, k;
+    i64 batch;
+    i64 tiles_m, tiles_n;
+    i64 tiles_per_batch; // tiles_m*tiles_n or the triangular count
+    i64 splits, kper;    // k per split (multiple of BK)
+    i64 total_items;
+    double alpha, beta;
+    double *c;
+    i64 ldc, stride_c;
+    int tri;             // 0 full, 1 upper (row<=col), 2 lower (row>=col)
+    double *partial;     // split-K partials [split][batch][n][ldp]
+    i64 ldp;
+    int a_batched, b_batched; // 0 => operand shared by all batches (TMA batch coordinate 0)
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1, int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ double2 lds128(uint32_t addr)
+{
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c[0]), "+d"(c[1])
+                 : "d"(a), "d"(b));
+}
+
+// work item -> (batch, tm, tn, split)
+__device__ __forceinline__ void decode_item(const GemmParams &p, i64 item, i64 &b, i64 &tm, i64 &tn, i64 &sp)
+{
+    sp = item % p.splits;
+    i64 tile = item / p.splits;
+    b = tile / p.tiles_per_batch;
+    i64 t = tile - b * p.tiles_per_batch;
+    if (p.tri == 0) {
+        i64 per_group = GROUP_M * p.tiles_n;
+        i64 grp = t / per_group;
+        i64 first_m = grp * GROUP_M;
+        i64 gsz = p.tiles_m - first_m < GROUP_M ? p.tiles_m - first_m : GROUP_M;
+        i64 r = t - grp * per_group;
+        tm = first_m + r % gsz;
+        tn = r / gsz;
+    } else {
+        // triangular enumeration: t = hi(hi+1)/2 + lo, lo <= hi
+        i64 hi = (i64)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+        while (hi * (hi + 1) / 2 > t) --hi;
+        while ((hi + 1) * (hi + 2) / 2 <= t) ++hi;
+        i64 lo = t - hi * (hi + 1) / 2;
+        if (p.tri == 1) { tm = lo; tn = hi; } else { tm = hi; tn = lo; }
+    }
+}
+
+// ---- the TMA + DMMA kernel --------------------------------------------------------------------------------------
+template <bool A_K, bool B_K>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+rb_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES; // full[STAGES], empty[STAGES]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar_base + 8 * s, 1);
+            mbar_init(bar_base + 8 * (STAGES + s), NUM_CONSUMER_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp >= NUM_CONSUMER_WARPS) {
+        // ===================== producer warpgroup: hand its registers to the consumers =====================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (warp == NUM_CONSUMER_WARPS && lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+            int stage = 0;
+            uint32_t phase = 0;
+            for (i64 item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+                i64 b, tm, tn, sp;
+                decode_item(p, item, b, tm, tn, sp);
+                const i64 k_begin = sp * p.kper;
+                const i64 k_end = (k_begin + p.kper < p.k) ? k_begin + p.kper : p.k;
+                const int ba = p.a_batched ? (int)b : 0, bb = p.b_batched ? (int)b : 0;
+                for (i64 k0 = k_begin; k0 < k_end; k0 += BK) {
+                    const uint32_t full = bar_base + 8 * stage, empty = bar_base + 8 * (STAGES + stage);
+                    mbar_wait(empty, phase ^ 1u);
+                    mbar_expect_tx(full, STAGE_BYTES);
+                    const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_TILE_BYTES;
+                    if (A_K) {
+#pragma unroll
+                        for (int kb = 0; kb < BK / 8; ++kb)
+                            tma_load_3d(sa + kb * (BM * 64), &tmA, full, (int)(k0 + kb * 8), (int)(tm * BM), ba);
+                    } else {
+#pragma unroll
+                        for (int blk = 0; blk < BM / 16; ++blk)
+                            tma_load_3d(sa + blk * (BK * 128), &tmA, full, (int)(tm * BM + blk * 16), (int)k0, ba);
+                    }
+                    if (B_K) {
+#pragma unroll
+                        for (int kb = 0; kb < BK / 8; ++kb)
+                            tma_load_3d(sb + kb * (BN * 64), &tmB, full, (int)(k0 + kb * 8), (int)(tn * BN), bb);
+                    } else {
+#pragma unroll
+                        for (int blk = 0; blk < BN / 16; ++blk)
+                            tma_load_3d(sb + blk * (BK * 128), &tmB, full, (int)(tn * BN + blk * 16), (int)k0, bb);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+        return;
+    }
+
+    // ===================== consumers =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    const int wm = warp & 1, wn = warp >> 1; // 2 x 4 warps; 16-row blocks are interleaved across warps
+    const int g = lane >> 2, t = lane & 3;
+    const int x = A_K ? (g & 1) : 0;
+
+    // per-thread byte offsets of the fragment reads inside a stage (k8-block and row-block offsets are immediates)
+    uint32_t a_off[2], b_off[2];
+    if (A_K) {
+        a_off[0] = (uint32_t)((2 * g + x) * 64 + t * 16);       // tile e : row 2g + x
+        a_off[1] = (uint32_t)((2 * g + 1 - x) * 64 + t * 16);   // tile o : row 2g + 1 - x
+    } else {
+        a_off[0] = (uint32_t)((2 * t) * 128 + ((g ^ (2 * t)) << 4));          // k = 2t   : rows (2g, 2g+1)
+        a_off[1] = (uint32_t)((2 * t + 1) * 128 + ((g ^ (2 * t + 1)) << 4));  // k = 2t+1
+    }
+    if (B_K) {
+        b_off[0] = (uint32_t)(g * 64 + t * 16);        // tile e : col g
+        b_off[1] = (uint32_t)((8 + g) * 64 + t * 16);  // tile o : col 8+g
+    } else {
+        b_off[0] = (uint32_t)((2 * t) * 128 + ((g ^ (2 * t)) << 4));
+        b_off[1] = (uint32_t)((2 * t + 1) * 128 + ((g ^ (2 * t + 1)) << 4));
+    }
+
+    int stage = 0;
+    uint32_t phase = 0;
+    for (i64 item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        i64 bidx, tm, tn, sp;
+        decode_item(p, item, bidx, tm, tn, sp);
+        const i64 k_begin = sp * p.kper;
+        const i64 k_end = (k_begin + p.kper < p.k) ? k_begin + p.kper : p.k;
+
+        double acc[4][2][2][2][2]; // [row block i][row tile e/o][col block j][col tile e/o][2]
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int pa = 0; pa < 2; ++pa)
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int pb = 0; pb < 2; ++pb) { acc[i][pa][j][pb][0] = 0.0; acc[i][pa][j][pb][1] = 0.0; }
+
+        for (i64 k0 = k_begin; k0 < k_end; k0 += BK) {
+            mbar_wait(bar_base + 8 * stage, phase);
+            const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_TILE_BYTES;
+#pragma unroll
+            for (int kb = 0; kb < BK / 8; ++kb) {
+                double af[4][2][2]; // [i][tile e/o][mma 0/1]
+                double bf[2][2][2]; // [j][tile e/o][mma 0/1]
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int blk = wm + 2 * i;
+                    if (A_K) {
+#pragma unroll
+                        for (int pa = 0; pa < 2; ++pa) {
+                            double2 v = lds128(sa + kb * (BM * 64) + blk * (16 * 64) + a_off[pa]);
+                            af[i][pa][0] = v.x; af[i][pa][1] = v.y;
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            double2 v = lds128(sa + blk * (BK * 128) + kb * (8 * 128) + a_off[q]);
+                            af[i][0][q] = v.x; af[i][1][q] = v.y;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int blk = wn + 4 * j;
+                    if (B_K) {
+#pragma unroll
+                        for (int pb = 0; pb < 2; ++pb) {
+                            double2 v = lds128(sb + kb * (BN * 64) + blk * (16 * 64) + b_off[pb]);
+                            bf[j][pb][0] = v.x; bf[j][pb][1] = v.y;
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            double2 v = lds128(sb + blk * (BK * 128) + kb * (8 * 128) + b_off[q]);
+                            bf[j][0][q] = v.x; bf[j][1][q] = v.y;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int pa = 0; pa < 2; ++pa)
+#pragma unroll
+                            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                                for (int pb = 0; pb < 2; ++pb) dmma(acc[i][pa][j][pb], af[i][pa][q], bf[j][pb][q]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_base + 8 * (STAGES + stage));
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+
+        // ---- epilogue: thread owns rows (2g, 2g+1) of each 16-row block -> 16-byte stores along M ----
+        double *cb;
+        i64 ldc;
+        double alpha, beta;
+        if (p.splits > 1) {
+            cb = p.partial + (sp * p.batch + bidx) * p.n * p.ldp;
+            ldc = p.ldp; alpha = 1.0; beta = 0.0;
+        } else {
+            cb = p.c + bidx * p.stride_c;
+            ldc = p.ldc; alpha = p.alpha; beta = p.beta;
+        }
+        const bool vec_ok = ((ldc & 1) == 0) && ((((uintptr_t)cb) & 15) == 0);
+        const int tri = (p.splits > 1) ? 0 : p.tri;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const i64 row0 = tm * BM + (wm + 2 * i) * 16 + 2 * g;
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int pb = 0; pb < 2; ++pb)
+#pragma unroll
+                    for (int cc = 0; cc < 2; ++cc) {
+                        const int coff = B_K ? (8 * pb + 2 * t + cc) : (4 * t + 2 * cc + pb);
+                        const i64 col = tn * BN + (wn + 4 * j) * 16 + coff;
+                        if (col >= p.n) continue;
+                        double v0 = x ? acc[i][1][j][pb][cc] : acc[i][0][j][pb][cc]; // row 2g
+                        double v1 = x ? acc[i][0][j][pb][cc] : acc[i][1][j][pb][cc]; // row 2g+1
+                        double *cp = cb + row0 + col * ldc;
+                        bool ok0 = row0 < p.m, ok1 = row0 + 1 < p.m;
+                        if (tri == 1) { ok0 = ok0 && row0 <= col; ok1 = ok1 && row0 + 1 <= col; }
+                        else if (tri == 2) { ok0 = ok0 && row0 >= col; ok1 = ok1 && row0 + 1 >= col; }
+                        if (ok0 && ok1 && vec_ok) {
+                            double2 o;
+                            if (beta == 0.0) { o.x = alpha * v0; o.y = alpha * v1; }
+                            else {
+                                double2 old = *reinterpret_cast<const double2 *>(cp);
+                                o.x = alpha * v0 + beta * old.x; o.y = alpha * v1 + beta * old.y;
+                            }
+                            *reinterpret_cast<double2 *>(cp) = o;
+                        } else {
+                            if (ok0) cp[0] = (beta == 0.0) ? alpha * v0 : alpha * v0 + beta * cp[0];
+                            if (ok1) cp[1] = (beta == 0.0) ? alpha * v1 : alpha * v1 + beta * cp[1];
+                        }
+                    }
+        }
+    }
+}
+
+// ---- split-K reduction (fixed order => deterministic) ------------------------------------------------------------
+__global__ void __launch_bounds__(256) rb_splitk_reduce_kernel(const double *__restrict__ partial, i64 ldp, i64 splits,
+                                                               i64 m, i64 n, i64 batch, double alpha, double beta,
+                                                               double *__restrict__ c, i64 ldc, i64 stride_c, int tri)
+{
+    i64 total = m * n * batch;
+    i64 stride = (i64)gridDim.x * blockDim.x;
+    i64 split_stride = batch * n * ldp;
+    for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        i64 i = e % m, r = e / m;
+        i64 j = r % n, b = r / n;
+        if (tri == 1 && i > j) continue;
+        if (tri == 2 && i < j) continue;
+        const double *pp = partial + (b * n + j) * ldp + i;
+        double s = 0.0;
+        for (i64 sp = 0; sp < splits; ++sp) s += pp[sp * split_stride];
+        double *cp = c + b * stride_c + i + j * ldc;
+        *cp = (beta == 0.0) ? alpha * s : alpha * s + beta * (*cp);
+    }
+}
+
+// ---- generic kernel: any alignment / leading dimension, plain loads -------------------------------------------------
+// 64x64 CTA tile, 4 warps (32x32 each = 4x4 DMMA tiles), BK = 16, smem [k][64+4] (conflict-free LDS.64 fragments).
+constexpr int GB = 64, GK = 16, GPAD = 4;
+
+__global__ void __launch_bounds__(128)
+rb_gemm_generic_kernel(bool ta, bool tb, i64 m, i64 n, i64 k, double alpha, const double *__restrict__ a, i64 lda,
+                       i64 stride_a, const double *__restrict__ b, i64 ldb, i64 stride_b, double beta,
+                       double *__restrict__ c, i64 ldc, i64 stride_c, i64 tiles_m, i64 tiles_n, int tri)
+{
+    __shared__ double As[GK][GB + GPAD];
+    __shared__ double Bs[GK][GB + GPAD];
+    const i64 tile = blockIdx.x;
+    const i64 bidx = blockIdx.y;
+    const i64 tm = tile % tiles_m, tn = tile / tiles_m;
+    if (tri == 1 && tm > tn) return;
+    if (tri == 2 && tm < tn) return;
+    const double *ab = a + bidx * stride_a;
+    const double *bb = b + bidx * stride_b;
+    double *cb = c + bidx * stride_c;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wm = warp & 1, wn = warp >> 1;
+    const int g = lane >> 2, t = lane & 3;
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+    for (i64 k0 = 0; k0 < k; k0 += GK) {
+        // cooperative loads: 64*16 elements per operand, 128 threads -> 8 each
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            int e = threadIdx.x + r * 128;
+            int mm, kk;
+            if (ta) { kk = e % GK; mm = e / GK; }  // K-major source: consecutive threads walk k
+            else { mm = e % GB; kk = e / GB; }
+            i64 gm = tm * GB + mm, gk = k0 + kk;
+            double v = 0.0;
+            if (gm < m && gk < k) v = ta ? ab[gk + gm * lda] : ab[gm + gk * lda];
+            As[kk][mm] = v;
+            int nn;
+            if (!tb) { kk = e % GK; nn = e / GK; } // B 'N' is K-major
+            else { nn = e % GB; kk = e / GB; }
+            i64 gn = tn * GB + nn;
+            gk = k0 + kk;
+            v = 0.0;
+            if (gn < n && gk < k) v = tb ? bb[gn + gk * ldb] : bb[gk + gn * ldb];
+            Bs[kk][nn] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int ks = 0; ks < GK; ks += 4) {
+            double af[4], bf[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) af[i] = As[ks + t][wm * 32 + i * 8 + g];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bf[j] = Bs[ks + t][wn * 32 + j * 8 + g];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma(acc[i][j], af[i], bf[j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                i64 row = tm * GB + wm * 32 + i * 8 + g;
+                i64 col = tn * GB + wn * 32 + j * 8 + 2 * t + cc;
+                if (row >= m || col >= n) continue;
+                if (tri == 1 && row > col) continue;
+                if (tri == 2 && row < col) continue;
+                double *cp = cb + row + col * ldc;
+                *cp = (beta == 0.0) ? alpha * acc[i][j][cc] : alpha * acc[i][j][cc] + beta * (*cp);
+            }
+}
+
+// C = beta*C over an m x n block (k == 0 or alpha == 0 degenerate cases)
+__global__ void __launch_bounds__(256) rb_scale_c_kernel(double *__restrict__ c, i64 m, i64 n, i64 ldc, i64 stride_c,
+                                                         i64 batch, double beta, int tri)
+{
+    i64 total = m * n * batch;
+    i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        i64 i = e % m, r = e / m;
+        i64 j = r % n, b = r / n;
+        if (tri == 1 && i > j) continue;
+        if (tri == 2 && i < j) continue;
+        double *cp = c + b * stride_c + i + j * ldc;
+        *cp = (beta == 0.0) ? 0.0 : beta * (*cp);
+    }
+}
+
+int encode_map(rb_ctx *ctx, CUtensorMap *tm, const double *base, bool k_major, i64 rows, i64 k, i64 ld, i64 stride,
+               i64 batch)
+{
+    // k_major: dims {k, rows, batch}, box {8, 128, 1}, no swizzle; else dims {rows, k, batch}, box {16, BK, 1}, 128B swizzle
+    cuuint64_t dims[3];
+    cuuint64_t strides[2];
+    cuuint32_t box[3];
+    cuuint32_t estr[3] = {1, 1, 1};
+    i64 d0 = k_major ? k : rows, d1 = k_major ? rows : k;
+    dims[0] = (cuuint64_t)d0; dims[1] = (cuuint64_t)d1; dims[2] = (cuuint64_t)(batch > 0 ? batch : 1);
+    strides[0] = (cuuint64_t)ld * 8;
+    i64 bs = (batch > 1) ? stride : ld * d1;
+    if (bs <= 0) bs = ld * d1;
+    strides[1] = (cuuint64_t)bs * 8;
+    if (k_major) { box[0] = 8; box[1] = 128; box[2] = 1; }
+    else { box[0] = 16; box[1] = BK; box[2] = 1; }
+    CUresult r = ctx->encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void *)base, dims, strides, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                   k_major ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        rb_set_error("cuTensorMapEncodeTiled failed (%d): dims {%lld,%lld,%lld} ld %lld stride %lld", (int)r,
+                     (long long)d0, (long long)d1, (long long)batch, (long long)ld, (long long)bs);
+        return RB_ERR_CUDA;
+    }
+    return RB_OK;
+}
+
+bool tma_eligible(const rb_ctx *ctx, const double *p, i64 ld, i64 stride, i64 batch, i64 d0, i64 d1)
+{
+    if (!ctx->encode_tiled) return false;
+    if (((uintptr_t)p) & 15) return false;
+    if (ld & 1) return false;
+    if (batch > 1 && (stride & 1)) return false;
+    if (batch > 1 && stride < 0) return false;
+    if (ld * 8 >= (1LL << 40)) return false;
+    if (batch > 1 && stride * 8 >= (1LL << 40)) return false;
+    if (d0 >= (1LL << 32) || d1 >= (1LL << 32) || batch >= (1LL << 32)) return false;
+    if (ld < d0) return false;
+    return true;
+}
+
+template <bool A_K, bool B_K>
+int launch_tma(rb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p, int grid)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        RB_CUDA(cudaFuncSetAttribute(rb_gemm_tma_kernel<A_K, B_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr_set = true;
+    }
+    rb_gemm_tma_kernel<A_K, B_K><<<grid, NUM_THREADS, SMEM_BYTES, ctx->stream>>>(tmA, tmB, p);
+    RB_LAUNCHED(ctx);
+    return RB_OK;
+}
+
+} // namespace
+
+int rb_gemm_core(rb_ctx *ctx, bool ta, bool tb, i64 m, i64 n, i64 k, double alpha, const double *a, i64 lda,
+                 i64 stride_a, const double *b, i64 ldb, i64 stride_b, double beta, double *c, i64 ldc, i64 stride_c,
+                 i64 batch, int tri)
+{
+    if (m <= 0 || n <= 0 || batch <= 0) return RB_OK;
+    RB_REQUIRE(c != nullptr, "gemm: C is NULL");
+    RB_REQUIRE(ldc >= m, "gemm: ldc (%lld) < m (%lld)", (long long)ldc, (long long)m);
+    if (k <= 0 || alpha == 0.0) {
+        if (beta == 1.0) return RB_OK;
+        i64 total = m * n * batch;
+        i64 blocks = rb_cdiv(total, 256);
+        i64 cap = (i64)ctx->num_sms * 16;
+        if (blocks > cap) blocks = cap;
+        rb_scale_c_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(c, m, n, ldc, stride_c, batch, beta, tri);
+        RB_LAUNCHED(ctx);
+        return RB_OK;
+    }
+    RB_REQUIRE(a && b, "gemm: NULL operand");
+    RB_REQUIRE(lda >= (ta ? k : m), "gemm: lda (%lld) too small", (long long)lda);
+    RB_REQUIRE(ldb >= (tb ? n : k), "gemm: ldb (%lld) too small", (long long)ldb);
+    if (tri) RB_REQUIRE(m == n, "gemm: triangular output needs m == n");
+
+    const bool a_k = ta, b_k = !tb; // K-major operands
+    bool use_tma = ctx->gemm_path == 0 &&
+                   tma_eligible(ctx, a, lda, stride_a, batch, a_k ? k : m, a_k ? m : k) &&
+                   tma_eligible(ctx, b, ldb, stride_b, batch, b_k ? k : n, b_k ? n : k);
+    if (use_tma) {
+        CUtensorMap tmA, tmB;
+        const bool a_batched = batch > 1 && stride_a != 0, b_batched = batch > 1 && stride_b != 0;
+        RB_TRY(encode_map(ctx, &tmA, a, a_k, m, k, lda, stride_a, a_batched ? batch : 1));
+        RB_TRY(encode_map(ctx, &tmB, b, b_k, n, k, ldb, stride_b, b_batched ? batch : 1));
+        GemmParams p;
+        p.m = m; p.n = n; p.k = k; p.batch = batch;
+        p.tiles_m = rb_cdiv(m, BM); p.tiles_n = rb_cdiv(n, BN);
+        p.tiles_per_batch = tri ? p.tiles_m * (p.tiles_m + 1) / 2 : p.tiles_m * p.tiles_n;
+        i64 tiles = p.tiles_per_batch * batch;
+        // split-K when the tile count cannot fill the chip and K is deep
+        i64 splits = 1;
+        i64 ksteps = rb_cdiv(k, BK);
+        if (tiles < ctx->num_sms && ksteps >= 8) {
+            splits = (2 * (i64)ctx->num_sms) / tiles;
+            if (splits > ksteps / 4) splits = ksteps / 4;
+            if (splits < 1) splits = 1;
+        }
+        i64 kper = rb_cdiv(ksteps, splits) * BK;
+        splits = rb_cdiv(k, kper);
+        p.splits = splits; p.kper = kper;
+        p.total_items = tiles * splits;
+        p.alpha = alpha; p.beta = beta; p.c = c; p.ldc = ldc; p.stride_c = stride_c; p.tri = tri;
+        p.partial = nullptr; p.ldp = (m + 1) & ~(i64)1;
+        p.a_batched = a_batched ? 1 : 0; p.b_batched = b_batched ? 1 : 0;
+        if (splits > 1) {
+            void *ws;
+            RB_TRY(rb_ws_reserve(ctx, 1, splits * batch * n * p.ldp * 8, &ws));
+            p.partial = (double *)ws;
+        }
+        int grid = (int)(p.total_items < ctx->num_sms ? p.total_items : ctx->num_sms);
+        if (a_k && b_k) RB_TRY((launch_tma<true, true>(ctx, tmA, tmB, p, grid)));
+        else if (a_k && !b_k) RB_TRY((launch_tma<true, false>(ctx, tmA, tmB, p, grid)));
+        else if (!a_k && b_k) RB_TRY((launch_tma<false, true>(ctx, tmA, tmB, p, grid)));
+        else RB_TRY((launch_tma<false, false>(ctx, tmA, tmB, p, grid)));
+        if (splits > 1) {
+            i64 total = m * n * batch;
+            i64 blocks = rb_cdiv(total, 256);
+            i64 cap = (i64)ctx->num_sms * 16;
+            if (blocks > cap) blocks = cap;
+            rb_splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(p.partial, p.ldp, splits, m, n, batch,
+                                                                              alpha, beta, c, ldc, stride_c, tri);
+            RB_LAUNCHED(ctx);
+        }
+        return RB_OK;
+    }
+    // generic path
+    i64 tiles_m = rb_cdiv(m, GB), tiles_n = rb_cdiv(n, GB);
+    RB_REQUIRE(tiles_m * tiles_n < 2147483647LL && batch <= 65535, "gemm(generic): problem too large for this path");
+    dim3 grid((unsigned)(tiles_m * tiles_n), (unsigned)batch);
+    rb_gemm_generic_kernel<<<grid, 128, 0, ctx->stream>>>(ta, tb, m, n, k, alpha, a, lda, stride_a, b, ldb, stride_b,
+                                                          beta, c, ldc, stride_c, tiles_m, tiles_n, tri);
+    RB_LAUNCHED(ctx);
+    return RB_OK;
+}

@@ -1,0 +1,477 @@
+// rb_layout.cu -- the HBM-bound, bit-exact half of the hot path:
+//   MatrixUpper pack/unpack, per-slab symmetric pack, strided sub-box copies (copy_mm/mr/rm/rr),
+//   rank-3 transposes, the axpy family and the counter-based synthetic generators.
+// Every kernel moves each algorithmic byte once, coalesced along the unit-stride index.
+#include "rb_common.cuh"
+
+// ---------------------------------------------------------------------------------------------------------
+// pack: packed[j(j+1)/2 + i] = full[i + j*n], i <= j      (matrixfull.rs:638-646, matrix_trait.rs:191-217)
+// One CTA per (64-row block, column); tiles strictly below the diagonal exit at once.  blockIdx.z = slab.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) rb_pack_upper_kernel(const double *__restrict__ full, double *__restrict__ packed,
+                                                           i64 n, i64 full_slab, i64 packed_slab)
+{
+    i64 j = blockIdx.y;
+    i64 i = (i64)blockIdx.x * 64 + threadIdx.x;
+    if (i > j) return;
+    const double *f = full + (i64)blockIdx.z * full_slab;
+    double *p = packed + (i64)blockIdx.z * packed_slab;
+    p[j * (j + 1) / 2 + i] = f[i + j * n];
+}
+
+// Wider variant for large n: each CTA handles a 256-row x 8-column panel (fewer, fatter CTAs).
+__global__ void __launch_bounds__(256) rb_pack_upper_panel_kernel(const double *__restrict__ full,
+                                                                  double *__restrict__ packed, i64 n, i64 full_slab,
+                                                                  i64 packed_slab)
+{
+    i64 j0 = (i64)blockIdx.y * 8;
+    i64 i = (i64)blockIdx.x * 256 + threadIdx.x;
+    if ((i64)blockIdx.x * 256 > j0 + 7) return;
+    const double *f = full + (i64)blockIdx.z * full_slab;
+    double *p = packed + (i64)blockIdx.z * packed_slab;
+    double v[8];
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+        i64 j = j0 + jj;
+        v[jj] = (j < n && i <= j) ? f[i + j * n] : 0.0;
+    }
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+        i64 j = j0 + jj;
+        if (j < n && i <= j) p[j * (j + 1) / 2 + i] = v[jj];
+    }
+}
+
+static int launch_pack(rb_ctx *ctx, const double *full, i64 n, i64 nslab, double *packed)
+{
+    if (n == 0 || nslab == 0) return RB_OK;
+    i64 np = n * (n + 1) / 2;
+    for (i64 z0 = 0; z0 < nslab; z0 += 65535) {
+        unsigned nz = (unsigned)((nslab - z0) < 65535 ? (nslab - z0) : 65535);
+        if (n >= 512) {
+            dim3 grid((unsigned)rb_cdiv(n, 256), (unsigned)rb_cdiv(n, 8), nz);
+            RB_REQUIRE(grid.y <= 65535, "pack: n too large");
+            rb_pack_upper_panel_kernel<<<grid, 256, 0, ctx->stream>>>(full + z0 * n * n, packed + z0 * np, n, n * n, np);
+        } else {
+            dim3 grid((unsigned)rb_cdiv(n, 64), (unsigned)n, nz);
+            rb_pack_upper_kernel<<<grid, 64, 0, ctx->stream>>>(full + z0 * n * n, packed + z0 * np, n, n * n, np);
+        }
+        RB_LAUNCHED(ctx);
+    }
+    return RB_OK;
+}
+
+extern "C" int rb_pack_upper(rb_ctx *ctx, const double *full, int64_t n, double *packed)
+{
+    RB_REQUIRE(ctx && n >= 0, "rb_pack_upper: bad arguments");
+    RB_REQUIRE(n == 0 || (full && packed), "rb_pack_upper: NULL buffer");
+    RB_CUDA(cudaSetDevice(ctx->device));
+    return launch_pack(ctx, full, n, 1, packed);
+}
+
+extern "C" int rb_ri_pack_symm(rb_ctx *ctx, const double *ri, int64_t nao, int64_t naux, double *out)
+{
+    RB_REQUIRE(ctx && nao >= 0 && naux >= 0, "rb_ri_pack_symm: bad arguments");
+    RB_CUDA(cudaSetDevice(ctx->device));
+    return launch_pack(ctx, ri, nao, naux, out);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// unpack: full[i + j*n] = full[j + i*n] = packed[j(j+1)/2 + i], i <= j          (matrixupper.rs:330-373)
+// One CTA per 32x32 tile pair (ti <= tj): the packed tile is read once (coalesced along i), written to the
+// upper position directly and to the mirrored lower position through a padded smem transpose, so every
+// access is unit-stride.  The reference's mirror loop reads stride-n; this reads each packed byte once.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rb_unpack_upper_kernel(const double *__restrict__ packed,
+                                                              double *__restrict__ full, i64 n)
+{
+    __shared__ double tile[32][33];
+    // linear tile-pair index -> (ti <= tj): pair p = tj(tj+1)/2 + ti
+    i64 p = blockIdx.x;
+    i64 tj = (i64)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
+    while (tj * (tj + 1) / 2 > p) --tj;
+    while ((tj + 1) * (tj + 2) / 2 <= p) ++tj;
+    i64 ti = p - tj * (tj + 1) / 2;
+    int tx = threadIdx.x & 31, ty = threadIdx.x >> 5; // 32 x 8
+    i64 i0 = ti * 32, j0 = tj * 32;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        int jj = ty + r * 8;
+        i64 i = i0 + tx, j = j0 + jj;
+        double v = 0.0;
+        if (i < n && j < n) {
+            // off-diagonal tiles have i < j everywhere; diagonal tiles fetch the (min,max) element
+            i64 a = i <= j ? i : j, b = i <= j ? j : i;
+            v = packed[b * (b + 1) / 2 + a];
+            full[i + j * n] = v; // upper tile (and, for the diagonal tile, the whole symmetric tile)
+        }
+        tile[jj][tx] = v;
+    }
+    if (ti == tj) return;
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        int ii = ty + r * 8;          // column index inside the mirrored tile = row i of the upper tile
+        i64 row = j0 + tx, col = i0 + ii; // full[row=j, col=i] = upper[i, j]
+        if (row < n && col < n) full[row + col * n] = tile[tx][ii];
+    }
+}
+
+extern "C" int rb_unpack_upper(rb_ctx *ctx, const double *packed, int64_t n, double *full)
+{
+    RB_REQUIRE(ctx && n >= 0, "rb_unpack_upper: bad arguments");
+    if (n == 0) return RB_OK;
+    RB_REQUIRE(packed && full, "rb_unpack_upper: NULL buffer");
+    RB_CUDA(cudaSetDevice(ctx->device));
+    i64 nt = rb_cdiv(n, 32);
+    i64 pairs = nt * (nt + 1) / 2;
+    RB_REQUIRE(pairs < 2147483647LL, "rb_unpack_upper: n too large");
+    rb_unpack_upper_kernel<<<(unsigned)pairs, 256, 0, ctx->stream>>>(packed, full, n);
+    RB_LAUNCHED(ctx);
+    return RB_OK;
+}
+
+// Copy one triangle of a square matrix onto the other (used after SYRK-style K builds).
+__global__ void __launch_bounds__(256) rb_symmetrize_kernel(double *__restrict__ c, i64 n, i64 ldc, int from_upper)
+{
+    __shared__ double tile[32][33];
+    i64 p = blockIdx.x;
+    i64 tj = (i64)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
+    while (tj * (tj + 1) / 2 > p) --tj;
+    while ((tj + 1) * (tj + 2) / 2 <= p) ++tj;
+    i64 ti = p - tj * (tj + 1) / 2; // ti <= tj
+    int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    // source tile: upper => rows from block ti, cols from block tj ; lower => rows tj, cols ti
+    i64 sr0 = from_upper ? ti * 32 : tj * 32, sc0 = from_upper ? tj * 32 : ti * 32;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        int cc = ty + r * 8;
+        i64 row = sr0 + tx, col = sc0 + cc;
+        tile[cc][tx] = (row < n && col < n) ? c[row + col * ldc] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        int cc = ty + r * 8;
+        i64 row = sc0 + tx, col = sr0 + cc; // destination (transposed position)
+        if (row < n && col < n) {
+            bool dst_is_target = from_upper ? (row > col) : (row < col);
+            if (dst_is_target) c[row + col * ldc] = tile[tx][cc];
+        }
+    }
+}
+
+int rb_symmetrize(rb_ctx *ctx, double *c, i64 n, i64 ldc, bool from_upper)
+{
+    if (n <= 1) return RB_OK;
+    i64 nt = rb_cdiv(n, 32);
+    i64 pairs = nt * (nt + 1) / 2;
+    rb_symmetrize_kernel<<<(unsigned)pairs, 256, 0, ctx->stream>>>(c, n, ldc, from_upper ? 1 : 0);
+    RB_LAUNCHED(ctx);
+    return RB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Generic strided 3-D copy -- copy_mm / copy_mr / copy_rm / copy_rr and transpose_ikj all reduce to it.
+// VEC=2 moves double2 along i when both sides are unit-stride and 16-byte aligned.
+// ---------------------------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(256) rb_copy3d_kernel(const double *__restrict__ src, i64 si, i64 sj, i64 sk,
+                                                        double *__restrict__ dst, i64 di, i64 dj, i64 dk, i64 ni,
+                                                        i64 nj, i64 nk)
+{
+    i64 niv = ni / VEC;
+    i64 rows = nj * nk;
+    i64 total = niv * rows;
+    i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        i64 i = t % niv, r = t / niv;
+        i64 j = r % nj, k = r / nj;
+        if (VEC == 2) {
+            const double2 *s = reinterpret_cast<const double2 *>(src + j * sj + k * sk) + i;
+            double2 *d = reinterpret_cast<double2 *>(dst + j * dj + k * dk) + i;
+            *d = *s;
+        } else {
+            dst[i * di + j * dj + k * dk] = src[i * si + j * sj + k * sk];
+        }
+    }
+}
+
+int rb_copy3d(rb_ctx *ctx, const double *src, i64 s0, i64 si, i64 sj, i64 sk, double *dst, i64 d0, i64 di, i64 dj,
+              i64 dk, i64 ni, i64 nj, i64 nk)
+{
+    if (ni <= 0 || nj <= 0 || nk <= 0) return RB_OK;
+    const double *s = src + s0;
+    double *d = dst + d0;
+    bool vec = si == 1 && di == 1 && (ni % 2 == 0) && (sj % 2 == 0) && (sk % 2 == 0) && (dj % 2 == 0) &&
+               (dk % 2 == 0) && (((uintptr_t)s & 15) == 0) && (((uintptr_t)d & 15) == 0);
+    i64 total = (vec ? ni / 2 : ni) * nj * nk;
+    i64 blocks = rb_cdiv(total, 256);
+    i64 cap = (i64)ctx->num_sms * 16;
+    if (blocks > cap) blocks = cap;
+    if (vec) rb_copy3d_kernel<2><<<(unsigned)blocks, 256, 0, ctx->stream>>>(s, si, sj, sk, d, di, dj, dk, ni, nj, nk);
+    else rb_copy3d_kernel<1><<<(unsigned)blocks, 256, 0, ctx->stream>>>(s, si, sj, sk, d, di, dj, dk, ni, nj, nk);
+    RB_LAUNCHED(ctx);
+    return RB_OK;
+}
+
+static bool box_ok(i64 start, i64 len, i64 dim) { return start >= 0 && len >= 0 && start + len <= dim; }
+
+extern "C" int rb_copy_mm(rb_ctx *ctx, int xl, int yl, const double *f, int fx, int fy, int fxs, int fys, double *t,
+                          int tx, int ty, int txs, int tys)
+{
+    RB_REQUIRE(ctx, "rb_copy_mm: ctx is NULL");
+    RB_REQUIRE(box_ok(fxs, xl, fx) && box_ok(fys, yl, fy) && box_ok(txs, xl, tx) && box_ok(tys, yl, ty),
+               "rb_copy_mm: block outside matrix");
+    RB_CUDA(cudaSetDevice(ctx->device));
+    return rb_copy3d(ctx, f, fxs + (i64)fys * fx, 1, fx, 0, t, txs + (i64)tys * tx, 1, tx, 0, xl, yl, 1);
+}
+
+// strides of the (x1, x2) block inside an RI tensor [X,Y,Z] for the three copy modes (restmatr.f90:227-237)
+static int ri_mode_strides(int mod, i64 X, i64 Y, i64 Z, i64 s1, i64 s2, i64 x3, i64 l1, i64 l2, i64 *off, i64 *st1,
+                           i64 *st2)
+{
+    if (mod == 0) {
+        if (!(box_ok(s1, l1, X) && box_ok(s2, l2, Y) && x3 >= 0 && x3 < Z)) return 1;
+        *off = s1 + s2 * X + x3 * X * Y; *st1 = 1; *st2 = X;
+    } else if (mod == 1) {
+        if (!(box_ok(s1, l1, X) && box_ok(s2, l2, Z) && x3 >= 0 && x3 < Y)) return 1;
+        *off = s1 + x3 * X + s2 * X * Y; *st1 = 1; *st2 = X * Y;
+    } else {
+        if (!(box_ok(s1, l1, Y) && box_ok(s2, l2, Z) && x3 >= 0 && x3 < X)) return 1;
+        *off = x3 + s1 * X + s2 * X * Y; *st1 = X; *st2 = X * Y;
+    }
+    return 0;
+}
+
+extern "C" int rb_copy_mr(rb_ctx *ctx, int xl, int yl, const double *f, int fx, int fy, int fxs, int fys, double *t,
+                          int tx, int ty, int tz, int txs, int tys, int t3, int mod)
+{
+    RB_REQUIRE(ctx, "rb_copy_mr: ctx is NULL");
+    if (mod < 0 || mod > 2) return RB_OK; // restmatr.f90:227-237: other mods are a no-op
+    RB_REQUIRE(box_ok(fxs, xl, fx) && box_ok(fys, yl, fy), "rb_copy_mr: block outside matrix");
+    i64 off, s1, s2;
+    RB_REQUIRE(ri_mode_strides(mod, tx, ty, tz, txs, tys, t3, xl, yl, &off, &s1, &s2) == 0,
+               "rb_copy_mr: block outside tensor");
+    RB_CUDA(cudaSetDevice(ctx->device));
+    return rb_copy3d(ctx, f, fxs + (i64)fys * fx, 1, fx, 0, t, off, s1, s2, 0, xl, yl, 1);
+}
+
+extern "C" int rb_copy_rm(rb_ctx *ctx, int xl, int yl, const double *f, int fx, int fy, int fz, int fxs, int fys,
+                          int f3, int mod, double *t, int tx, int ty, int txs, int tys)
+{
+    RB_REQUIRE(ctx, "rb_copy_rm: ctx is NULL");
+    if (mod < 0 || mod > 2) return RB_OK;
+    RB_REQUIRE(box_ok(txs, xl, tx) && box_ok(tys, yl, ty), "rb_copy_rm: block outside matrix");
+    i64 off, s1, s2;
+    RB_REQUIRE(ri_mode_strides(mod, fx, fy, fz, fxs, fys, f3, xl, yl, &off, &s1, &s2) == 0,
+               "rb_copy_rm: block outside tensor");
+    RB_CUDA(cudaSetDevice(ctx->device));
+    return rb_copy3d(ctx, f, off, s1, s2, 0, t, txs + (i64)tys * tx, 1, tx, 0, xl, yl, 1);
+}
+
+extern "C" int rb_copy_rr(rb_ctx *ctx, int xl, int yl, int zl, const double *f, int fx, int fy, int fz, int fxs,
+                          int fys, int fzs, double *t, int tx, int ty, int tz, int txs, int tys, int tzs)
+{
+    RB_REQUIRE(ctx, "rb_copy_rr: ctx is NULL");
+    RB_REQUIRE(box_ok(fxs, xl, fx) && box_ok(fys, yl, fy) && box_ok(fzs, zl, fz) && box_ok(txs, xl, tx) &&
+                   box_ok(tys, yl, ty) && box_ok(tzs, zl, tz),
+               "rb_copy_rr: box outside tensor");
+    RB_CUDA(cudaSetDevice(ctx->device));
+    i64 FX = fx, FY = fy, TX = tx, TY = ty;
+    return rb_copy3d(ctx, f, fxs + fys * FX + fzs * FX * FY, 1, FX, FX * FY, t, txs + tys * TX + tzs * TX * TY, 1, TX,
+                     TX * TY, xl, yl, zl);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Batched tiled 2-D transpose: out[c + r*ors + b*obs] = in[r + c*ics + b*ibs]   (r, c unit-stride on in / out)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rb_transpose_kernel(const double *__restrict__ in, i64 ics, i64 ibs,
+                                                           double *__restrict__ out, i64 ors, i64 obs, i64 nr, i64 nc,
+                                                           i64 tiles_r, i64 tiles_c, i64 total_tiles)
+{
+    __shared__ double tile[32][33];
+    int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (i64 t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        i64 tr = t % tiles_r, rest = t / tiles_r;
+        i64 tc = rest % tiles_c, b = rest / tiles_c;
+        const double *ib = in + b * ibs;
+        double *ob = out + b * obs;
+        i64 r0 = tr * 32, c0 = tc * 32;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            int cc = ty + q * 8;
+            i64 r = r0 + tx, c = c0 + cc;
+            tile[cc][tx] = (r < nr && c < nc) ? ib[r + c * ics] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            int rr = ty + q * 8;
+            i64 r = r0 + rr, c = c0 + tx;
+            if (r < nr && c < nc) ob[c + r * ors] = tile[tx][rr];
+        }
+        __syncthreads();
+    }
+}
+
+int rb_transpose_batched(rb_ctx *ctx, const double *in, i64 ics, i64 ibs, double *out, i64 ors, i64 obs, i64 nr,
+                         i64 nc, i64 nbatch)
+{
+    if (nr <= 0 || nc <= 0 || nbatch <= 0) return RB_OK;
+    i64 tiles_r = rb_cdiv(nr, 32), tiles_c = rb_cdiv(nc, 32);
+    i64 total = tiles_r * tiles_c * nbatch;
+    i64 blocks = total;
+    i64 cap = (i64)ctx->num_sms * 32;
+    if (blocks > cap) blocks = cap;
+    rb_transpose_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(in, ics, ibs, out, ors, obs, nr, nc, tiles_r,
+                                                                  tiles_c, total);
+    RB_LAUNCHED(ctx);
+    return RB_OK;
+}
+
+extern "C" int rb_matrix_transpose(rb_ctx *ctx, const double *in, int64_t rows, int64_t cols, double *out)
+{
+    RB_REQUIRE(ctx && rows >= 0 && cols >= 0, "rb_matrix_transpose: bad arguments");
+    RB_CUDA(cudaSetDevice(ctx->device));
+    return rb_transpose_batched(ctx, in, rows, 0, out, cols, 0, rows, cols, 1);
+}
+
+// ri.rs:227-294.  in [I,J,K]:  0 jik -> [J,I,K]; 1 jki -> [J,K,I]; 2 kji -> [K,J,I]; 3 ikj -> [I,K,J]
+extern "C" int rb_ri_transpose(rb_ctx *ctx, const double *in, int64_t I, int64_t J, int64_t K, int which, double *out)
+{
+    RB_REQUIRE(ctx && I >= 0 && J >= 0 && K >= 0, "rb_ri_transpose: bad arguments");
+    RB_REQUIRE(which >= 0 && which <= 3, "rb_ri_transpose: which must be 0..3");
+    RB_CUDA(cudaSetDevice(ctx->device));
+    switch (which) {
+    case 0: // per-slab transpose: out[j + i*J + k*IJ]
+        return rb_transpose_batched(ctx, in, I, I * J, out, J, I * J, I, J, K);
+    case 1: // [I,(JK)] -> [(JK),I]: out[n + i*JK], n = j + k*J
+        return rb_transpose_batched(ctx, in, I, 0, out, J * K, 0, I, J * K, 1);
+    case 2: // for each j: (i,k) -> (k,i): in i + k*IJ (+ j*I), out k + i*JK (+ j*K)
+        return rb_transpose_batched(ctx, in, I * J, I, out, J * K, K, I, K, J);
+    default: // ikj: out[i + k*I + j*IK] = in[i + j*I + k*IJ]; unit-stride runs of I
+        return rb_copy3d(ctx, in, 0, 1, I, I * J, out, 0, 1, I * K, I, I, J, K);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// axpy family.  __dmul_rn/__dadd_rn keep the reference's unfused "*c += p*b" rounding (Rust never emits FMA).
+// ---------------------------------------------------------------------------------------------------------
+template <int OP>
+__global__ void __launch_bounds__(256) rb_axpy_kernel(double *__restrict__ c, const double *__restrict__ p, double a,
+                                                      double b, i64 n)
+{
+    i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double cv = c[i];
+        double pv = (OP == 2) ? 0.0 : p[i];
+        double r;
+        if (OP == 0) r = __dadd_rn(cv, __dmul_rn(pv, b));                       // c += p*b
+        else if (OP == 1) r = __dadd_rn(__dmul_rn(cv, a), __dmul_rn(pv, b));    // c = c*a + p*b
+        else if (OP == 2) r = __dmul_rn(cv, a);                                 // c *= a
+        else if (OP == 3) r = __dadd_rn(cv, pv);                                // c += p
+        else r = __dsub_rn(cv, pv);                                             // c -= p
+        c[i] = r;
+    }
+}
+
+template <int OP>
+static int launch_axpy(rb_ctx *ctx, double *c, const double *p, double a, double b, i64 n)
+{
+    RB_REQUIRE(ctx && n >= 0, "axpy: bad arguments");
+    if (n == 0) return RB_OK;
+    RB_CUDA(cudaSetDevice(ctx->device));
+    i64 blocks = rb_cdiv(n, 256);
+    i64 cap = (i64)ctx->num_sms * 16;
+    if (blocks > cap) blocks = cap;
+    rb_axpy_kernel<OP><<<(unsigned)blocks, 256, 0, ctx->stream>>>(c, p, a, b, n);
+    RB_LAUNCHED(ctx);
+    return RB_OK;
+}
+extern "C" int rb_self_scaled_add(rb_ctx *ctx, double *c, const double *p, double b, int64_t n) { return launch_axpy<0>(ctx, c, p, 0.0, b, n); }
+extern "C" int rb_self_general_add(rb_ctx *ctx, double *c, const double *p, double a, double b, int64_t n) { return launch_axpy<1>(ctx, c, p, a, b, n); }
+extern "C" int rb_self_multiple(rb_ctx *ctx, double *c, double a, int64_t n) { return launch_axpy<2>(ctx, c, nullptr, a, 0.0, n); }
+extern "C" int rb_self_add(rb_ctx *ctx, double *c, const double *p, int64_t n) { return launch_axpy<3>(ctx, c, p, 0.0, 0.0, n); }
+extern "C" int rb_self_sub(rb_ctx *ctx, double *c, const double *p, int64_t n) { return launch_axpy<4>(ctx, c, p, 0.0, 0.0, n); }
+
+// y[i*inc] = beta == 0 ? 0 : beta*y[i*inc]
+__global__ void __launch_bounds__(256) rb_scale_or_zero_kernel(double *__restrict__ y, i64 n, i64 inc, double beta)
+{
+    i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        y[i * inc] = (beta == 0.0) ? 0.0 : beta * y[i * inc];
+}
+int rb_scale_or_zero(rb_ctx *ctx, double *y, i64 n, i64 inc, double beta)
+{
+    if (n <= 0 || beta == 1.0) return RB_OK;
+    i64 blocks = rb_cdiv(n, 256);
+    i64 cap = (i64)ctx->num_sms * 16;
+    if (blocks > cap) blocks = cap;
+    rb_scale_or_zero_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(y, n, inc, beta);
+    RB_LAUNCHED(ctx);
+    return RB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Counter-based synthetic inputs; same splitmix64 finaliser as oracle/rest_oracle.c.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double rb_synth(uint64_t seed, uint64_t idx, double scale)
+{
+    uint64_t z = seed + 0x9E3779B97F4A7C15ULL * (idx + 1ULL);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z ^= z >> 31;
+    double u = __dmul_rn((double)(z >> 11), 1.0 / 9007199254740992.0);
+    return __dmul_rn(__dsub_rn(__dmul_rn(2.0, u), 1.0), scale);
+}
+
+__global__ void __launch_bounds__(256) rb_fill_linear_kernel(double *__restrict__ v, i64 n, uint64_t seed,
+                                                             uint64_t idx0, double scale)
+{
+    i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        v[i] = rb_synth(seed, idx0 + (uint64_t)i, scale);
+}
+
+__global__ void __launch_bounds__(256) rb_fill_ri3ao_symm_kernel(double *__restrict__ a, i64 nb, i64 p_lo, i64 nslab,
+                                                                 uint64_t seed, double scale)
+{
+    i64 n2 = nb * nb;
+    i64 total = n2 * nslab;
+    i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        i64 p = t / n2, r = t - p * n2;
+        i64 nu = r / nb, mu = r - nu * nb;
+        i64 lo = mu < nu ? mu : nu, hi = mu < nu ? nu : mu;
+        a[t] = rb_synth(seed, (uint64_t)(lo + hi * nb + (p + p_lo) * n2), scale);
+    }
+}
+
+extern "C" int rb_fill_linear(rb_ctx *ctx, double *v, int64_t n, uint64_t seed, uint64_t idx0, double scale)
+{
+    RB_REQUIRE(ctx && n >= 0, "rb_fill_linear: bad arguments");
+    if (n == 0) return RB_OK;
+    RB_CUDA(cudaSetDevice(ctx->device));
+    i64 blocks = rb_cdiv(n, 256);
+    i64 cap = (i64)ctx->num_sms * 16;
+    if (blocks > cap) blocks = cap;
+    rb_fill_linear_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(v, n, seed, idx0, scale);
+    RB_LAUNCHED(ctx);
+    return RB_OK;
+}
+
+extern "C" int rb_fill_ri3ao_symm(rb_ctx *ctx, double *a, int64_t nb, int64_t p_lo, int64_t p_hi, uint64_t seed,
+                                  double scale)
+{
+    RB_REQUIRE(ctx && nb >= 0 && p_hi >= p_lo, "rb_fill_ri3ao_symm: bad arguments");
+    i64 total = nb * nb * (p_hi - p_lo);
+    if (total == 0) return RB_OK;
+    RB_CUDA(cudaSetDevice(ctx->device));
+    i64 blocks = rb_cdiv(total, 256);
+    i64 cap = (i64)ctx->num_sms * 16;
+    if (blocks > cap) blocks = cap;
+    rb_fill_ri3ao_symm_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(a, nb, p_lo, p_hi - p_lo, seed, scale);
+    RB_LAUNCHED(ctx);
+    return RB_OK;
+}

@@ -1,0 +1,160 @@
+// rb_ri.cu -- the RI three-centre contractions over one rank's P-shard ri3ao[nb, nb, nx] (device-resident).
+//
+//   ao2mo  (reference src/ri.rs:356-408 -> restmatr.f90:158-194)
+//       ri3mo[P,a,b] = sum_mu C_L[mu,a] sum_nu A[mu,nu,P] C_R[nu,b]
+//     Two DMMA GEMMs per P-chunk, both with K-major (TMA no-swizzle) operands and column-major output:
+//       (1) W[(nu,P), a] = sum_mu A[mu,(nu,P)] C_L[mu,a]         -- ONE 'T','N' GEMM, M = nb*pc, N = nl, K = nb:
+//           ri3ao viewed as the matrix [nb, nb*pc] needs no per-slab loop at all;
+//       (2) for every a:  O[P, b] = sum_nu W[nu, P, a] C_R[nu,b]  -- strided-batched 'T','N' GEMM, M = pc (P!),
+//           N = nr, K = nb, batch = nl, written straight into ri3mo[P + a*ldp + b*ldp*nl]: P is the M index of
+//           the MMA tile, so the P-fastest output of the reference (a stride-naux scatter per element there)
+//           becomes 128-byte contiguous stores.
+//     The reference contracts nu first (dgemm NN then TN); here mu goes first.  Same sums, different rounding
+//     order: agreement is ~1e-14 relative, the bar is 1e-10.
+//
+//   d_P, J, K  (not functions of the reference crate; composed as in SURVEY 3.5)
+//       d_P = dgemv('T') over A = [nb^2, nx];  J = dgemv('N');  both HBM-bound, one pass over ri3ao each.
+//       K   = sum_P (A_P Ct)(A_P Ct)^T : per chunk a strided-batched 'N','N' GEMM Y_P = A_P Ct followed by ONE
+//             SYRK ('U','N') over the stacked Y = [nb, no*pc] (split-K, deterministic reduction), then mirrored.
+#include "rb_common.cuh"
+
+static i64 ws_budget_bytes(rb_ctx *ctx)
+{
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return (i64)1 << 30; }
+    i64 have = (i64)free_b + ctx->ws_bytes[0];
+    i64 budget = have / 3;
+    const i64 cap = (i64)8 << 30;
+    if (budget > cap) budget = cap;
+    if (budget < ((i64)64 << 20)) budget = (i64)64 << 20;
+    return budget;
+}
+
+// P-chunk length: as large as the workspace budget allows, balanced across chunks, multiple of 8.
+static i64 pick_chunk(i64 nx, i64 bytes_per_slab, i64 budget)
+{
+    i64 pc_max = budget / (bytes_per_slab > 0 ? bytes_per_slab : 1);
+    if (pc_max < 8) pc_max = 8;
+    if (pc_max >= nx) return nx;
+    i64 nchunks = rb_cdiv(nx, pc_max);
+    i64 pc = rb_cdiv(nx, nchunks);
+    pc = (pc + 7) & ~(i64)7;
+    return pc < nx ? pc : nx;
+}
+
+extern "C" int rb_ri_ao2mo(rb_ctx *ctx, const double *c_left, int nl, const double *c_right, int nr,
+                           const double *ri3ao, double *out, int nb_, int nx_, int64_t out_ldp)
+{
+    RB_REQUIRE(ctx, "rb_ri_ao2mo: ctx is NULL");
+    RB_REQUIRE(nl >= 0 && nr >= 0 && nb_ >= 0 && nx_ >= 0, "rb_ri_ao2mo: negative dimension");
+    RB_REQUIRE(out_ldp >= nx_, "rb_ri_ao2mo: out_ldp (%lld) < nx (%d)", (long long)out_ldp, nx_);
+    const i64 nb = nb_, nx = nx_;
+    if (nx == 0 || nl == 0 || nr == 0) return RB_OK;
+    RB_REQUIRE(out, "rb_ri_ao2mo: out is NULL");
+    RB_CUDA(cudaSetDevice(ctx->device));
+    if (nb == 0) { // empty contraction: ri3mo = 0 (the Fortran zero-fills first, restmatr.f90:178)
+        for (i64 b = 0; b < nr; ++b)
+            for (i64 a = 0; a < nl; ++a) RB_TRY(rb_scale_or_zero(ctx, out + a * out_ldp + b * out_ldp * nl, nx, 1, 0.0));
+        return RB_OK;
+    }
+    RB_REQUIRE(c_left && c_right && ri3ao, "rb_ri_ao2mo: NULL input");
+    const i64 pc = pick_chunk(nx, nb * nl * 8, ws_budget_bytes(ctx));
+    void *ws;
+    RB_TRY(rb_ws_reserve(ctx, 0, nb * pc * nl * 8, &ws));
+    double *w = (double *)ws;
+    for (i64 p0 = 0; p0 < nx; p0 += pc) {
+        const i64 pn = (nx - p0 < pc) ? nx - p0 : pc;
+        // (1) W[(nu,P), a] : 'T','N'  M = nb*pn, N = nl, K = nb
+        RB_TRY(rb_gemm_core(ctx, true, false, nb * pn, nl, nb, 1.0, ri3ao + p0 * nb * nb, nb, 0, c_left, nb, 0, 0.0, w,
+                            nb * pn, 0, 1, 0));
+        // (2) per a: O_a[P, b] : 'T','N'  M = pn, N = nr, K = nb ; A = W_a [nb x pn], C = out + p0 + a*ldp, ldc = ldp*nl
+        RB_TRY(rb_gemm_core(ctx, true, false, pn, nr, nb, 1.0, w, nb, nb * pn, c_right, nb, 0, 0.0, out + p0,
+                            out_ldp * nl, out_ldp, nl, 0));
+    }
+    return RB_OK;
+}
+
+extern "C" int rb_ri_dp(rb_ctx *ctx, const double *ri3ao, const double *dm, double *d, int nb, int nx)
+{
+    RB_REQUIRE(ctx, "rb_ri_dp: ctx is NULL");
+    RB_REQUIRE(nb >= 0 && nx >= 0, "rb_ri_dp: negative dimension");
+    if (nx == 0) return RB_OK;
+    RB_CUDA(cudaSetDevice(ctx->device));
+    const i64 m = (i64)nb * nb;
+    if (m == 0) return rb_scale_or_zero(ctx, d, nx, 1, 0.0);
+    RB_REQUIRE(m <= 2147483647LL, "rb_ri_dp: nb too large");
+    return rb_dgemv(ctx, 'T', (int)m, nx, 1.0, ri3ao, m, dm, 1, 0.0, d, 1);
+}
+
+extern "C" int rb_ri_j(rb_ctx *ctx, const double *ri3ao, const double *d, double *j, int nb, int nx)
+{
+    RB_REQUIRE(ctx, "rb_ri_j: ctx is NULL");
+    RB_REQUIRE(nb >= 0 && nx >= 0, "rb_ri_j: negative dimension");
+    const i64 m = (i64)nb * nb;
+    if (m == 0) return RB_OK;
+    RB_CUDA(cudaSetDevice(ctx->device));
+    if (nx == 0) return rb_scale_or_zero(ctx, j, m, 1, 0.0);
+    RB_REQUIRE(m <= 2147483647LL, "rb_ri_j: nb too large");
+    return rb_dgemv(ctx, 'N', (int)m, nx, 1.0, ri3ao, m, d, 1, 0.0, j, 1);
+}
+
+extern "C" int rb_ri_k(rb_ctx *ctx, const double *ri3ao, const double *ct, int no_, double *k, int nb_, int nx_)
+{
+    RB_REQUIRE(ctx, "rb_ri_k: ctx is NULL");
+    RB_REQUIRE(no_ >= 0 && nb_ >= 0 && nx_ >= 0, "rb_ri_k: negative dimension");
+    const i64 nb = nb_, nx = nx_, no = no_;
+    if (nb == 0) return RB_OK;
+    RB_REQUIRE(k, "rb_ri_k: k is NULL");
+    RB_CUDA(cudaSetDevice(ctx->device));
+    if (nx == 0 || no == 0) return rb_scale_or_zero(ctx, k, nb * nb, 1, 0.0);
+    RB_REQUIRE(ct && ri3ao, "rb_ri_k: NULL input");
+    const i64 pc = pick_chunk(nx, nb * no * 8, ws_budget_bytes(ctx));
+    RB_REQUIRE(no * pc <= 2147483647LL, "rb_ri_k: chunk too large");
+    void *ws;
+    RB_TRY(rb_ws_reserve(ctx, 0, nb * no * pc * 8, &ws));
+    double *y = (double *)ws;
+    for (i64 p0 = 0; p0 < nx; p0 += pc) {
+        const i64 pn = (nx - p0 < pc) ? nx - p0 : pc;
+        // Y_P = A_P * Ct : 'N','N'  M = nb, N = no, K = nb, batch = pn
+        RB_TRY(rb_gemm_core(ctx, false, false, nb, no, nb, 1.0, ri3ao + p0 * nb * nb, nb, nb * nb, ct, nb, 0, 0.0, y, nb,
+                            nb * no, pn, 0));
+        // K(upper) (+)= Y Y^T : SYRK 'U','N' with k = no*pn
+        RB_TRY(rb_gemm_core(ctx, false, true, nb, nb, no * pn, 1.0, y, nb, 0, y, nb, 0, p0 == 0 ? 0.0 : 1.0, k, nb, 0, 1,
+                            1));
+    }
+    return rb_symmetrize(ctx, k, nb, nb, true);
+}
+
+// restmatr.f90:111-154 on device buffers: for every y, T[xr, y, zr] <- alpha * T[xr, y, zr] * B[:, 0..len_col_b) + beta * T[..]
+// (in place => len_col_b must equal len_z).  b points at the first element of the B block (ldb = rows of B).
+extern "C" int rb_special_dgemm_01(rb_ctx *ctx, double *ten3, int x_a, int y_a, int z_a, int start_x, int len_x,
+                                   int start_z, int len_z, const double *b, int64_t ldb, int len_col_b, double alpha,
+                                   double beta)
+{
+    RB_REQUIRE(ctx, "rb_special_dgemm_01: ctx is NULL");
+    RB_REQUIRE(x_a >= 0 && y_a >= 0 && z_a >= 0 && start_x >= 0 && len_x >= 0 && start_z >= 0 && len_z >= 0,
+               "rb_special_dgemm_01: negative dimension");
+    RB_REQUIRE(start_x + len_x <= x_a && start_z + len_z <= z_a, "rb_special_dgemm_01: block outside tensor");
+    RB_REQUIRE(len_col_b == len_z, "rb_special_dgemm_01: in-place update needs len_column_b == len_z_a (%d vs %d)",
+               len_col_b, len_z);
+    if (len_x == 0 || len_z == 0 || y_a == 0) return RB_OK;
+    RB_CUDA(cudaSetDevice(ctx->device));
+    const i64 X = x_a, Y = y_a;
+    const i64 lx = len_x, lz = len_z;
+    // process y in chunks bounded by the workspace budget
+    i64 yc = ws_budget_bytes(ctx) / (lx * lz * 8);
+    if (yc < 1) yc = 1;
+    if (yc > Y) yc = Y;
+    void *ws;
+    RB_TRY(rb_ws_reserve(ctx, 0, lx * lz * yc * 8, &ws));
+    double *tmp = (double *)ws;
+    for (i64 y0 = 0; y0 < Y; y0 += yc) {
+        const i64 yn = (Y - y0 < yc) ? Y - y0 : yc;
+        double *blk = ten3 + start_x + y0 * X + (i64)start_z * X * Y;
+        // tmp[x, z, y] = T[sx+x, y0+y, sz+z]
+        RB_TRY(rb_copy3d(ctx, blk, 0, 1, X * Y, X, tmp, 0, 1, lx, lx * lz, lx, lz, yn));
+        // T block (ldc = X*Y, batch stride X) = alpha * tmp_y * B + beta * T block
+        RB_TRY(rb_gemm_core(ctx, false, false, lx, lz, lz, alpha, tmp, lx, lx * lz, b, ldb, 0, beta, blk, X * Y, X, yn, 0));
+    }
+    return RB_OK;
+}

@@ -1,0 +1,237 @@
+"""Device-resident API: librest_b200's rb_* entry points on HBM buffers, plus the P-sharded RI tensor.
+
+PyTorch is plumbing only here -- it owns device memory (``torch.empty(..., device='cuda')``), the current CUDA
+stream and the NCCL process group.  Every kernel that runs is one of librest_b200.so's own sm_100a kernels,
+called through the C ABI with raw device pointers.
+
+Sharding: the auxiliary index P is the slowest index of ri3ao[nb, nb, naux], so rank r of G owns the
+contiguous block P in [floor(r*naux/G), floor((r+1)*naux/G)) -- exactly the reference's ``iter_auxbas(range)``
+(src/ri.rs:190-198).  ao2mo and d_P need no communication; J and K are partial sums over the local slabs and
+are completed by ONE all-reduce(sum, f64) each over NVLink (torch.distributed, backend nccl; gloo on CPU tests).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from ._lib import lib, check, ch, RestB200Error  # noqa: F401
+
+
+def shard_range(naux: int, rank: int, world: int) -> Tuple[int, int]:
+    """P_lo = floor(r*naux/G), P_hi = floor((r+1)*naux/G)"""
+    return (rank * naux) // world, ((rank + 1) * naux) // world
+
+
+def _p(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+class Context:
+    """One rb_ctx bound to a CUDA device; calls run on torch's current stream for that device."""
+
+    def __init__(self, device: Optional[int] = None):
+        if not torch.cuda.is_available():
+            raise RestB200Error("rest_tensors_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        h = C.c_void_p()
+        check(lib.rb_ctx_create(self.device, C.byref(h)), "rb_ctx_create")
+        self.h = h
+        self.bind_stream()
+
+    def bind_stream(self) -> None:
+        s = torch.cuda.current_stream(self.device)
+        check(lib.rb_ctx_set_stream(self.h, C.c_void_p(s.cuda_stream)), "rb_ctx_set_stream")
+
+    def close(self) -> None:
+        if getattr(self, "h", None):
+            lib.rb_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- helpers --
+    def empty(self, n: int) -> torch.Tensor:
+        return torch.empty(int(n), dtype=torch.float64, device=f"cuda:{self.device}")
+
+    def sync(self) -> None:
+        check(lib.rb_ctx_sync(self.h), "rb_ctx_sync")
+
+    @property
+    def num_sms(self) -> int:
+        return lib.rb_ctx_num_sms(self.h)
+
+    @property
+    def launches(self) -> int:
+        return int(lib.rb_ctx_launch_count(self.h))
+
+    def set_gemm_path(self, path: int) -> None:
+        check(lib.rb_ctx_set_gemm_path(self.h, path), "rb_ctx_set_gemm_path")
+
+    # -- BLAS --
+    def dgemm(self, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc) -> None:
+        check(lib.rb_dgemm(self.h, ch(ta), ch(tb), m, n, k, alpha, _p(a), lda, _p(b), ldb, beta, _p(c), ldc), "rb_dgemm")
+
+    def dgemm_strided_batched(self, ta, tb, m, n, k, alpha, a, lda, sa, b, ldb, sb, beta, c, ldc, sc, batch) -> None:
+        check(lib.rb_dgemm_strided_batched(self.h, ch(ta), ch(tb), m, n, k, alpha, _p(a), lda, sa, _p(b), ldb, sb, beta,
+                                           _p(c), ldc, sc, batch), "rb_dgemm_strided_batched")
+
+    def dsyrk(self, uplo, trans, n, k, alpha, a, lda, beta, c, ldc) -> None:
+        check(lib.rb_dsyrk(self.h, ch(uplo), ch(trans), n, k, alpha, _p(a), lda, beta, _p(c), ldc), "rb_dsyrk")
+
+    def dgemv(self, trans, m, n, alpha, a, lda, x, incx, beta, y, incy) -> None:
+        check(lib.rb_dgemv(self.h, ch(trans), m, n, alpha, _p(a), lda, _p(x), incx, beta, _p(y), incy), "rb_dgemv")
+
+    def dsymm(self, side, uplo, m, n, alpha, a, lda, b, ldb, beta, c, ldc) -> None:
+        check(lib.rb_dsymm(self.h, ch(side), ch(uplo), m, n, alpha, _p(a), lda, _p(b), ldb, beta, _p(c), ldc), "rb_dsymm")
+
+    # -- RI contractions --
+    def ri_ao2mo(self, c_left, nl, c_right, nr, ri3ao, out, nb, nx, out_ldp=None) -> None:
+        check(lib.rb_ri_ao2mo(self.h, _p(c_left), nl, _p(c_right), nr, _p(ri3ao), _p(out), nb, nx,
+                              nx if out_ldp is None else out_ldp), "rb_ri_ao2mo")
+
+    def ri_dp(self, ri3ao, dm, d, nb, nx) -> None:
+        check(lib.rb_ri_dp(self.h, _p(ri3ao), _p(dm), _p(d), nb, nx), "rb_ri_dp")
+
+    def ri_j(self, ri3ao, d, j, nb, nx) -> None:
+        check(lib.rb_ri_j(self.h, _p(ri3ao), _p(d), _p(j), nb, nx), "rb_ri_j")
+
+    def ri_k(self, ri3ao, ct, no, k, nb, nx) -> None:
+        check(lib.rb_ri_k(self.h, _p(ri3ao), _p(ct), no, _p(k), nb, nx), "rb_ri_k")
+
+    def special_dgemm_01(self, ten3, x_a, y_a, z_a, sx, lx, sz, lz, b, ldb, lcb, alpha, beta) -> None:
+        check(lib.rb_special_dgemm_01(self.h, _p(ten3), x_a, y_a, z_a, sx, lx, sz, lz, _p(b), ldb, lcb, alpha, beta),
+              "rb_special_dgemm_01")
+
+    # -- layout --
+    def pack_upper(self, full, n, packed) -> None:
+        check(lib.rb_pack_upper(self.h, _p(full), n, _p(packed)), "rb_pack_upper")
+
+    def unpack_upper(self, packed, n, full) -> None:
+        check(lib.rb_unpack_upper(self.h, _p(packed), n, _p(full)), "rb_unpack_upper")
+
+    def ri_pack_symm(self, ri, nao, naux, out) -> None:
+        check(lib.rb_ri_pack_symm(self.h, _p(ri), nao, naux, _p(out)), "rb_ri_pack_symm")
+
+    def copy_mm(self, xl, yl, f, fx, fy, fxs, fys, t, tx, ty, txs, tys) -> None:
+        check(lib.rb_copy_mm(self.h, xl, yl, _p(f), fx, fy, fxs, fys, _p(t), tx, ty, txs, tys), "rb_copy_mm")
+
+    def copy_mr(self, xl, yl, f, fx, fy, fxs, fys, t, tx, ty, tz, txs, tys, t3, mod) -> None:
+        check(lib.rb_copy_mr(self.h, xl, yl, _p(f), fx, fy, fxs, fys, _p(t), tx, ty, tz, txs, tys, t3, mod), "rb_copy_mr")
+
+    def copy_rm(self, xl, yl, f, fx, fy, fz, fxs, fys, f3, mod, t, tx, ty, txs, tys) -> None:
+        check(lib.rb_copy_rm(self.h, xl, yl, _p(f), fx, fy, fz, fxs, fys, f3, mod, _p(t), tx, ty, txs, tys), "rb_copy_rm")
+
+    def copy_rr(self, xl, yl, zl, f, fx, fy, fz, fxs, fys, fzs, t, tx, ty, tz, txs, tys, tzs) -> None:
+        check(lib.rb_copy_rr(self.h, xl, yl, zl, _p(f), fx, fy, fz, fxs, fys, fzs, _p(t), tx, ty, tz, txs, tys, tzs),
+              "rb_copy_rr")
+
+    def ri_transpose(self, inp, i, j, k, which, out) -> None:
+        check(lib.rb_ri_transpose(self.h, _p(inp), i, j, k, which, _p(out)), "rb_ri_transpose")
+
+    def matrix_transpose(self, inp, rows, cols, out) -> None:
+        check(lib.rb_matrix_transpose(self.h, _p(inp), rows, cols, _p(out)), "rb_matrix_transpose")
+
+    def self_scaled_add(self, c, p, b, n) -> None:
+        check(lib.rb_self_scaled_add(self.h, _p(c), _p(p), b, n), "rb_self_scaled_add")
+
+    def self_general_add(self, c, p, a, b, n) -> None:
+        check(lib.rb_self_general_add(self.h, _p(c), _p(p), a, b, n), "rb_self_general_add")
+
+    def self_multiple(self, c, a, n) -> None:
+        check(lib.rb_self_multiple(self.h, _p(c), a, n), "rb_self_multiple")
+
+    def self_add(self, c, p, n) -> None:
+        check(lib.rb_self_add(self.h, _p(c), _p(p), n), "rb_self_add")
+
+    def self_sub(self, c, p, n) -> None:
+        check(lib.rb_self_sub(self.h, _p(c), _p(p), n), "rb_self_sub")
+
+    # -- synthetic inputs / probes --
+    def fill_linear(self, v, n, seed, idx0, scale) -> None:
+        check(lib.rb_fill_linear(self.h, _p(v), n, seed, idx0, scale), "rb_fill_linear")
+
+    def fill_ri3ao_symm(self, a, nb, p_lo, p_hi, seed, scale) -> None:
+        check(lib.rb_fill_ri3ao_symm(self.h, _p(a), nb, p_lo, p_hi, seed, scale), "rb_fill_ri3ao_symm")
+
+    def fp64_peak_probe(self, kind: int, iters: int = 4096):
+        tf, ms = C.c_double(), C.c_double()
+        check(lib.rb_fp64_peak_probe(self.h, kind, iters, C.byref(tf), C.byref(ms)), "rb_fp64_peak_probe")
+        return tf.value, ms.value
+
+    def hbm_copy_probe(self, nbytes: int, iters: int = 10) -> float:
+        g = C.c_double()
+        check(lib.rb_hbm_copy_probe(self.h, nbytes, iters, C.byref(g)), "rb_hbm_copy_probe")
+        return g.value
+
+
+class ShardedRI:
+    """One rank's P-shard of ri3ao[nb, nb, naux], resident in HBM across calls (the SCF loop re-uses it)."""
+
+    def __init__(self, ctx: Context, nb: int, naux: int, rank: int = 0, world: int = 1,
+                 data: Optional[torch.Tensor] = None):
+        self.ctx, self.nb, self.naux, self.rank, self.world = ctx, int(nb), int(naux), int(rank), int(world)
+        self.p_lo, self.p_hi = shard_range(self.naux, self.rank, self.world)
+        self.nx = self.p_hi - self.p_lo
+        n = self.nb * self.nb * self.nx
+        if data is None:
+            data = ctx.empty(n)
+        elif data.numel() < n:
+            raise ValueError("ShardedRI: buffer smaller than the local shard")
+        self.data = data
+
+    def fill_synthetic(self, seed: int = 1, scale: float = 1.0) -> "ShardedRI":
+        self.ctx.fill_ri3ao_symm(self.data, self.nb, self.p_lo, self.p_hi, seed, scale)
+        return self
+
+    def ao2mo(self, c_left: torch.Tensor, nl: int, c_right: torch.Tensor, nr: int,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """local rows ri3mo[P_lo..P_hi, :, :] as a dense [nx_local, nl, nr] column-major buffer (no communication)"""
+        if out is None:
+            out = self.ctx.empty(self.nx * nl * nr)
+        self.ctx.ri_ao2mo(c_left, nl, c_right, nr, self.data, out, self.nb, self.nx)
+        return out
+
+    def dp(self, dm: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """d[P_lo..P_hi] from the replicated density (no communication needed before J)"""
+        if out is None:
+            out = self.ctx.empty(self.nx)
+        self.ctx.ri_dp(self.data, dm, out, self.nb, self.nx)
+        return out
+
+    def j(self, d_local: torch.Tensor, out: Optional[torch.Tensor] = None, reduce: bool = True) -> torch.Tensor:
+        if out is None:
+            out = self.ctx.empty(self.nb * self.nb)
+        self.ctx.ri_j(self.data, d_local, out, self.nb, self.nx)
+        if reduce:
+            all_reduce_sum(out, self.world)
+        return out
+
+    def k(self, ct: torch.Tensor, no: int, out: Optional[torch.Tensor] = None, reduce: bool = True) -> torch.Tensor:
+        if out is None:
+            out = self.ctx.empty(self.nb * self.nb)
+        self.ctx.ri_k(self.data, ct, no, out, self.nb, self.nx)
+        if reduce:
+            all_reduce_sum(out, self.world)
+        return out
+
+
+def all_reduce_sum(t: torch.Tensor, world: int) -> None:
+    """The only collective on the path: sum of the per-rank J / K partials (NCCL over NVLink on GPUs)."""
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+
+def gather_dp(d_local: torch.Tensor, naux: int, p_lo: int, world: int) -> torch.Tensor:
+    """Full d[0..naux) on every rank (38 KB at naux=4800): each rank drops its piece into a zero vector and the
+    pieces are summed -- shards may differ in length by one, which all_gather does not accept on every backend."""
+    full = torch.zeros(int(naux), dtype=d_local.dtype, device=d_local.device)
+    full[p_lo:p_lo + d_local.numel()] = d_local
+    all_reduce_sum(full, world)
+    return full

@@ -1,0 +1,636 @@
+"""Host-side mirror of the reference's tensor API for the RI hot path.
+
+Same type names, field names (``size`` / ``indicing`` / ``data``), method names, argument meaning and error
+behaviour as the reference's Rust structs, so that the parity tests read like the reference's own tests:
+
+    RIFull        src/ri.rs:18-433
+    MatrixFull    src/matrix/mod.rs:472-480, src/matrix/matrixfull.rs
+    MatrixUpper   src/matrix/matrixupper.rs:231-420, src/index.rs:209-233
+    _dgemm, _dgemm_full, _dgemm_full_new, _dsyrk, _dsymm, _dgemv      src/matrix/matrix_blas_lapack.rs
+    ri_ao2mo_f, general_dgemm_f, special_dgemm_f_01, matr_copy, ...   src/external_libs/mod.rs
+
+``data`` is a flat column-major ``numpy.float64`` array (the Rust ``Vec<f64>``).  A Rust ``panic!`` is a Python
+exception here (``ValueError`` for the shape panics, ``RestB200Error`` for library failures); ``Option::None``
+is ``None``.  Every numerical operation and every bulk data movement is a call into librest_b200.so; NumPy only
+owns the buffers (views, slicing, allocation) exactly as ``Vec``/slices do on the Rust side.  There is no
+NumPy/CPU implementation of any operation behind these methods.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterator, Optional, Sequence, Tuple
+
+import numpy as np
+
+from ._lib import lib, check, ch, RestB200Error  # noqa: F401
+
+Range = Tuple[int, int]  # half-open (start, end), the Rust `start..end`
+
+
+def _ptr(a: np.ndarray) -> C.c_void_p:
+    return C.c_void_p(a.ctypes.data)
+
+
+def _f64(v, n: Optional[int] = None) -> np.ndarray:
+    a = np.ascontiguousarray(np.asarray(v, dtype=np.float64).reshape(-1))
+    return a
+
+
+def _ci(v: int) -> C.c_int:
+    return C.c_int(int(v))
+
+
+def _rlen(r: Range) -> int:
+    return max(0, int(r[1]) - int(r[0]))
+
+
+def _indicing(size: Sequence[int]):
+    ind, ln = [], 1
+    for s in size:
+        ind.append(ln)
+        ln *= int(s)
+    return ind, ln
+
+
+# ======================================================================================================
+# external_libs (src/external_libs/mod.rs) -- safe wrappers over the Fortran-ABI symbols
+# ======================================================================================================
+def ri_ao2mo_f(eigenvector: np.ndarray, ri3fn: np.ndarray, ri3mo: np.ndarray, num_states: int, num_basis: int,
+               num_auxbas: int) -> None:
+    """src/external_libs/mod.rs:6-22 -> ffi ri_ao2mo_f_"""
+    lib.ri_ao2mo_f_(_ptr(eigenvector), _ptr(ri3fn), _ptr(ri3mo), C.byref(_ci(num_states)), C.byref(_ci(num_basis)),
+                    C.byref(_ci(num_auxbas)))
+
+
+def general_dgemm_f(matr_a, size_a, range_row_a: Range, range_column_a: Range, opa: str,
+                    matr_b, size_b, range_row_b: Range, range_column_b: Range, opb: str,
+                    matr_c, size_c, range_row_c: Range, range_column_c: Range, alpha: float, beta: float) -> None:
+    """src/external_libs/mod.rs:60-83 -> ffi general_dgemm_f_"""
+    a = [_ci(size_a[0]), _ci(size_a[1]), _ci(range_row_a[0]), _ci(_rlen(range_row_a)), _ci(range_column_a[0]),
+         _ci(_rlen(range_column_a))]
+    b = [_ci(size_b[0]), _ci(size_b[1]), _ci(range_row_b[0]), _ci(_rlen(range_row_b)), _ci(range_column_b[0]),
+         _ci(_rlen(range_column_b))]
+    c = [_ci(size_c[0]), _ci(size_c[1]), _ci(range_row_c[0]), _ci(_rlen(range_row_c)), _ci(range_column_c[0]),
+         _ci(_rlen(range_column_c))]
+    al, be = C.c_double(alpha), C.c_double(beta)
+    lib.general_dgemm_f_(_ptr(matr_a), *[C.byref(v) for v in a], ch(opa), _ptr(matr_b), *[C.byref(v) for v in b], ch(opb),
+                         _ptr(matr_c), *[C.byref(v) for v in c], C.byref(al), C.byref(be))
+
+
+def special_dgemm_f_01(ten3_a, size_a, range_x_a: Range, i_y: int, range_z_a: Range, matr_b, size_b,
+                       range_row_b: Range, range_column_b: Range, alpha: float, beta: float) -> None:
+    """src/external_libs/mod.rs:85-99 -> ffi special_dgemm_f_01_"""
+    v = [_ci(size_a[0]), _ci(size_a[1]), _ci(size_a[2]), _ci(range_x_a[0]), _ci(_rlen(range_x_a)), _ci(i_y),
+         _ci(range_z_a[0]), _ci(_rlen(range_z_a))]
+    w = [_ci(size_b[0]), _ci(size_b[1]), _ci(range_row_b[0]), _ci(_rlen(range_row_b)), _ci(range_column_b[0]),
+         _ci(_rlen(range_column_b))]
+    al, be = C.c_double(alpha), C.c_double(beta)
+    lib.special_dgemm_f_01_(_ptr(ten3_a), *[C.byref(x) for x in v], _ptr(matr_b), *[C.byref(x) for x in w],
+                            C.byref(al), C.byref(be))
+
+
+def matr_copy(matr_a, size_a, range_row_a: Range, range_column_a: Range, matr_b, size_b, range_row_b: Range,
+              range_column_b: Range) -> None:
+    """src/external_libs/mod.rs:102-120: from matr_a[(ra, ca)] to matr_b[(rb, cb)]"""
+    x_len, y_len = _rlen(range_row_a), _rlen(range_column_a)
+    if not (x_len == _rlen(range_row_b) and y_len == _rlen(range_column_b)):
+        raise ValueError("Error: the data block for copy has different size between two matrices")
+    v = [_ci(x_len), _ci(y_len)]
+    f = [_ci(size_a[0]), _ci(size_a[1]), _ci(range_row_a[0]), _ci(range_column_a[0])]
+    t = [_ci(size_b[0]), _ci(size_b[1]), _ci(range_row_b[0]), _ci(range_column_b[0])]
+    lib.copy_mm_(*[C.byref(x) for x in v], _ptr(matr_a), *[C.byref(x) for x in f], _ptr(matr_b),
+                 *[C.byref(x) for x in t])
+
+
+def matr_copy_from_ri(ri_a, size_a, range_x_a: Range, range_y_a: Range, i_z_a: int, copy_mod: int, matr_b, size_b,
+                      range_row_b: Range, range_column_b: Range) -> None:
+    """src/external_libs/mod.rs:123-140 -> copy_rm_"""
+    x_len, y_len = _rlen(range_x_a), _rlen(range_y_a)
+    if not (x_len == _rlen(range_row_b) and y_len == _rlen(range_column_b)):
+        raise ValueError("Error: the data block for copy has different size between matrix and ri-tensor")
+    v = [_ci(x_len), _ci(y_len)]
+    f = [_ci(size_a[0]), _ci(size_a[1]), _ci(size_a[2]), _ci(range_x_a[0]), _ci(range_y_a[0]), _ci(i_z_a), _ci(copy_mod)]
+    t = [_ci(size_b[0]), _ci(size_b[1]), _ci(range_row_b[0]), _ci(range_column_b[0])]
+    lib.copy_rm_(*[C.byref(x) for x in v], _ptr(ri_a), *[C.byref(x) for x in f], _ptr(matr_b),
+                 *[C.byref(x) for x in t])
+
+
+def ri_copy_from_matr(matr_a, size_a, range_row_a: Range, range_column_a: Range, ri_b, size_b, range_row_b: Range,
+                      range_column_b: Range, i_high_b: int, copy_mod: int) -> None:
+    """src/external_libs/mod.rs:145-165 -> copy_mr_"""
+    x_len, y_len = _rlen(range_row_a), _rlen(range_column_a)
+    if not (x_len == _rlen(range_row_b) and y_len == _rlen(range_column_b)):
+        raise ValueError("Error: the data block for copy has different size between the matrix and ri 3D-tensor")
+    v = [_ci(x_len), _ci(y_len)]
+    f = [_ci(size_a[0]), _ci(size_a[1]), _ci(range_row_a[0]), _ci(range_column_a[0])]
+    t = [_ci(size_b[0]), _ci(size_b[1]), _ci(size_b[2]), _ci(range_row_b[0]), _ci(range_column_b[0]), _ci(i_high_b),
+         _ci(copy_mod)]
+    lib.copy_mr_(*[C.byref(x) for x in v], _ptr(matr_a), *[C.byref(x) for x in f], _ptr(ri_b),
+                 *[C.byref(x) for x in t])
+
+
+def ri_copy_from_ri(ri_a, size_a, range_x_a: Range, range_y_a: Range, range_z_a: Range, ri_b, size_b,
+                    range_x_b: Range, range_y_b: Range, range_z_b: Range) -> None:
+    """src/external_libs/mod.rs:168-190 -> copy_rr_"""
+    x_len, y_len, z_len = _rlen(range_x_a), _rlen(range_y_a), _rlen(range_z_a)
+    if not (x_len == _rlen(range_x_b) and y_len == _rlen(range_y_b) and z_len == _rlen(range_z_b)):
+        raise ValueError("Error: the data block for copy has different size between ri 3D-tensors")
+    v = [_ci(x_len), _ci(y_len), _ci(z_len)]
+    f = [_ci(size_a[0]), _ci(size_a[1]), _ci(size_a[2]), _ci(range_x_a[0]), _ci(range_y_a[0]), _ci(range_z_a[0])]
+    t = [_ci(size_b[0]), _ci(size_b[1]), _ci(size_b[2]), _ci(range_x_b[0]), _ci(range_y_b[0]), _ci(range_z_b[0])]
+    lib.copy_rr_(*[C.byref(x) for x in v], _ptr(ri_a), *[C.byref(x) for x in f], _ptr(ri_b),
+                 *[C.byref(x) for x in t])
+
+
+# ======================================================================================================
+# MatrixFull
+# ======================================================================================================
+class MatrixFull:
+    """src/matrix/mod.rs:472-480: ``size: [usize;2]``, ``indicing: [usize;2]``, ``data: Vec<T>`` (column-major)."""
+
+    def __init__(self, size, indicing, data: np.ndarray):
+        self.size = [int(size[0]), int(size[1])]
+        self.indicing = list(indicing)
+        self.data = data
+
+    # -- constructors (matrixfull.rs:190-240) --
+    @staticmethod
+    def new(size, new_default: float) -> "MatrixFull":
+        ind, ln = _indicing(size)
+        return MatrixFull(size, ind, np.full(ln, float(new_default), dtype=np.float64))
+
+    @staticmethod
+    def empty() -> "MatrixFull":
+        return MatrixFull([0, 0], [0, 0], np.zeros(0, dtype=np.float64))
+
+    @staticmethod
+    def from_vec(size, new_vec) -> "MatrixFull":
+        ind, ln = _indicing(size)
+        data = _f64(new_vec)
+        if ln > data.size:
+            raise ValueError("Error: inconsistency happens when formating a matrix from a given vector, "
+                             f"(length from size, length of new vector) = ({ln},{data.size})")
+        return MatrixFull(size, ind, data)
+
+    # -- BasicMatrix (matrix/mod.rs:490-505) --
+    def data_ref(self) -> np.ndarray:
+        return self.data
+
+    def data_ref_mut(self) -> np.ndarray:
+        return self.data
+
+    def is_contiguous(self) -> bool:
+        return True
+
+    def check_shape(self, other: "MatrixFull") -> bool:
+        return self.size[0] == other.size[0] and self.size[1] == other.size[1]
+
+    def get2d(self, pos) -> float:
+        return float(self.data[pos[0] * self.indicing[0] + pos[1] * self.indicing[1]])
+
+    def reshape(self, size) -> None:
+        """matrixfull.rs:242-253 (metadata only)"""
+        ind, ln = _indicing(size)
+        if ln != self.size[0] * self.size[1]:
+            raise ValueError("Cannot reshape: element counts differ")
+        self.size, self.indicing = [int(size[0]), int(size[1])], ind
+
+    # -- layout ops --
+    def transpose(self) -> "MatrixFull":
+        """matrixfull.rs:579-596"""
+        r, c = self.size
+        out = MatrixFull.new([c, r], 0.0)
+        if r * c:
+            check(lib.rb_host_matrix_transpose(_ptr(self.data), r, c, _ptr(out.data)), "MatrixFull::transpose")
+        return out
+
+    transpose_and_drop = transpose
+
+    def to_matrixupper(self) -> "MatrixUpper":
+        """matrixfull.rs:638-646: panics unless square; packed[j(j+1)/2+i] = a[i+j*n], i<=j"""
+        if self.size[0] != self.size[1]:
+            raise ValueError("Error: Nonsymmetric matrix cannot be converted to the upper format")
+        n = self.size[0]
+        out = np.zeros(n * (n + 1) // 2, dtype=np.float64)
+        check(lib.rb_host_to_matrixupper(_ptr(self.data), n, _ptr(out)), "MatrixFull::to_matrixupper")
+        return MatrixUpper(out.size, out)
+
+    def to_rifull(self, i: int, j: int, k: int) -> "RIFull":
+        """matrixfull.rs:674-686 (note the reference's indicing quirk [1, i, j])"""
+        if i * j * k != self.size[0] * self.size[1]:
+            raise ValueError("Error in tranforming MatrixFull to RIFull: incompitable size")
+        return RIFull([i, j, k], [1, i, j], self.data.copy())
+
+    def copy_from_matr(self, range_x: Range, range_y: Range, from_matr: "MatrixFull", f_range_x: Range,
+                       f_range_y: Range) -> None:
+        """matrixfull.rs:1388-1396 -> matr_copy -> copy_mm_"""
+        matr_copy(from_matr.data, from_matr.size, f_range_x, f_range_y, self.data, self.size, range_x, range_y)
+
+    def lapack_dgemm(self, a: "MatrixFull", b: "MatrixFull", opa: str, opb: str, alpha: float, beta: float) -> None:
+        """matrix_blas_lapack.rs:739-774 (no shape check, like the reference)"""
+        m = a.size[0] if opa == 'N' else a.size[1]
+        k = a.size[1] if opa == 'N' else a.size[0]
+        n = b.size[1] if opb == 'N' else b.size[0]
+        lda = max(m, 1) if opa == 'N' else max(k, 1)
+        ldb = max(k, 1) if opb == 'N' else max(n, 1)
+        check(lib.rb_host_dgemm(ch(opa), ch(opb), m, n, k, alpha, _ptr(a.data), lda, _ptr(b.data), ldb, beta,
+                                _ptr(self.data), max(m, 1)), "lapack_dgemm")
+
+    def ddot(self, b: "MatrixFull") -> Optional["MatrixFull"]:
+        """matrix_blas_lapack.rs:714-730: a*b with beta=1 on a zeroed C"""
+        if self.size[1] != b.size[0]:
+            return None
+        m, n, k = self.size[0], b.size[1], self.size[1]
+        c = MatrixFull.new([m, n], 0.0)
+        check(lib.rb_host_dgemm(b'N', b'N', m, n, k, 1.0, _ptr(self.data), max(m, 1), _ptr(b.data), max(k, 1), 1.0,
+                                _ptr(c.data), max(m, 1)), "ddot")
+        return c
+
+    # -- MathMatrix (matrix/mod.rs:545-648) --
+    def _axpy(self, op: int, other: Optional["MatrixFull"], a: float, b: float) -> None:
+        p = _ptr(other.data) if other is not None else None
+        check(lib.rb_host_axpy(op, _ptr(self.data), p, a, b, self.size[0] * self.size[1]), "axpy")
+
+    def add(self, other: "MatrixFull") -> Optional["MatrixFull"]:
+        if not self.check_shape(other):
+            return None
+        out = MatrixFull(self.size, self.indicing, self.data.copy())
+        out._axpy(3, other, 0.0, 0.0)
+        return out
+
+    def scaled_add(self, other: "MatrixFull", scale_factor: float) -> Optional["MatrixFull"]:
+        if not self.check_shape(other):
+            return None
+        out = MatrixFull(self.size, self.indicing, self.data.copy())
+        out._axpy(0, other, 0.0, scale_factor)
+        return out
+
+    def sub(self, other: "MatrixFull") -> Optional["MatrixFull"]:
+        if not self.check_shape(other):
+            return None
+        out = MatrixFull(self.size, self.indicing, self.data.copy())
+        out._axpy(4, other, 0.0, 0.0)
+        return out
+
+    def _need_shape(self, bm: "MatrixFull", what: str) -> None:
+        if not self.check_shape(bm):
+            raise ValueError(f"Error: Shape inconsistency happens when {what} two matrices")
+
+    def self_add(self, bm: "MatrixFull") -> None:
+        self._need_shape(bm, "plus")
+        self._axpy(3, bm, 0.0, 0.0)
+
+    def self_sub(self, bm: "MatrixFull") -> None:
+        self._need_shape(bm, "subtract")
+        self._axpy(4, bm, 0.0, 0.0)
+
+    def self_scaled_add(self, bm: "MatrixFull", b: float) -> None:
+        self._need_shape(bm, "plus")
+        self._axpy(0, bm, 0.0, b)
+
+    def self_general_add(self, bm: "MatrixFull", a: float, b: float) -> None:
+        self._need_shape(bm, "plus")
+        self._axpy(1, bm, a, b)
+
+    def self_multiple(self, a: float) -> None:
+        self._axpy(2, None, a, 0.0)
+
+
+# ======================================================================================================
+# MatrixUpper
+# ======================================================================================================
+class MatrixUpper:
+    """src/matrix/matrixupper.rs:231-234: ``size`` = n(n+1)/2 (the packed length), ``data``."""
+
+    def __init__(self, size: int, data: np.ndarray):
+        self.size = int(size)
+        self.data = data
+
+    @staticmethod
+    def new(size: int, new_default: float) -> "MatrixUpper":
+        return MatrixUpper(size, np.full(int(size), float(new_default), dtype=np.float64))
+
+    @staticmethod
+    def empty() -> "MatrixUpper":
+        return MatrixUpper(0, np.zeros(0, dtype=np.float64))
+
+    @staticmethod
+    def from_vec(size: int, new_vec) -> "MatrixUpper":
+        data = _f64(new_vec)
+        if size > data.size:
+            raise ValueError("Error: inconsistency happens when formating a matrix from a given vector, "
+                             f"(length from size, length of new vector) = ({size},{data.size})")
+        return MatrixUpper(size, data)
+
+    def len(self) -> int:
+        return int(self.data.size)
+
+    def size2d(self):
+        """matrixupper.rs:289-292 (`size()` in the reference): [n, n] from the packed length"""
+        n = int((1.0 + 8.0 * float(self.size)) ** 0.5 * 0.5 - 0.5)
+        return [n, n]
+
+    def index2d(self, position) -> Optional[int]:
+        """index.rs:209-226: swaps so that i<=j; None when out of range"""
+        i, j = (position[0], position[1]) if position[0] <= position[1] else (position[1], position[0])
+        tp = (j + 1) * j // 2 + i
+        return tp if tp < self.data.size else None
+
+    def index2d_uncheck(self, position) -> Optional[int]:
+        """index.rs:227-233: no swap"""
+        tp = (position[1] + 1) * position[1] // 2 + position[0]
+        return tp if tp < self.data.size else None
+
+    def get2d(self, position) -> Optional[float]:
+        idx = self.index2d(position)
+        return None if idx is None else float(self.data[idx])
+
+    def to_matrixfull(self) -> Optional[MatrixFull]:
+        """matrixupper.rs:330-373: None unless size is triangular; empty() for length 0; unpack + mirror"""
+        if self.len() == 0:
+            return MatrixFull.empty()
+        n = int((1.0 + 8.0 * float(self.size)) ** 0.5 * 0.5 - 0.5)
+        if n * (n + 1) // 2 != self.size:
+            return None
+        out = MatrixFull.new([n, n], 0.0)
+        check(lib.rb_host_to_matrixfull(_ptr(self.data), self.size, _ptr(out.data)), "MatrixUpper::to_matrixfull")
+        return out
+
+    def _zip(self, other: "MatrixUpper", op: int) -> "MatrixUpper":
+        """matrixupper.rs:395-420: zip silently truncates to the shorter operand"""
+        out = MatrixUpper(self.size, self.data.copy())
+        n = min(out.data.size, other.data.size)
+        if n:
+            check(lib.rb_host_axpy(op, _ptr(out.data), _ptr(other.data), 0.0, 0.0, n), "MatrixUpper add/sub")
+        return out
+
+    def __add__(self, other: "MatrixUpper") -> "MatrixUpper":
+        return self._zip(other, 3)
+
+    def __sub__(self, other: "MatrixUpper") -> "MatrixUpper":
+        return self._zip(other, 4)
+
+
+# ======================================================================================================
+# RIFull
+# ======================================================================================================
+class RIFull:
+    """src/ri.rs:18-24: rank-3 column-major tensor, linear index x + y*s0 + z*s0*s1."""
+
+    def __init__(self, size, indicing, data: np.ndarray):
+        self.size = [int(s) for s in size]
+        self.indicing = list(indicing)
+        self.data = data
+
+    @staticmethod
+    def new(size, new_default: float) -> "RIFull":
+        ind, ln = _indicing(size)
+        return RIFull(size, ind, np.full(ln, float(new_default), dtype=np.float64))
+
+    @staticmethod
+    def empty() -> "RIFull":
+        return RIFull([0, 0, 0], [0, 0, 0], np.zeros(0, dtype=np.float64))
+
+    @staticmethod
+    def from_vec(size, new_vec) -> "RIFull":
+        """ri.rs:57-70: panics when the vector is too short, keeps (and warns about) a surplus"""
+        ind, ln = _indicing(size)
+        data = _f64(new_vec)
+        if ln > data.size:
+            raise ValueError("Error: inconsistency happens when formating a tensor from a given vector, "
+                             f"(length from size, length of new vector) = ({ln},{data.size})")
+        return RIFull(size, ind, data)
+
+    def check_shape(self, other: "RIFull") -> bool:
+        return all(a == b for a, b in zip(self.size, other.size))
+
+    # -- zero-copy slab access (ri.rs:71-218): pointer arithmetic only, as in the reference --
+    def get_reducing_matrix(self, i_reduced: int) -> MatrixFull:
+        p_length = self.indicing[2]
+        p_start = p_length * i_reduced
+        return MatrixFull(self.size[0:2], self.indicing[0:2], self.data[p_start:p_start + p_length])
+
+    get_reducing_matrix_mut = get_reducing_matrix
+
+    def get_reducing_matrix_columns(self, range_columns: Range, i_reduced: int) -> MatrixFull:
+        """ri.rs:102-115 (keeps the reference's indicing quirk [1, |cols|])"""
+        z_length, y_length = self.indicing[2], self.indicing[1]
+        start = z_length * i_reduced + y_length * range_columns[0]
+        end = start + y_length * _rlen(range_columns)
+        size = [self.size[0], _rlen(range_columns)]
+        return MatrixFull(size, [1, size[1]], self.data[start:end])
+
+    def iter_auxbas(self, auxbas_range: Range) -> Iterator[np.ndarray]:
+        """ri.rs:190-198: the P-shard primitive -- contiguous chunks of s0*s1"""
+        chunk = self.size[0] * self.size[1]
+        for p in range(auxbas_range[0], auxbas_range[1]):
+            yield self.data[chunk * p: chunk * (p + 1)]
+
+    iter_mut_auxbas = iter_auxbas
+    par_iter_auxbas = iter_auxbas
+    par_iter_mut_auxbas = iter_auxbas
+
+    def iter_slices_x(self, y: int, z: int) -> np.ndarray:
+        start = z * self.indicing[2] + y * self.indicing[1]
+        return self.data[start:start + self.indicing[1]]
+
+    def get_slices(self, x: Range, y: Range, z: Range) -> np.ndarray:
+        """ri.rs:117-128: x-runs flattened in (z outer, y inner) order (views into ``data`` concatenated)"""
+        s0, s1, s2 = self.size
+        cube = self.data[: s0 * s1 * s2].reshape((s0, s1, s2), order="F")
+        return cube[x[0]:x[1], y[0]:y[1], z[0]:z[1]].reshape(-1, order="F")
+
+    # -- transposes (ri.rs:227-294) --
+    def _transpose(self, which: int, new_size) -> "RIFull":
+        i, j, k = self.size
+        out = RIFull.new(new_size, 0.0)
+        if i * j * k:
+            check(lib.rb_host_ri_transpose(_ptr(self.data), i, j, k, which, _ptr(out.data)), "RIFull::transpose")
+        return out
+
+    def transpose_jik(self) -> "RIFull":
+        return self._transpose(0, [self.size[1], self.size[0], self.size[2]])
+
+    def transpose_jki(self) -> "RIFull":
+        return self._transpose(1, [self.size[1], self.size[2], self.size[0]])
+
+    def transpose_kji(self) -> "RIFull":
+        return self._transpose(2, [self.size[2], self.size[1], self.size[0]])
+
+    def transpose_ikj(self) -> "RIFull":
+        return self._transpose(3, [self.size[0], self.size[2], self.size[1]])
+
+    # -- reshapes (ri.rs:297-326) --
+    def rifull_to_matfull_symm(self) -> MatrixFull:
+        nao, naux = self.size[0], self.size[2]
+        out = MatrixFull.new([nao * (nao + 1) // 2, naux], 0.0)
+        if nao * naux:
+            check(lib.rb_host_ri_pack_symm(_ptr(self.data), nao, naux, _ptr(out.data)), "rifull_to_matfull_symm")
+        return out
+
+    def rifull_to_matfull_ij_k(self) -> MatrixFull:
+        i, j, k = self.size
+        return MatrixFull.from_vec([i * j, k], self.data.copy())
+
+    def rifull_to_matfull_i_jk(self) -> MatrixFull:
+        i, j, k = self.size
+        return MatrixFull.from_vec([i, j * k], self.data.copy())
+
+    # -- arithmetic --
+    def self_scaled_add(self, bm: "RIFull", b: float) -> None:
+        """ri.rs:345-354: A += b*B"""
+        if not self.check_shape(bm):
+            raise ValueError("Error: Shape inconsistency happens when plus two matrices")
+        n = self.size[0] * self.size[1] * self.size[2]
+        check(lib.rb_host_axpy(0, _ptr(self.data), _ptr(bm.data), 0.0, b, n), "RIFull::self_scaled_add")
+
+    # -- the hot path (ri.rs:356-408) --
+    def ao2mo(self, eigenvector: MatrixFull) -> "RIFull":
+        return self.ao2mo_v02(eigenvector)
+
+    def ao2mo_v02(self, eigenvector: MatrixFull) -> "RIFull":
+        """AO(num_basis, num_basis, num_auxbas) -> MO(num_auxbas, num_states, num_states), ri.rs:382-408"""
+        num_basis, num_states = eigenvector.size[0], eigenvector.size[1]
+        num_auxbas = self.size[2]
+        ri3mo = RIFull.new([num_auxbas, num_states, num_states], 0.0)
+        ri_ao2mo_f(eigenvector.data, self.data, ri3mo.data, num_states, num_basis, num_auxbas)
+        return ri3mo
+
+    def ao2mo_v01(self, eigenvector: MatrixFull) -> "RIFull":
+        """ri.rs:360-379 computes the same tensor with hand-rolled loops; here it is the same CUDA path."""
+        return self.ao2mo_v02(eigenvector)
+
+    def ao2mo_rect(self, c_left: MatrixFull, c_right: MatrixFull) -> "RIFull":
+        """North-star occ-vir form: out[P,a,b] = sum C_L[mu,a] A[mu,nu,P] C_R[nu,b] (not in the reference)."""
+        nb, nl, nr, nx = c_left.size[0], c_left.size[1], c_right.size[1], self.size[2]
+        if c_right.size[0] != nb or self.size[0] != nb or self.size[1] != nb:
+            raise ValueError("ao2mo_rect: inconsistent shapes")
+        out = RIFull.new([nx, nl, nr], 0.0)
+        check(lib.rb_host_ri_ao2mo(_ptr(c_left.data), nl, _ptr(c_right.data), nr, _ptr(self.data), _ptr(out.data), nb,
+                                   nx), "ao2mo_rect")
+        return out
+
+    # -- slab copies (ri.rs:410-433) --
+    def copy_from_ri(self, range_x: Range, range_y: Range, range_z: Range, from_ri: "RIFull", f_range_x: Range,
+                     f_range_y: Range, f_range_z: Range) -> None:
+        ri_copy_from_ri(from_ri.data, from_ri.size, f_range_x, f_range_y, f_range_z, self.data, self.size, range_x,
+                        range_y, range_z)
+
+    def copy_from_matr(self, range_x: Range, range_y: Range, i_z: int, copy_mod: int, from_matr: MatrixFull,
+                       f_range_x: Range, f_range_y: Range) -> None:
+        ri_copy_from_matr(from_matr.data, from_matr.size, f_range_x, f_range_y, self.data, self.size, range_x, range_y,
+                          i_z, copy_mod)
+
+    # -- RI-J / RI-K / d_P over this tensor (REST composes them from the primitives above) --
+    def ri_dp(self, dm: MatrixFull) -> np.ndarray:
+        nb, nx = self.size[0], self.size[2]
+        d = np.zeros(nx, dtype=np.float64)
+        check(lib.rb_host_ri_dp(_ptr(self.data), _ptr(dm.data), _ptr(d), nb, nx), "ri_dp")
+        return d
+
+    def ri_j(self, d: np.ndarray) -> MatrixFull:
+        nb, nx = self.size[0], self.size[2]
+        j = MatrixFull.new([nb, nb], 0.0)
+        check(lib.rb_host_ri_j(_ptr(self.data), _ptr(_f64(d)), _ptr(j.data), nb, nx), "ri_j")
+        return j
+
+    def ri_k(self, ct: MatrixFull) -> MatrixFull:
+        nb, nx, no = self.size[0], self.size[2], ct.size[1]
+        k = MatrixFull.new([nb, nb], 0.0)
+        check(lib.rb_host_ri_k(_ptr(self.data), _ptr(ct.data), no, _ptr(k.data), nb, nx), "ri_k")
+        return k
+
+
+# ======================================================================================================
+# matrix_blas_lapack (src/matrix/matrix_blas_lapack.rs)
+# ======================================================================================================
+def _gemm_shape_ok(sa, opa, sb, opb, sc) -> bool:
+    key = (opa, opb)
+    if key == ('N', 'N'):
+        return sa[1] == sb[0] and sa[0] == sc[0] and sb[1] == sc[1]
+    if key == ('T', 'N'):
+        return sa[0] == sb[0] and sa[1] == sc[0] and sb[1] == sc[1]
+    if key == ('N', 'T'):
+        return sa[1] == sb[1] and sa[0] == sc[0] and sb[0] == sc[1]
+    if key == ('T', 'T'):
+        return sa[0] == sb[1] and sa[1] == sc[0] and sb[0] == sc[1]
+    return False
+
+
+def _dgemm(matr_a: MatrixFull, sub_a_dim, opa: str, matr_b: MatrixFull, sub_b_dim, opb: str, matr_c: MatrixFull,
+           sub_c_dim, alpha: float, beta: float) -> None:
+    """matrix_blas_lapack.rs:122-178: sub-block GEMM; same three panics (shape, within, contiguity)."""
+    la = [_rlen(sub_a_dim[0]), _rlen(sub_a_dim[1])]
+    lb = [_rlen(sub_b_dim[0]), _rlen(sub_b_dim[1])]
+    lc = [_rlen(sub_c_dim[0]), _rlen(sub_c_dim[1])]
+    if not _gemm_shape_ok(la, opa, lb, opb, lc):
+        raise ValueError(f"ERROR:: Matr_A[{la[0]},{la[1]},{opa}] * Matr_B[{lb[0]},{lb[1]},{opb}] -> Matr_C[{lc[0]},{lc[1]}]")
+    within = (sub_a_dim[0][1] <= matr_a.size[0] and sub_a_dim[1][1] <= matr_a.size[1]
+              and sub_b_dim[0][1] <= matr_b.size[0] and sub_b_dim[1][1] <= matr_b.size[1]
+              and sub_c_dim[0][1] <= matr_c.size[0] and sub_c_dim[1][1] <= matr_c.size[1])
+    if not within:
+        raise ValueError("ERROR:: sub-matrix block is not within the matrix")
+    general_dgemm_f(matr_a.data, matr_a.size, sub_a_dim[0], sub_a_dim[1], opa,
+                    matr_b.data, matr_b.size, sub_b_dim[0], sub_b_dim[1], opb,
+                    matr_c.data, matr_c.size, sub_c_dim[0], sub_c_dim[1], alpha, beta)
+
+
+def _dgemm_full(matr_a: MatrixFull, opa: str, matr_b: MatrixFull, opb: str, matr_c: MatrixFull, alpha: float,
+                beta: float) -> None:
+    """matrix_blas_lapack.rs:180-252"""
+    sa, sb, sc = matr_a.size, matr_b.size, matr_c.size
+    if not _gemm_shape_ok(sa, opa, sb, opb, sc):
+        raise ValueError(f"ERROR:: Matr_A[{sa[0]},{sa[1]},{opa}] * Matr_B[{sb[0]},{sb[1]},{opb}] -> Matr_C[{sc[0]},{sc[1]}]")
+    m = sa[0] if opa == 'N' else sa[1]
+    k = sa[1] if opa == 'N' else sa[0]
+    n = sb[1] if opb == 'N' else sb[0]
+    lda = max(m, 1) if opa == 'N' else max(k, 1)
+    ldb = max(k, 1) if opb == 'N' else max(n, 1)
+    check(lib.rb_host_dgemm(ch(opa), ch(opb), m, n, k, alpha, _ptr(matr_a.data), lda, _ptr(matr_b.data), ldb, beta,
+                            _ptr(matr_c.data), max(m, 1)), "_dgemm_full")
+
+
+def _dgemm_full_new(matr_a: MatrixFull, opa: str, matr_b: MatrixFull, opb: str, alpha: float, beta: float) -> MatrixFull:
+    """matrix_blas_lapack.rs:256-278"""
+    axy, bxy = matr_a.size, matr_b.size
+    if axy[0] == 0 or bxy[1] == 0:
+        return MatrixFull.new([axy[0], bxy[1]], 0.0)
+    shape = {('N', 'N'): [axy[0], bxy[1]], ('T', 'N'): [axy[1], bxy[1]], ('N', 'T'): [axy[0], bxy[0]],
+             ('T', 'T'): [axy[1], bxy[0]]}.get((opa, opb), [0, 0])
+    c = MatrixFull.new(shape, 0.0)
+    _dgemm_full(matr_a, opa, matr_b, opb, c, alpha, beta)
+    return c
+
+
+def _dsyrk(matr_a: MatrixFull, matr_c: MatrixFull, uplo: str, trans: str, alpha: float, beta: float) -> None:
+    """matrix_blas_lapack.rs:392-413: panics unless C square; only the uplo triangle of C is read/written"""
+    m, n = matr_c.size
+    if m != n:
+        raise ValueError("matr_b should be symmetric")
+    is_n = trans.lower() == 'n'
+    k = matr_a.size[1] if is_n else matr_a.size[0]
+    lda = max(n, 1) if is_n else max(k, 1)
+    check(lib.rb_host_dsyrk(ch(uplo), ch(trans), n, k, alpha, _ptr(matr_a.data), lda, beta, _ptr(matr_c.data),
+                            max(n, 1)), "_dsyrk")
+
+
+def _dsymm(matr_a: MatrixFull, matr_b: MatrixFull, matr_c: MatrixFull, side: str, uplo: str, alpha: float,
+           beta: float) -> None:
+    """matrix_blas_lapack.rs:354-378 (no checks, like the reference)"""
+    m, n = matr_c.size
+    lda = m if side.lower() == 'l' else n
+    check(lib.rb_host_dsymm(ch(side), ch(uplo), m, n, alpha, _ptr(matr_a.data), lda, _ptr(matr_b.data), m, beta,
+                            _ptr(matr_c.data), m), "_dsymm")
+
+
+def _dgemv(matr_a: MatrixFull, vec_x: np.ndarray, vec_y: np.ndarray, trans: str, alpha: float, beta: float, incx: int,
+           incy: int) -> None:
+    """matrix_blas_lapack.rs:38-70: same length checks (=> panic) as the reference"""
+    m, n = matr_a.size
+    is_n = trans.lower() == 'n'
+    ok_x = vec_x.size == 1 + ((n if is_n else m) - 1) * abs(incx)
+    ok_y = vec_y.size == 1 + ((m if is_n else n) - 1) * abs(incy)
+    if not (ok_x and ok_y):
+        raise ValueError(f"ERROR:: Matr_A[{m},{n},{trans}] * Vec_X[{vec_x.size}] -> Vec_Y[{vec_y.size}]")
+    check(lib.rb_host_dgemv(ch(trans), m, n, alpha, _ptr(matr_a.data), max(m, 1), _ptr(vec_x), incx, beta, _ptr(vec_y),
+                            incy), "_dgemv")

@@ -1,0 +1,138 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/rest_b200.h declares, the product
+fails loudly without a GPU (no CPU fallback), and the host-side mirror keeps the reference's metadata / panics."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "rest_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = re.findall(r"\b(?:int|void|int64_t|const char \*)\s*\*?\s*([a-z_0-9]+)\s*\(", src)
+    return sorted(set(n for n in names if n.startswith("rb_") or n.endswith("_")))
+
+
+def test_library_exports_every_declared_symbol(rt):
+    names = _header_functions()
+    assert len(names) > 60
+    lib = ctypes.CDLL(rt.LIB_PATH)
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, f"declared in rest_b200.h but not exported: {missing}"
+    # and the ctypes signature table covers the header
+    assert sorted(rt.SIGNATURES) == names
+
+
+def test_reference_ffi_symbols_present(rt):
+    # exactly the seven symbols of reference src/external_libs/ffi_restmatr.rs:4-62
+    for n in ["ri_ao2mo_f_", "general_dgemm_f_", "special_dgemm_f_01_", "copy_mm_", "copy_mr_", "copy_rm_", "copy_rr_"]:
+        assert hasattr(rt.lib, n)
+
+
+def test_product_does_not_touch_the_oracle():
+    pkg = os.path.join(ROOT, "rest_tensors_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".rs")):
+                text = open(os.path.join(dirpath, f)).read()
+                # functional references only (imports, includes, symbols, the .so); prose in comments is fine
+                hits = re.findall(r"import\s+oracle|from\s+oracle|librest_oracle|\borc_[a-z]|#include[^\n]*oracle", text)
+                assert not hits, f"{f} uses the oracle: {hits}"
+
+
+def test_fails_loudly_without_gpu(rt):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(rt.RestB200Error, match="no CPU fallback"):
+        rt.MatrixFull.from_vec([2, 2], [1.0, 2.0, 3.0, 4.0]).to_matrixupper()
+    from rest_tensors_b200.device import Context
+    with pytest.raises(rt.RestB200Error):
+        Context(0)
+
+
+def test_constructors_and_panics(rt):
+    r = rt.RIFull.new([3, 2, 2], 1.5)
+    assert r.size == [3, 2, 2] and r.indicing == [1, 3, 6] and r.data.size == 12 and np.all(r.data == 1.5)
+    with pytest.raises(ValueError):
+        rt.RIFull.from_vec([3, 2, 2], np.zeros(11))        # ri.rs:61-63 panic
+    assert rt.RIFull.from_vec([3, 2, 2], np.zeros(13)).data.size == 13   # surplus kept (warning in the reference)
+    with pytest.raises(ValueError):
+        rt.MatrixFull.from_vec([3, 3], np.zeros(8))
+    with pytest.raises(ValueError):
+        rt.MatrixUpper.from_vec(7, np.zeros(6))
+    with pytest.raises(ValueError):
+        rt.MatrixFull.new([2, 3], 0.0).to_matrixupper()    # matrixfull.rs:639-641 panic
+    assert rt.MatrixUpper.from_vec(4, np.zeros(4)).to_matrixfull() is None   # not triangular -> None
+    e = rt.MatrixUpper.empty().to_matrixfull()
+    assert e.size == [0, 0] and e.data.size == 0           # matrixupper.rs:336-338
+    assert rt.RIFull.empty().size == [0, 0, 0]
+
+
+def test_index_maps(rt, oracle):
+    mu = rt.MatrixUpper.new(10, 0.0)
+    assert mu.size2d() == [4, 4]
+    for i in range(5):
+        for j in range(5):
+            assert mu.index2d([i, j]) == oracle.index2d(i, j, 10)
+    assert mu.index2d_uncheck([2, 1]) == 3   # no swap: (1+1)*1/2 + 2
+    assert mu.index2d([3, 3]) == 9 and mu.index2d([4, 4]) is None
+
+
+def test_slab_views_are_zero_copy(rt):
+    r = rt.RIFull.from_vec([3, 2, 4], np.arange(24.0))
+    m = r.get_reducing_matrix(2)
+    assert m.size == [3, 2] and m.data.tolist() == list(np.arange(12.0, 18.0))
+    m.data[0] = -1.0
+    assert r.data[12] == -1.0
+    chunks = list(r.iter_auxbas((1, 3)))
+    assert len(chunks) == 2 and chunks[0][1] == 7.0
+    sub = r.get_reducing_matrix_columns((1, 2), 3)
+    assert sub.size == [3, 1] and sub.indicing == [1, 1] and sub.data.tolist() == [21.0, 22.0, 23.0]
+    # get_slices: x-runs, z outer / y inner (ri.rs:117-128)
+    s = r.get_slices((1, 3), (0, 2), (1, 2))
+    assert s.tolist() == [7.0, 8.0, 10.0, 11.0]
+    q = rt.MatrixFull.from_vec([2, 6], np.arange(12.0)).to_rifull(2, 3, 2)
+    assert q.indicing == [1, 2, 3]   # the reference's quirk (matrixfull.rs:681-685)
+
+
+def test_wrapper_panics_before_ffi(rt):
+    a = rt.MatrixFull.new([3, 3], 1.0); b = rt.MatrixFull.new([3, 3], 1.0); c = rt.MatrixFull.new([3, 3], 0.0)
+    with pytest.raises(ValueError):     # shape mismatch, matrix_blas_lapack.rs:146-153
+        rt._dgemm(a, ((0, 2), (0, 3)), 'N', b, ((0, 2), (0, 2)), 'N', c, ((0, 2), (0, 2)), 1.0, 0.0)
+    with pytest.raises(ValueError):     # block outside the matrix, :154-164
+        rt._dgemm(a, ((2, 4), (0, 2)), 'N', b, ((0, 2), (0, 2)), 'N', c, ((0, 2), (0, 2)), 1.0, 0.0)
+    with pytest.raises(ValueError):     # unknown op -> shape check false -> panic
+        rt._dgemm(a, ((0, 2), (0, 2)), 'X', b, ((0, 2), (0, 2)), 'N', c, ((0, 2), (0, 2)), 1.0, 0.0)
+    with pytest.raises(ValueError):
+        rt._dgemm_full(a, 'N', rt.MatrixFull.new([2, 3], 0.0), 'N', c, 1.0, 0.0)
+    with pytest.raises(ValueError):
+        rt._dsyrk(a, rt.MatrixFull.new([3, 2], 0.0), 'U', 'N', 1.0, 0.0)
+    with pytest.raises(ValueError):
+        rt._dgemv(a, np.zeros(2), np.zeros(3), 'N', 1.0, 0.0, 1, 1)
+    with pytest.raises(ValueError):     # external_libs/mod.rs:118
+        rt.matr_copy(a.data, a.size, (0, 2), (0, 2), c.data, c.size, (0, 3), (0, 2))
+    r = rt.RIFull.new([3, 3, 2], 0.0)
+    with pytest.raises(ValueError):     # external_libs/mod.rs:188
+        r.copy_from_ri((0, 2), (0, 2), (0, 1), rt.RIFull.new([3, 3, 2], 1.0), (0, 2), (0, 2), (0, 2))
+    with pytest.raises(ValueError):     # external_libs/mod.rs:163
+        r.copy_from_matr((0, 2), (0, 2), 0, 0, a, (0, 3), (0, 2))
+    with pytest.raises(ValueError):
+        r.self_scaled_add(rt.RIFull.new([3, 3, 1], 0.0), 2.0)
+    assert a.add(rt.MatrixFull.new([2, 3], 0.0)) is None   # value-returning forms give None
+
+
+def test_shard_range_partitions_exactly():
+    from rest_tensors_b200.device import shard_range
+    for naux in (0, 1, 7, 400, 720, 1700, 4800):
+        for world in (1, 2, 3, 4, 8):
+            spans = [shard_range(naux, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == naux
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    assert shard_range(4800, 3, 8) == (1800, 2400)

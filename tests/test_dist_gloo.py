@@ -1,0 +1,65 @@
+"""world_size-2 gloo test of the multi-GPU host logic on CPU: the P-shard partition (shard_range ==
+iter_auxbas(P_lo..P_hi), reference src/ri.rs:190-198) plus ONE all-reduce(sum) of the J and K partials reproduces the
+unsharded result; ao2mo and d_P need no communication.  The per-rank partials come from the CPU oracle here (there is
+no GPU in this tier); the GPU tier runs the same flow with the CUDA kernels (tests/test_gpu_dist.py, bench.py --gpus N)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, nb, naux, no, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle.api import Oracle
+        from rest_tensors_b200.device import shard_range, all_reduce_sum, gather_dp
+        o = Oracle()
+        p_lo, p_hi = shard_range(naux, rank, world)
+        nx = p_hi - p_lo
+        ri_local = o.fill_ri3ao_symm(nb, p_lo, p_hi)           # this rank's slabs only
+        c = o.fill_linear(nb * nb, 3, scale=nb ** -0.5)
+        cm = c.reshape((nb, nb), order="F")
+        dm = np.ascontiguousarray((2.0 * cm[:, :no] @ cm[:, :no].T).reshape(-1, order="F"))
+        ct = np.ascontiguousarray((cm[:, :no] * np.sqrt(2.0)).reshape(-1, order="F"))
+        d_local = o.ri_dp(ri_local, dm, nb, nx)
+        j = torch.from_numpy(o.ri_j(ri_local, d_local, nb, nx))
+        k = torch.from_numpy(o.ri_k(ri_local, ct, nb, no, nx))
+        all_reduce_sum(j, world)
+        all_reduce_sum(k, world)
+        mo_local = o.ri_ao2mo_f(c, ri_local, nb, nb, nx)
+        # gather the d_P pieces and the P-rows of ri3mo for the check on rank 0
+        d_full = gather_dp(torch.from_numpy(d_local), naux, p_lo, world)
+        if rank == 0:
+            ri = o.fill_ri3ao_symm(nb, 0, naux)
+            d_ref = o.ri_dp(ri, dm, nb, naux)
+            ok = np.allclose(d_full.numpy(), d_ref, rtol=1e-12, atol=0)
+            ok &= np.allclose(j.numpy(), o.ri_j(ri, d_ref, nb, naux), rtol=1e-11, atol=1e-12)
+            ok &= np.allclose(k.numpy(), o.ri_k(ri, ct, nb, no, naux), rtol=1e-11, atol=1e-12)
+            mo = o.ri_ao2mo_f(c, ri, nb, nb, naux).reshape((naux, nb, nb), order="F")
+            ok &= np.array_equal(mo[p_lo:p_hi].reshape(-1, order="F"), mo_local)
+            ret.put(bool(ok))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_p_sharding_with_allreduce_world2():
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, 12, 9, 3, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert ret.get(timeout=5) is True

@@ -1,0 +1,314 @@
+"""GPU parity, FP64 half: the DMMA GEMM core (all op combinations, TMA and generic paths, batched, triangular,
+split-K), GEMV, SYMM, and the RI contractions ao2mo / d_P / J / K -- CUDA through the C ABI vs the CPU oracle
+(reference algorithm: restmatr.f90 loop structure + OpenBLAS) on identical synthetic inputs.
+Tolerance: 1e-10 relative (north star), norm-wise and element-wise (conftest.assert_close_1e10)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_close_1e10, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(ctx, a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(f"cuda:{ctx.device}")
+
+
+def _col(m):
+    return np.ascontiguousarray(np.asarray(m).reshape(-1, order="F"))
+
+
+# ---------------------------------------------------------------- golden vectors through the compat symbols ----
+@pytest.mark.parametrize("name", ["GV1", "GV2", "GV3"])
+def test_golden_sub_block_gemm(rt, golden, name):
+    g = golden[name]
+    a = rt.MatrixFull.from_vec(g["size_a"], g["a"]); b = rt.MatrixFull.from_vec(g["size_b"], g["b"])
+    c = rt.MatrixFull.new(g["size_c"], g["c_fill"])
+    rt._dgemm(a, tuple(map(tuple, g["sub_a"])), g["opa"], b, tuple(map(tuple, g["sub_b"])), g["opb"], c,
+              tuple(map(tuple, g["sub_c"])), g["alpha"], g["beta"])
+    cm = c.data.reshape(g["size_c"], order="F")
+    r, cc = g["sub_c"]
+    assert cm[r[0]:r[1], cc[0]:cc[1]].reshape(-1, order="F").tolist() == g["expect_block"]
+    cm[r[0]:r[1], cc[0]:cc[1]] = g["c_fill"]
+    assert np.all(cm == g["c_fill"])
+
+
+def test_golden_ao2mo_bench_case(rt, golden):
+    g = golden["GV9"]  # benches/bench_tensors.rs: every element 200.0 exactly
+    out = rt.RIFull.new(g["ri_size"], g["ri_fill"]).ao2mo_v02(rt.MatrixFull.new(g["c_size"], g["c_fill"]))
+    assert out.size == [20, 10, 10]
+    assert np.all(out.data == g["expect_every"])
+    out = rt.RIFull.new(g["ri_size"], g["ri_fill"]).ao2mo(rt.MatrixFull.new(g["c_size"], g["c_fill"]))
+    assert np.all(out.data == g["expect_every"])
+
+
+# ---------------------------------------------------------------- GEMM core ----
+SHAPES = [(1, 1, 1), (8, 8, 4), (17, 13, 29), (128, 128, 32), (130, 126, 70), (256, 384, 200), (300, 20, 1000),
+          (64, 64, 2048), (513, 257, 129)]
+
+
+@pytest.mark.parametrize("ta", "NT")
+@pytest.mark.parametrize("tb", "NT")
+@pytest.mark.parametrize("even", [True, False])
+def test_dgemm_all_ops(ctx, oracle_blas, ta, tb, even):
+    """even leading dimensions take the TMA kernel, odd ones the generic kernel; both must agree with OpenBLAS."""
+    for (m, n, k) in SHAPES:
+        ra, ca = (m, k) if ta == "N" else (k, m)
+        rb, cb = (k, n) if tb == "N" else (n, k)
+
+        def ld(rows):  # smallest leading dimension >= rows with the requested parity
+            return rows + (rows % 2 if even else 1 - rows % 2)
+        lda, ldb, ldc = ld(ra), ld(rb), ld(m)
+        a = oracle_blas.fill_linear(lda * ca, 21); b = oracle_blas.fill_linear(ldb * cb, 22)
+        c0 = oracle_blas.fill_linear(ldc * n, 23)
+        for alpha, beta in [(1.0, 0.0), (0.7, -0.3)]:
+            c_ref = c0.copy()
+            oracle_blas.dgemm(ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c_ref, ldc)
+            cd = _dev(ctx, c0)
+            ctx.dgemm(ta, tb, m, n, k, alpha, _dev(ctx, a), lda, _dev(ctx, b), ldb, beta, cd, ldc)
+            got = cd.cpu().numpy()
+            assert_close_1e10(got, c_ref, f"dgemm {ta}{tb} {m}x{n}x{k} even={even}")
+            # padding rows of C (between m and ldc) untouched
+            if ldc > m:
+                assert np.array_equal(got.reshape((ldc, n), order="F")[m:], c0.reshape((ldc, n), order="F")[m:])
+
+
+def test_dgemm_generic_path_forced(ctx, oracle_blas):
+    m, n, k = 200, 136, 264
+    a = oracle_blas.fill_linear(m * k, 24); b = oracle_blas.fill_linear(k * n, 25)
+    c_ref = np.zeros(m * n)
+    oracle_blas.dgemm("N", "N", m, n, k, 1.0, a, m, b, k, 0.0, c_ref, m)
+    ctx.set_gemm_path(1)
+    try:
+        cd = ctx.empty(m * n)
+        ctx.dgemm("N", "N", m, n, k, 1.0, _dev(ctx, a), m, _dev(ctx, b), k, 0.0, cd, m)
+        assert_close_1e10(cd.cpu().numpy(), c_ref, "generic kernel")
+    finally:
+        ctx.set_gemm_path(0)
+
+
+def test_dgemm_degenerate(ctx):
+    c = torch.full((12,), 3.0, dtype=torch.float64, device=f"cuda:{ctx.device}")
+    a = torch.ones(12, dtype=torch.float64, device=c.device)
+    ctx.dgemm("N", "N", 3, 4, 0, 1.0, a, 3, a, 1, 0.5, c, 3)      # k == 0: C = beta*C
+    assert torch.all(c == 1.5)
+    ctx.dgemm("N", "N", 3, 4, 2, 0.0, a, 3, a, 2, 0.0, c, 3)      # alpha == 0, beta == 0: C = 0
+    assert torch.all(c == 0.0)
+    ctx.dgemm("N", "N", 0, 4, 2, 1.0, a, 1, a, 2, 0.0, c, 1)      # m == 0: no-op
+    with pytest.raises(Exception):
+        ctx.dgemm("X", "N", 3, 4, 2, 1.0, a, 3, a, 2, 0.0, c, 3)
+
+
+def test_dgemm_strided_batched_and_broadcast(ctx, oracle_blas):
+    m, n, k, batch = 70, 52, 96, 5
+    a = oracle_blas.fill_linear(m * k * batch, 26); b = oracle_blas.fill_linear(k * n, 27)
+    c_ref = np.zeros(m * n * batch)
+    for i in range(batch):
+        ci = np.zeros(m * n)
+        oracle_blas.dgemm("N", "N", m, n, k, 1.0, a[i * m * k:(i + 1) * m * k], m, b, k, 0.0, ci, m)
+        c_ref[i * m * n:(i + 1) * m * n] = ci
+    cd = ctx.empty(m * n * batch)
+    ctx.dgemm_strided_batched("N", "N", m, n, k, 1.0, _dev(ctx, a), m, m * k, _dev(ctx, b), k, 0, 0.0, cd, m, m * n, batch)
+    assert_close_1e10(cd.cpu().numpy(), c_ref, "batched NN with shared B")
+
+
+def test_host_dgemm_wrappers(rt, oracle_blas):
+    m, n, k = 90, 41, 77
+    a = oracle_blas.fill_linear(m * k, 28); b = oracle_blas.fill_linear(n * k, 29)
+    A = rt.MatrixFull.from_vec([m, k], a); B = rt.MatrixFull.from_vec([n, k], b)
+    C = rt.MatrixFull.new([m, n], 1.0)
+    c_ref = np.ones(m * n)
+    oracle_blas.dgemm("N", "T", m, n, k, 2.0, a, m, b, n, 0.5, c_ref, m)
+    rt._dgemm_full(A, "N", B, "T", C, 2.0, 0.5)
+    assert_close_1e10(C.data, c_ref, "_dgemm_full NT")
+    C2 = rt._dgemm_full_new(A, "N", B, "T", 2.0, 0.0)
+    assert C2.size == [m, n]
+    c_ref2 = np.zeros(m * n)
+    oracle_blas.dgemm("N", "T", m, n, k, 2.0, a, m, b, n, 0.0, c_ref2, m)
+    assert_close_1e10(C2.data, c_ref2, "_dgemm_full_new")
+    D = A.ddot(rt.MatrixFull.from_vec([k, n], oracle_blas.fill_linear(k * n, 30)))
+    d_ref = np.zeros(m * n)
+    oracle_blas.dgemm("N", "N", m, n, k, 1.0, a, m, oracle_blas.fill_linear(k * n, 30), k, 0.0, d_ref, m)
+    assert_close_1e10(D.data, d_ref, "ddot")
+    assert A.ddot(A) is None
+
+
+# ---------------------------------------------------------------- SYRK / SYMM / GEMV ----
+@pytest.mark.parametrize("uplo", "UL")
+@pytest.mark.parametrize("trans", "NT")
+def test_dsyrk(rt, oracle_blas, uplo, trans):
+    for n, k in [(5, 3), (130, 70), (264, 1500), (600, 64)]:
+        ra, ca = (n, k) if trans == "N" else (k, n)
+        a = oracle_blas.fill_linear(ra * ca, 31)
+        c0 = oracle_blas.fill_linear(n * n, 32)
+        c_ref = c0.copy()
+        oracle_blas.dsyrk(uplo, trans, n, k, 0.9, a, ra, 0.2, c_ref, n)
+        C = rt.MatrixFull.from_vec([n, n], c0.copy())
+        rt._dsyrk(rt.MatrixFull.from_vec([ra, ca], a), C, uplo, trans, 0.9, 0.2)
+        got = C.data.reshape((n, n), order="F"); ref = c_ref.reshape((n, n), order="F"); orig = c0.reshape((n, n), order="F")
+        tri = np.triu if uplo == "U" else np.tril
+        other = (lambda x: np.tril(x, -1)) if uplo == "U" else (lambda x: np.triu(x, 1))
+        assert_close_1e10(tri(got), tri(ref), f"dsyrk {uplo}{trans} n={n} k={k}")
+        assert np.array_equal(other(got), other(orig)), "the other triangle must stay untouched"
+
+
+@pytest.mark.parametrize("side", "LR")
+@pytest.mark.parametrize("uplo", "UL")
+def test_dsymm(rt, oracle_blas, side, uplo):
+    m, n = 66, 35
+    ka = m if side == "L" else n
+    a = oracle_blas.fill_linear(ka * ka, 33); b = oracle_blas.fill_linear(m * n, 34); c0 = oracle_blas.fill_linear(m * n, 35)
+    c_ref = c0.copy()
+    oracle_blas.dsymm(side, uplo, m, n, 1.1, a, ka, b, m, -0.4, c_ref, m)
+    C = rt.MatrixFull.from_vec([m, n], c0.copy())
+    rt._dsymm(rt.MatrixFull.from_vec([ka, ka], a), rt.MatrixFull.from_vec([m, n], b), C, side, uplo, 1.1, -0.4)
+    assert_close_1e10(C.data, c_ref, f"dsymm {side}{uplo}")
+
+
+@pytest.mark.parametrize("trans", "NT")
+def test_dgemv(rt, oracle_blas, trans):
+    for m, n, incx, incy in [(7, 5, 1, 1), (1000, 33, 1, 1), (129, 257, 2, 3), (10000, 40, 1, 1), (64, 3000, 1, 1),
+                             (33, 9, -1, 1)]:
+        a = oracle_blas.fill_linear(m * n, 36)
+        lenx, leny = (n, m) if trans == "N" else (m, n)
+        x = oracle_blas.fill_linear(1 + (lenx - 1) * abs(incx), 37); y0 = oracle_blas.fill_linear(1 + (leny - 1) * abs(incy), 38)
+        y_ref = y0.copy()
+        oracle_blas.dgemv(trans, m, n, 0.8, a, m, x, incx, 0.25, y_ref, incy)
+        y = y0.copy()
+        rt._dgemv(rt.MatrixFull.from_vec([m, n], a), x, y, trans, 0.8, 0.25, incx, incy)
+        assert_close_1e10(y, y_ref, f"dgemv {trans} {m}x{n} inc {incx},{incy}")
+
+
+# ---------------------------------------------------------------- ao2mo ----
+def _inputs(o, nb, nx, no, symmetric=True):
+    ri = o.fill_ri3ao_symm(nb, 0, nx) if symmetric else o.fill_linear(nb * nb * nx, 2)
+    c = o.fill_linear(nb * nb, 3, scale=nb ** -0.5)
+    cm = c.reshape((nb, nb), order="F")
+    dm = _col(2.0 * cm[:, :no] @ cm[:, :no].T)
+    ct = _col(cm[:, :no] * np.sqrt(2.0))
+    return ri, c, dm, ct
+
+
+@pytest.mark.parametrize("nb,nx,symm", [(10, 20, True), (24, 7, False), (100, 400, True), (33, 5, False), (128, 130, False)])
+def test_ao2mo_square_vs_reference_algorithm(rt, oracle_blas, nb, nx, symm):
+    """square C (the only case the Fortran defines): compat symbol ri_ao2mo_f_ vs restmatr.f90 restatement + OpenBLAS.
+    (100, 400) is BASELINE config A in full; odd nb goes through the generic (non-TMA) kernel."""
+    ri, c, _, _ = _inputs(oracle_blas, nb, nx, 1, symm)
+    ref = oracle_blas.ri_ao2mo_f(c, ri, nb, nb, nx)
+    got = rt.RIFull.from_vec([nb, nb, nx], ri).ao2mo(rt.MatrixFull.from_vec([nb, nb], c))
+    assert got.size == [nx, nb, nb]
+    assert_close_1e10(got.data, ref, f"ao2mo nb={nb} nx={nx}")
+
+
+def test_ao2mo_vs_blas_free_restatement(rt, oracle):
+    nb, nx = 40, 9
+    ri, c, _, _ = _inputs(oracle, nb, nx, 1, False)
+    ref = oracle.ao2mo_v01(c, ri, nb, nb, nx)   # fixed summation order of the pure-Rust variant (ri.rs:360-379)
+    got = rt.RIFull.from_vec([nb, nb, nx], ri).ao2mo_v01(rt.MatrixFull.from_vec([nb, nb], c))
+    assert_close_1e10(got.data, ref, "ao2mo vs ao2mo_v01 order")
+
+
+def test_ao2mo_rect_occ_vir(rt, oracle_blas):
+    nb, nx, no = 64, 50, 12
+    ri, c, _, _ = _inputs(oracle_blas, nb, nx, no, False)
+    cm = c.reshape((nb, nb), order="F")
+    cl, cr = _col(cm[:, :no]), _col(cm[:, no:])
+    ref = oracle_blas.ri_ao2mo_rect(cl, no, cr, nb - no, ri, nb, nx)
+    got = rt.RIFull.from_vec([nb, nb, nx], ri).ao2mo_rect(rt.MatrixFull.from_vec([nb, no], cl), rt.MatrixFull.from_vec([nb, nb - no], cr))
+    assert got.size == [nx, no, nb - no]
+    assert_close_1e10(got.data, ref, "ao2mo occ-vir")
+
+
+def test_ao2mo_edge_cases(rt):
+    assert rt.RIFull.new([4, 4, 0], 1.0).ao2mo(rt.MatrixFull.new([4, 4], 1.0)).data.size == 0        # no slabs
+    out = rt.RIFull.new([1, 1, 3], 2.0).ao2mo(rt.MatrixFull.new([1, 1], 3.0))                         # 1x1 slabs
+    assert out.data.tolist() == [18.0, 18.0, 18.0]
+
+
+def test_ao2mo_multi_chunk_host_pipeline(rt, oracle_blas):
+    """nx > 256 exercises the 3-stream H2D | compute | D2H pipeline of ri_ao2mo_f_ (several P-chunks, ragged tail)."""
+    nb, nx = 48, 700
+    ri, c, _, _ = _inputs(oracle_blas, nb, nx, 1, True)
+    ref = oracle_blas.ri_ao2mo_f(c, ri, nb, nb, nx)
+    got = rt.RIFull.from_vec([nb, nb, nx], ri).ao2mo(rt.MatrixFull.from_vec([nb, nb], c))
+    assert_close_1e10(got.data, ref, "pipelined host ao2mo")
+
+
+def test_ao2mo_full_size_identity_property(ctx):
+    """BASELINE config B size (nb=264, nx=720) on device: with C = I the transform must return the input bits,
+    ri3mo[P,a,b] == ri3ao[a,b,P] (every sum has one non-zero term), and scaling C by 2 scales the result by 4 exactly."""
+    nb, nx = 264, 720
+    from rest_tensors_b200.device import ShardedRI
+    ri = ShardedRI(ctx, nb, nx).fill_synthetic()
+    eye = torch.eye(nb, dtype=torch.float64, device=ri.data.device).reshape(-1).contiguous()
+    out = ri.ao2mo(eye, nb, eye, nb)
+    # torch views are row-major: data.view(nx, nb(nu), nb(mu))[P, nu, mu]; out is column-major [P, a, b]
+    out_rm = out.view(nb, nb, nx)                                               # [b, a, P]
+    assert torch.equal(out_rm, ri.data.view(nx, nb, nb).permute(1, 2, 0)), "ao2mo(I) must reproduce ri3ao bit for bit"
+    c = ctx.empty(nb * nb)
+    ctx.fill_linear(c, nb * nb, 3, 0, nb ** -0.5)
+    o1 = ri.ao2mo(c, nb, c, nb)
+    c2 = c * 2.0
+    o2 = ri.ao2mo(c2, nb, c2, nb)
+    assert torch.equal(o2, o1 * 4.0)
+    # symmetric slabs + same C on both sides => ri3mo[P,a,b] == ri3mo[P,b,a] up to rounding
+    o1v = o1.view(nb, nb, nx)
+    assert rel_err(o1v.permute(1, 0, 2).cpu().numpy(), o1v.cpu().numpy()) < 1e-12
+
+
+# ---------------------------------------------------------------- d_P, J, K ----
+@pytest.mark.parametrize("nb,nx,no,symm", [(10, 20, 3, True), (100, 400, 20, True), (37, 11, 5, False), (64, 300, 64, False)])
+def test_dp_j_k_vs_oracle(rt, oracle_blas, nb, nx, no, symm):
+    ri, c, dm, ct = _inputs(oracle_blas, nb, nx, no, symm)
+    R = rt.RIFull.from_vec([nb, nb, nx], ri)
+    d_ref = oracle_blas.ri_dp(ri, dm, nb, nx)
+    d = R.ri_dp(rt.MatrixFull.from_vec([nb, nb], dm))
+    assert_close_1e10(d, d_ref, "d_P")
+    assert_close_1e10(R.ri_j(d_ref).data, oracle_blas.ri_j(ri, d_ref, nb, nx), "J")
+    assert_close_1e10(R.ri_k(rt.MatrixFull.from_vec([nb, no], ct)).data, oracle_blas.ri_k(ri, ct, nb, no, nx), "K")
+
+
+def test_jk_full_size_properties(ctx):
+    """config B size on device: J symmetric for symmetric slabs, K symmetric with non-negative diagonal,
+    linearity of d_P and J, and P-shard additivity (sum of two half-shards == whole) -- the multi-GPU invariant."""
+    nb, nx, no = 264, 720, 21
+    from rest_tensors_b200.device import ShardedRI
+    ri = ShardedRI(ctx, nb, nx).fill_synthetic()
+    c = ctx.empty(nb * nb); ctx.fill_linear(c, nb * nb, 3, 0, nb ** -0.5)
+    cm = c.view(nb, nb).t()                      # column-major [nb, nb] as a torch matrix
+    dm = (2.0 * cm[:, :no] @ cm[:, :no].t()).t().contiguous().reshape(-1)
+    ct = (cm[:, :no] * (2.0 ** 0.5)).t().contiguous().reshape(-1)
+    d = ri.dp(dm)
+    j = ri.j(d, reduce=False)
+    k = ri.k(ct, no, reduce=False)
+    jm, km = j.view(nb, nb), k.view(nb, nb)
+    assert rel_err(jm.t().cpu().numpy(), jm.cpu().numpy()) < 1e-12
+    assert torch.equal(km, km.t()) and bool((torch.diagonal(km) >= 0).all())
+    d2 = ri.dp(dm * 2.0)
+    assert torch.equal(d2, d * 2.0)
+    # shard additivity
+    half = nx // 2
+    lo = ShardedRI(ctx, nb, nx, rank=0, world=2, data=ri.data[: nb * nb * half])
+    hi = ShardedRI(ctx, nb, nx, rank=1, world=2, data=ri.data[nb * nb * half:])
+    assert (lo.p_lo, lo.p_hi, hi.p_lo, hi.p_hi) == (0, half, half, nx)
+    assert rel_err(torch.cat([lo.dp(dm), hi.dp(dm)]).cpu().numpy(), d.cpu().numpy()) < 1e-12
+    jsum = lo.j(d[:half], reduce=False) + hi.j(d[half:], reduce=False)
+    ksum = lo.k(ct, no, reduce=False) + hi.k(ct, no, reduce=False)
+    assert rel_err(jsum.cpu().numpy(), j.cpu().numpy()) < 1e-12
+    assert rel_err(ksum.cpu().numpy(), k.cpu().numpy()) < 1e-12
+
+
+# ---------------------------------------------------------------- special_dgemm_f_01 ----
+def test_special_dgemm_f_01(rt, oracle_blas):
+    X, Y, Z = 12, 7, 10
+    sx, lx, sz, lz = 2, 8, 1, 6
+    t0 = oracle_blas.fill_linear(X * Y * Z, 39)
+    b = oracle_blas.fill_linear(9 * 9, 40)
+    t_ref = t0.copy()
+    oracle_blas.special_dgemm_f_01(t_ref, [X, Y, Z], (sx, sx + lx), 0, (sz, sz + lz), b, [9, 9], (1, 1 + lz), (2, 2 + lz), 0.7, 0.1)
+    t = t0.copy()
+    rt.special_dgemm_f_01(t, [X, Y, Z], (sx, sx + lx), 0, (sz, sz + lz), b, [9, 9], (1, 1 + lz), (2, 2 + lz), 0.7, 0.1)
+    assert_close_1e10(t, t_ref, "special_dgemm_f_01")
+    mask = np.ones((X, Y, Z), dtype=bool); mask[sx:sx + lx, :, sz:sz + lz] = False
+    assert np.array_equal(t.reshape((X, Y, Z), order="F")[mask], t0.reshape((X, Y, Z), order="F")[mask])

@@ -1,0 +1,207 @@
+"""GPU parity, bit-exact half: pack/unpack, per-slab symmetric pack, sub-box copies, transposes, axpy family and the
+synthetic generators -- CUDA (through the C ABI) vs the CPU oracle on the same inputs.  Everything here must match
+BIT FOR BIT (np.array_equal)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(ctx, a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(f"cuda:{ctx.device}")
+
+
+# ---------------------------------------------------------------- golden vectors through the product ----
+def test_golden_pack_unpack_transpose(rt, golden):
+    g = golden["GV4"]
+    assert rt.MatrixFull.from_vec([4, 4], g["full"]).to_matrixupper().data.tolist() == g["packed"]
+    for case in golden["GV5"]["cases"]:
+        assert rt.MatrixUpper.from_vec(6, case["packed"]).to_matrixfull().data.tolist() == case["full_colmajor"]
+    g = golden["GV7"]
+    t = rt.MatrixFull.from_vec(g["size"], g["data"]).transpose()
+    assert t.size == [4, 3]
+    assert t.data.reshape((4, 3), order="F")[:, 2].tolist() == g["transposed_column_2"]
+
+
+def test_golden_ri_transposes(rt, golden):
+    g = golden["GV10"]
+    r = rt.RIFull.from_vec(g["size"], g["data"])
+    assert r.transpose_jik().data.tolist() == g["jik"] and r.transpose_jik().size == [2, 3, 2]
+    assert r.transpose_jki().data.tolist() == g["jki"] and r.transpose_jki().size == [2, 2, 3]
+    assert r.transpose_kji().data.tolist() == g["kji"] and r.transpose_kji().size == [2, 2, 3]
+    assert r.transpose_ikj().data.tolist() == g["ikj"] and r.transpose_ikj().size == [3, 2, 2]
+
+
+# ---------------------------------------------------------------- pack / unpack ----
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 100, 264, 511, 600, 1000])
+def test_pack_unpack_vs_oracle(rt, oracle, n):
+    full = oracle.fill_linear(n * n, 4)
+    packed_ref = oracle.to_matrixupper(full, n)
+    packed = rt.MatrixFull.from_vec([n, n], full).to_matrixupper()
+    assert packed.size == n * (n + 1) // 2
+    assert np.array_equal(packed.data, packed_ref)
+    unpacked = packed.to_matrixfull()
+    assert unpacked.size == [n, n]
+    assert np.array_equal(unpacked.data, oracle.to_matrixfull(packed_ref))
+    # round trip: pack(unpack(p)) == p ; unpack is symmetric
+    assert np.array_equal(unpacked.to_matrixupper().data, packed_ref)
+    m = unpacked.data.reshape((n, n), order="F")
+    assert np.array_equal(m, m.T)
+
+
+@pytest.mark.parametrize("n", [4000, 8000])
+def test_pack_unpack_full_size_properties(ctx, n):
+    """BASELINE config E sizes on device buffers: round trip, symmetry and a checksum of checksums."""
+    np_ = n * (n + 1) // 2
+    packed = ctx.empty(np_)
+    ctx.fill_linear(packed, np_, 4, 0, 1.0)
+    full = ctx.empty(n * n)
+    ctx.unpack_upper(packed, n, full)
+    back = ctx.empty(np_)
+    ctx.pack_upper(full, n, back)
+    assert torch.equal(back, packed)
+    f2 = full.view(n, n)  # column-major n x n viewed row-major == transpose; symmetric either way
+    assert torch.equal(f2, f2.t())
+    # diagonal of the full matrix == packed[j(j+1)/2 + j]
+    j = torch.arange(n, device=packed.device)
+    assert torch.equal(torch.diagonal(f2), packed[j * (j + 1) // 2 + j])
+
+
+def test_ri_pack_symm(rt, oracle):
+    for nao, naux in [(7, 5), (33, 9), (100, 40)]:
+        ri = oracle.fill_linear(nao * nao * naux, 2)
+        out = rt.RIFull.from_vec([nao, nao, naux], ri).rifull_to_matfull_symm()
+        assert out.size == [nao * (nao + 1) // 2, naux]
+        assert np.array_equal(out.data, oracle.rifull_to_matfull_symm(ri, nao, naux))
+    big = rt.RIFull.new([600, 600, 3], 0.0)
+    big.data[:] = oracle.fill_linear(big.data.size, 2)
+    assert np.array_equal(big.rifull_to_matfull_symm().data, oracle.rifull_to_matfull_symm(big.data, 600, 3))
+
+
+# ---------------------------------------------------------------- transposes ----
+@pytest.mark.parametrize("shape", [(1, 1, 1), (3, 2, 2), (9, 3, 2), (33, 65, 7), (100, 100, 17), (64, 1, 130)])
+def test_ri_transposes_vs_oracle(rt, oracle, shape):
+    i, j, k = shape
+    d = oracle.fill_linear(i * j * k, 5)
+    r = rt.RIFull.from_vec([i, j, k], d)
+    for which, fn in enumerate([r.transpose_jik, r.transpose_jki, r.transpose_kji, r.transpose_ikj]):
+        assert np.array_equal(fn().data, oracle.ri_transpose(d, i, j, k, which)), (shape, which)
+    # involutions: jik(jik(x)) == x, kji(kji(x)) == x, ikj(ikj(x)) == x
+    assert np.array_equal(r.transpose_jik().transpose_jik().data, d)
+    assert np.array_equal(r.transpose_kji().transpose_kji().data, d)
+    assert np.array_equal(r.transpose_ikj().transpose_ikj().data, d)
+
+
+@pytest.mark.parametrize("shape", [(3, 4), (1, 7), (129, 65), (600, 264)])
+def test_matrix_transpose_vs_oracle(rt, oracle, shape):
+    r, c = shape
+    d = oracle.fill_linear(r * c, 6)
+    t = rt.MatrixFull.from_vec([r, c], d).transpose()
+    assert np.array_equal(t.data, oracle.matrix_transpose(d, r, c))
+    assert np.array_equal(t.transpose().data, d)
+
+
+# ---------------------------------------------------------------- sub-box copies ----
+def test_copy_mm(rt, oracle):
+    src = oracle.fill_linear(13 * 11, 7)
+    for (xl, yl, fxs, fys, txs, tys) in [(5, 4, 2, 3, 1, 0), (13, 11, 0, 0, 0, 0), (1, 1, 12, 10, 16, 8), (0, 3, 0, 0, 0, 0),
+                                         (6, 2, 4, 4, 2, 2)]:
+        dst_ref = oracle.fill_linear(17 * 9, 8)
+        dst = rt.MatrixFull.from_vec([17, 9], dst_ref.copy())
+        if yl + tys > 9:
+            continue
+        oracle.copy_mm(xl, yl, src, 13, 11, fxs, fys, dst_ref, 17, 9, txs, tys)
+        dst.copy_from_matr((txs, txs + xl), (tys, tys + yl), rt.MatrixFull.from_vec([13, 11], src), (fxs, fxs + xl),
+                           (fys, fys + yl))
+        assert np.array_equal(dst.data, dst_ref)
+
+
+@pytest.mark.parametrize("mod", [0, 1, 2])
+def test_copy_mr_and_rm(rt, oracle, mod):
+    X, Y, Z = 6, 5, 4
+    dims = {0: (X, Y, Z), 1: (X, Z, Y), 2: (Y, Z, X)}[mod]   # extents of (x1, x2, x3) for this mode
+    src = oracle.fill_linear(9 * 8, 9)
+    for (l1, l2, f1, f2, t1, t2, x3) in [(3, 2, 1, 2, 1, 1, 2), (dims[0], dims[1], 0, 0, 0, 0, 0), (1, 1, 8, 7, 0, 0, dims[2] - 1)]:
+        if l1 + t1 > dims[0] or l2 + t2 > dims[1] or x3 >= dims[2] or l1 + f1 > 9 or l2 + f2 > 8:
+            continue
+        t_ref = oracle.fill_linear(X * Y * Z, 10)
+        t = rt.RIFull.from_vec([X, Y, Z], t_ref.copy())
+        oracle.copy_mr(l1, l2, src, 9, 8, f1, f2, t_ref, X, Y, Z, t1, t2, x3, mod)
+        t.copy_from_matr((t1, t1 + l1), (t2, t2 + l2), x3, mod, rt.MatrixFull.from_vec([9, 8], src), (f1, f1 + l1),
+                         (f2, f2 + l2))
+        assert np.array_equal(t.data, t_ref), (mod, l1, l2)
+        # and back out of the tensor (copy_rm, reachable through external_libs::matr_copy_from_ri)
+        m_ref = oracle.fill_linear(9 * 8, 11)
+        m = m_ref.copy()
+        oracle.copy_rm(l1, l2, t_ref, X, Y, Z, t1, t2, x3, mod, m_ref, 9, 8, f1, f2)
+        rt.matr_copy_from_ri(t.data, t.size, (t1, t1 + l1), (t2, t2 + l2), x3, mod, m, [9, 8], (f1, f1 + l1), (f2, f2 + l2))
+        assert np.array_equal(m, m_ref), (mod, l1, l2)
+    # unknown mod is a no-op (restmatr.f90:227-237)
+    t0 = oracle.fill_linear(X * Y * Z, 10)
+    t = rt.RIFull.from_vec([X, Y, Z], t0.copy())
+    t.copy_from_matr((0, 2), (0, 2), 0, 7, rt.MatrixFull.from_vec([9, 8], src), (0, 2), (0, 2))
+    assert np.array_equal(t.data, t0)
+
+
+def test_copy_rr(rt, oracle):
+    f = oracle.fill_linear(7 * 6 * 5, 12)
+    for (xl, yl, zl, fs, ts) in [((3, 2, 2), None, None, (1, 2, 1), (0, 1, 3)), ((7, 6, 5), None, None, (0, 0, 0), (0, 0, 0)),
+                                 ((2, 6, 1), None, None, (5, 0, 4), (6, 0, 0))]:
+        xl, yl, zl = xl
+        t_ref = oracle.fill_linear(8 * 7 * 6, 13)
+        t = rt.RIFull.from_vec([8, 7, 6], t_ref.copy())
+        oracle.copy_rr(xl, yl, zl, f, 7, 6, 5, fs[0], fs[1], fs[2], t_ref, 8, 7, 6, ts[0], ts[1], ts[2])
+        t.copy_from_ri((ts[0], ts[0] + xl), (ts[1], ts[1] + yl), (ts[2], ts[2] + zl), rt.RIFull.from_vec([7, 6, 5], f),
+                       (fs[0], fs[0] + xl), (fs[1], fs[1] + yl), (fs[2], fs[2] + zl))
+        assert np.array_equal(t.data, t_ref)
+
+
+def test_device_copies_large(ctx, oracle):
+    """device-pointer copies on a box large enough to exercise the vectorised and the scalar kernels"""
+    fx, fy, fz, tx, ty, tz = 130, 70, 9, 140, 80, 11
+    f = oracle.fill_linear(fx * fy * fz, 14)
+    for (xl, yl, zl, fs, ts) in [(128, 64, 8, (2, 4, 1), (4, 8, 2)), (127, 63, 7, (1, 3, 0), (3, 5, 1))]:
+        t_ref = oracle.fill_linear(tx * ty * tz, 15)
+        td = _dev(ctx, t_ref)
+        oracle.copy_rr(xl, yl, zl, f, fx, fy, fz, fs[0], fs[1], fs[2], t_ref, tx, ty, tz, ts[0], ts[1], ts[2])
+        ctx.copy_rr(xl, yl, zl, _dev(ctx, f), fx, fy, fz, fs[0], fs[1], fs[2], td, tx, ty, tz, ts[0], ts[1], ts[2])
+        assert np.array_equal(td.cpu().numpy(), t_ref)
+    with pytest.raises(Exception):
+        ctx.copy_rr(10, 10, 10, _dev(ctx, f), fx, fy, fz, 125, 0, 0, _dev(ctx, f), fx, fy, fz, 0, 0, 0)  # box outside
+
+
+# ---------------------------------------------------------------- axpy family ----
+def test_axpy_family_bit_exact(rt, oracle):
+    n = 12345
+    for op, a, b in [(0, 0.0, 0.37), (1, -1.25, 0.3333333333333333), (2, 1.0 / 3.0, 0.0), (3, 0.0, 0.0), (4, 0.0, 0.0)]:
+        c = oracle.fill_linear(n, 16); p = oracle.fill_linear(n, 17)
+        c_ref = c.copy()
+        oracle.axpy(op, c_ref, p, a, b)
+        m = rt.MatrixFull.from_vec([n, 1], c.copy()); q = rt.MatrixFull.from_vec([n, 1], p)
+        [lambda: m.self_scaled_add(q, b), lambda: m.self_general_add(q, a, b), lambda: m.self_multiple(a),
+         lambda: m.self_add(q), lambda: m.self_sub(q)][op]()
+        assert np.array_equal(m.data, c_ref), op
+    r = rt.RIFull.from_vec([5, 4, 3], oracle.fill_linear(60, 18))
+    ref = r.data.copy()
+    oracle.axpy(0, ref, oracle.fill_linear(60, 19), 0.0, -2.7)
+    r.self_scaled_add(rt.RIFull.from_vec([5, 4, 3], oracle.fill_linear(60, 19)), -2.7)
+    assert np.array_equal(r.data, ref)
+    # MatrixUpper +/- truncates to the shorter operand (matrixupper.rs:395-420)
+    u = rt.MatrixUpper.from_vec(6, np.arange(6.0)) + rt.MatrixUpper.from_vec(3, np.ones(3))
+    assert u.data.tolist() == [1.0, 2.0, 3.0, 3.0, 4.0, 5.0]
+    u = rt.MatrixUpper.from_vec(6, np.arange(6.0)) - rt.MatrixUpper.from_vec(6, np.ones(6))
+    assert u.data.tolist() == [-1.0, 0.0, 1.0, 2.0, 3.0, 4.0]
+    out = rt.MatrixFull.from_vec([2, 2], [1.0, 2.0, 3.0, 4.0]).scaled_add(rt.MatrixFull.from_vec([2, 2], [1.0, 1.0, 1.0, 1.0]), 0.5)
+    assert out.data.tolist() == [1.5, 2.5, 3.5, 4.5]
+
+
+# ---------------------------------------------------------------- synthetic generators ----
+def test_device_generators_match_oracle(ctx, oracle):
+    v = ctx.empty(10007)
+    ctx.fill_linear(v, 10007, 3, 5, 0.1)
+    assert np.array_equal(v.cpu().numpy(), oracle.fill_linear(10007, 3, 5, 0.1))
+    nb, p_lo, p_hi = 37, 3, 9
+    a = ctx.empty(nb * nb * (p_hi - p_lo))
+    ctx.fill_ri3ao_symm(a, nb, p_lo, p_hi, 1, 1.0)
+    assert np.array_equal(a.cpu().numpy(), oracle.fill_ri3ao_symm(nb, p_lo, p_hi, 1, 1.0))

@@ -1,0 +1,135 @@
+"""The oracle pinned against the reference's own asserted vectors (GV1-GV7) and our derived ones (GV9, GV10),
+plus internal consistency: netlib-loop BLAS vs OpenBLAS, ri_ao2mo_f (restmatr.f90) vs ao2mo_v01 (pure-Rust order)."""
+import numpy as np
+import pytest
+
+from conftest import assert_close_1e10
+
+
+def _gemm_case(o, g):
+    a = np.array(g["a"]); b = np.array(g["b"])
+    c = np.full(g["size_c"][0] * g["size_c"][1], g["c_fill"])
+    o.general_dgemm_f(a, g["size_a"], g["sub_a"][0], g["sub_a"][1], g["opa"], b, g["size_b"], g["sub_b"][0],
+                      g["sub_b"][1], g["opb"], c, g["size_c"], g["sub_c"][0], g["sub_c"][1], g["alpha"], g["beta"])
+    cm = c.reshape(g["size_c"], order="F")
+    r, cc = g["sub_c"]
+    blk = cm[r[0]:r[1], cc[0]:cc[1]].reshape(-1, order="F")
+    outside = cm.copy()
+    outside[r[0]:r[1], cc[0]:cc[1]] = g["c_fill"]
+    return blk, outside
+
+
+@pytest.mark.parametrize("name", ["GV1", "GV2", "GV3"])
+def test_general_dgemm_f_golden(oracle, golden, name):
+    g = golden[name]
+    blk, outside = _gemm_case(oracle, g)
+    assert blk.tolist() == g["expect_block"]
+    assert np.all(outside == g["c_fill"])  # elements outside the block untouched
+
+
+def test_general_dgemm_f_golden_openblas(oracle_blas, golden):
+    for name in ("GV1", "GV2", "GV3"):
+        blk, _ = _gemm_case(oracle_blas, golden[name])
+        assert blk.tolist() == golden[name]["expect_block"]
+
+
+def test_pack_order_gv4(oracle, golden):
+    g = golden["GV4"]
+    assert oracle.to_matrixupper(np.array(g["full"]), g["n"]).tolist() == g["packed"]
+
+
+def test_unpack_gv5(oracle, golden):
+    for case in golden["GV5"]["cases"]:
+        assert oracle.to_matrixfull(np.array(case["packed"])).tolist() == case["full_colmajor"]
+
+
+def test_unpack_edge_cases(oracle):
+    assert oracle.to_matrixfull(np.zeros(4)) is None          # 4 is not triangular -> None
+    assert oracle.to_matrixfull(np.zeros(0)).size == 0        # empty
+    assert oracle.index2d(2, 1, 6) == 4 and oracle.index2d(1, 2, 6) == 4
+    assert oracle.index2d(3, 3, 6) is None
+
+
+def test_transpose_gv7(oracle, golden):
+    g = golden["GV7"]
+    r, c = g["size"]
+    t = oracle.matrix_transpose(np.array(g["data"]), r, c).reshape((c, r), order="F")
+    assert t[:, 2].tolist() == g["transposed_column_2"]
+
+
+def test_ao2mo_gv9(oracle, golden):
+    g = golden["GV9"]
+    nb, _, nx = g["ri_size"]
+    ri = np.full(nb * nb * nx, g["ri_fill"]); c = np.full(nb * nb, g["c_fill"])
+    assert np.all(oracle.ri_ao2mo_f(c, ri, nb, nb, nx) == g["expect_every"])
+    assert np.all(oracle.ao2mo_v01(c, ri, nb, nb, nx) == g["expect_every"])
+
+
+def test_ri_transposes_gv10(oracle, golden):
+    g = golden["GV10"]
+    i, j, k = g["size"]
+    d = np.array(g["data"])
+    for which, name in enumerate(["jik", "jki", "kji", "ikj"]):
+        assert oracle.ri_transpose(d, i, j, k, which).tolist() == [float(v) for v in g[name]], name
+
+
+def test_ao2mo_two_restatements_agree(oracle, oracle_blas):
+    nb, nx = 23, 7
+    ri = oracle.fill_linear(nb * nb * nx, 2)
+    c = oracle.fill_linear(nb * nb, 3, scale=nb ** -0.5)
+    a = oracle.ri_ao2mo_f(c, ri, nb, nb, nx)
+    b = oracle.ao2mo_v01(c, ri, nb, nb, nx)
+    d = oracle_blas.ri_ao2mo_f(c, ri, nb, nb, nx)
+    assert_close_1e10(a, b, "ri_ao2mo_f vs ao2mo_v01")
+    assert_close_1e10(d, b, "ri_ao2mo_f(OpenBLAS) vs ao2mo_v01")
+    # rectangular generalisation collapses to the square one
+    assert np.array_equal(oracle.ri_ao2mo_rect(c, nb, c, nb, ri, nb, nx), a)
+
+
+def test_jk_against_einsum(oracle):
+    nb, nx, no = 11, 5, 3
+    ri = oracle.fill_ri3ao_symm(nb, 0, nx)
+    c = oracle.fill_linear(nb * nb, 3, scale=nb ** -0.5)
+    A = ri.reshape((nb, nb, nx), order="F")
+    Co = c.reshape((nb, nb), order="F")[:, :no]
+    D = 2.0 * Co @ Co.T
+    d = oracle.ri_dp(ri, np.ascontiguousarray(D.reshape(-1, order="F")), nb, nx)
+    assert_close_1e10(d, np.einsum("mnp,mn->p", A, D), "d_P")
+    assert_close_1e10(oracle.ri_j(ri, d, nb, nx), np.einsum("mnp,p->mn", A, d).reshape(-1, order="F"), "J")
+    ct = np.ascontiguousarray((Co * np.sqrt(2.0)).reshape(-1, order="F"))
+    B = np.einsum("mnp,ni->mip", A, Co * np.sqrt(2.0))
+    assert_close_1e10(oracle.ri_k(ri, ct, nb, no, nx), np.einsum("mip,lip->ml", B, B).reshape(-1, order="F"), "K")
+
+
+def test_blas_layers_agree(oracle, oracle_blas):
+    rng = np.random.default_rng(0)
+    m, n, k = 13, 9, 17
+    for ta in "NT":
+        for tb in "NT":
+            a = rng.standard_normal((m, k) if ta == "N" else (k, m)); b = rng.standard_normal((k, n) if tb == "N" else (n, k))
+            af, bf = np.asfortranarray(a).reshape(-1, order="F"), np.asfortranarray(b).reshape(-1, order="F")
+            c0 = rng.standard_normal(m * n)
+            c1, c2 = c0.copy(), c0.copy()
+            oracle.use_blas(False)
+            oracle.dgemm(ta, tb, m, n, k, 0.7, af, a.shape[0], bf, b.shape[0], -0.3, c1, m)
+            oracle_blas.dgemm(ta, tb, m, n, k, 0.7, af, a.shape[0], bf, b.shape[0], -0.3, c2, m)
+            assert_close_1e10(c1, c2, f"dgemm {ta}{tb}")
+            ref = 0.7 * (a if ta == "N" else a.T) @ (b if tb == "N" else b.T) - 0.3 * c0.reshape((m, n), order="F")
+            assert_close_1e10(c1, ref.reshape(-1, order="F"), f"dgemm {ta}{tb} vs numpy")
+
+
+def test_synth_generator_matches_numpy(oracle):
+    # the splitmix64 finaliser of SURVEY 8(d), restated in numpy uint64 arithmetic
+    idx = np.arange(1000, dtype=np.uint64)
+    seed = np.uint64(3)
+    with np.errstate(over="ignore"):
+        z = seed + np.uint64(0x9E3779B97F4A7C15) * (idx + np.uint64(1))
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z ^= z >> np.uint64(31)
+    u = (z >> np.uint64(11)).astype(np.float64) * 2.0 ** -53
+    v = (2.0 * u - 1.0) * 0.25
+    assert np.array_equal(oracle.fill_linear(1000, 3, 0, 0.25), v)
+    a = oracle.fill_ri3ao_symm(6, 2, 4).reshape((6, 6, 2), order="F")
+    assert np.array_equal(a, a.transpose(1, 0, 2))  # symmetric slabs
+    assert a[1, 4, 1] == oracle.lib.orc_synth(1, 1 + 4 * 6 + 3 * 36, 1.0)
