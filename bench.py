@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py -- RI ao2mo + JK build FP64 GFLOP/s on B200 (BASELINE.json metric), next to the reference CPU path.
+
+A "step" is one pass of the hot path over one rank's P-shard of a synthetic RI tensor:
+    ao2mo (square C, reference semantics: 4*nb^3*nx flop)  +  d_P  +  J  +  K  (+ ONE all-reduce each for J, K when N > 1)
+Workload at N=1: BASELINE config C (nb=600, naux=1700, nocc=60; ri3ao 4.9 GB) -- the largest configuration of
+BASELINE.json:configs that fits one GPU together with its square ri3mo and host staging (config D's square ri3mo
+is 124 GB + 124 GB).  N > 1 is weak scaling: every rank holds `nx` slabs (global naux = nx * N, P-sharded exactly
+like shard_range()).  `--config D` selects the north-star shard (nb=1800, 600 slabs/rank = naux 4800 on 8 GPUs).
+
+    python bench.py --gpus N --steps K --warmup W              # our arm (one process per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...    # the reference algorithm on the host cores (rank 0 only)
+
+`value` is device-timed (CUDA events, barrier + synchronize on both sides, max over ranks) with inputs resident in
+HBM; `e2e` goes through the host-pointer C ABI (rb_host_ri_ao2mo_jk: pinned host ri3ao in, host ri3mo/J/K out, H2D
+and D2H inside the timed region).  Inputs (4.9 GB) are larger than L2 (126 MB), so no explicit L2 flush is needed.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CONFIGS = {  # name: (nb, slabs per rank, nocc, description)
+    "A": (100, 400, 20, "A: bench_tensors.rs scale nb=100 naux=400 nocc=20"),
+    "B": (264, 720, 21, "B: benzene/def2-TZVP-sized nb=264 naux=720 nocc=21"),
+    "C": (600, 1700, 60, "C: C20/cc-pVTZ-sized nb=600 naux=1700 nocc=60"),
+    "D": (1800, 600, 180, "D: C60/cc-pVTZ-sized shard nb=1800 naux=4800/8 nocc=180"),
+}
+METRIC = "RI ao2mo + JK build FP64 GFLOP/s"
+UNIT = "GFLOP/s"
+
+
+def flops(nb, nx, no):
+    """algorithmic flop of one step over nx slabs"""
+    return {
+        "ao2mo": 4.0 * nb ** 3 * nx,
+        "k": (2.0 * nb * nb * no + nb * (nb + 1.0) * no) * nx,
+        "dp": 2.0 * nb * nb * nx,
+        "j": 2.0 * nb * nb * nx,
+    }
+
+
+# --------------------------------------------------------------------------------------------------------------
+# reference CPU path (oracle port + OpenBLAS) -- used by --impl reference and by the cpu_baseline leg
+# --------------------------------------------------------------------------------------------------------------
+class CpuPath:
+    def __init__(self, nb, no):
+        import numpy as np
+        from oracle.api import Oracle
+        self.np = np
+        self.o = Oracle()
+        self.cores = os.cpu_count() or 1
+        try:
+            self.cores = len(os.sched_getaffinity(0))
+        except Exception:
+            pass
+        self.have_blas = self.o.load_openblas(threads=self.cores)
+        self.threads = self.o.blas_threads() if self.have_blas else 1
+        self.nb, self.no = nb, no
+        c = self.o.fill_linear(nb * nb, 3, scale=nb ** -0.5)
+        cm = c.reshape((nb, nb), order="F")
+        self.c = c
+        self.dm = np.ascontiguousarray((2.0 * cm[:, :no] @ cm[:, :no].T).reshape(-1, order="F"))
+        self.ct = np.ascontiguousarray((cm[:, :no] * np.sqrt(2.0)).reshape(-1, order="F"))
+        self.ri = None
+        self.ns = 0
+
+    def set_sample(self, slabs):
+        self.ns = int(slabs)
+        self.ri = self.o.fill_ri3ao_symm(self.nb, 0, self.ns)
+
+    def step(self):
+        """reference algorithm on the sample: ri_ao2mo_f (restmatr.f90:158-194) + d_P/J (dgemv) + K (dgemm+dsyrk per slab)"""
+        o, nb, ns = self.o, self.nb, self.ns
+        mo = o.ri_ao2mo_f(self.c, self.ri, nb, nb, ns)
+        d = o.ri_dp(self.ri, self.dm, nb, ns)
+        j = o.ri_j(self.ri, d, nb, ns)
+        k = o.ri_k(self.ri, self.ct, nb, self.no, ns)
+        return mo, d, j, k
+
+    def calibrate(self, target_s, max_slabs):
+        """pick a sample size whose step takes about target_s seconds"""
+        probe = max(1, min(4, max_slabs))
+        self.set_sample(probe)
+        self.step()
+        t0 = time.perf_counter(); self.step(); dt = time.perf_counter() - t0
+        per_slab = max(dt / probe, 1e-6)
+        slabs = int(max(1, min(max_slabs, target_s / per_slab)))
+        self.set_sample(slabs)
+        return slabs
+
+    def describe(self, slabs, nx):
+        return (f"{slabs} of {nx} slabs (nb={self.nb}, nocc={self.no}); ri_ao2mo_f loop (dgemm NN + dgemm TN + strided "
+                f"scatter per slab) + dgemv T/N + per-slab dgemm/dsyrk; {self.o.blas_config()}")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    nb, nx, no, desc = CONFIGS[args.config]
+    cpu = CpuPath(nb, no)
+    slabs = cpu.calibrate(target_s=3.0, max_slabs=nx)
+    for _ in range(args.warmup):
+        cpu.step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu.step()
+    dt = (time.perf_counter() - t0) / max(1, args.steps)
+    f = flops(nb, slabs, no)
+    value = sum(f.values()) / dt / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "impl": "reference",
+        "config": {"workload": desc, "nb": nb, "slabs_per_rank": nx, "nocc": no,
+                   "note": "reference algorithm (oracle port of restmatr.f90 + OpenBLAS) on the host cores; each step is a "
+                           "bounded sample of the per-rank workload, throughput is per-slab so it scales linearly"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu.threads, "kind": "port",
+                         "sample": cpu.describe(slabs, nx)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md "clocks line")
+# --------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 and len(r) >= 8] or [r for _, r in self.rows if len(r) >= 8]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[1]) for r in rows)
+        reasons = []
+        for idx, name in [(4, "hw_slowdown"), (5, "hw_thermal_slowdown"), (6, "sw_thermal_slowdown"), (7, "sw_power_cap")]:
+            if any(r[idx].lower().startswith("active") for r in rows):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": reasons,
+                "power_w_max": max(float(r[3]) for r in rows), "samples": len(rows)}
+
+
+# --------------------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import ctypes as C
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from rest_tensors_b200 import lib
+    from rest_tensors_b200._lib import check
+    from rest_tensors_b200.device import Context, ShardedRI, all_reduce_sum
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs CUDA devices (no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{local}"))
+    dev = f"cuda:{local}"
+    nb, nx, no, desc = CONFIGS[args.config]
+    naux = nx * world
+    ctx = Context(local)
+    sh = ShardedRI(ctx, nb, naux, rank, world).fill_synthetic()
+    assert sh.nx == nx
+    n2 = nb * nb
+    c = ctx.empty(n2); ctx.fill_linear(c, n2, 3, 0, nb ** -0.5)
+    ct = ctx.empty(nb * no); ctx.fill_linear(ct, nb * no, 3, 0, nb ** -0.5); ctx.self_multiple(ct, 2.0 ** 0.5, nb * no)
+    dm = ctx.empty(n2)
+    ctx.dgemm("N", "T", nb, nb, no, 2.0, c, nb, c, nb, 0.0, dm, nb)       # D = 2 C_occ C_occ^T (our own GEMM)
+    mo = ctx.empty(nx * n2); d = ctx.empty(nx); j = ctx.empty(n2); k = ctx.empty(n2)
+    f = flops(nb, nx, no)
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    seg = {"ao2mo": [], "dp": [], "j": [], "k": []}
+
+    def step(record=False):
+        marks = [ev() for _ in range(5)] if record else None
+        if record: marks[0].record()
+        sh.ao2mo(c, nb, c, nb, out=mo)
+        if record: marks[1].record()
+        sh.dp(dm, out=d)
+        if record: marks[2].record()
+        sh.j(d, out=j, reduce=True)
+        if record: marks[3].record()
+        sh.k(ct, no, out=k, reduce=True)
+        if record: marks[4].record()
+        return marks
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # roofline denominators, measured live before the timed region
+    dmma_peak = max(ctx.fp64_peak_probe(0, 100000)[0] for _ in range(2))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak, hbm_src = (peaks["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (of measured)") if "hbm_gbs" in peaks else \
+        (6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)")
+
+    for _ in range(max(args.warmup, 3) if args.warmup >= 0 else 3):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.2)
+    launches0 = ctx.launches
+    barrier()
+    t_wall0 = time.perf_counter()
+    e0, e1 = ev(), ev()
+    e0.record()
+    all_marks = [step(record=True) for _ in range(args.steps)]
+    e1.record()
+    barrier()
+    t_wall1 = time.perf_counter()
+    launches = ctx.launches - launches0
+    ms_total = e0.elapsed_time(e1)
+    tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_step = float(tmax.item()) / args.steps
+    for m in all_marks:
+        for i, name in enumerate(["ao2mo", "dp", "j", "k"]):
+            seg[name].append(m[i].elapsed_time(m[i + 1]))
+    avg = {kname: sum(v) / len(v) for kname, v in seg.items()}
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    total_flop = sum(f.values()) * world
+    value = total_flop / (ms_step * 1e-3) / 1e9
+
+    # ---- e2e through the host-pointer C ABI (pinned host buffers; H2D + D2H inside the timed region) ----
+    ri_h = torch.empty(nx * n2, dtype=torch.float64, pin_memory=True)
+    ri_h.copy_(sh.data)
+    mo_h = torch.empty(nx * n2, dtype=torch.float64, pin_memory=True)
+    c_h, dm_h, ct_h = c.cpu().pin_memory(), dm.cpu().pin_memory(), ct.cpu().pin_memory()
+    d_h = torch.empty(nx, dtype=torch.float64, pin_memory=True)
+    j_h = torch.empty(n2, dtype=torch.float64, pin_memory=True)
+    k_h = torch.empty(n2, dtype=torch.float64, pin_memory=True)
+    torch.cuda.synchronize()
+    P = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+
+    def e2e_step():
+        check(lib.rb_host_ri_ao2mo_jk(P(c_h), nb, P(c_h), nb, P(ri_h), P(mo_h), nb, nx, P(dm_h), P(ct_h), no, P(d_h), P(j_h),
+                                      P(k_h)), "rb_host_ri_ao2mo_jk")
+        if world > 1:  # complete J and K across ranks (host results -> NVLink all-reduce -> host)
+            jk = torch.cat([j_h, k_h]).to(dev, non_blocking=True)
+            all_reduce_sum(jk, world)
+            jk_h = jk.cpu()
+            j_h.copy_(jk_h[:n2]); k_h.copy_(jk_h[n2:])
+
+    e2e_steps = max(2, min(args.steps, 5))
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    dt = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_value = total_flop / float(dt.item()) / 1e9
+    h2d = (nx * n2 + 2 * n2 + nb * no) * 8
+    d2h = (nx * n2 + 2 * n2 + nx) * 8
+    # parity spot check of the e2e results against the device-resident results of the same inputs
+    e2e_ok = bool(torch.allclose(mo_h[: 4096], mo[: 4096].cpu(), rtol=1e-12, atol=1e-14)) and \
+        bool(torch.allclose(k_h, k.cpu(), rtol=1e-10, atol=1e-12))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- cpu_baseline: the reference algorithm on this box's host cores, bounded sample (N == 1 only) ----
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu:
+        cpu = CpuPath(nb, no)
+        slabs = cpu.calibrate(target_s=6.0, max_slabs=nx)
+        cpu.step()
+        t0 = time.perf_counter(); cpu.step(); cdt = time.perf_counter() - t0
+        cpu_baseline = {"value": sum(flops(nb, slabs, no).values()) / cdt / 1e9, "unit": UNIT, "cores": cpu.threads,
+                        "kind": "port", "sample": cpu.describe(slabs, nx)}
+
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(args.config)
+    except Exception:
+        pass
+    gemm_launch_ms = avg["ao2mo"] / 2.0                      # ao2mo = 2 launches of the TMA+DMMA GEMM kernel
+    achieved = (f["ao2mo"] / 2.0) / (gemm_launch_ms * 1e-3) / 1e12
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": desc, "nb": nb, "slabs_per_rank": nx, "naux_global": naux, "nocc": no,
+                   "parallelism": f"P-shard x{world}; all-reduce(sum) of J and K only",
+                   "ao2mo": "square C (reference ri_ao2mo_f semantics), 4*nb^3*nx flop",
+                   "l2": "inputs (ri3ao %.1f GB/rank) larger than L2; no flush needed" % (nx * n2 * 8 / 1e9)},
+        "breakdown_ms": {kname: round(v, 4) for kname, v in avg.items()},
+        "breakdown_rate": {"ao2mo_tflops": f["ao2mo"] / (avg["ao2mo"] * 1e-3) / 1e12,
+                           "k_tflops": f["k"] / (avg["k"] * 1e-3) / 1e12,
+                           "dp_gbs": nx * n2 * 8 / (avg["dp"] * 1e-3) / 1e9, "j_gbs": nx * n2 * 8 / (avg["j"] * 1e-3) / 1e9},
+        "roofline": {"bound": "tensor", "kernel": "rb_gemm_tma_kernel<A_K=1,B_K=1> (ao2mo GEMMs; DMMA.8x8x4 fed by TMA)",
+                     "achieved": achieved, "peak": dmma_peak, "unit": "TFLOP/s", "frac": achieved / dmma_peak,
+                     "peak_source": "live register-resident DMMA.8x8x4 probe on this GPU (MEASURED_PEAKS.json holds only "
+                                    "bf16/HBM; nominal B200 FP64 tensor 37-40 TFLOP/s)",
+                     "flop_per_launch": f["ao2mo"] / 2.0, "launch_ms": gemm_launch_ms, "traffic": traffic},
+        "roofline_hbm": {"bound": "hbm", "kernel": "rb_gemv_t_kernel (d_P) / rb_gemv_n_kernel (J)",
+                         "achieved": nx * n2 * 8 / (avg["dp"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": nx * n2 * 8 / (avg["dp"] * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
+                         "j_achieved": nx * n2 * 8 / (avg["j"] * 1e-3) / 1e9},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "rb_host_ri_ao2mo_jk (host-pointer C ABI; pinned host buffers; 3-stream H2D|compute|D2H pipeline)",
+                "steps": e2e_steps, "matches_device_path": e2e_ok},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    if cpu_baseline is not None:
+        line["cpu_baseline"] = cpu_baseline
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C", choices=sorted(CONFIGS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -48,8 +48,10 @@ int rb_device_count(void);
 
 int rb_ctx_create(int device, rb_ctx **out);
 int rb_ctx_destroy(rb_ctx *ctx);
-/* Run subsequent calls on `cuda_stream` (a cudaStream_t, e.g. torch's current stream); NULL = the ctx's own. */
+/* Run subsequent calls on `cuda_stream` (a cudaStream_t, e.g. torch's current stream; NULL = the legacy default
+ * stream).  A fresh context runs on its own non-blocking stream; rb_ctx_use_own_stream() goes back to it. */
 int rb_ctx_set_stream(rb_ctx *ctx, void *cuda_stream);
+int rb_ctx_use_own_stream(rb_ctx *ctx);
 int rb_ctx_sync(rb_ctx *ctx);
 int rb_ctx_num_sms(rb_ctx *ctx);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
@@ -138,6 +140,11 @@ int rb_host_matrix_transpose(const double *in, int64_t rows, int64_t cols, doubl
 /* Rectangular ao2mo (north-star occ-vir form): out[P + a*nx + b*nx*nl] = sum C_L[mu,a] A[mu,nu,P] C_R[nu,b] */
 int rb_host_ri_ao2mo(const double *c_left, int nl, const double *c_right, int nr, const double *ri3ao, double *out,
                      int nb, int nx);
+/* Fused streaming step over a HOST ri3ao: each P-chunk is uploaded once and feeds ao2mo (ri3mo != NULL), d_P/J
+ * (dm != NULL; d, j may be NULL) and K (ct, k != NULL) -- H2D | DMMA | D2H overlapped on three streams. */
+int rb_host_ri_ao2mo_jk(const double *c_left, int nl, const double *c_right, int nr, const double *ri3ao,
+                        double *ri3mo, int nb, int nx, const double *dm, const double *ct, int no, double *d, double *j,
+                        double *k);
 /* axpy family on host buffers (matrix/mod.rs:545-648, ri.rs:345-354, matrixupper.rs:395-420):
  * op 0: c += p*b   1: c = c*a + p*b   2: c *= a   3: c += p   4: c -= p   (unfused mul-then-add, bit-exact) */
 int rb_host_axpy(int op, double *c, const double *p, double a, double b, int64_t n);

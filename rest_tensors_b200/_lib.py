@@ -38,6 +38,7 @@ SIGNATURES = {
     "rb_ctx_create": (C.c_int, [C.c_int, C.POINTER(c_vp)]),
     "rb_ctx_destroy": (C.c_int, [c_vp]),
     "rb_ctx_set_stream": (C.c_int, [c_vp, c_vp]),
+    "rb_ctx_use_own_stream": (C.c_int, [c_vp]),
     "rb_ctx_sync": (C.c_int, [c_vp]),
     "rb_ctx_num_sms": (C.c_int, [c_vp]),
     "rb_ctx_launch_count": (c_i64, [c_vp]),
@@ -75,6 +76,8 @@ SIGNATURES = {
     "rb_host_ri_transpose": (C.c_int, [c_vp, c_i64, c_i64, c_i64, C.c_int, c_vp]),
     "rb_host_matrix_transpose": (C.c_int, [c_vp, c_i64, c_i64, c_vp]),
     "rb_host_ri_ao2mo": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int, c_vp, c_vp, C.c_int, C.c_int]),
+    "rb_host_ri_ao2mo_jk": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int, c_vp, c_vp, C.c_int, C.c_int, c_vp, c_vp, C.c_int,
+                                      c_vp, c_vp, c_vp]),
     "rb_host_axpy": (C.c_int, [C.c_int, c_vp, c_vp, C.c_double, C.c_double, c_i64]),
     "rb_host_ri_dp": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, C.c_int]),
     "rb_host_ri_j": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, C.c_int]),

@@ -75,7 +75,14 @@ extern "C" int rb_ctx_destroy(rb_ctx *ctx)
 extern "C" int rb_ctx_set_stream(rb_ctx *ctx, void *cuda_stream)
 {
     RB_REQUIRE(ctx, "rb_ctx_set_stream: ctx is NULL");
-    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    ctx->stream = (cudaStream_t)cuda_stream; // NULL is the legacy default stream (what torch uses by default)
+    return RB_OK;
+}
+
+extern "C" int rb_ctx_use_own_stream(rb_ctx *ctx)
+{
+    RB_REQUIRE(ctx, "rb_ctx_use_own_stream: ctx is NULL");
+    ctx->stream = ctx->own_stream;
     return RB_OK;
 }
 

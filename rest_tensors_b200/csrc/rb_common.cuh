@@ -92,6 +92,9 @@ int rb_symmetrize(rb_ctx *ctx, double *c, i64 n, i64 ldc, bool from_upper);
 // y = beta-scaled / zero helper
 int rb_scale_or_zero(rb_ctx *ctx, double *y, i64 n, i64 inc, double beta);
 
+// rb_ri.cu: upper triangle of k (+)= sum_P (A_P ct)(A_P ct)^T over nx slabs (beta 0 overwrite / 1 accumulate)
+int rb_ri_k_upper(rb_ctx *ctx, const double *ri3ao, const double *ct, i64 no, double *k, i64 nb, i64 nx, double beta);
+
 // Default (process-wide) context for the host-pointer entry points.
 rb_ctx *rb_default_ctx(void);
 std::mutex &rb_default_mutex(void);

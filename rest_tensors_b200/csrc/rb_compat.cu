@@ -107,31 +107,46 @@ struct Pipe {
     }
 };
 
-int host_ao2mo(const double *cl, int nl, const double *cr, int nr, const double *ri3ao, double *out, int nb_, int nx_)
+// One streaming pass over the host ri3ao: every P-chunk is uploaded ONCE and feeds ao2mo (if out != NULL) and the
+// d_P / J / K builds (if dm / ct != NULL); J and K accumulate across chunks on the device.
+int host_ri_stream(const double *cl, int nl, const double *cr, int nr, const double *ri3ao, double *out, int nb_, int nx_,
+                   const double *dm, const double *ct, int no, double *d_out, double *j_out, double *k_out)
 {
-    RB_REQUIRE(nl >= 0 && nr >= 0 && nb_ >= 0 && nx_ >= 0, "ao2mo: negative dimension");
+    RB_REQUIRE(nl >= 0 && nr >= 0 && nb_ >= 0 && nx_ >= 0 && no >= 0, "ri stream: negative dimension");
     const i64 nb = nb_, nx = nx_;
-    if (nx == 0 || nl == 0 || nr == 0) return RB_OK;
+    const bool do_mo = out != nullptr && nl > 0 && nr > 0;
+    const bool do_j = dm != nullptr && (d_out != nullptr || j_out != nullptr);
+    const bool do_k = ct != nullptr && k_out != nullptr && no > 0;
+    if (nx == 0 || !(do_mo || do_j || do_k)) return RB_OK;
     HOST_CTX(op);
     rb_ctx *ctx = op.ctx;
     // chunk of P slabs staged per pipeline step: large enough for full 128-row MMA tiles along P, small enough
     // to overlap the PCIe transfers with compute
     i64 pc = 256;
-    const i64 slab_in = nb * nb, slab_out = (i64)nl * nr;
+    const i64 slab_in = nb * nb, slab_out = do_mo ? (i64)nl * nr : 0;
     while (pc > 8 && pc * (slab_in + slab_out) * 8 * 2 > ((i64)6 << 30)) pc >>= 1;
     if (pc > nx) pc = nx;
-    double *d_cl, *d_cr, *d_in[2], *d_out[2];
-    RB_TRY(op.alloc(nb * nl, &d_cl));
+    double *d_cl = nullptr, *d_cr = nullptr, *d_in[2], *d_mo[2] = {nullptr, nullptr};
+    double *d_dm = nullptr, *d_ct = nullptr, *d_d = nullptr, *d_j = nullptr, *d_k = nullptr;
     const bool same_c = (cl == cr && nl == nr);
-    if (same_c) d_cr = d_cl; else RB_TRY(op.alloc(nb * nr, &d_cr));
+    if (do_mo) {
+        RB_TRY(op.alloc(nb * nl, &d_cl));
+        if (same_c) d_cr = d_cl; else RB_TRY(op.alloc(nb * nr, &d_cr));
+    }
     for (int i = 0; i < 2; ++i) {
         RB_TRY(op.alloc(pc * slab_in, &d_in[i]));
-        RB_TRY(op.alloc(pc * slab_out, &d_out[i]));
+        if (do_mo) RB_TRY(op.alloc(pc * slab_out, &d_mo[i]));
     }
+    if (do_j) { RB_TRY(op.alloc(slab_in, &d_dm)); RB_TRY(op.alloc(nx, &d_d)); RB_TRY(op.alloc(slab_in, &d_j)); }
+    if (do_k) { RB_TRY(op.alloc(nb * no, &d_ct)); RB_TRY(op.alloc(slab_in, &d_k)); }
     Pipe pipe;
     RB_TRY(pipe.init());
-    RB_TRY(op.up(d_cl, cl, nb * nl));
-    if (!same_c) RB_TRY(op.up(d_cr, cr, nb * nr));
+    if (do_mo) {
+        RB_TRY(op.up(d_cl, cl, nb * nl));
+        if (!same_c) RB_TRY(op.up(d_cr, cr, nb * nr));
+    }
+    if (do_j) RB_TRY(op.up(d_dm, dm, slab_in));
+    if (do_k) RB_TRY(op.up(d_ct, ct, nb * no));
     int step = 0;
     for (i64 p0 = 0; p0 < nx; p0 += pc, ++step) {
         const int s = step & 1;
@@ -145,18 +160,37 @@ int host_ao2mo(const double *cl, int nl, const double *cr, int nr, const double 
         // compute needs the chunk in HBM and the previous D2H out of d_out[s]
         RB_CUDA(cudaStreamWaitEvent(ctx->stream, pipe.in_done[s], 0));
         if (step >= 2) RB_CUDA(cudaStreamWaitEvent(ctx->stream, pipe.out_done[s], 0));
-        RB_TRY(rb_ri_ao2mo(ctx, d_cl, nl, d_cr, nr, d_in[s], d_out[s], nb_, (int)pn, pn));
+        if (do_mo) RB_TRY(rb_ri_ao2mo(ctx, d_cl, nl, d_cr, nr, d_in[s], d_mo[s], nb_, (int)pn, pn));
+        if (do_j && slab_in > 0) {
+            RB_TRY(rb_ri_dp(ctx, d_in[s], d_dm, d_d + p0, nb_, (int)pn));
+            RB_TRY(rb_dgemv(ctx, 'N', (int)slab_in, (int)pn, 1.0, d_in[s], slab_in, d_d + p0, 1, p0 == 0 ? 0.0 : 1.0, d_j, 1));
+        }
+        if (do_k && slab_in > 0) RB_TRY(rb_ri_k_upper(ctx, d_in[s], d_ct, no, d_k, nb, pn, p0 == 0 ? 0.0 : 1.0));
         RB_CUDA(cudaEventRecord(pipe.comp_done[s], ctx->stream));
-        // D2H: rows of pn doubles into the P-fastest host tensor (pitch nx)
-        RB_CUDA(cudaStreamWaitEvent(pipe.s_out, pipe.comp_done[s], 0));
-        RB_CUDA(cudaMemcpy2DAsync(out + p0, (size_t)nx * 8, d_out[s], (size_t)pn * 8, (size_t)pn * 8, (size_t)slab_out,
-                                  cudaMemcpyDeviceToHost, pipe.s_out));
-        RB_CUDA(cudaEventRecord(pipe.out_done[s], pipe.s_out));
+        if (do_mo) {
+            // D2H: rows of pn doubles into the P-fastest host tensor (pitch nx)
+            RB_CUDA(cudaStreamWaitEvent(pipe.s_out, pipe.comp_done[s], 0));
+            RB_CUDA(cudaMemcpy2DAsync(out + p0, (size_t)nx * 8, d_mo[s], (size_t)pn * 8, (size_t)pn * 8, (size_t)slab_out,
+                                      cudaMemcpyDeviceToHost, pipe.s_out));
+            RB_CUDA(cudaEventRecord(pipe.out_done[s], pipe.s_out));
+        }
     }
+    if (do_k && slab_in > 0) RB_TRY(rb_symmetrize(ctx, d_k, nb, nb, true));
+    if (do_j) {
+        if (d_out) RB_TRY(op.down(d_out, d_d, nx));
+        if (j_out) RB_TRY(op.down(j_out, d_j, slab_in));
+    }
+    if (do_k) RB_TRY(op.down(k_out, d_k, slab_in));
     RB_CUDA(cudaStreamSynchronize(pipe.s_out));
     RB_CUDA(cudaStreamSynchronize(pipe.s_in));
     RB_CUDA(cudaStreamSynchronize(ctx->stream));
     return RB_OK;
+}
+
+int host_ao2mo(const double *cl, int nl, const double *cr, int nr, const double *ri3ao, double *out, int nb, int nx)
+{
+    if (nx == 0 || nl == 0 || nr == 0) return RB_OK;
+    return host_ri_stream(cl, nl, cr, nr, ri3ao, out, nb, nx, nullptr, nullptr, 0, nullptr, nullptr, nullptr);
 }
 
 int host_gemm_block(const double *a, i64 rows_a, i64 sra, i64 lra, i64 sca, i64 lca, char opa, const double *b,
@@ -374,6 +408,13 @@ extern "C" int rb_host_ri_ao2mo(const double *c_left, int nl, const double *c_ri
                                 double *out, int nb, int nx)
 {
     return host_ao2mo(c_left, nl, c_right, nr, ri3ao, out, nb, nx);
+}
+
+extern "C" int rb_host_ri_ao2mo_jk(const double *c_left, int nl, const double *c_right, int nr, const double *ri3ao,
+                                   double *ri3mo, int nb, int nx, const double *dm, const double *ct, int no, double *d,
+                                   double *j, double *k)
+{
+    return host_ri_stream(c_left, nl, c_right, nr, ri3ao, ri3mo, nb, nx, dm, ct, no, d, j, k);
 }
 
 extern "C" int rb_host_dgemm(char ta, char tb, int m, int n, int k, double alpha, const double *a, int lda,

@@ -98,16 +98,9 @@ extern "C" int rb_ri_j(rb_ctx *ctx, const double *ri3ao, const double *d, double
     return rb_dgemv(ctx, 'N', (int)m, nx, 1.0, ri3ao, m, d, 1, 0.0, j, 1);
 }
 
-extern "C" int rb_ri_k(rb_ctx *ctx, const double *ri3ao, const double *ct, int no_, double *k, int nb_, int nx_)
+// Upper triangle of k (+)= sum_P Y_P Y_P^T over the given slabs (beta = 0 overwrites, 1 accumulates); no mirroring.
+int rb_ri_k_upper(rb_ctx *ctx, const double *ri3ao, const double *ct, i64 no, double *k, i64 nb, i64 nx, double beta)
 {
-    RB_REQUIRE(ctx, "rb_ri_k: ctx is NULL");
-    RB_REQUIRE(no_ >= 0 && nb_ >= 0 && nx_ >= 0, "rb_ri_k: negative dimension");
-    const i64 nb = nb_, nx = nx_, no = no_;
-    if (nb == 0) return RB_OK;
-    RB_REQUIRE(k, "rb_ri_k: k is NULL");
-    RB_CUDA(cudaSetDevice(ctx->device));
-    if (nx == 0 || no == 0) return rb_scale_or_zero(ctx, k, nb * nb, 1, 0.0);
-    RB_REQUIRE(ct && ri3ao, "rb_ri_k: NULL input");
     const i64 pc = pick_chunk(nx, nb * no * 8, ws_budget_bytes(ctx));
     RB_REQUIRE(no * pc <= 2147483647LL, "rb_ri_k: chunk too large");
     void *ws;
@@ -119,9 +112,23 @@ extern "C" int rb_ri_k(rb_ctx *ctx, const double *ri3ao, const double *ct, int n
         RB_TRY(rb_gemm_core(ctx, false, false, nb, no, nb, 1.0, ri3ao + p0 * nb * nb, nb, nb * nb, ct, nb, 0, 0.0, y, nb,
                             nb * no, pn, 0));
         // K(upper) (+)= Y Y^T : SYRK 'U','N' with k = no*pn
-        RB_TRY(rb_gemm_core(ctx, false, true, nb, nb, no * pn, 1.0, y, nb, 0, y, nb, 0, p0 == 0 ? 0.0 : 1.0, k, nb, 0, 1,
+        RB_TRY(rb_gemm_core(ctx, false, true, nb, nb, no * pn, 1.0, y, nb, 0, y, nb, 0, p0 == 0 ? beta : 1.0, k, nb, 0, 1,
                             1));
     }
+    return RB_OK;
+}
+
+extern "C" int rb_ri_k(rb_ctx *ctx, const double *ri3ao, const double *ct, int no_, double *k, int nb_, int nx_)
+{
+    RB_REQUIRE(ctx, "rb_ri_k: ctx is NULL");
+    RB_REQUIRE(no_ >= 0 && nb_ >= 0 && nx_ >= 0, "rb_ri_k: negative dimension");
+    const i64 nb = nb_, nx = nx_, no = no_;
+    if (nb == 0) return RB_OK;
+    RB_REQUIRE(k, "rb_ri_k: k is NULL");
+    RB_CUDA(cudaSetDevice(ctx->device));
+    if (nx == 0 || no == 0) return rb_scale_or_zero(ctx, k, nb * nb, 1, 0.0);
+    RB_REQUIRE(ct && ri3ao, "rb_ri_k: NULL input");
+    RB_TRY(rb_ri_k_upper(ctx, ri3ao, ct, no, k, nb, nx, 0.0));
     return rb_symmetrize(ctx, k, nb, nb, true);
 }
 

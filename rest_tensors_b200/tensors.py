@@ -510,6 +510,21 @@ class RIFull:
                                    nx), "ao2mo_rect")
         return out
 
+    def ao2mo_jk(self, eigenvector: MatrixFull, dm: MatrixFull, ct: MatrixFull, ri3mo: Optional["RIFull"] = None):
+        """One streaming pass over this (host) tensor: ao2mo + d_P + J + K with every P-chunk uploaded once
+        (H2D | DMMA GEMMs | D2H overlapped).  Returns (ri3mo, d, J, K).  Not in the reference: REST makes the
+        equivalent calls one by one (ao2mo, then _dgemv/_dgemm/_dsyrk per slab)."""
+        nb, ns, nx, no = eigenvector.size[0], eigenvector.size[1], self.size[2], ct.size[1]
+        if ri3mo is None:
+            ri3mo = RIFull.new([nx, ns, ns], 0.0)
+        d = np.zeros(nx, dtype=np.float64)
+        j = MatrixFull.new([nb, nb], 0.0)
+        k = MatrixFull.new([nb, nb], 0.0)
+        check(lib.rb_host_ri_ao2mo_jk(_ptr(eigenvector.data), ns, _ptr(eigenvector.data), ns, _ptr(self.data),
+                                      _ptr(ri3mo.data), nb, nx, _ptr(dm.data), _ptr(ct.data), no, _ptr(d), _ptr(j.data),
+                                      _ptr(k.data)), "ao2mo_jk")
+        return ri3mo, d, j, k
+
     # -- slab copies (ri.rs:410-433) --
     def copy_from_ri(self, range_x: Range, range_y: Range, range_z: Range, from_ri: "RIFull", f_range_x: Range,
                      f_range_y: Range, f_range_z: Range) -> None:

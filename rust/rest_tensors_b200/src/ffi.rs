@@ -1,0 +1,57 @@
+//! Raw declarations of include/rest_b200.h (status-returning part).  0 == RB_OK.
+use std::ffi::{c_char, c_double, c_int, c_void};
+
+#[repr(C)]
+pub struct RbCtx { _private: [u8; 0] }
+
+extern "C" {
+    pub fn rb_last_error() -> *const c_char;
+    pub fn rb_ctx_create(device: c_int, out: *mut *mut RbCtx) -> c_int;
+    pub fn rb_ctx_destroy(ctx: *mut RbCtx) -> c_int;
+    pub fn rb_ctx_sync(ctx: *mut RbCtx) -> c_int;
+    pub fn rb_dev_alloc(ctx: *mut RbCtx, bytes: i64, out: *mut *mut c_void) -> c_int;
+    pub fn rb_dev_free(ctx: *mut RbCtx, p: *mut c_void) -> c_int;
+    pub fn rb_host_alloc_pinned(bytes: i64, out: *mut *mut c_void) -> c_int;
+    pub fn rb_host_free_pinned(p: *mut c_void) -> c_int;
+    pub fn rb_memcpy_h2d(ctx: *mut RbCtx, dst: *mut c_void, src: *const c_void, bytes: i64) -> c_int;
+    pub fn rb_memcpy_d2h(ctx: *mut RbCtx, dst: *mut c_void, src: *const c_void, bytes: i64) -> c_int;
+
+    // host-pointer BLAS / layout wrappers
+    pub fn rb_host_dgemm(ta: c_char, tb: c_char, m: c_int, n: c_int, k: c_int, alpha: c_double, a: *const c_double,
+                         lda: c_int, b: *const c_double, ldb: c_int, beta: c_double, c: *mut c_double, ldc: c_int) -> c_int;
+    pub fn rb_host_dsyrk(uplo: c_char, trans: c_char, n: c_int, k: c_int, alpha: c_double, a: *const c_double, lda: c_int,
+                         beta: c_double, c: *mut c_double, ldc: c_int) -> c_int;
+    pub fn rb_host_dgemv(trans: c_char, m: c_int, n: c_int, alpha: c_double, a: *const c_double, lda: c_int,
+                         x: *const c_double, incx: c_int, beta: c_double, y: *mut c_double, incy: c_int) -> c_int;
+    pub fn rb_host_dsymm(side: c_char, uplo: c_char, m: c_int, n: c_int, alpha: c_double, a: *const c_double, lda: c_int,
+                         b: *const c_double, ldb: c_int, beta: c_double, c: *mut c_double, ldc: c_int) -> c_int;
+    pub fn rb_host_to_matrixupper(full: *const c_double, n: i64, packed: *mut c_double) -> c_int;
+    pub fn rb_host_to_matrixfull(packed: *const c_double, len: i64, full: *mut c_double) -> c_int;
+    pub fn rb_host_ri_pack_symm(ri: *const c_double, nao: i64, naux: i64, out: *mut c_double) -> c_int;
+    pub fn rb_host_ri_transpose(inp: *const c_double, i: i64, j: i64, k: i64, which: c_int, out: *mut c_double) -> c_int;
+    pub fn rb_host_matrix_transpose(inp: *const c_double, rows: i64, cols: i64, out: *mut c_double) -> c_int;
+    pub fn rb_host_axpy(op: c_int, c: *mut c_double, p: *const c_double, a: c_double, b: c_double, n: i64) -> c_int;
+    pub fn rb_host_ri_ao2mo(cl: *const c_double, nl: c_int, cr: *const c_double, nr: c_int, ri3ao: *const c_double,
+                            out: *mut c_double, nb: c_int, nx: c_int) -> c_int;
+    pub fn rb_host_ri_ao2mo_jk(cl: *const c_double, nl: c_int, cr: *const c_double, nr: c_int, ri3ao: *const c_double,
+                               ri3mo: *mut c_double, nb: c_int, nx: c_int, dm: *const c_double, ct: *const c_double,
+                               no: c_int, d: *mut c_double, j: *mut c_double, k: *mut c_double) -> c_int;
+    pub fn rb_host_ri_dp(ri3ao: *const c_double, dm: *const c_double, d: *mut c_double, nb: c_int, nx: c_int) -> c_int;
+    pub fn rb_host_ri_j(ri3ao: *const c_double, d: *const c_double, j: *mut c_double, nb: c_int, nx: c_int) -> c_int;
+    pub fn rb_host_ri_k(ri3ao: *const c_double, ct: *const c_double, no: c_int, k: *mut c_double, nb: c_int, nx: c_int) -> c_int;
+
+    // device-resident API (device pointers)
+    pub fn rb_ri_ao2mo(ctx: *mut RbCtx, cl: *const c_double, nl: c_int, cr: *const c_double, nr: c_int,
+                       ri3ao: *const c_double, out: *mut c_double, nb: c_int, nx: c_int, out_ldp: i64) -> c_int;
+    pub fn rb_ri_dp(ctx: *mut RbCtx, ri3ao: *const c_double, dm: *const c_double, d: *mut c_double, nb: c_int, nx: c_int) -> c_int;
+    pub fn rb_ri_j(ctx: *mut RbCtx, ri3ao: *const c_double, d: *const c_double, j: *mut c_double, nb: c_int, nx: c_int) -> c_int;
+    pub fn rb_ri_k(ctx: *mut RbCtx, ri3ao: *const c_double, ct: *const c_double, no: c_int, k: *mut c_double, nb: c_int, nx: c_int) -> c_int;
+}
+
+/// Turn a non-zero status into the panic the reference's wrappers raise on bad shapes.
+pub fn check(status: c_int, what: &str) {
+    if status != 0 {
+        let msg = unsafe { std::ffi::CStr::from_ptr(rb_last_error()) }.to_string_lossy().into_owned();
+        panic!("{} failed (status {}): {}", what, status, msg);
+    }
+}

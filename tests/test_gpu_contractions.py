@@ -299,6 +299,20 @@ def test_jk_full_size_properties(ctx):
     assert rel_err(ksum.cpu().numpy(), k.cpu().numpy()) < 1e-12
 
 
+def test_fused_streaming_step(rt, oracle_blas):
+    """ao2mo_jk: one upload per P-chunk feeding ao2mo, d_P, J (accumulated) and K (accumulated), several chunks."""
+    nb, nx, no = 40, 600, 6
+    ri, c, dm, ct = _inputs(oracle_blas, nb, nx, no, True)
+    mo, d, j, k = rt.RIFull.from_vec([nb, nb, nx], ri).ao2mo_jk(rt.MatrixFull.from_vec([nb, nb], c),
+                                                                   rt.MatrixFull.from_vec([nb, nb], dm),
+                                                                   rt.MatrixFull.from_vec([nb, no], ct))
+    d_ref = oracle_blas.ri_dp(ri, dm, nb, nx)
+    assert_close_1e10(mo.data, oracle_blas.ri_ao2mo_f(c, ri, nb, nb, nx), "fused ao2mo")
+    assert_close_1e10(d, d_ref, "fused d_P")
+    assert_close_1e10(j.data, oracle_blas.ri_j(ri, d_ref, nb, nx), "fused J")
+    assert_close_1e10(k.data, oracle_blas.ri_k(ri, ct, nb, no, nx), "fused K")
+
+
 # ---------------------------------------------------------------- special_dgemm_f_01 ----
 def test_special_dgemm_f_01(rt, oracle_blas):
     X, Y, Z = 12, 7, 10
