@@ -50,6 +50,7 @@ struct rb_ctx {
     cudaStream_t stream = nullptr; // the stream calls run on (own_stream or the caller's)
     void *ws[4] = {nullptr, nullptr, nullptr, nullptr}; // grow-only workspaces (slot 0: RI ops, 1: GEMM split-K, 2: host staging, 3: probes)
     i64 ws_bytes[4] = {0, 0, 0, 0};
+    i64 ws_budget = 0;             // cached workspace budget (bytes), 0 = not yet queried
     i64 launches = 0;
     int gemm_path = 0;
     rb_encode_tiled_fn encode_tiled = nullptr;

@@ -129,6 +129,61 @@ __device__ __forceinline__ void decode_item(const GemmParams &p, i64 item, i64 &
     }
 }
 
+// One 32-deep k stage for a warp that owns NI x NJ 16x16 blocks (compile-time, so that every DMMA is unpredicated:
+// predicated mma.sync costs a WARPSYNC per group).  12 LDS.128 feed 64 DMMAs per k8 block in the full 2 x 4 case.
+template <bool A_K, bool B_K, int NI, int NJ>
+__device__ __forceinline__ void consume_stage(double (&acc)[2][2][4][2][2], uint32_t sa, uint32_t sb,
+                                              const uint32_t (&a_off)[2], const uint32_t (&b_off)[2])
+{
+#pragma unroll
+    for (int kb = 0; kb < BK / 8; ++kb) {
+        double af[NI][2][2]; // [i][tile e/o][mma 0/1]
+        double bf[NJ][2][2]; // [j][tile e/o][mma 0/1]
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            if (A_K) {
+#pragma unroll
+                for (int pa = 0; pa < 2; ++pa) {
+                    double2 v = lds128(sa + kb * (BM * 64) + i * (16 * 64) + a_off[pa]);
+                    af[i][pa][0] = v.x; af[i][pa][1] = v.y;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    double2 v = lds128(sa + i * (BK * 128) + kb * (8 * 128) + a_off[q]);
+                    af[i][0][q] = v.x; af[i][1][q] = v.y;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            if (B_K) {
+#pragma unroll
+                for (int pb = 0; pb < 2; ++pb) {
+                    double2 v = lds128(sb + kb * (BN * 64) + j * (16 * 64) + b_off[pb]);
+                    bf[j][pb][0] = v.x; bf[j][pb][1] = v.y;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    double2 v = lds128(sb + j * (BK * 128) + kb * (8 * 128) + b_off[q]);
+                    bf[j][0][q] = v.x; bf[j][1][q] = v.y;
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int i = 0; i < NI; ++i)
+#pragma unroll
+                for (int pa = 0; pa < 2; ++pa)
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j)
+#pragma unroll
+                        for (int pb = 0; pb < 2; ++pb) dmma(acc[i][pa][j][pb], af[i][pa][q], bf[j][pb][q]);
+    }
+}
+
 // ---- the TMA + DMMA kernel --------------------------------------------------------------------------------------
 template <bool A_K, bool B_K>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -194,11 +249,10 @@ rb_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
     // ===================== consumers =====================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-    const int wm = warp & 1, wn = warp >> 1; // 2 x 4 warps; 16-row blocks are interleaved across warps
     const int g = lane >> 2, t = lane & 3;
     const int x = A_K ? (g & 1) : 0;
 
-    // per-thread byte offsets of the fragment reads inside a stage (k8-block and row-block offsets are immediates)
+    // per-thread byte offsets of the fragment reads inside a 16-row block (k8-block / block offsets are added per use)
     uint32_t a_off[2], b_off[2];
     if (A_K) {
         a_off[0] = (uint32_t)((2 * g + x) * 64 + t * 16);       // tile e : row 2g + x
@@ -223,67 +277,50 @@ rb_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const i64 k_begin = sp * p.kper;
         const i64 k_end = (k_begin + p.kper < p.k) ? k_begin + p.kper : p.k;
 
-        double acc[4][2][2][2][2]; // [row block i][row tile e/o][col block j][col tile e/o][2]
+        // Valid 16x16 blocks of this tile (edge tiles are ragged; TMA zero-fills the rest) and this warp's rectangle
+        // of them.  The 8 warps form a gm x gn grid chosen per tile so that every warp holds at most 2 x 4 blocks and
+        // the busiest warp has as little work as possible: 4 x 2 for full tiles, 8 x 1 / 1 x 8 / 2 x 4 for thin
+        // ones.  Cost of a tile is therefore proportional to its valid blocks, not to 128 x 128.
+        const i64 mrem = p.m - tm * BM, nrem = p.n - tn * BN;
+        const int mb = mrem >= BM ? BM / 16 : (int)((mrem + 15) >> 4);
+        const int nbk = nrem >= BN ? BN / 16 : (int)((nrem + 15) >> 4);
+        int gm = 4, rpg = 2, cpg = 4, best = 1 << 30;
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int cand = 8; cand >= 1; cand >>= 1) {
+            const int r = (mb + cand - 1) / cand, c = (nbk + (8 / cand) - 1) / (8 / cand);
+            if (r <= 2 && c <= 4 && r * c < best) { best = r * c; gm = cand; rpg = r; cpg = c; }
+        }
+        const int gi = warp % gm, gj = warp / gm;
+        const int rb0 = gi * rpg, cb0 = gj * cpg;
+        int ni = mb - rb0; ni = ni < 0 ? 0 : (ni > rpg ? rpg : ni);
+        int nj = nbk - cb0; nj = nj < 0 ? 0 : (nj > cpg ? cpg : nj);
+        if (ni == 0 || nj == 0) { ni = 0; nj = 0; }
+        const uint32_t a_blk = (uint32_t)rb0 * (A_K ? (16 * 64) : (BK * 128));
+        const uint32_t b_blk = (uint32_t)cb0 * (B_K ? (16 * 64) : (BK * 128));
+
+        double acc[2][2][4][2][2]; // [row block i][row tile e/o][col block j][col tile e/o][2]
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
 #pragma unroll
             for (int pa = 0; pa < 2; ++pa)
 #pragma unroll
-                for (int j = 0; j < 2; ++j)
+                for (int j = 0; j < 4; ++j)
 #pragma unroll
                     for (int pb = 0; pb < 2; ++pb) { acc[i][pa][j][pb][0] = 0.0; acc[i][pa][j][pb][1] = 0.0; }
 
         for (i64 k0 = k_begin; k0 < k_end; k0 += BK) {
             mbar_wait(bar_base + 8 * stage, phase);
-            const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_TILE_BYTES;
-#pragma unroll
-            for (int kb = 0; kb < BK / 8; ++kb) {
-                double af[4][2][2]; // [i][tile e/o][mma 0/1]
-                double bf[2][2][2]; // [j][tile e/o][mma 0/1]
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int blk = wm + 2 * i;
-                    if (A_K) {
-#pragma unroll
-                        for (int pa = 0; pa < 2; ++pa) {
-                            double2 v = lds128(sa + kb * (BM * 64) + blk * (16 * 64) + a_off[pa]);
-                            af[i][pa][0] = v.x; af[i][pa][1] = v.y;
-                        }
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 2; ++q) {
-                            double2 v = lds128(sa + blk * (BK * 128) + kb * (8 * 128) + a_off[q]);
-                            af[i][0][q] = v.x; af[i][1][q] = v.y;
-                        }
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const int blk = wn + 4 * j;
-                    if (B_K) {
-#pragma unroll
-                        for (int pb = 0; pb < 2; ++pb) {
-                            double2 v = lds128(sb + kb * (BN * 64) + blk * (16 * 64) + b_off[pb]);
-                            bf[j][pb][0] = v.x; bf[j][pb][1] = v.y;
-                        }
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 2; ++q) {
-                            double2 v = lds128(sb + blk * (BK * 128) + kb * (8 * 128) + b_off[q]);
-                            bf[j][0][q] = v.x; bf[j][1][q] = v.y;
-                        }
-                    }
-                }
-#pragma unroll
-                for (int q = 0; q < 2; ++q)
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-#pragma unroll
-                        for (int pa = 0; pa < 2; ++pa)
-#pragma unroll
-                            for (int j = 0; j < 2; ++j)
-#pragma unroll
-                                for (int pb = 0; pb < 2; ++pb) dmma(acc[i][pa][j][pb], af[i][pa][q], bf[j][pb][q]);
+            const uint32_t sa = smem_base + stage * STAGE_BYTES + a_blk, sb = smem_base + stage * STAGE_BYTES + A_TILE_BYTES + b_blk;
+            switch (ni * 8 + nj) { // warp-uniform
+            case 2 * 8 + 4: consume_stage<A_K, B_K, 2, 4>(acc, sa, sb, a_off, b_off); break;
+            case 2 * 8 + 3: consume_stage<A_K, B_K, 2, 3>(acc, sa, sb, a_off, b_off); break;
+            case 2 * 8 + 2: consume_stage<A_K, B_K, 2, 2>(acc, sa, sb, a_off, b_off); break;
+            case 2 * 8 + 1: consume_stage<A_K, B_K, 2, 1>(acc, sa, sb, a_off, b_off); break;
+            case 1 * 8 + 4: consume_stage<A_K, B_K, 1, 4>(acc, sa, sb, a_off, b_off); break;
+            case 1 * 8 + 3: consume_stage<A_K, B_K, 1, 3>(acc, sa, sb, a_off, b_off); break;
+            case 1 * 8 + 2: consume_stage<A_K, B_K, 1, 2>(acc, sa, sb, a_off, b_off); break;
+            case 1 * 8 + 1: consume_stage<A_K, B_K, 1, 1>(acc, sa, sb, a_off, b_off); break;
+            default: break; // this warp has no valid block in this tile
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_base + 8 * (STAGES + stage));
@@ -303,17 +340,43 @@ rb_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
         const bool vec_ok = ((ldc & 1) == 0) && ((((uintptr_t)cb) & 15) == 0);
         const int tri = (p.splits > 1) ? 0 : p.tri;
+        // Lean path for interior tiles (the common case): no bounds / triangle tests, 16-byte stores, one IMAD per
+        // store.  The epilogue is pure issue overhead for the DMMA pipe, so it is kept as short as possible.
+        if (vec_ok && tri == 0 && beta == 0.0 && mrem >= BM && nrem >= BN) {
+            double *pbase = cb + (tm * BM + rb0 * 16 + 2 * g) + (tn * BN + cb0 * 16 + (B_K ? 2 * t : 4 * t)) * ldc;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const i64 row0 = tm * BM + (wm + 2 * i) * 16 + 2 * g;
+            for (int i = 0; i < 2; ++i) {
+                if (i >= ni) continue;
 #pragma unroll
-            for (int j = 0; j < 2; ++j)
+                for (int j = 0; j < 4; ++j) {
+                    if (j >= nj) continue;
+#pragma unroll
+                    for (int pb = 0; pb < 2; ++pb)
+#pragma unroll
+                        for (int cc = 0; cc < 2; ++cc) {
+                            const int cconst = j * 16 + (B_K ? (8 * pb + cc) : (2 * cc + pb));
+                            double2 o;
+                            o.x = alpha * (x ? acc[i][1][j][pb][cc] : acc[i][0][j][pb][cc]);
+                            o.y = alpha * (x ? acc[i][0][j][pb][cc] : acc[i][1][j][pb][cc]);
+                            *reinterpret_cast<double2 *>(pbase + i * 16 + (i64)cconst * ldc) = o;
+                        }
+                }
+            }
+            continue;
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            if (i >= ni) continue;
+            const i64 row0 = tm * BM + (rb0 + i) * 16 + 2 * g;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (j >= nj) continue;
 #pragma unroll
                 for (int pb = 0; pb < 2; ++pb)
 #pragma unroll
                     for (int cc = 0; cc < 2; ++cc) {
                         const int coff = B_K ? (8 * pb + 2 * t + cc) : (4 * t + 2 * cc + pb);
-                        const i64 col = tn * BN + (wn + 4 * j) * 16 + coff;
+                        const i64 col = tn * BN + (cb0 + j) * 16 + coff;
                         if (col >= p.n) continue;
                         double v0 = x ? acc[i][1][j][pb][cc] : acc[i][0][j][pb][cc]; // row 2g
                         double v1 = x ? acc[i][0][j][pb][cc] : acc[i][1][j][pb][cc]; // row 2g+1
@@ -334,6 +397,7 @@ rb_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                             if (ok1) cp[1] = (beta == 0.0) ? alpha * v1 : alpha * v1 + beta * cp[1];
                         }
                     }
+            }
         }
     }
 }

@@ -20,6 +20,9 @@
 
 static i64 ws_budget_bytes(rb_ctx *ctx)
 {
+    // cudaMemGetInfo costs ~a millisecond: query once per context (workspaces are grow-only, so the first answer
+    // stays a valid bound) instead of once per call.
+    if (ctx->ws_budget > 0) return ctx->ws_budget;
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return (i64)1 << 30; }
     i64 have = (i64)free_b + ctx->ws_bytes[0];
@@ -27,6 +30,7 @@ static i64 ws_budget_bytes(rb_ctx *ctx)
     const i64 cap = (i64)8 << 30;
     if (budget > cap) budget = cap;
     if (budget < ((i64)64 << 20)) budget = (i64)64 << 20;
+    ctx->ws_budget = budget;
     return budget;
 }
 
