@@ -222,6 +222,10 @@ int rb_fp64_peak_probe(rb_ctx *ctx, int kind, int iters, double *tflops_out, dou
 /* Stream copy probe (read+write bytes / time) for the HBM denominator cross-check. */
 int rb_hbm_copy_probe(rb_ctx *ctx, int64_t bytes, int iters, double *gbs_out);
 
+/* PCIe probe for the host-pointer paths: mode 0 H2D, 1 D2H, 2 D2H 2-D (rows of `width` bytes), 3 H2D+D2H duplex
+ * (sum of both directions), 4 D2H by kernel stores into mapped pinned memory, 5 like 4 with rows of `width` bytes. */
+int rb_pcie_probe(rb_ctx *ctx, int mode, int64_t bytes, int64_t width, int iters, double *gbs_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -118,6 +118,7 @@ SIGNATURES = {
     "rb_fill_ri3ao_symm": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, C.c_uint64, C.c_double]),
     "rb_fp64_peak_probe": (C.c_int, [c_vp, C.c_int, C.c_int, c_dp, c_dp]),
     "rb_hbm_copy_probe": (C.c_int, [c_vp, c_i64, C.c_int, c_dp]),
+    "rb_pcie_probe": (C.c_int, [c_vp, C.c_int, c_i64, c_i64, C.c_int, c_dp]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

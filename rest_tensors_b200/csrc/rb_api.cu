@@ -272,3 +272,67 @@ extern "C" int rb_hbm_copy_probe(rb_ctx *ctx, int64_t bytes, int iters, double *
     *gbs_out = (double)half * 2.0 * iters / (ms * 1e-3) / 1e9;
     return RB_OK;
 }
+
+
+// ---- PCIe probe: what the host-pointer paths can hope for on this box -------------------------------------------------
+// mode 0: H2D contiguous (pinned)      1: D2H contiguous (pinned)        2: D2H cudaMemcpy2D with rows of `width` bytes
+// mode 3: H2D and D2H contiguous at the same time (full duplex)          4: D2H by kernel stores into mapped pinned memory
+// mode 5: like 4 but rows of `width` bytes scattered at twice the pitch (the P-chunk pattern of ri3mo)
+__global__ void __launch_bounds__(256) rb_zero_copy_store_kernel(const double2 *__restrict__ src, double2 *__restrict__ dst,
+                                                                 i64 n2, i64 row2, i64 pitch2)
+{
+    i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+        i64 r = i / row2, c = i - r * row2;
+        dst[r * pitch2 + c] = src[i];
+    }
+}
+
+extern "C" int rb_pcie_probe(rb_ctx *ctx, int mode, int64_t bytes, int64_t width, int iters, double *gbs_out)
+{
+    RB_REQUIRE(ctx && gbs_out && bytes >= 4096 && iters > 0 && mode >= 0 && mode <= 5, "rb_pcie_probe: bad arguments");
+    RB_CUDA(cudaSetDevice(ctx->device));
+    if (width <= 0) width = 2048;
+    bytes = (bytes / width) * width;
+    void *h = nullptr, *h2 = nullptr, *d = nullptr, *d2 = nullptr;
+    const i64 hbytes = (mode == 5 || mode == 2) ? bytes * 2 : bytes;
+    RB_CUDA(cudaMallocHost(&h, (size_t)hbytes));
+    RB_CUDA(cudaMalloc(&d, (size_t)bytes));
+    if (mode == 3) { RB_CUDA(cudaMallocHost(&h2, (size_t)bytes)); RB_CUDA(cudaMalloc(&d2, (size_t)bytes)); }
+    cudaStream_t s2 = nullptr;
+    RB_CUDA(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+    RB_CUDA(cudaMemsetAsync(d, 0, (size_t)bytes, ctx->stream));
+    int status = RB_OK;
+    for (int rep = 0; rep < 2 && status == RB_OK; ++rep) { // rep 0 = warm-up
+        RB_CUDA(cudaStreamSynchronize(ctx->stream));
+        RB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+        for (int it = 0; it < (rep == 0 ? 1 : iters); ++it) {
+            switch (mode) {
+            case 0: RB_CUDA(cudaMemcpyAsync(d, h, (size_t)bytes, cudaMemcpyHostToDevice, ctx->stream)); break;
+            case 1: RB_CUDA(cudaMemcpyAsync(h, d, (size_t)bytes, cudaMemcpyDeviceToHost, ctx->stream)); break;
+            case 2: RB_CUDA(cudaMemcpy2DAsync(h, (size_t)width * 2, d, (size_t)width, (size_t)width, (size_t)(bytes / width),
+                                              cudaMemcpyDeviceToHost, ctx->stream)); break;
+            case 3:
+                RB_CUDA(cudaMemcpyAsync(d, h, (size_t)bytes, cudaMemcpyHostToDevice, ctx->stream));
+                RB_CUDA(cudaMemcpyAsync(h2, d2, (size_t)bytes, cudaMemcpyDeviceToHost, s2));
+                break;
+            default: {
+                i64 row2 = (mode == 5) ? width / 16 : bytes / 16, pitch2 = (mode == 5) ? width / 8 : bytes / 16;
+                rb_zero_copy_store_kernel<<<64, 256, 0, ctx->stream>>>((const double2 *)d, (double2 *)h, bytes / 16, row2, pitch2);
+                RB_LAUNCHED(ctx);
+            }
+            }
+        }
+        if (mode == 3) RB_CUDA(cudaStreamSynchronize(s2));
+        RB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+        RB_CUDA(cudaEventSynchronize(ctx->ev1));
+    }
+    float ms = 0;
+    RB_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    *gbs_out = (double)bytes * iters * (mode == 3 ? 2.0 : 1.0) / (ms * 1e-3) / 1e9;
+    cudaStreamDestroy(s2);
+    cudaFreeHost(h); cudaFree(d);
+    if (h2) cudaFreeHost(h2);
+    if (d2) cudaFree(d2);
+    return status;
+}

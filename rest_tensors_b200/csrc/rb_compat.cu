@@ -8,6 +8,12 @@
 // transfers overlap the contraction; pass pinned buffers (rb_host_alloc_pinned) to make the copies truly async.
 #include "rb_common.cuh"
 #include <vector>
+#include <chrono>
+
+static double now_ms()
+{
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 namespace {
 
@@ -118,11 +124,16 @@ int host_ri_stream(const double *cl, int nl, const double *cr, int nr, const dou
     const bool do_j = dm != nullptr && (d_out != nullptr || j_out != nullptr);
     const bool do_k = ct != nullptr && k_out != nullptr && no > 0;
     if (nx == 0 || !(do_mo || do_j || do_k)) return RB_OK;
+    const bool trace = getenv("REST_B200_TRACE") != nullptr;
+    const double t_start = now_ms();
     HOST_CTX(op);
     rb_ctx *ctx = op.ctx;
     // chunk of P slabs staged per pipeline step: large enough for full 128-row MMA tiles along P, small enough
     // to overlap the PCIe transfers with compute
     i64 pc = 256;
+    if (const char *e = getenv("REST_B200_PC")) { i64 v = atoll(e); if (v >= 8) pc = v; }
+    // (Measured on this pool, profiles/r01_e2e_variants.md: letting GEMM 2 store straight into mapped pinned host memory
+    //  is slower -- 223 ms vs 130 ms per pass at config C -- than staging in HBM and draining with 2-D copies.)
     const i64 slab_in = nb * nb, slab_out = do_mo ? (i64)nl * nr : 0;
     while (pc > 8 && pc * (slab_in + slab_out) * 8 * 2 > ((i64)6 << 30)) pc >>= 1;
     if (pc > nx) pc = nx;
@@ -147,6 +158,7 @@ int host_ri_stream(const double *cl, int nl, const double *cr, int nr, const dou
     }
     if (do_j) RB_TRY(op.up(d_dm, dm, slab_in));
     if (do_k) RB_TRY(op.up(d_ct, ct, nb * no));
+    const double t_alloc = now_ms();
     int step = 0;
     for (i64 p0 = 0; p0 < nx; p0 += pc, ++step) {
         const int s = step & 1;
@@ -175,6 +187,7 @@ int host_ri_stream(const double *cl, int nl, const double *cr, int nr, const dou
             RB_CUDA(cudaEventRecord(pipe.out_done[s], pipe.s_out));
         }
     }
+    const double t_enq = now_ms();
     if (do_k && slab_in > 0) RB_TRY(rb_symmetrize(ctx, d_k, nb, nb, true));
     if (do_j) {
         if (d_out) RB_TRY(op.down(d_out, d_d, nx));
@@ -184,6 +197,9 @@ int host_ri_stream(const double *cl, int nl, const double *cr, int nr, const dou
     RB_CUDA(cudaStreamSynchronize(pipe.s_out));
     RB_CUDA(cudaStreamSynchronize(pipe.s_in));
     RB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (trace)
+        fprintf(stderr, "[rest_b200] ri stream: nb=%lld nx=%lld pc=%lld chunks=%d  setup %.2f ms, enqueue %.2f ms, drain %.2f ms\n",
+                (long long)nb, (long long)nx, (long long)pc, step, t_alloc - t_start, t_enq - t_alloc, now_ms() - t_enq);
     return RB_OK;
 }
 

@@ -1,0 +1,91 @@
+// C++ host-mirror test (compiled and run by tests/test_gpu_cpp_host.py on a GPU box): the reference's own worked
+// examples through rest_tensors.hpp -> C ABI -> CUDA, checked against the golden vectors and the CPU oracle.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include "../../rest_tensors_b200/host/rest_tensors.hpp"
+
+extern "C" { // oracle (test infrastructure)
+void orc_fill_linear(double *v, int64_t n, uint64_t seed, uint64_t idx0, double scale);
+void orc_ri_ao2mo_f(const double *c, const double *ri, double *mo, int ns, int nb, int nx);
+void orc_ri_dp(const double *ri, const double *dm, double *d, int nb, int nx);
+void orc_ri_j(const double *ri, const double *d, double *j, int nb, int nx);
+void orc_ri_k(const double *ri, const double *ct, double *k, int nb, int no, int nx);
+void orc_ri_transpose(const double *in, int64_t I, int64_t J, int64_t K, int which, double *out);
+}
+using namespace rest_tensors;
+
+static int fails = 0;
+#define CHECK(cond, what) do { if (!(cond)) { std::printf("FAIL: %s\n", what); ++fails; } } while (0)
+
+static double rel_err(const std::vector<double> &x, const std::vector<double> &y)
+{
+    double num = 0, den = 0;
+    for (size_t i = 0; i < y.size(); ++i) { num = std::fmax(num, std::fabs(x[i] - y[i])); den = std::fmax(den, std::fabs(y[i])); }
+    return den > 0 ? num / den : num;
+}
+static std::vector<double> fill(size_t n, uint64_t seed, double scale = 1.0)
+{
+    std::vector<double> v(n);
+    orc_fill_linear(v.data(), (int64_t)n, seed, 0, scale);
+    return v;
+}
+
+int main()
+{
+    // GV4: iter_matrixupper of 4x4 (1..16)  (reference src/matrix/mod.rs:437-452)
+    std::vector<double> a16(16);
+    for (int i = 0; i < 16; ++i) a16[i] = i + 1;
+    auto up = MatrixFull::from_vec({4, 4}, a16).to_matrixupper();
+    CHECK((up.data == std::vector<double>{1, 5, 6, 9, 10, 11, 13, 14, 15, 16}), "GV4 pack order");
+    // GV5: MatrixUpper -> MatrixFull  (reference matrix_blas_lapack.rs:507-513)
+    auto full = MatrixUpper::from_vec(6, {4, 12, 37, -16, -43, 98}).to_matrixfull();
+    CHECK(full.has_value() && (full->data == std::vector<double>{4, 12, -16, 12, 37, -43, -16, -43, 98}), "GV5 unpack");
+    CHECK(!MatrixUpper::from_vec(4, {1, 2, 3, 4}).to_matrixfull().has_value(), "non-triangular length -> None");
+    // GV7: transpose of 3x4 (1..12)
+    std::vector<double> a12(12);
+    for (int i = 0; i < 12; ++i) a12[i] = i + 1;
+    auto t = MatrixFull::from_vec({3, 4}, a12).transpose();
+    CHECK(t.size[0] == 4 && t.data[8] == 3 && t.data[9] == 6 && t.data[10] == 9 && t.data[11] == 12, "GV7 transpose");
+    // GV9: benches/bench_tensors.rs -- every element 200
+    auto mo = RIFull::make({10, 10, 20}, 2.0).ao2mo_v02(MatrixFull::make({10, 10}, 1.0));
+    bool all200 = mo.size[0] == 20;
+    for (double v : mo.data) all200 = all200 && v == 200.0;
+    CHECK(all200, "GV9 ao2mo bench case");
+    // GV10: the four transposes of RIFull[3,2,2] 0..12 vs oracle
+    std::vector<double> r12(12);
+    for (int i = 0; i < 12; ++i) r12[i] = i;
+    auto ri = RIFull::from_vec({3, 2, 2}, r12);
+    RIFull trs[4] = {ri.transpose_jik(), ri.transpose_jki(), ri.transpose_kji(), ri.transpose_ikj()};
+    for (int w = 0; w < 4; ++w) {
+        std::vector<double> ref(12);
+        orc_ri_transpose(r12.data(), 3, 2, 2, w, ref.data());
+        CHECK(trs[w].data == ref, "GV10 RIFull transposes");
+    }
+    // ao2mo / d_P / J / K vs the oracle on a random case
+    const int nb = 48, nx = 30, no = 7;
+    auto riv = fill((size_t)nb * nb * nx, 2), c = fill((size_t)nb * nb, 3, 1.0 / std::sqrt((double)nb));
+    auto R = RIFull::from_vec({(size_t)nb, (size_t)nb, (size_t)nx}, riv);
+    auto C = MatrixFull::from_vec({(size_t)nb, (size_t)nb}, c);
+    std::vector<double> ref((size_t)nx * nb * nb);
+    orc_ri_ao2mo_f(c.data(), riv.data(), ref.data(), nb, nb, nx);
+    CHECK(rel_err(R.ao2mo(C).data, ref) < 1e-10, "ao2mo vs oracle");
+    auto dm = fill((size_t)nb * nb, 5);
+    std::vector<double> dref(nx), jref((size_t)nb * nb), kref((size_t)nb * nb);
+    orc_ri_dp(riv.data(), dm.data(), dref.data(), nb, nx);
+    orc_ri_j(riv.data(), dref.data(), jref.data(), nb, nx);
+    std::vector<double> ct(c.begin(), c.begin() + (size_t)nb * no);
+    orc_ri_k(riv.data(), ct.data(), kref.data(), nb, no, nx);
+    CHECK(rel_err(R.ri_dp(MatrixFull::from_vec({(size_t)nb, (size_t)nb}, dm)), dref) < 1e-10, "d_P vs oracle");
+    CHECK(rel_err(R.ri_j(dref).data, jref) < 1e-10, "J vs oracle");
+    CHECK(rel_err(R.ri_k(MatrixFull::from_vec({(size_t)nb, (size_t)no}, ct)).data, kref) < 1e-10, "K vs oracle");
+    // panics
+    bool threw = false;
+    try { RIFull::from_vec({3, 2, 2}, std::vector<double>(11)); } catch (const std::runtime_error &) { threw = true; }
+    CHECK(threw, "from_vec too short must throw");
+    threw = false;
+    try { MatrixFull::make({2, 3}, 0.0).to_matrixupper(); } catch (const std::runtime_error &) { threw = true; }
+    CHECK(threw, "to_matrixupper of a non-square matrix must throw");
+    if (fails == 0) std::printf("CPP_HOST_MIRROR_OK\n");
+    return fails == 0 ? 0 : 1;
+}
