@@ -192,6 +192,7 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs CUDA devices (no CPU fallback)"
     torch.cuda.set_device(local)
+    os.environ["REST_B200_DEVICE"] = str(local)   # the host-pointer C ABI (e2e leg) runs on this rank's GPU
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{local}"))

@@ -17,28 +17,55 @@ static double now_ms()
 
 namespace {
 
+// Device staging blocks of the host-pointer entry points are cached between calls (cudaMalloc/cudaFree of GB-sized
+// buffers cost tens of ms per call otherwise).  Calls are serialised by the default-context mutex, so a plain list is
+// enough; blocks beyond the cap are released when a call ends.
+struct StageBlock { void *p; i64 bytes; bool busy; };
+static std::vector<StageBlock> g_stage;
+static const i64 STAGE_CACHE_CAP = (i64)24 << 30;
+
 struct HostOp {
     rb_ctx *ctx;
     std::unique_lock<std::mutex> lock;
-    std::vector<void *> bufs;
     HostOp() : ctx(nullptr), lock(rb_default_mutex()) { ctx = rb_default_ctx(); }
     ~HostOp()
     {
         if (ctx) cudaStreamSynchronize(ctx->stream);
-        for (void *p : bufs) cudaFree(p);
+        i64 total = 0;
+        for (auto &b : g_stage) { b.busy = false; total += b.bytes; }
+        while (total > STAGE_CACHE_CAP && !g_stage.empty()) { // drop the largest blocks first
+            size_t big = 0;
+            for (size_t i = 1; i < g_stage.size(); ++i) if (g_stage[i].bytes > g_stage[big].bytes) big = i;
+            cudaFree(g_stage[big].p);
+            total -= g_stage[big].bytes;
+            g_stage.erase(g_stage.begin() + big);
+        }
     }
     int alloc(i64 elems, double **out)
     {
         *out = nullptr;
         if (elems <= 0) elems = 1;
+        const i64 need = elems * 8;
+        int best = -1;
+        for (size_t i = 0; i < g_stage.size(); ++i) // best fit among free cached blocks (at most 2x oversize)
+            if (!g_stage[i].busy && g_stage[i].bytes >= need && g_stage[i].bytes <= 2 * need + 4096 &&
+                (best < 0 || g_stage[i].bytes < g_stage[best].bytes)) best = (int)i;
+        if (best >= 0) { g_stage[best].busy = true; *out = (double *)g_stage[best].p; return RB_OK; }
         void *p = nullptr;
-        cudaError_t e = cudaMalloc(&p, (size_t)elems * 8);
+        cudaError_t e = cudaMalloc(&p, (size_t)need);
+        if (e != cudaSuccess) { // release the idle cache and retry once
+            cudaGetLastError();
+            for (size_t i = 0; i < g_stage.size();) {
+                if (!g_stage[i].busy) { cudaFree(g_stage[i].p); g_stage.erase(g_stage.begin() + i); } else ++i;
+            }
+            e = cudaMalloc(&p, (size_t)need);
+        }
         if (e != cudaSuccess) {
             cudaGetLastError();
             rb_set_error("host wrapper: cudaMalloc(%lld doubles) failed: %s", (long long)elems, cudaGetErrorString(e));
             return RB_ERR_NOMEM;
         }
-        bufs.push_back(p);
+        g_stage.push_back({p, need, true});
         *out = (double *)p;
         return RB_OK;
     }
@@ -159,6 +186,8 @@ int host_ri_stream(const double *cl, int nl, const double *cr, int nr, const dou
     if (do_j) RB_TRY(op.up(d_dm, dm, slab_in));
     if (do_k) RB_TRY(op.up(d_ct, ct, nb * no));
     const double t_alloc = now_ms();
+    // (A geometric ramp of small first/last chunks was measured and does not help: the pass is bound by PCIe duplex
+    //  bandwidth, 9.8 GB at ~94 GB/s, not by pipeline fill/drain -- profiles/r01_e2e_variants.md.)
     int step = 0;
     for (i64 p0 = 0; p0 < nx; p0 += pc, ++step) {
         const int s = step & 1;

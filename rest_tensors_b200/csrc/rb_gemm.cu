@@ -564,10 +564,11 @@ bool tma_eligible(const rb_ctx *ctx, const double *p, i64 ld, i64 stride, i64 ba
 template <bool A_K, bool B_K>
 int launch_tma(rb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p, int grid)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false}; // the opt-in shared-memory size is a per-device function attribute
+    const int dev = ctx->device & 63;
+    if (!attr_set[dev]) {
         RB_CUDA(cudaFuncSetAttribute(rb_gemm_tma_kernel<A_K, B_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        attr_set = true;
+        attr_set[dev] = true;
     }
     rb_gemm_tma_kernel<A_K, B_K><<<grid, NUM_THREADS, SMEM_BYTES, ctx->stream>>>(tmA, tmB, p);
     RB_LAUNCHED(ctx);

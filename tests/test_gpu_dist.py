@@ -1,0 +1,68 @@
+"""Multi-GPU parity (needs >= 2 GPUs; skipped otherwise): each rank holds its P-shard of a synthetic ri3ao in HBM, runs
+the CUDA kernels on it, and ONE NCCL all-reduce(sum) each completes J and K.  Checked against the unsharded CPU oracle."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, nb, naux, no, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    try:
+        from oracle.api import Oracle
+        from rest_tensors_b200.device import Context, ShardedRI, gather_dp
+        o = Oracle(); o.load_openblas()
+        ctx = Context(rank)
+        sh = ShardedRI(ctx, nb, naux, rank, world).fill_synthetic()
+        c = o.fill_linear(nb * nb, 3, scale=nb ** -0.5)
+        cm = c.reshape((nb, nb), order="F")
+        dm = np.ascontiguousarray((2.0 * cm[:, :no] @ cm[:, :no].T).reshape(-1, order="F"))
+        ct = np.ascontiguousarray((cm[:, :no] * np.sqrt(2.0)).reshape(-1, order="F"))
+        dev = lambda a: torch.from_numpy(a).to(f"cuda:{rank}")  # noqa: E731
+        cd = dev(c)
+        d_local = sh.dp(dev(dm))
+        j = sh.j(d_local)                  # partial + all-reduce
+        k = sh.k(dev(ct), no)              # partial + all-reduce
+        mo_local = sh.ao2mo(cd, nb, cd, nb)
+        d_full = gather_dp(d_local, naux, sh.p_lo, world)
+        torch.cuda.synchronize()
+        ri = o.fill_ri3ao_symm(nb, 0, naux)
+        d_ref = o.ri_dp(ri, dm, nb, naux)
+
+        def err(x, y):
+            return float(np.max(np.abs(x - y)) / np.max(np.abs(y)))
+        mo_ref = o.ri_ao2mo_f(c, ri, nb, nb, naux).reshape((naux, nb, nb), order="F")[sh.p_lo:sh.p_hi].reshape(-1, order="F")
+        errs = [err(d_full.cpu().numpy(), d_ref), err(j.cpu().numpy(), o.ri_j(ri, d_ref, nb, naux)),
+                err(k.cpu().numpy(), o.ri_k(ri, ct, nb, no, naux)), err(mo_local.cpu().numpy(), mo_ref)]
+        ret.put((rank, max(errs)))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_jk_allreduce(world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = 29600 + (os.getpid() % 2000) + world
+    procs = [ctx.Process(target=_worker, args=(r, world, port, 64, 203, 9, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    res = [ret.get(timeout=5) for _ in range(world)]
+    assert all(e <= 1e-10 for _, e in res), res
