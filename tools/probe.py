@@ -47,7 +47,10 @@ def main():
     out["gemm"] = gem
     # RI ops
     ri_out = {}
-    for name, nb, nx, no in [("A", 100, 400, 20), ("B", 264, 720, 21), ("C", 600, 1700, 60)]:
+    cfgs = [("A", 100, 400, 20), ("B", 264, 720, 21), ("C", 600, 1700, 60)]
+    if "--with-d" in sys.argv:
+        cfgs.append(("D", 1800, 600, 180))
+    for name, nb, nx, no in cfgs:
         sh = ShardedRI(ctx, nb, nx).fill_synthetic()
         c = ctx.empty(nb * nb); ctx.fill_linear(c, nb * nb, 3, 0, nb ** -0.5)
         mo = ctx.empty(nx * nb * nb)
@@ -76,7 +79,8 @@ def main():
     med, best = timed(lambda: ctx.copy_mm(n, n, f, n, n, 0, 0, g, n, n, 0, 0)); out["copy_8000_gbs"] = 2 * n * n * 8 / (best * 1e-3) / 1e9
     med, best = timed(lambda: ctx.self_scaled_add(g, f, 0.5, n * n)); out["axpy_8000_gbs"] = 3 * n * n * 8 / (best * 1e-3) / 1e9
     print({k: v for k, v in out.items() if k.endswith("gbs")}, flush=True)
-    path = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/probe.json"
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    path = args[0] if args else "gpurun_out/probe.json"
     with open(path, "w") as fh:
         json.dump(out, fh, indent=1)
 
