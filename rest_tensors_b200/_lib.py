@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librest_b200.so")
+# REST_B200_LIB: development override used by tools/ to A/B kernel variants (still a build of csrc/)
+LIB_PATH = os.environ.get("REST_B200_LIB") or os.path.join(_HERE, "librest_b200.so")
 
 
 class RestB200Error(RuntimeError):

@@ -49,6 +49,8 @@ extern "C" int rb_ctx_create(int device, rb_ctx **out)
     c->stream = c->own_stream;
     RB_CUDA(cudaEventCreate(&c->ev0));
     RB_CUDA(cudaEventCreate(&c->ev1));
+    RB_CUDA(cudaMalloc((void **)&c->sched, 64));
+    RB_CUDA(cudaMemset(c->sched, 0, 64));
     // cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link against libcuda).
     void *fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -65,6 +67,7 @@ extern "C" int rb_ctx_destroy(rb_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (int s = 0; s < 4; ++s) if (ctx->ws[s]) cudaFree(ctx->ws[s]);
+    if (ctx->sched) cudaFree(ctx->sched);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);

@@ -55,6 +55,7 @@ struct rb_ctx {
     int gemm_path = 0;
     rb_encode_tiled_fn encode_tiled = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    unsigned long long *sched = nullptr; // GEMM tile-scheduler words (device), zero between launches
 };
 
 // Grow-only device workspace (synchronises the stream before freeing the old block).

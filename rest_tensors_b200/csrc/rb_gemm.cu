@@ -33,7 +33,9 @@ constexpr int STAGES = 3;
 constexpr int A_TILE_BYTES = BM * BK * 8;
 constexpr int B_TILE_BYTES = BN * BK * 8;
 constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 64 /*barriers*/;
+constexpr int INFO_SLOTS = 8;  // tile-descriptor queue depth (> STAGES + 1: the producer is at most STAGES stages ahead)
+constexpr int INFO_INTS = 8;   // tm, tn, batch, split, full 32-deep stages, tail k8 blocks, warp-grid code, unused
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 64 /*barriers*/ + INFO_SLOTS * INFO_INTS * 4;
 constexpr int NUM_CONSUMER_WARPS = 8;
 constexpr int NUM_THREADS = (NUM_CONSUMER_WARPS + 4) * 32; // 2 consumer warpgroups + 1 producer warpgroup
 constexpr int GROUP_M = 8;
@@ -52,6 +54,7 @@ struct GemmParams {
     double *partial;     // split-K partials [split][batch][n][ldp]
     i64 ldp;
     int a_batched, b_batched; // 0 => operand shared by all batches (TMA batch coordinate 0)
+    unsigned long long *sched; // [0] next work item - gridDim.x, [1] CTAs done (both 0 between launches)
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------
@@ -129,58 +132,116 @@ __device__ __forceinline__ void decode_item(const GemmParams &p, i64 item, i64 &
     }
 }
 
-// One 32-deep k stage for a warp that owns NI x NJ 16x16 blocks (compile-time, so that every DMMA is unpredicated:
-// predicated mma.sync costs a WARPSYNC per group).  12 LDS.128 feed 64 DMMAs per k8 block in the full 2 x 4 case.
+// One k8 block (two DMMA k4 steps) for a warp that owns NI x NJ 16x16 blocks (compile-time, so that every DMMA is
+// unpredicated: predicated mma.sync costs a WARPSYNC per group).  12 LDS.128 feed 64 DMMAs in the full 2 x 4 case.
 template <bool A_K, bool B_K, int NI, int NJ>
-__device__ __forceinline__ void consume_stage(double (&acc)[2][2][4][2][2], uint32_t sa, uint32_t sb,
-                                              const uint32_t (&a_off)[2], const uint32_t (&b_off)[2])
+__device__ __forceinline__ void consume_kb(double (&acc)[2][2][4][2][2], uint32_t sa, uint32_t sb,
+                                           const uint32_t (&a_off)[2], const uint32_t (&b_off)[2], int kb)
+{
+    double af[NI][2][2]; // [i][tile e/o][mma 0/1]
+    double bf[NJ][2][2]; // [j][tile e/o][mma 0/1]
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+        if (A_K) {
+#pragma unroll
+            for (int pa = 0; pa < 2; ++pa) {
+                double2 v = lds128(sa + kb * (BM * 64) + i * (16 * 64) + a_off[pa]);
+                af[i][pa][0] = v.x; af[i][pa][1] = v.y;
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                double2 v = lds128(sa + i * (BK * 128) + kb * (8 * 128) + a_off[q]);
+                af[i][0][q] = v.x; af[i][1][q] = v.y;
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        if (B_K) {
+#pragma unroll
+            for (int pb = 0; pb < 2; ++pb) {
+                double2 v = lds128(sb + kb * (BN * 64) + j * (16 * 64) + b_off[pb]);
+                bf[j][pb][0] = v.x; bf[j][pb][1] = v.y;
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                double2 v = lds128(sb + j * (BK * 128) + kb * (8 * 128) + b_off[q]);
+                bf[j][0][q] = v.x; bf[j][1][q] = v.y;
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int i = 0; i < NI; ++i)
+#pragma unroll
+            for (int pa = 0; pa < 2; ++pa)
+#pragma unroll
+                for (int j = 0; j < NJ; ++j)
+#pragma unroll
+                    for (int pb = 0; pb < 2; ++pb) dmma(acc[i][pa][j][pb], bf[j][pb][q], af[i][pa][q]); // D[n][m]: see header
+}
+
+// The whole k loop of one tile for a warp with NI x NJ blocks: `full_steps` 32-deep stages (fully unrolled body) and
+// one last stage of which only `tail_kb` k8 blocks hold data (K is consumed at k8 granularity, not padded to 32).
+// The (NI, NJ) dispatch sits outside this loop, so the hot loop has no per-stage branching.  NI == 0: the warp has
+// no valid block in this tile and only keeps the barrier protocol going.
+template <bool A_K, bool B_K, int NI, int NJ>
+__device__ __forceinline__ void run_tile(double (&acc)[2][2][4][2][2], uint32_t smem_base, uint32_t bar_base, int &stage,
+                                         uint32_t &phase, uint32_t a_blk, uint32_t b_blk, const uint32_t (&a_off)[2],
+                                         const uint32_t (&b_off)[2], int full_steps, int tail_kb, int lane)
+{
+    for (int ks = 0; ks < full_steps; ++ks) {
+        mbar_wait(bar_base + 8 * stage, phase);
+        if (NI > 0) {
+            const uint32_t sa = smem_base + stage * STAGE_BYTES + a_blk, sb = smem_base + stage * STAGE_BYTES + A_TILE_BYTES + b_blk;
+#pragma unroll
+            for (int kb = 0; kb < BK / 8; ++kb) consume_kb<A_K, B_K, (NI > 0 ? NI : 1), NJ>(acc, sa, sb, a_off, b_off, kb);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_base + 8 * (STAGES + stage));
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+    }
+    if (tail_kb > 0) {
+        mbar_wait(bar_base + 8 * stage, phase);
+        if (NI > 0) {
+            const uint32_t sa = smem_base + stage * STAGE_BYTES + a_blk, sb = smem_base + stage * STAGE_BYTES + A_TILE_BYTES + b_blk;
+#pragma unroll 1
+            for (int kb = 0; kb < tail_kb; ++kb) consume_kb<A_K, B_K, (NI > 0 ? NI : 1), NJ>(acc, sa, sb, a_off, b_off, kb);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_base + 8 * (STAGES + stage));
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+    }
+}
+
+// Interior-tile epilogue of one warp.  pbase points at (row_t, col_t) of the warp's rectangle; a thread owns two
+// (A_K) or, across the e/o tiles, four (!A_K) consecutive rows of a column -> 16-byte stores.
+template <bool A_K, bool B_K, bool SCALE>
+__device__ __forceinline__ void store_lean(const double (&acc)[2][2][4][2][2], double *pbase, i64 ldc, double alpha, int ni,
+                                           int nj)
 {
 #pragma unroll
-    for (int kb = 0; kb < BK / 8; ++kb) {
-        double af[NI][2][2]; // [i][tile e/o][mma 0/1]
-        double bf[NJ][2][2]; // [j][tile e/o][mma 0/1]
+    for (int i = 0; i < 2; ++i) {
+        if (i >= ni) continue;
 #pragma unroll
-        for (int i = 0; i < NI; ++i) {
-            if (A_K) {
+        for (int j = 0; j < 4; ++j) {
+            if (j >= nj) continue;
 #pragma unroll
-                for (int pa = 0; pa < 2; ++pa) {
-                    double2 v = lds128(sa + kb * (BM * 64) + i * (16 * 64) + a_off[pa]);
-                    af[i][pa][0] = v.x; af[i][pa][1] = v.y;
-                }
-            } else {
+            for (int pb = 0; pb < 2; ++pb) {
+                double *pc = pbase + i * 16 + (i64)(j * 16 + (B_K ? 8 * pb : pb)) * ldc;
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    double2 v = lds128(sa + i * (BK * 128) + kb * (8 * 128) + a_off[q]);
-                    af[i][0][q] = v.x; af[i][1][q] = v.y;
-                }
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-            if (B_K) {
-#pragma unroll
-                for (int pb = 0; pb < 2; ++pb) {
-                    double2 v = lds128(sb + kb * (BN * 64) + j * (16 * 64) + b_off[pb]);
-                    bf[j][pb][0] = v.x; bf[j][pb][1] = v.y;
-                }
-            } else {
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    double2 v = lds128(sb + j * (BK * 128) + kb * (8 * 128) + b_off[q]);
-                    bf[j][0][q] = v.x; bf[j][1][q] = v.y;
+                for (int h = 0; h < 2; ++h) { // A_K: h = pa (rows +8); !A_K: h = cc (rows +2)
+                    double2 o;
+                    if (A_K) { o.x = acc[i][h][j][pb][0]; o.y = acc[i][h][j][pb][1]; }
+                    else { o.x = acc[i][0][j][pb][h]; o.y = acc[i][1][j][pb][h]; }
+                    if (SCALE) { o.x *= alpha; o.y *= alpha; }
+                    *reinterpret_cast<double2 *>(pc + (A_K ? 8 * h : 2 * h)) = o;
                 }
             }
         }
-#pragma unroll
-        for (int q = 0; q < 2; ++q)
-#pragma unroll
-            for (int i = 0; i < NI; ++i)
-#pragma unroll
-                for (int pa = 0; pa < 2; ++pa)
-#pragma unroll
-                    for (int j = 0; j < NJ; ++j)
-#pragma unroll
-                        for (int pb = 0; pb < 2; ++pb) dmma(acc[i][pa][j][pb], af[i][pa][q], bf[j][pb][q]);
     }
 }
 
@@ -192,6 +253,7 @@ rb_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES; // full[STAGES], empty[STAGES]
+    const uint32_t info_base = bar_base + 64;                   // tile-descriptor queue
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
@@ -205,21 +267,50 @@ rb_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
     if (warp >= NUM_CONSUMER_WARPS) {
         // ===================== producer warpgroup: hand its registers to the consumers =====================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         if (warp == NUM_CONSUMER_WARPS && lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
             int stage = 0;
             uint32_t phase = 0;
-            for (i64 item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+            int tcount = 0;
+            // Dynamic tile scheduler: the first item is static, the rest come from a global counter (tiles differ in
+            // cost -- ragged edges, triangles -- so a static round-robin leaves SMs idle at the end).  The next item is
+            // fetched one tile ahead so that the atomic's latency never sits between two tiles.
+            i64 item = blockIdx.x;
+            while (item < p.total_items) {
+                const i64 next = (i64)gridDim.x + (i64)atomicAdd(p.sched, 1ULL);
                 i64 b, tm, tn, sp;
                 decode_item(p, item, b, tm, tn, sp);
                 const i64 k_begin = sp * p.kper;
                 const i64 k_end = (k_begin + p.kper < p.k) ? k_begin + p.kper : p.k;
                 const int ba = p.a_batched ? (int)b : 0, bb = p.b_batched ? (int)b : 0;
+                // Tile descriptor for the consumers (they do no index arithmetic of their own).  Valid 16x16 blocks of
+                // the tile (edge tiles are ragged; TMA zero-fills the rest) and the gm x gn warp grid that gives the
+                // busiest warp the fewest blocks with at most 2 x 4 per warp: 4 x 2 for full tiles, 8 x 1 / 1 x 8 /
+                // 2 x 4 for thin ones.  The cost of a tile is thus proportional to its valid blocks, not to 128 x 128.
+                const i64 mrem = p.m - tm * BM, nrem = p.n - tn * BN;
+                const int mb = mrem >= BM ? BM / 16 : (int)((mrem + 15) >> 4);
+                const int nbk = nrem >= BN ? BN / 16 : (int)((nrem + 15) >> 4);
+                int lgm = 2, rpg = 2, cpg = 4, best = 1 << 30;
+#pragma unroll
+                for (int lg = 3; lg >= 0; --lg) { // gm = 8, 4, 2, 1; gn = 8 / gm
+                    const int r = (mb + (1 << lg) - 1) >> lg, c = (nbk + (8 >> lg) - 1) >> (3 - lg);
+                    if (r <= 2 && c <= 4 && r * c < best) { best = r * c; lgm = lg; rpg = r; cpg = c; }
+                }
+                const uint32_t grid_code = (uint32_t)lgm | ((uint32_t)rpg << 4) | ((uint32_t)cpg << 8) | ((uint32_t)mb << 12) | ((uint32_t)nbk << 16);
+                bool first = true;
                 for (i64 k0 = k_begin; k0 < k_end; k0 += BK) {
                     const uint32_t full = bar_base + 8 * stage, empty = bar_base + 8 * (STAGES + stage);
                     mbar_wait(empty, phase ^ 1u);
+                    if (first) { // the arrive below releases the descriptor together with the tile's first stage
+                        const uint32_t slot = info_base + (tcount & (INFO_SLOTS - 1)) * INFO_INTS * 4;
+                        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(slot), "r"((uint32_t)tm), "r"((uint32_t)tn),
+                                     "r"((uint32_t)b), "r"((uint32_t)sp) : "memory");
+                        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(slot + 16), "r"((uint32_t)((k_end - k_begin) / BK)),
+                                     "r"((uint32_t)(((k_end - k_begin) % BK + 7) >> 3)), "r"(grid_code), "r"(0u) : "memory");
+                        first = false;
+                    }
                     mbar_expect_tx(full, STAGE_BYTES);
                     const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_TILE_BYTES;
                     if (A_K) {
@@ -242,21 +333,35 @@ rb_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
+                item = next;
+                ++tcount;
+            }
+            { // end-of-work descriptor, released through the next stage's full barrier (no data)
+                const uint32_t full = bar_base + 8 * stage, empty = bar_base + 8 * (STAGES + stage);
+                mbar_wait(empty, phase ^ 1u);
+                const uint32_t slot = info_base + (tcount & (INFO_SLOTS - 1)) * INFO_INTS * 4;
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(slot + 16), "r"(0xffffffffu), "r"(0u), "r"(0u), "r"(0u) : "memory");
+                mbar_arrive(full);
+            }
+            // the last CTA to run dry re-arms the scheduler for the next launch on this stream
+            if (atomicAdd(p.sched + 1, 1ULL) == (unsigned long long)gridDim.x - 1ULL) {
+                p.sched[0] = 0ULL;
+                p.sched[1] = 0ULL;
+                __threadfence();
             }
         }
         return;
     }
 
     // ===================== consumers =====================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     const int g = lane >> 2, t = lane & 3;
-    const int x = A_K ? (g & 1) : 0;
 
     // per-thread byte offsets of the fragment reads inside a 16-row block (k8-block / block offsets are added per use)
     uint32_t a_off[2], b_off[2];
     if (A_K) {
-        a_off[0] = (uint32_t)((2 * g + x) * 64 + t * 16);       // tile e : row 2g + x
-        a_off[1] = (uint32_t)((2 * g + 1 - x) * 64 + t * 16);   // tile o : row 2g + 1 - x
+        a_off[0] = (uint32_t)(g * 64 + t * 16);        // tile e : row g
+        a_off[1] = (uint32_t)((8 + g) * 64 + t * 16);  // tile o : row 8+g
     } else {
         a_off[0] = (uint32_t)((2 * t) * 128 + ((g ^ (2 * t)) << 4));          // k = 2t   : rows (2g, 2g+1)
         a_off[1] = (uint32_t)((2 * t + 1) * 128 + ((g ^ (2 * t + 1)) << 4));  // k = 2t+1
@@ -268,29 +373,29 @@ rb_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         b_off[0] = (uint32_t)((2 * t) * 128 + ((g ^ (2 * t)) << 4));
         b_off[1] = (uint32_t)((2 * t + 1) * 128 + ((g ^ (2 * t + 1)) << 4));
     }
+    // Position of accumulator acc[i][pa][j][pb][cc] inside the warp's rectangle (the DMMA computes the TRANSPOSED 8x8
+    // tile, so a thread holds two consecutive rows m = 2t, 2t+1 of column n = g):
+    //   row = 16 i + (A_K ? 8 pa + 2t + cc : 4t + 2 cc + pa),   col = 16 j + (B_K ? 8 pb + g : 2g + pb)
+    const int row_t = A_K ? 2 * t : 4 * t;
+    const int col_t = B_K ? g : 2 * g;
 
     int stage = 0;
     uint32_t phase = 0;
-    for (i64 item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-        i64 bidx, tm, tn, sp;
-        decode_item(p, item, bidx, tm, tn, sp);
-        const i64 k_begin = sp * p.kper;
-        const i64 k_end = (k_begin + p.kper < p.k) ? k_begin + p.kper : p.k;
-
-        // Valid 16x16 blocks of this tile (edge tiles are ragged; TMA zero-fills the rest) and this warp's rectangle
-        // of them.  The 8 warps form a gm x gn grid chosen per tile so that every warp holds at most 2 x 4 blocks and
-        // the busiest warp has as little work as possible: 4 x 2 for full tiles, 8 x 1 / 1 x 8 / 2 x 4 for thin
-        // ones.  Cost of a tile is therefore proportional to its valid blocks, not to 128 x 128.
-        const i64 mrem = p.m - tm * BM, nrem = p.n - tn * BN;
-        const int mb = mrem >= BM ? BM / 16 : (int)((mrem + 15) >> 4);
-        const int nbk = nrem >= BN ? BN / 16 : (int)((nrem + 15) >> 4);
-        int gm = 4, rpg = 2, cpg = 4, best = 1 << 30;
-#pragma unroll
-        for (int cand = 8; cand >= 1; cand >>= 1) {
-            const int r = (mb + cand - 1) / cand, c = (nbk + (8 / cand) - 1) / (8 / cand);
-            if (r <= 2 && c <= 4 && r * c < best) { best = r * c; gm = cand; rpg = r; cpg = c; }
+    int tcount = 0;
+    for (;; ++tcount) {
+        // the first stage of the tile carries the tile descriptor published by the producer
+        mbar_wait(bar_base + 8 * stage, phase);
+        uint32_t utm, utn, ub, usp, ufull, utail, ucode, upad;
+        {
+            const uint32_t slot = info_base + (tcount & (INFO_SLOTS - 1)) * INFO_INTS * 4;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(utm), "=r"(utn), "=r"(ub), "=r"(usp) : "r"(slot) : "memory");
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(ufull), "=r"(utail), "=r"(ucode), "=r"(upad) : "r"(slot + 16) : "memory");
         }
-        const int gi = warp % gm, gj = warp / gm;
+        if (ufull == 0xffffffffu) break; // no more work for this CTA
+        const i64 tm = utm, tn = utn, bidx = ub, sp = usp;
+        const int full_steps = (int)ufull, tail_kb = (int)utail;
+        const int lgm = ucode & 15, rpg = (ucode >> 4) & 15, cpg = (ucode >> 8) & 15, mb = (ucode >> 12) & 15, nbk = (ucode >> 16) & 15;
+        const int gi = warp & ((1 << lgm) - 1), gj = warp >> lgm;
         const int rb0 = gi * rpg, cb0 = gj * cpg;
         int ni = mb - rb0; ni = ni < 0 ? 0 : (ni > rpg ? rpg : ni);
         int nj = nbk - cb0; nj = nj < 0 ? 0 : (nj > cpg ? cpg : nj);
@@ -308,24 +413,19 @@ rb_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
                     for (int pb = 0; pb < 2; ++pb) { acc[i][pa][j][pb][0] = 0.0; acc[i][pa][j][pb][1] = 0.0; }
 
-        for (i64 k0 = k_begin; k0 < k_end; k0 += BK) {
-            mbar_wait(bar_base + 8 * stage, phase);
-            const uint32_t sa = smem_base + stage * STAGE_BYTES + a_blk, sb = smem_base + stage * STAGE_BYTES + A_TILE_BYTES + b_blk;
-            switch (ni * 8 + nj) { // warp-uniform
-            case 2 * 8 + 4: consume_stage<A_K, B_K, 2, 4>(acc, sa, sb, a_off, b_off); break;
-            case 2 * 8 + 3: consume_stage<A_K, B_K, 2, 3>(acc, sa, sb, a_off, b_off); break;
-            case 2 * 8 + 2: consume_stage<A_K, B_K, 2, 2>(acc, sa, sb, a_off, b_off); break;
-            case 2 * 8 + 1: consume_stage<A_K, B_K, 2, 1>(acc, sa, sb, a_off, b_off); break;
-            case 1 * 8 + 4: consume_stage<A_K, B_K, 1, 4>(acc, sa, sb, a_off, b_off); break;
-            case 1 * 8 + 3: consume_stage<A_K, B_K, 1, 3>(acc, sa, sb, a_off, b_off); break;
-            case 1 * 8 + 2: consume_stage<A_K, B_K, 1, 2>(acc, sa, sb, a_off, b_off); break;
-            case 1 * 8 + 1: consume_stage<A_K, B_K, 1, 1>(acc, sa, sb, a_off, b_off); break;
-            default: break; // this warp has no valid block in this tile
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_base + 8 * (STAGES + stage));
-            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+#define RB_RUN(NI_, NJ_) run_tile<A_K, B_K, NI_, NJ_>(acc, smem_base, bar_base, stage, phase, a_blk, b_blk, a_off, b_off, full_steps, tail_kb, lane)
+        switch (ni * 8 + nj) { // warp-uniform
+        case 2 * 8 + 4: RB_RUN(2, 4); break;
+        case 2 * 8 + 3: RB_RUN(2, 3); break;
+        case 2 * 8 + 2: RB_RUN(2, 2); break;
+        case 2 * 8 + 1: RB_RUN(2, 1); break;
+        case 1 * 8 + 4: RB_RUN(1, 4); break;
+        case 1 * 8 + 3: RB_RUN(1, 3); break;
+        case 1 * 8 + 2: RB_RUN(1, 2); break;
+        case 1 * 8 + 1: RB_RUN(1, 1); break;
+        default: RB_RUN(0, 1); break; // this warp has no valid block in this tile
         }
+#undef RB_RUN
 
         // ---- epilogue: thread owns rows (2g, 2g+1) of each 16-row block -> 16-byte stores along M ----
         double *cb;
@@ -340,46 +440,31 @@ rb_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
         const bool vec_ok = ((ldc & 1) == 0) && ((((uintptr_t)cb) & 15) == 0);
         const int tri = (p.splits > 1) ? 0 : p.tri;
-        // Lean path for interior tiles (the common case): no bounds / triangle tests, 16-byte stores, one IMAD per
-        // store.  The epilogue is pure issue overhead for the DMMA pipe, so it is kept as short as possible.
-        if (vec_ok && tri == 0 && beta == 0.0 && mrem >= BM && nrem >= BN) {
-            double *pbase = cb + (tm * BM + rb0 * 16 + 2 * g) + (tn * BN + cb0 * 16 + (B_K ? 2 * t : 4 * t)) * ldc;
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                if (i >= ni) continue;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (j >= nj) continue;
-#pragma unroll
-                    for (int pb = 0; pb < 2; ++pb)
-#pragma unroll
-                        for (int cc = 0; cc < 2; ++cc) {
-                            const int cconst = j * 16 + (B_K ? (8 * pb + cc) : (2 * cc + pb));
-                            double2 o;
-                            o.x = alpha * (x ? acc[i][1][j][pb][cc] : acc[i][0][j][pb][cc]);
-                            o.y = alpha * (x ? acc[i][0][j][pb][cc] : acc[i][1][j][pb][cc]);
-                            *reinterpret_cast<double2 *>(pbase + i * 16 + (i64)cconst * ldc) = o;
-                        }
-                }
-            }
+        // Lean path when every block of this warp lies inside the matrix (the common case): no bounds / triangle
+        // tests, 16-byte stores, one IMAD per store, no scaling when alpha == 1.  The epilogue is pure issue overhead
+        // for the DMMA pipe, so it is kept as short as possible.
+        if (vec_ok && tri == 0 && beta == 0.0 && tm * BM + (rb0 + ni) * 16 <= p.m && tn * BN + (cb0 + nj) * 16 <= p.n) {
+            double *pbase = cb + (tm * BM + rb0 * 16 + row_t) + (tn * BN + cb0 * 16 + col_t) * ldc;
+            if (alpha == 1.0) store_lean<A_K, B_K, false>(acc, pbase, ldc, alpha, ni, nj);
+            else store_lean<A_K, B_K, true>(acc, pbase, ldc, alpha, ni, nj);
             continue;
         }
+        // Edge tiles / triangles / beta != 0: full tests per row pair.
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
             if (i >= ni) continue;
-            const i64 row0 = tm * BM + (rb0 + i) * 16 + 2 * g;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 if (j >= nj) continue;
 #pragma unroll
-                for (int pb = 0; pb < 2; ++pb)
+                for (int pb = 0; pb < 2; ++pb) {
+                    const i64 col = tn * BN + (cb0 + j) * 16 + col_t + (B_K ? 8 * pb : pb);
+                    if (col >= p.n) continue;
 #pragma unroll
-                    for (int cc = 0; cc < 2; ++cc) {
-                        const int coff = B_K ? (8 * pb + 2 * t + cc) : (4 * t + 2 * cc + pb);
-                        const i64 col = tn * BN + (cb0 + j) * 16 + coff;
-                        if (col >= p.n) continue;
-                        double v0 = x ? acc[i][1][j][pb][cc] : acc[i][0][j][pb][cc]; // row 2g
-                        double v1 = x ? acc[i][0][j][pb][cc] : acc[i][1][j][pb][cc]; // row 2g+1
+                    for (int h = 0; h < 2; ++h) { // A_K: h = pa (rows +8); !A_K: h = cc (rows +2)
+                        const double v0 = A_K ? acc[i][h][j][pb][0] : acc[i][0][j][pb][h];
+                        const double v1 = A_K ? acc[i][h][j][pb][1] : acc[i][1][j][pb][h];
+                        const i64 row0 = tm * BM + (rb0 + i) * 16 + row_t + (A_K ? 8 * h : 2 * h);
                         double *cp = cb + row0 + col * ldc;
                         bool ok0 = row0 < p.m, ok1 = row0 + 1 < p.m;
                         if (tri == 1) { ok0 = ok0 && row0 <= col; ok1 = ok1 && row0 + 1 <= col; }
@@ -388,7 +473,7 @@ rb_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                             double2 o;
                             if (beta == 0.0) { o.x = alpha * v0; o.y = alpha * v1; }
                             else {
-                                double2 old = *reinterpret_cast<const double2 *>(cp);
+                                const double2 old = *reinterpret_cast<const double2 *>(cp);
                                 o.x = alpha * v0 + beta * old.x; o.y = alpha * v1 + beta * old.y;
                             }
                             *reinterpret_cast<double2 *>(cp) = o;
@@ -397,6 +482,7 @@ rb_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                             if (ok1) cp[1] = (beta == 0.0) ? alpha * v1 : alpha * v1 + beta * cp[1];
                         }
                     }
+                }
             }
         }
     }
@@ -628,6 +714,7 @@ int rb_gemm_core(rb_ctx *ctx, bool ta, bool tb, i64 m, i64 n, i64 k, double alph
         p.alpha = alpha; p.beta = beta; p.c = c; p.ldc = ldc; p.stride_c = stride_c; p.tri = tri;
         p.partial = nullptr; p.ldp = (m + 1) & ~(i64)1;
         p.a_batched = a_batched ? 1 : 0; p.b_batched = b_batched ? 1 : 0;
+        p.sched = ctx->sched;
         if (splits > 1) {
             void *ws;
             RB_TRY(rb_ws_reserve(ctx, 1, splits * batch * n * p.ldp * 8, &ws));

@@ -34,15 +34,21 @@ static i64 ws_budget_bytes(rb_ctx *ctx)
     return budget;
 }
 
-// P-chunk length: as large as the workspace budget allows, balanced across chunks, multiple of 8.
-static i64 pick_chunk(i64 nx, i64 bytes_per_slab, i64 budget)
+// P-chunk length: as large as the workspace budget allows, balanced across chunks, a multiple of `align` (128 where P
+// is the M index of a GEMM tile, so that only the last chunk has a ragged tile row).
+static i64 pick_chunk(i64 nx, i64 bytes_per_slab, i64 budget, i64 align)
 {
     i64 pc_max = budget / (bytes_per_slab > 0 ? bytes_per_slab : 1);
     if (pc_max < 8) pc_max = 8;
     if (pc_max >= nx) return nx;
     i64 nchunks = rb_cdiv(nx, pc_max);
     i64 pc = rb_cdiv(nx, nchunks);
-    pc = (pc + 7) & ~(i64)7;
+    if (pc >= align && (pc_max / align) * align >= align) {
+        pc = rb_cdiv(pc, align) * align;
+        if (pc > pc_max) pc = (pc_max / align) * align;
+    } else {
+        pc = (pc + 7) & ~(i64)7;
+    }
     return pc < nx ? pc : nx;
 }
 
@@ -62,7 +68,7 @@ extern "C" int rb_ri_ao2mo(rb_ctx *ctx, const double *c_left, int nl, const doub
         return RB_OK;
     }
     RB_REQUIRE(c_left && c_right && ri3ao, "rb_ri_ao2mo: NULL input");
-    const i64 pc = pick_chunk(nx, nb * nl * 8, ws_budget_bytes(ctx));
+    const i64 pc = pick_chunk(nx, nb * nl * 8, ws_budget_bytes(ctx), 128);
     void *ws;
     RB_TRY(rb_ws_reserve(ctx, 0, nb * pc * nl * 8, &ws));
     double *w = (double *)ws;
@@ -71,9 +77,15 @@ extern "C" int rb_ri_ao2mo(rb_ctx *ctx, const double *c_left, int nl, const doub
         // (1) W[(nu,P), a] : 'T','N'  M = nb*pn, N = nl, K = nb
         RB_TRY(rb_gemm_core(ctx, true, false, nb * pn, nl, nb, 1.0, ri3ao + p0 * nb * nb, nb, 0, c_left, nb, 0, 0.0, w,
                             nb * pn, 0, 1, 0));
-        // (2) per a: O_a[P, b] : 'T','N'  M = pn, N = nr, K = nb ; A = W_a [nb x pn], C = out + p0 + a*ldp, ldc = ldp*nl
-        RB_TRY(rb_gemm_core(ctx, true, false, pn, nr, nb, 1.0, w, nb, nb * pn, c_right, nb, 0, 0.0, out + p0,
-                            out_ldp * nl, out_ldp, nl, 0));
+        // (2) per a: O_a[P, b] : 'T','N'  M = pn, N = nr, K = nb ; A = W_a [nb x pn], C = out + p0 + a*ldp, ldc = ldp*nl.
+        // When the chunk is the whole P range of `out` (pn == ldp) the rows (P, a) of all a are one contiguous run in
+        // both W and out, so the nl batches collapse into ONE GEMM with M = pn*nl: no ragged tile row per a.
+        if (pn == out_ldp)
+            RB_TRY(rb_gemm_core(ctx, true, false, pn * nl, nr, nb, 1.0, w, nb, 0, c_right, nb, 0, 0.0, out, out_ldp * nl, 0,
+                                1, 0));
+        else
+            RB_TRY(rb_gemm_core(ctx, true, false, pn, nr, nb, 1.0, w, nb, nb * pn, c_right, nb, 0, 0.0, out + p0,
+                                out_ldp * nl, out_ldp, nl, 0));
     }
     return RB_OK;
 }
@@ -105,7 +117,7 @@ extern "C" int rb_ri_j(rb_ctx *ctx, const double *ri3ao, const double *d, double
 // Upper triangle of k (+)= sum_P Y_P Y_P^T over the given slabs (beta = 0 overwrites, 1 accumulates); no mirroring.
 int rb_ri_k_upper(rb_ctx *ctx, const double *ri3ao, const double *ct, i64 no, double *k, i64 nb, i64 nx, double beta)
 {
-    const i64 pc = pick_chunk(nx, nb * no * 8, ws_budget_bytes(ctx));
+    const i64 pc = pick_chunk(nx, nb * no * 8, ws_budget_bytes(ctx), 8);
     RB_REQUIRE(no * pc <= 2147483647LL, "rb_ri_k: chunk too large");
     void *ws;
     RB_TRY(rb_ws_reserve(ctx, 0, nb * no * pc * 8, &ws));
