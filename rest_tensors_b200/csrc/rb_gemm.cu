@@ -1,27 +1,45 @@
 // rb_gemm.cu -- FP64 GEMM core for sm_100a.
 //
 // sm_100a has no tcgen05 FP64 MMA kind; the FP64 tensor path is warp-level mma.sync.m8n8k4.f64, which ptxas
-// lowers to DMMA.8x8x4.  The fast kernel here is a persistent, warp-specialised pipeline:
+// lowers to DMMA.8x8x4 (measured 37.0 TFLOP/s on this pool's B200 = one DMMA per 16 clk per SM sub-partition).
+// The fast kernel is a persistent, warp-specialised pipeline, one CTA of 384 threads per SM:
 //
-//   producer warp : one elected lane issues TMA (cp.async.bulk.tensor.3d) box loads of the A and B tiles into a
-//                   3-stage shared-memory ring, completion signalled on per-stage "full" mbarriers;
-//   8 consumer warps (2 x 4): each owns a 64 x 32 slice of the 128 x 128 CTA tile as 8 x 4 DMMA 8x8 tiles
-//                   (128 accumulator registers), reads fragments with conflict-free LDS.128, and releases the
-//                   stage on a per-stage "empty" mbarrier.
+//   producer warp : one elected lane owns all index arithmetic.  It takes work items from a dynamic scheduler (first
+//                   item static, then a global atomic counter fetched one tile ahead; the last CTA re-arms the
+//                   counter), decodes (batch, tile, k-split), picks the warp grid for ragged tiles, publishes a tile
+//                   descriptor in a small shared-memory queue, and issues TMA (cp.async.bulk.tensor.3d; third
+//                   coordinate = batch) box loads of the A and B tiles into a 3-stage ring of 64 KB stages, completion
+//                   signalled on per-stage "full" mbarriers.  setmaxnreg moves registers from this warpgroup (56) to
+//                   the consumers (224).
+//   8 consumer warps: each owns up to 2 x 4 blocks of 16 x 16 (32 x 64 of the 128 x 128 CTA tile = 32 DMMA 8x8
+//                   accumulator tiles = 128 registers), reads fragments with conflict-free LDS.128, and releases the
+//                   stage on a per-stage "empty" mbarrier.  The descriptor arrives with the tile's first stage, so
+//                   the consumers do no integer divisions; their per-tile code is ~300 instructions.
+//
+// The DMMA computes the TRANSPOSED 8x8 tile (A-operand = the B-matrix fragment, B-operand = the A-matrix fragment):
+// its accumulator fragment then gives a thread two consecutive rows m = 2t, 2t+1 of column n = g, i.e. 16-byte stores
+// along M straight from the accumulator registers (no shuffles, no selects), 64 contiguous bytes per 4 lanes.
 //
 // Operand layouts in shared memory (chosen so that every fragment read is one LDS.128 with no bank conflicts):
 //   K-major operand (op='T' for A, 'N' for B; element (r,k) at k + r*ld):  TMA box {8 k, 128 rows}, no swizzle,
-//       smem [kb][row][8 doubles]; a quarter-warp reads two 64-byte rows that sit in opposite halves of a 128-byte
-//       bank window.  The 16 bytes a lane reads are k = 2t, 2t+1 -> the two DMMAs of a k8 block use the k-sets
-//       {0,2,4,6} and {1,3,5,7} (the summation index may be permuted freely as long as A and B agree).
+//       smem [k8-block][row][8 doubles]; lanes (g, t) read row g (tile e) / 8+g (tile o), bytes 16t..16t+15: a
+//       quarter-warp covers two adjacent 64-byte rows = one 128-byte bank window.  The 16 bytes are k = 2t, 2t+1 ->
+//       the two DMMAs of a k8 block use the k-sets {0,2,4,6} and {1,3,5,7} (the summation index may be permuted
+//       freely as long as A and B agree).
 //   MN-major operand (op='N' for A, 'T' for B; element (r,k) at r + k*ld): TMA box {16 rows, 32 k}, SWIZZLE_128B,
-//       smem [rowblock][k][16 doubles ^ swizzle]; a lane reads rows (2g, 2g+1) of a 16-row block at k = 2t+j.
-//   The rows (2g, 2g+1) of every 16-row block end up in the same thread (one in each of the two 8-row DMMA
-//   tiles), so the epilogue stores 16 bytes per thread and 128 contiguous bytes per 8 lanes along M.
+//       smem [16-row block][k][16 doubles ^ swizzle]; a lane reads rows (2g, 2g+1) of a block at k = 2t+j, so the
+//       e / o DMMA tiles are the even / odd rows.
 //
-// Work decomposition: work item = (batch, tile_m, tile_n, k-split); grouped rasterisation (8 tile rows per group)
-// keeps the operands of concurrently running CTAs in L2; `tri` enumerates only the tiles of one triangle (SYRK);
-// split-K writes partials that a second kernel reduces in a fixed order (deterministic, no FP64 atomics).
+// K is consumed at k8 granularity: full 32-deep stages run a fully unrolled body, the last stage only its valid k8
+// blocks (TMA zero-fills out-of-range rows / k, so edge tiles need no special loads).  Ragged tiles are worked on at
+// 16 x 16 block granularity: the 8 warps form a gm x gn grid chosen per tile so that the busiest warp has as few
+// blocks as possible, and the k loop is specialised on (blocks_m, blocks_n) per warp OUTSIDE the loop -- every DMMA is
+// unpredicated and the hot loop has no dispatch.
+//
+// Work item = (batch, tile_m, tile_n, k-split); grouped rasterisation (8 tile rows per group) keeps the operands of
+// concurrently running CTAs in L2; `tri` enumerates only the tiles of one triangle (SYRK); split-K writes partials
+// that a second kernel reduces in a fixed order (deterministic, no FP64 atomics; the dynamic scheduler only changes
+// WHICH CTA computes a tile, never how).
 //
 // A second, generic kernel (plain loads, any alignment / leading dimension) covers operands TMA cannot describe.
 #include "rb_common.cuh"

@@ -190,11 +190,13 @@ class ShardedRI:
         return self
 
     def ao2mo(self, c_left: torch.Tensor, nl: int, c_right: torch.Tensor, nr: int,
-              out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """local rows ri3mo[P_lo..P_hi, :, :] as a dense [nx_local, nl, nr] column-major buffer (no communication)"""
+              out: Optional[torch.Tensor] = None, out_ldp: Optional[int] = None) -> torch.Tensor:
+        """local rows ri3mo[P_lo..P_hi, :, :] as a dense [nx_local, nl, nr] column-major buffer (no communication).
+        With out_ldp > nx_local the rows land in a wider P-fastest tensor (out already offset to this shard's first P):
+        that is how a rank's pitched sub-array of the global ri3mo is written in place."""
         if out is None:
             out = self.ctx.empty(self.nx * nl * nr)
-        self.ctx.ri_ao2mo(c_left, nl, c_right, nr, self.data, out, self.nb, self.nx)
+        self.ctx.ri_ao2mo(c_left, nl, c_right, nr, self.data, out, self.nb, self.nx, out_ldp)
         return out
 
     def dp(self, dm: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:

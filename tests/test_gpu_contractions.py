@@ -134,11 +134,49 @@ def test_host_dgemm_wrappers(rt, oracle_blas):
     assert A.ddot(A) is None
 
 
+def test_dgemm_many_tiles_dynamic_scheduler(ctx, oracle_blas):
+    """More tiles than SMs (ragged edges in both directions, K tail not a multiple of 8 or 32): the tiles beyond the
+    first wave come from the global work counter; repeated launches must re-arm it and reproduce the same bits."""
+    for ta, tb, (m, n, k) in [("T", "N", (2100, 1420, 77)), ("N", "N", (1700, 1900, 40)), ("N", "T", (2570, 1300, 9)),
+                              ("T", "T", (1330, 2050, 100))]:
+        ra, ca = (m, k) if ta == "N" else (k, m)
+        rb, cb = (k, n) if tb == "N" else (n, k)
+        a = oracle_blas.fill_linear(ra * ca, 41); b = oracle_blas.fill_linear(rb * cb, 42)
+        c_ref = np.zeros(m * n)
+        oracle_blas.dgemm(ta, tb, m, n, k, 1.0, a, ra, b, rb, 0.0, c_ref, m)
+        ad, bd = _dev(ctx, a), _dev(ctx, b)
+        first = None
+        for rep in range(4):
+            cd = torch.full((m * n,), float("nan"), dtype=torch.float64, device=ad.device)
+            ctx.dgemm(ta, tb, m, n, k, 1.0, ad, ra, bd, rb, 0.0, cd, m)
+            if first is None:
+                first = cd.clone()
+                assert_close_1e10(first.cpu().numpy(), c_ref, f"many-tile dgemm {ta}{tb} {m}x{n}x{k}")
+            else:
+                assert torch.equal(cd, first), "GEMM result must not depend on which CTA computed a tile"
+
+
+def test_dgemm_split_k_deterministic(ctx, oracle_blas):
+    """few tiles + deep K -> split-K partials reduced in a fixed order: bitwise repeatable, 1e-10 vs OpenBLAS."""
+    m, n, k = 200, 130, 20000
+    a = oracle_blas.fill_linear(m * k, 43); b = oracle_blas.fill_linear(k * n, 44)
+    c_ref = np.zeros(m * n)
+    oracle_blas.dgemm("N", "N", m, n, k, 1.0, a, m, b, k, 0.0, c_ref, m)
+    ad, bd = _dev(ctx, a), _dev(ctx, b)
+    outs = []
+    for _ in range(3):
+        cd = ctx.empty(m * n)
+        ctx.dgemm("N", "N", m, n, k, 1.0, ad, m, bd, k, 0.0, cd, m)
+        outs.append(cd.clone())
+    assert_close_1e10(outs[0].cpu().numpy(), c_ref, "split-K dgemm")
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
+
+
 # ---------------------------------------------------------------- SYRK / SYMM / GEMV ----
 @pytest.mark.parametrize("uplo", "UL")
 @pytest.mark.parametrize("trans", "NT")
 def test_dsyrk(rt, oracle_blas, uplo, trans):
-    for n, k in [(5, 3), (130, 70), (264, 1500), (600, 64)]:
+    for n, k in [(5, 3), (130, 70), (264, 1500), (600, 64), (1500, 24)]:
         ra, ca = (n, k) if trans == "N" else (k, n)
         a = oracle_blas.fill_linear(ra * ca, 31)
         c0 = oracle_blas.fill_linear(n * n, 32)
@@ -233,6 +271,26 @@ def test_ao2mo_multi_chunk_host_pipeline(rt, oracle_blas):
     ref = oracle_blas.ri_ao2mo_f(c, ri, nb, nb, nx)
     got = rt.RIFull.from_vec([nb, nb, nx], ri).ao2mo(rt.MatrixFull.from_vec([nb, nb], c))
     assert_close_1e10(got.data, ref, "pipelined host ao2mo")
+
+
+def test_ao2mo_device_chunked_matches_single_pass(ctx, oracle_blas):
+    """Device path: a small workspace budget forces several P-chunks (strided-batched GEMM 2, ragged last chunk); the
+    single-chunk path runs GEMM 2 as one flat GEMM.  Both must agree with the reference algorithm and, since every
+    output element is the same fixed-order sum either way, with each other bit for bit."""
+    from rest_tensors_b200.device import ShardedRI
+    nb, nx = 72, 333
+    ri, c, _, _ = _inputs(oracle_blas, nb, nx, 1, False)
+    ref = oracle_blas.ri_ao2mo_f(c, ri, nb, nb, nx)
+    sh = ShardedRI(ctx, nb, nx, data=_dev(ctx, ri))
+    cd = _dev(ctx, c)
+    one = sh.ao2mo(cd, nb, cd, nb).clone()
+    assert_close_1e10(one.cpu().numpy(), ref, "device ao2mo, one chunk")
+    # sub-shards written into a wider output (out_ldp = nx > chunk) take the batched path
+    out = ctx.empty(nx * nb * nb)
+    for p0, p1 in [(0, 128), (128, 300), (300, nx)]:
+        part = ShardedRI(ctx, nb, p1 - p0, data=sh.data[nb * nb * p0: nb * nb * p1].clone())
+        part.ao2mo(cd, nb, cd, nb, out=out[p0:], out_ldp=nx)
+    assert torch.equal(out, one), "chunked (batched GEMM 2) and single-pass (flat GEMM 2) ao2mo must agree bitwise"
 
 
 def test_ao2mo_full_size_identity_property(ctx):
