@@ -39,6 +39,25 @@ METRIC = "RI ao2mo + JK build FP64 GFLOP/s"
 UNIT = "GFLOP/s"
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Libraries (NCCL's version banner, OpenBLAS warnings) write to fd 1; the contract is ONE JSON line on stdout.
+    Point fd 1 at stderr for the duration of the run and keep the real stdout for emit_json_line()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json_line(obj):
+    sys.stdout.flush()
+    data = (json.dumps(obj) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def flops(nb, nx, no):
     """algorithmic flop of one step over nx slabs"""
     return {
@@ -107,6 +126,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    quiet_stdout()
     nb, nx, no, desc = CONFIGS[args.config]
     cpu = CpuPath(nb, no)
     slabs = cpu.calibrate(target_s=3.0, max_slabs=nx)
@@ -130,7 +150,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_json_line(line)
     return 0
 
 
@@ -192,6 +212,24 @@ def run_e2e(args, torch, dist, lib, check, all_reduce_sum, world, dev, nb, nx, n
     import ctypes as C
     if args.no_e2e:
         return {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "skipped": "--no-e2e"}
+    # Host placement: pin this rank's host buffers next to its GPU's PCIe root (8 ranks streaming through the far
+    # socket share one inter-socket link otherwise).  Restored afterwards so the CPU baseline sees every core.
+    saved_affinity = os.sched_getaffinity(0)
+    node = C.c_int(-1)
+    if not args.no_numa:
+        check(lib.rb_bind_host_to_device_numa(int(dev.split(":")[1]), C.byref(node)), "rb_bind_host_to_device_numa")
+    try:
+        out = _run_e2e_bound(args, torch, dist, lib, check, all_reduce_sum, world, dev, nb, nx, no, n2, sh, c, dm, ct, mo, k,
+                             total_flop, barrier)
+    finally:
+        os.sched_setaffinity(0, saved_affinity)
+    out["host_numa_node"] = int(node.value)
+    return out
+
+
+def _run_e2e_bound(args, torch, dist, lib, check, all_reduce_sum, world, dev, nb, nx, no, n2, sh, c, dm, ct, mo, k, total_flop,
+                   barrier):
+    import ctypes as C
     slabs = nx
     avail = host_mem_available_bytes()
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
@@ -260,6 +298,7 @@ def run_e2e(args, torch, dist, lib, check, all_reduce_sum, world, dev, nb, nx, n
 # our arm
 # --------------------------------------------------------------------------------------------------------------
 def run_ours(args):
+    quiet_stdout()
     import ctypes as C
     import numpy as np
     import torch
@@ -404,7 +443,7 @@ def run_ours(args):
     }
     if cpu_baseline is not None:
         line["cpu_baseline"] = cpu_baseline
-    print(json.dumps(line), flush=True)
+    emit_json_line(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -418,6 +457,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-numa", action="store_true", help="e2e leg: do not bind the rank to its GPU's NUMA node")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-pointer e2e leg (e.g. config D: 2 x 15.5 GB pinned per rank)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -226,6 +226,13 @@ int rb_hbm_copy_probe(rb_ctx *ctx, int64_t bytes, int iters, double *gbs_out);
  * (sum of both directions), 4 D2H by kernel stores into mapped pinned memory, 5 like 4 with rows of `width` bytes. */
 int rb_pcie_probe(rb_ctx *ctx, int mode, int64_t bytes, int64_t width, int iters, double *gbs_out);
 
+/* Host placement helper for the host-pointer paths on multi-socket boxes: restrict the calling thread (and the
+ * threads / allocations it makes afterwards) to the CPUs of the NUMA node `device` hangs off, so that pinned buffers
+ * are first-touched next to the GPU's PCIe root and its DMA does not cross the socket interconnect.  Call it once
+ * per rank before allocating ri3ao / ri3mo.  Writes the node (or -1 when the platform reports none) to *node_out.
+ * Returns RB_OK also when there is nothing to bind to (single-node hosts). */
+int rb_bind_host_to_device_numa(int device, int *node_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -120,6 +120,7 @@ SIGNATURES = {
     "rb_fp64_peak_probe": (C.c_int, [c_vp, C.c_int, C.c_int, c_dp, c_dp]),
     "rb_hbm_copy_probe": (C.c_int, [c_vp, c_i64, C.c_int, c_dp]),
     "rb_pcie_probe": (C.c_int, [c_vp, C.c_int, c_i64, c_i64, C.c_int, c_dp]),
+    "rb_bind_host_to_device_numa": (C.c_int, [C.c_int, c_ip]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

@@ -1,5 +1,8 @@
 // rb_api.cu -- context, error reporting, memory helpers, FP64/HBM probes.
 #include "rb_common.cuh"
+#include <sched.h>
+#include <cstring>
+#include <cctype>
 #include <cstring>
 
 static thread_local char g_err[1024] = "";
@@ -185,6 +188,45 @@ rb_ctx *rb_default_ctx(void)
     }
     cudaSetDevice(g_default->device);
     return g_default;
+}
+
+// ---- host placement -----------------------------------------------------------------------------------------
+// sysfs: /sys/bus/pci/devices/<domain:bus:dev.fn>/{numa_node,local_cpulist}
+static bool read_line(const char *path, char *buf, size_t n)
+{
+    FILE *f = fopen(path, "r");
+    if (!f) return false;
+    bool ok = fgets(buf, (int)n, f) != nullptr;
+    fclose(f);
+    return ok;
+}
+
+extern "C" int rb_bind_host_to_device_numa(int device, int *node_out)
+{
+    if (node_out) *node_out = -1;
+    char bus[32] = {0};
+    RB_CUDA(cudaDeviceGetPCIBusId(bus, sizeof bus, device));
+    for (char *c = bus; *c; ++c) *c = (char)tolower((unsigned char)*c);
+    char path[128], line[4096];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    int node = -1;
+    if (read_line(path, line, sizeof line)) node = atoi(line);
+    if (node_out) *node_out = node;
+    if (node < 0) return RB_OK; // no NUMA information: leave the affinity alone
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/local_cpulist", bus);
+    if (!read_line(path, line, sizeof line)) return RB_OK;
+    cpu_set_t want, have, both;
+    CPU_ZERO(&want);
+    for (char *tok = strtok(line, ",\n"); tok; tok = strtok(nullptr, ",\n")) { // "0-31,64-95"
+        int lo = 0, hi = 0;
+        if (sscanf(tok, "%d-%d", &lo, &hi) == 2) { for (int c = lo; c <= hi && c < CPU_SETSIZE; ++c) CPU_SET(c, &want); }
+        else if (sscanf(tok, "%d", &lo) == 1 && lo < CPU_SETSIZE) CPU_SET(lo, &want);
+    }
+    if (sched_getaffinity(0, sizeof have, &have) != 0) return RB_OK;
+    CPU_AND(&both, &want, &have); // never widen what the container / launcher allowed
+    if (CPU_COUNT(&both) == 0) return RB_OK;
+    if (sched_setaffinity(0, sizeof both, &both) != 0) return RB_OK;
+    return RB_OK;
 }
 
 // ---- probes ------------------------------------------------------------------------------------------------
