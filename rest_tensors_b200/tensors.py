@@ -6,7 +6,9 @@ behaviour as the reference's Rust structs, so that the parity tests read like th
     RIFull        src/ri.rs:18-433
     MatrixFull    src/matrix/mod.rs:472-480, src/matrix/matrixfull.rs
     MatrixUpper   src/matrix/matrixupper.rs:231-420, src/index.rs:209-233
-    _dgemm, _dgemm_full, _dgemm_full_new, _dsyrk, _dsymm, _dgemv      src/matrix/matrix_blas_lapack.rs
+    MatrixFullSlice(Mut), MatrixUpperSlice, MatrixUpperStepBy, map_upper_to_full, map_full_to_upper
+    _dgemm, _dgemm_full, _dgemm_full_new, _dsyrk, _dsymm, _dgemv, general_check_shape,
+    _dgemm_nn(_serial), _dgemm_tn(_serial), _dgemm_tn_v02            src/matrix/matrix_blas_lapack.rs
     ri_ao2mo_f, general_dgemm_f, special_dgemm_f_01, matr_copy, ...   src/external_libs/mod.rs
 
 ``data`` is a flat column-major ``numpy.float64`` array (the Rust ``Vec<f64>``).  A Rust ``panic!`` is a Python
@@ -221,6 +223,33 @@ class MatrixFull:
             raise ValueError("Error in tranforming MatrixFull to RIFull: incompitable size")
         return RIFull([i, j, k], [1, i, j], self.data.copy())
 
+    # -- views (matrixfull.rs:648-672): zero-copy, share ``data`` with the parent like the Rust borrows --
+    def to_matrixfullslice(self) -> "MatrixFullSlice":
+        return MatrixFullSlice(self.size[0:2], self.indicing[0:2], self.data)
+
+    def to_matrixfullslicemut(self) -> "MatrixFullSliceMut":
+        return MatrixFullSliceMut(self.size[0:2], self.indicing[0:2], self.data)
+
+    def to_matrixfullslice_columns(self, range_columns: Range) -> "MatrixFullSlice":
+        """matrixfull.rs:664-672 (keeps the reference's indicing quirk [0, rows])"""
+        start = range_columns[0] * self.indicing[1]
+        end = start + _rlen(range_columns) * self.indicing[1]
+        return MatrixFullSlice([self.size[0], _rlen(range_columns)], [0, self.size[0]], self.data[start:end])
+
+    def iter_matrixupper(self) -> Optional["MatrixUpperStepBy"]:
+        """matrixfull.rs:407-413: None unless square and non-empty; yields a[i + j*n], i <= j, in packed order"""
+        x, y = self.size
+        if x == 0 or y == 0 or x != y:
+            return None
+        return MatrixUpperStepBy(iter(range(x * y)), [x, y], source=self.data)
+
+    def iter_matrixupper_mut(self) -> Optional["MatrixUpperStepBy"]:
+        """matrixfull.rs:415-423: same walk; the items are linear positions to assign through (`data[pos] = v`)"""
+        x, y = self.size
+        if x == 0 or y == 0 or x != y:
+            return None
+        return MatrixUpperStepBy(iter(range(x * y)), [x, y])
+
     def copy_from_matr(self, range_x: Range, range_y: Range, from_matr: "MatrixFull", f_range_x: Range,
                        f_range_y: Range) -> None:
         """matrixfull.rs:1388-1396 -> matr_copy -> copy_mm_"""
@@ -356,6 +385,9 @@ class MatrixUpper:
         check(lib.rb_host_to_matrixfull(_ptr(self.data), self.size, _ptr(out.data)), "MatrixUpper::to_matrixfull")
         return out
 
+    def to_matrixupperslice(self) -> "MatrixUpperSlice":
+        return MatrixUpperSlice(self.data)
+
     def _zip(self, other: "MatrixUpper", op: int) -> "MatrixUpper":
         """matrixupper.rs:395-420: zip silently truncates to the shorter operand"""
         out = MatrixUpper(self.size, self.data.copy())
@@ -439,6 +471,20 @@ class RIFull:
         s0, s1, s2 = self.size
         cube = self.data[: s0 * s1 * s2].reshape((s0, s1, s2), order="F")
         return cube[x[0]:x[1], y[0]:y[1], z[0]:z[1]].reshape(-1, order="F")
+
+    def get_slices_mut(self, x: Range, y: Range, z: Range):
+        """ri.rs:130-166 (`get_slices_mut`, `_v01`, `_v02` differ only in how the Vec is built): the x-runs as a list
+        of writable views into ``data`` in (z outer, y inner) order -- the Rust `Vec<&mut [T]>` before flattening"""
+        len_y, len_z = self.indicing[1], self.indicing[2]
+        out = []
+        for zz in range(z[0], z[1]):
+            for yy in range(y[0], y[1]):
+                start = x[0] + yy * len_y + zz * len_z
+                out.append(self.data[start:start + _rlen(x)])
+        return out
+
+    get_slices_mut_v01 = get_slices_mut
+    get_slices_mut_v02 = get_slices_mut
 
     # -- transposes (ri.rs:227-294) --
     def _transpose(self, which: int, new_size) -> "RIFull":
@@ -557,8 +603,209 @@ class RIFull:
 
 
 # ======================================================================================================
+# views and index maps
+# ======================================================================================================
+class MatrixFullSlice:
+    """src/matrix/matrixfullslice.rs:184-188: borrowed column-major view (``size``, ``indicing``, ``data`` slices)."""
+
+    def __init__(self, size, indicing, data: np.ndarray):
+        self.size = [int(size[0]), int(size[1])]
+        self.indicing = list(indicing)
+        self.data = data
+
+    def get_slice_x(self, y: int) -> np.ndarray:
+        """matrixfullslice.rs:292-296"""
+        return self.data[self.indicing[1] * y: self.indicing[1] * (y + 1)]
+
+    def transpose(self) -> MatrixFull:
+        """matrixfullslice.rs:298-318"""
+        r, c = self.size
+        out = MatrixFull.new([c, r], 0.0)
+        if r * c:
+            src = np.ascontiguousarray(self.data[: r * c])
+            check(lib.rb_host_matrix_transpose(_ptr(src), r, c, _ptr(out.data)), "MatrixFullSlice::transpose")
+        return out
+
+    transpose_and_drop = transpose
+
+    def ddot(self, b: "MatrixFullSlice") -> Optional[MatrixFull]:
+        """matrix_blas_lapack.rs:714-730: a*b accumulated (beta = 1) onto a zeroed C; None on a shape mismatch"""
+        if self.size[1] != b.size[0]:
+            return None
+        m, n, k = self.size[0], b.size[1], self.size[1]
+        c = MatrixFull.new([m, n], 0.0)
+        check(lib.rb_host_dgemm(b'N', b'N', m, n, k, 1.0, _ptr(self.data), max(m, 1), _ptr(b.data), max(k, 1), 1.0,
+                                _ptr(c.data), max(m, 1)), "MatrixFullSlice::ddot")
+        return c
+
+
+class MatrixFullSliceMut(MatrixFullSlice):
+    """src/matrix/matrixfullslice.rs (MatrixFullSliceMut): the mutable view; writes land in the parent's ``data``."""
+
+    def lapack_dgemm(self, a: MatrixFullSlice, b: MatrixFullSlice, opa: str, opb: str, alpha: float, beta: float) -> None:
+        """matrix_blas_lapack.rs:739-774: c = alpha*op(a)*op(b) + beta*c (the reference's shape check is disabled)"""
+        m = a.size[0] if opa == 'N' else a.size[1]
+        k = a.size[1] if opa == 'N' else a.size[0]
+        n = b.size[1] if opb == 'N' else b.size[0]
+        lda = max(m, 1) if opa == 'N' else max(k, 1)
+        ldb = max(k, 1) if opb == 'N' else max(n, 1)
+        check(lib.rb_host_dgemm(ch(opa), ch(opb), m, n, k, alpha, _ptr(a.data), lda, _ptr(b.data), ldb, beta,
+                                _ptr(self.data), max(m, 1)), "MatrixFullSliceMut::lapack_dgemm")
+
+
+class MatrixUpperSlice:
+    """src/matrix/matrixupper.rs:507-520: borrowed packed-upper view."""
+
+    def __init__(self, data: np.ndarray):
+        self.size = int(data.size)
+        self.data = data
+
+    @staticmethod
+    def from_vec(new_vec: np.ndarray) -> "MatrixUpperSlice":
+        return MatrixUpperSlice(new_vec)
+
+    def to_matrixfull(self) -> Optional[MatrixFull]:
+        """matrixupper.rs:521-561: unpack + mirror; None unless the length is triangular"""
+        n = int((1.0 + 8.0 * float(self.size)) ** 0.5 * 0.5 - 0.5)
+        if n * (n + 1) // 2 != self.size:
+            return None
+        if self.size == 0:
+            return MatrixFull.empty()
+        out = MatrixFull.new([n, n], 0.0)
+        src = np.ascontiguousarray(self.data)
+        check(lib.rb_host_to_matrixfull(_ptr(src), self.size, _ptr(out.data)), "MatrixUpperSlice::to_matrixfull")
+        return out
+
+
+class MatrixUpperStepBy:
+    """src/matrix/matrix_trait.rs:170-217: iterator adaptor that walks a column-major n x n sequence and keeps the
+    positions with row <= column (the packed-upper order).  ``iter`` yields linear positions; with ``source`` the items
+    are the elements at those positions (the `Iter<T>` form), without it the positions themselves (`IterMut` form)."""
+
+    def __init__(self, it, size, shift: int = 0, source: Optional[np.ndarray] = None):
+        self.iter = it
+        self.size = [int(size[0]), int(size[1])]
+        self.step = self.size[0]
+        self.position = int(shift)
+        self.first_take = True
+        self._source = source
+
+    @staticmethod
+    def new_shift(it, size, shift: int) -> "MatrixUpperStepBy":
+        return MatrixUpperStepBy(it, size, shift)
+
+    def _nth(self, n: int):
+        v = None
+        for _ in range(n + 1):
+            v = next(self.iter)  # StopIteration ends the walk exactly like `None` from `nth`
+        return v
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        curr_row = self.position % self.size[0]
+        curr_column = self.position // self.size[0]
+        if self.first_take:
+            self.position += 1
+            self.first_take = False
+            pos = self._nth(self.position - 1)
+        elif curr_row <= curr_column:
+            self.position += 1
+            pos = next(self.iter)
+        else:
+            step = self.size[0] - curr_column
+            self.position += step
+            pos = self._nth(step - 1)
+        return pos if self._source is None else float(self._source[pos])
+
+
+def map_upper_to_full(size: int) -> Optional[np.ndarray]:
+    """matrixupper.rs:587-604: packed index -> [i, j] (an int array [size, 2], the `MatrixUpper<[usize;2]>` data);
+    None unless ``size`` is triangular.  Integer index arithmetic only."""
+    n = int((1.0 + 8.0 * float(size)) ** 0.5 * 0.5 - 0.5)
+    if n * (n + 1) // 2 != size:
+        return None
+    j = np.repeat(np.arange(n, dtype=np.int64), np.arange(1, n + 1, dtype=np.int64))
+    i = np.arange(size, dtype=np.int64) - j * (j + 1) // 2
+    return np.stack([i, j], axis=1)
+
+
+def map_full_to_upper(size) -> Optional[np.ndarray]:
+    """matrixupper.rs:605-617: n x n column-major int matrix holding the packed index at every i <= j (0 elsewhere);
+    None unless square.  (The reference fills it through iter_matrixupper_mut, which is None for n == 0.)"""
+    if size[0] != size[1]:
+        return None
+    n = int(size[0])
+    out = np.zeros(n * n, dtype=np.int64)
+    if n:
+        m = map_upper_to_full(n * (n + 1) // 2)
+        out[m[:, 0] + m[:, 1] * n] = np.arange(m.shape[0], dtype=np.int64)
+    return out
+
+
+# ======================================================================================================
 # matrix_blas_lapack (src/matrix/matrix_blas_lapack.rs)
 # ======================================================================================================
+def general_check_shape(matr_a, matr_b, opa: str, opb: str) -> bool:
+    """matrix_blas_lapack.rs:14-34 (as written there: equal sizes for NN / TT, reversed-equal for TN / NT)"""
+    sa, sb = list(matr_a.size), list(matr_b.size)
+    if (opa, opb) in (('N', 'N'), ('T', 'T')):
+        return all(a == b for a, b in zip(sa, sb))
+    if (opa, opb) in (('T', 'N'), ('N', 'T')):
+        return all(a == b for a, b in zip(reversed(sa), sb))
+    return False
+
+
+def _dgemm_nn(mat_a, mat_b) -> MatrixFull:
+    """matrix_blas_lapack.rs:1185-1203: c = a*b.  The reference's rayon / scalar loops (and `_dgemm_nn_serial`,
+    1206-1221) define only a summation order; here all of them are the DMMA GEMM (1e-10 parity, not bitwise)."""
+    (ax, ay), (bx, by) = mat_a.size, mat_b.size
+    if ay != bx:
+        raise ValueError("For the input matrices: mat_a[ax,ay], mat_b[bx,by], ay!=bx. dgemm false")
+    c = MatrixFull.new([ax, by], 0.0)
+    if ax == 0 or by == 0:
+        return c
+    check(lib.rb_host_dgemm(b'N', b'N', ax, by, ay, 1.0, _ptr(mat_a.data), max(ax, 1), _ptr(mat_b.data), max(bx, 1), 0.0,
+                            _ptr(c.data), max(ax, 1)), "_dgemm_nn")
+    return c
+
+
+_dgemm_nn_serial = _dgemm_nn
+
+
+def _dgemm_tn(mat_a, mat_b) -> MatrixFull:
+    """matrix_blas_lapack.rs:1224-1237 (`_dgemm_tn_serial`: 1240-1253): c = a^T*b"""
+    (ax, ay), (bx, by) = mat_a.size, mat_b.size
+    if ax != bx:
+        raise ValueError("For the input matrices: mat_a[ax,ay], mat_b[bx,by], ay!=bx. dgemm false")
+    c = MatrixFull.new([ay, by], 0.0)
+    if ay == 0 or by == 0:
+        return c
+    check(lib.rb_host_dgemm(b'T', b'N', ay, by, ax, 1.0, _ptr(mat_a.data), max(ax, 1), _ptr(mat_b.data), max(bx, 1), 0.0,
+                            _ptr(c.data), max(ay, 1)), "_dgemm_tn")
+    return c
+
+
+_dgemm_tn_serial = _dgemm_tn
+
+
+def _dgemm_tn_v02(mat_a, mat_b, to_slice) -> None:
+    """matrix_blas_lapack.rs:1254-1271: c = a^T*b written through ``to_slice`` -- the flattened x-runs of
+    RIFull::get_slices_mut (a list of writable views), column-major [ay, by] across the concatenation."""
+    (ax, ay), (bx, by) = mat_a.size, mat_b.size
+    if ax != bx:
+        raise ValueError("For the input matrices: mat_a[ax,ay], mat_b[bx,by], ay!=bx. dgemm false")
+    c = _dgemm_tn(mat_a, mat_b)
+    off = 0
+    for run in to_slice:  # zip semantics: stops at the shorter of (destination, ay*by)
+        n = min(run.size, c.data.size - off)
+        if n <= 0:
+            break
+        run[:n] = c.data[off:off + n]
+        off += n
+
+
 def _gemm_shape_ok(sa, opa, sb, opb, sc) -> bool:
     key = (opa, opb)
     if key == ('N', 'N'):

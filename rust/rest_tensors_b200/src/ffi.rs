@@ -9,6 +9,8 @@ extern "C" {
     pub fn rb_ctx_create(device: c_int, out: *mut *mut RbCtx) -> c_int;
     pub fn rb_ctx_destroy(ctx: *mut RbCtx) -> c_int;
     pub fn rb_ctx_sync(ctx: *mut RbCtx) -> c_int;
+    /// bind the calling thread to the CPUs next to `device` before allocating pinned ri3ao / ri3mo (multi-socket hosts)
+    pub fn rb_bind_host_to_device_numa(device: c_int, node_out: *mut c_int) -> c_int;
     pub fn rb_dev_alloc(ctx: *mut RbCtx, bytes: i64, out: *mut *mut c_void) -> c_int;
     pub fn rb_dev_free(ctx: *mut RbCtx, p: *mut c_void) -> c_int;
     pub fn rb_host_alloc_pinned(bytes: i64, out: *mut *mut c_void) -> c_int;

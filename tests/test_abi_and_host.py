@@ -100,6 +100,61 @@ def test_slab_views_are_zero_copy(rt):
     assert q.indicing == [1, 2, 3]   # the reference's quirk (matrixfull.rs:681-685)
 
 
+def test_views_iterators_and_index_maps(rt, oracle, golden):
+    """Host-side index logic of the views (no compute): iter_matrixupper order pinned by the reference's own assert
+    (GV4, matrix/mod.rs:437-452), MatrixUpperStepBy, map_upper_to_full / map_full_to_upper, get_slices_mut order."""
+    g = golden["GV4"]
+    n = g["n"]
+    a = rt.MatrixFull.from_vec([n, n], np.array(g["full"], dtype=np.float64))
+    assert list(a.iter_matrixupper()) == g["packed"]
+    assert rt.MatrixFull.new([2, 3], 0.0).iter_matrixupper() is None and rt.MatrixFull.empty().iter_matrixupper() is None
+    # the _mut form walks the same positions; writing through them packs in place
+    b = rt.MatrixFull.new([n, n], 0.0)
+    for k, pos in enumerate(b.iter_matrixupper_mut()):
+        b.data[pos] = float(k)
+    bm = b.data.reshape((n, n), order="F")
+    for j in range(n):
+        for i in range(n):
+            assert bm[i, j] == (oracle.index2d(i, j, n * (n + 1) // 2) if i <= j else 0.0)
+    # index maps
+    for nn in (1, 2, 5, 9):
+        ln = nn * (nn + 1) // 2
+        up = rt.map_upper_to_full(ln)
+        assert up.shape == (ln, 2)
+        for t, (i, j) in enumerate(up.tolist()):
+            assert i <= j and oracle.index2d(i, j, ln) == t
+        full = rt.map_full_to_upper([nn, nn]).reshape((nn, nn), order="F")
+        for j in range(nn):
+            for i in range(nn):
+                assert full[i, j] == (oracle.index2d(i, j, ln) if i <= j else 0)
+    assert rt.map_upper_to_full(5) is None and rt.map_full_to_upper([2, 3]) is None
+    # MatrixUpperStepBy over an arbitrary iterator, with and without a shift
+    assert list(rt.MatrixUpperStepBy(iter("abcdefghi"), [3, 3])) == list("adeghi")
+    assert list(rt.MatrixUpperStepBy.new_shift(iter(range(9)), [3, 3], 3)) == [3, 4, 6, 7, 8]
+    # get_slices_mut: writable x-runs, z outer / y inner
+    r = rt.RIFull.from_vec([3, 2, 4], np.arange(24.0))
+    runs = r.get_slices_mut((1, 3), (0, 2), (1, 3))
+    assert [x.tolist() for x in runs] == [[7.0, 8.0], [10.0, 11.0], [13.0, 14.0], [16.0, 17.0]]
+    runs[2][:] = -1.0
+    assert r.data[13] == -1.0 and r.data[14] == -1.0
+    assert np.concatenate(r.get_slices_mut_v02((0, 3), (1, 2), (0, 1))).tolist() == r.get_slices((0, 3), (1, 2), (0, 1)).tolist()
+    # slices share storage with the parent
+    m = rt.MatrixFull.from_vec([3, 4], np.arange(12.0))
+    sl = m.to_matrixfullslice_columns((1, 3))
+    assert sl.size == [3, 2] and sl.indicing == [0, 3] and sl.data.tolist() == list(np.arange(3.0, 9.0))
+    mut = m.to_matrixfullslicemut(); mut.data[0] = 99.0
+    assert m.data[0] == 99.0 and m.to_matrixfullslice().get_slice_x(1).tolist() == [3.0, 4.0, 5.0]
+    # general_check_shape as written in the reference (equal sizes for NN/TT, reversed for TN/NT)
+    p, q = rt.MatrixFull.new([2, 3], 0.0), rt.MatrixFull.new([3, 2], 0.0)
+    assert rt.general_check_shape(p, p, 'N', 'N') and not rt.general_check_shape(p, q, 'N', 'N')
+    assert rt.general_check_shape(p, q, 'T', 'N') and rt.general_check_shape(p, q, 'N', 'T')
+    assert not rt.general_check_shape(p, q, 'X', 'N')
+    with pytest.raises(ValueError):
+        rt._dgemm_nn(p, p)
+    with pytest.raises(ValueError):
+        rt._dgemm_tn(p, q)
+
+
 def test_wrapper_panics_before_ffi(rt):
     a = rt.MatrixFull.new([3, 3], 1.0); b = rt.MatrixFull.new([3, 3], 1.0); c = rt.MatrixFull.new([3, 3], 0.0)
     with pytest.raises(ValueError):     # shape mismatch, matrix_blas_lapack.rs:146-153

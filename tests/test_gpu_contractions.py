@@ -172,6 +172,43 @@ def test_dgemm_split_k_deterministic(ctx, oracle_blas):
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
 
 
+def test_hand_rolled_gemm_names_and_slice_views(rt, oracle, oracle_blas):
+    """_dgemm_nn / _dgemm_tn / _dgemm_tn_v02 (matrix_blas_lapack.rs:1185-1271) and the MatrixFullSlice(Mut) methods
+    against the BLAS-free oracle loops (the summation order the reference's scalar code uses) and OpenBLAS."""
+    m, k, n = 37, 52, 23
+    a = oracle.fill_linear(m * k, 45); b = oracle.fill_linear(k * n, 46); at = oracle.fill_linear(k * m, 47)
+    A = rt.MatrixFull.from_vec([m, k], a); B = rt.MatrixFull.from_vec([k, n], b); At = rt.MatrixFull.from_vec([k, m], at)
+    ref_nn = np.zeros(m * n); oracle.dgemm("N", "N", m, n, k, 1.0, a, m, b, k, 0.0, ref_nn, m)
+    ref_tn = np.zeros(m * n); oracle.dgemm("T", "N", m, n, k, 1.0, at, k, b, k, 0.0, ref_tn, m)
+    for fn in (rt._dgemm_nn, rt._dgemm_nn_serial):
+        c = fn(A.to_matrixfullslice(), B.to_matrixfullslice())
+        assert c.size == [m, n]
+        assert_close_1e10(c.data, ref_nn, fn.__name__)
+    for fn in (rt._dgemm_tn, rt._dgemm_tn_serial):
+        assert_close_1e10(fn(At.to_matrixfullslice(), B.to_matrixfullslice()).data, ref_tn, fn.__name__)
+    assert rt._dgemm_nn(rt.MatrixFull.new([0, 4], 0.0), rt.MatrixFull.new([4, 3], 0.0)).size == [0, 3]
+    # _dgemm_tn_v02 writes through the x-runs of a RIFull block: here the [m, n] block at (x0, :, z0..) of a tensor
+    x0, sx, sy, sz = 2, m + 5, n, 3
+    ten = rt.RIFull.new([sx, sy, sz], 7.0)
+    rt._dgemm_tn_v02(At.to_matrixfullslice(), B.to_matrixfullslice(), ten.get_slices_mut((x0, x0 + m), (0, n), (1, 2)))
+    cube = ten.data.reshape((sx, sy, sz), order="F")
+    assert_close_1e10(cube[x0:x0 + m, :, 1].reshape(-1, order="F"), ref_tn, "_dgemm_tn_v02")
+    mask = np.ones_like(cube, dtype=bool); mask[x0:x0 + m, :, 1] = False
+    assert np.all(cube[mask] == 7.0)
+    # slice methods
+    assert np.array_equal(A.to_matrixfullslice().transpose().data, oracle.matrix_transpose(a, m, k))
+    assert_close_1e10(A.to_matrixfullslice().ddot(B.to_matrixfullslice()).data, ref_nn, "MatrixFullSlice::ddot")
+    assert A.to_matrixfullslice().ddot(A.to_matrixfullslice()) is None
+    C = rt.MatrixFull.new([m, n], 1.0)
+    ref = np.ones(m * n); oracle_blas.dgemm("T", "N", m, n, k, 0.5, at, k, b, k, 2.0, ref, m)
+    C.to_matrixfullslicemut().lapack_dgemm(At.to_matrixfullslice(), B.to_matrixfullslice(), 'T', 'N', 0.5, 2.0)
+    assert_close_1e10(C.data, ref, "MatrixFullSliceMut::lapack_dgemm")
+    # MatrixUpperSlice::to_matrixfull == MatrixUpper::to_matrixfull (bit-exact data movement)
+    packed = oracle.fill_linear(21, 48)
+    assert np.array_equal(rt.MatrixUpperSlice.from_vec(packed).to_matrixfull().data, oracle.to_matrixfull(packed))
+    assert rt.MatrixUpperSlice.from_vec(np.zeros(4)).to_matrixfull() is None
+
+
 # ---------------------------------------------------------------- SYRK / SYMM / GEMV ----
 @pytest.mark.parametrize("uplo", "UL")
 @pytest.mark.parametrize("trans", "NT")
