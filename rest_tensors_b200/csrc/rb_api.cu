@@ -288,8 +288,13 @@ extern "C" int rb_fp64_peak_probe(rb_ctx *ctx, int kind, int iters, double *tflo
 __global__ void __launch_bounds__(256) rb_copy_probe_kernel(const double2 *__restrict__ src, double2 *__restrict__ dst,
                                                             i64 n2)
 {
-    i64 stride = (i64)gridDim.x * blockDim.x;
-    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) dst[i] = src[i];
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n2; i += 4 * stride) { // 4 independent 16-byte loads in flight per thread
+        const double2 v0 = src[i], v1 = src[i + stride], v2 = src[i + 2 * stride], v3 = src[i + 3 * stride];
+        dst[i] = v0; dst[i + stride] = v1; dst[i + 2 * stride] = v2; dst[i + 3 * stride] = v3;
+    }
+    for (; i < n2; i += stride) dst[i] = src[i];
 }
 
 extern "C" int rb_hbm_copy_probe(rb_ctx *ctx, int64_t bytes, int iters, double *gbs_out)

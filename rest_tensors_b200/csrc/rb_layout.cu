@@ -78,42 +78,75 @@ extern "C" int rb_ri_pack_symm(rb_ctx *ctx, const double *ri, int64_t nao, int64
 
 // ---------------------------------------------------------------------------------------------------------
 // unpack: full[i + j*n] = full[j + i*n] = packed[j(j+1)/2 + i], i <= j          (matrixupper.rs:330-373)
-// One CTA per 32x32 tile pair (ti <= tj): the packed tile is read once (coalesced along i), written to the
-// upper position directly and to the mirrored lower position through a padded smem transpose, so every
-// access is unit-stride.  The reference's mirror loop reads stride-n; this reads each packed byte once.
+// One CTA per 64x64 tile pair (ti <= tj): the packed tile is read once (coalesced along i, 16 loads in flight per
+// thread), parked in shared memory, written to the upper position and -- transposed -- to the mirrored lower
+// position, both with 16-byte stores when n is even.  The reference's mirror loop reads stride-n; this reads each
+// packed byte once and writes each full byte once.
 // ---------------------------------------------------------------------------------------------------------
+constexpr int UT = 64; // tile edge
+
+template <bool VEC>
 __global__ void __launch_bounds__(256) rb_unpack_upper_kernel(const double *__restrict__ packed,
                                                               double *__restrict__ full, i64 n)
 {
-    __shared__ double tile[32][33];
+    __shared__ double tile[UT][UT + 1]; // [column jj][row ii]
     // linear tile-pair index -> (ti <= tj): pair p = tj(tj+1)/2 + ti
-    i64 p = blockIdx.x;
+    const i64 p = blockIdx.x;
     i64 tj = (i64)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
     while (tj * (tj + 1) / 2 > p) --tj;
     while ((tj + 1) * (tj + 2) / 2 <= p) ++tj;
-    i64 ti = p - tj * (tj + 1) / 2;
-    int tx = threadIdx.x & 31, ty = threadIdx.x >> 5; // 32 x 8
-    i64 i0 = ti * 32, j0 = tj * 32;
+    const i64 ti = p - tj * (tj + 1) / 2;
+    const i64 i0 = ti * UT, j0 = tj * UT;
+    {
+        const int tx = threadIdx.x & (UT - 1), ty = threadIdx.x >> 6; // 64 rows x 4 columns per pass
+        const i64 i = i0 + tx;
+        double v[UT / 4];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        int jj = ty + r * 8;
-        i64 i = i0 + tx, j = j0 + jj;
-        double v = 0.0;
-        if (i < n && j < n) {
-            // off-diagonal tiles have i < j everywhere; diagonal tiles fetch the (min,max) element
-            i64 a = i <= j ? i : j, b = i <= j ? j : i;
-            v = packed[b * (b + 1) / 2 + a];
-            full[i + j * n] = v; // upper tile (and, for the diagonal tile, the whole symmetric tile)
+        for (int r = 0; r < UT / 4; ++r) {
+            const i64 j = j0 + ty + r * 4;
+            v[r] = 0.0;
+            if (i < n && j < n) {
+                // off-diagonal tiles have i < j everywhere; the diagonal tile fetches the (min, max) element
+                const i64 lo = i <= j ? i : j, hi = i <= j ? j : i;
+                v[r] = packed[hi * (hi + 1) / 2 + lo];
+            }
         }
-        tile[jj][tx] = v;
-    }
-    if (ti == tj) return;
-    __syncthreads();
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        int ii = ty + r * 8;          // column index inside the mirrored tile = row i of the upper tile
-        i64 row = j0 + tx, col = i0 + ii; // full[row=j, col=i] = upper[i, j]
-        if (row < n && col < n) full[row + col * n] = tile[tx][ii];
+        for (int r = 0; r < UT / 4; ++r) tile[ty + r * 4][tx] = v[r];
+    }
+    __syncthreads();
+    if (VEC) { // n even: rows (2t, 2t+1) of every column start 16-byte aligned
+        const int t2 = threadIdx.x & 31, ty = threadIdx.x >> 5; // 32 row pairs x 8 columns per pass
+#pragma unroll
+        for (int r = 0; r < UT / 8; ++r) {
+            const int jj = ty + r * 8;
+            const i64 i = i0 + 2 * t2, j = j0 + jj;
+            if (i < n && j < n) // n even and i even => i + 1 < n as well
+                *reinterpret_cast<double2 *>(full + i + j * n) = make_double2(tile[jj][2 * t2], tile[jj][2 * t2 + 1]);
+        }
+        if (ti == tj) return; // the diagonal tile is already symmetric
+#pragma unroll
+        for (int r = 0; r < UT / 8; ++r) {
+            const int ii = ty + r * 8; // column of the mirrored tile = row of the upper tile
+            const i64 row = j0 + 2 * t2, col = i0 + ii;
+            if (row < n && col < n)
+                *reinterpret_cast<double2 *>(full + row + col * n) = make_double2(tile[2 * t2][ii], tile[2 * t2 + 1][ii]);
+        }
+    } else {
+        const int tx = threadIdx.x & (UT - 1), ty = threadIdx.x >> 6;
+#pragma unroll
+        for (int r = 0; r < UT / 4; ++r) {
+            const int jj = ty + r * 4;
+            const i64 i = i0 + tx, j = j0 + jj;
+            if (i < n && j < n) full[i + j * n] = tile[jj][tx];
+        }
+        if (ti == tj) return;
+#pragma unroll
+        for (int r = 0; r < UT / 4; ++r) {
+            const int ii = ty + r * 4;
+            const i64 row = j0 + tx, col = i0 + ii;
+            if (row < n && col < n) full[row + col * n] = tile[tx][ii];
+        }
     }
 }
 
@@ -123,10 +156,13 @@ extern "C" int rb_unpack_upper(rb_ctx *ctx, const double *packed, int64_t n, dou
     if (n == 0) return RB_OK;
     RB_REQUIRE(packed && full, "rb_unpack_upper: NULL buffer");
     RB_CUDA(cudaSetDevice(ctx->device));
-    i64 nt = rb_cdiv(n, 32);
+    i64 nt = rb_cdiv(n, UT);
     i64 pairs = nt * (nt + 1) / 2;
     RB_REQUIRE(pairs < 2147483647LL, "rb_unpack_upper: n too large");
-    rb_unpack_upper_kernel<<<(unsigned)pairs, 256, 0, ctx->stream>>>(packed, full, n);
+    if ((n & 1) == 0 && (((uintptr_t)full) & 15) == 0)
+        rb_unpack_upper_kernel<true><<<(unsigned)pairs, 256, 0, ctx->stream>>>(packed, full, n);
+    else
+        rb_unpack_upper_kernel<false><<<(unsigned)pairs, 256, 0, ctx->stream>>>(packed, full, n);
     RB_LAUNCHED(ctx);
     return RB_OK;
 }
@@ -173,26 +209,40 @@ int rb_symmetrize(rb_ctx *ctx, double *c, i64 n, i64 ldc, bool from_upper)
 
 // ---------------------------------------------------------------------------------------------------------
 // Generic strided 3-D copy -- copy_mm / copy_mr / copy_rm / copy_rr and transpose_ikj all reduce to it.
-// VEC=2 moves double2 along i when both sides are unit-stride and 16-byte aligned.
+// A CTA is a (lanes along i) x (rows) thread grid; rows (j, k) are decoded once per row, never per element, and a
+// thread keeps 4 independent loads in flight.  VEC=2 moves double2 along i when both sides are unit-stride and
+// 16-byte aligned.
 // ---------------------------------------------------------------------------------------------------------
 template <int VEC>
 __global__ void __launch_bounds__(256) rb_copy3d_kernel(const double *__restrict__ src, i64 si, i64 sj, i64 sk,
                                                         double *__restrict__ dst, i64 di, i64 dj, i64 dk, i64 ni,
-                                                        i64 nj, i64 nk)
+                                                        i64 nj, i64 nk, int lg_lanes)
 {
-    i64 niv = ni / VEC;
-    i64 rows = nj * nk;
-    i64 total = niv * rows;
-    i64 stride = (i64)gridDim.x * blockDim.x;
-    for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
-        i64 i = t % niv, r = t / niv;
-        i64 j = r % nj, k = r / nj;
+    const int lanes = 1 << lg_lanes;                 // threads along i (power of two <= 256)
+    const int lane = threadIdx.x & (lanes - 1);
+    const int rsub = threadIdx.x >> lg_lanes;        // row handled by this thread inside the CTA's row group
+    const int rows_per_cta = 256 >> lg_lanes;
+    const i64 niv = ni / VEC;
+    const i64 rows = nj * nk;
+    for (i64 r = (i64)blockIdx.x * rows_per_cta + rsub; r < rows; r += (i64)gridDim.x * rows_per_cta) {
+        const i64 j = r % nj, k = r / nj;
+        const double *s = src + j * sj + k * sk;
+        double *d = dst + j * dj + k * dk;
+        i64 i = lane;
         if (VEC == 2) {
-            const double2 *s = reinterpret_cast<const double2 *>(src + j * sj + k * sk) + i;
-            double2 *d = reinterpret_cast<double2 *>(dst + j * dj + k * dk) + i;
-            *d = *s;
+            const double2 *s2 = reinterpret_cast<const double2 *>(s);
+            double2 *d2 = reinterpret_cast<double2 *>(d);
+            for (; i + 3 * lanes < niv; i += 4 * lanes) {
+                const double2 v0 = s2[i], v1 = s2[i + lanes], v2 = s2[i + 2 * lanes], v3 = s2[i + 3 * lanes];
+                d2[i] = v0; d2[i + lanes] = v1; d2[i + 2 * lanes] = v2; d2[i + 3 * lanes] = v3;
+            }
+            for (; i < niv; i += lanes) d2[i] = s2[i];
         } else {
-            dst[i * di + j * dj + k * dk] = src[i * si + j * sj + k * sk];
+            for (; i + 3 * lanes < niv; i += 4 * lanes) {
+                const double v0 = s[i * si], v1 = s[(i + lanes) * si], v2 = s[(i + 2 * lanes) * si], v3 = s[(i + 3 * lanes) * si];
+                d[i * di] = v0; d[(i + lanes) * di] = v1; d[(i + 2 * lanes) * di] = v2; d[(i + 3 * lanes) * di] = v3;
+            }
+            for (; i < niv; i += lanes) d[i * di] = s[i * si];
         }
     }
 }
@@ -205,12 +255,16 @@ int rb_copy3d(rb_ctx *ctx, const double *src, i64 s0, i64 si, i64 sj, i64 sk, do
     double *d = dst + d0;
     bool vec = si == 1 && di == 1 && (ni % 2 == 0) && (sj % 2 == 0) && (sk % 2 == 0) && (dj % 2 == 0) &&
                (dk % 2 == 0) && (((uintptr_t)s & 15) == 0) && (((uintptr_t)d & 15) == 0);
-    i64 total = (vec ? ni / 2 : ni) * nj * nk;
-    i64 blocks = rb_cdiv(total, 256);
-    i64 cap = (i64)ctx->num_sms * 16;
+    const i64 niv = vec ? ni / 2 : ni;
+    int lg = 0;
+    while (lg < 8 && ((i64)2 << lg) * 4 <= niv) ++lg; // lanes = largest power of two <= niv / 4 (4 loads in flight per
+    if (lg < 3 && niv >= 8) lg = 3;                   // thread), at most 256; at least a quarter-warp per row
+    const i64 rows = nj * nk, rows_per_cta = 256 >> lg;
+    i64 blocks = rb_cdiv(rows, rows_per_cta);
+    i64 cap = (i64)ctx->num_sms * 8;
     if (blocks > cap) blocks = cap;
-    if (vec) rb_copy3d_kernel<2><<<(unsigned)blocks, 256, 0, ctx->stream>>>(s, si, sj, sk, d, di, dj, dk, ni, nj, nk);
-    else rb_copy3d_kernel<1><<<(unsigned)blocks, 256, 0, ctx->stream>>>(s, si, sj, sk, d, di, dj, dk, ni, nj, nk);
+    if (vec) rb_copy3d_kernel<2><<<(unsigned)blocks, 256, 0, ctx->stream>>>(s, si, sj, sk, d, di, dj, dk, ni, nj, nk, lg);
+    else rb_copy3d_kernel<1><<<(unsigned)blocks, 256, 0, ctx->stream>>>(s, si, sj, sk, d, di, dj, dk, ni, nj, nk, lg);
     RB_LAUNCHED(ctx);
     return RB_OK;
 }
@@ -285,31 +339,62 @@ extern "C" int rb_copy_rr(rb_ctx *ctx, int xl, int yl, int zl, const double *f, 
 
 // ---------------------------------------------------------------------------------------------------------
 // Batched tiled 2-D transpose: out[c + r*ors + b*obs] = in[r + c*ics + b*ibs]   (r, c unit-stride on in / out)
+// 64x64 tiles through padded shared memory; VEC: 16-byte loads along r and 16-byte stores along c (all strides even,
+// bases 16-byte aligned), 16 loads in flight per thread.
 // ---------------------------------------------------------------------------------------------------------
+constexpr int TT = 64;
+
+template <bool VEC>
 __global__ void __launch_bounds__(256) rb_transpose_kernel(const double *__restrict__ in, i64 ics, i64 ibs,
                                                            double *__restrict__ out, i64 ors, i64 obs, i64 nr, i64 nc,
                                                            i64 tiles_r, i64 tiles_c, i64 total_tiles)
 {
-    __shared__ double tile[32][33];
-    int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    __shared__ double tile[TT][TT + 1]; // [c][r]
     for (i64 t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        i64 tr = t % tiles_r, rest = t / tiles_r;
-        i64 tc = rest % tiles_c, b = rest / tiles_c;
+        const i64 tr = t % tiles_r, rest = t / tiles_r;
+        const i64 tc = rest % tiles_c, b = rest / tiles_c;
         const double *ib = in + b * ibs;
         double *ob = out + b * obs;
-        i64 r0 = tr * 32, c0 = tc * 32;
+        const i64 r0 = tr * TT, c0 = tc * TT;
+        if (VEC) {
+            const int t2 = threadIdx.x & 31, ty = threadIdx.x >> 5; // 32 pairs x 8 per pass
+            double2 v[TT / 8];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            int cc = ty + q * 8;
-            i64 r = r0 + tx, c = c0 + cc;
-            tile[cc][tx] = (r < nr && c < nc) ? ib[r + c * ics] : 0.0;
-        }
-        __syncthreads();
+            for (int q = 0; q < TT / 8; ++q) {
+                const i64 r = r0 + 2 * t2, c = c0 + ty + q * 8;
+                v[q] = make_double2(0.0, 0.0);
+                if (r + 1 < nr && c < nc) v[q] = *reinterpret_cast<const double2 *>(ib + r + c * ics);
+                else if (r < nr && c < nc) v[q].x = ib[r + c * ics];
+            }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            int rr = ty + q * 8;
-            i64 r = r0 + rr, c = c0 + tx;
-            if (r < nr && c < nc) ob[c + r * ors] = tile[tx][rr];
+            for (int q = 0; q < TT / 8; ++q) { tile[ty + q * 8][2 * t2] = v[q].x; tile[ty + q * 8][2 * t2 + 1] = v[q].y; }
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < TT / 8; ++q) {
+                const int rr = ty + q * 8;
+                const i64 r = r0 + rr, c = c0 + 2 * t2;
+                if (r < nr) {
+                    if (c + 1 < nc) *reinterpret_cast<double2 *>(ob + c + r * ors) = make_double2(tile[2 * t2][rr], tile[2 * t2 + 1][rr]);
+                    else if (c < nc) ob[c + r * ors] = tile[2 * t2][rr];
+                }
+            }
+        } else {
+            const int tx = threadIdx.x & (TT - 1), ty = threadIdx.x >> 6; // 64 x 4 per pass
+            double v[TT / 4];
+#pragma unroll
+            for (int q = 0; q < TT / 4; ++q) {
+                const i64 r = r0 + tx, c = c0 + ty + q * 4;
+                v[q] = (r < nr && c < nc) ? ib[r + c * ics] : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < TT / 4; ++q) tile[ty + q * 4][tx] = v[q];
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < TT / 4; ++q) {
+                const int rr = ty + q * 4;
+                const i64 r = r0 + rr, c = c0 + tx;
+                if (r < nr && c < nc) ob[c + r * ors] = tile[tx][rr];
+            }
         }
         __syncthreads();
     }
@@ -319,13 +404,18 @@ int rb_transpose_batched(rb_ctx *ctx, const double *in, i64 ics, i64 ibs, double
                          i64 nc, i64 nbatch)
 {
     if (nr <= 0 || nc <= 0 || nbatch <= 0) return RB_OK;
-    i64 tiles_r = rb_cdiv(nr, 32), tiles_c = rb_cdiv(nc, 32);
+    i64 tiles_r = rb_cdiv(nr, TT), tiles_c = rb_cdiv(nc, TT);
     i64 total = tiles_r * tiles_c * nbatch;
     i64 blocks = total;
-    i64 cap = (i64)ctx->num_sms * 32;
+    i64 cap = (i64)ctx->num_sms * 16;
     if (blocks > cap) blocks = cap;
-    rb_transpose_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(in, ics, ibs, out, ors, obs, nr, nc, tiles_r,
-                                                                  tiles_c, total);
+    const bool vec = ((ics | ibs | ors | obs) & 1) == 0 && ((((uintptr_t)in) | ((uintptr_t)out)) & 15) == 0;
+    if (vec)
+        rb_transpose_kernel<true><<<(unsigned)blocks, 256, 0, ctx->stream>>>(in, ics, ibs, out, ors, obs, nr, nc, tiles_r,
+                                                                            tiles_c, total);
+    else
+        rb_transpose_kernel<false><<<(unsigned)blocks, 256, 0, ctx->stream>>>(in, ics, ibs, out, ors, obs, nr, nc, tiles_r,
+                                                                             tiles_c, total);
     RB_LAUNCHED(ctx);
     return RB_OK;
 }
