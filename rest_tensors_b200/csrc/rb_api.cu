@@ -52,8 +52,8 @@ extern "C" int rb_ctx_create(int device, rb_ctx **out)
     c->stream = c->own_stream;
     RB_CUDA(cudaEventCreate(&c->ev0));
     RB_CUDA(cudaEventCreate(&c->ev1));
-    RB_CUDA(cudaMalloc((void **)&c->sched, 64));
-    RB_CUDA(cudaMemset(c->sched, 0, 64));
+    RB_CUDA(cudaMalloc((void **)&c->sched, 64 * 2 * sizeof(unsigned long long)));
+    RB_CUDA(cudaMemset(c->sched, 0, 64 * 2 * sizeof(unsigned long long)));
     // cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link against libcuda).
     void *fn = nullptr;
     cudaDriverEntryPointQueryResult qres;

@@ -55,7 +55,8 @@ struct rb_ctx {
     int gemm_path = 0;
     rb_encode_tiled_fn encode_tiled = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    unsigned long long *sched = nullptr; // GEMM tile-scheduler words (device), zero between launches
+    unsigned long long *sched = nullptr; // GEMM tile-scheduler slots (64 x 2 words on the device), zero between launches
+    unsigned sched_next = 0;             // slot of the next GEMM launch (round-robin)
 };
 
 // Grow-only device workspace (synchronises the stream before freeing the old block).

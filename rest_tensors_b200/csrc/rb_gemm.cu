@@ -732,7 +732,9 @@ int rb_gemm_core(rb_ctx *ctx, bool ta, bool tb, i64 m, i64 n, i64 k, double alph
         p.alpha = alpha; p.beta = beta; p.c = c; p.ldc = ldc; p.stride_c = stride_c; p.tri = tri;
         p.partial = nullptr; p.ldp = (m + 1) & ~(i64)1;
         p.a_batched = a_batched ? 1 : 0; p.b_batched = b_batched ? 1 : 0;
-        p.sched = ctx->sched;
+        // one of 64 self-re-arming scheduler slots per launch: launches of one context may overlap (the caller can
+        // move the context between streams) without sharing a work counter
+        p.sched = ctx->sched + 2 * (ctx->sched_next++ & 63);
         if (splits > 1) {
             void *ws;
             RB_TRY(rb_ws_reserve(ctx, 1, splits * batch * n * p.ldp * 8, &ws));
