@@ -186,8 +186,9 @@ int host_ri_stream(const double *cl, int nl, const double *cr, int nr, const dou
     if (do_j) RB_TRY(op.up(d_dm, dm, slab_in));
     if (do_k) RB_TRY(op.up(d_ct, ct, nb * no));
     const double t_alloc = now_ms();
-    // (A geometric ramp of small first/last chunks was measured and does not help: the pass is bound by PCIe duplex
-    //  bandwidth, 9.8 GB at ~94 GB/s, not by pipeline fill/drain -- profiles/r01_e2e_variants.md.)
+    // (A ramp of small first/last chunks was measured twice and is slower -- 123.7 vs 118.8 ms at config C: the D2H rows
+    //  are pn*8 bytes wide, so short chunks make the 2-D copy inefficient; 128- and 512-slab chunks: 147.6 / 140.2 ms.
+    //  The pass is bound by PCIe duplex bandwidth, 9.8 GB at ~94 GB/s = 104 ms -- profiles/r01_e2e_variants.md.)
     int step = 0;
     for (i64 p0 = 0; p0 < nx; p0 += pc, ++step) {
         const int s = step & 1;
