@@ -352,6 +352,49 @@ def test_ao2mo_full_size_identity_property(ctx):
     assert rel_err(o1v.permute(1, 0, 2).cpu().numpy(), o1v.cpu().numpy()) < 1e-12
 
 
+@pytest.mark.parametrize("name,nb,nx,no", [("C", 600, 1700, 60), ("D-shard", 1800, 600, 180)])
+def test_full_size_configs_properties(ctx, name, nb, nx, no):
+    """BASELINE configs C (whole) and D (one rank's 600-slab shard of naux = 4800) at full size, device-resident.
+    Size-independent properties instead of an oracle run: ao2mo(I) returns the input bits; ao2mo(2C) == 4 ao2mo(C)
+    exactly; d_P/J linear; K symmetric with a non-negative diagonal; two half-shards add up to the whole (the
+    multi-GPU invariant); occ-vir ao2mo equals the matching sub-block of the square one bit for bit."""
+    from rest_tensors_b200.device import ShardedRI
+    ri = ShardedRI(ctx, nb, nx).fill_synthetic()
+    n2 = nb * nb
+    eye = torch.eye(nb, dtype=torch.float64, device=ri.data.device).reshape(-1).contiguous()
+    out = ri.ao2mo(eye, nb, eye, nb)
+    src = ri.data.view(nx, nb, nb)                       # [P, nu, mu] (row-major view of the column-major tensor)
+    for b0 in range(0, nb, 256):                          # compare in slices: no 15 GB temporaries
+        b1 = min(nb, b0 + 256)
+        assert torch.equal(out.view(nb, nb, nx)[b0:b1], src[:, b0:b1, :].permute(1, 2, 0)), f"{name}: ao2mo(I) != ri3ao"
+    c = ctx.empty(n2); ctx.fill_linear(c, n2, 3, 0, nb ** -0.5)
+    ri.ao2mo(c, nb, c, nb, out=out)
+    probe = out[:: 1000003].clone()
+    sub_sq = out.view(nb, nb, nx)[no:no + 7, :no, :].clone()           # [b in vir, a in occ, P]
+    c2 = c * 2.0
+    out2 = ri.ao2mo(c2, nb, c2, nb, out=out)
+    assert torch.equal(out2[:: 1000003], probe * 4.0), f"{name}: power-of-two scaling must be exact"
+    # occ-vir (north-star form) on a few virtual columns == sub-block of the square transform (same sums, same order)
+    ov = ri.ao2mo(c[: nb * no], no, c[nb * no: nb * (no + 7)], 7)
+    assert torch.equal(ov.view(7, no, nx), sub_sq), f"{name}: occ-vir block differs from the square transform"
+    del out, out2, ov
+    torch.cuda.empty_cache()
+    cm = c.view(nb, nb).t()
+    dm = (2.0 * cm[:, :no] @ cm[:, :no].t()).t().contiguous().reshape(-1)
+    ct = (cm[:, :no] * (2.0 ** 0.5)).t().contiguous().reshape(-1)
+    d = ri.dp(dm); j = ri.j(d, reduce=False); k = ri.k(ct, no, reduce=False)
+    assert torch.equal(ri.dp(dm * 2.0), d * 2.0)
+    jm, km = j.view(nb, nb), k.view(nb, nb)
+    assert rel_err(jm.t().cpu().numpy(), jm.cpu().numpy()) < 1e-12
+    assert torch.equal(km, km.t()) and bool((torch.diagonal(km) >= 0).all())
+    half = (nx // 2) // 8 * 8 + 4                          # deliberately not a multiple of 8
+    lo = ShardedRI(ctx, nb, half, data=ri.data[: n2 * half])
+    hi = ShardedRI(ctx, nb, nx - half, data=ri.data[n2 * half:])
+    assert rel_err(torch.cat([lo.dp(dm), hi.dp(dm)]).cpu().numpy(), d.cpu().numpy()) < 1e-12
+    assert rel_err((lo.j(d[:half], reduce=False) + hi.j(d[half:], reduce=False)).cpu().numpy(), j.cpu().numpy()) < 1e-12
+    assert rel_err((lo.k(ct, no, reduce=False) + hi.k(ct, no, reduce=False)).cpu().numpy(), k.cpu().numpy()) < 1e-12
+
+
 # ---------------------------------------------------------------- d_P, J, K ----
 @pytest.mark.parametrize("nb,nx,no,symm", [(10, 20, 3, True), (100, 400, 20, True), (37, 11, 5, False), (64, 300, 64, False)])
 def test_dp_j_k_vs_oracle(rt, oracle_blas, nb, nx, no, symm):
