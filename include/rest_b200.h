@@ -148,6 +148,9 @@ int rb_host_ri_ao2mo_jk(const double *c_left, int nl, const double *c_right, int
 /* axpy family on host buffers (matrix/mod.rs:545-648, ri.rs:345-354, matrixupper.rs:395-420):
  * op 0: c += p*b   1: c = c*a + p*b   2: c *= a   3: c += p   4: c -= p   (unfused mul-then-add, bit-exact) */
 int rb_host_axpy(int op, double *c, const double *p, double a, double b, int64_t n);
+/* einsum helpers on host buffers: which = 1 "ij,j->ij" (a [ni,nj], b [nj], out [ni,nj]); 2 "ip,ip->p" (a, b [ni,nj],
+ * out [nj]); 3 "i,j->ij" (a [ni], b [nj], out [ni,nj]).  Dense column-major operands (lda = ldb = ni). */
+int rb_host_einsum(int which, const double *a, const double *b, double *out, int64_t ni, int64_t nj);
 /* d_P, J, K with host buffers (composed by REST from _dgemv/_dgemm/_dsyrk) */
 int rb_host_ri_dp(const double *ri3ao, const double *dm, double *d, int nb, int nx);
 int rb_host_ri_j(const double *ri3ao, const double *d, double *j, int nb, int nx);
@@ -182,6 +185,14 @@ int rb_ri_k(rb_ctx *ctx, const double *ri3ao, const double *ct, int no, double *
 /* in-place slab x matrix of restmatr.f90:111-154 on device buffers */
 int rb_special_dgemm_01(rb_ctx *ctx, double *ten3, int x_a, int y_a, int z_a, int start_x, int len_x, int start_z,
                         int len_z, const double *b, int64_t ldb, int len_col_b, double alpha, double beta);
+
+/* einsum helpers (matrix_blas_lapack.rs:1273-1387, matrix/einsum.rs) on device buffers:
+ * "ij,j->ij" and "i,j->ij" are one multiply per element (bit-exact), "ip,ip->p" is a column dot (1e-10). */
+int rb_einsum_ij_j(rb_ctx *ctx, const double *a, int64_t lda, const double *b, double *out, int64_t ldo, int64_t ni,
+                   int64_t nj);
+int rb_einsum_ip_ip(rb_ctx *ctx, const double *a, int64_t lda, const double *b, int64_t ldb, double *out, int64_t ni,
+                    int64_t np);
+int rb_einsum_i_j(rb_ctx *ctx, const double *a, const double *b, double *out, int64_t ni, int64_t nj);
 
 /* pack / unpack (bit-exact) */
 int rb_pack_upper(rb_ctx *ctx, const double *full, int64_t n, double *packed);

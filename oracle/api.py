@@ -92,6 +92,9 @@ class Oracle:
         L.orc_ri_dp.argtypes = [_vp, _vp, _vp, _i, _i]
         L.orc_ri_j.argtypes = [_vp, _vp, _vp, _i, _i]
         L.orc_ri_k.argtypes = [_vp, _vp, _vp, _i, _i, _i]
+        for name in ("orc_einsum_01", "orc_einsum_02", "orc_einsum_03"):
+            getattr(L, name).argtypes = [_vp, _vp, _vp, _i64, _i64]
+            getattr(L, name).restype = None
         self.blas_path = None
 
     # -- BLAS selection --
@@ -159,6 +162,22 @@ class Oracle:
         k = np.empty(nb * nb, dtype=np.float64)
         self.lib.orc_ri_k(ri3ao.ctypes.data, ct.ctypes.data, k.ctypes.data, nb, no, nx)
         return k
+
+    # -- einsum helpers (matrix_blas_lapack.rs:1273-1387) --
+    def einsum_01(self, a, b, ni, nj) -> np.ndarray:
+        out = np.empty(ni * nj, dtype=np.float64)
+        self.lib.orc_einsum_01(a.ctypes.data, b.ctypes.data, out.ctypes.data, ni, nj)
+        return out
+
+    def einsum_02(self, a, b, ni, np_) -> np.ndarray:
+        out = np.empty(np_, dtype=np.float64)
+        self.lib.orc_einsum_02(a.ctypes.data, b.ctypes.data, out.ctypes.data, ni, np_)
+        return out
+
+    def einsum_03(self, a, b, ni, nj) -> np.ndarray:
+        out = np.empty(ni * nj, dtype=np.float64)
+        self.lib.orc_einsum_03(a.ctypes.data, b.ctypes.data, out.ctypes.data, ni, nj)
+        return out
 
     # -- BLAS --
     def dgemm(self, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc) -> None:

@@ -539,3 +539,28 @@ void orc_ri_k(const double *ri3ao, const double *ct, double *k, int nb, int no, 
         for (i64 i = j + 1; i < nb; ++i) k[i + j * nb] = k[j + i * nb];
     free(bp);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * einsum helpers (src/matrix/matrix_blas_lapack.rs:1273-1387, src/matrix/einsum.rs:17-79): the serial forms.
+ * ---------------------------------------------------------------------------------------------- */
+/* "ij,j->ij": om[i,j] = a[i,j] * b[j]  (1275-1290 / 1315-1330) */
+void orc_einsum_01(const double *a, const double *b, double *out, i64 ni, i64 nj)
+{
+    for (i64 j = 0; j < nj; ++j)
+        for (i64 i = 0; i < ni; ++i) out[i + j * ni] = a[i + j * ni] * b[j];
+}
+/* "ip,ip->p": out[p] = fold(0.0, acc + a[i,p]*b[i,p]) over i ascending (1293-1311 / 1333-1351) */
+void orc_einsum_02(const double *a, const double *b, double *out, i64 ni, i64 np)
+{
+    for (i64 p = 0; p < np; ++p) {
+        double acc = 0.0;
+        for (i64 i = 0; i < ni; ++i) acc = acc + a[i + p * ni] * b[i + p * ni];
+        out[p] = acc;
+    }
+}
+/* "i,j->ij": om[i,j] = a[i] * b[j]  (1355-1387) */
+void orc_einsum_03(const double *a, const double *b, double *out, i64 ni, i64 nj)
+{
+    for (i64 j = 0; j < nj; ++j)
+        for (i64 i = 0; i < ni; ++i) out[i + j * ni] = a[i] * b[j];
+}

@@ -12,6 +12,7 @@ from .tensors import (  # noqa: F401
     map_upper_to_full, map_full_to_upper, general_check_shape,
     _dgemm, _dgemm_full, _dgemm_full_new, _dsyrk, _dsymm, _dgemv,
     _dgemm_nn, _dgemm_nn_serial, _dgemm_tn, _dgemm_tn_serial, _dgemm_tn_v02,
+    _einsum_01_rayon, _einsum_01_serial, _einsum_02_rayon, _einsum_02_serial, _einsum_03, _einsum_03_forvec, _einsum_general,
     ri_ao2mo_f, general_dgemm_f, special_dgemm_f_01, matr_copy, matr_copy_from_ri, ri_copy_from_matr, ri_copy_from_ri,
 )
 
@@ -20,6 +21,8 @@ __all__ = [
     "map_upper_to_full", "map_full_to_upper", "general_check_shape", "RestB200Error",
     "_dgemm", "_dgemm_full", "_dgemm_full_new", "_dsyrk", "_dsymm", "_dgemv",
     "_dgemm_nn", "_dgemm_nn_serial", "_dgemm_tn", "_dgemm_tn_serial", "_dgemm_tn_v02",
+    "_einsum_01_rayon", "_einsum_01_serial", "_einsum_02_rayon", "_einsum_02_serial", "_einsum_03", "_einsum_03_forvec",
+    "_einsum_general",
     "ri_ao2mo_f", "general_dgemm_f", "special_dgemm_f_01", "matr_copy", "matr_copy_from_ri", "ri_copy_from_matr",
     "ri_copy_from_ri",
 ]

@@ -101,6 +101,10 @@ SIGNATURES = {
     "rb_ri_k": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, c_vp, C.c_int, C.c_int]),
     "rb_special_dgemm_01": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                       c_vp, c_i64, C.c_int, C.c_double, C.c_double]),
+    "rb_einsum_ij_j": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_i64]),
+    "rb_einsum_ip_ip": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64]),
+    "rb_einsum_i_j": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64]),
+    "rb_host_einsum": (C.c_int, [C.c_int, c_vp, c_vp, c_vp, c_i64, c_i64]),
     "rb_pack_upper": (C.c_int, [c_vp, c_vp, c_i64, c_vp]),
     "rb_unpack_upper": (C.c_int, [c_vp, c_vp, c_i64, c_vp]),
     "rb_ri_pack_symm": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp]),

@@ -660,6 +660,26 @@ extern "C" int rb_host_axpy(int opc, double *c, const double *p, double a, doubl
     return op.sync();
 }
 
+extern "C" int rb_host_einsum(int which, const double *a, const double *b, double *out, int64_t ni, int64_t nj)
+{
+    RB_REQUIRE(which >= 1 && which <= 3, "rb_host_einsum: which must be 1..3");
+    RB_REQUIRE(ni >= 0 && nj >= 0, "rb_host_einsum: negative dimension");
+    const i64 na = which == 3 ? ni : ni * nj, nb_ = which == 2 ? ni * nj : nj, no = which == 2 ? nj : ni * nj;
+    if (no == 0) return RB_OK;
+    HOST_CTX(op);
+    double *da, *db, *dout;
+    RB_TRY(op.alloc(na, &da));
+    RB_TRY(op.alloc(nb_, &db));
+    RB_TRY(op.alloc(no, &dout));
+    RB_TRY(op.up(da, a, na));
+    RB_TRY(op.up(db, b, nb_));
+    if (which == 1) RB_TRY(rb_einsum_ij_j(op.ctx, da, ni, db, dout, ni, ni, nj));
+    else if (which == 2) RB_TRY(rb_einsum_ip_ip(op.ctx, da, ni > 0 ? ni : 1, db, ni > 0 ? ni : 1, dout, ni, nj));
+    else RB_TRY(rb_einsum_i_j(op.ctx, da, db, dout, ni, nj));
+    RB_TRY(op.down(out, dout, no));
+    return op.sync();
+}
+
 extern "C" int rb_host_ri_dp(const double *ri3ao, const double *dm, double *d, int nb, int nx)
 {
     RB_REQUIRE(nb >= 0 && nx >= 0, "rb_host_ri_dp: negative dimension");

@@ -806,6 +806,67 @@ def _dgemm_tn_v02(mat_a, mat_b, to_slice) -> None:
         off += n
 
 
+# -- einsum helpers (matrix_blas_lapack.rs:1273-1387, matrix/einsum.rs) --
+def _einsum_01_rayon(mat_a, vec_b: np.ndarray) -> MatrixFull:
+    """matrix_blas_lapack.rs:1275-1290: "ij,j->ij"; the first len(vec_b) columns of mat_a scaled by vec_b"""
+    i_len, j_len = mat_a.size[0], int(np.asarray(vec_b).size)
+    om = MatrixFull.new([i_len, j_len], 0.0)
+    if i_len == 0 or j_len == 0:
+        return om
+    if j_len > mat_a.size[1]:
+        raise ValueError("einsum ij,j->ij: vec_b longer than the number of columns of mat_a")  # `.unwrap()` on None
+    b = _f64(vec_b)
+    check(lib.rb_host_einsum(1, _ptr(mat_a.data), _ptr(b), _ptr(om.data), i_len, j_len), "_einsum_01")
+    return om
+
+
+_einsum_01_serial = _einsum_01_rayon
+
+
+def _einsum_02_rayon(mat_a, mat_b) -> np.ndarray:
+    """matrix_blas_lapack.rs:1293-1311: "ip,ip->p" over the common columns (zip stops at the shorter operand)"""
+    (a_x, a_y), (b_x, b_y) = mat_a.size, mat_b.size
+    n_p = min(a_y, b_y)
+    out = np.zeros(n_p, dtype=np.float64)
+    if a_x == 0 or b_x == 0 or n_p == 0:
+        return out
+    if a_x != b_x:  # zip of unequal columns truncates to the shorter one in the reference; not a hot-path shape
+        raise ValueError("einsum ip,ip->p: operands with different row counts are not supported on the device path")
+    check(lib.rb_host_einsum(2, _ptr(mat_a.data), _ptr(mat_b.data), _ptr(out), a_x, n_p), "_einsum_02")
+    return out
+
+
+_einsum_02_serial = _einsum_02_rayon
+
+
+def _einsum_03(vec_a: np.ndarray, vec_b: np.ndarray) -> MatrixFull:
+    """matrix_blas_lapack.rs:1355-1387 (`_einsum_03`, `_einsum_03_forvec`): "i,j->ij" outer product"""
+    a, b = _f64(vec_a), _f64(vec_b)
+    om = MatrixFull.new([a.size, b.size], 0.0)
+    if a.size and b.size:
+        check(lib.rb_host_einsum(3, _ptr(a), _ptr(b), _ptr(om.data), a.size, b.size), "_einsum_03")
+    return om
+
+
+_einsum_03_forvec = _einsum_03
+
+
+def _einsum_general(mat_a, mat_b, opt: str) -> MatrixFull:
+    """matrix/einsum.rs:3-14: dispatch on the subscript string; panics on anything else"""
+    if opt == "ij,j->ij":
+        return _einsum_01_rayon(mat_a, mat_b.data)
+    if opt == "ip,ip->p":
+        v = _einsum_02_rayon(mat_a, mat_b)
+        return MatrixFull.from_vec([v.size, 1], v)
+    if opt == "i,j->ij":
+        return _einsum_03(mat_a.data, mat_b.data)
+    if opt == "ij,ji->ij":  # einsum.rs:81-91 (`_einsum_04_general`): despite the label it is a plain dgemm NN
+        c = MatrixFull.new([mat_a.size[0], mat_b.size[1]], 0.0)
+        _dgemm_full(mat_a, 'N', mat_b, 'N', c, 1.0, 0.0)
+        return c
+    raise ValueError(f"Not implemented for einsum: {opt}")
+
+
 def _gemm_shape_ok(sa, opa, sb, opb, sc) -> bool:
     key = (opa, opb)
     if key == ('N', 'N'):

@@ -38,6 +38,8 @@ extern "C" {
     pub fn rb_host_ri_ao2mo_jk(cl: *const c_double, nl: c_int, cr: *const c_double, nr: c_int, ri3ao: *const c_double,
                                ri3mo: *mut c_double, nb: c_int, nx: c_int, dm: *const c_double, ct: *const c_double,
                                no: c_int, d: *mut c_double, j: *mut c_double, k: *mut c_double) -> c_int;
+    /// which = 1 "ij,j->ij", 2 "ip,ip->p", 3 "i,j->ij" (matrix_blas_lapack.rs:1273-1387)
+    pub fn rb_host_einsum(which: c_int, a: *const c_double, b: *const c_double, out: *mut c_double, ni: i64, nj: i64) -> c_int;
     pub fn rb_host_ri_dp(ri3ao: *const c_double, dm: *const c_double, d: *mut c_double, nb: c_int, nx: c_int) -> c_int;
     pub fn rb_host_ri_j(ri3ao: *const c_double, d: *const c_double, j: *mut c_double, nb: c_int, nx: c_int) -> c_int;
     pub fn rb_host_ri_k(ri3ao: *const c_double, ct: *const c_double, no: c_int, k: *mut c_double, nb: c_int, nx: c_int) -> c_int;

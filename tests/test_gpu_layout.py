@@ -205,3 +205,29 @@ def test_device_generators_match_oracle(ctx, oracle):
     a = ctx.empty(nb * nb * (p_hi - p_lo))
     ctx.fill_ri3ao_symm(a, nb, p_lo, p_hi, 1, 1.0)
     assert np.array_equal(a.cpu().numpy(), oracle.fill_ri3ao_symm(nb, p_lo, p_hi, 1, 1.0))
+
+
+def test_einsum_helpers(rt, oracle):
+    """"ij,j->ij" and "i,j->ij" are single multiplies (bit-exact), "ip,ip->p" a column dot (1e-10)."""
+    from conftest import assert_close_1e10
+    for ni, nj in [(1, 1), (7, 5), (1000, 33), (4097, 3), (64, 3000)]:
+        a = oracle.fill_linear(ni * nj, 51); b = oracle.fill_linear(ni * nj, 52)
+        vj = oracle.fill_linear(nj, 53); vi = oracle.fill_linear(ni, 54)
+        A = rt.MatrixFull.from_vec([ni, nj], a); B = rt.MatrixFull.from_vec([ni, nj], b)
+        for fn in (rt._einsum_01_rayon, rt._einsum_01_serial):
+            assert np.array_equal(fn(A.to_matrixfullslice(), vj).data, oracle.einsum_01(a, vj, ni, nj))
+        for fn in (rt._einsum_02_rayon, rt._einsum_02_serial):
+            assert_close_1e10(fn(A.to_matrixfullslice(), B.to_matrixfullslice()), oracle.einsum_02(a, b, ni, nj), "ip,ip->p")
+        for fn in (rt._einsum_03, rt._einsum_03_forvec):
+            assert np.array_equal(fn(vi, vj).data, oracle.einsum_03(vi, vj, ni, nj))
+    # fewer scale factors than columns: only the leading columns are produced (zip semantics)
+    A = rt.MatrixFull.from_vec([5, 4], oracle.fill_linear(20, 55))
+    out = rt._einsum_01_rayon(A, np.array([2.0, -1.0]))
+    assert out.size == [5, 2] and np.array_equal(out.data, np.concatenate([A.data[:5] * 2.0, A.data[5:10] * -1.0]))
+    # dispatcher
+    g = rt._einsum_general(A, rt.MatrixFull.from_vec([4, 1], np.arange(4.0)), "ij,j->ij")
+    assert g.size == [5, 4] and np.array_equal(g.data, oracle.einsum_01(A.data, np.arange(4.0), 5, 4))
+    assert rt._einsum_general(A, A, "ip,ip->p").size == [4, 1]
+    with pytest.raises(ValueError):
+        rt._einsum_general(A, A, "ijk->i")
+    assert rt._einsum_03(np.zeros(0), np.ones(3)).size == [0, 3]

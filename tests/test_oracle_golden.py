@@ -133,3 +133,17 @@ def test_synth_generator_matches_numpy(oracle):
     a = oracle.fill_ri3ao_symm(6, 2, 4).reshape((6, 6, 2), order="F")
     assert np.array_equal(a, a.transpose(1, 0, 2))  # symmetric slabs
     assert a[1, 4, 1] == oracle.lib.orc_synth(1, 1 + 4 * 6 + 3 * 36, 1.0)
+
+
+def test_einsum_helpers_oracle(oracle):
+    """matrix_blas_lapack.rs:1273-1387 restated; the reference's own test (1388-1395) only prints:
+    [3,4;2,6] (column-major [3,4,2,6]) with itself under "ip,ip->p" gives [25, 40]."""
+    a = np.array([3.0, 4.0, 2.0, 6.0])
+    assert oracle.einsum_02(a, a, 2, 2).tolist() == [25.0, 40.0]
+    rng = np.random.default_rng(5)
+    ni, nj = 13, 7
+    m = rng.standard_normal((ni, nj)); b = rng.standard_normal(nj); v = rng.standard_normal(ni)
+    mc = np.ascontiguousarray(m.reshape(-1, order="F"))
+    assert np.array_equal(oracle.einsum_01(mc, b, ni, nj).reshape((ni, nj), order="F"), m * b[None, :])
+    assert np.array_equal(oracle.einsum_03(v, b, ni, nj).reshape((ni, nj), order="F"), np.outer(v, b))
+    assert np.allclose(oracle.einsum_02(mc, mc, ni, nj), np.einsum("ip,ip->p", m, m), rtol=1e-14)
