@@ -41,6 +41,13 @@ def launches(path, out):
         f.write("| launches | total ms | share | kernel |\n|---:|---:|---:|---|\n")
         for k, a in sorted(agg.items(), key=lambda x: -x[1][1]):
             f.write(f"| {a[0]} | {a[1] / 1e6:.3f} | {100 * a[1] / tot:.2f}% | `{k[:110]}` |\n")
+        # the step's own kernels only: the FP64 peak probe and the synthetic-input generators run outside the timed region
+        step = {k: a for k, a in agg.items() if "probe" not in k and "fill" not in k and "axpy" not in k}
+        stot = sum(a[1] for a in step.values())
+        f.write("\nKernels of the timed step only (probe / generator launches excluded):\n\n")
+        f.write("| launches | total ms | share of step | kernel |\n|---:|---:|---:|---|\n")
+        for k, a in sorted(step.items(), key=lambda x: -x[1][1]):
+            f.write(f"| {a[0]} | {a[1] / 1e6:.3f} | {100 * a[1] / stot:.2f}% | `{k[:110]}` |\n")
 
 
 def full(path, out):
