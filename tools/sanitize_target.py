@@ -1,0 +1,40 @@
+"""Small, fast exercise of every kernel family for compute-sanitizer (memcheck / racecheck / synccheck)."""
+import sys
+import numpy as np
+import torch
+sys.path.insert(0, ".")
+from rest_tensors_b200.device import Context, ShardedRI  # noqa: E402
+
+ctx = Context(0)
+dev = "cuda:0"
+rng = np.random.default_rng(0)
+for ta, tb, (m, n, k) in [("T", "N", (300, 200, 77)), ("N", "N", (130, 260, 40)), ("N", "T", (257, 130, 9)), ("T", "T", (64, 140, 100)),
+                          ("N", "N", (200, 130, 6000))]:
+    ra, ca = (m, k) if ta == "N" else (k, m)
+    rb, cb = (k, n) if tb == "N" else (n, k)
+    a = torch.from_numpy(rng.standard_normal(ra * ca)).to(dev); b = torch.from_numpy(rng.standard_normal(rb * cb)).to(dev)
+    c = ctx.empty(m * n)
+    ctx.dgemm(ta, tb, m, n, k, 1.0, a, ra, b, rb, 0.0, c, m)
+    ref = (a.view(ca, ra).t() if ta == "N" else a.view(ca, ra)) @ (b.view(cb, rb).t() if tb == "N" else b.view(cb, rb))
+    err = float((c.view(n, m).t() - ref).abs().max() / ref.abs().max())
+    assert err < 1e-12, (ta, tb, m, n, k, err)
+a = torch.from_numpy(rng.standard_normal(300 * 50)).to(dev); c = ctx.empty(300 * 300); c.zero_()
+ctx.dsyrk("U", "N", 300, 50, 1.0, a, 300, 0.0, c, 300)
+nb, nx, no = 40, 70, 6
+sh = ShardedRI(ctx, nb, nx).fill_synthetic()
+cm = ctx.empty(nb * nb); ctx.fill_linear(cm, nb * nb, 3, 0, nb ** -0.5)
+mo = sh.ao2mo(cm, nb, cm, nb)
+d = sh.dp(cm); j = sh.j(d); kk = sh.k(cm[: nb * no].clone(), no)
+n = 150; npk = n * (n + 1) // 2
+p = ctx.empty(npk); f = ctx.empty(n * n); g = ctx.empty(n * n); ctx.fill_linear(p, npk, 4, 0, 1.0)
+ctx.unpack_upper(p, n, f); ctx.pack_upper(f, n, p); ctx.matrix_transpose(f, n, n, g)
+n = 151; npk = n * (n + 1) // 2
+p = ctx.empty(npk); f = ctx.empty(n * n); g = ctx.empty(n * n); ctx.fill_linear(p, npk, 4, 0, 1.0)
+ctx.unpack_upper(p, n, f); ctx.pack_upper(f, n, p); ctx.matrix_transpose(f, n, n, g)
+t = ctx.empty(30 * 22 * 14); u = ctx.empty(30 * 22 * 14); ctx.fill_linear(t, 30 * 22 * 14, 5, 0, 1.0)
+for w in range(4):
+    ctx.ri_transpose(t, 30, 22, 14, w, u)
+ctx.copy_rr(10, 12, 5, t, 30, 22, 14, 3, 2, 1, u, 30, 22, 14, 0, 4, 6)
+ctx.self_scaled_add(g, f, 0.5, n * n)
+torch.cuda.synchronize()
+print("sanitize target ok")
