@@ -231,3 +231,34 @@ def test_einsum_helpers(rt, oracle):
     with pytest.raises(ValueError):
         rt._einsum_general(A, A, "ijk->i")
     assert rt._einsum_03(np.zeros(0), np.ones(3)).size == [0, 3]
+
+
+def test_c_abi_error_codes_and_recovery(ctx, rt):
+    """Device API: invalid arguments return RB_ERR_INVALID with a message (never a CUDA error / abort), and the
+    context keeps working afterwards.  The Rust wrappers panic on the same conditions before the FFI call."""
+    import ctypes as C
+    from rest_tensors_b200._lib import lib, last_error, RestB200Error
+    a = ctx.empty(64); b = ctx.empty(64); c = ctx.empty(64)
+    P = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    bad = [
+        (lambda: lib.rb_dgemm(ctx.h, b"N", b"N", 8, 8, 8, 1.0, P(a), 4, P(b), 8, 0.0, P(c), 8), "lda"),       # lda < m
+        (lambda: lib.rb_dgemm(ctx.h, b"N", b"N", 8, 8, 8, 1.0, P(a), 8, P(b), 8, 0.0, P(c), 4), "ldc"),       # ldc < m
+        (lambda: lib.rb_dgemm(ctx.h, b"Q", b"N", 8, 8, 8, 1.0, P(a), 8, P(b), 8, 0.0, P(c), 8), "trans"),
+        (lambda: lib.rb_dsyrk(ctx.h, b"X", b"N", 8, 8, 1.0, P(a), 8, 0.0, P(c), 8), "uplo"),
+        (lambda: lib.rb_ri_ao2mo(ctx.h, P(a), 2, P(a), 2, P(b), P(c), 2, 4, 3), "out_ldp"),                   # ldp < nx
+        (lambda: lib.rb_ri_transpose(ctx.h, P(a), 2, 2, 2, 9, P(c)), "which"),
+        (lambda: lib.rb_copy_mm(ctx.h, 5, 5, P(a), 8, 8, 6, 0, P(c), 8, 8, 0, 0), "outside"),
+        (lambda: lib.rb_unpack_upper(ctx.h, None, 4, P(c)), "NULL"),
+    ]
+    for call, word in bad:
+        st = call()
+        assert st == 1, f"expected RB_ERR_INVALID, got {st}"
+        assert word.lower() in last_error().lower(), (word, last_error())
+    with pytest.raises(RestB200Error):
+        ctx.dgemm("N", "N", 8, 8, 8, 1.0, a, 4, b, 8, 0.0, c, 8)
+    # still healthy
+    a.fill_(1.0); b.fill_(2.0)
+    ctx.dgemm("N", "N", 8, 8, 8, 1.0, a, 8, b, 8, 0.0, c, 8)
+    assert torch.all(c == 16.0)
+    node = C.c_int(-5)
+    assert lib.rb_bind_host_to_device_numa(0, C.byref(node)) == 0 and node.value >= -1
