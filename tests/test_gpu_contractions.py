@@ -265,10 +265,11 @@ def _inputs(o, nb, nx, no, symmetric=True):
     return ri, c, dm, ct
 
 
-@pytest.mark.parametrize("nb,nx,symm", [(10, 20, True), (24, 7, False), (100, 400, True), (33, 5, False), (128, 130, False)])
+@pytest.mark.parametrize("nb,nx,symm", [(10, 20, True), (24, 7, False), (100, 400, True), (33, 5, False), (128, 130, False),
+                                        (264, 720, True)])
 def test_ao2mo_square_vs_reference_algorithm(rt, oracle_blas, nb, nx, symm):
     """square C (the only case the Fortran defines): compat symbol ri_ao2mo_f_ vs restmatr.f90 restatement + OpenBLAS.
-    (100, 400) is BASELINE config A in full; odd nb goes through the generic (non-TMA) kernel."""
+    (100, 400) and (264, 720) are BASELINE configs A and B in full; odd nb goes through the generic (non-TMA) kernel."""
     ri, c, _, _ = _inputs(oracle_blas, nb, nx, 1, symm)
     ref = oracle_blas.ri_ao2mo_f(c, ri, nb, nb, nx)
     got = rt.RIFull.from_vec([nb, nb, nx], ri).ao2mo(rt.MatrixFull.from_vec([nb, nb], c))
@@ -395,8 +396,39 @@ def test_full_size_configs_properties(ctx, name, nb, nx, no):
     assert rel_err((lo.k(ct, no, reduce=False) + hi.k(ct, no, reduce=False)).cpu().numpy(), k.cpu().numpy()) < 1e-12
 
 
+def test_config_c_full_size_parity_vs_oracle(ctx, oracle_blas):
+    """The bench workload itself (config C: nb=600, naux=1700, nocc=60; 4.9 GB in, 4.9 GB out) against the reference
+    algorithm on the host (restmatr.f90 loop structure + OpenBLAS, ~10 s): ao2mo, d_P, J and K at full size, 1e-10."""
+    import os
+    try:
+        avail = int([l for l in open("/proc/meminfo") if l.startswith("MemAvailable:")][0].split()[1]) * 1024
+    except Exception:
+        avail = None
+    if avail is not None and avail < 24e9:
+        pytest.skip("needs ~20 GB of host memory for the oracle's copy of config C")
+    from rest_tensors_b200.device import ShardedRI
+    nb, nx, no = 600, 1700, 60
+    oracle_blas.set_threads(len(os.sched_getaffinity(0)))
+    ri, c, dm, ct = _inputs(oracle_blas, nb, nx, no, True)
+    sh = ShardedRI(ctx, nb, nx).fill_synthetic()
+    assert np.array_equal(sh.data[: nb * nb * 3].cpu().numpy(), ri[: nb * nb * 3])
+    cd = _dev(ctx, c)
+    got = sh.ao2mo(cd, nb, cd, nb).cpu().numpy()
+    ref = oracle_blas.ri_ao2mo_f(c, ri, nb, nb, nx)
+    scale = float(np.max(np.abs(ref)))
+    assert float(np.max(np.abs(got - ref))) / scale <= 1e-10
+    assert_close_1e10(got[::97], ref[::97], "config C ao2mo (every 97th element, element-wise bound)")
+    del got, ref
+    d_ref = oracle_blas.ri_dp(ri, dm, nb, nx)
+    d = sh.dp(_dev(ctx, dm))
+    assert_close_1e10(d.cpu().numpy(), d_ref, "config C d_P")
+    assert_close_1e10(sh.j(d, reduce=False).cpu().numpy(), oracle_blas.ri_j(ri, d_ref, nb, nx), "config C J")
+    assert_close_1e10(sh.k(_dev(ctx, ct), no, reduce=False).cpu().numpy(), oracle_blas.ri_k(ri, ct, nb, no, nx), "config C K")
+
+
 # ---------------------------------------------------------------- d_P, J, K ----
-@pytest.mark.parametrize("nb,nx,no,symm", [(10, 20, 3, True), (100, 400, 20, True), (37, 11, 5, False), (64, 300, 64, False)])
+@pytest.mark.parametrize("nb,nx,no,symm", [(10, 20, 3, True), (100, 400, 20, True), (37, 11, 5, False), (64, 300, 64, False),
+                                           (264, 720, 21, True)])
 def test_dp_j_k_vs_oracle(rt, oracle_blas, nb, nx, no, symm):
     ri, c, dm, ct = _inputs(oracle_blas, nb, nx, no, symm)
     R = rt.RIFull.from_vec([nb, nb, nx], ri)
