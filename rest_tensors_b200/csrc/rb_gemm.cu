@@ -660,7 +660,7 @@ bool tma_eligible(const rb_ctx *ctx, const double *p, i64 ld, i64 stride, i64 ba
     if (batch > 1 && stride < 0) return false;
     if (ld * 8 >= (1LL << 40)) return false;
     if (batch > 1 && stride * 8 >= (1LL << 40)) return false;
-    if (d0 >= (1LL << 32) || d1 >= (1LL << 32) || batch >= (1LL << 32)) return false;
+    if (d0 >= (1LL << 31) || d1 >= (1LL << 31) || batch >= (1LL << 31)) return false; // TMA coordinates are int32
     if (ld < d0) return false;
     return true;
 }
