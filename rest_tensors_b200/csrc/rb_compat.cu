@@ -8,6 +8,10 @@
 // transfers overlap the contraction; pass pinned buffers (rb_host_alloc_pinned) to make the copies truly async.
 #include "rb_common.cuh"
 #include <vector>
+#include <string>
+#ifndef RB_DEFAULT_HEAD
+#define RB_DEFAULT_HEAD ""
+#endif
 #include <chrono>
 
 static double now_ms()
@@ -189,10 +193,29 @@ int host_ri_stream(const double *cl, int nl, const double *cr, int nr, const dou
     // (A ramp of small first/last chunks was measured twice and is slower -- 123.7 vs 118.8 ms at config C: the D2H rows
     //  are pn*8 bytes wide, so short chunks make the 2-D copy inefficient; 128- and 512-slab chunks: 147.6 / 140.2 ms.
     //  The pass is bound by PCIe duplex bandwidth, 9.8 GB at ~94 GB/s = 104 ms -- profiles/r01_e2e_variants.md.)
+    // Chunk schedule: optional short head chunks (REST_B200_HEAD="64,128": the D2H stream, which bounds the pass, starts
+    // earlier), then equal chunks of pc slabs.
+    std::vector<i64> sizes;
+    {
+        i64 rem = nx;
+        const char *e = getenv("REST_B200_HEAD");
+        std::string head = e ? e : RB_DEFAULT_HEAD;
+        size_t pos = 0;
+        while (pos < head.size() && rem > 2 * pc) {
+            size_t comma = head.find(',', pos);
+            if (comma == std::string::npos) comma = head.size();
+            i64 v = atoll(head.substr(pos, comma - pos).c_str());
+            pos = comma + 1;
+            if (v < 8 || v > pc) continue;
+            sizes.push_back(v); rem -= v;
+        }
+        while (rem > 0) { const i64 pn = rem < pc ? rem : pc; sizes.push_back(pn); rem -= pn; }
+    }
     int step = 0;
-    for (i64 p0 = 0; p0 < nx; p0 += pc, ++step) {
+    i64 p0 = 0;
+    for (size_t ci = 0; ci < sizes.size(); p0 += sizes[ci], ++ci, ++step) {
         const int s = step & 1;
-        const i64 pn = (nx - p0 < pc) ? nx - p0 : pc;
+        const i64 pn = sizes[ci];
         // H2D of this chunk may start once the compute that last read d_in[s] is done
         if (step >= 2) RB_CUDA(cudaStreamWaitEvent(pipe.s_in, pipe.comp_done[s], 0));
         if (nb > 0)
