@@ -211,6 +211,14 @@ int host_ri_stream(const double *cl, int nl, const double *cr, int nr, const dou
         }
         while (rem > 0) { const i64 pn = rem < pc ? rem : pc; sizes.push_back(pn); rem -= pn; }
     }
+    // REST_B200_TRACE: per-chunk timeline (timing events; start of H2D, end of H2D / compute / D2H relative to t0)
+    std::vector<cudaEvent_t> tl;
+    cudaEvent_t tl0 = nullptr;
+    auto mark = [&](cudaStream_t st) {
+        if (!trace) return;
+        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tl.push_back(e);
+    };
+    if (trace) { cudaEventCreate(&tl0); cudaEventRecord(tl0, pipe.s_in); }
     int step = 0;
     i64 p0 = 0;
     for (size_t ci = 0; ci < sizes.size(); p0 += sizes[ci], ++ci, ++step) {
@@ -218,10 +226,12 @@ int host_ri_stream(const double *cl, int nl, const double *cr, int nr, const dou
         const i64 pn = sizes[ci];
         // H2D of this chunk may start once the compute that last read d_in[s] is done
         if (step >= 2) RB_CUDA(cudaStreamWaitEvent(pipe.s_in, pipe.comp_done[s], 0));
+        mark(pipe.s_in);
         if (nb > 0)
             RB_CUDA(cudaMemcpyAsync(d_in[s], ri3ao + p0 * slab_in, (size_t)(pn * slab_in) * 8, cudaMemcpyHostToDevice,
                                     pipe.s_in));
         RB_CUDA(cudaEventRecord(pipe.in_done[s], pipe.s_in));
+        mark(pipe.s_in);
         // compute needs the chunk in HBM and the previous D2H out of d_out[s]
         RB_CUDA(cudaStreamWaitEvent(ctx->stream, pipe.in_done[s], 0));
         if (step >= 2) RB_CUDA(cudaStreamWaitEvent(ctx->stream, pipe.out_done[s], 0));
@@ -232,12 +242,14 @@ int host_ri_stream(const double *cl, int nl, const double *cr, int nr, const dou
         }
         if (do_k && slab_in > 0) RB_TRY(rb_ri_k_upper(ctx, d_in[s], d_ct, no, d_k, nb, pn, p0 == 0 ? 0.0 : 1.0));
         RB_CUDA(cudaEventRecord(pipe.comp_done[s], ctx->stream));
+        mark(ctx->stream);
         if (do_mo) {
             // D2H: rows of pn doubles into the P-fastest host tensor (pitch nx)
             RB_CUDA(cudaStreamWaitEvent(pipe.s_out, pipe.comp_done[s], 0));
             RB_CUDA(cudaMemcpy2DAsync(out + p0, (size_t)nx * 8, d_mo[s], (size_t)pn * 8, (size_t)pn * 8, (size_t)slab_out,
                                       cudaMemcpyDeviceToHost, pipe.s_out));
             RB_CUDA(cudaEventRecord(pipe.out_done[s], pipe.s_out));
+            mark(pipe.s_out);
         }
     }
     const double t_enq = now_ms();
@@ -250,6 +262,16 @@ int host_ri_stream(const double *cl, int nl, const double *cr, int nr, const dou
     RB_CUDA(cudaStreamSynchronize(pipe.s_out));
     RB_CUDA(cudaStreamSynchronize(pipe.s_in));
     RB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (trace && do_mo && tl.size() == 4 * sizes.size()) {
+        for (size_t ci = 0; ci < sizes.size(); ++ci) {
+            float t[4];
+            for (int q = 0; q < 4; ++q) cudaEventElapsedTime(&t[q], tl0, tl[4 * ci + q]);
+            fprintf(stderr, "[rest_b200]   chunk %2zu (%4lld slabs): H2D %7.2f -> %7.2f  compute done %7.2f  D2H done %7.2f ms\n", ci,
+                    (long long)sizes[ci], t[0], t[1], t[2], t[3]);
+        }
+    }
+    for (auto e : tl) cudaEventDestroy(e);
+    if (tl0) cudaEventDestroy(tl0);
     if (trace)
         fprintf(stderr, "[rest_b200] ri stream: nb=%lld nx=%lld pc=%lld chunks=%d  setup %.2f ms, enqueue %.2f ms, drain %.2f ms\n",
                 (long long)nb, (long long)nx, (long long)pc, step, t_alloc - t_start, t_enq - t_alloc, now_ms() - t_enq);
