@@ -237,6 +237,10 @@ int rb_hbm_copy_probe(rb_ctx *ctx, int64_t bytes, int iters, double *gbs_out);
  * (sum of both directions), 4 D2H by kernel stores into mapped pinned memory, 5 like 4 with rows of `width` bytes. */
 int rb_pcie_probe(rb_ctx *ctx, int mode, int64_t bytes, int64_t width, int iters, double *gbs_out);
 
+/* The host-pointer entry points keep their device staging blocks (<= 24 GB) and the pinned bounce blocks used for
+ * pageable caller buffers (<= 8 GB) cached between calls; this releases them. */
+int rb_host_trim(void);
+
 /* Host placement helper for the host-pointer paths on multi-socket boxes: restrict the calling thread (and the
  * threads / allocations it makes afterwards) to the CPUs of the NUMA node `device` hangs off, so that pinned buffers
  * are first-touched next to the GPU's PCIe root and its DMA does not cross the socket interconnect.  Call it once

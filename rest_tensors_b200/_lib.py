@@ -125,6 +125,7 @@ SIGNATURES = {
     "rb_hbm_copy_probe": (C.c_int, [c_vp, c_i64, C.c_int, c_dp]),
     "rb_pcie_probe": (C.c_int, [c_vp, C.c_int, c_i64, c_i64, C.c_int, c_dp]),
     "rb_bind_host_to_device_numa": (C.c_int, [C.c_int, c_ip]),
+    "rb_host_trim": (C.c_int, []),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

@@ -3,9 +3,12 @@
 //   (2) rb_host_* mirrors of the reference's BLAS / layout calls (src/matrix/matrix_blas_lapack.rs, matrixupper.rs,
 //       matrixfull.rs, ri.rs).
 // Every call stages its operands into HBM, runs the same CUDA kernels as the device API and copies the result back
-// before returning; nothing is retained.  There is no CPU arithmetic here: the only host work is cudaMemcpy.
+// before returning; nothing is retained.  There is no CPU arithmetic here: the only host work is moving bytes
+// (cudaMemcpy, and memcpy into / out of pinned bounce blocks when the caller's buffers are pageable).
 // ri_ao2mo_f_ / rb_host_ri_ao2mo stream P-chunks through a 3-stream pipeline (H2D | DMMA GEMMs | D2H) so that PCIe
-// transfers overlap the contraction; pass pinned buffers (rb_host_alloc_pinned) to make the copies truly async.
+// transfers overlap the contraction.  Pinned caller buffers (rb_host_alloc_pinned) go straight to the DMA engines
+// (config C: ~120-130 ms per pass); pageable ones (a Rust Vec<f64>) are bounced by host threads (~250 ms instead of
+// the ~720 ms the driver's synchronous staged copies take).
 #include "rb_common.cuh"
 #include <vector>
 #include <string>
@@ -13,6 +16,10 @@
 #define RB_DEFAULT_HEAD ""
 #endif
 #include <chrono>
+#include <atomic>
+#include <thread>
+#include <cstring>
+#include <sched.h>
 
 static double now_ms()
 {
@@ -28,6 +35,90 @@ struct StageBlock { void *p; i64 bytes; bool busy; };
 static std::vector<StageBlock> g_stage;
 static const i64 STAGE_CACHE_CAP = (i64)24 << 30;
 
+// ---- pageable caller buffers -----------------------------------------------------------------------------------
+// A Rust Vec<f64> (what the reference's RIFull / MatrixFull own) is pageable: cudaMemcpyAsync on it is staged by the
+// driver and synchronous, which serialises the 3-stream pipeline (measured: 740 ms instead of 132 ms per config-C
+// pass).  For such buffers the streaming pass bounces every chunk through cached PINNED blocks: host threads copy
+// chunk i+1 in / scatter chunk i-1 out (plain memcpy -- data movement, no arithmetic) while the GPU works on chunk i.
+struct PinBlock { void *p; i64 bytes; bool busy; };
+static std::vector<PinBlock> g_pin;
+static const i64 PIN_CACHE_CAP = (i64)8 << 30;
+
+static bool host_ptr_is_pinned(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+
+static void *pin_take(i64 bytes)
+{
+    int best = -1;
+    for (size_t i = 0; i < g_pin.size(); ++i)
+        if (!g_pin[i].busy && g_pin[i].bytes >= bytes && (best < 0 || g_pin[i].bytes < g_pin[best].bytes)) best = (int)i;
+    if (best >= 0) { g_pin[best].busy = true; return g_pin[best].p; }
+    i64 total = 0;
+    for (auto &b : g_pin) total += b.bytes;
+    for (size_t i = 0; i < g_pin.size() && total + bytes > PIN_CACHE_CAP;) { // make room: drop idle blocks
+        if (!g_pin[i].busy) { cudaFreeHost(g_pin[i].p); total -= g_pin[i].bytes; g_pin.erase(g_pin.begin() + i); } else ++i;
+    }
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    g_pin.push_back({p, bytes, true});
+    return p;
+}
+
+static void pin_release_all()
+{
+    for (auto &b : g_pin) b.busy = false;
+}
+
+static int host_threads()
+{
+    static int n = 0;
+    if (n) return n;
+    int have = 1;
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof set, &set) == 0) have = CPU_COUNT(&set);
+    int t = have > 16 ? 16 : have; // a transient burst of memcpy threads; measured 8 -> 16 threads: 279 -> 248 ms per config-C pass
+    if (const char *e = getenv("REST_B200_HOST_THREADS")) t = atoi(e);
+    n = t < 1 ? 1 : (t > 64 ? 64 : t);
+    return n;
+}
+
+// run fn(task) for task in [0, ntasks) on host_threads() threads (the caller is one of them)
+template <typename F>
+static void parallel_tasks(i64 ntasks, F fn)
+{
+    const int nt = (int)(ntasks < host_threads() ? ntasks : host_threads());
+    std::atomic<i64> next(0);
+    auto work = [&]() { for (i64 t = next.fetch_add(1); t < ntasks; t = next.fetch_add(1)) fn(t); };
+    std::vector<std::thread> th;
+    for (int i = 1; i < nt; ++i) th.emplace_back(work);
+    work();
+    for (auto &x : th) x.join();
+}
+
+// dst[r*dpitch .. +width) = src[r*spitch .. +width) for r in [0, rows): split into ~4 MB tasks
+static void host_copy_2d(double *dst, i64 dpitch, const double *src, i64 spitch, i64 width, i64 rows)
+{
+    if (width <= 0 || rows <= 0) return;
+    if (dpitch == width && spitch == width) { // contiguous: split by bytes
+        const i64 total = width * rows, piece = (i64)1 << 19; // 4 MB of doubles
+        parallel_tasks((total + piece - 1) / piece, [&](i64 t) {
+            const i64 o = t * piece, n = (total - o < piece) ? total - o : piece;
+            memcpy(dst + o, src + o, (size_t)n * 8);
+        });
+        return;
+    }
+    i64 rpt = ((i64)1 << 19) / width;
+    if (rpt < 1) rpt = 1;
+    parallel_tasks((rows + rpt - 1) / rpt, [&](i64 t) {
+        const i64 r0 = t * rpt, r1 = (r0 + rpt < rows) ? r0 + rpt : rows;
+        for (i64 r = r0; r < r1; ++r) memcpy(dst + r * dpitch, src + r * spitch, (size_t)width * 8);
+    });
+}
+
 struct HostOp {
     rb_ctx *ctx;
     std::unique_lock<std::mutex> lock;
@@ -36,6 +127,7 @@ struct HostOp {
     {
         if (ctx) cudaStreamSynchronize(ctx->stream);
         i64 total = 0;
+        pin_release_all();
         for (auto &b : g_stage) { b.busy = false; total += b.bytes; }
         while (total > STAGE_CACHE_CAP && !g_stage.empty()) { // drop the largest blocks first
             size_t big = 0;
@@ -104,6 +196,24 @@ struct HostOp {
         return RB_OK;
     }
 };
+
+} // namespace
+
+// Release the cached device staging blocks and pinned bounce blocks of the host-pointer entry points.
+extern "C" int rb_host_trim(void)
+{
+    std::unique_lock<std::mutex> lock(rb_default_mutex());
+    rb_ctx *ctx = rb_default_ctx();
+    if (ctx) cudaStreamSynchronize(ctx->stream);
+    for (auto &b : g_stage) cudaFree(b.p);
+    g_stage.clear();
+    for (auto &b : g_pin) cudaFreeHost(b.p);
+    g_pin.clear();
+    cudaGetLastError();
+    return RB_OK;
+}
+
+namespace {
 
 #define HOST_CTX(op)                                                                                     \
     HostOp op;                                                                                           \
@@ -211,6 +321,17 @@ int host_ri_stream(const double *cl, int nl, const double *cr, int nr, const dou
         }
         while (rem > 0) { const i64 pn = rem < pc ? rem : pc; sizes.push_back(pn); rem -= pn; }
     }
+    // Pageable caller buffers (a plain Vec<f64>) are bounced through pinned blocks by host threads (see PinBlock above);
+    // pinned / registered buffers go straight to the DMA engines.  REST_B200_BOUNCE=0 disables the bounce.
+    bool bounce = true;
+    if (const char *e = getenv("REST_B200_BOUNCE")) bounce = atoi(e) != 0;
+    bool in_pageable = bounce && nb > 0 && !host_ptr_is_pinned(ri3ao);
+    bool out_pageable = bounce && do_mo && !host_ptr_is_pinned(out);
+    double *pin_in[2] = {nullptr, nullptr}, *pin_out[2] = {nullptr, nullptr};
+    if (in_pageable)
+        for (int i = 0; i < 2; ++i) if (!(pin_in[i] = (double *)pin_take(pc * slab_in * 8))) in_pageable = false;
+    if (out_pageable)
+        for (int i = 0; i < 2; ++i) if (!(pin_out[i] = (double *)pin_take(pc * slab_out * 8))) out_pageable = false;
     // REST_B200_TRACE: per-chunk timeline (timing events; start of H2D, end of H2D / compute / D2H relative to t0)
     std::vector<cudaEvent_t> tl;
     cudaEvent_t tl0 = nullptr;
@@ -226,10 +347,15 @@ int host_ri_stream(const double *cl, int nl, const double *cr, int nr, const dou
         const i64 pn = sizes[ci];
         // H2D of this chunk may start once the compute that last read d_in[s] is done
         if (step >= 2) RB_CUDA(cudaStreamWaitEvent(pipe.s_in, pipe.comp_done[s], 0));
+        const double *h_src = ri3ao + p0 * slab_in;
+        if (in_pageable) { // the H2D that last read pin_in[s] (two chunks ago) is long done; the GPU is busy with chunk ci-1
+            if (step >= 2) RB_CUDA(cudaEventSynchronize(pipe.in_done[s]));
+            host_copy_2d(pin_in[s], pn * slab_in, h_src, pn * slab_in, pn * slab_in, 1);
+            h_src = pin_in[s];
+        }
         mark(pipe.s_in);
         if (nb > 0)
-            RB_CUDA(cudaMemcpyAsync(d_in[s], ri3ao + p0 * slab_in, (size_t)(pn * slab_in) * 8, cudaMemcpyHostToDevice,
-                                    pipe.s_in));
+            RB_CUDA(cudaMemcpyAsync(d_in[s], h_src, (size_t)(pn * slab_in) * 8, cudaMemcpyHostToDevice, pipe.s_in));
         RB_CUDA(cudaEventRecord(pipe.in_done[s], pipe.s_in));
         mark(pipe.s_in);
         // compute needs the chunk in HBM and the previous D2H out of d_out[s]
@@ -246,11 +372,25 @@ int host_ri_stream(const double *cl, int nl, const double *cr, int nr, const dou
         if (do_mo) {
             // D2H: rows of pn doubles into the P-fastest host tensor (pitch nx)
             RB_CUDA(cudaStreamWaitEvent(pipe.s_out, pipe.comp_done[s], 0));
-            RB_CUDA(cudaMemcpy2DAsync(out + p0, (size_t)nx * 8, d_mo[s], (size_t)pn * 8, (size_t)pn * 8, (size_t)slab_out,
-                                      cudaMemcpyDeviceToHost, pipe.s_out));
+            if (out_pageable) // dense copy into the pinned block; host threads scatter it one chunk later
+                RB_CUDA(cudaMemcpyAsync(pin_out[s], d_mo[s], (size_t)(pn * slab_out) * 8, cudaMemcpyDeviceToHost, pipe.s_out));
+            else
+                RB_CUDA(cudaMemcpy2DAsync(out + p0, (size_t)nx * 8, d_mo[s], (size_t)pn * 8, (size_t)pn * 8, (size_t)slab_out,
+                                          cudaMemcpyDeviceToHost, pipe.s_out));
             RB_CUDA(cudaEventRecord(pipe.out_done[s], pipe.s_out));
             mark(pipe.s_out);
+            if (out_pageable && ci >= 1) { // previous chunk: its D2H ran while this chunk was copied in and enqueued
+                const i64 pp = sizes[ci - 1];
+                RB_CUDA(cudaEventSynchronize(pipe.out_done[s ^ 1]));
+                host_copy_2d(out + (p0 - pp), nx, pin_out[s ^ 1], pp, pp, slab_out);
+            }
         }
+    }
+    if (out_pageable && !sizes.empty()) { // last chunk
+        const i64 pp = sizes.back();
+        const int s = (step - 1) & 1;
+        RB_CUDA(cudaEventSynchronize(pipe.out_done[s]));
+        host_copy_2d(out + (nx - pp), nx, pin_out[s], pp, pp, slab_out);
     }
     const double t_enq = now_ms();
     if (do_k && slab_in > 0) RB_TRY(rb_symmetrize(ctx, d_k, nb, nb, true));
@@ -273,8 +413,9 @@ int host_ri_stream(const double *cl, int nl, const double *cr, int nr, const dou
     for (auto e : tl) cudaEventDestroy(e);
     if (tl0) cudaEventDestroy(tl0);
     if (trace)
-        fprintf(stderr, "[rest_b200] ri stream: nb=%lld nx=%lld pc=%lld chunks=%d  setup %.2f ms, enqueue %.2f ms, drain %.2f ms\n",
-                (long long)nb, (long long)nx, (long long)pc, step, t_alloc - t_start, t_enq - t_alloc, now_ms() - t_enq);
+        fprintf(stderr, "[rest_b200] ri stream: nb=%lld nx=%lld pc=%lld chunks=%d bounce(in,out)=%d,%d threads=%d  setup %.2f ms, enqueue %.2f ms, drain %.2f ms\n",
+                (long long)nb, (long long)nx, (long long)pc, step, (int)in_pageable, (int)out_pageable, host_threads(),
+                t_alloc - t_start, t_enq - t_alloc, now_ms() - t_enq);
     return RB_OK;
 }
 

@@ -13,6 +13,8 @@ extern "C" {
     pub fn rb_bind_host_to_device_numa(device: c_int, node_out: *mut c_int) -> c_int;
     pub fn rb_dev_alloc(ctx: *mut RbCtx, bytes: i64, out: *mut *mut c_void) -> c_int;
     pub fn rb_dev_free(ctx: *mut RbCtx, p: *mut c_void) -> c_int;
+    /// drop the cached device staging / pinned bounce blocks of the host-pointer entry points
+    pub fn rb_host_trim() -> c_int;
     pub fn rb_host_alloc_pinned(bytes: i64, out: *mut *mut c_void) -> c_int;
     pub fn rb_host_free_pinned(p: *mut c_void) -> c_int;
     pub fn rb_memcpy_h2d(ctx: *mut RbCtx, dst: *mut c_void, src: *const c_void, bytes: i64) -> c_int;

@@ -311,6 +311,42 @@ def test_ao2mo_multi_chunk_host_pipeline(rt, oracle_blas):
     assert_close_1e10(got.data, ref, "pipelined host ao2mo")
 
 
+def test_host_pass_pageable_pinned_and_unbounced_agree(rt, oracle_blas):
+    """The streaming host pass must give the same bits whether the caller's buffers are pinned (straight DMA), pageable
+    and bounced through pinned blocks by host threads (the default for a plain Vec<f64> / numpy array), or pageable with
+    the bounce disabled (driver-staged copies).  Several chunks with a ragged tail; then the caches are trimmed."""
+    import ctypes as C
+    import os
+    from rest_tensors_b200._lib import lib, check
+    nb, nx, no = 40, 777, 5
+    ri, c, dm, ct = _inputs(oracle_blas, nb, nx, no, False)
+    n2 = nb * nb
+
+    def run(pinned):
+        mk = (lambda n: torch.empty(n, dtype=torch.float64, pin_memory=True)) if pinned else (lambda n: torch.empty(n, dtype=torch.float64))
+        ri_h = mk(nx * n2); ri_h.copy_(torch.from_numpy(ri))
+        mo_h, d_h, j_h, k_h = mk(nx * n2), mk(nx), mk(n2), mk(n2)
+        c_h = torch.from_numpy(c.copy()); dm_h = torch.from_numpy(dm.copy()); ct_h = torch.from_numpy(ct.copy())
+        P = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+        check(lib.rb_host_ri_ao2mo_jk(P(c_h), nb, P(c_h), nb, P(ri_h), P(mo_h), nb, nx, P(dm_h), P(ct_h), no, P(d_h), P(j_h), P(k_h)),
+              "rb_host_ri_ao2mo_jk")
+        return [t.clone() for t in (mo_h, d_h, j_h, k_h)]
+
+    pinned = run(True)
+    bounced = run(False)
+    os.environ["REST_B200_BOUNCE"] = "0"
+    try:
+        direct = run(False)
+    finally:
+        del os.environ["REST_B200_BOUNCE"]
+    for a, b, d in zip(pinned, bounced, direct):
+        assert torch.equal(a, b) and torch.equal(a, d)
+    assert_close_1e10(pinned[0].numpy(), oracle_blas.ri_ao2mo_f(c, ri, nb, nb, nx), "host pass ao2mo")
+    assert lib.rb_host_trim() == 0
+    again = run(False)          # caches rebuild after a trim
+    assert torch.equal(again[0], pinned[0])
+
+
 def test_ao2mo_device_chunked_matches_single_pass(ctx, oracle_blas):
     """Device path: a small workspace budget forces several P-chunks (strided-batched GEMM 2, ragged last chunk); the
     single-chunk path runs GEMM 2 as one flat GEMM.  Both must agree with the reference algorithm and, since every

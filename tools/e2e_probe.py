@@ -8,8 +8,11 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     from rest_tensors_b200._lib import check
     nb, nx, no = 600, 1700, 60
     n2 = nb * nb
-    ri = torch.empty(nx * n2, dtype=torch.float64, pin_memory=True).uniform_(-1, 1)
-    mo = torch.empty(nx * n2, dtype=torch.float64, pin_memory=True)
+    pin = os.environ.get("PAGEABLE") != "1"
+    ri = torch.empty(nx * n2, dtype=torch.float64, pin_memory=pin).uniform_(-1, 1)
+    mo = torch.empty(nx * n2, dtype=torch.float64, pin_memory=pin)
+    if not pin:
+        mo.zero_()   # touch the pages
     c = torch.empty(n2, dtype=torch.float64, pin_memory=True).uniform_(-0.04, 0.04)
     dm = torch.empty(n2, dtype=torch.float64, pin_memory=True).uniform_(-1, 1)
     ct = c[: nb * no].clone().pin_memory()
@@ -21,7 +24,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         t0 = time.perf_counter(); check(fn(), "step"); ts.append(time.perf_counter() - t0)
     print(f"  total per call: {min(ts[1:])*1e3:.1f} ms (best of 3)  checksum {float(mo[::100003].sum()):.6e}", flush=True)
 else:
-    for env in [{}, {"REST_B200_HEAD": ""}]:
+    for env in [{}, {"PAGEABLE": "1"}, {"PAGEABLE": "1", "REST_B200_HOST_THREADS": "4"}, {"PAGEABLE": "1", "REST_B200_HOST_THREADS": "16"}, {"PAGEABLE": "1", "REST_B200_BOUNCE": "0"}]:
         print("variant", env, flush=True)
         e = dict(os.environ); e.update(env)
         out = subprocess.run([sys.executable, __file__, "child"], env=e, capture_output=True, text=True)
