@@ -126,6 +126,7 @@ struct HostOp {
     ~HostOp()
     {
         if (ctx) cudaStreamSynchronize(ctx->stream);
+        for (int i = 0; i < 2; ++i) if (piece_ev[i]) cudaEventDestroy(piece_ev[i]);
         i64 total = 0;
         pin_release_all();
         for (auto &b : g_stage) { b.busy = false; total += b.bytes; }
@@ -166,28 +167,127 @@ struct HostOp {
         return RB_OK;
     }
     // upload a host matrix block [rows x cols] with leading dimension ld into a dense device buffer
+    // ---- large pageable operands: pipelined bounce through two pinned pieces (memcpy threads | DMA) ----
+    static constexpr i64 PIECE = (i64)8 << 20;     // doubles per pinned piece (64 MB)
+    static constexpr i64 BOUNCE_MIN = (i64)2 << 20; // doubles (16 MB): below this the driver's staged copy is fine
+    double *piece[2] = {nullptr, nullptr};
+    cudaEvent_t piece_ev[2] = {nullptr, nullptr};
+    bool want_bounce(const void *host, i64 n)
+    {
+        if (n < BOUNCE_MIN) return false;
+        if (const char *e = getenv("REST_B200_BOUNCE")) if (atoi(e) == 0) return false;
+        if (host_ptr_is_pinned(host)) return false;
+        for (int i = 0; i < 2; ++i) {
+            if (!piece[i]) piece[i] = (double *)pin_take(PIECE * 8);
+            if (!piece[i]) return false;
+            if (!piece_ev[i] && cudaEventCreateWithFlags(&piece_ev[i], cudaEventDisableTiming) != cudaSuccess) return false;
+        }
+        return true;
+    }
+    // host [rows x cols] with pitch ld  ->  dense device [rows x cols]
     int up2d(double *dst, const double *src, i64 rows, i64 cols, i64 ld)
     {
         if (rows <= 0 || cols <= 0) return RB_OK;
-        RB_CUDA(cudaMemcpy2DAsync(dst, (size_t)rows * 8, src, (size_t)ld * 8, (size_t)rows * 8, (size_t)cols,
-                                  cudaMemcpyHostToDevice, ctx->stream));
+        if (!want_bounce(src, rows * cols)) {
+            RB_CUDA(cudaMemcpy2DAsync(dst, (size_t)rows * 8, src, (size_t)ld * 8, (size_t)rows * 8, (size_t)cols,
+                                      cudaMemcpyHostToDevice, ctx->stream));
+            return RB_OK;
+        }
+        i64 cpp = PIECE / rows; // whole columns per piece
+        if (cpp < 1) { // a single column longer than a piece: split it
+            for (i64 c = 0; c < cols; ++c) RB_TRY(up_dense(dst + c * rows, src + c * ld, rows));
+            return RB_OK;
+        }
+        int k = 0;
+        for (i64 c0 = 0; c0 < cols; c0 += cpp, ++k) {
+            const int s = k & 1;
+            const i64 cn = cols - c0 < cpp ? cols - c0 : cpp;
+            if (k >= 2) RB_CUDA(cudaEventSynchronize(piece_ev[s]));
+            host_copy_2d(piece[s], rows, src + c0 * ld, ld, rows, cn);
+            RB_CUDA(cudaMemcpyAsync(dst + c0 * rows, piece[s], (size_t)(rows * cn) * 8, cudaMemcpyHostToDevice, ctx->stream));
+            RB_CUDA(cudaEventRecord(piece_ev[s], ctx->stream));
+        }
+        RB_CUDA(cudaEventSynchronize(piece_ev[0]));
+        if (k > 1) RB_CUDA(cudaEventSynchronize(piece_ev[1])); // the pieces may be reused by the next transfer
         return RB_OK;
     }
+    int up_dense(double *dst, const double *src, i64 n)
+    {
+        int k = 0;
+        for (i64 o = 0; o < n; o += PIECE, ++k) {
+            const int s = k & 1;
+            const i64 len = n - o < PIECE ? n - o : PIECE;
+            if (k >= 2) RB_CUDA(cudaEventSynchronize(piece_ev[s]));
+            host_copy_2d(piece[s], len, src + o, len, len, 1);
+            RB_CUDA(cudaMemcpyAsync(dst + o, piece[s], (size_t)len * 8, cudaMemcpyHostToDevice, ctx->stream));
+            RB_CUDA(cudaEventRecord(piece_ev[s], ctx->stream));
+        }
+        RB_CUDA(cudaEventSynchronize(piece_ev[0]));
+        if (k > 1) RB_CUDA(cudaEventSynchronize(piece_ev[1]));
+        return RB_OK;
+    }
+    // dense device [rows x cols]  ->  host with pitch ld.  The bounced form returns with the data in place.
     int down2d(double *dst, i64 ld, const double *src, i64 rows, i64 cols)
     {
         if (rows <= 0 || cols <= 0) return RB_OK;
-        RB_CUDA(cudaMemcpy2DAsync(dst, (size_t)ld * 8, src, (size_t)rows * 8, (size_t)rows * 8, (size_t)cols,
-                                  cudaMemcpyDeviceToHost, ctx->stream));
+        if (!want_bounce(dst, rows * cols)) {
+            RB_CUDA(cudaMemcpy2DAsync(dst, (size_t)ld * 8, src, (size_t)rows * 8, (size_t)rows * 8, (size_t)cols,
+                                      cudaMemcpyDeviceToHost, ctx->stream));
+            return RB_OK;
+        }
+        i64 cpp = PIECE / rows;
+        if (cpp < 1) {
+            for (i64 c = 0; c < cols; ++c) RB_TRY(down_dense(dst + c * ld, src + c * rows, rows));
+            return RB_OK;
+        }
+        int k = 0;
+        i64 prev_c0 = 0, prev_cn = 0;
+        for (i64 c0 = 0; c0 < cols; c0 += cpp, ++k) {
+            const int s = k & 1;
+            const i64 cn = cols - c0 < cpp ? cols - c0 : cpp;
+            RB_CUDA(cudaMemcpyAsync(piece[s], src + c0 * rows, (size_t)(rows * cn) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            RB_CUDA(cudaEventRecord(piece_ev[s], ctx->stream));
+            if (k >= 1) { // scatter the previous piece while this one is in flight
+                RB_CUDA(cudaEventSynchronize(piece_ev[s ^ 1]));
+                host_copy_2d(dst + prev_c0 * ld, ld, piece[s ^ 1], rows, rows, prev_cn);
+            }
+            prev_c0 = c0; prev_cn = cn;
+        }
+        RB_CUDA(cudaEventSynchronize(piece_ev[(k - 1) & 1]));
+        host_copy_2d(dst + prev_c0 * ld, ld, piece[(k - 1) & 1], rows, rows, prev_cn);
+        return RB_OK;
+    }
+    int down_dense(double *dst, const double *src, i64 n)
+    {
+        int k = 0;
+        i64 prev_o = 0, prev_len = 0;
+        for (i64 o = 0; o < n; o += PIECE, ++k) {
+            const int s = k & 1;
+            const i64 len = n - o < PIECE ? n - o : PIECE;
+            RB_CUDA(cudaMemcpyAsync(piece[s], src + o, (size_t)len * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            RB_CUDA(cudaEventRecord(piece_ev[s], ctx->stream));
+            if (k >= 1) {
+                RB_CUDA(cudaEventSynchronize(piece_ev[s ^ 1]));
+                host_copy_2d(dst + prev_o, prev_len, piece[s ^ 1], prev_len, prev_len, 1);
+            }
+            prev_o = o; prev_len = len;
+        }
+        RB_CUDA(cudaEventSynchronize(piece_ev[(k - 1) & 1]));
+        host_copy_2d(dst + prev_o, prev_len, piece[(k - 1) & 1], prev_len, prev_len, 1);
         return RB_OK;
     }
     int up(double *dst, const double *src, i64 n)
     {
-        if (n > 0) RB_CUDA(cudaMemcpyAsync(dst, src, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        if (n <= 0) return RB_OK;
+        if (want_bounce(src, n)) return up_dense(dst, src, n);
+        RB_CUDA(cudaMemcpyAsync(dst, src, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
         return RB_OK;
     }
     int down(double *dst, const double *src, i64 n)
     {
-        if (n > 0) RB_CUDA(cudaMemcpyAsync(dst, src, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (n <= 0) return RB_OK;
+        if (want_bounce(dst, n)) return down_dense(dst, src, n);
+        RB_CUDA(cudaMemcpyAsync(dst, src, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
         return RB_OK;
     }
     int sync()

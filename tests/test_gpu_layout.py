@@ -262,3 +262,29 @@ def test_c_abi_error_codes_and_recovery(ctx, rt):
     assert torch.all(c == 16.0)
     node = C.c_int(-5)
     assert lib.rb_bind_host_to_device_numa(0, C.byref(node)) == 0 and node.value >= -1
+
+
+def test_host_wrappers_large_pageable_operands(rt, oracle, oracle_blas):
+    """Operands >= 16 MB in pageable memory (numpy arrays) take the pipelined pinned-bounce path of the host wrappers
+    (dense and pitched, several 64 MB pieces); results must be what the small direct path gives: bit-exact layout ops,
+    1e-10 GEMM with leading dimensions larger than the rows."""
+    from conftest import assert_close_1e10
+    n = 4300                                         # packed 9.2 M doubles (2 pieces), full 18.5 M (3 pieces)
+    packed = oracle.fill_linear(n * (n + 1) // 2, 61)
+    full = rt.MatrixUpper.from_vec(packed.size, packed).to_matrixfull()
+    assert np.array_equal(full.data, oracle.to_matrixfull(packed))
+    assert np.array_equal(full.to_matrixupper().data, packed)
+    r, c = 3000, 2500
+    a = oracle.fill_linear(r * c, 62)
+    assert np.array_equal(rt.MatrixFull.from_vec([r, c], a).transpose().data, oracle.matrix_transpose(a, r, c))
+    # sub-block GEMM through general_dgemm_f_: pitched uploads / download of blocks inside larger matrices
+    ra, ca, rb, cb, rc, cc = 2600, 1700, 1700, 2300, 2700, 2400
+    m, k, nn = 2500, 1600, 2200
+    A = rt.MatrixFull.from_vec([ra, ca], oracle.fill_linear(ra * ca, 63))
+    B = rt.MatrixFull.from_vec([rb, cb], oracle.fill_linear(rb * cb, 64))
+    Cm = rt.MatrixFull.from_vec([rc, cc], oracle.fill_linear(rc * cc, 65))
+    c_ref = Cm.data.copy()
+    oracle_blas.general_dgemm_f(A.data, [ra, ca], (50, 50 + m), (60, 60 + k), "N", B.data, [rb, cb], (70, 70 + k), (30, 30 + nn), "N",
+                                c_ref, [rc, cc], (100, 100 + m), (90, 90 + nn), 0.7, 0.2)
+    rt._dgemm(A, ((50, 50 + m), (60, 60 + k)), "N", B, ((70, 70 + k), (30, 30 + nn)), "N", Cm, ((100, 100 + m), (90, 90 + nn)), 0.7, 0.2)
+    assert_close_1e10(Cm.data, c_ref, "large sub-block dgemm, pageable operands")
