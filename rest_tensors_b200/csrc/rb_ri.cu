@@ -34,22 +34,38 @@ static i64 ws_budget_bytes(rb_ctx *ctx)
     return budget;
 }
 
-// P-chunk length: as large as the workspace budget allows, balanced across chunks, a multiple of `align` (128 where P
-// is the M index of a GEMM tile, so that only the last chunk has a ragged tile row).
-static i64 pick_chunk(i64 nx, i64 bytes_per_slab, i64 budget, i64 align)
+// Cost, in 128-row GEMM tiles, of a chunk of p slabs when P is the M index of the tile (ao2mo GEMM 2): full tiles plus
+// the ragged one, which the kernel works on at 16-row block granularity with at most 2 block rows per warp row
+// (1 block -> 1/8, 2 -> 1/4, 3-4 -> 1/2, 5-8 -> a full tile; see the warp-grid choice in rb_gemm.cu).
+static double chunk_tile_cost(i64 p)
+{
+    const i64 full = p / 128, blocks = ((p % 128) + 15) / 16;
+    const double rag = blocks == 0 ? 0.0 : blocks == 1 ? 0.125 : blocks == 2 ? 0.25 : blocks <= 4 ? 0.5 : 1.0;
+    return (double)full + rag;
+}
+
+// P-chunk length: as large as the workspace budget allows.  tile_m: P is the M index of a GEMM tile -> among the chunk
+// lengths that need the fewest chunks pick the one with the cheapest tiling (e.g. 600 slabs in two chunks: 320 + 280
+// costs 4.75 tiles, 304 + 296 or 256 + 256 + 88 cost 5).
+static i64 pick_chunk(i64 nx, i64 bytes_per_slab, i64 budget, bool tile_m)
 {
     i64 pc_max = budget / (bytes_per_slab > 0 ? bytes_per_slab : 1);
     if (pc_max < 8) pc_max = 8;
     if (pc_max >= nx) return nx;
-    i64 nchunks = rb_cdiv(nx, pc_max);
-    i64 pc = rb_cdiv(nx, nchunks);
-    if (pc >= align && (pc_max / align) * align >= align) {
-        pc = rb_cdiv(pc, align) * align;
-        if (pc > pc_max) pc = (pc_max / align) * align;
-    } else {
-        pc = (pc + 7) & ~(i64)7;
+    const i64 nchunks = rb_cdiv(nx, pc_max);
+    i64 pc = (rb_cdiv(nx, nchunks) + 7) & ~(i64)7;
+    if (pc > pc_max) pc = pc_max & ~(i64)7;
+    if (pc < 8) pc = 8;
+    if (!tile_m) return pc < nx ? pc : nx;
+    i64 best = pc;
+    double best_cost = 1e300;
+    for (i64 cand = pc; cand <= pc_max; cand += 8) {
+        if (rb_cdiv(nx, cand) != nchunks) break;
+        const i64 whole = nx / cand, rem = nx - whole * cand;
+        const double cost = (double)whole * chunk_tile_cost(cand) + chunk_tile_cost(rem);
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = cand; }
     }
-    return pc < nx ? pc : nx;
+    return best < nx ? best : nx;
 }
 
 extern "C" int rb_ri_ao2mo(rb_ctx *ctx, const double *c_left, int nl, const double *c_right, int nr,
@@ -68,7 +84,7 @@ extern "C" int rb_ri_ao2mo(rb_ctx *ctx, const double *c_left, int nl, const doub
         return RB_OK;
     }
     RB_REQUIRE(c_left && c_right && ri3ao, "rb_ri_ao2mo: NULL input");
-    const i64 pc = pick_chunk(nx, nb * nl * 8, ws_budget_bytes(ctx), 128);
+    const i64 pc = pick_chunk(nx, nb * nl * 8, ws_budget_bytes(ctx), true);
     void *ws;
     RB_TRY(rb_ws_reserve(ctx, 0, nb * pc * nl * 8, &ws));
     double *w = (double *)ws;
@@ -117,7 +133,7 @@ extern "C" int rb_ri_j(rb_ctx *ctx, const double *ri3ao, const double *d, double
 // Upper triangle of k (+)= sum_P Y_P Y_P^T over the given slabs (beta = 0 overwrites, 1 accumulates); no mirroring.
 int rb_ri_k_upper(rb_ctx *ctx, const double *ri3ao, const double *ct, i64 no, double *k, i64 nb, i64 nx, double beta)
 {
-    const i64 pc = pick_chunk(nx, nb * no * 8, ws_budget_bytes(ctx), 8);
+    const i64 pc = pick_chunk(nx, nb * no * 8, ws_budget_bytes(ctx), false);
     RB_REQUIRE(no * pc <= 2147483647LL, "rb_ri_k: chunk too large");
     void *ws;
     RB_TRY(rb_ws_reserve(ctx, 0, nb * no * pc * 8, &ws));
