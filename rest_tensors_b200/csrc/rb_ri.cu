@@ -27,7 +27,10 @@ static i64 ws_budget_bytes(rb_ctx *ctx)
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return (i64)1 << 30; }
     i64 have = (i64)free_b + ctx->ws_bytes[0];
     i64 budget = have / 3;
-    const i64 cap = (i64)8 << 30;
+    // 16 GB by default: config D's whole per-rank intermediate (nb * 600 * nb doubles = 15.6 GB) then fits in ONE chunk,
+    // which makes ao2mo GEMM 2 a single flat GEMM; REST_B200_WS_CAP_GB overrides.
+    i64 cap = (i64)16 << 30;
+    if (const char *e = getenv("REST_B200_WS_CAP_GB")) { const i64 v = atoll(e); if (v >= 1) cap = v << 30; }
     if (budget > cap) budget = cap;
     if (budget < ((i64)64 << 20)) budget = (i64)64 << 20;
     ctx->ws_budget = budget;
