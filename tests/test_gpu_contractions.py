@@ -156,6 +156,40 @@ def test_dgemm_many_tiles_dynamic_scheduler(ctx, oracle_blas):
                 assert torch.equal(cd, first), "GEMM result must not depend on which CTA computed a tile"
 
 
+def test_dgemm_random_shape_sweep(ctx, oracle_blas):
+    """Seeded sweep over ops, ragged m / n (all block-row / block-column counts of an edge tile), K tails (k mod 8, k mod
+    32), even leading dimensions with padding, alpha / beta, batches with and without a shared B -- TMA path vs OpenBLAS."""
+    rng = np.random.default_rng(20260)
+    for case in range(60):
+        ta, tb = rng.choice(["N", "T"]), rng.choice(["N", "T"])
+        m = int(rng.choice([rng.integers(1, 40), 128 + 16 * rng.integers(0, 8) + rng.integers(0, 16), rng.integers(200, 700)]))
+        n = int(rng.choice([rng.integers(1, 40), 128 + 16 * rng.integers(0, 8) + rng.integers(0, 16), rng.integers(200, 700)]))
+        k = int(rng.choice([rng.integers(1, 9), 32 * rng.integers(1, 6) + rng.integers(0, 32), rng.integers(100, 900)]))
+        batch = int(rng.choice([1, 1, 3]))
+        ra, ca = (m, k) if ta == "N" else (k, m)
+        rb, cb = (k, n) if tb == "N" else (n, k)
+        lda, ldb, ldc = ra + ra % 2 + 2 * int(rng.integers(0, 3)), rb + rb % 2 + 2 * int(rng.integers(0, 3)), m + m % 2 + 2 * int(rng.integers(0, 3))
+        sa, sc = lda * ca + 2 * int(rng.integers(0, 3)), ldc * n
+        shared_b = bool(rng.integers(0, 2))
+        sb = 0 if shared_b else ldb * cb
+        alpha, beta = [(1.0, 0.0), (0.5, 0.0), (1.0, 1.0), (-0.7, 0.3)][int(rng.integers(0, 4))]
+        a = rng.standard_normal(sa * batch); b = rng.standard_normal(ldb * cb * (1 if shared_b else batch)); c0 = rng.standard_normal(sc * batch)
+        c_ref = c0.copy()
+        for bi in range(batch):
+            cb_ = c_ref[bi * sc:(bi + 1) * sc]
+            oracle_blas.dgemm(ta, tb, m, n, k, alpha, a[bi * sa:], lda, b[bi * sb:], ldb, beta, cb_, ldc)
+        cd = _dev(ctx, c0)
+        ctx.dgemm_strided_batched(ta, tb, m, n, k, alpha, _dev(ctx, a), lda, sa, _dev(ctx, b), ldb, sb, beta, cd, ldc, sc, batch)
+        got = cd.cpu().numpy()
+        what = f"case {case}: {ta}{tb} m={m} n={n} k={k} batch={batch} ld=({lda},{ldb},{ldc}) alpha={alpha} beta={beta}"
+        ok_rows = np.zeros(sc * batch, dtype=bool)
+        for bi in range(batch):
+            blk = ok_rows[bi * sc:(bi + 1) * sc].reshape((ldc, n), order="F")
+            blk[:m, :] = True
+        assert_close_1e10(got[ok_rows], c_ref[ok_rows], what)
+        assert np.array_equal(got[~ok_rows], c0[~ok_rows]), what + " (padding rows of C touched)"
+
+
 def test_dgemm_split_k_deterministic(ctx, oracle_blas):
     """few tiles + deep K -> split-K partials reduced in a fixed order: bitwise repeatable, 1e-10 vs OpenBLAS."""
     m, n, k = 200, 130, 20000
