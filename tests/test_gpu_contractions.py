@@ -262,6 +262,31 @@ def test_dsyrk(rt, oracle_blas, uplo, trans):
         assert np.array_equal(other(got), other(orig)), "the other triangle must stay untouched"
 
 
+def test_dsyrk_random_sweep(ctx, oracle_blas):
+    """Seeded sweep: both triangles / transposes, ragged n across tile boundaries, shallow and deep k (split-K), even
+    and odd leading dimensions (TMA and generic kernels), beta 0 / 1 / other; the other triangle stays bit-identical."""
+    rng = np.random.default_rng(777)
+    for case in range(40):
+        uplo, trans = rng.choice(["U", "L"]), rng.choice(["N", "T"])
+        n = int(rng.choice([rng.integers(1, 30), 128 * rng.integers(1, 4) + rng.integers(0, 128), rng.integers(250, 600)]))
+        k = int(rng.choice([rng.integers(1, 40), rng.integers(100, 700), rng.integers(3000, 9000)]))
+        ra, ca = (n, k) if trans == "N" else (k, n)
+        lda = ra + int(rng.integers(0, 4)); ldc = n + int(rng.integers(0, 4))
+        alpha, beta = [(1.0, 0.0), (1.0, 1.0), (0.9, -0.4)][int(rng.integers(0, 3))]
+        a = rng.standard_normal(lda * ca); c0 = rng.standard_normal(ldc * n)
+        c_ref = c0.copy()
+        oracle_blas.dsyrk(uplo, trans, n, k, alpha, a, lda, beta, c_ref, ldc)
+        cd = _dev(ctx, c0)
+        ctx.dsyrk(uplo, trans, n, k, alpha, _dev(ctx, a), lda, beta, cd, ldc)
+        got = cd.cpu().numpy().reshape((ldc, n), order="F"); ref = c_ref.reshape((ldc, n), order="F"); orig = c0.reshape((ldc, n), order="F")
+        tri = np.triu if uplo == "U" else np.tril
+        mask = tri(np.ones((n, n), dtype=bool))
+        what = f"case {case}: dsyrk {uplo}{trans} n={n} k={k} lda={lda} ldc={ldc} alpha={alpha} beta={beta}"
+        assert_close_1e10(got[:n][mask], ref[:n][mask], what)
+        assert np.array_equal(got[:n][~mask], orig[:n][~mask]), what + " (other triangle touched)"
+        assert np.array_equal(got[n:], orig[n:]), what + " (padding rows touched)"
+
+
 @pytest.mark.parametrize("side", "LR")
 @pytest.mark.parametrize("uplo", "UL")
 def test_dsymm(rt, oracle_blas, side, uplo):
