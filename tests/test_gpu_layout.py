@@ -288,3 +288,35 @@ def test_host_wrappers_large_pageable_operands(rt, oracle, oracle_blas):
                                 c_ref, [rc, cc], (100, 100 + m), (90, 90 + nn), 0.7, 0.2)
     rt._dgemm(A, ((50, 50 + m), (60, 60 + k)), "N", B, ((70, 70 + k), (30, 30 + nn)), "N", Cm, ((100, 100 + m), (90, 90 + nn)), 0.7, 0.2)
     assert_close_1e10(Cm.data, c_ref, "large sub-block dgemm, pageable operands")
+
+
+def test_host_entry_points_from_many_threads(rt, oracle_blas):
+    """REST calls the wrappers from rayon worker threads (per-slab work inside par_iter_auxbas): the host-pointer entry
+    points must be safe to call concurrently (they serialise on the default context) and keep every result intact."""
+    import threading
+    from conftest import assert_close_1e10
+    m, k, n = 150, 90, 70
+    jobs = []
+    for t in range(8):
+        a = oracle_blas.fill_linear(m * k, 70 + t); b = oracle_blas.fill_linear(k * n, 90 + t)
+        ref = np.zeros(m * n); oracle_blas.dgemm("N", "N", m, n, k, 1.0, a, m, b, k, 0.0, ref, m)
+        jobs.append((a, b, ref))
+    errors = []
+
+    def work(t):
+        try:
+            a, b, ref = jobs[t]
+            for _ in range(5):
+                c = rt._dgemm_full_new(rt.MatrixFull.from_vec([m, k], a), "N", rt.MatrixFull.from_vec([k, n], b), "N", 1.0, 0.0)
+                assert_close_1e10(c.data, ref, f"thread {t}")
+                p = rt.MatrixFull.from_vec([n, n], ref[: n * n].copy()).to_matrixupper()
+                assert p.data.size == n * (n + 1) // 2
+        except Exception as exc:  # noqa: BLE001
+            errors.append(f"thread {t}: {exc}")
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(8)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
