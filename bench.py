@@ -424,6 +424,15 @@ def run_ours(args):
         t0 = time.perf_counter(); cpu.step(); cdt = time.perf_counter() - t0
         cpu_baseline = {"value": sum(flops(nb, slabs, no).values()) / cdt / 1e9, "unit": UNIT, "cores": cpu.threads,
                         "kind": "port", "sample": cpu.describe(slabs, nx)}
+        # the same algorithm on ONE host thread (SURVEY 8d asks for both), on a ~3 s sample
+        if cpu.have_blas and cpu.threads > 1:
+            all_threads = cpu.threads
+            cpu.o.set_threads(1)
+            s1 = cpu.calibrate(target_s=3.0, max_slabs=slabs)
+            t0 = time.perf_counter(); cpu.step(); c1 = time.perf_counter() - t0
+            cpu.o.set_threads(all_threads)
+            cpu_baseline["value_single_thread"] = sum(flops(nb, s1, no).values()) / c1 / 1e9
+            cpu_baseline["single_thread_sample_slabs"] = s1
 
     traffic = None
     try:
