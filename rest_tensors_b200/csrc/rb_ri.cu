@@ -71,6 +71,83 @@ static i64 pick_chunk(i64 nx, i64 bytes_per_slab, i64 budget, bool tile_m)
     return best < nx ? best : nx;
 }
 
+// ---- odd nb / unaligned tensors ------------------------------------------------------------------------------
+// TMA needs 16-byte aligned bases and row pitches, i.e. an even leading dimension.  Basis-set sizes are arbitrary, so
+// for odd nb (or an 8-byte-aligned tensor) every P-chunk is first copied into zero-padded slabs [nbp, nbp], nbp = nb
+// rounded up to even, C gets a zero row, and the same two GEMMs run with K = nbp: the extra products are exact zeros, so
+// every sum keeps its value, at the cost of one HBM pass over the chunk (measured at nb = 601: the plain-load fallback
+// GEMM kernel gives 5 TFLOP/s, this path the TMA kernel's rate minus the copy).
+__global__ void __launch_bounds__(256) rb_pad_rows_kernel(const double *__restrict__ src, i64 n_in, i64 rows_in, i64 group_stride,
+                                                          double *__restrict__ dst, i64 n_out, i64 rows_out, i64 total_rows)
+{
+    const int lane = threadIdx.x & 31;
+    const i64 warps = (i64)gridDim.x * 8;
+    for (i64 r = (i64)blockIdx.x * 8 + (threadIdx.x >> 5); r < total_rows; r += warps) {
+        const i64 g = r / rows_out, v = r - g * rows_out;
+        const bool valid = v < rows_in;
+        const double *srow = src + g * group_stride + v * n_in;
+        double *drow = dst + r * n_out;
+        for (i64 i = lane; i < n_out; i += 32) drow[i] = (valid && i < n_in) ? srow[i] : 0.0;
+    }
+}
+
+// dst[groups][rows_out][n_out] <- src[groups][rows_in][n_in] (dense), zero elsewhere
+static int pad_rows(rb_ctx *ctx, const double *src, i64 n_in, i64 rows_in, double *dst, i64 n_out, i64 rows_out, i64 groups)
+{
+    const i64 total = rows_out * groups;
+    if (total <= 0 || n_out <= 0) return RB_OK;
+    i64 blocks = rb_cdiv(total, 8);
+    const i64 cap = (i64)ctx->num_sms * 8;
+    if (blocks > cap) blocks = cap;
+    rb_pad_rows_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(src, n_in, rows_in, n_in * rows_in, dst, n_out, rows_out, total);
+    RB_LAUNCHED(ctx);
+    return RB_OK;
+}
+
+// dst[i + j*ldd] = beta*dst + src[i + j*lds] for the m x n block (upper: only i <= j)
+__global__ void __launch_bounds__(256) rb_add_block_kernel(double *__restrict__ dst, i64 ldd, const double *__restrict__ src,
+                                                           i64 lds, i64 m, i64 n, double beta, int upper)
+{
+    const i64 total = m * n, stride = (i64)gridDim.x * blockDim.x;
+    for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const i64 i = e % m, j = e / m;
+        if (upper && i > j) continue;
+        double *d = dst + i + j * ldd;
+        const double v = src[i + j * lds];
+        *d = (beta == 0.0) ? v : beta * (*d) + v;
+    }
+}
+
+static bool ri_needs_pad(i64 nb, const double *ri3ao) { return (nb & 1) || (((uintptr_t)ri3ao) & 15); }
+
+static int ri_ao2mo_padded(rb_ctx *ctx, const double *c_left, i64 nl, const double *c_right, i64 nr, const double *ri3ao,
+                           double *out, i64 nb, i64 nx, i64 out_ldp)
+{
+    const i64 nbp = nb + (nb & 1);
+    const bool same_c = c_left == c_right && nl == nr;
+    const i64 c_elems = nbp * nl + (same_c ? 0 : nbp * nr);
+    i64 budget = ws_budget_bytes(ctx) - c_elems * 8;
+    if (budget < ((i64)32 << 20)) budget = (i64)32 << 20;
+    const i64 pc = pick_chunk(nx, (nbp * nbp + nbp * nl) * 8, budget, true);
+    void *ws;
+    RB_TRY(rb_ws_reserve(ctx, 0, (c_elems + nbp * nbp * pc + nbp * pc * nl) * 8, &ws));
+    double *clp = (double *)ws, *crp = same_c ? clp : clp + nbp * nl;
+    double *rip = clp + c_elems, *w = rip + nbp * nbp * pc;
+    RB_TRY(pad_rows(ctx, c_left, nb, nl, clp, nbp, nl, 1));
+    if (!same_c) RB_TRY(pad_rows(ctx, c_right, nb, nr, crp, nbp, nr, 1));
+    for (i64 p0 = 0; p0 < nx; p0 += pc) {
+        const i64 pn = (nx - p0 < pc) ? nx - p0 : pc;
+        RB_TRY(pad_rows(ctx, ri3ao + p0 * nb * nb, nb, nb, rip, nbp, nbp, pn));
+        RB_TRY(rb_gemm_core(ctx, true, false, nbp * pn, nl, nbp, 1.0, rip, nbp, 0, clp, nbp, 0, 0.0, w, nbp * pn, 0, 1, 0));
+        if (pn == out_ldp)
+            RB_TRY(rb_gemm_core(ctx, true, false, pn * nl, nr, nbp, 1.0, w, nbp, 0, crp, nbp, 0, 0.0, out, out_ldp * nl, 0, 1, 0));
+        else
+            RB_TRY(rb_gemm_core(ctx, true, false, pn, nr, nbp, 1.0, w, nbp, nbp * pn, crp, nbp, 0, 0.0, out + p0, out_ldp * nl,
+                                out_ldp, nl, 0));
+    }
+    return RB_OK;
+}
+
 extern "C" int rb_ri_ao2mo(rb_ctx *ctx, const double *c_left, int nl, const double *c_right, int nr,
                            const double *ri3ao, double *out, int nb_, int nx_, int64_t out_ldp)
 {
@@ -87,6 +164,8 @@ extern "C" int rb_ri_ao2mo(rb_ctx *ctx, const double *c_left, int nl, const doub
         return RB_OK;
     }
     RB_REQUIRE(c_left && c_right && ri3ao, "rb_ri_ao2mo: NULL input");
+    if (ri_needs_pad(nb, ri3ao) || (((uintptr_t)c_left | (uintptr_t)c_right) & 15))
+        return ri_ao2mo_padded(ctx, c_left, nl, c_right, nr, ri3ao, out, nb, nx, out_ldp);
     const i64 pc = pick_chunk(nx, nb * nl * 8, ws_budget_bytes(ctx), true);
     void *ws;
     RB_TRY(rb_ws_reserve(ctx, 0, nb * pc * nl * 8, &ws));
@@ -136,6 +215,29 @@ extern "C" int rb_ri_j(rb_ctx *ctx, const double *ri3ao, const double *d, double
 // Upper triangle of k (+)= sum_P Y_P Y_P^T over the given slabs (beta = 0 overwrites, 1 accumulates); no mirroring.
 int rb_ri_k_upper(rb_ctx *ctx, const double *ri3ao, const double *ct, i64 no, double *k, i64 nb, i64 nx, double beta)
 {
+    if (ri_needs_pad(nb, ri3ao) || (((uintptr_t)ct) & 15)) { // see the note above ri_ao2mo_padded
+        const i64 nbp = nb + (nb & 1);
+        const i64 fixed = nbp * no + nbp * nbp; // padded Ct and the padded accumulator K'
+        i64 budget = ws_budget_bytes(ctx) - fixed * 8;
+        if (budget < ((i64)32 << 20)) budget = (i64)32 << 20;
+        const i64 pc = pick_chunk(nx, (nbp * nbp + nbp * no) * 8, budget, false);
+        RB_REQUIRE(no * pc <= 2147483647LL, "rb_ri_k: chunk too large");
+        void *ws;
+        RB_TRY(rb_ws_reserve(ctx, 0, (fixed + nbp * nbp * pc + nbp * no * pc) * 8, &ws));
+        double *ctp = (double *)ws, *kp = ctp + nbp * no, *rip = kp + nbp * nbp, *y = rip + nbp * nbp * pc;
+        RB_TRY(pad_rows(ctx, ct, nb, no, ctp, nbp, no, 1));
+        for (i64 p0 = 0; p0 < nx; p0 += pc) {
+            const i64 pn = (nx - p0 < pc) ? nx - p0 : pc;
+            RB_TRY(pad_rows(ctx, ri3ao + p0 * nb * nb, nb, nb, rip, nbp, nbp, pn));
+            RB_TRY(rb_gemm_core(ctx, false, false, nbp, no, nbp, 1.0, rip, nbp, nbp * nbp, ctp, nbp, 0, 0.0, y, nbp, nbp * no, pn, 0));
+            RB_TRY(rb_gemm_core(ctx, false, true, nbp, nbp, no * pn, 1.0, y, nbp, 0, y, nbp, 0, p0 == 0 ? 0.0 : 1.0, kp, nbp, 0, 1, 1));
+        }
+        i64 blocks = rb_cdiv(nb * nb, 256);
+        if (blocks > (i64)ctx->num_sms * 8) blocks = (i64)ctx->num_sms * 8;
+        rb_add_block_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(k, nb, kp, nbp, nb, nb, beta, 1);
+        RB_LAUNCHED(ctx);
+        return RB_OK;
+    }
     const i64 pc = pick_chunk(nx, nb * no * 8, ws_budget_bytes(ctx), false);
     RB_REQUIRE(no * pc <= 2147483647LL, "rb_ri_k: chunk too large");
     void *ws;

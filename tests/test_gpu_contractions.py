@@ -406,6 +406,30 @@ def test_host_pass_pageable_pinned_and_unbounced_agree(rt, oracle_blas):
     assert torch.equal(again[0], pinned[0])
 
 
+@pytest.mark.parametrize("nb,nx,no,offset", [(131, 50, 9, 0), (257, 12, 30, 0), (64, 40, 8, 1)])
+def test_odd_nb_and_unaligned_tensors_take_the_padded_tma_path(ctx, oracle_blas, nb, nx, no, offset):
+    """Odd basis sizes (and 8-byte-aligned device tensors) cannot be described by TMA directly: ao2mo and K copy each
+    chunk into zero-padded slabs and run the same GEMMs.  Parity with the reference algorithm, square and occ-vir."""
+    from rest_tensors_b200.device import ShardedRI
+    ri, c, dm, ct = _inputs(oracle_blas, nb, nx, no, False)
+    n2 = nb * nb
+    buf = ctx.empty(nx * n2 + 1)
+    buf[offset: offset + nx * n2].copy_(torch.from_numpy(ri))
+    sh = ShardedRI(ctx, nb, nx, data=buf[offset: offset + nx * n2])
+    cbuf = ctx.empty(n2 + 1); cbuf[offset: offset + n2].copy_(torch.from_numpy(c)); cd = cbuf[offset: offset + n2]
+    assert_close_1e10(sh.ao2mo(cd, nb, cd, nb).cpu().numpy(), oracle_blas.ri_ao2mo_f(c, ri, nb, nb, nx), "padded ao2mo")
+    cm = c.reshape((nb, nb), order="F")
+    cl, cr = _col(cm[:, :no]), _col(cm[:, no:])
+    got = sh.ao2mo(cd[: nb * no], no, cd[nb * no:], nb - no)
+    assert_close_1e10(got.cpu().numpy(), oracle_blas.ri_ao2mo_rect(cl, no, cr, nb - no, ri, nb, nx), "padded occ-vir ao2mo")
+    ctb = ctx.empty(nb * no + 1); ctb[offset: offset + nb * no].copy_(torch.from_numpy(ct))
+    k = sh.k(ctb[offset: offset + nb * no], no, reduce=False)
+    assert_close_1e10(k.cpu().numpy(), oracle_blas.ri_k(ri, ct, nb, no, nx), "padded K")
+    d = sh.dp(_dev(ctx, dm))
+    assert_close_1e10(d.cpu().numpy(), oracle_blas.ri_dp(ri, dm, nb, nx), "d_P on an odd / unaligned tensor")
+    assert_close_1e10(sh.j(d, reduce=False).cpu().numpy(), oracle_blas.ri_j(ri, oracle_blas.ri_dp(ri, dm, nb, nx), nb, nx), "J")
+
+
 def test_ao2mo_device_chunked_matches_single_pass(ctx, oracle_blas):
     """Device path: a small workspace budget forces several P-chunks (strided-batched GEMM 2, ragged last chunk); the
     single-chunk path runs GEMM 2 as one flat GEMM.  Both must agree with the reference algorithm and, since every
