@@ -112,8 +112,17 @@ __global__ void __launch_bounds__(256) rb_gemv_t_kernel(const double *__restrict
         }
         for (; i < n2; i += 256) { double2 a0 = c2[i], x0 = x2[i]; s0 += a0.x * x0.x + a0.y * x0.y; }
         if (((r1 - r0) & 1) && threadIdx.x == 0) s1 += col[r1 - 1] * x[r1 - 1];
-    } else {
-        for (i64 i = r0 + threadIdx.x; i < r1; i += 256) s0 += col[i] * x[i * incx];
+    } else { // odd lda / unaligned: 8-byte coalesced loads, 8 of them in flight per thread
+        i64 i = r0 + threadIdx.x;
+        double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+        for (; i + 7 * 256 < r1; i += 8 * 256) {
+            const double a0 = col[i], a1 = col[i + 256], a2 = col[i + 512], a3 = col[i + 768];
+            const double a4 = col[i + 1024], a5 = col[i + 1280], a6 = col[i + 1536], a7 = col[i + 1792];
+            s0 += a0 * x[i * incx]; s1 += a1 * x[(i + 256) * incx]; s2 += a2 * x[(i + 512) * incx]; s3 += a3 * x[(i + 768) * incx];
+            t0 += a4 * x[(i + 1024) * incx]; t1 += a5 * x[(i + 1280) * incx]; t2 += a6 * x[(i + 1536) * incx]; t3 += a7 * x[(i + 1792) * incx];
+        }
+        for (; i < r1; i += 256) s0 += col[i] * x[i * incx];
+        s0 += t0; s1 += t1; s2 += t2; s3 += t3;
     }
     double s = (s0 + s1) + (s2 + s3);
     s = warp_sum(s);
@@ -196,6 +205,57 @@ __global__ void __launch_bounds__(256, 4) rb_gemv_t_vec_kernel(const double *__r
 #pragma unroll
             for (int w = 0; w < 8; ++w) s += red[w][tid];
             partial[rc + (j0 + tid) * row_chunks] = s;
+        }
+        __syncthreads();
+    }
+}
+
+// Same unit decomposition with 8-byte loads, for matrices whose columns are not 16-byte aligned (odd lda: nb odd makes
+// m = nb^2 odd): x is still shared by the 4 columns of a group, 8 independent loads of A in flight per thread.
+__global__ void __launch_bounds__(256, 4) rb_gemv_t_cols4_kernel(const double *__restrict__ a, i64 lda, i64 m, i64 n,
+                                                                  const double *__restrict__ x, double *__restrict__ partial,
+                                                                  i64 row_chunks, i64 col_groups)
+{
+    __shared__ double red[8][GT_COLS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const i64 units = row_chunks * col_groups;
+    for (i64 u = blockIdx.x; u < units; u += gridDim.x) {
+        const i64 rc = u % row_chunks, cg = u / row_chunks;
+        const i64 r0 = rc * GT_RCH;
+        const i64 r1 = (r0 + GT_RCH < m) ? r0 + GT_RCH : m;
+        const i64 j0 = cg * GT_COLS;
+        const double *col[GT_COLS];
+#pragma unroll
+        for (int g = 0; g < GT_COLS; ++g) {
+            i64 j = j0 + g < n ? j0 + g : n - 1;
+            col[g] = a + j * lda;
+        }
+        double acc[GT_COLS] = {0.0, 0.0, 0.0, 0.0};
+        i64 i = r0 + tid;
+        for (; i + 256 < r1; i += 512) {
+            const double x0 = x[i], x1 = x[i + 256];
+            double v0[GT_COLS], v1[GT_COLS];
+#pragma unroll
+            for (int g = 0; g < GT_COLS; ++g) { v0[g] = col[g][i]; v1[g] = col[g][i + 256]; }
+#pragma unroll
+            for (int g = 0; g < GT_COLS; ++g) acc[g] += v0[g] * x0 + v1[g] * x1;
+        }
+        for (; i < r1; i += 256) {
+            const double x0 = x[i];
+#pragma unroll
+            for (int g = 0; g < GT_COLS; ++g) acc[g] += col[g][i] * x0;
+        }
+#pragma unroll
+        for (int g = 0; g < GT_COLS; ++g) {
+            double v = warp_sum(acc[g]);
+            if (lane == 0) red[warp][g] = v;
+        }
+        __syncthreads();
+        if (tid < GT_COLS && j0 + tid < n) {
+            double sum = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) sum += red[w][tid];
+            partial[rc + (j0 + tid) * row_chunks] = sum;
         }
         __syncthreads();
     }
@@ -311,7 +371,20 @@ extern "C" int rb_dgemv(rb_ctx *ctx, char trans, int m_, int n_, double alpha, c
             RB_LAUNCHED(ctx);
             return RB_OK;
         }
-        // scalar path (odd lda / unaligned / strided x): one CTA per (row chunk, column)
+        if (incx == 1) { // unit-stride x but unaligned / odd-pitch columns
+            const i64 row_chunks = rb_cdiv(m, GT_RCH), col_groups = rb_cdiv(n, GT_COLS);
+            void *ws;
+            RB_TRY(rb_ws_reserve(ctx, 1, row_chunks * n * 8, &ws));
+            i64 units = row_chunks * col_groups;
+            i64 grid = (i64)ctx->num_sms * 4;
+            if (grid > units) grid = units;
+            rb_gemv_t_cols4_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>(a, lda, m, n, xb, (double *)ws, row_chunks, col_groups);
+            RB_LAUNCHED(ctx);
+            rb_gemv_t_finish_kernel<<<(unsigned)rb_cdiv(n, 256), 256, 0, ctx->stream>>>((const double *)ws, row_chunks, n, alpha, beta, yb, incy);
+            RB_LAUNCHED(ctx);
+            return RB_OK;
+        }
+        // scalar path (strided x): one CTA per (row chunk, column)
         i64 chunks = 1;
         i64 want = (i64)ctx->num_sms * 4;
         if (n < want) chunks = rb_cdiv(want, n);

@@ -32,3 +32,11 @@ for nb, nx, no in ((600, 400, 60), (601, 400, 60)):
     print(f"ao2mo nb={nb} nx={nx}: {4.0 * nb ** 3 * nx / ms / 1e9:.2f} TFLOP/s", flush=True)
     ms = best_ms(lambda: sh.k(ct, no, out=k))
     print(f"K     nb={nb} nx={nx}: {(2.0 * nb * nb * no + nb * (nb + 1.0) * no) * nx / ms / 1e9:.2f} TFLOP/s", flush=True)
+for nb, nx in ((600, 400), (601, 400)):
+    sh = ShardedRI(ctx, nb, nx).fill_synthetic()
+    dm = ctx.empty(nb * nb); ctx.fill_linear(dm, nb * nb, 5, 0, 1.0)
+    d = ctx.empty(nx); j = ctx.empty(nb * nb)
+    ms = best_ms(lambda: sh.dp(dm, out=d), reps=5)
+    print(f"d_P nb={nb}: {nb * nb * nx * 8 / ms / 1e6:.0f} GB/s", flush=True)
+    ms = best_ms(lambda: sh.j(d, out=j), reps=5)
+    print(f"J   nb={nb}: {nb * nb * nx * 8 / ms / 1e6:.0f} GB/s", flush=True)
