@@ -151,6 +151,10 @@ int rb_host_axpy(int op, double *c, const double *p, double a, double b, int64_t
 /* einsum helpers on host buffers: which = 1 "ij,j->ij" (a [ni,nj], b [nj], out [ni,nj]); 2 "ip,ip->p" (a, b [ni,nj],
  * out [nj]); 3 "i,j->ij" (a [ni], b [nj], out [ni,nj]).  Dense column-major operands (lda = ldb = ni). */
 int rb_host_einsum(int which, const double *a, const double *b, double *out, int64_t ni, int64_t nj);
+/* (ia|jb)-type blocks from dense host tensors moA[np, nl_a, nr_a], moB[np, nl_b, nr_b] (moB may alias moA); out is the
+ * dense [lla*rla, llb*rlb] block, overwritten.  See rb_ri_iajb. */
+int rb_host_ri_iajb(int np, const double *mo_a, int nl_a, int nr_a, int l0a, int lla, int r0a, int rla,
+                    const double *mo_b, int nl_b, int nr_b, int l0b, int llb, int r0b, int rlb, double *out);
 /* d_P, J, K with host buffers (composed by REST from _dgemv/_dgemm/_dsyrk) */
 int rb_host_ri_dp(const double *ri3ao, const double *dm, double *d, int nb, int nx);
 int rb_host_ri_j(const double *ri3ao, const double *d, double *j, int nb, int nx);
@@ -185,6 +189,14 @@ int rb_ri_k(rb_ctx *ctx, const double *ri3ao, const double *ct, int no, double *
 /* in-place slab x matrix of restmatr.f90:111-154 on device buffers */
 int rb_special_dgemm_01(rb_ctx *ctx, double *ten3, int x_a, int y_a, int z_a, int start_x, int len_x, int start_z,
                         int len_z, const double *b, int64_t ldb, int len_col_b, double alpha, double beta);
+
+/* (ia|jb)-type consumers of ri3mo (the P-fastest layout of src/ri.rs:381-386 exists for them):
+ *   out[(l-l0a) + (r-r0a)*lla + ((l'-l0b) + (r'-r0b)*llb)*ldo] = beta*out + sum_{P<np} moA[P,l,r] * moB[P,l',r']
+ * with mo[P + l*ldp + r*ldp*nl].  moA == moB with identical boxes runs as SYRK (both triangles written).  One rank's
+ * partial sum over its local P rows; all-reduce `out` across P-sharded ranks. */
+int rb_ri_iajb(rb_ctx *ctx, int np, const double *mo_a, int64_t ldp_a, int nl_a, int nr_a, int l0a, int lla, int r0a,
+               int rla, const double *mo_b, int64_t ldp_b, int nl_b, int nr_b, int l0b, int llb, int r0b, int rlb,
+               double beta, double *out, int64_t ldo);
 
 /* einsum helpers (matrix_blas_lapack.rs:1273-1387, matrix/einsum.rs) on device buffers:
  * "ij,j->ij" and "i,j->ij" are one multiply per element (bit-exact), "ip,ip->p" is a column dot (1e-10). */

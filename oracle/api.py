@@ -92,6 +92,7 @@ class Oracle:
         L.orc_ri_dp.argtypes = [_vp, _vp, _vp, _i, _i]
         L.orc_ri_j.argtypes = [_vp, _vp, _vp, _i, _i]
         L.orc_ri_k.argtypes = [_vp, _vp, _vp, _i, _i, _i]
+        L.orc_ri_iajb.argtypes = [_i, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp]
         for name in ("orc_einsum_01", "orc_einsum_02", "orc_einsum_03"):
             getattr(L, name).argtypes = [_vp, _vp, _vp, _i64, _i64]
             getattr(L, name).restype = None
@@ -162,6 +163,12 @@ class Oracle:
         k = np.empty(nb * nb, dtype=np.float64)
         self.lib.orc_ri_k(ri3ao.ctypes.data, ct.ctypes.data, k.ctypes.data, nb, no, nx)
         return k
+
+    def ri_iajb(self, np_, mo_a, nl_a, box_a, mo_b, nl_b, box_b) -> np.ndarray:
+        """box = (l0, ll, r0, rl); returns the dense column-major [ll_a*rl_a, ll_b*rl_b] block, flattened"""
+        out = np.zeros(box_a[1] * box_a[3] * box_b[1] * box_b[3], dtype=np.float64)
+        self.lib.orc_ri_iajb(np_, mo_a.ctypes.data, nl_a, *box_a, mo_b.ctypes.data, nl_b, *box_b, out.ctypes.data)
+        return out
 
     # -- einsum helpers (matrix_blas_lapack.rs:1273-1387) --
     def einsum_01(self, a, b, ni, nj) -> np.ndarray:

@@ -18,6 +18,8 @@
  *   index2d               src/index.rs:209-233
  *   axpy family           src/matrix/mod.rs:545-648, src/ri.rs:345-354, src/matrix/matrixupper.rs:395-420
  *   _dgemv/_dgemm_full/_dsyrk/_dsymm argument conventions  src/matrix/matrix_blas_lapack.rs:38-70,180-252,354-413
+ *   (ia|jb) blocks        NOT in the reference crate: dgemm('T','N') over P on the ri3mo layout
+ *                         of src/ri.rs:381-386.
  *   d_P / J / K           NOT in the reference crate: composed per SURVEY §3.5 from the
  *                         primitives above (dgemv 'T', dgemv 'N', per-slab dgemm + dsyrk).
  *
@@ -538,6 +540,34 @@ void orc_ri_k(const double *ri3ao, const double *ct, double *k, int nb, int no, 
     for (i64 j = 0; j < nb; ++j)
         for (i64 i = j + 1; i < nb; ++i) k[i + j * nb] = k[j + i * nb];
     free(bp);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * (ia|jb)-type consumers of ri3mo (no function in the reference crate -- REST's RPA/MP2 code
+ * contracts the P-fastest ri3mo of src/ri.rs:381-386 over P with _dgemm('T','N') / _dsyrk on column blocks).
+ * out[(l-l0a) + (r-r0a)*lla, (l'-l0b) + (r'-r0b)*llb] = sum_P moA[P,l,r] * moB[P,l',r'],  mo[P + l*np + r*np*nl].
+ * The boxes are gathered into dense [np, cols] panels and contracted with one dgemm('T','N').
+ * ---------------------------------------------------------------------------------------------- */
+static double *gather_box(const double *mo, i64 np, i64 nl, i64 l0, i64 ll, i64 r0, i64 rl)
+{
+    i64 cols = ll * rl;
+    double *g = (double *)malloc(sizeof(double) * (size_t)(np * cols > 0 ? np * cols : 1));
+    for (i64 r = 0; r < rl; ++r)
+        for (i64 l = 0; l < ll; ++l)
+            memcpy(g + (l + r * ll) * np, mo + (l0 + l) * np + (r0 + r) * np * nl, sizeof(double) * (size_t)np);
+    return g;
+}
+
+void orc_ri_iajb(int np, const double *mo_a, int nl_a, int l0a, int lla, int r0a, int rla, const double *mo_b, int nl_b,
+                 int l0b, int llb, int r0b, int rlb, double *out)
+{
+    int m = lla * rla, n = llb * rlb;
+    if (m == 0 || n == 0) return;
+    double *ga = gather_box(mo_a, np, nl_a, l0a, lla, r0a, rla);
+    double *gb = gather_box(mo_b, np, nl_b, l0b, llb, r0b, rlb);
+    orc_dgemm('T', 'N', m, n, np, 1.0, ga, np > 1 ? np : 1, gb, np > 1 ? np : 1, 0.0, out, m);
+    free(ga);
+    free(gb);
 }
 
 /* ------------------------------------------------------------------------------------------------

@@ -1016,3 +1016,33 @@ extern "C" int rb_host_ri_k(const double *ri3ao, const double *ct, int no, doubl
     RB_TRY(op.down(k, dk, n2));
     return op.sync();
 }
+
+// (ia|jb)-type blocks of dense host tensors moA[np, nl_a, nr_a], moB[np, nl_b, nr_b] (moB may be
+// moA): only the r-ranges the two boxes touch are uploaded (each is one contiguous block of a P-fastest tensor);
+// out is the dense [lla*rla, llb*rlb] block.
+extern "C" int rb_host_ri_iajb(int np, const double *mo_a, int nl_a, int nr_a, int l0a, int lla, int r0a, int rla,
+                               const double *mo_b, int nl_b, int nr_b, int l0b, int llb, int r0b, int rlb, double *out)
+{
+    RB_REQUIRE(np >= 0 && nl_a >= 0 && nr_a >= 0 && nl_b >= 0 && nr_b >= 0, "rb_host_ri_iajb: negative dimension");
+    RB_REQUIRE(l0a >= 0 && lla >= 0 && l0a + (i64)lla <= nl_a && r0a >= 0 && rla >= 0 && r0a + (i64)rla <= nr_a &&
+                   l0b >= 0 && llb >= 0 && l0b + (i64)llb <= nl_b && r0b >= 0 && rlb >= 0 && r0b + (i64)rlb <= nr_b,
+               "rb_host_ri_iajb: box outside the tensor");
+    const i64 m = (i64)lla * rla, n = (i64)llb * rlb;
+    if (m == 0 || n == 0) return RB_OK;
+    RB_REQUIRE(out && (np == 0 || (mo_a && mo_b)), "rb_host_ri_iajb: NULL buffer");
+    HOST_CTX(op);
+    const i64 plane_a = (i64)np * nl_a, plane_b = (i64)np * nl_b;
+    const bool same = mo_a == mo_b && nl_a == nl_b && r0a == r0b && rla == rlb; // one upload serves both sides
+    double *da, *db, *dout;
+    RB_TRY(op.alloc(plane_a * rla, &da));
+    RB_TRY(op.up(da, mo_a + plane_a * r0a, plane_a * rla));
+    if (same) db = da;
+    else {
+        RB_TRY(op.alloc(plane_b * rlb, &db));
+        RB_TRY(op.up(db, mo_b + plane_b * r0b, plane_b * rlb));
+    }
+    RB_TRY(op.alloc(m * n, &dout));
+    RB_TRY(rb_ri_iajb(op.ctx, np, da, np, nl_a, rla, l0a, lla, 0, rla, db, np, nl_b, rlb, l0b, llb, 0, rlb, 0.0, dout, m));
+    RB_TRY(op.down(out, dout, m * n));
+    return op.sync();
+}

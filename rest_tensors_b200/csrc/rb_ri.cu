@@ -302,3 +302,73 @@ extern "C" int rb_special_dgemm_01(rb_ctx *ctx, double *ten3, int x_a, int y_a, 
     }
     return RB_OK;
 }
+
+// ---- (ia|jb)-type consumers of ri3mo -------------------------------------------------------
+// ri3mo is P-fastest, mo[P + l*ldp + r*ldp*nl] (reference src/ri.rs:381-386): a box of MO pairs (l in [l0,l0+ll),
+// r in [r0,r0+rl)) is a set of length-np columns, so
+//     out[(l,r)_A, (l',r')_B] (+)= sum_P moA[P,l,r] * moB[P,l',r']
+// is ONE 'T','N' DMMA GEMM with K = np and both operands K-major (the layout ao2mo writes is already the layout this
+// GEMM reads; no transposition anywhere).  A box that spans the whole l range is a contiguous column block of mo and
+// is read in place; a partial l range is gathered once into a dense workspace panel (one HBM pass, <= 1/M of the
+// GEMM's work).  Same tensor and same box on both sides: SYRK (upper-triangle tiles only) + mirror.  moA != moB covers
+// the alpha/beta spin blocks.  P-sharded ranks each produce a partial sum over their local rows; the caller all-reduces.
+struct MoBox { const double *mo; i64 ldp, nl, nr, l0, ll, r0, rl; };
+
+static bool box_is_panel(const MoBox &x) { return x.l0 == 0 && x.ll == x.nl; }
+static bool box_valid(const MoBox &x)
+{
+    return x.nl >= 0 && x.nr >= 0 && x.l0 >= 0 && x.ll >= 0 && x.l0 + x.ll <= x.nl && x.r0 >= 0 && x.rl >= 0 && x.r0 + x.rl <= x.nr;
+}
+
+extern "C" int rb_ri_iajb(rb_ctx *ctx, int np_, const double *mo_a, int64_t ldp_a, int nl_a, int nr_a, int l0a, int lla,
+                          int r0a, int rla, const double *mo_b, int64_t ldp_b, int nl_b, int nr_b, int l0b, int llb,
+                          int r0b, int rlb, double beta, double *out, int64_t ldo)
+{
+    RB_REQUIRE(ctx, "rb_ri_iajb: ctx is NULL");
+    RB_REQUIRE(np_ >= 0, "rb_ri_iajb: negative dimension");
+    const MoBox A = {mo_a, ldp_a, nl_a, nr_a, l0a, lla, r0a, rla}, B = {mo_b, ldp_b, nl_b, nr_b, l0b, llb, r0b, rlb};
+    RB_REQUIRE(box_valid(A), "rb_ri_iajb: box A [%d+%d, %d+%d] outside [%d, %d]", l0a, lla, r0a, rla, nl_a, nr_a);
+    RB_REQUIRE(box_valid(B), "rb_ri_iajb: box B [%d+%d, %d+%d] outside [%d, %d]", l0b, llb, r0b, rlb, nl_b, nr_b);
+    RB_REQUIRE(ldp_a >= np_ && ldp_b >= np_, "rb_ri_iajb: ldp (%lld, %lld) < np (%d)", (long long)ldp_a, (long long)ldp_b, np_);
+    const i64 np = np_, m = A.ll * A.rl, n = B.ll * B.rl;
+    if (m == 0 || n == 0) return RB_OK;
+    RB_REQUIRE(out, "rb_ri_iajb: out is NULL");
+    RB_REQUIRE(ldo >= m, "rb_ri_iajb: ldo (%lld) < rows of the block (%lld)", (long long)ldo, (long long)m);
+    RB_CUDA(cudaSetDevice(ctx->device));
+    if (np == 0) // empty contraction: out = beta * out
+        return rb_gemm_core(ctx, true, false, m, n, 0, 1.0, nullptr, 1, 0, nullptr, 1, 0, beta, out, ldo, 0, 1, 0);
+    RB_REQUIRE(mo_a && mo_b, "rb_ri_iajb: mo is NULL");
+    const double *xa = mo_a + A.l0 * A.ldp + A.r0 * A.ldp * A.nl, *xb = mo_b + B.l0 * B.ldp + B.r0 * B.ldp * B.nl;
+    const bool same = xa == xb && A.ldp == B.ldp && A.nl == B.nl && A.ll == B.ll && A.rl == B.rl;
+    const int tri = same ? 1 : 0;
+    const bool pa = box_is_panel(A), pb = same ? pa : box_is_panel(B);
+    if (pa && pb) { // both boxes are column panels of mo: read in place
+        RB_TRY(rb_gemm_core(ctx, true, false, m, n, np, 1.0, xa, A.ldp, 0, xb, B.ldp, 0, beta, out, ldo, 0, 1, tri));
+        return same ? rb_symmetrize(ctx, out, m, ldo, true) : RB_OK;
+    }
+    // gather the non-panel boxes, P-chunked so the panels fit the workspace budget (chunks accumulate with beta = 1)
+    const i64 cols = (pa ? 0 : m) + ((pb || same) ? 0 : n);
+    i64 pc = (ws_budget_bytes(ctx) / (cols * 8)) & ~(i64)7;
+    if (pc < 8) pc = 8;
+    if (pc > np) pc = np;
+    const i64 ldx = pc + (pc & 1); // even pitch: the TMA path needs 16-byte aligned columns
+    void *ws;
+    RB_TRY(rb_ws_reserve(ctx, 0, ldx * cols * 8, &ws));
+    double *ga = (double *)ws, *gb = pa ? ga : ga + ldx * m;
+    for (i64 p0 = 0; p0 < np; p0 += pc) {
+        const i64 pn = (np - p0 < pc) ? np - p0 : pc;
+        const double *a = xa + p0, *b = xb + p0;
+        i64 lda = A.ldp, ldb = B.ldp;
+        if (!pa) {
+            RB_TRY(rb_copy3d(ctx, xa + p0, 0, 1, A.ldp, A.ldp * A.nl, ga, 0, 1, ldx, ldx * A.ll, pn, A.ll, A.rl));
+            a = ga; lda = ldx;
+        }
+        if (same) { b = a; ldb = lda; }
+        else if (!pb) {
+            RB_TRY(rb_copy3d(ctx, xb + p0, 0, 1, B.ldp, B.ldp * B.nl, gb, 0, 1, ldx, ldx * B.ll, pn, B.ll, B.rl));
+            b = gb; ldb = ldx;
+        }
+        RB_TRY(rb_gemm_core(ctx, true, false, m, n, pn, 1.0, a, lda, 0, b, ldb, 0, p0 == 0 ? beta : 1.0, out, ldo, 0, 1, tri));
+    }
+    return same ? rb_symmetrize(ctx, out, m, ldo, true) : RB_OK;
+}

@@ -104,6 +104,11 @@ class Context:
     def ri_k(self, ri3ao, ct, no, k, nb, nx) -> None:
         check(lib.rb_ri_k(self.h, _p(ri3ao), _p(ct), no, _p(k), nb, nx), "rb_ri_k")
 
+    def ri_iajb(self, np_, mo_a, ldp_a, nl_a, nr_a, box_a, mo_b, ldp_b, nl_b, nr_b, box_b, beta, out, ldo) -> None:
+        """box = (l0, ll, r0, rl)"""
+        check(lib.rb_ri_iajb(self.h, np_, _p(mo_a), ldp_a, nl_a, nr_a, *box_a, _p(mo_b), ldp_b, nl_b, nr_b, *box_b, beta,
+                             _p(out), ldo), "rb_ri_iajb")
+
     def special_dgemm_01(self, ten3, x_a, y_a, z_a, sx, lx, sz, lz, b, ldb, lcb, alpha, beta) -> None:
         check(lib.rb_special_dgemm_01(self.h, _p(ten3), x_a, y_a, z_a, sx, lx, sz, lz, _p(b), ldb, lcb, alpha, beta),
               "rb_special_dgemm_01")
@@ -218,6 +223,21 @@ class ShardedRI:
         if out is None:
             out = self.ctx.empty(self.nb * self.nb)
         self.ctx.ri_k(self.data, ct, no, out, self.nb, self.nx)
+        if reduce:
+            all_reduce_sum(out, self.world)
+        return out
+
+    def iajb(self, mo: torch.Tensor, nl: int, nr: int, box_a, box_b, mo_b: Optional[torch.Tensor] = None,
+             nl_b: Optional[int] = None, nr_b: Optional[int] = None, out: Optional[torch.Tensor] = None,
+             reduce: bool = True) -> torch.Tensor:
+        """(ia|jb)-type block from this rank's rows of ri3mo (the dense [nx_local, nl, nr] buffer ao2mo returned): a
+        partial sum over the local P, completed by ONE all-reduce like J and K.  box = (l0, ll, r0, rl)."""
+        if mo_b is None:
+            mo_b, nl_b, nr_b = mo, nl, nr
+        m, n = box_a[1] * box_a[3], box_b[1] * box_b[3]
+        if out is None:
+            out = self.ctx.empty(m * n)
+        self.ctx.ri_iajb(self.nx, mo, self.nx, nl, nr, box_a, mo_b, self.nx, nl_b, nr_b, box_b, 0.0, out, m)
         if reduce:
             all_reduce_sum(out, self.world)
         return out

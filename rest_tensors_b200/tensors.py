@@ -602,6 +602,26 @@ class RIFull:
         return k
 
 
+    # -- (ia|jb)-type consumers of a P-fastest MO tensor --
+    def ri_iajb(self, range_l_a: Range, range_r_a: Range, range_l_b: Range, range_r_b: Range,
+                other: Optional["RIFull"] = None) -> MatrixFull:
+        """self = ri3mo[P, l, r] (the output layout of ao2mo, src/ri.rs:381-386), other = a second such tensor (alpha /
+        beta spin blocks; default self).  Returns the [|l_a||r_a|, |l_b||r_b|] matrix
+        sum_P self[P,l,r] * other[P,l',r'] with row index (l - l0) + (r - r0)*|l| -- REST's (ia|jb) blocks."""
+        b = self if other is None else other
+        if b.size[0] != self.size[0]:
+            raise RestB200Error("ri_iajb: the two MO tensors have different auxiliary dimensions")
+        for t, (rl_, rr_) in ((self, (range_l_a, range_r_a)), (b, (range_l_b, range_r_b))):
+            if not (0 <= rl_[0] <= rl_[1] <= t.size[1] and 0 <= rr_[0] <= rr_[1] <= t.size[2]):
+                raise RestB200Error("ri_iajb: box outside the tensor")  # the Rust slicing would panic
+        m, n = _rlen(range_l_a) * _rlen(range_r_a), _rlen(range_l_b) * _rlen(range_r_b)
+        out = MatrixFull.new([m, n], 0.0)
+        check(lib.rb_host_ri_iajb(self.size[0], _ptr(self.data), self.size[1], self.size[2], range_l_a[0],
+                                  _rlen(range_l_a), range_r_a[0], _rlen(range_r_a), _ptr(b.data), b.size[1], b.size[2],
+                                  range_l_b[0], _rlen(range_l_b), range_r_b[0], _rlen(range_r_b), _ptr(out.data)),
+              "ri_iajb")
+        return out
+
 # ======================================================================================================
 # views and index maps
 # ======================================================================================================

@@ -1,7 +1,7 @@
 """world_size-2 gloo test of the multi-GPU host logic on CPU: the P-shard partition (shard_range ==
 iter_auxbas(P_lo..P_hi), reference src/ri.rs:190-198) plus ONE all-reduce(sum) of the J and K partials reproduces the
-unsharded result; ao2mo and d_P need no communication.  The per-rank partials come from the CPU oracle here (there is
-no GPU in this tier); the GPU tier runs the same flow with the CUDA kernels (tests/test_gpu_dist.py, bench.py --gpus N)."""
+unsharded result (likewise the (ia|jb) blocks built from the local rows of ri3mo); ao2mo and d_P need no
+communication.  The per-rank partials come from the CPU oracle here (there is no GPU in this tier); the GPU tier runs the same flow with the CUDA kernels (tests/test_gpu_dist.py, bench.py --gpus N)."""
 import os
 import sys
 
@@ -36,6 +36,10 @@ def _worker(rank, world, port, nb, naux, no, ret):
         all_reduce_sum(j, world)
         all_reduce_sum(k, world)
         mo_local = o.ri_ao2mo_f(c, ri_local, nb, nb, nx)
+        # (ia|jb) block from the local rows of ri3mo: a partial sum over P, completed by one all-reduce like J and K
+        box_a, box_b = (0, no, no, nb - no), (1, no - 1, no, nb - no)
+        g = torch.from_numpy(o.ri_iajb(nx, mo_local, nb, box_a, mo_local, nb, box_b))
+        all_reduce_sum(g, world)
         # gather the d_P pieces and the P-rows of ri3mo for the check on rank 0
         d_full = gather_dp(torch.from_numpy(d_local), naux, p_lo, world)
         if rank == 0:
@@ -46,6 +50,8 @@ def _worker(rank, world, port, nb, naux, no, ret):
             ok &= np.allclose(k.numpy(), o.ri_k(ri, ct, nb, no, naux), rtol=1e-11, atol=1e-12)
             mo = o.ri_ao2mo_f(c, ri, nb, nb, naux).reshape((naux, nb, nb), order="F")
             ok &= np.array_equal(mo[p_lo:p_hi].reshape(-1, order="F"), mo_local)
+            mo_flat = np.ascontiguousarray(mo.reshape(-1, order="F"))
+            ok &= np.allclose(g.numpy(), o.ri_iajb(naux, mo_flat, nb, box_a, mo_flat, nb, box_b), rtol=1e-11, atol=1e-12)
             ret.put(bool(ok))
         dist.barrier()
     finally:

@@ -1,0 +1,149 @@
+"""GPU parity for the (ia|jb)-type consumers of ri3mo: rb_ri_iajb / rb_host_ri_iajb through the
+C ABI vs the CPU oracle (gather + dgemm('T','N') over P on the ri3mo layout of reference src/ri.rs:381-386).
+Tolerance: 1e-10 relative, norm-wise and element-wise; symmetric blocks must be bitwise symmetric."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_close_1e10
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(ctx, a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(f"cuda:{ctx.device}")
+
+
+CASES = [
+    # np, nl, nr, box A (l0, ll, r0, rl), box B
+    (40, 6, 9, (0, 6, 0, 9), (0, 6, 0, 9)),        # whole tensor, symmetric -> SYRK in place
+    (41, 6, 9, (0, 6, 0, 9), (0, 6, 0, 9)),        # odd np: pitch repack inside the GEMM core
+    (64, 5, 12, (0, 5, 2, 7), (0, 5, 4, 8)),       # two different panels, in place
+    (100, 8, 10, (1, 4, 2, 6), (1, 4, 2, 6)),      # partial l range, symmetric -> gather + SYRK
+    (100, 8, 10, (0, 3, 0, 10), (3, 5, 1, 4)),     # occ/vir style: different partial boxes
+    (333, 16, 24, (2, 9, 3, 17), (0, 16, 5, 11)),  # one gathered, one in place, ragged everything
+    (257, 12, 20, (0, 12, 0, 20), (4, 1, 7, 1)),   # single column on one side
+    (1, 3, 3, (0, 3, 0, 3), (0, 3, 0, 3)),         # np = 1
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_iajb_vs_oracle(ctx, oracle_blas, case):
+    np_, nl, nr, ba, bb = case
+    mo = oracle_blas.fill_linear(np_ * nl * nr, 31)
+    ref = oracle_blas.ri_iajb(np_, mo, nl, ba, mo, nl, bb)
+    m, n = ba[1] * ba[3], bb[1] * bb[3]
+    mod = _dev(ctx, mo)
+    out = ctx.empty(m * n)
+    out.fill_(float("nan"))  # beta = 0 must overwrite, never read
+    ctx.ri_iajb(np_, mod, np_, nl, nr, ba, mod, np_, nl, nr, bb, 0.0, out, m)
+    got = out.cpu().numpy()
+    assert_close_1e10(got, ref, f"iajb {case}")
+    if ba == bb:
+        g = got.reshape((m, m), order="F")
+        assert np.array_equal(g, g.T), "symmetric block is not bitwise symmetric"
+
+
+def test_iajb_beta_ldo_and_padding(ctx, oracle_blas):
+    """beta accumulates, ldo > rows leaves the padding rows untouched, ldp > np reads a pitched (sharded) tensor."""
+    np_, ldp, nl, nr = 70, 96, 7, 11
+    ba, bb = (0, 7, 1, 9), (2, 3, 0, 11)
+    m, n, ldo = ba[1] * ba[3], bb[1] * bb[3], ba[1] * ba[3] + 5
+    full = oracle_blas.fill_linear(ldp * nl * nr, 32)
+    dense = np.ascontiguousarray(full.reshape((ldp, nl, nr), order="F")[:np_].reshape(-1, order="F"))
+    ref = oracle_blas.ri_iajb(np_, dense, nl, ba, dense, nl, bb).reshape((m, n), order="F")
+    c0 = oracle_blas.fill_linear(ldo * n, 33)
+    out = _dev(ctx, c0)
+    fd = _dev(ctx, full)
+    ctx.ri_iajb(np_, fd, ldp, nl, nr, ba, fd, ldp, nl, nr, bb, -0.5, out, ldo)
+    got = out.cpu().numpy().reshape((ldo, n), order="F")
+    c0m = c0.reshape((ldo, n), order="F")
+    assert_close_1e10(got[:m], ref - 0.5 * c0m[:m], "iajb beta/ldo")
+    assert np.array_equal(got[m:], c0m[m:])
+
+
+def test_iajb_two_tensors_alpha_beta_spin(ctx, oracle_blas):
+    """moA != moB (alpha / beta spin blocks with different occupations)."""
+    np_ = 90
+    nla, nra, nlb, nrb = 5, 14, 4, 15
+    a = oracle_blas.fill_linear(np_ * nla * nra, 34)
+    b = oracle_blas.fill_linear(np_ * nlb * nrb, 35)
+    ba, bb = (0, 5, 0, 14), (1, 3, 2, 13)
+    ref = oracle_blas.ri_iajb(np_, a, nla, ba, b, nlb, bb)
+    m = ba[1] * ba[3]
+    out = ctx.empty(m * bb[1] * bb[3])
+    ctx.ri_iajb(np_, _dev(ctx, a), np_, nla, nra, ba, _dev(ctx, b), np_, nlb, nrb, bb, 0.0, out, m)
+    assert_close_1e10(out.cpu().numpy(), ref, "iajb two tensors")
+
+
+def test_iajb_p_shard_additivity(ctx, oracle_blas):
+    """P-shard additivity (the multi-GPU contract): the blocks of two row ranges of ri3mo sum to the block of the whole."""
+    np_, nl, nr = 200, 6, 10
+    ba, bb = (1, 4, 0, 10), (0, 6, 3, 5)
+    mo = oracle_blas.fill_linear(np_ * nl * nr, 36)
+    ref = oracle_blas.ri_iajb(np_, mo, nl, ba, mo, nl, bb)
+    mod = _dev(ctx, mo)
+    m, n = ba[1] * ba[3], bb[1] * bb[3]
+    out = ctx.empty(m * n)
+    split = 87  # odd: the second view is only 8-byte aligned (pitch repack inside the GEMM core)
+    # rows [0, split) then rows [split, np) accumulated with beta = 1, each read through the pitched view ldp = np_
+    ctx.ri_iajb(split, mod, np_, nl, nr, ba, mod, np_, nl, nr, bb, 0.0, out, m)
+    ctx.ri_iajb(np_ - split, mod[split:], np_, nl, nr, ba, mod[split:], np_, nl, nr, bb, 1.0, out, m)
+    assert_close_1e10(out.cpu().numpy(), ref, "iajb P-additivity")
+
+
+def test_iajb_after_ao2mo_occ_vir(ctx, oracle_blas):
+    """The real pipeline: occ-vir ao2mo on the device, then (ia|jb) for an (i, j) block pair straight from its output."""
+    from rest_tensors_b200.device import ShardedRI
+    nb, nx, no = 48, 130, 6
+    nv = nb - no
+    sh = ShardedRI(ctx, nb, nx).fill_synthetic()
+    c = oracle_blas.fill_linear(nb * nb, 3, scale=nb ** -0.5)
+    cm = c.reshape((nb, nb), order="F")
+    cocc = np.ascontiguousarray(cm[:, :no].reshape(-1, order="F"))
+    cvir = np.ascontiguousarray(cm[:, no:].reshape(-1, order="F"))
+    mo = sh.ao2mo(_dev(ctx, cocc), no, _dev(ctx, cvir), nv)      # [nx, no, nv]
+    ri = oracle_blas.fill_ri3ao_symm(nb, 0, nx)
+    mo_ref = oracle_blas.ri_ao2mo_rect(cocc, no, cvir, nv, ri, nb, nx)
+    ba = bb = (0, no, 0, nv)
+    ref = oracle_blas.ri_iajb(nx, mo_ref, no, ba, mo_ref, no, bb)
+    got = sh.iajb(mo, no, nv, ba, bb).cpu().numpy()
+    assert_close_1e10(got, ref, "(ia|jb) after occ-vir ao2mo")
+    # MP2-like scalar from the block: sum_ijab (ia|jb) [2 (ia|jb) - (ib|ja)]
+    g = got.reshape((no, nv, no, nv), order="F"); r = ref.reshape((no, nv, no, nv), order="F")
+    e_got = float(np.sum(g * (2.0 * g - g.transpose(0, 3, 2, 1))))
+    e_ref = float(np.sum(r * (2.0 * r - r.transpose(0, 3, 2, 1))))
+    assert abs(e_got - e_ref) <= 1e-10 * abs(e_ref)
+
+
+def test_host_iajb_mirror(rt, oracle_blas):
+    np_, nl, nr = 75, 6, 9
+    mo = oracle_blas.fill_linear(np_ * nl * nr, 37)
+    t = rt.RIFull.from_vec([np_, nl, nr], mo)
+    for (rla, rra, rlb, rrb) in [((0, 6), (0, 9), (0, 6), (0, 9)), ((1, 4), (2, 8), (0, 6), (3, 5)),
+                                 ((0, 6), (1, 3), (0, 6), (6, 9))]:
+        ba = (rla[0], rla[1] - rla[0], rra[0], rra[1] - rra[0]); bb = (rlb[0], rlb[1] - rlb[0], rrb[0], rrb[1] - rrb[0])
+        ref = oracle_blas.ri_iajb(np_, mo, nl, ba, mo, nl, bb)
+        got = t.ri_iajb(rla, rra, rlb, rrb)
+        assert got.size == [ba[1] * ba[3], bb[1] * bb[3]]
+        assert_close_1e10(got.data, ref, f"host iajb {ba} {bb}")
+    with pytest.raises(rt.RestB200Error):
+        t.ri_iajb((0, 7), (0, 9), (0, 6), (0, 9))
+    # empty boxes are fine and return an empty matrix
+    assert t.ri_iajb((2, 2), (0, 9), (0, 6), (0, 9)).size == [0, 54]
+
+
+def test_iajb_error_codes(ctx):
+    from rest_tensors_b200 import RestB200Error
+    mo = ctx.empty(10 * 3 * 4)
+    out = ctx.empty(144)
+    with pytest.raises(RestB200Error):   # box outside
+        ctx.ri_iajb(10, mo, 10, 3, 4, (0, 4, 0, 4), mo, 10, 3, 4, (0, 3, 0, 4), 0.0, out, 16)
+    with pytest.raises(RestB200Error):   # ldp < np
+        ctx.ri_iajb(10, mo, 9, 3, 4, (0, 3, 0, 4), mo, 10, 3, 4, (0, 3, 0, 4), 0.0, out, 12)
+    with pytest.raises(RestB200Error):   # ldo < rows
+        ctx.ri_iajb(10, mo, 10, 3, 4, (0, 3, 0, 4), mo, 10, 3, 4, (0, 3, 0, 4), 0.0, out, 11)
+    # the context is still usable afterwards
+    mo.fill_(1.0)
+    ctx.ri_iajb(10, mo, 10, 3, 4, (0, 3, 0, 4), mo, 10, 3, 4, (0, 3, 0, 4), 0.0, out, 12)
+    assert torch.all(out == 10.0)

@@ -147,3 +147,21 @@ def test_einsum_helpers_oracle(oracle):
     assert np.array_equal(oracle.einsum_01(mc, b, ni, nj).reshape((ni, nj), order="F"), m * b[None, :])
     assert np.array_equal(oracle.einsum_03(v, b, ni, nj).reshape((ni, nj), order="F"), np.outer(v, b))
     assert np.allclose(oracle.einsum_02(mc, mc, ni, nj), np.einsum("ip,ip->p", m, m), rtol=1e-14)
+
+
+def test_oracle_iajb_vs_numpy_einsum(oracle):
+    """(ia|jb) blocks of the oracle against an independent numpy einsum over the ri3mo layout [P, l, r] (P fastest)."""
+    np_, nl, nr = 23, 5, 7
+    mo = oracle.fill_linear(np_ * nl * nr, 41)
+    other = oracle.fill_linear(np_ * 4 * 6, 42)
+    t = mo.reshape((np_, nl, nr), order="F"); u = other.reshape((np_, 4, 6), order="F")
+    for (ba, bb, tb, nlb) in [((0, 5, 0, 7), (0, 5, 0, 7), t, nl), ((1, 3, 2, 4), (0, 5, 1, 6), t, nl),
+                              ((2, 1, 6, 1), (0, 4, 0, 6), u, 4), ((0, 0, 0, 7), (0, 5, 0, 7), t, nl)]:
+        xa = t[:, ba[0]:ba[0] + ba[1], ba[2]:ba[2] + ba[3]]
+        xb = tb[:, bb[0]:bb[0] + bb[1], bb[2]:bb[2] + bb[3]]
+        ref = np.einsum("pia,pjb->iajb", xa, xb).reshape(-1, order="F")
+        flat_b = np.ascontiguousarray(tb.reshape(-1, order="F"))
+        got = oracle.ri_iajb(np_, mo, nl, ba, flat_b, nlb, bb)
+        assert got.shape == ref.shape
+        if ref.size:
+            assert np.max(np.abs(got - ref)) <= 1e-13 * max(1.0, np.max(np.abs(ref)))
