@@ -404,6 +404,34 @@ def run_ours(args):
     ov_flop = (2.0 * no * nb * nb + 2.0 * no * nb * nv) * nx
     occ_vir = {"ms": min(ov_ms), "tflops_per_gpu": ov_flop / (min(ov_ms) * 1e-3) / 1e12,
                "note": "ao2mo with C_left = C_occ [nb,nocc], C_right = C_vir [nb,nb-nocc]; best of 3, per rank"}
+    # ---- extra: the step after ao2mo -- (ia|jb) blocks straight from the occ-vir ri3mo above:
+    #      diagonal block pair (i-block == j-block; SYRK, M(M+1)K flop) and an off-diagonal pair (GEMM, 2MNK flop);
+    #      the i-block is as many occupied orbitals as keep the [M, M] block under 6 GB ----
+    iajb = None
+    try:
+        li = max(1, min(no // 2 if no >= 2 else 1, int(((6 << 30) / 8) ** 0.5) // max(nv, 1)))
+        if (6 << 30) / 8 >= float(no * nv) ** 2:
+            li = no
+        m_blk = li * nv
+        g = ctx.empty(m_blk * m_blk)
+        res = {}
+        pairs = [("diag", (0, li, 0, nv), (0, li, 0, nv), float(m_blk) * (m_blk + 1) * nx)]
+        if 2 * li <= no:
+            pairs.append(("offdiag", (0, li, 0, nv), (li, li, 0, nv), 2.0 * m_blk * m_blk * nx))
+        for name, ba, bb, fl in pairs:
+            best = None
+            for it in range(3):
+                a0, a1 = ev(), ev()
+                a0.record(); sh.iajb(ov, no, nv, ba, bb, out=g, reduce=False); a1.record()
+                torch.cuda.synchronize()
+                if it:
+                    best = a0.elapsed_time(a1) if best is None else min(best, a0.elapsed_time(a1))
+            res[name] = {"ms": best, "tflops_per_gpu": fl / (best * 1e-3) / 1e12}
+        iajb = {"occ_block": li, "rows": m_blk, "k": nx, **res,
+                "note": "rb_ri_iajb on this rank's rows of the occ-vir ri3mo (partial sum; all-reduce not timed); best of 2"}
+        del g
+    except Exception as exc:  # noqa: BLE001
+        iajb = {"error": f"{type(exc).__name__}: {exc}"[:200]}
     del ov
 
     # ---- e2e through the host-pointer C ABI (pinned host buffers; H2D + D2H inside the timed region) ----
@@ -464,6 +492,7 @@ def run_ours(args):
                          "j_achieved": nx * n2 * 8 / (avg["j"] * 1e-3) / 1e9},
         "e2e": e2e,
         "ao2mo_occ_vir": occ_vir,
+        "iajb_occ_vir": iajb,
         "gpu_launches": int(launches),
         "clocks": clocks,
     }

@@ -155,6 +155,9 @@ int rb_host_einsum(int which, const double *a, const double *b, double *out, int
  * dense [lla*rla, llb*rlb] block, overwritten.  See rb_ri_iajb. */
 int rb_host_ri_iajb(int np, const double *mo_a, int nl_a, int nr_a, int l0a, int lla, int r0a, int rla,
                     const double *mo_b, int nl_b, int nr_b, int l0b, int llb, int r0b, int rlb, double *out);
+/* RPA-type consumer from a dense host ri3mo[np, nl, nr]; out is the dense symmetric [np, np] matrix.  See rb_ri_mo_pq. */
+int rb_host_ri_mo_pq(const double *mo, int np, int nl, int nr, int l0, int ll, int r0, int rl, const double *w,
+                     double *out);
 /* d_P, J, K with host buffers (composed by REST from _dgemv/_dgemm/_dsyrk) */
 int rb_host_ri_dp(const double *ri3ao, const double *dm, double *d, int nb, int nx);
 int rb_host_ri_j(const double *ri3ao, const double *d, double *j, int nb, int nx);
@@ -197,6 +200,13 @@ int rb_special_dgemm_01(rb_ctx *ctx, double *ten3, int x_a, int y_a, int z_a, in
 int rb_ri_iajb(rb_ctx *ctx, int np, const double *mo_a, int64_t ldp_a, int nl_a, int nr_a, int l0a, int lla, int r0a,
                int rla, const double *mo_b, int64_t ldp_b, int nl_b, int nr_b, int l0b, int llb, int r0b, int rlb,
                double beta, double *out, int64_t ldo);
+
+/* RPA-type consumer of ri3mo: contraction over the MO pairs of a box, output in the auxiliary basis,
+ *   out[P + Q*ldo] = beta*out + sum_{(l,r) in box} w[(l-l0) + (r-r0)*ll] * moA[P,l,r] * moB[Q,l,r]      (w NULL: ones)
+ * moA (np_a rows, pitch ldp_a) and moB (np_b rows, pitch ldp_b) are row blocks (P-shards) of [.., nl, nr] tensors;
+ * moA == moB is computed as the upper triangle + mirror.  'N','T' DMMA GEMM with K = ll*rl. */
+int rb_ri_mo_pq(rb_ctx *ctx, const double *mo_a, int64_t ldp_a, int np_a, const double *mo_b, int64_t ldp_b, int np_b,
+                int nl, int nr, int l0, int ll, int r0, int rl, const double *w, double beta, double *out, int64_t ldo);
 
 /* einsum helpers (matrix_blas_lapack.rs:1273-1387, matrix/einsum.rs) on device buffers:
  * "ij,j->ij" and "i,j->ij" are one multiply per element (bit-exact), "ip,ip->p" is a column dot (1e-10). */

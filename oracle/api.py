@@ -92,6 +92,7 @@ class Oracle:
         L.orc_ri_dp.argtypes = [_vp, _vp, _vp, _i, _i]
         L.orc_ri_j.argtypes = [_vp, _vp, _vp, _i, _i]
         L.orc_ri_k.argtypes = [_vp, _vp, _vp, _i, _i, _i]
+        L.orc_ri_mo_pq.argtypes = [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]
         L.orc_ri_iajb.argtypes = [_i, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp]
         for name in ("orc_einsum_01", "orc_einsum_02", "orc_einsum_03"):
             getattr(L, name).argtypes = [_vp, _vp, _vp, _i64, _i64]
@@ -168,6 +169,13 @@ class Oracle:
         """box = (l0, ll, r0, rl); returns the dense column-major [ll_a*rl_a, ll_b*rl_b] block, flattened"""
         out = np.zeros(box_a[1] * box_a[3] * box_b[1] * box_b[3], dtype=np.float64)
         self.lib.orc_ri_iajb(np_, mo_a.ctypes.data, nl_a, *box_a, mo_b.ctypes.data, nl_b, *box_b, out.ctypes.data)
+        return out
+
+    def ri_mo_pq(self, mo_a, npa, mo_b, npb, nl, box, w=None) -> np.ndarray:
+        """box = (l0, ll, r0, rl); w = weights over the box's (l, r) pairs or None; returns [npa, npb] flattened"""
+        out = np.zeros(npa * npb, dtype=np.float64)
+        self.lib.orc_ri_mo_pq(mo_a.ctypes.data, npa, mo_b.ctypes.data, npb, nl, *box,
+                              None if w is None else w.ctypes.data, out.ctypes.data)
         return out
 
     # -- einsum helpers (matrix_blas_lapack.rs:1273-1387) --

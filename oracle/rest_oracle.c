@@ -570,6 +570,25 @@ void orc_ri_iajb(int np, const double *mo_a, int nl_a, int l0a, int lla, int r0a
     free(gb);
 }
 
+/* RPA-type consumer: out[P,Q] = sum_{(l,r) in box} w[l,r] * moA[P,l,r] * moB[Q,l,r]  (w NULL: ones); moA [npa, nl, nr],
+ * moB [npb, nl, nr] dense.  REST forms it as _dgemm('N','T') on the [naux, pairs] view with the weights folded into one
+ * side (the "ij,j->ij" helper, matrix_blas_lapack.rs:1275-1290); restated the same way. */
+void orc_ri_mo_pq(const double *mo_a, int npa, const double *mo_b, int npb, int nl, int l0, int ll, int r0, int rl,
+                  const double *w, double *out)
+{
+    int cols = ll * rl;
+    if (npa == 0 || npb == 0) return;
+    if (cols == 0) { memset(out, 0, sizeof(double) * (size_t)npa * (size_t)npb); return; }
+    double *ga = gather_box(mo_a, npa, nl, l0, ll, r0, rl);
+    double *gb = gather_box(mo_b, npb, nl, l0, ll, r0, rl);
+    if (w)
+        for (i64 c = 0; c < cols; ++c)
+            for (i64 q = 0; q < npb; ++q) gb[q + c * npb] = gb[q + c * npb] * w[c];
+    orc_dgemm('N', 'T', npa, npb, cols, 1.0, ga, npa, gb, npb, 0.0, out, npa);
+    free(ga);
+    free(gb);
+}
+
 /* ------------------------------------------------------------------------------------------------
  * einsum helpers (src/matrix/matrix_blas_lapack.rs:1273-1387, src/matrix/einsum.rs:17-79): the serial forms.
  * ---------------------------------------------------------------------------------------------- */

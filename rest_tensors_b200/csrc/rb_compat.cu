@@ -1046,3 +1046,29 @@ extern "C" int rb_host_ri_iajb(int np, const double *mo_a, int nl_a, int nr_a, i
     RB_TRY(op.down(out, dout, m * n));
     return op.sync();
 }
+
+// RPA-type consumer on a dense host ri3mo[np, nl, nr]: out[P,Q] = sum_{(l,r) in box} w[l,r] mo[P,l,r] mo[Q,l,r]
+// (w == NULL: all ones); out is the dense symmetric [np, np] matrix, overwritten.  Only the box's r-range is uploaded.
+extern "C" int rb_host_ri_mo_pq(const double *mo, int np, int nl, int nr, int l0, int ll, int r0, int rl, const double *w,
+                                double *out)
+{
+    RB_REQUIRE(np >= 0 && nl >= 0 && nr >= 0, "rb_host_ri_mo_pq: negative dimension");
+    RB_REQUIRE(l0 >= 0 && ll >= 0 && l0 + (i64)ll <= nl && r0 >= 0 && rl >= 0 && r0 + (i64)rl <= nr,
+               "rb_host_ri_mo_pq: box outside the tensor");
+    if (np == 0) return RB_OK;
+    RB_REQUIRE(out, "rb_host_ri_mo_pq: out is NULL");
+    const i64 plane = (i64)np * nl, cols = (i64)ll * rl;
+    RB_REQUIRE(cols == 0 || mo, "rb_host_ri_mo_pq: mo is NULL");
+    HOST_CTX(op);
+    double *dm = nullptr, *dw = nullptr, *dout;
+    RB_TRY(op.alloc(plane * rl, &dm));
+    RB_TRY(op.up(dm, mo + plane * r0, plane * rl));
+    if (w && cols > 0) {
+        RB_TRY(op.alloc(cols, &dw));
+        RB_TRY(op.up(dw, w, cols));
+    }
+    RB_TRY(op.alloc((i64)np * np, &dout));
+    RB_TRY(rb_ri_mo_pq(op.ctx, dm, np, np, dm, np, np, nl, rl, l0, ll, 0, rl, dw, 0.0, dout, np));
+    RB_TRY(op.down(out, dout, (i64)np * np));
+    return op.sync();
+}

@@ -372,3 +372,102 @@ extern "C" int rb_ri_iajb(rb_ctx *ctx, int np_, const double *mo_a, int64_t ldp_
     }
     return same ? rb_symmetrize(ctx, out, m, ldo, true) : RB_OK;
 }
+
+// ---- RPA-type consumer of ri3mo: contraction over the MO pairs, output in the auxiliary basis ------------------------
+//     out[P, Q] (+)= sum_{(l,r) in box} w[l,r] * moA[P,l,r] * moB[Q,l,r]        (w == NULL: all ones)
+// e.g. the RPA polarisability Pi(omega) = sum_ia R_ia^P f_ia(omega) R_ia^Q, which REST builds with _dgemm on
+// [naux, n_occ*n_vir] views of ri3mo.  moA / moB are row blocks (P-shards) of the same P-fastest tensor: a rank that
+// owns rows P_r gets out[P_r, Q_s] from its own rows and rank s's rows.  ONE 'N','T' DMMA GEMM with K = the box's MO
+// pairs; both operands are MN-major (P fastest), i.e. the swizzled TMA path.  The weights are folded into a scaled
+// copy of the B panel (one HBM pass); a partial l range is gathered by the same kernel.  moA == moB: only the upper
+// triangle's tiles are computed, then mirrored (sum_c w_c x_c x_c^T is symmetric).
+__global__ void __launch_bounds__(256) rb_mo_box_gather_kernel(const double *__restrict__ src, i64 ldp, i64 nl, i64 ll,
+                                                               i64 c0, const double *__restrict__ w,
+                                                               double *__restrict__ dst, i64 ldd, i64 np, i64 cols)
+{
+    for (i64 c = blockIdx.y; c < cols; c += gridDim.y) {
+        const i64 cb = c0 + c, l = cb % ll, r = cb / ll;
+        const double *s = src + l * ldp + r * ldp * nl;
+        double *d = dst + c * ldd;
+        const i64 stride = (i64)gridDim.x * blockDim.x;
+        i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+        if (w) {
+            const double wc = w[cb];
+            for (; p + stride < np; p += 2 * stride) {
+                const double v0 = s[p], v1 = s[p + stride];
+                d[p] = __dmul_rn(v0, wc); d[p + stride] = __dmul_rn(v1, wc);
+            }
+            for (; p < np; p += stride) d[p] = __dmul_rn(s[p], wc);
+        } else {
+            for (; p + stride < np; p += 2 * stride) {
+                const double v0 = s[p], v1 = s[p + stride];
+                d[p] = v0; d[p + stride] = v1;
+            }
+            for (; p < np; p += stride) d[p] = s[p];
+        }
+    }
+}
+
+static int mo_box_gather(rb_ctx *ctx, const double *box, i64 ldp, i64 nl, i64 ll, i64 c0, const double *w, double *dst,
+                         i64 ldd, i64 np, i64 cols)
+{
+    i64 bx = rb_cdiv(np, 512);
+    if (bx > 16) bx = 16;
+    i64 by = cols < 65535 ? cols : 65535;
+    const i64 cap = (i64)ctx->num_sms * 16;
+    if (bx * by > cap) by = cap / bx > 0 ? cap / bx : 1;
+    rb_mo_box_gather_kernel<<<dim3((unsigned)bx, (unsigned)by), 256, 0, ctx->stream>>>(box, ldp, nl, ll, c0, w, dst, ldd, np, cols);
+    RB_LAUNCHED(ctx);
+    return RB_OK;
+}
+
+extern "C" int rb_ri_mo_pq(rb_ctx *ctx, const double *mo_a, int64_t ldp_a, int np_a, const double *mo_b, int64_t ldp_b,
+                           int np_b, int nl_, int nr_, int l0, int ll_, int r0, int rl_, const double *w, double beta,
+                           double *out, int64_t ldo)
+{
+    RB_REQUIRE(ctx, "rb_ri_mo_pq: ctx is NULL");
+    RB_REQUIRE(np_a >= 0 && np_b >= 0, "rb_ri_mo_pq: negative dimension");
+    const MoBox X = {mo_a, ldp_a, nl_, nr_, l0, ll_, r0, rl_};
+    RB_REQUIRE(box_valid(X), "rb_ri_mo_pq: box [%d+%d, %d+%d] outside [%d, %d]", l0, ll_, r0, rl_, nl_, nr_);
+    RB_REQUIRE(ldp_a >= np_a && ldp_b >= np_b, "rb_ri_mo_pq: ldp (%lld, %lld) < np (%d, %d)", (long long)ldp_a,
+               (long long)ldp_b, np_a, np_b);
+    const i64 m = np_a, n = np_b, nl = nl_, ll = ll_, cols = (i64)ll_ * rl_;
+    if (m == 0 || n == 0) return RB_OK;
+    RB_REQUIRE(out, "rb_ri_mo_pq: out is NULL");
+    RB_REQUIRE(ldo >= m, "rb_ri_mo_pq: ldo (%lld) < np_a (%lld)", (long long)ldo, (long long)m);
+    RB_CUDA(cudaSetDevice(ctx->device));
+    if (cols == 0) // empty contraction: out = beta * out
+        return rb_gemm_core(ctx, false, true, m, n, 0, 1.0, nullptr, 1, 0, nullptr, 1, 0, beta, out, ldo, 0, 1, 0);
+    RB_REQUIRE(mo_a && mo_b, "rb_ri_mo_pq: mo is NULL");
+    const bool same = mo_a == mo_b && ldp_a == ldp_b && np_a == np_b;
+    const int tri = same ? 1 : 0;
+    const bool panel = box_is_panel(X);
+    const double *xa = mo_a + (i64)l0 * ldp_a + (i64)r0 * ldp_a * nl, *xb = mo_b + (i64)l0 * ldp_b + (i64)r0 * ldp_b * nl;
+    const bool copy_a = !panel, copy_b = !panel || w != nullptr;
+    if (!copy_a && !copy_b) {
+        RB_TRY(rb_gemm_core(ctx, false, true, m, n, cols, 1.0, xa, ldp_a, 0, xb, ldp_b, 0, beta, out, ldo, 0, 1, tri));
+        return same ? rb_symmetrize(ctx, out, m, ldo, true) : RB_OK;
+    }
+    // column-chunked: gathered / weighted copies of the panels live in the workspace, chunks accumulate with beta = 1
+    const i64 lda_g = m + (m & 1), ldb_g = n + (n & 1);
+    const i64 per_col = ((copy_a ? lda_g : 0) + (copy_b ? ldb_g : 0)) * 8;
+    i64 cc = ws_budget_bytes(ctx) / per_col;
+    if (cc > 8) cc &= ~(i64)7;
+    if (cc < 1) cc = 1;
+    if (cc > cols) cc = cols;
+    void *ws;
+    RB_TRY(rb_ws_reserve(ctx, 0, per_col * cc, &ws));
+    double *ga = (double *)ws, *gb = copy_a ? ga + lda_g * cc : ga;
+    for (i64 c0 = 0; c0 < cols; c0 += cc) {
+        const i64 cn = (cols - c0 < cc) ? cols - c0 : cc;
+        const double *a = xa + c0 * ldp_a, *b = gb;
+        i64 lda = ldp_a;
+        if (copy_a) {
+            RB_TRY(mo_box_gather(ctx, xa, ldp_a, nl, ll, c0, nullptr, ga, lda_g, m, cn));
+            a = ga; lda = lda_g;
+        }
+        RB_TRY(mo_box_gather(ctx, xb, ldp_b, nl, ll, c0, w, gb, ldb_g, n, cn));
+        RB_TRY(rb_gemm_core(ctx, false, true, m, n, cn, 1.0, a, lda, 0, b, ldb_g, 0, c0 == 0 ? beta : 1.0, out, ldo, 0, 1, tri));
+    }
+    return same ? rb_symmetrize(ctx, out, m, ldo, true) : RB_OK;
+}

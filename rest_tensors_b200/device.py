@@ -109,6 +109,10 @@ class Context:
         check(lib.rb_ri_iajb(self.h, np_, _p(mo_a), ldp_a, nl_a, nr_a, *box_a, _p(mo_b), ldp_b, nl_b, nr_b, *box_b, beta,
                              _p(out), ldo), "rb_ri_iajb")
 
+    def ri_mo_pq(self, mo_a, ldp_a, np_a, mo_b, ldp_b, np_b, nl, nr, box, w, beta, out, ldo) -> None:
+        check(lib.rb_ri_mo_pq(self.h, _p(mo_a), ldp_a, np_a, _p(mo_b), ldp_b, np_b, nl, nr, *box, _p(w), beta, _p(out),
+                              ldo), "rb_ri_mo_pq")
+
     def special_dgemm_01(self, ten3, x_a, y_a, z_a, sx, lx, sz, lz, b, ldb, lcb, alpha, beta) -> None:
         check(lib.rb_special_dgemm_01(self.h, _p(ten3), x_a, y_a, z_a, sx, lx, sz, lz, _p(b), ldb, lcb, alpha, beta),
               "rb_special_dgemm_01")
@@ -241,6 +245,38 @@ class ShardedRI:
         if reduce:
             all_reduce_sum(out, self.world)
         return out
+
+    def mo_pq(self, mo: torch.Tensor, nl: int, nr: int, box, w: Optional[torch.Tensor] = None,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """RPA-type block row out[P_local, Q] = sum_{(l,r) in box} w[l,r] mo[P,l,r] mo[Q,l,r] over ALL Q in [0, naux):
+        the one exchange step on this side of the path -- every rank needs every other rank's rows of ri3mo for the
+        box.  The row blocks travel by all-gather (NCCL over NVLink; shards may differ by one row, so the pieces are
+        padded to the longest shard) and each received block feeds one 'N','T' GEMM into its column range of `out`
+        ([nx_local, naux], column-major).  world == 1: one symmetric GEMM, no communication."""
+        if out is None:
+            out = self.ctx.empty(self.nx * self.naux)
+        if self.world == 1:
+            self.ctx.ri_mo_pq(mo, self.nx, self.nx, mo, self.nx, self.nx, nl, nr, box, w, 0.0, out, self.nx)
+            return out
+        import torch.distributed as dist
+        l0, ll, r0, rl = box
+        nx_max = -(-self.naux // self.world)
+        mine = torch.zeros(nx_max * ll * rl, dtype=mo.dtype, device=mo.device)
+        if mo.is_cuda:  # gather this rank's box columns into a dense [nx_max, ll*rl] panel with our own copy kernel
+            check(lib.rb_copy_rr(self.ctx.h, self.nx, ll, rl, _p(mo), self.nx, nl, nr, 0, l0, r0, _p(mine), nx_max, ll, rl,
+                                 0, 0, 0), "rb_copy_rr")
+        else:           # gloo tier (host logic test): same gather with tensor views
+            mine.view(rl, ll, nx_max)[:, :, : self.nx] = mo.view(nr, nl, self.nx)[r0:r0 + rl, l0:l0 + ll, :]
+        pieces = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(pieces, mine)
+        for s, piece in enumerate(pieces):
+            q_lo, q_hi = shard_range(self.naux, s, self.world)
+            self._mo_pq_block(mine, piece, nx_max, q_hi - q_lo, ll, rl, w, out, q_lo)
+        return out
+
+    def _mo_pq_block(self, mine, piece, ldp, nq, ll, rl, w, out, q_lo) -> None:
+        self.ctx.ri_mo_pq(mine, ldp, self.nx, piece, ldp, nq, ll, rl, (0, ll, 0, rl), w, 0.0,
+                          out[q_lo * self.nx:], self.nx)
 
 
 def all_reduce_sum(t: torch.Tensor, world: int) -> None:

@@ -622,6 +622,22 @@ class RIFull:
               "ri_iajb")
         return out
 
+    def ri_mo_pq(self, range_l: Range, range_r: Range, w: Optional[np.ndarray] = None) -> MatrixFull:
+        """self = ri3mo[P, l, r]; returns the symmetric [naux, naux] matrix sum_{(l,r) in box} w[l,r] self[P,l,r]
+        self[Q,l,r] (w over the box's pairs, l fastest; None = ones) -- e.g. REST's RPA polarisability."""
+        if not (0 <= range_l[0] <= range_l[1] <= self.size[1] and 0 <= range_r[0] <= range_r[1] <= self.size[2]):
+            raise RestB200Error("ri_mo_pq: box outside the tensor")
+        ll, rl = _rlen(range_l), _rlen(range_r)
+        wv = None
+        if w is not None:
+            wv = _f64(w)
+            if wv.size != ll * rl:
+                raise RestB200Error("ri_mo_pq: one weight per MO pair of the box is needed")
+        out = MatrixFull.new([self.size[0], self.size[0]], 0.0)
+        check(lib.rb_host_ri_mo_pq(_ptr(self.data), self.size[0], self.size[1], self.size[2], range_l[0], ll, range_r[0],
+                                   rl, None if wv is None else _ptr(wv), _ptr(out.data)), "ri_mo_pq")
+        return out
+
 # ======================================================================================================
 # views and index maps
 # ======================================================================================================

@@ -40,6 +40,24 @@ def _worker(rank, world, port, nb, naux, no, ret):
         box_a, box_b = (0, no, no, nb - no), (1, no - 1, no, nb - no)
         g = torch.from_numpy(o.ri_iajb(nx, mo_local, nb, box_a, mo_local, nb, box_b))
         all_reduce_sum(g, world)
+        # RPA-type block row out[P_local, all Q]: the host logic of ShardedRI.mo_pq (all-gather of the box's row blocks,
+        # one GEMM per received block) with the per-block GEMM supplied by the oracle instead of the CUDA kernel
+        from rest_tensors_b200.device import ShardedRI
+        box = (0, no, no, nb - no)
+        wts = o.fill_linear(box[1] * box[3], 7)
+
+        class _OracleBlocks(ShardedRI):
+            def _mo_pq_block(self, mine, piece, ldp, nq, ll, rl, w, out, q_lo):
+                a = np.ascontiguousarray(mine.numpy().reshape((ldp, ll * rl), order="F")[: self.nx].reshape(-1, order="F"))
+                b = np.ascontiguousarray(piece.numpy().reshape((ldp, ll * rl), order="F")[:nq].reshape(-1, order="F"))
+                blk = o.ri_mo_pq(a, self.nx, b, nq, ll, (0, ll, 0, rl), w.numpy())
+                out[q_lo * self.nx:(q_lo + nq) * self.nx] = torch.from_numpy(blk)
+
+        shd = _OracleBlocks(None, nb, naux, rank, world, data=torch.from_numpy(ri_local))
+        pq_rows = shd.mo_pq(torch.from_numpy(mo_local), nb, nb, box, torch.from_numpy(wts), out=torch.zeros(nx * naux, dtype=torch.float64))
+        pq_all = [torch.zeros((naux - naux // world) * naux + naux, dtype=torch.float64) for _ in range(world)]
+        pad = torch.zeros_like(pq_all[0]); pad[: pq_rows.numel()] = pq_rows
+        dist.all_gather(pq_all, pad)
         # gather the d_P pieces and the P-rows of ri3mo for the check on rank 0
         d_full = gather_dp(torch.from_numpy(d_local), naux, p_lo, world)
         if rank == 0:
@@ -52,6 +70,11 @@ def _worker(rank, world, port, nb, naux, no, ret):
             ok &= np.array_equal(mo[p_lo:p_hi].reshape(-1, order="F"), mo_local)
             mo_flat = np.ascontiguousarray(mo.reshape(-1, order="F"))
             ok &= np.allclose(g.numpy(), o.ri_iajb(naux, mo_flat, nb, box_a, mo_flat, nb, box_b), rtol=1e-11, atol=1e-12)
+            pq_ref = o.ri_mo_pq(mo_flat, naux, mo_flat, naux, nb, box, wts).reshape((naux, naux), order="F")
+            for s_ in range(world):
+                lo, hi = shard_range(naux, s_, world)
+                rows = pq_all[s_][: (hi - lo) * naux].numpy().reshape((hi - lo, naux), order="F")
+                ok &= np.allclose(rows, pq_ref[lo:hi], rtol=1e-11, atol=1e-12)
             ret.put(bool(ok))
         dist.barrier()
     finally:

@@ -36,15 +36,24 @@ def _worker(rank, world, port, nb, naux, no, ret):
         k = sh.k(dev(ct), no)              # partial + all-reduce
         mo_local = sh.ao2mo(cd, nb, cd, nb)
         d_full = gather_dp(d_local, naux, sh.p_lo, world)
+        # consumers of ri3mo: (ia|jb) block (partial + all-reduce) and the RPA-type block row (all-gather of row blocks)
+        box_a, box_b = (0, no, no, nb - no), (1, no - 1, no, nb - no)
+        g = sh.iajb(mo_local, nb, nb, box_a, box_b)
+        wts = o.fill_linear(box_a[1] * box_a[3], 7)
+        pq = sh.mo_pq(mo_local, nb, nb, box_a, dev(wts))
         torch.cuda.synchronize()
         ri = o.fill_ri3ao_symm(nb, 0, naux)
         d_ref = o.ri_dp(ri, dm, nb, naux)
 
         def err(x, y):
             return float(np.max(np.abs(x - y)) / np.max(np.abs(y)))
-        mo_ref = o.ri_ao2mo_f(c, ri, nb, nb, naux).reshape((naux, nb, nb), order="F")[sh.p_lo:sh.p_hi].reshape(-1, order="F")
+        mo_all = o.ri_ao2mo_f(c, ri, nb, nb, naux)
+        mo_ref = mo_all.reshape((naux, nb, nb), order="F")[sh.p_lo:sh.p_hi].reshape(-1, order="F")
+        g_ref = o.ri_iajb(naux, mo_all, nb, box_a, mo_all, nb, box_b)
+        pq_ref = o.ri_mo_pq(mo_all, naux, mo_all, naux, nb, box_a, wts).reshape((naux, naux), order="F")[sh.p_lo:sh.p_hi]
         errs = [err(d_full.cpu().numpy(), d_ref), err(j.cpu().numpy(), o.ri_j(ri, d_ref, nb, naux)),
-                err(k.cpu().numpy(), o.ri_k(ri, ct, nb, no, naux)), err(mo_local.cpu().numpy(), mo_ref)]
+                err(k.cpu().numpy(), o.ri_k(ri, ct, nb, no, naux)), err(mo_local.cpu().numpy(), mo_ref),
+                err(g.cpu().numpy(), g_ref), err(pq.cpu().numpy(), pq_ref.reshape(-1, order="F"))]
         ret.put((rank, max(errs)))
         dist.barrier()
     finally:

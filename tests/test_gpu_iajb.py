@@ -147,3 +147,87 @@ def test_iajb_error_codes(ctx):
     mo.fill_(1.0)
     ctx.ri_iajb(10, mo, 10, 3, 4, (0, 3, 0, 4), mo, 10, 3, 4, (0, 3, 0, 4), 0.0, out, 12)
     assert torch.all(out == 10.0)
+
+
+# ---------------------------------------------------------------- RPA-type consumer: contraction over the MO pairs ----
+PQ_CASES = [
+    # np, nl, nr, box (l0, ll, r0, rl), weighted
+    (48, 5, 8, (0, 5, 0, 8), False),      # whole tensor in place, SYRK-like
+    (48, 5, 8, (0, 5, 0, 8), True),       # weights: scaled copy of the B panel
+    (49, 5, 8, (0, 5, 2, 5), True),       # odd np (odd pitch) panel
+    (130, 9, 14, (2, 6, 3, 10), False),   # gathered box
+    (130, 9, 14, (2, 6, 3, 10), True),
+    (300, 4, 50, (1, 2, 0, 50), True),    # np > one tile, ragged
+    (7, 3, 3, (1, 1, 2, 1), True),        # a single MO pair: rank-1 update
+]
+
+
+@pytest.mark.parametrize("case", PQ_CASES)
+def test_mo_pq_vs_oracle(ctx, oracle_blas, case):
+    np_, nl, nr, box, weighted = case
+    mo = oracle_blas.fill_linear(np_ * nl * nr, 51)
+    w = oracle_blas.fill_linear(box[1] * box[3], 52) if weighted else None
+    ref = oracle_blas.ri_mo_pq(mo, np_, mo, np_, nl, box, w)
+    mod = _dev(ctx, mo)
+    out = ctx.empty(np_ * np_)
+    out.fill_(float("nan"))
+    ctx.ri_mo_pq(mod, np_, np_, mod, np_, np_, nl, nr, box, None if w is None else _dev(ctx, w), 0.0, out, np_)
+    got = out.cpu().numpy()
+    assert_close_1e10(got, ref, f"mo_pq {case}")
+    g = got.reshape((np_, np_), order="F")
+    assert np.array_equal(g, g.T), "moA == moB must give a bitwise symmetric matrix"
+
+
+def test_mo_pq_row_blocks_and_beta(ctx, oracle_blas):
+    """Row blocks of one tensor (what two P-shards exchange): out[P_a, Q_b] with pitched views, beta accumulation,
+    ldo > rows; and the four blocks tile the full symmetric matrix."""
+    np_, nl, nr = 101, 6, 9
+    box = (1, 4, 2, 6)
+    mo = oracle_blas.fill_linear(np_ * nl * nr, 53)
+    w = oracle_blas.fill_linear(box[1] * box[3], 54)
+    full = oracle_blas.ri_mo_pq(mo, np_, mo, np_, nl, box, w).reshape((np_, np_), order="F")
+    mod, wd = _dev(ctx, mo), _dev(ctx, w)
+    split = 37
+    blocks = [(0, split), (split, np_)]
+    for (a0, a1) in blocks:
+        for (b0, b1) in blocks:
+            ma, mb = a1 - a0, b1 - b0
+            ldo = ma + 3
+            c0 = oracle_blas.fill_linear(ldo * mb, 55)
+            out = _dev(ctx, c0)
+            ctx.ri_mo_pq(mod[a0:], np_, ma, mod[b0:], np_, mb, nl, nr, box, wd, 2.0, out, ldo)
+            got = out.cpu().numpy().reshape((ldo, mb), order="F")
+            c0m = c0.reshape((ldo, mb), order="F")
+            assert_close_1e10(got[:ma], full[a0:a1, b0:b1] + 2.0 * c0m[:ma], f"mo_pq block {a0}:{a1} x {b0}:{b1}")
+            assert np.array_equal(got[ma:], c0m[ma:])
+
+
+def test_mo_pq_is_iajb_trace_identity(ctx, oracle_blas):
+    """Size-independent cross-check of the two consumers: ||G||_F^2 over the (ia|jb) block of a box equals ||Pi||_F^2
+    of the unweighted auxiliary-basis matrix of the same box (both are tr(X X^T X X^T))."""
+    np_, nl, nr = 96, 7, 12
+    box = (0, 7, 0, 12)
+    mo = oracle_blas.fill_linear(np_ * nl * nr, 56)
+    mod = _dev(ctx, mo)
+    m = nl * nr
+    g = ctx.empty(m * m); pi = ctx.empty(np_ * np_)
+    ctx.ri_iajb(np_, mod, np_, nl, nr, box, mod, np_, nl, nr, box, 0.0, g, m)
+    ctx.ri_mo_pq(mod, np_, np_, mod, np_, np_, nl, nr, box, None, 0.0, pi, np_)
+    a, b = float(torch.sum(g * g)), float(torch.sum(pi * pi))
+    assert abs(a - b) <= 1e-11 * abs(b)
+
+
+def test_host_mo_pq_mirror(rt, oracle_blas):
+    np_, nl, nr = 66, 5, 8
+    mo = oracle_blas.fill_linear(np_ * nl * nr, 57)
+    t = rt.RIFull.from_vec([np_, nl, nr], mo)
+    w = oracle_blas.fill_linear(3 * 5, 58)
+    got = t.ri_mo_pq((1, 4), (2, 7), w)
+    assert got.size == [np_, np_]
+    assert_close_1e10(got.data, oracle_blas.ri_mo_pq(mo, np_, mo, np_, nl, (1, 3, 2, 5), w), "host mo_pq weighted")
+    got = t.ri_mo_pq((0, 5), (0, 8))
+    assert_close_1e10(got.data, oracle_blas.ri_mo_pq(mo, np_, mo, np_, nl, (0, 5, 0, 8), None), "host mo_pq")
+    with pytest.raises(rt.RestB200Error):
+        t.ri_mo_pq((0, 6), (0, 8))
+    with pytest.raises(rt.RestB200Error):
+        t.ri_mo_pq((0, 5), (0, 8), np.ones(3))
