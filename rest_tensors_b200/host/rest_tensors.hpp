@@ -233,6 +233,31 @@ struct RIFull {
         rb_check(rb_host_ri_k(data.data(), ct.data.data(), (int)ct.size[1], k.data.data(), (int)size[0], (int)size[2]), "ri_k");
         return k;
     }
+    // consumers of a P-fastest MO tensor (this = ri3mo[P, l, r]); ranges are half-open [lo, hi)
+    MatrixFull ri_iajb(std::array<size_t, 2> la, std::array<size_t, 2> ra, std::array<size_t, 2> lb, std::array<size_t, 2> rb,
+                       const RIFull *other = nullptr) const
+    {
+        const RIFull &b = other ? *other : *this;
+        if (b.size[0] != size[0]) throw std::runtime_error("ri_iajb: the two MO tensors have different auxiliary dimensions");
+        if (la[0] > la[1] || la[1] > size[1] || ra[0] > ra[1] || ra[1] > size[2] || lb[0] > lb[1] || lb[1] > b.size[1] ||
+            rb[0] > rb[1] || rb[1] > b.size[2])
+            throw std::runtime_error("ri_iajb: box outside the tensor");
+        const size_t m = (la[1] - la[0]) * (ra[1] - ra[0]), n = (lb[1] - lb[0]) * (rb[1] - rb[0]);
+        MatrixFull out = MatrixFull::make({m, n}, 0.0);
+        rb_check(rb_host_ri_iajb((int)size[0], data.data(), (int)size[1], (int)size[2], (int)la[0], (int)(la[1] - la[0]),
+                                 (int)ra[0], (int)(ra[1] - ra[0]), b.data.data(), (int)b.size[1], (int)b.size[2], (int)lb[0],
+                                 (int)(lb[1] - lb[0]), (int)rb[0], (int)(rb[1] - rb[0]), out.data.data()), "ri_iajb");
+        return out;
+    }
+    MatrixFull ri_mo_pq(std::array<size_t, 2> l, std::array<size_t, 2> r, const std::vector<double> *w = nullptr) const
+    {
+        if (l[0] > l[1] || l[1] > size[1] || r[0] > r[1] || r[1] > size[2]) throw std::runtime_error("ri_mo_pq: box outside the tensor");
+        if (w && w->size() != (l[1] - l[0]) * (r[1] - r[0])) throw std::runtime_error("ri_mo_pq: one weight per MO pair of the box is needed");
+        MatrixFull out = MatrixFull::make({size[0], size[0]}, 0.0);
+        rb_check(rb_host_ri_mo_pq(data.data(), (int)size[0], (int)size[1], (int)size[2], (int)l[0], (int)(l[1] - l[0]), (int)r[0],
+                                  (int)(r[1] - r[0]), w ? w->data() : nullptr, out.data.data()), "ri_mo_pq");
+        return out;
+    }
 
   private:
     RIFull tr(int which, std::array<size_t, 3> ns) const

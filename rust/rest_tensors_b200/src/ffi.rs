@@ -45,6 +45,13 @@ extern "C" {
     pub fn rb_host_ri_dp(ri3ao: *const c_double, dm: *const c_double, d: *mut c_double, nb: c_int, nx: c_int) -> c_int;
     pub fn rb_host_ri_j(ri3ao: *const c_double, d: *const c_double, j: *mut c_double, nb: c_int, nx: c_int) -> c_int;
     pub fn rb_host_ri_k(ri3ao: *const c_double, ct: *const c_double, no: c_int, k: *mut c_double, nb: c_int, nx: c_int) -> c_int;
+    /// (ia|jb)-type blocks of host ri3mo tensors [np, nl, nr]; out = dense [lla*rla, llb*rlb]
+    pub fn rb_host_ri_iajb(np: c_int, mo_a: *const c_double, nl_a: c_int, nr_a: c_int, l0a: c_int, lla: c_int, r0a: c_int,
+                           rla: c_int, mo_b: *const c_double, nl_b: c_int, nr_b: c_int, l0b: c_int, llb: c_int, r0b: c_int,
+                           rlb: c_int, out: *mut c_double) -> c_int;
+    /// RPA-type out[P,Q] = sum_{(l,r) in box} w[l,r] mo[P,l,r] mo[Q,l,r]; w may be null
+    pub fn rb_host_ri_mo_pq(mo: *const c_double, np: c_int, nl: c_int, nr: c_int, l0: c_int, ll: c_int, r0: c_int, rl: c_int,
+                            w: *const c_double, out: *mut c_double) -> c_int;
 
     // device-resident API (device pointers)
     pub fn rb_ri_ao2mo(ctx: *mut RbCtx, cl: *const c_double, nl: c_int, cr: *const c_double, nr: c_int,
@@ -52,6 +59,12 @@ extern "C" {
     pub fn rb_ri_dp(ctx: *mut RbCtx, ri3ao: *const c_double, dm: *const c_double, d: *mut c_double, nb: c_int, nx: c_int) -> c_int;
     pub fn rb_ri_j(ctx: *mut RbCtx, ri3ao: *const c_double, d: *const c_double, j: *mut c_double, nb: c_int, nx: c_int) -> c_int;
     pub fn rb_ri_k(ctx: *mut RbCtx, ri3ao: *const c_double, ct: *const c_double, no: c_int, k: *mut c_double, nb: c_int, nx: c_int) -> c_int;
+    pub fn rb_ri_iajb(ctx: *mut RbCtx, np: c_int, mo_a: *const c_double, ldp_a: i64, nl_a: c_int, nr_a: c_int, l0a: c_int,
+                      lla: c_int, r0a: c_int, rla: c_int, mo_b: *const c_double, ldp_b: i64, nl_b: c_int, nr_b: c_int,
+                      l0b: c_int, llb: c_int, r0b: c_int, rlb: c_int, beta: c_double, out: *mut c_double, ldo: i64) -> c_int;
+    pub fn rb_ri_mo_pq(ctx: *mut RbCtx, mo_a: *const c_double, ldp_a: i64, np_a: c_int, mo_b: *const c_double, ldp_b: i64,
+                       np_b: c_int, nl: c_int, nr: c_int, l0: c_int, ll: c_int, r0: c_int, rl: c_int, w: *const c_double,
+                       beta: c_double, out: *mut c_double, ldo: i64) -> c_int;
 }
 
 /// Turn a non-zero status into the panic the reference's wrappers raise on bad shapes.

@@ -11,6 +11,10 @@ void orc_ri_ao2mo_f(const double *c, const double *ri, double *mo, int ns, int n
 void orc_ri_dp(const double *ri, const double *dm, double *d, int nb, int nx);
 void orc_ri_j(const double *ri, const double *d, double *j, int nb, int nx);
 void orc_ri_k(const double *ri, const double *ct, double *k, int nb, int no, int nx);
+void orc_ri_iajb(int np, const double *mo_a, int nl_a, int l0a, int lla, int r0a, int rla, const double *mo_b, int nl_b,
+                 int l0b, int llb, int r0b, int rlb, double *out);
+void orc_ri_mo_pq(const double *mo_a, int npa, const double *mo_b, int npb, int nl, int l0, int ll, int r0, int rl,
+                  const double *w, double *out);
 void orc_ri_transpose(const double *in, int64_t I, int64_t J, int64_t K, int which, double *out);
 }
 using namespace rest_tensors;
@@ -79,6 +83,20 @@ int main()
     CHECK(rel_err(R.ri_dp(MatrixFull::from_vec({(size_t)nb, (size_t)nb}, dm)), dref) < 1e-10, "d_P vs oracle");
     CHECK(rel_err(R.ri_j(dref).data, jref) < 1e-10, "J vs oracle");
     CHECK(rel_err(R.ri_k(MatrixFull::from_vec({(size_t)nb, (size_t)no}, ct)).data, kref) < 1e-10, "K vs oracle");
+    // consumers of ri3mo: (ia|jb) block and the RPA-type auxiliary-basis matrix
+    {
+        const int np = 40, nl = 5, nr = 7;
+        auto mov = fill((size_t)np * nl * nr, 8), wv = fill(3 * 4, 9);
+        auto M = RIFull::from_vec({(size_t)np, (size_t)nl, (size_t)nr}, mov);
+        std::vector<double> gref(12 * 35), pref((size_t)np * np);
+        orc_ri_iajb(np, mov.data(), nl, 1, 3, 2, 4, mov.data(), nl, 0, 5, 0, 7, gref.data());
+        orc_ri_mo_pq(mov.data(), np, mov.data(), np, nl, 1, 3, 2, 4, wv.data(), pref.data());
+        CHECK(rel_err(M.ri_iajb({1, 4}, {2, 6}, {0, 5}, {0, 7}).data, gref) < 1e-10, "(ia|jb) vs oracle");
+        CHECK(rel_err(M.ri_mo_pq({1, 4}, {2, 6}, &wv).data, pref) < 1e-10, "mo_pq vs oracle");
+        bool thr = false;
+        try { M.ri_iajb({0, 6}, {0, 7}, {0, 5}, {0, 7}); } catch (const std::runtime_error &) { thr = true; }
+        CHECK(thr, "ri_iajb box outside the tensor must throw");
+    }
     // panics
     bool threw = false;
     try { RIFull::from_vec({3, 2, 2}, std::vector<double>(11)); } catch (const std::runtime_error &) { threw = true; }
