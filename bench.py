@@ -427,6 +427,19 @@ def run_ours(args):
                 if it:
                     best = a0.elapsed_time(a1) if best is None else min(best, a0.elapsed_time(a1))
             res[name] = {"ms": best, "tflops_per_gpu": fl / (best * 1e-3) / 1e12}
+        # RPA-type consumer on the same tensor: Pi[P,Q] = sum_ia w_ia R_ia^P R_ia^Q (upper triangle + mirror, np(np+1)K flop)
+        wts = ctx.empty(no * nv); ctx.fill_linear(wts, no * nv, 9, 0, 1.0)
+        pi = ctx.empty(nx * nx)
+        best = None
+        for it in range(3):
+            a0, a1 = ev(), ev()
+            a0.record(); ctx.ri_mo_pq(ov, nx, nx, ov, nx, nx, no, nv, (0, no, 0, nv), wts, 0.0, pi, nx); a1.record()
+            torch.cuda.synchronize()
+            if it:
+                best = a0.elapsed_time(a1) if best is None else min(best, a0.elapsed_time(a1))
+        res["mo_pq_weighted"] = {"ms": best, "tflops_per_gpu": float(nx) * (nx + 1) * no * nv / (best * 1e-3) / 1e12,
+                                 "m": nx, "k": no * nv}
+        del pi, wts
         iajb = {"occ_block": li, "rows": m_blk, "k": nx, **res,
                 "note": "rb_ri_iajb on this rank's rows of the occ-vir ri3mo (partial sum; all-reduce not timed); best of 2"}
         del g

@@ -56,7 +56,8 @@ int rb_ctx_sync(rb_ctx *ctx);
 int rb_ctx_num_sms(rb_ctx *ctx);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 int64_t rb_ctx_launch_count(rb_ctx *ctx);
-/* Select the GEMM implementation: 0 = auto (TMA+DMMA when alignment allows, else generic DMMA), 1 = force generic. */
+/* Select the GEMM implementation: 0 = auto (TMA+DMMA when alignment allows, else generic DMMA), 1 = force generic,
+ * 2 = auto without the thin-edge-tile loads (edge tiles stream full zero-filled boxes; A/B measurements only). */
 int rb_ctx_set_gemm_path(rb_ctx *ctx, int path);
 
 /* device memory helpers for hosts without their own allocator (Rust/C++ side) */
