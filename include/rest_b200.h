@@ -56,8 +56,7 @@ int rb_ctx_sync(rb_ctx *ctx);
 int rb_ctx_num_sms(rb_ctx *ctx);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 int64_t rb_ctx_launch_count(rb_ctx *ctx);
-/* Select the GEMM implementation: 0 = auto (TMA+DMMA when alignment allows, else generic DMMA), 1 = force generic,
- * 2 = auto without the thin-edge-tile loads (edge tiles stream full zero-filled boxes; A/B measurements only). */
+/* Select the GEMM implementation: 0 = auto (TMA+DMMA when alignment allows, else generic DMMA), 1 = force generic. */
 int rb_ctx_set_gemm_path(rb_ctx *ctx, int path);
 
 /* device memory helpers for hosts without their own allocator (Rust/C++ side) */
@@ -196,7 +195,8 @@ int rb_special_dgemm_01(rb_ctx *ctx, double *ten3, int x_a, int y_a, int z_a, in
 
 /* (ia|jb)-type consumers of ri3mo (the P-fastest layout of src/ri.rs:381-386 exists for them):
  *   out[(l-l0a) + (r-r0a)*lla + ((l'-l0b) + (r'-r0b)*llb)*ldo] = beta*out + sum_{P<np} moA[P,l,r] * moB[P,l',r']
- * with mo[P + l*ldp + r*ldp*nl].  moA == moB with identical boxes runs as SYRK (both triangles written).  One rank's
+ * with mo[P + l*ldp + r*ldp*nl].  moA == moB with identical boxes and beta == 0 runs as SYRK + mirror (both triangles
+ * written, bitwise symmetric); with beta != 0 the full product is formed, so out need not be symmetric.  One rank's
  * partial sum over its local P rows; all-reduce `out` across P-sharded ranks. */
 int rb_ri_iajb(rb_ctx *ctx, int np, const double *mo_a, int64_t ldp_a, int nl_a, int nr_a, int l0a, int lla, int r0a,
                int rla, const double *mo_b, int64_t ldp_b, int nl_b, int nr_b, int l0b, int llb, int r0b, int rlb,
@@ -205,7 +205,7 @@ int rb_ri_iajb(rb_ctx *ctx, int np, const double *mo_a, int64_t ldp_a, int nl_a,
 /* RPA-type consumer of ri3mo: contraction over the MO pairs of a box, output in the auxiliary basis,
  *   out[P + Q*ldo] = beta*out + sum_{(l,r) in box} w[(l-l0) + (r-r0)*ll] * moA[P,l,r] * moB[Q,l,r]      (w NULL: ones)
  * moA (np_a rows, pitch ldp_a) and moB (np_b rows, pitch ldp_b) are row blocks (P-shards) of [.., nl, nr] tensors;
- * moA == moB is computed as the upper triangle + mirror.  'N','T' DMMA GEMM with K = ll*rl. */
+ * moA == moB with beta == 0 is computed as the upper triangle + mirror.  'N','T' DMMA GEMM with K = ll*rl. */
 int rb_ri_mo_pq(rb_ctx *ctx, const double *mo_a, int64_t ldp_a, int np_a, const double *mo_b, int64_t ldp_b, int np_b,
                 int nl, int nr, int l0, int ll, int r0, int rl, const double *w, double beta, double *out, int64_t ldo);
 

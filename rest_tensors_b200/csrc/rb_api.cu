@@ -60,8 +60,6 @@ extern "C" int rb_ctx_create(int device, rb_ctx **out)
     e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
     if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) c->encode_tiled = (rb_encode_tiled_fn)fn;
     else cudaGetLastError();
-    // REST_B200_THIN=0: edge tiles stream full zero-filled TMA boxes (gemm path 2; see rb_ctx_set_gemm_path)
-    if (const char *thin = getenv("REST_B200_THIN")) if (atoi(thin) == 0) c->gemm_path = 2;
     *out = c;
     return RB_OK;
 }

@@ -57,7 +57,6 @@ constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 64 /*ba
 constexpr int NUM_CONSUMER_WARPS = 8;
 constexpr int NUM_THREADS = (NUM_CONSUMER_WARPS + 4) * 32; // 2 consumer warpgroups + 1 producer warpgroup
 constexpr int GROUP_M = 8;
-constexpr int THIN_MAX = 4;    // K-major operands: tiles with <= THIN_MAX valid 16-row blocks use 16-row TMA boxes
 
 struct GemmParams {
     i64 m, n, k;
@@ -74,7 +73,6 @@ struct GemmParams {
     i64 ldp;
     int a_batched, b_batched; // 0 => operand shared by all batches (TMA batch coordinate 0)
     unsigned long long *sched; // [0] next work item - gridDim.x, [1] CTAs done (both 0 between launches)
-    int thin_loads;            // 1: edge tiles load only their valid 16-row blocks (see the producer)
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------
@@ -268,8 +266,7 @@ __device__ __forceinline__ void store_lean(const double (&acc)[2][2][4][2][2], d
 // ---- the TMA + DMMA kernel --------------------------------------------------------------------------------------
 template <bool A_K, bool B_K>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-rb_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                   const __grid_constant__ CUtensorMap tmA16, const __grid_constant__ CUtensorMap tmB16, const GemmParams p)
+rb_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p)
 {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -332,52 +329,25 @@ rb_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                                      "r"((uint32_t)(((k_end - k_begin) % BK + 7) >> 3)), "r"(grid_code), "r"(0u) : "memory");
                         first = false;
                     }
-                    // Edge tiles load only their valid 16-row blocks: the TMA unit's fill rate counts zero-filled
-                    // out-of-bounds bytes like real ones, so a 1-block-wide tile that streams two full 32 KB boxes per
-                    // stage is bound by the fill, not by its DMMAs.  MN-major operands are loaded block by block
-                    // anyway (skip the rest); K-major operands switch to 16-row boxes (second tensor map) when at
-                    // most THIN_MAX blocks are valid.  The consumers never read a block beyond mb / nbk.
-                    const bool thin_a = p.thin_loads && (A_K ? mb <= THIN_MAX : mb < BM / 16);
-                    const bool thin_b = p.thin_loads && (B_K ? nbk <= THIN_MAX : nbk < BN / 16);
-                    const uint32_t a_bytes = thin_a ? (uint32_t)mb * 4096u : (uint32_t)A_TILE_BYTES;
-                    const uint32_t b_bytes = thin_b ? (uint32_t)nbk * 4096u : (uint32_t)B_TILE_BYTES;
-                    mbar_expect_tx(full, a_bytes + b_bytes);
+                    mbar_expect_tx(full, STAGE_BYTES);
                     const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_TILE_BYTES;
                     if (A_K) {
-                        if (thin_a) {
 #pragma unroll
-                            for (int kb = 0; kb < BK / 8; ++kb)
-                                for (int blk = 0; blk < mb; ++blk)
-                                    tma_load_3d(sa + kb * (BM * 64) + blk * (16 * 64), &tmA16, full, (int)(k0 + kb * 8),
-                                                (int)(tm * BM + blk * 16), ba);
-                        } else {
-#pragma unroll
-                            for (int kb = 0; kb < BK / 8; ++kb)
-                                tma_load_3d(sa + kb * (BM * 64), &tmA, full, (int)(k0 + kb * 8), (int)(tm * BM), ba);
-                        }
+                        for (int kb = 0; kb < BK / 8; ++kb)
+                            tma_load_3d(sa + kb * (BM * 64), &tmA, full, (int)(k0 + kb * 8), (int)(tm * BM), ba);
                     } else {
-                        const int nblk = thin_a ? mb : BM / 16;
 #pragma unroll
                         for (int blk = 0; blk < BM / 16; ++blk)
-                            if (blk < nblk) tma_load_3d(sa + blk * (BK * 128), &tmA, full, (int)(tm * BM + blk * 16), (int)k0, ba);
+                            tma_load_3d(sa + blk * (BK * 128), &tmA, full, (int)(tm * BM + blk * 16), (int)k0, ba);
                     }
                     if (B_K) {
-                        if (thin_b) {
 #pragma unroll
-                            for (int kb = 0; kb < BK / 8; ++kb)
-                                for (int blk = 0; blk < nbk; ++blk)
-                                    tma_load_3d(sb + kb * (BN * 64) + blk * (16 * 64), &tmB16, full, (int)(k0 + kb * 8),
-                                                (int)(tn * BN + blk * 16), bb);
-                        } else {
-#pragma unroll
-                            for (int kb = 0; kb < BK / 8; ++kb)
-                                tma_load_3d(sb + kb * (BN * 64), &tmB, full, (int)(k0 + kb * 8), (int)(tn * BN), bb);
-                        }
+                        for (int kb = 0; kb < BK / 8; ++kb)
+                            tma_load_3d(sb + kb * (BN * 64), &tmB, full, (int)(k0 + kb * 8), (int)(tn * BN), bb);
                     } else {
-                        const int nblk = thin_b ? nbk : BN / 16;
 #pragma unroll
                         for (int blk = 0; blk < BN / 16; ++blk)
-                            if (blk < nblk) tma_load_3d(sb + blk * (BK * 128), &tmB, full, (int)(tn * BN + blk * 16), (int)k0, bb);
+                            tma_load_3d(sb + blk * (BK * 128), &tmB, full, (int)(tn * BN + blk * 16), (int)k0, bb);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
@@ -654,7 +624,7 @@ __global__ void __launch_bounds__(256) rb_scale_c_kernel(double *__restrict__ c,
 }
 
 int encode_map(rb_ctx *ctx, CUtensorMap *tm, const double *base, bool k_major, i64 rows, i64 k, i64 ld, i64 stride,
-               i64 batch, int k_major_box_rows = 128)
+               i64 batch)
 {
     // k_major: dims {k, rows, batch}, box {8, 128, 1}, no swizzle; else dims {rows, k, batch}, box {16, BK, 1}, 128B swizzle
     cuuint64_t dims[3];
@@ -667,7 +637,7 @@ int encode_map(rb_ctx *ctx, CUtensorMap *tm, const double *base, bool k_major, i
     i64 bs = (batch > 1) ? stride : ld * d1;
     if (bs <= 0) bs = ld * d1;
     strides[1] = (cuuint64_t)bs * 8;
-    if (k_major) { box[0] = 8; box[1] = (cuuint32_t)k_major_box_rows; box[2] = 1; }
+    if (k_major) { box[0] = 8; box[1] = 128; box[2] = 1; }
     else { box[0] = 16; box[1] = BK; box[2] = 1; }
     CUresult r = ctx->encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void *)base, dims, strides, box, estr,
                                    CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -696,8 +666,7 @@ bool tma_eligible(const rb_ctx *ctx, const double *p, i64 ld, i64 stride, i64 ba
 }
 
 template <bool A_K, bool B_K>
-int launch_tma(rb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmA16, const CUtensorMap &tmB16,
-               const GemmParams &p, int grid)
+int launch_tma(rb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p, int grid)
 {
     static bool attr_set[64] = {false}; // the opt-in shared-memory size is a per-device function attribute
     const int dev = ctx->device & 63;
@@ -705,7 +674,7 @@ int launch_tma(rb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, cons
         RB_CUDA(cudaFuncSetAttribute(rb_gemm_tma_kernel<A_K, B_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_set[dev] = true;
     }
-    rb_gemm_tma_kernel<A_K, B_K><<<grid, NUM_THREADS, SMEM_BYTES, ctx->stream>>>(tmA, tmB, tmA16, tmB16, p);
+    rb_gemm_tma_kernel<A_K, B_K><<<grid, NUM_THREADS, SMEM_BYTES, ctx->stream>>>(tmA, tmB, p);
     RB_LAUNCHED(ctx);
     return RB_OK;
 }
@@ -741,7 +710,7 @@ int rb_gemm_core(rb_ctx *ctx, bool ta, bool tb, i64 m, i64 n, i64 k, double alph
     // into a dense even-pitch workspace block and the TMA kernel runs on the copy: one HBM pass over the operand
     // instead of the 6x slower plain-load kernel (2049^3: 6 vs ~33 TFLOP/s).  The pad element of an odd extent lies
     // outside the tensor map's bounds, so it is never read.
-    if (ctx->gemm_path != 1 && ctx->encode_tiled && k < (1LL << 31) && (!a_ok || !b_ok) && m * n * k >= (1LL << 21)) {
+    if (ctx->gemm_path == 0 && ctx->encode_tiled && k < (1LL << 31) && (!a_ok || !b_ok) && m * n * k >= (1LL << 21)) {
         const bool same = (a == b && lda == ldb && stride_a == stride_b && a_k == b_k && m == n); // SYRK: one copy serves both
         auto extents = [&](bool is_a, i64 &d0, i64 &d1, i64 &bat) {
             const bool km = is_a ? a_k : b_k;
@@ -771,30 +740,34 @@ int rb_gemm_core(rb_ctx *ctx, bool ta, bool tb, i64 m, i64 n, i64 k, double alph
             }
         }
     }
-    bool use_tma = ctx->gemm_path != 1 && a_ok && b_ok;
+    bool use_tma = ctx->gemm_path == 0 && a_ok && b_ok;
     if (use_tma) {
-        CUtensorMap tmA, tmB, tmA16, tmB16;
+        CUtensorMap tmA, tmB;
         const bool a_batched = batch > 1 && stride_a != 0, b_batched = batch > 1 && stride_b != 0;
         RB_TRY(encode_map(ctx, &tmA, a, a_k, m, k, lda, stride_a, a_batched ? batch : 1));
         RB_TRY(encode_map(ctx, &tmB, b, b_k, n, k, ldb, stride_b, b_batched ? batch : 1));
-        // 16-row boxes for the thin edge tiles of K-major operands (only encoded when such a tile exists)
-        const bool thin = ctx->gemm_path != 2;
-        const bool a16 = thin && a_k && (m % BM) != 0 && (m % BM) <= THIN_MAX * 16;
-        const bool b16 = thin && b_k && (n % BN) != 0 && (n % BN) <= THIN_MAX * 16;
-        if (a16) RB_TRY(encode_map(ctx, &tmA16, a, true, m, k, lda, stride_a, a_batched ? batch : 1, 16)); else tmA16 = tmA;
-        if (b16) RB_TRY(encode_map(ctx, &tmB16, b, true, n, k, ldb, stride_b, b_batched ? batch : 1, 16)); else tmB16 = tmB;
         GemmParams p;
         p.m = m; p.n = n; p.k = k; p.batch = batch;
         p.tiles_m = rb_cdiv(m, BM); p.tiles_n = rb_cdiv(n, BN);
         p.tiles_per_batch = tri ? p.tiles_m * (p.tiles_m + 1) / 2 : p.tiles_m * p.tiles_n;
         i64 tiles = p.tiles_per_batch * batch;
-        // split-K when the tile count cannot fill the chip and K is deep
+        // split-K when the tiles do not fill whole waves of the chip and K is deep: pick the split count that minimises
+        // waves(s) * (k steps per item + a fixed per-item cost of ~2 steps for the descriptor / epilogue / partial
+        // store), e.g. 105 tiles x 1013 steps: s = 7 -> 5 waves of 147 steps instead of 1 wave of 1015.  The partials
+        // are reduced in a fixed order, so the result does not depend on which CTA ran which item.
         i64 splits = 1;
         i64 ksteps = rb_cdiv(k, BK);
-        if (tiles < ctx->num_sms && ksteps >= 8) {
-            splits = (2 * (i64)ctx->num_sms) / tiles;
-            if (splits > ksteps / 4) splits = ksteps / 4;
-            if (splits < 1) splits = 1;
+        if (tiles < 4 * (i64)ctx->num_sms && ksteps >= 8) {
+            i64 smax = ksteps / 4;
+            if (smax > 64) smax = 64;
+            const i64 part_elems = batch * n * ((m + 1) & ~(i64)1);
+            while (smax > 1 && smax * part_elems * 8 > ((i64)1 << 30)) --smax; // partial workspace <= 1 GB
+            i64 best_cost = -1;
+            for (i64 s = 1; s <= smax; ++s) {
+                // + the partial round trip through HBM (s writes + s reads of every tile, ~1/200 step per tile each)
+                const i64 cost = rb_cdiv(tiles * s, ctx->num_sms) * (rb_cdiv(ksteps, s) + 2) + (s > 1 ? (2 * s * tiles) / 200 : 0);
+                if (best_cost < 0 || cost < best_cost) { best_cost = cost; splits = s; }
+            }
         }
         i64 kper = rb_cdiv(ksteps, splits) * BK;
         splits = rb_cdiv(k, kper);
@@ -806,17 +779,16 @@ int rb_gemm_core(rb_ctx *ctx, bool ta, bool tb, i64 m, i64 n, i64 k, double alph
         // one of 64 self-re-arming scheduler slots per launch: launches of one context may overlap (the caller can
         // move the context between streams) without sharing a work counter
         p.sched = ctx->sched + 2 * (ctx->sched_next++ & 63);
-        p.thin_loads = thin ? 1 : 0;
         if (splits > 1) {
             void *ws;
             RB_TRY(rb_ws_reserve(ctx, 1, splits * batch * n * p.ldp * 8, &ws));
             p.partial = (double *)ws;
         }
         int grid = (int)(p.total_items < ctx->num_sms ? p.total_items : ctx->num_sms);
-        if (a_k && b_k) RB_TRY((launch_tma<true, true>(ctx, tmA, tmB, tmA16, tmB16, p, grid)));
-        else if (a_k && !b_k) RB_TRY((launch_tma<true, false>(ctx, tmA, tmB, tmA16, tmB16, p, grid)));
-        else if (!a_k && b_k) RB_TRY((launch_tma<false, true>(ctx, tmA, tmB, tmA16, tmB16, p, grid)));
-        else RB_TRY((launch_tma<false, false>(ctx, tmA, tmB, tmA16, tmB16, p, grid)));
+        if (a_k && b_k) RB_TRY((launch_tma<true, true>(ctx, tmA, tmB, p, grid)));
+        else if (a_k && !b_k) RB_TRY((launch_tma<true, false>(ctx, tmA, tmB, p, grid)));
+        else if (!a_k && b_k) RB_TRY((launch_tma<false, true>(ctx, tmA, tmB, p, grid)));
+        else RB_TRY((launch_tma<false, false>(ctx, tmA, tmB, p, grid)));
         if (splits > 1) {
             i64 total = m * n * batch;
             i64 blocks = rb_cdiv(total, 256);

@@ -340,11 +340,13 @@ extern "C" int rb_ri_iajb(rb_ctx *ctx, int np_, const double *mo_a, int64_t ldp_
     RB_REQUIRE(mo_a && mo_b, "rb_ri_iajb: mo is NULL");
     const double *xa = mo_a + A.l0 * A.ldp + A.r0 * A.ldp * A.nl, *xb = mo_b + B.l0 * B.ldp + B.r0 * B.ldp * B.nl;
     const bool same = xa == xb && A.ldp == B.ldp && A.nl == B.nl && A.ll == B.ll && A.rl == B.rl;
-    const int tri = same ? 1 : 0;
+    // SYRK form (upper-triangle tiles + mirror) only when out is overwritten: with beta != 0 the caller's out need not be
+    // symmetric, so the full product is formed like any GEMM
+    const int tri = (same && beta == 0.0) ? 1 : 0;
     const bool pa = box_is_panel(A), pb = same ? pa : box_is_panel(B);
     if (pa && pb) { // both boxes are column panels of mo: read in place
         RB_TRY(rb_gemm_core(ctx, true, false, m, n, np, 1.0, xa, A.ldp, 0, xb, B.ldp, 0, beta, out, ldo, 0, 1, tri));
-        return same ? rb_symmetrize(ctx, out, m, ldo, true) : RB_OK;
+        return tri ? rb_symmetrize(ctx, out, m, ldo, true) : RB_OK;
     }
     // gather the non-panel boxes, P-chunked so the panels fit the workspace budget (chunks accumulate with beta = 1)
     const i64 cols = (pa ? 0 : m) + ((pb || same) ? 0 : n);
@@ -370,7 +372,7 @@ extern "C" int rb_ri_iajb(rb_ctx *ctx, int np_, const double *mo_a, int64_t ldp_
         }
         RB_TRY(rb_gemm_core(ctx, true, false, m, n, pn, 1.0, a, lda, 0, b, ldb, 0, p0 == 0 ? beta : 1.0, out, ldo, 0, 1, tri));
     }
-    return same ? rb_symmetrize(ctx, out, m, ldo, true) : RB_OK;
+    return tri ? rb_symmetrize(ctx, out, m, ldo, true) : RB_OK;
 }
 
 // ---- RPA-type consumer of ri3mo: contraction over the MO pairs, output in the auxiliary basis ------------------------
@@ -440,13 +442,13 @@ extern "C" int rb_ri_mo_pq(rb_ctx *ctx, const double *mo_a, int64_t ldp_a, int n
         return rb_gemm_core(ctx, false, true, m, n, 0, 1.0, nullptr, 1, 0, nullptr, 1, 0, beta, out, ldo, 0, 1, 0);
     RB_REQUIRE(mo_a && mo_b, "rb_ri_mo_pq: mo is NULL");
     const bool same = mo_a == mo_b && ldp_a == ldp_b && np_a == np_b;
-    const int tri = same ? 1 : 0;
+    const int tri = (same && beta == 0.0) ? 1 : 0; // beta != 0: out need not be symmetric on entry -> full product
     const bool panel = box_is_panel(X);
     const double *xa = mo_a + (i64)l0 * ldp_a + (i64)r0 * ldp_a * nl, *xb = mo_b + (i64)l0 * ldp_b + (i64)r0 * ldp_b * nl;
     const bool copy_a = !panel, copy_b = !panel || w != nullptr;
     if (!copy_a && !copy_b) {
         RB_TRY(rb_gemm_core(ctx, false, true, m, n, cols, 1.0, xa, ldp_a, 0, xb, ldp_b, 0, beta, out, ldo, 0, 1, tri));
-        return same ? rb_symmetrize(ctx, out, m, ldo, true) : RB_OK;
+        return tri ? rb_symmetrize(ctx, out, m, ldo, true) : RB_OK;
     }
     // column-chunked: gathered / weighted copies of the panels live in the workspace, chunks accumulate with beta = 1
     const i64 lda_g = m + (m & 1), ldb_g = n + (n & 1);
@@ -469,5 +471,5 @@ extern "C" int rb_ri_mo_pq(rb_ctx *ctx, const double *mo_a, int64_t ldp_a, int n
         RB_TRY(mo_box_gather(ctx, xb, ldp_b, nl, ll, c0, w, gb, ldb_g, n, cn));
         RB_TRY(rb_gemm_core(ctx, false, true, m, n, cn, 1.0, a, lda, 0, b, ldb_g, 0, c0 == 0 ? beta : 1.0, out, ldo, 0, 1, tri));
     }
-    return same ? rb_symmetrize(ctx, out, m, ldo, true) : RB_OK;
+    return tri ? rb_symmetrize(ctx, out, m, ldo, true) : RB_OK;
 }

@@ -231,3 +231,18 @@ def test_host_mo_pq_mirror(rt, oracle_blas):
         t.ri_mo_pq((0, 6), (0, 8))
     with pytest.raises(rt.RestB200Error):
         t.ri_mo_pq((0, 5), (0, 8), np.ones(3))
+
+
+def test_symmetric_case_with_beta_keeps_blas_semantics(ctx, oracle_blas):
+    """moA == moB with identical boxes and beta != 0: out need not be symmetric on entry, so the result must be
+    beta*out + G element by element (no triangle is rebuilt from the other one)."""
+    np_, nl, nr = 60, 4, 6
+    box = (0, 4, 1, 5)
+    m = box[1] * box[3]
+    mo = oracle_blas.fill_linear(np_ * nl * nr, 61)
+    g = oracle_blas.ri_iajb(np_, mo, nl, box, mo, nl, box)
+    c0 = oracle_blas.fill_linear(m * m, 62)       # not symmetric
+    out = _dev(ctx, c0)
+    mod = _dev(ctx, mo)
+    ctx.ri_iajb(np_, mod, np_, nl, nr, box, mod, np_, nl, nr, box, 1.0, out, m)
+    assert_close_1e10(out.cpu().numpy(), g + c0, "iajb symmetric box, beta = 1")
