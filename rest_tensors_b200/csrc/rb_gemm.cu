@@ -751,22 +751,41 @@ int rb_gemm_core(rb_ctx *ctx, bool ta, bool tb, i64 m, i64 n, i64 k, double alph
         p.tiles_m = rb_cdiv(m, BM); p.tiles_n = rb_cdiv(n, BN);
         p.tiles_per_batch = tri ? p.tiles_m * (p.tiles_m + 1) / 2 : p.tiles_m * p.tiles_n;
         i64 tiles = p.tiles_per_batch * batch;
-        // split-K when the tiles do not fill whole waves of the chip and K is deep: pick the split count that minimises
-        // waves(s) * (k steps per item + a fixed per-item cost of ~2 steps for the descriptor / epilogue / partial
-        // store), e.g. 105 tiles x 1013 steps: s = 7 -> 5 waves of 147 steps instead of 1 wave of 1015.  The partials
-        // are reduced in a fixed order, so the result does not depend on which CTA ran which item.
+        // split-K when the tiles do not fill whole waves of the chip and K is deep.  The split count minimises a
+        // makespan estimate in k steps: rounds(s) * item cost, where an item costs k/s steps + ~2 fixed (descriptor,
+        // epilogue, partial store), rounds = ceil(items / SMs) is the number of items the busiest SM takes, and ragged
+        // edge tiles weigh what they were measured to cost (the kernel works at 16 x 16 block granularity; the
+        // dynamic scheduler back-fills cheap items) -- e.g. 105 tiles x 1013 steps: s = 7 -> 5 rounds of 147 steps
+        // instead of one of 1015; a 264^2 SYRK (3 full + 3 thin tiles): s = 49, not the s = 24 that fills one round
+        // with half-empty SMs.  Partials are reduced in a fixed order: results do not depend on the schedule.
         i64 splits = 1;
         i64 ksteps = rb_cdiv(k, BK);
         if (tiles < 4 * (i64)ctx->num_sms && ksteps >= 8) {
+            const i64 me = m - (p.tiles_m - 1) * BM, ne = n - (p.tiles_n - 1) * BN; // extents of the last tile row / column
+            const int mbe = (int)((me + 15) >> 4), nbe = (int)((ne + 15) >> 4);
+            const double wm_edge = mbe >= 5 ? 1.0 : mbe >= 3 ? 0.5 : mbe == 2 ? 0.25 : 0.125; // <= 2 block rows per warp row
+            const double wn_edge = nbe / 8.0;
+            double eff = 0.0, max_w = 0.0;
+            for (i64 tn = 0; tn < p.tiles_n; ++tn)
+                for (i64 tm = 0; tm < p.tiles_m; ++tm) {
+                    if ((tri == 1 && tm > tn) || (tri == 2 && tm < tn)) continue;
+                    double w = (tm == p.tiles_m - 1 ? wm_edge : 1.0) * (tn == p.tiles_n - 1 ? wn_edge : 1.0);
+                    if (w < 0.22) w = 0.22; // measured floor of a 1-block-wide tile
+                    eff += w;
+                    if (w > max_w) max_w = w;
+                }
+            const double avg_w = eff / (double)p.tiles_per_batch;
             i64 smax = ksteps / 4;
             if (smax > 64) smax = 64;
             const i64 part_elems = batch * n * ((m + 1) & ~(i64)1);
             while (smax > 1 && smax * part_elems * 8 > ((i64)1 << 30)) --smax; // partial workspace <= 1 GB
-            i64 best_cost = -1;
+            double best_cost = -1.0;
             for (i64 s = 1; s <= smax; ++s) {
+                const i64 rounds = rb_cdiv(tiles * s, ctx->num_sms);
+                const double busiest = rounds == 1 ? max_w : (double)rounds * avg_w;
                 // + the partial round trip through HBM (s writes + s reads of every tile, ~1/200 step per tile each)
-                const i64 cost = rb_cdiv(tiles * s, ctx->num_sms) * (rb_cdiv(ksteps, s) + 2) + (s > 1 ? (2 * s * tiles) / 200 : 0);
-                if (best_cost < 0 || cost < best_cost) { best_cost = cost; splits = s; }
+                const double cost = busiest * (double)(rb_cdiv(ksteps, s) + 2) + (s > 1 ? (double)(2 * s * tiles) / 200.0 : 0.0);
+                if (best_cost < 0.0 || cost < best_cost) { best_cost = cost; splits = s; }
             }
         }
         i64 kper = rb_cdiv(ksteps, splits) * BK;
