@@ -395,20 +395,23 @@ def run_ours(args):
     nv = nb - no
     ov = ctx.empty(nx * no * nv)
     ov_ms = []
-    for it in range(4):
+    for it in range(0 if args.no_extras else 4):
         a0, a1 = ev(), ev()
         a0.record(); sh.ao2mo(c[: nb * no], no, c[nb * no:], nv, out=ov); a1.record()
         torch.cuda.synchronize()
         if it:
             ov_ms.append(a0.elapsed_time(a1))
     ov_flop = (2.0 * no * nb * nb + 2.0 * no * nb * nv) * nx
-    occ_vir = {"ms": min(ov_ms), "tflops_per_gpu": ov_flop / (min(ov_ms) * 1e-3) / 1e12,
-               "note": "ao2mo with C_left = C_occ [nb,nocc], C_right = C_vir [nb,nb-nocc]; best of 3, per rank"}
+    occ_vir = None if args.no_extras else {
+        "ms": min(ov_ms), "tflops_per_gpu": ov_flop / (min(ov_ms) * 1e-3) / 1e12,
+        "note": "ao2mo with C_left = C_occ [nb,nocc], C_right = C_vir [nb,nb-nocc]; best of 3, per rank"}
     # ---- extra: the step after ao2mo -- (ia|jb) blocks straight from the occ-vir ri3mo above:
     #      diagonal block pair (i-block == j-block; SYRK, M(M+1)K flop) and an off-diagonal pair (GEMM, 2MNK flop);
     #      the i-block is as many occupied orbitals as keep the [M, M] block under 6 GB ----
     iajb = None
     try:
+        if args.no_extras:
+            raise RuntimeError("skipped (--no-extras)")
         li = max(1, min(no // 2 if no >= 2 else 1, int(((6 << 30) / 8) ** 0.5) // max(nv, 1)))
         if (6 << 30) / 8 >= float(no * nv) ** 2:
             li = no
@@ -526,6 +529,8 @@ def main():
     ap.add_argument("--config", default="C", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-numa", action="store_true", help="e2e leg: do not bind the rank to its GPU's NUMA node")
+    ap.add_argument("--no-extras", action="store_true", help="skip the untimed extras (occ-vir ao2mo, ri3mo consumers): "
+                    "the ncu launch list then holds the timed step's kernels only")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-pointer e2e leg (e.g. config D: 2 x 15.5 GB pinned per rank)")
     args = ap.parse_args()
     if args.impl == "reference":

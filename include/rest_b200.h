@@ -67,6 +67,17 @@ int rb_host_free_pinned(void *p);
 int rb_memcpy_h2d(rb_ctx *ctx, void *dst, const void *src, int64_t bytes); /* async on the ctx stream */
 int rb_memcpy_d2h(rb_ctx *ctx, void *dst, const void *src, int64_t bytes);
 
+/* Peer memory over NVLink / NVSwitch.  Every rb_* device entry point accepts operands that live in another GPU's HBM
+ * once the mapping exists (the TMA tensor maps are encoded over plain global addresses):
+ *   same process, several devices : rb_peer_enable(ctx, peer_device) once per reading context;
+ *   one process per GPU           : the owner exports a block obtained from rb_dev_alloc as a 64-byte handle, every
+ *                                   reader opens it (rb_ipc_open enables peer access lazily) and closes it when done.
+ * Used by the RPA-type consumer rb_ri_mo_pq, whose B operand is another rank's row block of ri3mo. */
+int rb_peer_enable(rb_ctx *ctx, int peer_device);
+int rb_ipc_export(rb_ctx *ctx, void *dev_ptr, unsigned char handle[64]);
+int rb_ipc_open(rb_ctx *ctx, const unsigned char handle[64], void **out);
+int rb_ipc_close(rb_ctx *ctx, void *ptr);
+
 /* ---- (1) COMPAT: reference src/external_libs/ffi_restmatr.rs:4-62 == restmatr.f90 ---------------------- */
 
 /* ffi_restmatr.rs:5-11 / restmatr.f90:158-194:

@@ -48,6 +48,10 @@ SIGNATURES = {
     "rb_dev_free": (C.c_int, [c_vp, c_vp]),
     "rb_host_alloc_pinned": (C.c_int, [c_i64, C.POINTER(c_vp)]),
     "rb_host_free_pinned": (C.c_int, [c_vp]),
+    "rb_peer_enable": (C.c_int, [c_vp, C.c_int]),
+    "rb_ipc_export": (C.c_int, [c_vp, c_vp, c_vp]),
+    "rb_ipc_open": (C.c_int, [c_vp, c_vp, C.POINTER(c_vp)]),
+    "rb_ipc_close": (C.c_int, [c_vp, c_vp]),
     "rb_memcpy_h2d": (C.c_int, [c_vp, c_vp, c_vp, c_i64]),
     "rb_memcpy_d2h": (C.c_int, [c_vp, c_vp, c_vp, c_i64]),
     # compat (Fortran ABI, everything by pointer)

@@ -146,6 +146,58 @@ extern "C" int rb_dev_free(rb_ctx *ctx, void *p)
     if (p) RB_CUDA(cudaFree(p));
     return RB_OK;
 }
+// ---- peer memory (NVLink / NVSwitch) -----------------------------------------------------------------------------
+// Kernels of this library take plain global pointers, and TMA tensor maps are encoded over plain global addresses, so
+// an operand may live in another GPU's HBM once the mapping exists: same process -> rb_peer_enable; another process
+// (one rank per GPU) -> export the cudaMalloc'd block as a 64-byte handle and open it on the reading rank.
+extern "C" int rb_peer_enable(rb_ctx *ctx, int peer_device)
+{
+    RB_REQUIRE(ctx, "rb_peer_enable: ctx is NULL");
+    if (peer_device == ctx->device) return RB_OK;
+    RB_CUDA(cudaSetDevice(ctx->device));
+    int can = 0;
+    RB_CUDA(cudaDeviceCanAccessPeer(&can, ctx->device, peer_device));
+    if (!can) {
+        rb_set_error("rb_peer_enable: device %d cannot access device %d", ctx->device, peer_device);
+        return RB_ERR_UNSUPPORTED;
+    }
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return RB_OK; }
+    RB_CUDA(e);
+    return RB_OK;
+}
+
+extern "C" int rb_ipc_export(rb_ctx *ctx, void *dev_ptr, unsigned char handle[64])
+{
+    RB_REQUIRE(ctx && dev_ptr && handle, "rb_ipc_export: bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    RB_CUDA(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    RB_CUDA(cudaIpcGetMemHandle(&h, dev_ptr));
+    memcpy(handle, &h, 64);
+    return RB_OK;
+}
+
+extern "C" int rb_ipc_open(rb_ctx *ctx, const unsigned char handle[64], void **out)
+{
+    RB_REQUIRE(ctx && handle && out, "rb_ipc_open: bad arguments");
+    RB_CUDA(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    *out = nullptr;
+    RB_CUDA(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+    return RB_OK;
+}
+
+extern "C" int rb_ipc_close(rb_ctx *ctx, void *ptr)
+{
+    RB_REQUIRE(ctx, "rb_ipc_close: ctx is NULL");
+    if (!ptr) return RB_OK;
+    RB_CUDA(cudaSetDevice(ctx->device));
+    RB_CUDA(cudaIpcCloseMemHandle(ptr));
+    return RB_OK;
+}
+
 extern "C" int rb_host_alloc_pinned(int64_t bytes, void **out)
 {
     RB_REQUIRE(out && bytes >= 0, "rb_host_alloc_pinned: bad arguments");

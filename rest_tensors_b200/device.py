@@ -24,8 +24,13 @@ def shard_range(naux: int, rank: int, world: int) -> Tuple[int, int]:
     return (rank * naux) // world, ((rank + 1) * naux) // world
 
 
-def _p(t: Optional[torch.Tensor]) -> C.c_void_p:
-    return C.c_void_p(0 if t is None else t.data_ptr())
+def _p(t) -> C.c_void_p:
+    """device pointer of a tensor (None -> NULL); a raw integer address (e.g. an opened peer block) passes through"""
+    if t is None:
+        return C.c_void_p(0)
+    if isinstance(t, int):
+        return C.c_void_p(t)
+    return C.c_void_p(t.data_ptr())
 
 
 class Context:
@@ -247,12 +252,17 @@ class ShardedRI:
         return out
 
     def mo_pq(self, mo: torch.Tensor, nl: int, nr: int, box, w: Optional[torch.Tensor] = None,
-              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+              out: Optional[torch.Tensor] = None, exchange: str = "auto") -> torch.Tensor:
         """RPA-type block row out[P_local, Q] = sum_{(l,r) in box} w[l,r] mo[P,l,r] mo[Q,l,r] over ALL Q in [0, naux):
         the one exchange step on this side of the path -- every rank needs every other rank's rows of ri3mo for the
-        box.  The row blocks travel by all-gather (NCCL over NVLink; shards may differ by one row, so the pieces are
-        padded to the longest shard) and each received block feeds one 'N','T' GEMM into its column range of `out`
-        ([nx_local, naux], column-major).  world == 1: one symmetric GEMM, no communication."""
+        box.  out is [nx_local, naux], column-major.  world == 1: one symmetric GEMM, no communication.
+
+        exchange = "p2p" (default on GPUs): each rank gathers its box into a panel it exposes to its peers (CUDA IPC
+        over NVLink / NVSwitch) and runs one 'N','T' GEMM per peer whose B operand is the PEER's panel, read in place:
+        the TMA loads of the GEMM pull the remote tiles while the DMMAs of earlier tiles run, so the all-gather and
+        the GEMM are one kernel and no staging copy exists (with weights, the weighted copy of the B panel is the
+        pull).  exchange = "allgather": NCCL all-gather of the panels, then one GEMM per received block (also the
+        gloo / CPU host-logic tier)."""
         if out is None:
             out = self.ctx.empty(self.nx * self.naux)
         if self.world == 1:
@@ -261,6 +271,23 @@ class ShardedRI:
         import torch.distributed as dist
         l0, ll, r0, rl = box
         nx_max = -(-self.naux // self.world)
+        nx_max += nx_max & 1                        # even pitch: TMA-describable panels
+        if exchange == "auto":
+            exchange = "p2p" if mo.is_cuda else "allgather"
+        if exchange == "p2p":
+            panels = self._peer_panels(nx_max * ll * rl * 8)
+            check(lib.rb_copy_rr(self.ctx.h, self.nx, ll, rl, _p(mo), self.nx, nl, nr, 0, l0, r0, _p(panels.local), nx_max,
+                                 ll, rl, 0, 0, 0), "rb_copy_rr")
+            self.ctx.sync()
+            dist.barrier()                          # every rank's panel is complete and visible
+            for i in range(self.world):             # start with the own block, then walk the ring: spreads NVLink load
+                s = (self.rank + i) % self.world
+                q_lo, q_hi = shard_range(self.naux, s, self.world)
+                self.ctx.ri_mo_pq(panels.ptrs[self.rank], nx_max, self.nx, panels.ptrs[s], nx_max, q_hi - q_lo, ll, rl,
+                                  (0, ll, 0, rl), w, 0.0, out[q_lo * self.nx:], self.nx)
+            self.ctx.sync()
+            dist.barrier()                          # nobody rewrites its panel while a peer still reads it
+            return out
         mine = torch.zeros(nx_max * ll * rl, dtype=mo.dtype, device=mo.device)
         if mo.is_cuda:  # gather this rank's box columns into a dense [nx_max, ll*rl] panel with our own copy kernel
             check(lib.rb_copy_rr(self.ctx.h, self.nx, ll, rl, _p(mo), self.nx, nl, nr, 0, l0, r0, _p(mine), nx_max, ll, rl,
@@ -274,9 +301,54 @@ class ShardedRI:
             self._mo_pq_block(mine, piece, nx_max, q_hi - q_lo, ll, rl, w, out, q_lo)
         return out
 
+    def _peer_panels(self, nbytes: int) -> "PeerBlocks":
+        cur = getattr(self, "_panels", None)
+        if cur is None or cur.nbytes < nbytes:      # same size on every rank, so all ranks re-create together
+            if cur is not None:
+                cur.close()
+            self._panels = PeerBlocks(self.ctx, nbytes, self.rank, self.world)
+        return self._panels
+
     def _mo_pq_block(self, mine, piece, ldp, nq, ll, rl, w, out, q_lo) -> None:
         self.ctx.ri_mo_pq(mine, ldp, self.nx, piece, ldp, nq, ll, rl, (0, ll, 0, rl), w, 0.0,
                           out[q_lo * self.nx:], self.nx)
+
+
+class PeerBlocks:
+    """One block of `nbytes` per rank, mapped into every rank's address space: the owner allocates it with
+    rb_dev_alloc (plain cudaMalloc, exportable), exports it as a 64-byte CUDA IPC handle, the handles travel through
+    the process group and every rank opens its peers' blocks.  ptrs[s] is the address of rank s's block as seen from
+    this rank (own block: the local pointer); any rb_* device entry point can read or write it over NVLink."""
+
+    def __init__(self, ctx: Context, nbytes: int, rank: int, world: int):
+        import torch.distributed as dist
+        self.ctx, self.nbytes, self.rank, self.world = ctx, int(nbytes), rank, world
+        base = C.c_void_p()
+        check(lib.rb_dev_alloc(ctx.h, self.nbytes, C.byref(base)), "rb_dev_alloc")
+        self.local = int(base.value)
+        handle = (C.c_ubyte * 64)()
+        check(lib.rb_ipc_export(ctx.h, C.c_void_p(self.local), handle), "rb_ipc_export")
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle))
+        self.ptrs = []
+        for s, hb in enumerate(handles):
+            if s == rank:
+                self.ptrs.append(self.local)
+                continue
+            p = C.c_void_p()
+            check(lib.rb_ipc_open(ctx.h, (C.c_ubyte * 64).from_buffer_copy(hb), C.byref(p)), "rb_ipc_open")
+            self.ptrs.append(int(p.value))
+
+    def close(self) -> None:
+        import torch.distributed as dist
+        self.ctx.sync()
+        dist.barrier()                              # no peer is still reading
+        for s, p in enumerate(self.ptrs):
+            if s != self.rank and p:
+                check(lib.rb_ipc_close(self.ctx.h, C.c_void_p(p)), "rb_ipc_close")
+        dist.barrier()                              # every mapping is gone before the owner frees
+        check(lib.rb_dev_free(self.ctx.h, C.c_void_p(self.local)), "rb_dev_free")
+        self.ptrs, self.local = [], 0
 
 
 def all_reduce_sum(t: torch.Tensor, world: int) -> None:

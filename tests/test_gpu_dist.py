@@ -40,7 +40,10 @@ def _worker(rank, world, port, nb, naux, no, ret):
         box_a, box_b = (0, no, no, nb - no), (1, no - 1, no, nb - no)
         g = sh.iajb(mo_local, nb, nb, box_a, box_b)
         wts = o.fill_linear(box_a[1] * box_a[3], 7)
-        pq = sh.mo_pq(mo_local, nb, nb, box_a, dev(wts))
+        pq = sh.mo_pq(mo_local, nb, nb, box_a, dev(wts))                              # peer panels over NVLink (default)
+        pq_ag = sh.mo_pq(mo_local, nb, nb, box_a, dev(wts), exchange="allgather")      # NCCL all-gather of the panels
+        pq_nw = sh.mo_pq(mo_local, nb, nb, box_a, None)                               # no weights: TMA reads the peer panel
+        pq_nw_ag = sh.mo_pq(mo_local, nb, nb, box_a, None, exchange="allgather")
         torch.cuda.synchronize()
         ri = o.fill_ri3ao_symm(nb, 0, naux)
         d_ref = o.ri_dp(ri, dm, nb, naux)
@@ -53,7 +56,9 @@ def _worker(rank, world, port, nb, naux, no, ret):
         pq_ref = o.ri_mo_pq(mo_all, naux, mo_all, naux, nb, box_a, wts).reshape((naux, naux), order="F")[sh.p_lo:sh.p_hi]
         errs = [err(d_full.cpu().numpy(), d_ref), err(j.cpu().numpy(), o.ri_j(ri, d_ref, nb, naux)),
                 err(k.cpu().numpy(), o.ri_k(ri, ct, nb, no, naux)), err(mo_local.cpu().numpy(), mo_ref),
-                err(g.cpu().numpy(), g_ref), err(pq.cpu().numpy(), pq_ref.reshape(-1, order="F"))]
+                err(g.cpu().numpy(), g_ref), err(pq.cpu().numpy(), pq_ref.reshape(-1, order="F")),
+                err(pq_ag.cpu().numpy(), pq_ref.reshape(-1, order="F")),
+                0.0 if torch.equal(pq_nw, pq_nw_ag) else 1.0]   # both exchanges feed the same GEMMs: bitwise equal
         ret.put((rank, max(errs)))
         dist.barrier()
     finally:
@@ -103,3 +108,27 @@ def test_one_process_two_devices():
         ref = mo_ref[shards[r].p_lo:shards[r].p_hi].reshape(-1, order="F")
         got = outs[r].cpu().numpy()
         assert float(np.max(np.abs(got - ref)) / np.max(np.abs(ref))) <= 1e-10, f"device {r}"
+
+
+def test_one_process_peer_operand():
+    """rb_peer_enable: a kernel of device 0's context reads an operand that lives in device 1's HBM (TMA loads over
+    NVLink) and gives bitwise the result of the same call on a local copy."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sys.path.insert(0, ROOT)
+    from rest_tensors_b200.device import Context
+    from rest_tensors_b200._lib import lib, check
+    c0, c1 = Context(0), Context(1)
+    check(lib.rb_peer_enable(c0.h, 1), "rb_peer_enable")
+    m, n, k = 200, 136, 2000
+    with torch.cuda.device(1):
+        b_remote = c1.empty(n * k); c1.fill_linear(b_remote, n * k, 5, 0, 1.0)
+        torch.cuda.synchronize(1)
+    with torch.cuda.device(0):
+        a = c0.empty(m * k); c0.fill_linear(a, m * k, 4, 0, 1.0)
+        b_local = c0.empty(n * k); c0.fill_linear(b_local, n * k, 5, 0, 1.0)
+        o1, o2 = c0.empty(m * n), c0.empty(m * n)
+        c0.dgemm("N", "T", m, n, k, 1.0, a, m, b_local, n, 0.0, o1, m)
+        c0.dgemm("N", "T", m, n, k, 1.0, a, m, b_remote, n, 0.0, o2, m)
+        torch.cuda.synchronize(0)
+        assert torch.equal(o1, o2)
