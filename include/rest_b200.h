@@ -220,6 +220,14 @@ int rb_ri_iajb(rb_ctx *ctx, int np, const double *mo_a, int64_t ldp_a, int nl_a,
 int rb_ri_mo_pq(rb_ctx *ctx, const double *mo_a, int64_t ldp_a, int np_a, const double *mo_b, int64_t ldp_b, int np_b,
                 int nl, int nr, int l0, int ll, int r0, int rl, const double *w, double beta, double *out, int64_t ldo);
 
+/* P-sharded form of rb_ri_mo_pq, all-gather -> GEMM as ONE pipeline over peer memory: panels[s] = rank s's dense box
+ * panel [np[s] rows, pitch ld, cols columns] as seen from this rank (rb_ipc_open mapping, or a local pointer for
+ * s == rank); out[:, q_off[s] .. q_off[s] + np[s]) = sum_c w[c] * own[:, c] * panels[s][:, c] for every s.  The peers'
+ * panels are pulled by the copy engines on a second stream, one peer ahead of the DMMA GEMM that consumes them, so the
+ * NVLink transfer overlaps the math.  Callers synchronise the ranks before (panels complete) and after (panels free). */
+int rb_ri_mo_pq_peers(rb_ctx *ctx, int rank, int world, const double *const *panels, int64_t ld, const int *np,
+                      int64_t cols, const double *w, double *out, int64_t ldo, const int64_t *q_off);
+
 /* einsum helpers (matrix_blas_lapack.rs:1273-1387, matrix/einsum.rs) on device buffers:
  * "ij,j->ij" and "i,j->ij" are one multiply per element (bit-exact), "ip,ip->p" is a column dot (1e-10). */
 int rb_einsum_ij_j(rb_ctx *ctx, const double *a, int64_t lda, const double *b, double *out, int64_t ldo, int64_t ni,

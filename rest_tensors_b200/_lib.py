@@ -109,6 +109,8 @@ SIGNATURES = {
     "rb_ri_mo_pq": (C.c_int, [c_vp, c_vp, c_i64, C.c_int, c_vp, c_i64, C.c_int] + [C.c_int] * 6
                     + [c_vp, C.c_double, c_vp, c_i64]),
     "rb_host_ri_mo_pq": (C.c_int, [c_vp] + [C.c_int] * 7 + [c_vp, c_vp]),
+    "rb_ri_mo_pq_peers": (C.c_int, [c_vp, C.c_int, C.c_int, C.POINTER(c_vp), c_i64, c_ip, c_i64, c_vp, c_vp, c_i64,
+                                    C.POINTER(c_i64)]),
     "rb_special_dgemm_01": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                       c_vp, c_i64, C.c_int, C.c_double, C.c_double]),
     "rb_einsum_ij_j": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_i64]),

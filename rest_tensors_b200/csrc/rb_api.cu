@@ -71,6 +71,8 @@ extern "C" int rb_ctx_destroy(rb_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     for (int s = 0; s < 4; ++s) if (ctx->ws[s]) cudaFree(ctx->ws[s]);
     if (ctx->sched) cudaFree(ctx->sched);
+    for (int i = 0; i < 5; ++i) if (ctx->aux_ev[i]) cudaEventDestroy(ctx->aux_ev[i]);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);

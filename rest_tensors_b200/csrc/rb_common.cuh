@@ -55,6 +55,8 @@ struct rb_ctx {
     int gemm_path = 0;
     rb_encode_tiled_fn encode_tiled = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t aux_stream = nullptr;   // copy stream of the peer pipeline (rb_ri_mo_pq_peers), created on first use
+    cudaEvent_t aux_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}; // [0] fork, [1..2] pulled, [3..4] buffer free
     unsigned long long *sched = nullptr; // GEMM tile-scheduler slots (64 x 2 words on the device), zero between launches
     unsigned sched_next = 0;             // slot of the next GEMM launch (round-robin)
 };

@@ -473,3 +473,76 @@ extern "C" int rb_ri_mo_pq(rb_ctx *ctx, const double *mo_a, int64_t ldp_a, int n
     }
     return tri ? rb_symmetrize(ctx, out, m, ldo, true) : RB_OK;
 }
+
+// ---- all-gather -> GEMM as one pipeline over peer memory ---------------------------------------------------------------
+// P-sharded form of the RPA-type consumer: rank r owns rows P_r of the box panel X = [naux, cols] and needs
+//     out[P_r, Q_s] = sum_c w_c X[P_r, c] X[Q_s, c]      for every rank s.
+// panels[s] is rank s's dense panel [np[s] rows, pitch ld, cols columns] as seen from this rank (a CUDA IPC mapping of
+// the peer's HBM, or a local pointer for s == rank).  Measured on 2 x B200 (tools/peer_probe.py): a GEMM whose TMA loads
+// read the peer panel in place re-reads it once per tile row over NVLink (850 rows: 10.7 TFLOP/s vs 32.1 local), so the
+// panels are pulled instead -- by the copy engines, on a second stream, one peer ahead of the DMMA GEMM that consumes
+// them (double-buffered): NVLink transfer of peer s+1 overlaps the math on peer s, the own block is computed while the
+// first pull is in flight, and no SM time goes into communication.  The weights are folded into a scaled copy of the
+// OWN panel (A side), so the pulled panels are used as they are.
+extern "C" int rb_ri_mo_pq_peers(rb_ctx *ctx, int rank, int world, const double *const *panels, int64_t ld, const int *np,
+                                 int64_t cols, const double *w, double *out, int64_t ldo, const int64_t *q_off)
+{
+    RB_REQUIRE(ctx && panels && np && q_off, "rb_ri_mo_pq_peers: NULL argument");
+    RB_REQUIRE(world >= 1 && rank >= 0 && rank < world && cols >= 0, "rb_ri_mo_pq_peers: bad rank / world / cols");
+    const i64 m = np[rank];
+    RB_REQUIRE(m >= 0 && ldo >= m, "rb_ri_mo_pq_peers: ldo (%lld) < local rows (%lld)", (long long)ldo, (long long)m);
+    i64 np_max = 0;
+    for (int s = 0; s < world; ++s) {
+        RB_REQUIRE(np[s] >= 0 && np[s] <= ld && q_off[s] >= 0, "rb_ri_mo_pq_peers: bad row count / offset of rank %d", s);
+        RB_REQUIRE(np[s] == 0 || cols == 0 || panels[s], "rb_ri_mo_pq_peers: panel of rank %d is NULL", s);
+        if (np[s] > np_max) np_max = np[s];
+    }
+    if (m == 0) return RB_OK;
+    RB_REQUIRE(out, "rb_ri_mo_pq_peers: out is NULL");
+    RB_CUDA(cudaSetDevice(ctx->device));
+    if (cols == 0) {
+        for (int s = 0; s < world; ++s)
+            RB_TRY(rb_gemm_core(ctx, false, true, m, np[s], 0, 1.0, nullptr, 1, 0, nullptr, 1, 0, 0.0, out + q_off[s] * ldo, ldo, 0, 1, 0));
+        return RB_OK;
+    }
+    if (!ctx->aux_stream) {
+        RB_CUDA(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 5; ++i) RB_CUDA(cudaEventCreateWithFlags(&ctx->aux_ev[i], cudaEventDisableTiming));
+    }
+    const i64 panel_elems = ld * cols;
+    const int remote = world - 1;
+    void *ws;
+    RB_TRY(rb_ws_reserve(ctx, 0, (panel_elems * ((w ? 1 : 0) + (remote > 1 ? 2 : remote))) * 8 + 16, &ws));
+    double *aw = (double *)ws;                                    // own panel * diag(w)
+    double *buf[2] = {aw + (w ? panel_elems : 0), aw + (w ? panel_elems : 0) + panel_elems};
+    const double *a = panels[rank];
+    // the copy stream starts after everything already queued on the main stream (workspace reuse by earlier calls)
+    RB_CUDA(cudaEventRecord(ctx->aux_ev[0], ctx->stream));
+    RB_CUDA(cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_ev[0], 0));
+    auto peer_of = [&](int i) { return (rank + 1 + i) % world; };  // ring order: spreads the NVLink load over the switch
+    auto pull = [&](int i) -> int {
+        const int s = peer_of(i), b = i & 1;
+        if (i >= 2) RB_CUDA(cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_ev[3 + b], 0)); // the GEMM that read buf[b] is done
+        if (np[s] > 0) // the whole panel as one run (its <= 2 pad rows per column travel too and are never read)
+            RB_CUDA(cudaMemcpyAsync(buf[b], panels[s], (size_t)panel_elems * 8, cudaMemcpyDefault, ctx->aux_stream));
+        RB_CUDA(cudaEventRecord(ctx->aux_ev[1 + b], ctx->aux_stream));
+        return RB_OK;
+    };
+    if (remote > 0) RB_TRY(pull(0));
+    if (w) { RB_TRY(mo_box_gather(ctx, a, ld, 1, 1, 0, w, aw, ld, m, cols)); a = aw; }
+    // own block while the first pull is in flight; unweighted: upper triangle + mirror (bitwise symmetric)
+    {
+        const int tri = w ? 0 : 1;
+        RB_TRY(rb_gemm_core(ctx, false, true, m, m, cols, 1.0, a, ld, 0, panels[rank], ld, 0, 0.0, out + q_off[rank] * ldo, ldo, 0, 1, tri));
+        if (tri) RB_TRY(rb_symmetrize(ctx, out + q_off[rank] * ldo, m, ldo, true));
+    }
+    for (int i = 0; i < remote; ++i) {
+        const int s = peer_of(i), b = i & 1;
+        if (i + 1 < remote) RB_TRY(pull(i + 1));
+        RB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->aux_ev[1 + b], 0));
+        if (np[s] > 0)
+            RB_TRY(rb_gemm_core(ctx, false, true, m, np[s], cols, 1.0, a, ld, 0, buf[b], ld, 0, 0.0, out + q_off[s] * ldo, ldo, 0, 1, 0));
+        RB_CUDA(cudaEventRecord(ctx->aux_ev[3 + b], ctx->stream));
+    }
+    return RB_OK;
+}

@@ -258,11 +258,10 @@ class ShardedRI:
         box.  out is [nx_local, naux], column-major.  world == 1: one symmetric GEMM, no communication.
 
         exchange = "p2p" (default on GPUs): each rank gathers its box into a panel it exposes to its peers (CUDA IPC
-        over NVLink / NVSwitch) and runs one 'N','T' GEMM per peer whose B operand is the PEER's panel, read in place:
-        the TMA loads of the GEMM pull the remote tiles while the DMMAs of earlier tiles run, so the all-gather and
-        the GEMM are one kernel and no staging copy exists (with weights, the weighted copy of the B panel is the
-        pull).  exchange = "allgather": NCCL all-gather of the panels, then one GEMM per received block (also the
-        gloo / CPU host-logic tier)."""
+        over NVLink / NVSwitch) and rb_ri_mo_pq_peers runs the all-gather and the GEMMs as one pipeline: the copy
+        engines pull peer s+1's panel on a second stream while the DMMA GEMM on peer s's panel runs.
+        exchange = "allgather": NCCL all-gather of the panels, then one GEMM per received block (also the gloo / CPU
+        host-logic tier)."""
         if out is None:
             out = self.ctx.empty(self.nx * self.naux)
         if self.world == 1:
@@ -280,11 +279,12 @@ class ShardedRI:
                                  ll, rl, 0, 0, 0), "rb_copy_rr")
             self.ctx.sync()
             dist.barrier()                          # every rank's panel is complete and visible
-            for i in range(self.world):             # start with the own block, then walk the ring: spreads NVLink load
-                s = (self.rank + i) % self.world
-                q_lo, q_hi = shard_range(self.naux, s, self.world)
-                self.ctx.ri_mo_pq(panels.ptrs[self.rank], nx_max, self.nx, panels.ptrs[s], nx_max, q_hi - q_lo, ll, rl,
-                                  (0, ll, 0, rl), w, 0.0, out[q_lo * self.nx:], self.nx)
+            ranges = [shard_range(self.naux, s, self.world) for s in range(self.world)]
+            ptrs = (C.c_void_p * self.world)(*panels.ptrs)
+            rows = (C.c_int * self.world)(*[hi - lo for lo, hi in ranges])
+            offs = (C.c_int64 * self.world)(*[lo for lo, _ in ranges])
+            check(lib.rb_ri_mo_pq_peers(self.ctx.h, self.rank, self.world, ptrs, nx_max, rows, ll * rl, _p(w), _p(out),
+                                        self.nx, offs), "rb_ri_mo_pq_peers")
             self.ctx.sync()
             dist.barrier()                          # nobody rewrites its panel while a peer still reads it
             return out

@@ -54,11 +54,13 @@ def _worker(rank, world, port, nb, naux, no, ret):
         mo_ref = mo_all.reshape((naux, nb, nb), order="F")[sh.p_lo:sh.p_hi].reshape(-1, order="F")
         g_ref = o.ri_iajb(naux, mo_all, nb, box_a, mo_all, nb, box_b)
         pq_ref = o.ri_mo_pq(mo_all, naux, mo_all, naux, nb, box_a, wts).reshape((naux, naux), order="F")[sh.p_lo:sh.p_hi]
+        pq_nw_ref = o.ri_mo_pq(mo_all, naux, mo_all, naux, nb, box_a, None).reshape((naux, naux), order="F")[sh.p_lo:sh.p_hi]
         errs = [err(d_full.cpu().numpy(), d_ref), err(j.cpu().numpy(), o.ri_j(ri, d_ref, nb, naux)),
                 err(k.cpu().numpy(), o.ri_k(ri, ct, nb, no, naux)), err(mo_local.cpu().numpy(), mo_ref),
                 err(g.cpu().numpy(), g_ref), err(pq.cpu().numpy(), pq_ref.reshape(-1, order="F")),
                 err(pq_ag.cpu().numpy(), pq_ref.reshape(-1, order="F")),
-                0.0 if torch.equal(pq_nw, pq_nw_ag) else 1.0]   # both exchanges feed the same GEMMs: bitwise equal
+                err(pq_nw.cpu().numpy(), pq_nw_ref.reshape(-1, order="F")),
+                err(pq_nw_ag.cpu().numpy(), pq_nw_ref.reshape(-1, order="F"))]
         ret.put((rank, max(errs)))
         dist.barrier()
     finally:
