@@ -530,12 +530,10 @@ extern "C" int rb_ri_mo_pq_peers(rb_ctx *ctx, int rank, int world, const double 
     };
     if (remote > 0) RB_TRY(pull(0));
     if (w) { RB_TRY(mo_box_gather(ctx, a, ld, 1, 1, 0, w, aw, ld, m, cols)); a = aw; }
-    // own block while the first pull is in flight; unweighted: upper triangle + mirror (bitwise symmetric)
-    {
-        const int tri = w ? 0 : 1;
-        RB_TRY(rb_gemm_core(ctx, false, true, m, m, cols, 1.0, a, ld, 0, panels[rank], ld, 0, 0.0, out + q_off[rank] * ldo, ldo, 0, 1, tri));
-        if (tri) RB_TRY(rb_symmetrize(ctx, out + q_off[rank] * ldo, m, ldo, true));
-    }
+    // own block while the first pull is in flight: sum_c w_c x_c x_c^T is symmetric with or without weights, so only the
+    // upper triangle's tiles are computed and mirrored
+    RB_TRY(rb_gemm_core(ctx, false, true, m, m, cols, 1.0, a, ld, 0, panels[rank], ld, 0, 0.0, out + q_off[rank] * ldo, ldo, 0, 1, 1));
+    RB_TRY(rb_symmetrize(ctx, out + q_off[rank] * ldo, m, ldo, true));
     for (int i = 0; i < remote; ++i) {
         const int s = peer_of(i), b = i & 1;
         if (i + 1 < remote) RB_TRY(pull(i + 1));

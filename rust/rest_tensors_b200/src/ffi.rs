@@ -62,6 +62,13 @@ extern "C" {
     pub fn rb_ri_iajb(ctx: *mut RbCtx, np: c_int, mo_a: *const c_double, ldp_a: i64, nl_a: c_int, nr_a: c_int, l0a: c_int,
                       lla: c_int, r0a: c_int, rla: c_int, mo_b: *const c_double, ldp_b: i64, nl_b: c_int, nr_b: c_int,
                       l0b: c_int, llb: c_int, r0b: c_int, rlb: c_int, beta: c_double, out: *mut c_double, ldo: i64) -> c_int;
+    pub fn rb_peer_enable(ctx: *mut RbCtx, peer_device: c_int) -> c_int;
+    pub fn rb_ipc_export(ctx: *mut RbCtx, dev_ptr: *mut std::ffi::c_void, handle: *mut u8) -> c_int;
+    pub fn rb_ipc_open(ctx: *mut RbCtx, handle: *const u8, out: *mut *mut std::ffi::c_void) -> c_int;
+    pub fn rb_ipc_close(ctx: *mut RbCtx, ptr: *mut std::ffi::c_void) -> c_int;
+    pub fn rb_ri_mo_pq_peers(ctx: *mut RbCtx, rank: c_int, world: c_int, panels: *const *const c_double, ld: i64,
+                             np: *const c_int, cols: i64, w: *const c_double, out: *mut c_double, ldo: i64,
+                             q_off: *const i64) -> c_int;
     pub fn rb_ri_mo_pq(ctx: *mut RbCtx, mo_a: *const c_double, ldp_a: i64, np_a: c_int, mo_b: *const c_double, ldp_b: i64,
                        np_b: c_int, nl: c_int, nr: c_int, l0: c_int, ll: c_int, r0: c_int, rl: c_int, w: *const c_double,
                        beta: c_double, out: *mut c_double, ldo: i64) -> c_int;

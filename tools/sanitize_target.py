@@ -36,5 +36,16 @@ for w in range(4):
     ctx.ri_transpose(t, 30, 22, 14, w, u)
 ctx.copy_rr(10, 12, 5, t, 30, 22, 14, 3, 2, 1, u, 30, 22, 14, 0, 4, 6)
 ctx.self_scaled_add(g, f, 0.5, n * n)
+# consumers of ri3mo: in-place panels, gathered boxes, weights, symmetric + general, beta accumulation
+mo3 = ctx.empty(50 * 5 * 8); ctx.fill_linear(mo3, 50 * 5 * 8, 6, 0, 1.0)
+wv = ctx.empty(5 * 8); ctx.fill_linear(wv, 40, 7, 0, 1.0)
+gg = ctx.empty(40 * 40); gg.zero_()
+ctx.ri_iajb(50, mo3, 50, 5, 8, (0, 5, 0, 8), mo3, 50, 5, 8, (0, 5, 0, 8), 0.0, gg, 40)
+ctx.ri_iajb(50, mo3, 50, 5, 8, (1, 3, 2, 5), mo3, 50, 5, 8, (0, 5, 1, 6), 1.0, gg, 40)
+ctx.ri_iajb(49, mo3[1:], 50, 5, 8, (1, 3, 2, 5), mo3[1:], 50, 5, 8, (1, 3, 2, 5), 0.0, gg, 40)
+pp = ctx.empty(50 * 50)
+ctx.ri_mo_pq(mo3, 50, 50, mo3, 50, 50, 5, 8, (0, 5, 0, 8), None, 0.0, pp, 50)
+ctx.ri_mo_pq(mo3, 50, 50, mo3, 50, 50, 5, 8, (1, 3, 2, 5), wv, 0.0, pp, 50)
+ctx.ri_mo_pq(mo3, 50, 20, mo3[20:], 50, 30, 5, 8, (0, 5, 0, 8), wv, 1.0, pp, 50)
 torch.cuda.synchronize()
 print("sanitize target ok")
