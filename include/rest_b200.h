@@ -70,11 +70,13 @@ int rb_memcpy_d2h(rb_ctx *ctx, void *dst, const void *src, int64_t bytes);
 /* Peer memory over NVLink / NVSwitch.  Every rb_* device entry point accepts operands that live in another GPU's HBM
  * once the mapping exists (the TMA tensor maps are encoded over plain global addresses):
  *   same process, several devices : rb_peer_enable(ctx, peer_device) once per reading context;
- *   one process per GPU           : the owner exports a block obtained from rb_dev_alloc as a 64-byte handle, every
- *                                   reader opens it (rb_ipc_open enables peer access lazily) and closes it when done.
- * Used by the RPA-type consumer rb_ri_mo_pq, whose B operand is another rank's row block of ri3mo. */
+ *   one process per GPU           : the owner exports a device buffer as a 64-byte handle of the allocation that holds
+ *                                   it plus the buffer's byte offset inside that allocation (offset_out may be NULL for
+ *                                   a block that came straight from rb_dev_alloc), every reader opens the handle
+ *                                   (rb_ipc_open enables peer access lazily; add the offset) and closes it when done.
+ * Used by rb_ri_mo_pq_peers and rb_special_dgemm_01_peers, which consume other ranks' blocks. */
 int rb_peer_enable(rb_ctx *ctx, int peer_device);
-int rb_ipc_export(rb_ctx *ctx, void *dev_ptr, unsigned char handle[64]);
+int rb_ipc_export(rb_ctx *ctx, void *dev_ptr, unsigned char handle[64], int64_t *offset_out);
 int rb_ipc_open(rb_ctx *ctx, const unsigned char handle[64], void **out);
 int rb_ipc_close(rb_ctx *ctx, void *ptr);
 
@@ -227,6 +229,17 @@ int rb_ri_mo_pq(rb_ctx *ctx, const double *mo_a, int64_t ldp_a, int np_a, const 
  * NVLink transfer overlaps the math.  Callers synchronise the ranks before (panels complete) and after (panels free). */
 int rb_ri_mo_pq_peers(rb_ctx *ctx, int rank, int world, const double *const *panels, int64_t ld, const int *np,
                       int64_t cols, const double *w, double *out, int64_t ldo, const int64_t *q_off);
+
+/* P-sharded form of special_dgemm_f_01 (restmatr.f90:111-154 with the full x range, every y, and z = the auxiliary index):
+ *   out[xy, P'] = alpha * sum_P T[xy, P] * B[P, P'] + beta * T[xy, P']   for P' in this rank's shard, P over ALL ranks,
+ * T viewed as the matrix [xy = X*Y, naux] whose column block P_s lives on rank s (shards[s], as seen from this rank:
+ * rb_ipc_open mapping or local pointer).  The contraction runs over the sharded index, so every rank needs every
+ * other rank's shard: row chunks of the peers' shards are pulled by the copy engines over NVLink on a second stream,
+ * one chunk ahead of the DMMA GEMM that accumulates them into `out` (a separate buffer: peers are still reading T).
+ * b = the full [naux, naux] matrix (ldb >= naux), np[s] / p_off[s] = columns and first column of rank s.
+ * Callers synchronise the ranks before (shards complete) and after (then `out` may replace the shard). */
+int rb_special_dgemm_01_peers(rb_ctx *ctx, int rank, int world, const double *const *shards, int64_t xy, const int *np,
+                              const int64_t *p_off, const double *b, int64_t ldb, double alpha, double beta, double *out);
 
 /* einsum helpers (matrix_blas_lapack.rs:1273-1387, matrix/einsum.rs) on device buffers:
  * "ij,j->ij" and "i,j->ij" are one multiply per element (bit-exact), "ip,ip->p" is a column dot (1e-10). */

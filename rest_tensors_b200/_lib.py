@@ -49,7 +49,7 @@ SIGNATURES = {
     "rb_host_alloc_pinned": (C.c_int, [c_i64, C.POINTER(c_vp)]),
     "rb_host_free_pinned": (C.c_int, [c_vp]),
     "rb_peer_enable": (C.c_int, [c_vp, C.c_int]),
-    "rb_ipc_export": (C.c_int, [c_vp, c_vp, c_vp]),
+    "rb_ipc_export": (C.c_int, [c_vp, c_vp, c_vp, C.POINTER(c_i64)]),
     "rb_ipc_open": (C.c_int, [c_vp, c_vp, C.POINTER(c_vp)]),
     "rb_ipc_close": (C.c_int, [c_vp, c_vp]),
     "rb_memcpy_h2d": (C.c_int, [c_vp, c_vp, c_vp, c_i64]),
@@ -111,6 +111,8 @@ SIGNATURES = {
     "rb_host_ri_mo_pq": (C.c_int, [c_vp] + [C.c_int] * 7 + [c_vp, c_vp]),
     "rb_ri_mo_pq_peers": (C.c_int, [c_vp, C.c_int, C.c_int, C.POINTER(c_vp), c_i64, c_ip, c_i64, c_vp, c_vp, c_i64,
                                     C.POINTER(c_i64)]),
+    "rb_special_dgemm_01_peers": (C.c_int, [c_vp, C.c_int, C.c_int, C.POINTER(c_vp), c_i64, c_ip, C.POINTER(c_i64), c_vp, c_i64,
+                                            C.c_double, C.c_double, c_vp]),
     "rb_special_dgemm_01": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                       c_vp, c_i64, C.c_int, C.c_double, C.c_double]),
     "rb_einsum_ij_j": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_i64]),

@@ -169,14 +169,34 @@ extern "C" int rb_peer_enable(rb_ctx *ctx, int peer_device)
     return RB_OK;
 }
 
-extern "C" int rb_ipc_export(rb_ctx *ctx, void *dev_ptr, unsigned char handle[64])
+extern "C" int rb_ipc_export(rb_ctx *ctx, void *dev_ptr, unsigned char handle[64], int64_t *offset_out)
 {
     RB_REQUIRE(ctx && dev_ptr && handle, "rb_ipc_export: bad arguments");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
     RB_CUDA(cudaSetDevice(ctx->device));
     cudaIpcMemHandle_t h;
-    RB_CUDA(cudaIpcGetMemHandle(&h, dev_ptr));
+    RB_CUDA(cudaIpcGetMemHandle(&h, dev_ptr)); // the handle names the whole allocation that contains dev_ptr
     memcpy(handle, &h, 64);
+    if (offset_out) {
+        // offset of dev_ptr inside that allocation (a sub-block of a caching allocator's segment is exported this way)
+        typedef CUresult (*range_fn)(CUdeviceptr *, size_t *, CUdeviceptr);
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+            cudaGetLastError();
+            rb_set_error("rb_ipc_export: cuMemGetAddressRange is not available");
+            return RB_ERR_CUDA;
+        }
+        CUdeviceptr base = 0;
+        size_t size = 0;
+        const CUresult r = ((range_fn)fn)(&base, &size, (CUdeviceptr)(uintptr_t)dev_ptr);
+        if (r != CUDA_SUCCESS) {
+            rb_set_error("rb_ipc_export: cuMemGetAddressRange failed (%d)", (int)r);
+            return RB_ERR_CUDA;
+        }
+        *offset_out = (int64_t)((uintptr_t)dev_ptr - (uintptr_t)base);
+    }
     return RB_OK;
 }
 

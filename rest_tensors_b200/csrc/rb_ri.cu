@@ -544,3 +544,90 @@ extern "C" int rb_ri_mo_pq_peers(rb_ctx *ctx, int rank, int world, const double 
     }
     return RB_OK;
 }
+
+// ---- special_dgemm_f_01 contracted over the SHARDED index -------------------------------------------
+// With the full x range the reference's per-y loop T[:, y, :] <- alpha T[:, y, :] B + beta T[:, y, :] is ONE matrix product
+// on the [X*Y, naux] view of the tensor, and with P-sharding the contraction index is the sharded one: rank s needs
+//     out_s[xy, P'_s] = alpha * sum_r T_r[xy, P_r] B[P_r, P'_s] + beta * T_s[xy, P'_s].
+// Same pipeline as rb_ri_mo_pq_peers, at row-chunk granularity (a whole shard is up to 15.5 GB at config D): the copy
+// engines pull chunk (c, r+1) of peer r+1's shard -- a pitched [rows, np_r] block -- while the 'N','N' DMMA GEMM on chunk
+// (c, r) accumulates into out; the own shard's term needs no pull and opens every chunk (beta * T_s is folded into it).
+extern "C" int rb_special_dgemm_01_peers(rb_ctx *ctx, int rank, int world, const double *const *shards, int64_t xy,
+                                         const int *np, const int64_t *p_off, const double *b, int64_t ldb, double alpha,
+                                         double beta, double *out)
+{
+    RB_REQUIRE(ctx && shards && np && p_off, "rb_special_dgemm_01_peers: NULL argument");
+    RB_REQUIRE(world >= 1 && rank >= 0 && rank < world && xy >= 0, "rb_special_dgemm_01_peers: bad rank / world / rows");
+    i64 naux = 0, np_max = 0;
+    for (int s = 0; s < world; ++s) {
+        RB_REQUIRE(np[s] >= 0 && p_off[s] >= 0, "rb_special_dgemm_01_peers: bad shard of rank %d", s);
+        RB_REQUIRE(np[s] == 0 || xy == 0 || shards[s], "rb_special_dgemm_01_peers: shard of rank %d is NULL", s);
+        if (p_off[s] + np[s] > naux) naux = p_off[s] + np[s];
+        if (s != rank && np[s] > np_max) np_max = np[s];
+    }
+    const i64 n = np[rank];
+    if (n == 0 || xy == 0) return RB_OK;
+    RB_REQUIRE(out && b, "rb_special_dgemm_01_peers: NULL buffer");
+    RB_REQUIRE(ldb >= naux, "rb_special_dgemm_01_peers: ldb (%lld) < naux (%lld)", (long long)ldb, (long long)naux);
+    RB_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->aux_stream) {
+        RB_CUDA(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 5; ++i) RB_CUDA(cudaEventCreateWithFlags(&ctx->aux_ev[i], cudaEventDisableTiming));
+    }
+    const int remote = world - 1;
+    // row chunk: two pull buffers of [mc, np_max] within a quarter of the workspace budget; multiples of 128 rows (GEMM tiles)
+    i64 mc = xy;
+    if (remote > 0 && np_max > 0) {
+        mc = (ws_budget_bytes(ctx) / 4) / (2 * np_max * 8);
+        mc &= ~(i64)127;
+        if (mc < 128) mc = 128;
+        if (mc > xy) mc = xy;
+    }
+    const i64 ldbuf = mc + (mc & 1);
+    double *buf[2] = {nullptr, nullptr};
+    if (remote > 0 && np_max > 0) {
+        void *ws;
+        RB_TRY(rb_ws_reserve(ctx, 0, 2 * ldbuf * np_max * 8, &ws));
+        buf[0] = (double *)ws; buf[1] = buf[0] + ldbuf * np_max;
+    }
+    RB_CUDA(cudaEventRecord(ctx->aux_ev[0], ctx->stream));
+    RB_CUDA(cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_ev[0], 0));
+    const i64 nchunks = rb_cdiv(xy, mc), steps = nchunks * remote;
+    auto step_of = [&](i64 t, i64 &row0, i64 &rows, int &peer) {
+        const i64 c = t / remote;
+        row0 = c * mc; rows = (xy - row0 < mc) ? xy - row0 : mc;
+        peer = (rank + 1 + (int)(t % remote)) % world;
+    };
+    auto pull = [&](i64 t) -> int {
+        i64 row0, rows; int r;
+        step_of(t, row0, rows, r);
+        const int bsel = (int)(t & 1);
+        if (t >= 2) RB_CUDA(cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_ev[3 + bsel], 0));
+        if (np[r] > 0)
+            RB_CUDA(cudaMemcpy2DAsync(buf[bsel], (size_t)ldbuf * 8, shards[r] + row0, (size_t)xy * 8, (size_t)rows * 8, (size_t)np[r],
+                                      cudaMemcpyDefault, ctx->aux_stream));
+        RB_CUDA(cudaEventRecord(ctx->aux_ev[1 + bsel], ctx->aux_stream));
+        return RB_OK;
+    };
+    if (steps > 0) RB_TRY(pull(0));
+    const double *bcol = b + p_off[rank] * ldb; // columns P'_s of B
+    i64 t = 0;
+    for (i64 c = 0; c < nchunks; ++c) {
+        const i64 row0 = c * mc, rows = (xy - row0 < mc) ? xy - row0 : mc;
+        double *oc = out + row0;
+        // own term: out = alpha * T_s B[P_s, P'_s] + beta * T_s   (out starts as a copy of T_s when beta != 0)
+        if (beta != 0.0) RB_TRY(rb_copy3d(ctx, shards[rank] + row0, 0, 1, xy, 0, oc, 0, 1, xy, 0, rows, n, 1));
+        RB_TRY(rb_gemm_core(ctx, false, false, rows, n, n, alpha, shards[rank] + row0, xy, 0, bcol + p_off[rank], ldb, 0, beta, oc, xy, 0, 1, 0));
+        for (int i = 0; i < remote; ++i, ++t) {
+            i64 r0, rr; int r;
+            step_of(t, r0, rr, r);
+            const int bsel = (int)(t & 1);
+            if (t + 1 < steps) RB_TRY(pull(t + 1));
+            RB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->aux_ev[1 + bsel], 0));
+            if (np[r] > 0)
+                RB_TRY(rb_gemm_core(ctx, false, false, rows, n, np[r], alpha, buf[bsel], ldbuf, 0, bcol + p_off[r], ldb, 0, 1.0, oc, xy, 0, 1, 0));
+            RB_CUDA(cudaEventRecord(ctx->aux_ev[3 + bsel], ctx->stream));
+        }
+    }
+    return RB_OK;
+}

@@ -301,6 +301,32 @@ class ShardedRI:
             self._mo_pq_block(mine, piece, nx_max, q_hi - q_lo, ll, rl, w, out, q_lo)
         return out
 
+    def special_dgemm_p(self, b: torch.Tensor, alpha: float = 1.0, beta: float = 0.0) -> "ShardedRI":
+        """special_dgemm_f_01 over the SHARDED index (restmatr.f90:111-154 with the full x range, every y, z = P):
+        T[:, :, P'] <- alpha * sum_P T[:, :, P] b[P, P'] + beta * T[:, :, P'], b = [naux, naux] replicated (e.g. V^-1/2
+        when ri3ao is built from the raw three-centre integrals).  In place in the reference's sense:
+        afterwards self.data holds the transformed shard.  world > 1: every rank needs every other rank's shard; they are
+        pulled chunk by chunk over NVLink by rb_special_dgemm_01_peers while the GEMMs run (no NCCL on the data path)."""
+        xy = self.nb * self.nb
+        if self.world == 1:
+            self.ctx.special_dgemm_01(self.data, self.nb, self.nb, self.nx, 0, self.nb, 0, self.nx, b, self.naux, self.nx,
+                                      alpha, beta)
+            return self
+        import torch.distributed as dist
+        views = PeerViews(self.ctx, self.data, self.rank, self.world)
+        out = self.ctx.empty(xy * self.nx)
+        ranges = [shard_range(self.naux, s, self.world) for s in range(self.world)]
+        ptrs = (C.c_void_p * self.world)(*views.ptrs)
+        cols = (C.c_int * self.world)(*[hi - lo for lo, hi in ranges])
+        offs = (C.c_int64 * self.world)(*[lo for lo, _ in ranges])
+        self.ctx.sync()
+        dist.barrier()                              # every shard is complete and visible
+        check(lib.rb_special_dgemm_01_peers(self.ctx.h, self.rank, self.world, ptrs, xy, cols, offs, _p(b), self.naux, alpha,
+                                            beta, _p(out)), "rb_special_dgemm_01_peers")
+        views.close()                               # sync + barrier: nobody is still reading the old shard
+        self.data = out
+        return self
+
     def _peer_panels(self, nbytes: int) -> "PeerBlocks":
         cur = getattr(self, "_panels", None)
         if cur is None or cur.nbytes < nbytes:      # same size on every rank, so all ranks re-create together
@@ -314,41 +340,75 @@ class ShardedRI:
                           out[q_lo * self.nx:], self.nx)
 
 
-class PeerBlocks:
-    """One block of `nbytes` per rank, mapped into every rank's address space: the owner allocates it with
-    rb_dev_alloc (plain cudaMalloc, exportable), exports it as a 64-byte CUDA IPC handle, the handles travel through
-    the process group and every rank opens its peers' blocks.  ptrs[s] is the address of rank s's block as seen from
-    this rank (own block: the local pointer); any rb_* device entry point can read or write it over NVLink."""
+_IPC_OPEN = {}  # handle bytes -> [mapped base address, reference count]: a handle is opened once per process
 
-    def __init__(self, ctx: Context, nbytes: int, rank: int, world: int):
+
+def _ipc_open(ctx: "Context", handle: bytes) -> int:
+    ent = _IPC_OPEN.get(handle)
+    if ent is None:
+        p = C.c_void_p()
+        check(lib.rb_ipc_open(ctx.h, (C.c_ubyte * 64).from_buffer_copy(handle), C.byref(p)), "rb_ipc_open")
+        ent = _IPC_OPEN[handle] = [int(p.value), 0]
+    ent[1] += 1
+    return ent[0]
+
+
+def _ipc_close(ctx: "Context", handle: bytes) -> None:
+    ent = _IPC_OPEN.get(handle)
+    if ent is None:
+        return
+    ent[1] -= 1
+    if ent[1] <= 0:
+        check(lib.rb_ipc_close(ctx.h, C.c_void_p(ent[0])), "rb_ipc_close")
+        del _IPC_OPEN[handle]
+
+
+class PeerViews:
+    """Every rank's device buffer `local` (any allocation: a torch tensor's storage or an rb_dev_alloc block) mapped into
+    every rank's address space.  The owner exports the allocation that holds the buffer as a 64-byte CUDA IPC handle plus
+    the buffer's offset inside it, the (handle, offset) pairs travel through the process group, and every rank opens its
+    peers' handles.  ptrs[s] is the address of rank s's buffer as seen from this rank (own buffer: the local pointer);
+    any rb_* device entry point and cudaMemcpy can read it over NVLink."""
+
+    def __init__(self, ctx: Context, local, rank: int, world: int):
         import torch.distributed as dist
-        self.ctx, self.nbytes, self.rank, self.world = ctx, int(nbytes), rank, world
-        base = C.c_void_p()
-        check(lib.rb_dev_alloc(ctx.h, self.nbytes, C.byref(base)), "rb_dev_alloc")
-        self.local = int(base.value)
+        self.ctx, self.rank, self.world = ctx, rank, world
+        self.local = local if isinstance(local, int) else int(local.data_ptr())
         handle = (C.c_ubyte * 64)()
-        check(lib.rb_ipc_export(ctx.h, C.c_void_p(self.local), handle), "rb_ipc_export")
-        handles = [None] * world
-        dist.all_gather_object(handles, bytes(handle))
+        off = C.c_int64(0)
+        check(lib.rb_ipc_export(ctx.h, C.c_void_p(self.local), handle, C.byref(off)), "rb_ipc_export")
+        pairs = [None] * world
+        dist.all_gather_object(pairs, (bytes(handle), int(off.value)))
+        self.handles = [h for h, _ in pairs]
         self.ptrs = []
-        for s, hb in enumerate(handles):
-            if s == rank:
-                self.ptrs.append(self.local)
-                continue
-            p = C.c_void_p()
-            check(lib.rb_ipc_open(ctx.h, (C.c_ubyte * 64).from_buffer_copy(hb), C.byref(p)), "rb_ipc_open")
-            self.ptrs.append(int(p.value))
+        for s, (hb, o) in enumerate(pairs):
+            self.ptrs.append(self.local if s == rank else _ipc_open(ctx, hb) + o)
 
     def close(self) -> None:
         import torch.distributed as dist
         self.ctx.sync()
         dist.barrier()                              # no peer is still reading
-        for s, p in enumerate(self.ptrs):
-            if s != self.rank and p:
-                check(lib.rb_ipc_close(self.ctx.h, C.c_void_p(p)), "rb_ipc_close")
-        dist.barrier()                              # every mapping is gone before the owner frees
-        check(lib.rb_dev_free(self.ctx.h, C.c_void_p(self.local)), "rb_dev_free")
-        self.ptrs, self.local = [], 0
+        for s, hb in enumerate(self.handles):
+            if s != self.rank:
+                _ipc_close(self.ctx, hb)
+        dist.barrier()                              # every mapping is gone before an owner may free
+        self.ptrs, self.handles = [], []
+
+
+class PeerBlocks(PeerViews):
+    """One block of `nbytes` per rank, allocated with rb_dev_alloc (plain cudaMalloc) and mapped on every rank."""
+
+    def __init__(self, ctx: Context, nbytes: int, rank: int, world: int):
+        self.nbytes = int(nbytes)
+        base = C.c_void_p()
+        check(lib.rb_dev_alloc(ctx.h, self.nbytes, C.byref(base)), "rb_dev_alloc")
+        super().__init__(ctx, int(base.value), rank, world)
+
+    def close(self) -> None:
+        local = self.local
+        super().close()
+        check(lib.rb_dev_free(self.ctx.h, C.c_void_p(local)), "rb_dev_free")
+        self.local = 0
 
 
 def all_reduce_sum(t: torch.Tensor, world: int) -> None:

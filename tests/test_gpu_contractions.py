@@ -615,3 +615,15 @@ def test_special_dgemm_f_01(rt, oracle_blas):
     assert_close_1e10(t, t_ref, "special_dgemm_f_01")
     mask = np.ones((X, Y, Z), dtype=bool); mask[sx:sx + lx, :, sz:sz + lz] = False
     assert np.array_equal(t.reshape((X, Y, Z), order="F")[mask], t0.reshape((X, Y, Z), order="F")[mask])
+
+
+def test_special_dgemm_over_p_single_rank(ctx, oracle_blas):
+    """ShardedRI.special_dgemm_p at world == 1 == special_dgemm_f_01 with the full x and z ranges on the resident tensor."""
+    from rest_tensors_b200.device import ShardedRI
+    nb, nx = 24, 37
+    sh = ShardedRI(ctx, nb, nx).fill_synthetic()
+    t_ref = oracle_blas.fill_ri3ao_symm(nb, 0, nx)
+    b = oracle_blas.fill_linear(nx * nx, 8, scale=nx ** -0.5)
+    oracle_blas.special_dgemm_f_01(t_ref, [nb, nb, nx], (0, nb), 0, (0, nx), b, [nx, nx], (0, nx), (0, nx), 0.7, -0.2)
+    sh.special_dgemm_p(_dev(ctx, b), 0.7, -0.2)
+    assert_close_1e10(sh.data.cpu().numpy(), t_ref, "special_dgemm over P, one rank")

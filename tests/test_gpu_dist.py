@@ -61,6 +61,18 @@ def _worker(rank, world, port, nb, naux, no, ret):
                 err(pq_ag.cpu().numpy(), pq_ref.reshape(-1, order="F")),
                 err(pq_nw.cpu().numpy(), pq_nw_ref.reshape(-1, order="F")),
                 err(pq_nw_ag.cpu().numpy(), pq_nw_ref.reshape(-1, order="F"))]
+        # the step BEFORE the hot path: T <- alpha T B + beta T contracted over the SHARDED index,
+        # peers' shards pulled over NVLink while the GEMMs run; afterwards sh.data is the transformed shard
+        bmat = o.fill_linear(naux * naux, 8, scale=naux ** -0.5)
+        t_ref = ri.copy()
+        o.special_dgemm_f_01(t_ref, [nb, nb, naux], (0, nb), 0, (0, naux), bmat, [naux, naux], (0, naux), (0, naux), 0.7, -0.2)
+        sh.special_dgemm_p(dev(bmat), 0.7, -0.2)
+        torch.cuda.synchronize()
+        errs.append(err(sh.data.cpu().numpy(), t_ref[sh.p_lo * nb * nb: sh.p_hi * nb * nb]))
+        sh.special_dgemm_p(dev(bmat), 1.0, 0.0)       # a second pass on the transformed shards (beta = 0 branch)
+        o.special_dgemm_f_01(t_ref, [nb, nb, naux], (0, nb), 0, (0, naux), bmat, [naux, naux], (0, naux), (0, naux), 1.0, 0.0)
+        torch.cuda.synchronize()
+        errs.append(err(sh.data.cpu().numpy(), t_ref[sh.p_lo * nb * nb: sh.p_hi * nb * nb]))
         ret.put((rank, max(errs)))
         dist.barrier()
     finally:
