@@ -63,7 +63,10 @@ extern "C" {
                       lla: c_int, r0a: c_int, rla: c_int, mo_b: *const c_double, ldp_b: i64, nl_b: c_int, nr_b: c_int,
                       l0b: c_int, llb: c_int, r0b: c_int, rlb: c_int, beta: c_double, out: *mut c_double, ldo: i64) -> c_int;
     pub fn rb_peer_enable(ctx: *mut RbCtx, peer_device: c_int) -> c_int;
-    pub fn rb_ipc_export(ctx: *mut RbCtx, dev_ptr: *mut std::ffi::c_void, handle: *mut u8) -> c_int;
+    pub fn rb_ipc_export(ctx: *mut RbCtx, dev_ptr: *mut std::ffi::c_void, handle: *mut u8, offset_out: *mut i64) -> c_int;
+    pub fn rb_special_dgemm_01_peers(ctx: *mut RbCtx, rank: c_int, world: c_int, shards: *const *const c_double, xy: i64,
+                                     np: *const c_int, p_off: *const i64, b: *const c_double, ldb: i64, alpha: c_double,
+                                     beta: c_double, out: *mut c_double) -> c_int;
     pub fn rb_ipc_open(ctx: *mut RbCtx, handle: *const u8, out: *mut *mut std::ffi::c_void) -> c_int;
     pub fn rb_ipc_close(ctx: *mut RbCtx, ptr: *mut std::ffi::c_void) -> c_int;
     pub fn rb_ri_mo_pq_peers(ctx: *mut RbCtx, rank: c_int, world: c_int, panels: *const *const c_double, ld: i64,
