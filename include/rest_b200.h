@@ -171,6 +171,12 @@ int rb_host_ri_iajb(int np, const double *mo_a, int nl_a, int nr_a, int l0a, int
 /* RPA-type consumer from a dense host ri3mo[np, nl, nr]; out is the dense symmetric [np, np] matrix.  See rb_ri_mo_pq. */
 int rb_host_ri_mo_pq(const double *mo, int np, int nl, int nr, int l0, int ll, int r0, int rl, const double *w,
                      double *out);
+/* eigen-solvers on host buffers, with the reference's argument conventions: _dsyev / lapack_dsyev (lower triangle read),
+ * lapack_dspevx (*n_found = n), lapack_dspgvx / _dspgvx (z [n, num_orb]), _power / lapack_power */
+int rb_host_dsyev(char jobz, int n, const double *a, double *w, double *z);
+int rb_host_dspevx(int n, const double *ap, double *w, double *z, int *n_found);
+int rb_host_dspgvx(int n, const double *ap, const double *bp, int num_orb, double *w, double *z);
+int rb_host_power(int n, const double *a, double p, double threshold, double *out, int *n_nonsingular);
 /* d_P, J, K with host buffers (composed by REST from _dgemv/_dgemm/_dsyrk) */
 int rb_host_ri_dp(const double *ri3ao, const double *dm, double *d, int nb, int nx);
 int rb_host_ri_j(const double *ri3ao, const double *d, double *j, int nb, int nx);
@@ -248,6 +254,22 @@ int rb_einsum_ij_j(rb_ctx *ctx, const double *a, int64_t lda, const double *b, d
 int rb_einsum_ip_ip(rb_ctx *ctx, const double *a, int64_t lda, const double *b, int64_t ldb, double *out, int64_t ni,
                     int64_t np);
 int rb_einsum_i_j(rb_ctx *ctx, const double *a, const double *b, double *out, int64_t ni, int64_t nj);
+
+/* Symmetric eigen-solvers (the reference's LAPACK wrappers _dsyev / lapack_dspevx / lapack_dspgvx /
+ * _power, matrix_blas_lapack.rs:319-352, 599-652, 1004-1147, 2123-2185) as a parallel one-sided Jacobi method on device
+ * buffers.  Eigenvalues ascending; eigenvectors in the columns of z, normalised, largest component positive (LAPACK
+ * leaves the sign open).  These calls synchronise the context's stream (the sweep count is data dependent).
+ *   rb_dsyev : a [n, n] (the `uplo` triangle is read), w [n], z [n, n] (jobz 'V') or NULL ('N')
+ *   rb_dspev : packed upper ap [n(n+1)/2]
+ *   rb_dspgv : A x = lambda B x with packed upper ap, bp (B positive definite, else RB_ERR_INVALID); the m lowest
+ *              pairs: w [m], z [n, m] with z^T B z = I
+ *   rb_matrix_power : out = sum over eigenvalues lambda_i >= threshold of lambda_i^p v_i v_i^T (lower triangle of a is
+ *              read, like the reference's dsyev('L')); *n_nonsingular = number of eigenvalues kept */
+int rb_dsyev(rb_ctx *ctx, char jobz, char uplo, int n, const double *a, int64_t lda, double *w, double *z, int64_t ldz);
+int rb_dspev(rb_ctx *ctx, int n, const double *ap, double *w, double *z, int64_t ldz);
+int rb_dspgv(rb_ctx *ctx, int n, const double *ap, const double *bp, int m, double *w, double *z, int64_t ldz);
+int rb_matrix_power(rb_ctx *ctx, int n, const double *a, int64_t lda, double p, double threshold, double *out, int64_t ldo,
+                    int *n_nonsingular);
 
 /* pack / unpack (bit-exact) */
 int rb_pack_upper(rb_ctx *ctx, const double *full, int64_t n, double *packed);

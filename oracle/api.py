@@ -92,6 +92,10 @@ class Oracle:
         L.orc_ri_dp.argtypes = [_vp, _vp, _vp, _i, _i]
         L.orc_ri_j.argtypes = [_vp, _vp, _vp, _i, _i]
         L.orc_ri_k.argtypes = [_vp, _vp, _vp, _i, _i, _i]
+        L.orc_dsyev.argtypes = [_ch, _i, _vp, _vp]
+        L.orc_dspevx.argtypes = [_i, _vp, _vp, _vp, _vp]
+        L.orc_dspgvx.argtypes = [_i, _vp, _vp, _i, _vp, _vp, _vp]
+        L.orc_power.argtypes = [_vp, _i, _d, _d, _vp, _vp]
         L.orc_ri_mo_pq.argtypes = [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]
         L.orc_ri_iajb.argtypes = [_i, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp]
         for name in ("orc_einsum_01", "orc_einsum_02", "orc_einsum_03"):
@@ -177,6 +181,36 @@ class Oracle:
         self.lib.orc_ri_mo_pq(mo_a.ctypes.data, npa, mo_b.ctypes.data, npb, nl, *box,
                               None if w is None else w.ctypes.data, out.ctypes.data)
         return out
+
+    # -- eigen-solvers: the reference's LAPACK calls (needs load_openblas) --
+    def dsyev(self, a, n, jobz="V"):
+        """returns (eigenvectors [n*n] or None, eigenvalues ascending)"""
+        v = np.array(a, dtype=np.float64, copy=True)
+        w = np.zeros(n, dtype=np.float64)
+        info = self.lib.orc_dsyev(jobz.encode(), n, v.ctypes.data, w.ctypes.data)
+        assert info == 0, f"dsyev info {info}"
+        return (v if jobz == "V" else None), w
+
+    def dspevx(self, ap, n):
+        w = np.zeros(n, dtype=np.float64); z = np.zeros(n * n, dtype=np.float64)
+        m = C.c_int(0)
+        info = self.lib.orc_dspevx(n, ap.ctypes.data, w.ctypes.data, z.ctypes.data, C.addressof(m))
+        assert info == 0, f"dspevx info {info}"
+        return z, w, m.value
+
+    def dspgvx(self, ap, bp, n, num_orb):
+        w = np.zeros(num_orb, dtype=np.float64); z = np.zeros(n * num_orb, dtype=np.float64)
+        m = C.c_int(0)
+        info = self.lib.orc_dspgvx(n, ap.ctypes.data, bp.ctypes.data, num_orb, w.ctypes.data, z.ctypes.data, C.addressof(m))
+        assert info == 0 and m.value == num_orb, f"dspgvx info {info} m {m.value}"
+        return z, w
+
+    def power(self, a, n, p, threshold):
+        out = np.zeros(n * n, dtype=np.float64)
+        nns = C.c_int(0)
+        info = self.lib.orc_power(a.ctypes.data, n, p, threshold, out.ctypes.data, C.addressof(nns))
+        assert info == 0, f"power info {info}"
+        return out, nns.value
 
     # -- einsum helpers (matrix_blas_lapack.rs:1273-1387) --
     def einsum_01(self, a, b, ni, nj) -> np.ndarray:

@@ -20,6 +20,8 @@
  *   _dgemv/_dgemm_full/_dsyrk/_dsymm argument conventions  src/matrix/matrix_blas_lapack.rs:38-70,180-252,354-413
  *   (ia|jb) blocks        NOT in the reference crate: dgemm('T','N') over P on the ri3mo layout
  *                         of src/ri.rs:381-386.
+ *   _dsyev / lapack_dspevx / lapack_dspgvx / _power   src/matrix/matrix_blas_lapack.rs:319-352, 599-652, 1004-1147, 2123-2185
+ *                         (argument conventions; the arithmetic is LAPACK's, taken from the dlopen'ed OpenBLAS)
  *   d_P / J / K           NOT in the reference crate: composed per SURVEY §3.5 from the
  *                         primitives above (dgemv 'T', dgemv 'N', per-slab dgemm + dsyrk).
  *
@@ -106,6 +108,17 @@ static set_threads_fn g_set_threads = NULL;
 static get_threads_fn g_get_threads = NULL;
 static get_config_fn g_get_config = NULL;
 static int g_use_blas = 0;
+/* LAPACK entry points of the same library (the reference resolves them from -lopenblas through lapack-sys 0.14) */
+typedef void (*dsyev_fn)(const char *, const char *, const int *, double *, const int *, double *, double *, const int *, int *);
+typedef void (*dspevx_fn)(const char *, const char *, const char *, const int *, double *, const double *, const double *,
+                          const int *, const int *, const double *, int *, double *, double *, const int *, double *, int *,
+                          int *, int *);
+typedef void (*dspgvx_fn)(const int *, const char *, const char *, const char *, const int *, double *, double *,
+                          const double *, const double *, const int *, const int *, const double *, int *, double *, double *,
+                          const int *, double *, int *, int *, int *);
+static dsyev_fn g_dsyev = NULL;
+static dspevx_fn g_dspevx = NULL;
+static dspgvx_fn g_dspgvx = NULL;
 
 static void *sym2(void *h, const char *a, const char *b)
 {
@@ -128,9 +141,13 @@ int orc_load_blas(const char *path)
     g_set_threads = (set_threads_fn)sym2(h, "scipy_openblas_set_num_threads", "openblas_set_num_threads");
     g_get_threads = (get_threads_fn)sym2(h, "scipy_openblas_get_num_threads", "openblas_get_num_threads");
     g_get_config = (get_config_fn)sym2(h, "scipy_openblas_get_config", "openblas_get_config");
+    g_dsyev = (dsyev_fn)sym2(h, "scipy_dsyev_", "dsyev_");
+    g_dspevx = (dspevx_fn)sym2(h, "scipy_dspevx_", "dspevx_");
+    g_dspgvx = (dspgvx_fn)sym2(h, "scipy_dspgvx_", "dspgvx_");
     g_use_blas = 1;
     return 0;
 }
+int orc_lapack_loaded(void) { return g_dsyev && g_dspevx && g_dspgvx; }
 void orc_use_blas(int on) { g_use_blas = (on && g_dgemm) ? 1 : 0; }
 int orc_blas_loaded(void) { return g_dgemm != NULL; }
 void orc_blas_set_threads(int n) { if (g_set_threads) g_set_threads(n); }
@@ -587,6 +604,84 @@ void orc_ri_mo_pq(const double *mo_a, int npa, const double *mo_b, int npb, int 
     orc_dgemm('N', 'T', npa, npb, cols, 1.0, ga, npa, gb, npb, 0.0, out, npa);
     free(ga);
     free(gb);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Eigen-solvers: the reference's LAPACK calls with the reference's own arguments.  The arithmetic
+ * lives in LAPACK (third-party, resolved from OpenBLAS; here the LAPACK of the dlopen'ed OpenBLAS), so these functions
+ * need orc_load_blas() first and return -1000 without it.  Return value = LAPACK info.
+ * ---------------------------------------------------------------------------------------------- */
+#define ORC_SAFE_MINIMUM 1.0e-16 /* src/lib.rs:99 */
+
+/* _dsyev / lapack_dsyev (matrix_blas_lapack.rs:319-352, 775-797): dsyev(jobz, 'L', n, a, n, w, work, 4n); a is
+ * overwritten by the eigenvectors (jobz 'V'); w ascending. */
+int orc_dsyev(char jobz, int n, double *a, double *w)
+{
+    if (!g_dsyev) return -1000;
+    int lwork = 4 * n > 1 ? 4 * n : 1, info = 0, lda = n > 1 ? n : 1;
+    double *work = (double *)malloc(sizeof(double) * (size_t)lwork);
+    g_dsyev(&jobz, "L", &n, a, &lda, w, work, &lwork, &info);
+    free(work);
+    return info;
+}
+
+/* lapack_dspevx (1075-1095): dspevx('V','A','U', n, ap, 0, 0, 0, 0, SAFE_MINIMUM, m, w, z, n, work, iwork, ifail, info) */
+int orc_dspevx(int n, const double *ap_in, double *w, double *z, int *n_found)
+{
+    if (!g_dspevx) return -1000;
+    size_t np = (size_t)n * (size_t)(n + 1) / 2;
+    double *ap = (double *)malloc(sizeof(double) * (np ? np : 1));
+    memcpy(ap, ap_in, sizeof(double) * np);
+    double *work = (double *)malloc(sizeof(double) * (size_t)(8 * n > 1 ? 8 * n : 1));
+    int *iwork = (int *)malloc(sizeof(int) * (size_t)(5 * n > 1 ? 5 * n : 1)), *ifail = (int *)malloc(sizeof(int) * (size_t)(n > 1 ? n : 1));
+    double vl = 0.0, vu = 0.0, abstol = ORC_SAFE_MINIMUM;
+    int il = 0, iu = 0, info = 0, ldz = n > 1 ? n : 1;
+    g_dspevx("V", "A", "U", &n, ap, &vl, &vu, &il, &iu, &abstol, n_found, w, z, &ldz, work, iwork, ifail, &info);
+    free(ap); free(work); free(iwork); free(ifail);
+    return info;
+}
+
+/* lapack_dspgvx / _dspgvx (1096-1147, 2123-2185): dspgvx(1,'V','I','U', n, ap, bp, 0, 0, 1, num_orb, SAFE_MINIMUM, ...);
+ * z = [n, num_orb] B-orthonormal eigenvectors of the num_orb lowest eigenvalues. */
+int orc_dspgvx(int n, const double *ap_in, const double *bp_in, int num_orb, double *w, double *z, int *m_found)
+{
+    if (!g_dspgvx) return -1000;
+    size_t np = (size_t)n * (size_t)(n + 1) / 2;
+    double *ap = (double *)malloc(sizeof(double) * (np ? np : 1)), *bp = (double *)malloc(sizeof(double) * (np ? np : 1));
+    memcpy(ap, ap_in, sizeof(double) * np);
+    memcpy(bp, bp_in, sizeof(double) * np);
+    double *work = (double *)malloc(sizeof(double) * (size_t)(8 * n > 1 ? 8 * n : 1));
+    double *zz = (double *)malloc(sizeof(double) * (size_t)n * (size_t)n + 8), *ww = (double *)malloc(sizeof(double) * (size_t)(n > 1 ? n : 1));
+    int *iwork = (int *)malloc(sizeof(int) * (size_t)(5 * n > 1 ? 5 * n : 1)), *ifail = (int *)malloc(sizeof(int) * (size_t)(n > 1 ? n : 1));
+    double vl = 0.0, vu = 0.0, abstol = ORC_SAFE_MINIMUM;
+    int itype = 1, il = 1, iu = num_orb, info = 0, ldz = n > 1 ? n : 1;
+    g_dspgvx(&itype, "V", "I", "U", &n, ap, bp, &vl, &vu, &il, &iu, &abstol, m_found, ww, zz, &ldz, work, iwork, ifail, &info);
+    if (info == 0) {
+        memcpy(w, ww, sizeof(double) * (size_t)num_orb);
+        memcpy(z, zz, sizeof(double) * (size_t)n * (size_t)num_orb);
+    }
+    free(ap); free(bp); free(work); free(zz); free(ww); free(iwork); free(ifail);
+    return info;
+}
+
+/* _power / lapack_power (599-652, 1004-1062): A^p over the eigenvalues >= threshold.  om = -A; dsyev('V'); the eigenvalues
+ * come out as -lambda ascending = lambda descending; the first n_nonsingular (lambda >= threshold) eigenvectors are
+ * scaled by sqrt(lambda)^p, the rest zeroed; out = Vs Vs^T (dgemm 'N','T'). */
+int orc_power(const double *a, int n, double p, double threshold, double *out, int *n_nonsingular)
+{
+    size_t nn = (size_t)n * (size_t)n;
+    double *om = (double *)malloc(sizeof(double) * (nn ? nn : 1)), *w = (double *)malloc(sizeof(double) * (size_t)(n > 1 ? n : 1));
+    for (size_t i = 0; i < nn; ++i) om[i] = a[i] * -1.0;
+    int info = orc_dsyev('V', n, om, w);
+    if (info != 0) { free(om); free(w); return info; }
+    int nns = 0;
+    for (int i = 0; i < n; ++i) { w[i] = w[i] * -1.0; if (w[i] >= threshold) ++nns; }
+    for (int i = 0; i < n; ++i)
+        for (int k = 0; k < n; ++k) om[k + (size_t)i * n] = i < nns ? om[k + (size_t)i * n] * pow(sqrt(w[i]), p) : 0.0;
+    orc_dgemm('N', 'T', n, n, n, 1.0, om, n > 1 ? n : 1, om, n > 1 ? n : 1, 0.0, out, n > 1 ? n : 1);
+    *n_nonsingular = nns;
+    free(om); free(w);
+    return 0;
 }
 
 /* ------------------------------------------------------------------------------------------------

@@ -14,6 +14,7 @@ from .tensors import (  # noqa: F401
     _dgemm_nn, _dgemm_nn_serial, _dgemm_tn, _dgemm_tn_serial, _dgemm_tn_v02,
     _einsum_01_rayon, _einsum_01_serial, _einsum_02_rayon, _einsum_02_serial, _einsum_03, _einsum_03_forvec, _einsum_general,
     ri_ao2mo_f, general_dgemm_f, special_dgemm_f_01, matr_copy, matr_copy_from_ri, ri_copy_from_matr, ri_copy_from_ri,
+    _dsyev, _power, _dspgvx,
 )
 
 __all__ = [
@@ -24,5 +25,5 @@ __all__ = [
     "_einsum_01_rayon", "_einsum_01_serial", "_einsum_02_rayon", "_einsum_02_serial", "_einsum_03", "_einsum_03_forvec",
     "_einsum_general",
     "ri_ao2mo_f", "general_dgemm_f", "special_dgemm_f_01", "matr_copy", "matr_copy_from_ri", "ri_copy_from_matr",
-    "ri_copy_from_ri",
+    "ri_copy_from_ri", "_dsyev", "_power", "_dspgvx",
 ]

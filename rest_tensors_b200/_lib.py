@@ -111,6 +111,14 @@ SIGNATURES = {
     "rb_host_ri_mo_pq": (C.c_int, [c_vp] + [C.c_int] * 7 + [c_vp, c_vp]),
     "rb_ri_mo_pq_peers": (C.c_int, [c_vp, C.c_int, C.c_int, C.POINTER(c_vp), c_i64, c_ip, c_i64, c_vp, c_vp, c_i64,
                                     C.POINTER(c_i64)]),
+    "rb_dsyev": (C.c_int, [c_vp, C.c_char, C.c_char, C.c_int, c_vp, c_i64, c_vp, c_vp, c_i64]),
+    "rb_dspev": (C.c_int, [c_vp, C.c_int, c_vp, c_vp, c_vp, c_i64]),
+    "rb_dspgv": (C.c_int, [c_vp, C.c_int, c_vp, c_vp, C.c_int, c_vp, c_vp, c_i64]),
+    "rb_matrix_power": (C.c_int, [c_vp, C.c_int, c_vp, c_i64, C.c_double, C.c_double, c_vp, c_i64, c_ip]),
+    "rb_host_dsyev": (C.c_int, [C.c_char, C.c_int, c_vp, c_vp, c_vp]),
+    "rb_host_dspevx": (C.c_int, [C.c_int, c_vp, c_vp, c_vp, c_ip]),
+    "rb_host_dspgvx": (C.c_int, [C.c_int, c_vp, c_vp, C.c_int, c_vp, c_vp]),
+    "rb_host_power": (C.c_int, [C.c_int, c_vp, C.c_double, C.c_double, c_vp, c_ip]),
     "rb_special_dgemm_01_peers": (C.c_int, [c_vp, C.c_int, C.c_int, C.POINTER(c_vp), c_i64, c_ip, C.POINTER(c_i64), c_vp, c_i64,
                                             C.c_double, C.c_double, c_vp]),
     "rb_special_dgemm_01": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -1072,3 +1072,85 @@ extern "C" int rb_host_ri_mo_pq(const double *mo, int np, int nl, int nr, int l0
     RB_TRY(op.down(out, dout, (i64)np * np));
     return op.sync();
 }
+
+// ---- eigen-solvers on host buffers (matrix_blas_lapack.rs:319-352, 599-652, 1004-1147, 2123-2185) ----
+// _dsyev / lapack_dsyev: dsyev(jobz, 'L', ...) -- the lower triangle of a [n, n] is read; w ascending; z [n, n] (jobz 'V')
+extern "C" int rb_host_dsyev(char jobz, int n, const double *a, double *w, double *z)
+{
+    RB_REQUIRE(n >= 0, "rb_host_dsyev: negative dimension");
+    RB_REQUIRE(jobz == 'V' || jobz == 'v' || jobz == 'N' || jobz == 'n', "rb_host_dsyev: jobz must be 'V' or 'N'");
+    if (n == 0) return RB_OK;
+    const bool want_z = jobz == 'V' || jobz == 'v';
+    RB_REQUIRE(a && w && (!want_z || z), "rb_host_dsyev: NULL buffer");
+    HOST_CTX(op);
+    const i64 nn = (i64)n * n;
+    double *da, *dw, *dz = nullptr;
+    RB_TRY(op.alloc(nn, &da));
+    RB_TRY(op.alloc(n, &dw));
+    if (want_z) RB_TRY(op.alloc(nn, &dz));
+    RB_TRY(op.up(da, a, nn));
+    RB_TRY(rb_dsyev(op.ctx, jobz, 'L', n, da, n, dw, dz, n));
+    RB_TRY(op.down(w, dw, n));
+    if (want_z) RB_TRY(op.down(z, dz, nn));
+    return op.sync();
+}
+
+// lapack_dspevx: packed upper input, all eigenpairs; *n_found = n
+extern "C" int rb_host_dspevx(int n, const double *ap, double *w, double *z, int *n_found)
+{
+    RB_REQUIRE(n >= 0, "rb_host_dspevx: negative dimension");
+    if (n_found) *n_found = 0;
+    if (n == 0) return RB_OK;
+    RB_REQUIRE(ap && w && z, "rb_host_dspevx: NULL buffer");
+    HOST_CTX(op);
+    const i64 nn = (i64)n * n, np = (i64)n * (n + 1) / 2;
+    double *dp, *dw, *dz;
+    RB_TRY(op.alloc(np, &dp));
+    RB_TRY(op.alloc(n, &dw));
+    RB_TRY(op.alloc(nn, &dz));
+    RB_TRY(op.up(dp, ap, np));
+    RB_TRY(rb_dspev(op.ctx, n, dp, dw, dz, n));
+    RB_TRY(op.down(w, dw, n));
+    RB_TRY(op.down(z, dz, nn));
+    if (n_found) *n_found = n;
+    return op.sync();
+}
+
+// lapack_dspgvx / _dspgvx: A x = lambda B x, packed upper A and B, the num_orb lowest pairs; z [n, num_orb], z^T B z = I
+extern "C" int rb_host_dspgvx(int n, const double *ap, const double *bp, int num_orb, double *w, double *z)
+{
+    RB_REQUIRE(n >= 0 && num_orb >= 0 && num_orb <= n, "rb_host_dspgvx: bad dimensions (n = %d, num_orb = %d)", n, num_orb);
+    if (n == 0 || num_orb == 0) return RB_OK;
+    RB_REQUIRE(ap && bp && w && z, "rb_host_dspgvx: NULL buffer");
+    HOST_CTX(op);
+    const i64 np = (i64)n * (n + 1) / 2;
+    double *da, *db, *dw, *dz;
+    RB_TRY(op.alloc(np, &da));
+    RB_TRY(op.alloc(np, &db));
+    RB_TRY(op.alloc(num_orb, &dw));
+    RB_TRY(op.alloc((i64)n * num_orb, &dz));
+    RB_TRY(op.up(da, ap, np));
+    RB_TRY(op.up(db, bp, np));
+    RB_TRY(rb_dspgv(op.ctx, n, da, db, num_orb, dw, dz, n));
+    RB_TRY(op.down(w, dw, num_orb));
+    RB_TRY(op.down(z, dz, (i64)n * num_orb));
+    return op.sync();
+}
+
+// _power / lapack_power: out = sum over eigenvalues >= threshold of lambda^p v v^T
+extern "C" int rb_host_power(int n, const double *a, double p, double threshold, double *out, int *n_nonsingular)
+{
+    RB_REQUIRE(n >= 0, "rb_host_power: negative dimension");
+    if (n_nonsingular) *n_nonsingular = 0;
+    if (n == 0) return RB_OK;
+    RB_REQUIRE(a && out, "rb_host_power: NULL buffer");
+    HOST_CTX(op);
+    const i64 nn = (i64)n * n;
+    double *da, *dout;
+    RB_TRY(op.alloc(nn, &da));
+    RB_TRY(op.alloc(nn, &dout));
+    RB_TRY(op.up(da, a, nn));
+    RB_TRY(rb_matrix_power(op.ctx, n, da, n, p, threshold, dout, n, n_nonsingular));
+    RB_TRY(op.down(out, dout, nn));
+    return op.sync();
+}

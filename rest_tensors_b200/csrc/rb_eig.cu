@@ -1,0 +1,394 @@
+// rb_eig.cu -- symmetric eigen-solvers of the reference's LAPACK wrappers:
+//   _dsyev / lapack_dsyev        src/matrix/matrix_blas_lapack.rs:319-352, 775-797   (all eigenpairs, ascending)
+//   lapack_dspevx                1075-1095                                            (packed upper input)
+//   lapack_dspgvx / _dspgvx      1096-1147, 2123-2185                                 (A x = lambda B x, lowest num_orb pairs)
+//   _power / lapack_power        599-652, 1004-1062                                   (A^p over the eigenvalues >= threshold)
+//
+// The reference calls LAPACK (tridiagonalisation + QR / bisection: sequential, host-shaped).  Here: a parallel one-sided
+// Jacobi method (Hestenes), which is nothing but column rotations -- the access pattern the rest of this library is
+// built around.  G starts as the symmetric matrix (shifted to be positive definite), n/2 disjoint column pairs are
+// orthogonalised per launch (round-robin tournament ordering, n-1 launches per sweep), one CTA per pair: the two columns
+// are read once (coalesced), their three inner products are reduced in a fixed order, and the rotated columns are
+// written back from shared memory.  G and V (<= 2 n^2 doubles, 52 MB at n = 1800) stay in the 126 MB L2 across rounds.
+// At convergence the columns of G are lambda_i v_i: the eigenvectors are the normalised columns (or the accumulated
+// rotations for semi-definite input), the eigenvalues are Rayleigh quotients v_i^T S v_i of the ORIGINAL matrix (one DMMA
+// GEMM + column dots), so the shift costs no accuracy.  Convergence: a sweep without a pair above
+// |g_i.g_j| > sqrt(n) eps |g_i||g_j| (the dgesvj criterion).  Results agree with LAPACK to ~1e-13 relative to the norm;
+// eigenvectors are defined up to sign (largest component made positive) and up to rotations inside degenerate spaces.
+#include "rb_common.cuh"
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+#include <vector>
+
+namespace {
+
+constexpr int EIG_THREADS = 256;
+constexpr int EIG_CACHE_MAX_N = 3072; // both columns of a pair cached in 48 KB of shared memory up to this n
+constexpr int EIG_MAX_SWEEPS = 60;
+
+// g = symmetric expansion of one triangle of a (+ shift on the diagonal); v = identity (if v != NULL)
+__global__ void __launch_bounds__(256) rb_eig_init_kernel(const double *__restrict__ a, i64 lda, int upper, double shift,
+                                                          double *__restrict__ g, double *__restrict__ v, i64 n)
+{
+    const i64 total = n * n, stride = (i64)gridDim.x * blockDim.x;
+    for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const i64 i = e % n, j = e / n;
+        const bool in_tri = upper ? (i <= j) : (i >= j);
+        double x = in_tri ? a[i + j * lda] : a[j + i * lda];
+        if (i == j) x += shift;
+        g[e] = x;
+        if (v) v[e] = (i == j) ? 1.0 : 0.0;
+    }
+}
+
+__global__ void __launch_bounds__(256) rb_eig_shift_diag_kernel(double *__restrict__ g, i64 n, double shift)
+{
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) g[i + i * n] += shift;
+}
+
+// fixed-order block reduction of three partial sums; every thread returns the totals
+__device__ __forceinline__ void block_sum3(double &a, double &b, double &c, double *red)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { red[warp * 3 + 0] = a; red[warp * 3 + 1] = b; red[warp * 3 + 2] = c; }
+    __syncthreads();
+    a = 0.0; b = 0.0; c = 0.0;
+#pragma unroll
+    for (int w = 0; w < EIG_THREADS / 32; ++w) { a += red[w * 3 + 0]; b += red[w * 3 + 1]; c += red[w * 3 + 2]; }
+    __syncthreads();
+}
+
+// per column: out[j] = sum_i |g[i,j]| (mode 0) or sqrt(sum_i g[i,j]^2) (mode 1); one CTA per column
+__global__ void __launch_bounds__(EIG_THREADS) rb_eig_colstat_kernel(const double *__restrict__ g, i64 n, int mode,
+                                                                    double *__restrict__ out)
+{
+    __shared__ double red[3 * EIG_THREADS / 32];
+    for (i64 j = blockIdx.x; j < n; j += gridDim.x) {
+        const double *col = g + j * n;
+        double a = 0.0, b = 0.0, c = 0.0;
+        for (i64 i = threadIdx.x; i < n; i += EIG_THREADS) {
+            const double x = col[i];
+            a += mode ? x * x : fabs(x);
+        }
+        block_sum3(a, b, c, red);
+        if (threadIdx.x == 0) out[j] = mode ? sqrt(a) : a;
+    }
+}
+
+// One round of the tournament: CTA k orthogonalises the column pair (i, j) of round `round`.
+template <bool ACCUM_V, bool CACHE>
+__global__ void __launch_bounds__(EIG_THREADS) rb_jacobi_round_kernel(double *__restrict__ g, double *__restrict__ v, i64 n,
+                                                                     i64 n_even, i64 round, double tol,
+                                                                     unsigned long long *__restrict__ rotations)
+{
+    extern __shared__ double cols[]; // CACHE: [2][n]
+    __shared__ double red[3 * EIG_THREADS / 32];
+    const i64 m = n_even - 1, k = blockIdx.x;
+    i64 i, j;
+    if (k == 0) { i = round; j = m; }
+    else { i = (round + k) % m; j = (round - k + m) % m; }
+    if (i > j) { const i64 t = i; i = j; j = t; }
+    if (j >= n) return; // odd n: this pair is the bye
+    double *gi = g + i * n, *gj = g + j * n;
+    double a = 0.0, b = 0.0, c = 0.0;
+    for (i64 r = threadIdx.x; r < n; r += EIG_THREADS) {
+        const double x = gi[r], y = gj[r];
+        if (CACHE) { cols[r] = x; cols[n + r] = y; }
+        a += x * x; b += y * y; c += x * y;
+    }
+    block_sum3(a, b, c, red);
+    if (!(fabs(c) > tol * (sqrt(a) * sqrt(b)))) return; // already orthogonal (also: zero column, NaN)
+    const double zeta = (b - a) / (2.0 * c);
+    const double t = copysign(1.0, zeta) / (fabs(zeta) + hypot(1.0, zeta));
+    const double cs = 1.0 / hypot(1.0, t), sn = cs * t;
+    for (i64 r = threadIdx.x; r < n; r += EIG_THREADS) {
+        const double x = CACHE ? cols[r] : gi[r], y = CACHE ? cols[n + r] : gj[r];
+        gi[r] = cs * x - sn * y;
+        gj[r] = sn * x + cs * y;
+    }
+    if (ACCUM_V) {
+        double *vi = v + i * n, *vj = v + j * n;
+        for (i64 r = threadIdx.x; r < n; r += EIG_THREADS) {
+            const double x = vi[r], y = vj[r];
+            vi[r] = cs * x - sn * y;
+            vj[r] = sn * x + cs * y;
+        }
+    }
+    if (threadIdx.x == 0) atomicAdd(rotations, 1ULL);
+}
+
+// v[:, j] = g[:, j] / norm[j]
+__global__ void __launch_bounds__(256) rb_eig_normalize_kernel(const double *__restrict__ g, const double *__restrict__ norm,
+                                                               double *__restrict__ v, i64 n)
+{
+    const i64 total = n * n, stride = (i64)gridDim.x * blockDim.x;
+    for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const double d = norm[e / n];
+        v[e] = d > 0.0 ? g[e] / d : 0.0;
+    }
+}
+
+// z[:, c] = sign * v[:, perm[c]] for c < ncols, sign chosen so that the component of largest magnitude (lowest index on
+// ties) is positive; one CTA per output column
+__global__ void __launch_bounds__(EIG_THREADS) rb_eig_permute_kernel(const double *__restrict__ v, i64 n,
+                                                                    const i64 *__restrict__ perm, double *__restrict__ z,
+                                                                    i64 ldz, i64 ncols)
+{
+    __shared__ double bestv[EIG_THREADS];
+    __shared__ i64 besti[EIG_THREADS];
+    for (i64 c = blockIdx.x; c < ncols; c += gridDim.x) {
+        const double *src = v + perm[c] * n;
+        double bv = -1.0;
+        i64 bi = 0;
+        for (i64 r = threadIdx.x; r < n; r += EIG_THREADS) {
+            const double x = fabs(src[r]);
+            if (x > bv) { bv = x; bi = r; }
+        }
+        bestv[threadIdx.x] = bv; besti[threadIdx.x] = bi;
+        __syncthreads();
+        for (int o = EIG_THREADS / 2; o > 0; o >>= 1) {
+            if (threadIdx.x < o) {
+                const double ov = bestv[threadIdx.x + o];
+                const i64 oi = besti[threadIdx.x + o];
+                if (ov > bestv[threadIdx.x] || (ov == bestv[threadIdx.x] && oi < besti[threadIdx.x])) {
+                    bestv[threadIdx.x] = ov; besti[threadIdx.x] = oi;
+                }
+            }
+            __syncthreads();
+        }
+        const double sgn = (n > 0 && src[besti[0]] < 0.0) ? -1.0 : 1.0;
+        __syncthreads();
+        for (i64 r = threadIdx.x; r < n; r += EIG_THREADS) z[r + c * ldz] = sgn * src[r];
+    }
+}
+
+int grid_for(rb_ctx *ctx, i64 total, int per_block)
+{
+    i64 blocks = rb_cdiv(total, per_block);
+    const i64 cap = (i64)ctx->num_sms * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+template <bool ACCUM_V>
+int launch_round(rb_ctx *ctx, double *g, double *v, i64 n, i64 n_even, i64 round, double tol, unsigned long long *rot)
+{
+    const unsigned blocks = (unsigned)(n_even / 2);
+    if (n <= EIG_CACHE_MAX_N)
+        rb_jacobi_round_kernel<ACCUM_V, true><<<blocks, EIG_THREADS, (size_t)(2 * n * 8), ctx->stream>>>(g, v, n, n_even, round, tol, rot);
+    else
+        rb_jacobi_round_kernel<ACCUM_V, false><<<blocks, EIG_THREADS, 0, ctx->stream>>>(g, v, n, n_even, round, tol, rot);
+    RB_LAUNCHED(ctx);
+    return RB_OK;
+}
+
+// Workspace of one solve, in doubles: G, V, W (n^2 each) + lam, stat (n each) + perm (n int64) + the rotation counter.
+i64 eig_work_elems(i64 n) { return 3 * n * n + 3 * n + 8; }
+
+// Eigen-decomposition of the full symmetric n x n matrix s (dense, ld = n; not modified).  psd: no shift and accumulated
+// rotations (accurate small eigenvalues of positive semi-definite input); else Gershgorin shift and normalised columns.
+// lam_host[n] ascending; z (device, ldz) receives the first ncols eigenvectors (NULL: none).  Synchronises the stream.
+int jacobi_eig(rb_ctx *ctx, i64 n, const double *s, bool psd, double *work, std::vector<double> &lam_host, double *z, i64 ldz,
+               i64 ncols, int *sweeps_out)
+{
+    lam_host.assign((size_t)n, 0.0);
+    if (sweeps_out) *sweeps_out = 0;
+    if (n == 0) return RB_OK;
+    double *g = work, *v = g + n * n, *w = v + n * n, *lam = w + n * n, *stat = lam + n;
+    i64 *perm = (i64 *)(stat + n);
+    unsigned long long *rot = (unsigned long long *)(perm + n);
+    std::vector<double> host((size_t)n);
+    double shift = 0.0;
+    rb_eig_init_kernel<<<grid_for(ctx, n * n, 256), 256, 0, ctx->stream>>>(s, n, 1, 0.0, g, psd ? v : nullptr, n);
+    RB_LAUNCHED(ctx);
+    if (!psd) { // Gershgorin: every eigenvalue lies in [-R, R], R = max column sum of |s|; G = S + 1.5 R I has cond <= 5
+        rb_eig_colstat_kernel<<<grid_for(ctx, n, 1), EIG_THREADS, 0, ctx->stream>>>(g, n, 0, stat);
+        RB_LAUNCHED(ctx);
+        RB_CUDA(cudaMemcpyAsync(host.data(), stat, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        RB_CUDA(cudaStreamSynchronize(ctx->stream));
+        double r = 0.0;
+        for (double x : host) {
+            if (!(x == x) || std::isinf(x)) { rb_set_error("eigen-solver: the matrix holds non-finite values"); return RB_ERR_INVALID; }
+            if (x > r) r = x;
+        }
+        shift = r > 0.0 ? 1.5 * r : 1.0; // zero matrix: G = I, every vector is an eigenvector
+        if (shift > 0.0) {
+            rb_eig_shift_diag_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(g, n, shift);
+            RB_LAUNCHED(ctx);
+        }
+    }
+    const i64 n_even = n + (n & 1);
+    const double tol = std::sqrt((double)n) * 1.1102230246251565e-16;
+    int sweeps = 0;
+    bool converged = n < 2;
+    for (; sweeps < EIG_MAX_SWEEPS && !converged; ++sweeps) {
+        RB_CUDA(cudaMemsetAsync(rot, 0, 8, ctx->stream));
+        for (i64 round = 0; round < n_even - 1; ++round) {
+            if (psd) RB_TRY(launch_round<true>(ctx, g, v, n, n_even, round, tol, rot));
+            else RB_TRY(launch_round<false>(ctx, g, v, n, n_even, round, tol, rot));
+        }
+        unsigned long long nrot = 0;
+        RB_CUDA(cudaMemcpyAsync(&nrot, rot, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        RB_CUDA(cudaStreamSynchronize(ctx->stream));
+        converged = nrot == 0;
+    }
+    if (sweeps_out) *sweeps_out = sweeps;
+    if (!converged) {
+        rb_set_error("eigen-solver: Jacobi sweeps did not converge in %d sweeps (n = %lld)", EIG_MAX_SWEEPS, (long long)n);
+        return RB_ERR_CUDA;
+    }
+    if (!psd) { // eigenvectors = normalised columns of G (= lambda_i v_i with lambda_i >= 0.5 R > 0)
+        rb_eig_colstat_kernel<<<grid_for(ctx, n, 1), EIG_THREADS, 0, ctx->stream>>>(g, n, 1, stat);
+        RB_LAUNCHED(ctx);
+        rb_eig_normalize_kernel<<<grid_for(ctx, n * n, 256), 256, 0, ctx->stream>>>(g, stat, v, n);
+        RB_LAUNCHED(ctx);
+    }
+    // Rayleigh quotients with the original matrix: W = S V, lam_i = v_i . w_i
+    RB_TRY(rb_gemm_core(ctx, false, false, n, n, n, 1.0, s, n, 0, v, n, 0, 0.0, w, n, 0, 1, 0));
+    RB_TRY(rb_einsum_ip_ip(ctx, v, n, w, n, lam, n, n));
+    RB_CUDA(cudaMemcpyAsync(host.data(), lam, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    RB_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::vector<i64> order((size_t)n);
+    std::iota(order.begin(), order.end(), (i64)0);
+    std::stable_sort(order.begin(), order.end(), [&](i64 x, i64 y) { return host[(size_t)x] < host[(size_t)y]; });
+    for (i64 c = 0; c < n; ++c) lam_host[(size_t)c] = host[(size_t)order[(size_t)c]];
+    if (z && ncols > 0) {
+        RB_CUDA(cudaMemcpyAsync(perm, order.data(), (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        rb_eig_permute_kernel<<<grid_for(ctx, ncols, 1), EIG_THREADS, 0, ctx->stream>>>(v, n, perm, z, ldz, ncols);
+        RB_LAUNCHED(ctx);
+        RB_CUDA(cudaStreamSynchronize(ctx->stream)); // `order` must outlive the upload
+    }
+    return RB_OK;
+}
+
+// positive semi-definite path with a fallback: if the Rayleigh quotients reveal an indefinite matrix, one-sided Jacobi
+// without a shift only sees |lambda|, so the solve is repeated with the shift
+int jacobi_eig_psd(rb_ctx *ctx, i64 n, const double *s, double *work, std::vector<double> &lam, double *z, i64 ldz, i64 ncols)
+{
+    RB_TRY(jacobi_eig(ctx, n, s, true, work, lam, z, ldz, ncols, nullptr));
+    double lo = 0.0, hi = 0.0;
+    for (double x : lam) { lo = std::min(lo, x); hi = std::max(hi, std::fabs(x)); }
+    if (lo < -1e-10 * hi) RB_TRY(jacobi_eig(ctx, n, s, false, work, lam, z, ldz, ncols, nullptr));
+    return RB_OK;
+}
+
+} // namespace
+
+extern "C" int rb_dsyev(rb_ctx *ctx, char jobz, char uplo, int n_, const double *a, int64_t lda, double *w, double *z,
+                        int64_t ldz)
+{
+    RB_REQUIRE(ctx, "rb_dsyev: ctx is NULL");
+    RB_REQUIRE(jobz == 'V' || jobz == 'v' || jobz == 'N' || jobz == 'n', "rb_dsyev: jobz must be 'V' or 'N'");
+    RB_REQUIRE(rb_is_u(uplo) || rb_is_l(uplo), "rb_dsyev: uplo must be 'U' or 'L'");
+    RB_REQUIRE(n_ >= 0, "rb_dsyev: negative dimension");
+    const i64 n = n_;
+    if (n == 0) return RB_OK;
+    const bool want_z = jobz == 'V' || jobz == 'v';
+    RB_REQUIRE(a && w && lda >= n && (!want_z || (z && ldz >= n)), "rb_dsyev: NULL buffer or leading dimension too small");
+    RB_CUDA(cudaSetDevice(ctx->device));
+    void *ws;
+    RB_TRY(rb_ws_reserve(ctx, 0, (n * n + eig_work_elems(n)) * 8, &ws));
+    double *s = (double *)ws, *work = s + n * n;
+    rb_eig_init_kernel<<<grid_for(ctx, n * n, 256), 256, 0, ctx->stream>>>(a, lda, rb_is_u(uplo) ? 1 : 0, 0.0, s, nullptr, n);
+    RB_LAUNCHED(ctx);
+    std::vector<double> lam;
+    RB_TRY(jacobi_eig(ctx, n, s, false, work, lam, want_z ? z : nullptr, ldz, want_z ? n : 0, nullptr));
+    RB_CUDA(cudaMemcpyAsync(w, lam.data(), (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    RB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return RB_OK;
+}
+
+extern "C" int rb_dspev(rb_ctx *ctx, int n_, const double *ap, double *w, double *z, int64_t ldz)
+{
+    RB_REQUIRE(ctx, "rb_dspev: ctx is NULL");
+    RB_REQUIRE(n_ >= 0, "rb_dspev: negative dimension");
+    const i64 n = n_;
+    if (n == 0) return RB_OK;
+    RB_REQUIRE(ap && w && (!z || ldz >= n), "rb_dspev: NULL buffer or ldz too small");
+    RB_CUDA(cudaSetDevice(ctx->device));
+    void *ws;
+    RB_TRY(rb_ws_reserve(ctx, 0, (n * n + eig_work_elems(n)) * 8, &ws));
+    double *s = (double *)ws, *work = s + n * n;
+    RB_TRY(rb_unpack_upper(ctx, ap, n, s)); // full symmetric matrix, both triangles
+    std::vector<double> lam;
+    RB_TRY(jacobi_eig(ctx, n, s, false, work, lam, z, ldz, z ? n : 0, nullptr));
+    RB_CUDA(cudaMemcpyAsync(w, lam.data(), (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    RB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return RB_OK;
+}
+
+extern "C" int rb_dspgv(rb_ctx *ctx, int n_, const double *ap, const double *bp, int m_, double *w, double *z, int64_t ldz)
+{
+    RB_REQUIRE(ctx, "rb_dspgv: ctx is NULL");
+    RB_REQUIRE(n_ >= 0 && m_ >= 0 && m_ <= n_, "rb_dspgv: bad dimensions (n = %d, num_orb = %d)", n_, m_);
+    const i64 n = n_, m = m_;
+    if (n == 0 || m == 0) return RB_OK;
+    RB_REQUIRE(ap && bp && w && z && ldz >= n, "rb_dspgv: NULL buffer or ldz too small");
+    RB_CUDA(cudaSetDevice(ctx->device));
+    void *ws;
+    RB_TRY(rb_ws_reserve(ctx, 0, (5 * n * n + n + eig_work_elems(n)) * 8, &ws));
+    double *a = (double *)ws, *b = a + n * n, *us = b + n * n, *t1 = us + n * n, *y = t1 + n * n, *scale = y + n * n,
+           *work = scale + n;
+    RB_TRY(rb_unpack_upper(ctx, ap, n, a));
+    RB_TRY(rb_unpack_upper(ctx, bp, n, b));
+    // B = U D U^T (positive definite); Us = U D^-1/2 makes Us^T B Us = I
+    std::vector<double> d;
+    RB_TRY(jacobi_eig_psd(ctx, n, b, work, d, us, n, n));
+    RB_REQUIRE(d[0] > 0.0, "rb_dspgv: the overlap matrix is not positive definite (smallest eigenvalue %.3e)", d[0]);
+    std::vector<double> sc((size_t)n);
+    for (i64 i = 0; i < n; ++i) sc[(size_t)i] = 1.0 / std::sqrt(d[(size_t)i]);
+    RB_CUDA(cudaMemcpyAsync(scale, sc.data(), (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    RB_TRY(rb_einsum_ij_j(ctx, us, n, scale, t1, n, n, n)); // t1 = Us (scaled copy)
+    RB_CUDA(cudaStreamSynchronize(ctx->stream));
+    // A' = Us^T A Us
+    RB_TRY(rb_gemm_core(ctx, false, false, n, n, n, 1.0, a, n, 0, t1, n, 0, 0.0, y, n, 0, 1, 0));   // y = A Us
+    RB_TRY(rb_gemm_core(ctx, true, false, n, n, n, 1.0, t1, n, 0, y, n, 0, 0.0, b, n, 0, 1, 1));    // b = upper(Us^T A Us)
+    RB_TRY(rb_symmetrize(ctx, b, n, n, true));
+    std::vector<double> lam;
+    RB_TRY(jacobi_eig(ctx, n, b, false, work, lam, y, n, m, nullptr));                                // y[:, :m] = eigenvectors of A'
+    RB_TRY(rb_gemm_core(ctx, false, false, n, m, n, 1.0, t1, n, 0, y, n, 0, 0.0, z, ldz, 0, 1, 0));  // z = Us Y
+    RB_CUDA(cudaMemcpyAsync(w, lam.data(), (size_t)m * 8, cudaMemcpyHostToDevice, ctx->stream));
+    RB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return RB_OK;
+}
+
+extern "C" int rb_matrix_power(rb_ctx *ctx, int n_, const double *a, int64_t lda, double p, double threshold, double *out,
+                               int64_t ldo, int *n_nonsingular)
+{
+    RB_REQUIRE(ctx, "rb_matrix_power: ctx is NULL");
+    RB_REQUIRE(n_ >= 0, "rb_matrix_power: negative dimension");
+    const i64 n = n_;
+    if (n_nonsingular) *n_nonsingular = 0;
+    if (n == 0) return RB_OK;
+    RB_REQUIRE(a && out && lda >= n && ldo >= n, "rb_matrix_power: NULL buffer or leading dimension too small");
+    RB_CUDA(cudaSetDevice(ctx->device));
+    void *ws;
+    RB_TRY(rb_ws_reserve(ctx, 0, (3 * n * n + n + eig_work_elems(n)) * 8, &ws));
+    double *s = (double *)ws, *vz = s + n * n, *vs = vz + n * n, *scale = vs + n * n, *work = scale + n;
+    // dsyev(.., 'L', ..) in the reference: the lower triangle is the one that is read
+    rb_eig_init_kernel<<<grid_for(ctx, n * n, 256), 256, 0, ctx->stream>>>(a, lda, 0, 0.0, s, nullptr, n);
+    RB_LAUNCHED(ctx);
+    std::vector<double> lam;
+    RB_TRY(jacobi_eig_psd(ctx, n, s, work, lam, vz, n, n));
+    std::vector<double> sc((size_t)n);
+    int kept = 0;
+    for (i64 i = 0; i < n; ++i) {
+        const double ev = lam[(size_t)i];
+        if (ev >= threshold) { sc[(size_t)i] = std::pow(std::sqrt(ev), p); ++kept; }
+        else sc[(size_t)i] = 0.0;
+    }
+    if (n_nonsingular) *n_nonsingular = kept;
+    RB_CUDA(cudaMemcpyAsync(scale, sc.data(), (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    RB_TRY(rb_einsum_ij_j(ctx, vz, n, scale, vs, n, n, n));
+    RB_CUDA(cudaStreamSynchronize(ctx->stream));
+    RB_TRY(rb_gemm_core(ctx, false, true, n, n, n, 1.0, vs, n, 0, vs, n, 0, 0.0, out, ldo, 0, 1, 1));
+    return rb_symmetrize(ctx, out, n, ldo, true);
+}

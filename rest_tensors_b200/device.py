@@ -122,6 +122,21 @@ class Context:
         check(lib.rb_special_dgemm_01(self.h, _p(ten3), x_a, y_a, z_a, sx, lx, sz, lz, _p(b), ldb, lcb, alpha, beta),
               "rb_special_dgemm_01")
 
+    # -- eigen-solvers (one-sided Jacobi; these synchronise) --
+    def dsyev(self, jobz, uplo, n, a, lda, w, z, ldz) -> None:
+        check(lib.rb_dsyev(self.h, ch(jobz), ch(uplo), n, _p(a), lda, _p(w), _p(z), ldz), "rb_dsyev")
+
+    def dspev(self, n, ap, w, z, ldz) -> None:
+        check(lib.rb_dspev(self.h, n, _p(ap), _p(w), _p(z), ldz), "rb_dspev")
+
+    def dspgv(self, n, ap, bp, m, w, z, ldz) -> None:
+        check(lib.rb_dspgv(self.h, n, _p(ap), _p(bp), m, _p(w), _p(z), ldz), "rb_dspgv")
+
+    def matrix_power(self, n, a, lda, p, threshold, out, ldo) -> int:
+        kept = C.c_int(0)
+        check(lib.rb_matrix_power(self.h, n, _p(a), lda, p, threshold, _p(out), ldo, C.byref(kept)), "rb_matrix_power")
+        return kept.value
+
     # -- layout --
     def pack_upper(self, full, n, packed) -> None:
         check(lib.rb_pack_upper(self.h, _p(full), n, _p(packed)), "rb_pack_upper")

@@ -328,6 +328,18 @@ class MatrixFull:
 # ======================================================================================================
 # MatrixUpper
 # ======================================================================================================
+    # -- eigen-solvers (matrix_blas_lapack.rs:775-797, 1004-1062): one-sided Jacobi on the GPU behind the LAPACK names --
+    def lapack_dsyev(self):
+        """(eigenvectors [n, n], eigenvalues ascending, n) or None for a non-square matrix"""
+        if self.size[0] != self.size[1]:
+            return None
+        vec, w, n = _dsyev(self, "V")
+        return vec, w, n
+
+    def lapack_power(self, p: float, threshold: float) -> Optional["MatrixFull"]:
+        return _power(self, p, threshold)
+
+
 class MatrixUpper:
     """src/matrix/matrixupper.rs:231-234: ``size`` = n(n+1)/2 (the packed length), ``data``."""
 
@@ -406,6 +418,23 @@ class MatrixUpper:
 # ======================================================================================================
 # RIFull
 # ======================================================================================================
+    # -- packed eigen-solvers (matrix_blas_lapack.rs:1075-1147) --
+    def lapack_dspevx(self):
+        """(eigenvectors [n, n], eigenvalues ascending, n_found) of the packed-upper symmetric matrix"""
+        n = self.size2d()[0]
+        if n * (n + 1) // 2 != self.data.size:
+            raise RestB200Error("lapack_dspevx: the packed length is not triangular")
+        w = np.zeros(n, dtype=np.float64)
+        z = MatrixFull.new([n, n], 0.0)
+        found = C.c_int(0)
+        check(lib.rb_host_dspevx(n, _ptr(self.data), _ptr(w), _ptr(z.data), C.byref(found)), "lapack_dspevx")
+        return z, w, found.value
+
+    def lapack_dspgvx(self, ovlp: "MatrixUpper", num_orb: int):
+        """solve A x = lambda B x (A = self, B = ovlp, both packed upper): (eigenvectors [n, num_orb], eigenvalues)"""
+        return _dspgvx(self, ovlp, num_orb)
+
+
 class RIFull:
     """src/ri.rs:18-24: rank-3 column-major tensor, linear index x + y*s0 + z*s0*s1."""
 
@@ -993,3 +1022,40 @@ def _dgemv(matr_a: MatrixFull, vec_x: np.ndarray, vec_y: np.ndarray, trans: str,
         raise ValueError(f"ERROR:: Matr_A[{m},{n},{trans}] * Vec_X[{vec_x.size}] -> Vec_Y[{vec_y.size}]")
     check(lib.rb_host_dgemv(ch(trans), m, n, alpha, _ptr(matr_a.data), max(m, 1), _ptr(vec_x), incx, beta, _ptr(vec_y),
                             incy), "_dgemv")
+
+
+# ======================================================================================================
+# eigen-solvers (matrix_blas_lapack.rs:319-352, 599-652, 2123-2185)
+# ======================================================================================================
+def _dsyev(matr_a: MatrixFull, jobz: str):
+    """(Some(eigenvectors) | None, eigenvalues ascending, n); panics (raises) for a non-square matrix like the reference"""
+    n = matr_a.size[0]
+    if matr_a.size[0] != matr_a.size[1]:
+        raise RestB200Error("Error in _dsyev: the algorithm is only vaild for real symmetric matrices")
+    w = np.zeros(n, dtype=np.float64)
+    vec = MatrixFull.new([n, n], 0.0) if jobz in ("V", "v") else None
+    check(lib.rb_host_dsyev(ch(jobz), n, _ptr(matr_a.data), _ptr(w), None if vec is None else _ptr(vec.data)), "_dsyev")
+    return vec, w, n
+
+
+def _power(matr_a: MatrixFull, p: float, threshold: float) -> Optional[MatrixFull]:
+    """A^p over the eigenvalues >= threshold (e.g. p = -0.5: S^-1/2); None for a non-square matrix"""
+    if matr_a.size[0] != matr_a.size[1]:
+        return None
+    n = matr_a.size[0]
+    om = MatrixFull.new([n, n], 0.0)
+    kept = C.c_int(0)
+    check(lib.rb_host_power(n, _ptr(matr_a.data), float(p), float(threshold), _ptr(om.data), C.byref(kept)), "_power")
+    return om
+
+
+def _dspgvx(matr_a: MatrixUpper, matr_b: MatrixUpper, num_orb: int):
+    if matr_a.data.size != matr_b.data.size:
+        raise RestB200Error("ERROR:: _dspgvx for BasicMatUp, Matr_A and Matr_B have different size")
+    n = matr_a.size2d()[0]
+    if not 0 <= num_orb <= n:
+        raise RestB200Error("Error:: The number of outcoming eigenvectors is unequal to the orbital number")
+    w = np.zeros(num_orb, dtype=np.float64)
+    z = MatrixFull.new([n, num_orb], 0.0)
+    check(lib.rb_host_dspgvx(n, _ptr(matr_a.data), _ptr(matr_b.data), num_orb, _ptr(w), _ptr(z.data)), "_dspgvx")
+    return z, w

@@ -165,3 +165,26 @@ def test_oracle_iajb_vs_numpy_einsum(oracle):
         assert got.shape == ref.shape
         if ref.size:
             assert np.max(np.abs(got - ref)) <= 1e-13 * max(1.0, np.max(np.abs(ref)))
+
+
+def test_oracle_lapack_wrappers_vs_numpy(oracle_blas):
+    """The oracle's eigen-solver entry points (the reference's LAPACK calls with its arguments) against numpy.linalg."""
+    n = 9
+    a = oracle_blas.fill_linear(n * n, 51).reshape((n, n), order="F"); a = a + a.T
+    b = oracle_blas.fill_linear(n * n, 52).reshape((n, n), order="F"); b = b @ b.T + n * np.eye(n)
+    flat = lambda m: np.ascontiguousarray(m.reshape(-1, order="F"))  # noqa: E731
+    pack = lambda m: np.ascontiguousarray(np.concatenate([m[: j + 1, j] for j in range(n)]))  # noqa: E731
+    wnp = np.linalg.eigvalsh(a)
+    _, w = oracle_blas.dsyev(flat(a), n)
+    assert np.max(np.abs(w - wnp)) <= 1e-13 * np.max(np.abs(wnp))
+    z, w2, m = oracle_blas.dspevx(pack(a), n)
+    assert m == n and np.max(np.abs(w2 - wnp)) <= 1e-13 * np.max(np.abs(wnp))
+    zz, w3 = oracle_blas.dspgvx(pack(a), pack(b), n, 4)
+    l = np.linalg.cholesky(b); li = np.linalg.inv(l)
+    wgen = np.linalg.eigvalsh(li @ a @ li.T)[:4]
+    assert np.max(np.abs(w3 - wgen)) <= 1e-12 * np.max(np.abs(wgen))
+    zm = zz.reshape((n, 4), order="F")
+    assert np.max(np.abs(zm.T @ b @ zm - np.eye(4))) <= 1e-12
+    x, kept = oracle_blas.power(flat(b), n, -0.5, 1e-10)
+    xm = x.reshape((n, n), order="F")
+    assert kept == n and np.max(np.abs(xm @ b @ xm - np.eye(n))) <= 1e-12
