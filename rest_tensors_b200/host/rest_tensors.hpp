@@ -68,6 +68,25 @@ struct MatrixFull {
     }
     inline MatrixUpper to_matrixupper() const; // matrixfull.rs:638-646
 
+    // matrix_blas_lapack.rs:775-797: (eigenvectors, eigenvalues ascending); the lower triangle is read
+    std::pair<MatrixFull, std::vector<double>> lapack_dsyev() const
+    {
+        if (size[0] != size[1]) throw std::runtime_error("Error in _dsyev: the algorithm is only vaild for real symmetric matrices");
+        MatrixFull z = make(size, 0.0);
+        std::vector<double> w(size[0], 0.0);
+        rb_check(rb_host_dsyev('V', (int)size[0], data.data(), w.data(), z.data.data()), "lapack_dsyev");
+        return {std::move(z), std::move(w)};
+    }
+    // matrix_blas_lapack.rs:599-652 / 1004-1062: A^p over the eigenvalues >= threshold
+    MatrixFull lapack_power(double p, double threshold) const
+    {
+        if (size[0] != size[1]) throw std::runtime_error("Error: The matrix for power operations should be NxN");
+        MatrixFull om = make(size, 0.0);
+        int kept = 0;
+        rb_check(rb_host_power((int)size[0], data.data(), p, threshold, om.data.data(), &kept), "lapack_power");
+        return om;
+    }
+
     // matrixfull.rs:1388-1396 -> copy_mm_
     void copy_from_matr(Range rx, Range ry, const MatrixFull &from, Range frx, Range fry)
     {
@@ -109,6 +128,29 @@ struct MatrixUpper {
         if (i > j) std::swap(i, j);
         size_t tp = (j + 1) * j / 2 + i;
         return tp < data.size() ? std::optional<size_t>(tp) : std::nullopt;
+    }
+    size_t dim() const { return (size_t)(std::sqrt(1.0 + 8.0 * (double)size) * 0.5 - 0.5); }
+    // matrix_blas_lapack.rs:1075-1095: (eigenvectors [n, n], eigenvalues ascending)
+    std::pair<MatrixFull, std::vector<double>> lapack_dspevx() const
+    {
+        const size_t n = dim();
+        if (n * (n + 1) / 2 != size) throw std::runtime_error("lapack_dspevx: the packed length is not triangular");
+        MatrixFull z = MatrixFull::make({n, n}, 0.0);
+        std::vector<double> w(n, 0.0);
+        int found = 0;
+        rb_check(rb_host_dspevx((int)n, data.data(), w.data(), z.data.data(), &found), "lapack_dspevx");
+        return {std::move(z), std::move(w)};
+    }
+    // matrix_blas_lapack.rs:1096-1147: A x = lambda B x, the num_orb lowest pairs; eigenvectors [n, num_orb]
+    std::pair<MatrixFull, std::vector<double>> lapack_dspgvx(const MatrixUpper &ovlp, size_t num_orb) const
+    {
+        const size_t n = dim();
+        if (ovlp.size != size) throw std::runtime_error("ERROR:: _dspgvx for BasicMatUp, Matr_A and Matr_B have different size");
+        if (num_orb > n) throw std::runtime_error("Error:: The number of outcoming eigenvectors is unequal to the orbital number");
+        MatrixFull z = MatrixFull::make({n, num_orb}, 0.0);
+        std::vector<double> w(num_orb, 0.0);
+        rb_check(rb_host_dspgvx((int)n, data.data(), ovlp.data.data(), (int)num_orb, w.data(), z.data.data()), "lapack_dspgvx");
+        return {std::move(z), std::move(w)};
     }
     // matrixupper.rs:330-373
     std::optional<MatrixFull> to_matrixfull() const

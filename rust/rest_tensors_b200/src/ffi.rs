@@ -52,6 +52,11 @@ extern "C" {
     /// RPA-type out[P,Q] = sum_{(l,r) in box} w[l,r] mo[P,l,r] mo[Q,l,r]; w may be null
     pub fn rb_host_ri_mo_pq(mo: *const c_double, np: c_int, nl: c_int, nr: c_int, l0: c_int, ll: c_int, r0: c_int, rl: c_int,
                             w: *const c_double, out: *mut c_double) -> c_int;
+    /// eigen-solvers with the reference's conventions (matrix_blas_lapack.rs:319-352, 599-652, 1075-1147, 2123-2185)
+    pub fn rb_host_dsyev(jobz: c_char, n: c_int, a: *const c_double, w: *mut c_double, z: *mut c_double) -> c_int;
+    pub fn rb_host_dspevx(n: c_int, ap: *const c_double, w: *mut c_double, z: *mut c_double, n_found: *mut c_int) -> c_int;
+    pub fn rb_host_dspgvx(n: c_int, ap: *const c_double, bp: *const c_double, num_orb: c_int, w: *mut c_double, z: *mut c_double) -> c_int;
+    pub fn rb_host_power(n: c_int, a: *const c_double, p: c_double, threshold: c_double, out: *mut c_double, n_nonsingular: *mut c_int) -> c_int;
 
     // device-resident API (device pointers)
     pub fn rb_ri_ao2mo(ctx: *mut RbCtx, cl: *const c_double, nl: c_int, cr: *const c_double, nr: c_int,

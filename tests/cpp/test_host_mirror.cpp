@@ -11,6 +11,8 @@ void orc_ri_ao2mo_f(const double *c, const double *ri, double *mo, int ns, int n
 void orc_ri_dp(const double *ri, const double *dm, double *d, int nb, int nx);
 void orc_ri_j(const double *ri, const double *d, double *j, int nb, int nx);
 void orc_ri_k(const double *ri, const double *ct, double *k, int nb, int no, int nx);
+int orc_dsyev(char jobz, int n, double *a, double *w);
+int orc_load_blas(const char *path);
 void orc_ri_iajb(int np, const double *mo_a, int nl_a, int l0a, int lla, int r0a, int rla, const double *mo_b, int nl_b,
                  int l0b, int llb, int r0b, int rlb, double *out);
 void orc_ri_mo_pq(const double *mo_a, int npa, const double *mo_b, int npb, int nl, int l0, int ll, int r0, int rl,
@@ -96,6 +98,45 @@ int main()
         bool thr = false;
         try { M.ri_iajb({0, 6}, {0, 7}, {0, 5}, {0, 7}); } catch (const std::runtime_error &) { thr = true; }
         CHECK(thr, "ri_iajb box outside the tensor must throw");
+    }
+    // eigen-solver behind lapack_dsyev: eigenvalues vs residual / orthogonality invariants (and vs LAPACK when OPENBLAS_PATH is set)
+    {
+        const int n = 50;
+        auto av = fill((size_t)n * n, 10);
+        for (int j = 0; j < n; ++j) for (int i = 0; i < j; ++i) av[(size_t)i + (size_t)j * n] = av[(size_t)j + (size_t)i * n]; // symmetric
+        auto A = MatrixFull::from_vec({(size_t)n, (size_t)n}, av);
+        auto zw = A.lapack_dsyev();
+        double res = 0.0, orth = 0.0, wmax = 0.0;
+        for (int c = 0; c < n; ++c) wmax = std::max(wmax, std::fabs(zw.second[c]));
+        for (int c = 0; c < n; ++c)
+            for (int r = 0; r < n; ++r) {
+                double s = 0.0;
+                for (int k = 0; k < n; ++k) s += av[(size_t)r + (size_t)k * n] * zw.first.data[(size_t)k + (size_t)c * n];
+                res = std::max(res, std::fabs(s - zw.second[c] * zw.first.data[(size_t)r + (size_t)c * n]));
+            }
+        for (int c = 0; c < n; ++c)
+            for (int d = 0; d < n; ++d) {
+                double s = 0.0;
+                for (int k = 0; k < n; ++k) s += zw.first.data[(size_t)k + (size_t)c * n] * zw.first.data[(size_t)k + (size_t)d * n];
+                orth = std::max(orth, std::fabs(s - (c == d ? 1.0 : 0.0)));
+            }
+        CHECK(res < 1e-11 * wmax * n && orth < 1e-12 * n, "lapack_dsyev residual / orthogonality");
+        if (const char *blas = std::getenv("OPENBLAS_PATH")) {
+            if (orc_load_blas(blas) == 0) {
+                std::vector<double> aref = av, wref(n);
+                CHECK(orc_dsyev('V', n, aref.data(), wref.data()) == 0, "oracle dsyev");
+                CHECK(rel_err(zw.second, wref) < 1e-10, "lapack_dsyev eigenvalues vs LAPACK");
+            }
+        }
+        auto S = MatrixFull::from_vec({(size_t)n, (size_t)n}, av);
+        for (int i = 0; i < n; ++i) S.data[(size_t)i * (n + 1)] += 2.0 * n;   // diagonally dominant -> positive definite
+        auto X = S.lapack_power(-0.5, 1e-10);
+        double dev = 0.0;   // X S X = I
+        std::vector<double> t((size_t)n * n, 0.0), u((size_t)n * n, 0.0);
+        for (int j = 0; j < n; ++j) for (int k = 0; k < n; ++k) for (int i = 0; i < n; ++i) t[(size_t)i + (size_t)j * n] += X.data[(size_t)i + (size_t)k * n] * S.data[(size_t)k + (size_t)j * n];
+        for (int j = 0; j < n; ++j) for (int k = 0; k < n; ++k) for (int i = 0; i < n; ++i) u[(size_t)i + (size_t)j * n] += t[(size_t)i + (size_t)k * n] * X.data[(size_t)k + (size_t)j * n];
+        for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) dev = std::max(dev, std::fabs(u[(size_t)i + (size_t)j * n] - (i == j ? 1.0 : 0.0)));
+        CHECK(dev < 1e-11 * n, "lapack_power(-0.5): X S X = I");
     }
     // panics
     bool threw = false;

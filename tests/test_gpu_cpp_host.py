@@ -31,5 +31,10 @@ def test_cpp_host_mirror_compiles_and_links(tmp_path):
 @pytest.mark.gpu
 def test_cpp_host_mirror_runs(tmp_path):
     exe = _build(str(tmp_path))
-    out = subprocess.run([exe], capture_output=True, text=True, timeout=240)
+    from oracle.api import find_openblas
+    env = dict(os.environ)
+    blas = find_openblas()
+    if blas:
+        env["OPENBLAS_PATH"] = blas           # lets the C++ test compare lapack_dsyev with LAPACK's dsyev too
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=240, env=env)
     assert out.returncode == 0 and "CPP_HOST_MIRROR_OK" in out.stdout, out.stdout + out.stderr
