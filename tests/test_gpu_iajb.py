@@ -246,3 +246,37 @@ def test_symmetric_case_with_beta_keeps_blas_semantics(ctx, oracle_blas):
     mod = _dev(ctx, mo)
     ctx.ri_iajb(np_, mod, np_, nl, nr, box, mod, np_, nl, nr, box, 1.0, out, m)
     assert_close_1e10(out.cpu().numpy(), g + c0, "iajb symmetric box, beta = 1")
+
+
+def test_consumers_at_config_c_scale(ctx, oracle_blas):
+    """Bench-sized inputs (config C: naux = 1700, nocc = 60, nvir = 540) straight from the device-side occ-vir ao2mo:
+    an (ia|jb) block of 12 x 12 occupied orbitals (6480 x 6480, K = 1700) in full against the oracle + OpenBLAS, and the
+    size-independent cross-check ||G||_F^2 = ||Pi||_F^2 between the two consumers on a whole-l box."""
+    from rest_tensors_b200.device import ShardedRI
+    nb, nx, no = 600, 1700, 60
+    nv = nb - no
+    sh = ShardedRI(ctx, nb, nx).fill_synthetic()
+    c = ctx.empty(nb * nb); ctx.fill_linear(c, nb * nb, 3, 0, nb ** -0.5)
+    mo = sh.ao2mo(c[: nb * no], no, c[nb * no:], nv)              # [1700, 60, 540] in HBM
+    del sh
+    mo_h = mo.cpu().numpy()
+    li = 12
+    ba, bb = (0, li, 0, nv), (li, li, 0, nv)
+    m = li * nv
+    g = ctx.empty(m * m)
+    ctx.ri_iajb(nx, mo, nx, no, nv, ba, mo, nx, no, nv, bb, 0.0, g, m)
+    assert_close_1e10(g.cpu().numpy(), oracle_blas.ri_iajb(nx, mo_h, no, ba, mo_h, no, bb), "(ia|jb) off-diagonal block, config C")
+    ctx.ri_iajb(nx, mo, nx, no, nv, ba, mo, nx, no, nv, ba, 0.0, g, m)
+    gd = g.cpu().numpy()
+    assert_close_1e10(gd, oracle_blas.ri_iajb(nx, mo_h, no, ba, mo_h, no, ba), "(ia|jb) diagonal block, config C")
+    gm = gd.reshape((m, m), order="F")
+    assert np.array_equal(gm, gm.T)
+    # whole-l box of 4 virtuals: both consumers are functions of X = mo[:, :, 0:4] (1700 x 240)
+    box = (0, no, 0, 4)
+    k = no * 4
+    g2 = ctx.empty(k * k); pi = ctx.empty(nx * nx)
+    ctx.ri_iajb(nx, mo, nx, no, nv, box, mo, nx, no, nv, box, 0.0, g2, k)
+    ctx.ri_mo_pq(mo, nx, nx, mo, nx, nx, no, nv, box, None, 0.0, pi, nx)
+    a, b = float(torch.sum(g2 * g2)), float(torch.sum(pi * pi))
+    assert abs(a - b) <= 1e-11 * abs(b)
+    assert_close_1e10(pi.cpu().numpy(), oracle_blas.ri_mo_pq(mo_h, nx, mo_h, nx, no, box, None), "Pi, config C rows")
