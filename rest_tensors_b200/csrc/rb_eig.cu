@@ -255,7 +255,19 @@ int jacobi_eig(rb_ctx *ctx, i64 n, const double *s, bool psd, double *work, std:
     RB_TRY(rb_gemm_core(ctx, false, false, n, n, n, 1.0, s, n, 0, v, n, 0, 0.0, w, n, 0, 1, 0));
     RB_TRY(rb_einsum_ip_ip(ctx, v, n, w, n, lam, n, n));
     RB_CUDA(cudaMemcpyAsync(host.data(), lam, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (psd) { // semi-definite input: |g_i| = lambda_i carries the relative accuracy of small eigenvalues, the quotient does not
+        rb_eig_colstat_kernel<<<grid_for(ctx, n, 1), EIG_THREADS, 0, ctx->stream>>>(g, n, 1, stat);
+        RB_LAUNCHED(ctx);
+    }
     RB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (psd) {
+        double lo = 0.0, hi = 0.0;
+        for (double x : host) { lo = std::min(lo, x); hi = std::max(hi, std::fabs(x)); }
+        if (!(lo < -1e-10 * hi)) { // genuinely semi-definite (else the caller repeats the solve with the shift)
+            RB_CUDA(cudaMemcpyAsync(host.data(), stat, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            RB_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+    }
     std::vector<i64> order((size_t)n);
     std::iota(order.begin(), order.end(), (i64)0);
     std::stable_sort(order.begin(), order.end(), [&](i64 x, i64 y) { return host[(size_t)x] < host[(size_t)y]; });

@@ -169,3 +169,44 @@ def test_device_api_on_resident_buffers(ctx, oracle_blas):
     kept = ctx.matrix_power(n, torch.from_numpy(_flat(s)).to(f"cuda:{ctx.device}"), n, -0.5, 1e-10, out, n)
     assert kept == n
     assert_close_1e10(out.cpu().numpy(), oracle_blas.power(_flat(s), n, -0.5, 1e-10)[0], "rb_matrix_power")
+
+
+def test_dsyev_beyond_the_shared_memory_cache(ctx, oracle_blas):
+    """n > 3072: the column pair no longer fits the 48 KB cache and the rotation re-reads the columns through L2."""
+    n = 3100
+    a = _sym(oracle_blas, n, 83)
+    _, wref = oracle_blas.dsyev(_flat(a), n, "N")
+    ad = torch.from_numpy(_flat(a)).to(f"cuda:{ctx.device}")
+    w = ctx.empty(n); z = ctx.empty(n * n)
+    ctx.dsyev("V", "L", n, ad, n, w, z, n)
+    wg = w.cpu().numpy()
+    scale = np.max(np.abs(wref))
+    assert np.max(np.abs(wg - wref)) <= 1e-10 * scale
+    zt = z.view(n, n)                               # row-major view of the column-major matrix = Z^T
+    at = ad.view(n, n)                              # symmetric
+    res = torch.max(torch.abs(zt @ at - w[:, None] * zt)).item()
+    orth = torch.max(torch.abs(zt @ zt.T - torch.eye(n, dtype=torch.float64, device=zt.device))).item()
+    assert res <= 1e-11 * scale * n and orth <= 1e-12 * n, (res, orth)
+
+
+def test_clustered_and_ill_conditioned_spectra(rt, oracle_blas):
+    n = 120
+    q, _ = np.linalg.qr(oracle_blas.fill_linear(n * n, 84).reshape((n, n), order="F"))
+    # tight cluster next to isolated eigenvalues, both signs
+    lam = np.concatenate([np.full(40, 1.0) + 1e-9 * np.arange(40), -np.linspace(0.5, 3.0, 40), np.linspace(10.0, 1e3, 40)])
+    a = (q * lam) @ q.T
+    a = 0.5 * (a + a.T)
+    vec, w, _ = rt._dsyev(rt.MatrixFull.from_vec([n, n], _flat(a)), "V")
+    _, wref = oracle_blas.dsyev(_flat(a), n, "N")
+    z = vec.data.reshape((n, n), order="F")
+    assert np.max(np.abs(w - wref)) <= 1e-10 * 1e3
+    assert np.max(np.abs(a @ z - z * w)) <= 1e-10 * 1e3 and np.max(np.abs(z.T @ z - np.eye(n))) <= 1e-12 * n
+    # overlap-like SPD matrix with condition 1e8: S^-1/2 S S^-1/2 = I holds to cond * eps, small eigenvalues keep their
+    # relative accuracy (no shift on the semi-definite path)
+    lam = np.logspace(-8, 0, n)
+    s = (q * lam) @ q.T
+    s = 0.5 * (s + s.T)
+    x = rt._power(rt.MatrixFull.from_vec([n, n], _flat(s)), -0.5, 1e-12).data.reshape((n, n), order="F")
+    assert np.max(np.abs(x @ s @ x - np.eye(n))) <= 1e-6
+    vec, w, _ = rt._dsyev(rt.MatrixFull.from_vec([n, n], _flat(s)), "N")
+    assert np.max(np.abs(w - lam)) <= 1e-12          # absolute accuracy relative to the norm, like LAPACK
