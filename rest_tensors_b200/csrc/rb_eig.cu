@@ -16,6 +16,7 @@
 // |g_i.g_j| > sqrt(n) eps |g_i||g_j| (the dgesvj criterion).  Results agree with LAPACK to ~1e-13 relative to the norm;
 // eigenvectors are defined up to sign (largest component made positive) and up to rotations inside degenerate spaces.
 #include "rb_common.cuh"
+#include <cooperative_groups.h>
 #include <algorithm>
 #include <cmath>
 #include <numeric>
@@ -124,6 +125,138 @@ __global__ void __launch_bounds__(EIG_THREADS) rb_jacobi_round_kernel(double *__
     if (threadIdx.x == 0) atomicAdd(rotations, 1ULL);
 }
 
+// ---- cluster-resident solver for small matrices ---------------------------------------------------------------------
+// For n <= EIG_CLUSTER_MAX_N the whole working matrix lives in the DISTRIBUTED SHARED MEMORY of one thread-block cluster
+// (column c in CTA c % C, slot c / C; 16 CTAs x 182 KB hold n = 600), and the complete solve -- every round of every sweep
+// -- is ONE kernel: a warp takes a column pair into registers (<= 20 doubles per lane and column, local or remote shared
+// memory alike), reduces the three inner products with shuffles, writes the rotated columns back, and cluster.sync()
+// (~0.2 us) separates the rounds instead of a kernel boundary (~5-10 us with the dependent launch).  The round-per-launch
+// kernel above is latency-bound at these sizes (n = 264: 23 ms for ~2400 launches).  Convergence is decided uniformly by
+// every CTA from the per-CTA rotation counts of the sweep (read through DSMEM).
+namespace cg = cooperative_groups;
+constexpr int EIG_CLUSTER_MAX_N = 640;    // 20 elements per lane and column
+constexpr int EIG_CLUSTER_THREADS = 512;  // 16 warps per CTA
+
+__global__ void __launch_bounds__(EIG_CLUSTER_THREADS, 1)
+rb_jacobi_cluster_kernel(double *__restrict__ g, int n, int n_even, double tol, int max_sweeps, int *__restrict__ result)
+{
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ double cols[];            // this CTA's columns: [slots][n]
+    __shared__ int rot_count[2];
+    const int C = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = EIG_CLUSTER_THREADS / 32;
+    const int slots = (n - rank + C - 1) / C;   // columns rank, rank + C, ...
+    for (int sidx = 0; sidx < slots; ++sidx) {
+        const double *src = g + (size_t)(rank + sidx * C) * n;
+        for (int r = threadIdx.x; r < n; r += EIG_CLUSTER_THREADS) cols[(size_t)sidx * n + r] = src[r];
+    }
+    if (threadIdx.x < 2) rot_count[threadIdx.x] = 0;
+    cluster.sync();
+    const int m = n_even - 1, pairs = n_even / 2, total_warps = C * warps, gw = rank * warps + warp;
+    int sweep = 0, converged = 0;
+    for (; sweep < max_sweeps && !converged; ++sweep) {
+        const int slot = sweep & 1;
+        int my_rot = 0;
+        for (int round = 0; round < m; ++round) {
+            for (int k = gw; k < pairs; k += total_warps) {
+                int i, j;
+                if (k == 0) { i = round; j = m; }
+                else { i = (round + k) % m; j = (round - k + m) % m; }
+                if (i > j) { const int t = i; i = j; j = t; }
+                if (j >= n) continue;           // odd n: the bye
+                double *ci = cluster.map_shared_rank(cols + (size_t)(i / C) * n, i % C);
+                double *cj = cluster.map_shared_rank(cols + (size_t)(j / C) * n, j % C);
+                double x[EIG_CLUSTER_MAX_N / 32], y[EIG_CLUSTER_MAX_N / 32];
+                double a = 0.0, b = 0.0, c = 0.0;
+#pragma unroll
+                for (int e = 0; e < EIG_CLUSTER_MAX_N / 32; ++e) {
+                    const int r = lane + 32 * e;
+                    x[e] = r < n ? ci[r] : 0.0;
+                    y[e] = r < n ? cj[r] : 0.0;
+                    a += x[e] * x[e]; b += y[e] * y[e]; c += x[e] * y[e];
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    a += __shfl_xor_sync(0xffffffffu, a, o);
+                    b += __shfl_xor_sync(0xffffffffu, b, o);
+                    c += __shfl_xor_sync(0xffffffffu, c, o);
+                }
+                if (!(fabs(c) > tol * (sqrt(a) * sqrt(b)))) continue;
+                const double zeta = (b - a) / (2.0 * c);
+                const double t = copysign(1.0, zeta) / (fabs(zeta) + hypot(1.0, zeta));
+                const double cs = 1.0 / hypot(1.0, t), sn = cs * t;
+#pragma unroll
+                for (int e = 0; e < EIG_CLUSTER_MAX_N / 32; ++e) {
+                    const int r = lane + 32 * e;
+                    if (r < n) { ci[r] = cs * x[e] - sn * y[e]; cj[r] = sn * x[e] + cs * y[e]; }
+                }
+                ++my_rot;
+            }
+            cluster.sync();                     // every column of this round is written before the next pairing reads it
+        }
+        if (lane == 0 && my_rot) atomicAdd(&rot_count[slot], my_rot);
+        cluster.sync();
+        int total = 0;
+        for (int q = 0; q < C; ++q) total += *cluster.map_shared_rank(&rot_count[slot], q);
+        converged = total == 0;
+        // the other slot is next written one sweep from now, after at least m more cluster barriers: safe to clear here
+        if (threadIdx.x == 0) rot_count[slot ^ 1] = 0;
+    }
+    for (int sidx = 0; sidx < slots; ++sidx) {
+        double *dst = g + (size_t)(rank + sidx * C) * n;
+        for (int r = threadIdx.x; r < n; r += EIG_CLUSTER_THREADS) dst[r] = cols[(size_t)sidx * n + r];
+    }
+    if (rank == 0 && threadIdx.x == 0) { result[0] = sweep; result[1] = converged; }
+    cluster.sync();                             // nobody leaves while a peer may still address its shared memory
+}
+
+// Returns RB_OK and sets *done = true when the cluster kernel ran (converged or not); *done = false: not applicable or the
+// cluster could not be placed -> the caller uses the round-per-launch path.
+int try_cluster_solve(rb_ctx *ctx, double *g, i64 n, double tol, int *result_dev, int *sweeps, bool *converged, bool *done)
+{
+    *done = false;
+    if (n < 32 || n > EIG_CLUSTER_MAX_N) return RB_OK;
+    if (const char *e = getenv("REST_B200_EIG_CLUSTER")) if (atoi(e) == 0) return RB_OK;
+    const int csize = n > 256 ? 16 : 8; // 16 (non-portable size) for more warps and for the shared-memory capacity
+    const size_t smem = (size_t)(rb_cdiv(n, csize) * n * 8);
+    if (smem > 220 * 1024) return RB_OK;
+    static bool attr_set[64] = {false};
+    const int dev = ctx->device & 63;
+    if (!attr_set[dev]) {
+        if (cudaFuncSetAttribute(rb_jacobi_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(rb_jacobi_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+            cudaGetLastError();
+            return RB_OK;
+        }
+        attr_set[dev] = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)csize, 1, 1);
+    cfg.blockDim = dim3(EIG_CLUSTER_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int max_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, rb_jacobi_cluster_kernel, &cfg) != cudaSuccess || max_clusters < 1) {
+        cudaGetLastError();
+        return RB_OK; // this cluster shape cannot be placed on the device right now
+    }
+    const int ni = (int)n, ne = (int)(n + (n & 1)), ms = EIG_MAX_SWEEPS;
+    if (cudaLaunchKernelEx(&cfg, rb_jacobi_cluster_kernel, g, ni, ne, tol, ms, result_dev) != cudaSuccess) {
+        cudaGetLastError();
+        return RB_OK;
+    }
+    ctx->launches++;
+    int res[2] = {0, 0};
+    RB_CUDA(cudaMemcpyAsync(res, result_dev, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    RB_CUDA(cudaStreamSynchronize(ctx->stream));
+    *sweeps = res[0]; *converged = res[1] != 0; *done = true;
+    return RB_OK;
+}
+
 // v[:, j] = g[:, j] / norm[j]
 __global__ void __launch_bounds__(256) rb_eig_normalize_kernel(const double *__restrict__ g, const double *__restrict__ norm,
                                                                double *__restrict__ v, i64 n)
@@ -229,6 +362,11 @@ int jacobi_eig(rb_ctx *ctx, i64 n, const double *s, bool psd, double *work, std:
     const double tol = std::sqrt((double)n) * 1.1102230246251565e-16;
     int sweeps = 0;
     bool converged = n < 2;
+    if (!psd && !converged) { // small matrices: the whole solve as one cluster-resident kernel
+        bool done = false;
+        RB_TRY(try_cluster_solve(ctx, g, n, tol, (int *)rot, &sweeps, &converged, &done));
+        if (done && !converged) sweeps = EIG_MAX_SWEEPS; // fall through to the error below
+    }
     for (; sweeps < EIG_MAX_SWEEPS && !converged; ++sweeps) {
         RB_CUDA(cudaMemsetAsync(rot, 0, 8, ctx->stream));
         for (i64 round = 0; round < n_even - 1; ++round) {
