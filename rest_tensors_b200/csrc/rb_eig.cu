@@ -48,6 +48,19 @@ __global__ void __launch_bounds__(256) rb_eig_shift_diag_kernel(double *__restri
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) g[i + i * n] += shift;
 }
 
+// Jacobi rotation that makes two columns with squared norms a, b and inner product c orthogonal: tan(theta) is the smaller
+// root of t^2 + 2 zeta t - 1 = 0, zeta = (b - a) / (2c).  Plain sqrt (hypot's overflow handling costs ~200 instructions):
+// |zeta| > 1e150 only when c is negligible, and then t = 1 / (2 zeta) to working precision.
+__device__ __forceinline__ void jacobi_rotation(double a, double b, double c, double &cs, double &sn)
+{
+    const double zeta = (b - a) / (2.0 * c);
+    const double az = fabs(zeta);
+    const double t = az > 1e150 ? 0.5 / zeta : copysign(1.0, zeta) / (az + sqrt(1.0 + zeta * zeta));
+    cs = rsqrt(1.0 + t * t);
+    cs = cs * (1.5 - 0.5 * (1.0 + t * t) * cs * cs); // one Newton step: rsqrt is ~1 ulp-ish, make it correctly rounded-ish
+    sn = cs * t;
+}
+
 // fixed-order block reduction of three partial sums; every thread returns the totals
 __device__ __forceinline__ void block_sum3(double &a, double &b, double &c, double *red)
 {
@@ -106,9 +119,8 @@ __global__ void __launch_bounds__(EIG_THREADS) rb_jacobi_round_kernel(double *__
     }
     block_sum3(a, b, c, red);
     if (!(fabs(c) > tol * (sqrt(a) * sqrt(b)))) return; // already orthogonal (also: zero column, NaN)
-    const double zeta = (b - a) / (2.0 * c);
-    const double t = copysign(1.0, zeta) / (fabs(zeta) + hypot(1.0, zeta));
-    const double cs = 1.0 / hypot(1.0, t), sn = cs * t;
+    double cs, sn;
+    jacobi_rotation(a, b, c, cs, sn);
     for (i64 r = threadIdx.x; r < n; r += EIG_THREADS) {
         const double x = CACHE ? cols[r] : gi[r], y = CACHE ? cols[n + r] : gj[r];
         gi[r] = cs * x - sn * y;
@@ -127,14 +139,15 @@ __global__ void __launch_bounds__(EIG_THREADS) rb_jacobi_round_kernel(double *__
 
 // ---- cluster-resident solver for small matrices ---------------------------------------------------------------------
 // For n <= EIG_CLUSTER_MAX_N the whole working matrix lives in the DISTRIBUTED SHARED MEMORY of one thread-block cluster
-// (column c in CTA c % C, slot c / C; 16 CTAs x 182 KB hold n = 600), and the complete solve -- every round of every sweep
-// -- is ONE kernel: a warp takes a column pair into registers (<= 20 doubles per lane and column, local or remote shared
+// (column c in CTA c % C, slot c / C), and the complete solve -- every round of every sweep
+// -- is ONE kernel: a warp takes a column pair into registers (<= 10 doubles per lane and column, local or remote shared
 // memory alike), reduces the three inner products with shuffles, writes the rotated columns back, and cluster.sync()
 // (~0.2 us) separates the rounds instead of a kernel boundary (~5-10 us with the dependent launch).  The round-per-launch
 // kernel above is latency-bound at these sizes (n = 264: 23 ms for ~2400 launches).  Convergence is decided uniformly by
 // every CTA from the per-CTA rotation counts of the sweep (read through DSMEM).
 namespace cg = cooperative_groups;
-constexpr int EIG_CLUSTER_MAX_N = 640;    // 20 elements per lane and column
+constexpr int EIG_CLUSTER_MAX_N = 320;    // 10 elements per lane and column; measured: wins below ~320 (n = 264: 13 vs 23 ms),
+                                          // loses above (n = 600 in a 16-CTA cluster: 114 vs 44 ms -- DSMEM bandwidth)
 constexpr int EIG_CLUSTER_THREADS = 512;  // 16 warps per CTA
 
 __global__ void __launch_bounds__(EIG_CLUSTER_THREADS, 1)
@@ -182,9 +195,8 @@ rb_jacobi_cluster_kernel(double *__restrict__ g, int n, int n_even, double tol, 
                     c += __shfl_xor_sync(0xffffffffu, c, o);
                 }
                 if (!(fabs(c) > tol * (sqrt(a) * sqrt(b)))) continue;
-                const double zeta = (b - a) / (2.0 * c);
-                const double t = copysign(1.0, zeta) / (fabs(zeta) + hypot(1.0, zeta));
-                const double cs = 1.0 / hypot(1.0, t), sn = cs * t;
+                double cs, sn;
+                jacobi_rotation(a, b, c, cs, sn);
 #pragma unroll
                 for (int e = 0; e < EIG_CLUSTER_MAX_N / 32; ++e) {
                     const int r = lane + 32 * e;
@@ -217,7 +229,7 @@ int try_cluster_solve(rb_ctx *ctx, double *g, i64 n, double tol, int *result_dev
     *done = false;
     if (n < 32 || n > EIG_CLUSTER_MAX_N) return RB_OK;
     if (const char *e = getenv("REST_B200_EIG_CLUSTER")) if (atoi(e) == 0) return RB_OK;
-    const int csize = n > 256 ? 16 : 8; // 16 (non-portable size) for more warps and for the shared-memory capacity
+    const int csize = 8; // portable cluster size; 8 x 16 warps cover the <= 160 pairs of a round
     const size_t smem = (size_t)(rb_cdiv(n, csize) * n * 8);
     if (smem > 220 * 1024) return RB_OK;
     static bool attr_set[64] = {false};
@@ -323,6 +335,48 @@ int launch_round(rb_ctx *ctx, double *g, double *v, i64 n, i64 n_even, i64 round
     return RB_OK;
 }
 
+// A whole sweep as an executable graph: memset of the rotation counter, then the n-1 rounds as a chain of kernel nodes.
+struct SweepGraph {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    ~SweepGraph()
+    {
+        if (exec) cudaGraphExecDestroy(exec);
+        if (graph) cudaGraphDestroy(graph);
+    }
+};
+
+bool build_sweep_graph(rb_ctx *ctx, SweepGraph &sg, bool psd, double *g, double *v, i64 n, i64 n_even, double tol,
+                       unsigned long long *rot)
+{
+    if (const char *e = getenv("REST_B200_EIG_GRAPH")) if (atoi(e) == 0) return false;
+    if (cudaGraphCreate(&sg.graph, 0) != cudaSuccess) { cudaGetLastError(); return false; }
+    cudaMemsetParams mp = {};
+    mp.dst = rot; mp.value = 0; mp.elementSize = 4; mp.width = 2; mp.height = 1; mp.pitch = 8;
+    cudaGraphNode_t prev = nullptr;
+    if (cudaGraphAddMemsetNode(&prev, sg.graph, nullptr, 0, &mp) != cudaSuccess) { cudaGetLastError(); return false; }
+    const bool cache = n <= EIG_CACHE_MAX_N;
+    void *fn = psd ? (cache ? (void *)rb_jacobi_round_kernel<true, true> : (void *)rb_jacobi_round_kernel<true, false>)
+                   : (cache ? (void *)rb_jacobi_round_kernel<false, true> : (void *)rb_jacobi_round_kernel<false, false>);
+    for (i64 round = 0; round < n_even - 1; ++round) {
+        i64 round_arg = round;
+        void *args[7] = {&g, &v, &n, &n_even, &round_arg, &tol, &rot};
+        cudaKernelNodeParams kp = {};
+        kp.func = fn;
+        kp.gridDim = dim3((unsigned)(n_even / 2), 1, 1);
+        kp.blockDim = dim3(EIG_THREADS, 1, 1);
+        kp.sharedMemBytes = cache ? (unsigned)(2 * n * 8) : 0u;
+        kp.kernelParams = args; // copied by the call
+        kp.extra = nullptr;
+        cudaGraphNode_t node = nullptr;
+        if (cudaGraphAddKernelNode(&node, sg.graph, &prev, 1, &kp) != cudaSuccess) { cudaGetLastError(); return false; }
+        prev = node;
+    }
+    if (cudaGraphInstantiate(&sg.exec, sg.graph, 0) != cudaSuccess) { cudaGetLastError(); sg.exec = nullptr; return false; }
+    (void)ctx;
+    return true;
+}
+
 // Workspace of one solve, in doubles: G, V, W (n^2 each) + lam, stat (n each) + perm (n int64) + the rotation counter.
 i64 eig_work_elems(i64 n) { return 3 * n * n + 3 * n + 8; }
 
@@ -367,11 +421,23 @@ int jacobi_eig(rb_ctx *ctx, i64 n, const double *s, bool psd, double *work, std:
         RB_TRY(try_cluster_solve(ctx, g, n, tol, (int *)rot, &sweeps, &converged, &done));
         if (done && !converged) sweeps = EIG_MAX_SWEEPS; // fall through to the error below
     }
+    // One sweep = n-1 dependent launches of a few microseconds each: issued one by one the host's launch cost (~5 us)
+    // bounds the sweep, so the sweep is built once as a CUDA graph (a chain of kernel nodes, one per round) and replayed.
+    SweepGraph graph;
+    bool use_graph = !converged && n_even - 1 >= 16 && build_sweep_graph(ctx, graph, psd, g, v, n, n_even, tol, rot);
     for (; sweeps < EIG_MAX_SWEEPS && !converged; ++sweeps) {
-        RB_CUDA(cudaMemsetAsync(rot, 0, 8, ctx->stream));
-        for (i64 round = 0; round < n_even - 1; ++round) {
-            if (psd) RB_TRY(launch_round<true>(ctx, g, v, n, n_even, round, tol, rot));
-            else RB_TRY(launch_round<false>(ctx, g, v, n, n_even, round, tol, rot));
+        if (use_graph && cudaGraphLaunch(graph.exec, ctx->stream) != cudaSuccess) { // e.g. a stream that takes no graphs
+            cudaGetLastError();
+            use_graph = false;
+        }
+        if (use_graph) {
+            ctx->launches += n_even - 1;
+        } else {
+            RB_CUDA(cudaMemsetAsync(rot, 0, 8, ctx->stream));
+            for (i64 round = 0; round < n_even - 1; ++round) {
+                if (psd) RB_TRY(launch_round<true>(ctx, g, v, n, n_even, round, tol, rot));
+                else RB_TRY(launch_round<false>(ctx, g, v, n, n_even, round, tol, rot));
+            }
         }
         unsigned long long nrot = 0;
         RB_CUDA(cudaMemcpyAsync(&nrot, rot, 8, cudaMemcpyDeviceToHost, ctx->stream));
