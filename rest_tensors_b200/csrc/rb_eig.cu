@@ -140,14 +140,15 @@ __global__ void __launch_bounds__(EIG_THREADS) rb_jacobi_round_kernel(double *__
 // ---- cluster-resident solver for small matrices ---------------------------------------------------------------------
 // For n <= EIG_CLUSTER_MAX_N the whole working matrix lives in the DISTRIBUTED SHARED MEMORY of one thread-block cluster
 // (column c in CTA c % C, slot c / C), and the complete solve -- every round of every sweep
-// -- is ONE kernel: a warp takes a column pair into registers (<= 10 doubles per lane and column, local or remote shared
+// -- is ONE kernel: a warp takes a column pair into registers (<= 4 doubles per lane and column, local or remote shared
 // memory alike), reduces the three inner products with shuffles, writes the rotated columns back, and cluster.sync()
-// (~0.2 us) separates the rounds instead of a kernel boundary (~5-10 us with the dependent launch).  The round-per-launch
-// kernel above is latency-bound at these sizes (n = 264: 23 ms for ~2400 launches).  Convergence is decided uniformly by
+// (~0.2 us) separates the rounds instead of a kernel boundary (a few microseconds per dependent graph node).  Convergence is decided uniformly by
 // every CTA from the per-CTA rotation counts of the sweep (read through DSMEM).
 namespace cg = cooperative_groups;
-constexpr int EIG_CLUSTER_MAX_N = 320;    // 10 elements per lane and column; measured: wins below ~320 (n = 264: 13 vs 23 ms),
-                                          // loses above (n = 600 in a 16-CTA cluster: 114 vs 44 ms -- DSMEM bandwidth)
+constexpr int EIG_CLUSTER_MAX_N = 128;    // 4 elements per lane and column.  Measured crossover against the graph-replayed round
+                                          // kernels (tools/eig_small_probe.py): n = 64 1.26 vs 1.95 ms, 128 3.2 vs 3.6 ms, but
+                                          // 200 7.7 vs 5.9 ms, 264 15.8 vs 8.2 ms -- remote shared memory traffic grows as n^2
+                                          // per round on 8 SMs while the round kernels spread it over the chip's L2
 constexpr int EIG_CLUSTER_THREADS = 512;  // 16 warps per CTA
 
 __global__ void __launch_bounds__(EIG_CLUSTER_THREADS, 1)
@@ -229,7 +230,7 @@ int try_cluster_solve(rb_ctx *ctx, double *g, i64 n, double tol, int *result_dev
     *done = false;
     if (n < 32 || n > EIG_CLUSTER_MAX_N) return RB_OK;
     if (const char *e = getenv("REST_B200_EIG_CLUSTER")) if (atoi(e) == 0) return RB_OK;
-    const int csize = 8; // portable cluster size; 8 x 16 warps cover the <= 160 pairs of a round
+    const int csize = 8; // portable cluster size; 8 x 16 warps cover the <= 64 pairs of a round
     const size_t smem = (size_t)(rb_cdiv(n, csize) * n * 8);
     if (smem > 220 * 1024) return RB_OK;
     static bool attr_set[64] = {false};
