@@ -478,9 +478,10 @@ def run_ours(args):
             cpu_baseline["value_single_thread"] = sum(flops(nb, s1, no).values()) / c1 / 1e9
             cpu_baseline["single_thread_sample_slabs"] = s1
 
-    traffic = None
+    traffic = traffic_dp = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(args.config)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+        traffic, traffic_dp = tj.get(args.config), tj.get(args.config + "_dp")
     except Exception:
         pass
     gemm_launch_ms = avg["ao2mo"] / 2.0                      # ao2mo = 2 launches of the TMA+DMMA GEMM kernel
@@ -505,7 +506,7 @@ def run_ours(args):
         "roofline_hbm": {"bound": "hbm", "kernel": "rb_gemv_t_vec_kernel (d_P) / rb_gemv_n_kernel (J)",
                          "achieved": nx * n2 * 8 / (avg["dp"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                          "frac": nx * n2 * 8 / (avg["dp"] * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
-                         "j_achieved": nx * n2 * 8 / (avg["j"] * 1e-3) / 1e9},
+                         "j_achieved": nx * n2 * 8 / (avg["j"] * 1e-3) / 1e9, "traffic": traffic_dp},
         "e2e": e2e,
         "ao2mo_occ_vir": occ_vir,
         "iajb_occ_vir": iajb,

@@ -304,6 +304,13 @@ int rb_self_sub(rb_ctx *ctx, double *c, const double *p, int64_t n);            
 int rb_fill_linear(rb_ctx *ctx, double *v, int64_t n, uint64_t seed, uint64_t idx0, double scale);
 int rb_fill_ri3ao_symm(rb_ctx *ctx, double *a, int64_t nb, int64_t p_lo, int64_t p_hi, uint64_t seed, double scale);
 
+/* Host-side planners, exported so that they can be tested without a GPU (pure arithmetic, no device call):
+ *   rb_gemm_plan_splits : split-K count the TMA+DMMA GEMM uses for (m, n, k, batch, tri) on a chip of num_sms SMs
+ *   rb_ri_plan_chunk    : P-chunk length of the RI contractions for nx slabs of bytes_per_slab workspace each under a
+ *                         workspace budget (tile_m != 0: P is the M index of a GEMM tile, cheapest tiling wins) */
+int64_t rb_gemm_plan_splits(int64_t m, int64_t n, int64_t k, int64_t batch, int tri, int num_sms);
+int64_t rb_ri_plan_chunk(int64_t nx, int64_t bytes_per_slab, int64_t budget_bytes, int tile_m);
+
 /* FP64 pipe micro-benchmarks used by bench.py for the roofline denominator: returns achieved TFLOP/s of a
  * register-resident DMMA (kind=0) or DFMA (kind=1) loop over the whole chip, timed with CUDA events. */
 int rb_fp64_peak_probe(rb_ctx *ctx, int kind, int iters, double *tflops_out, double *ms_out);

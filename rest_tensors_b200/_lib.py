@@ -143,6 +143,8 @@ SIGNATURES = {
     "rb_self_sub": (C.c_int, [c_vp, c_vp, c_vp, c_i64]),
     "rb_fill_linear": (C.c_int, [c_vp, c_vp, c_i64, C.c_uint64, C.c_uint64, C.c_double]),
     "rb_fill_ri3ao_symm": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, C.c_uint64, C.c_double]),
+    "rb_gemm_plan_splits": (c_i64, [c_i64, c_i64, c_i64, c_i64, C.c_int, C.c_int]),
+    "rb_ri_plan_chunk": (c_i64, [c_i64, c_i64, c_i64, C.c_int]),
     "rb_fp64_peak_probe": (C.c_int, [c_vp, C.c_int, C.c_int, c_dp, c_dp]),
     "rb_hbm_copy_probe": (C.c_int, [c_vp, c_i64, C.c_int, c_dp]),
     "rb_pcie_probe": (C.c_int, [c_vp, C.c_int, c_i64, c_i64, C.c_int, c_dp]),

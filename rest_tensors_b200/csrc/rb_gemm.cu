@@ -665,6 +665,52 @@ bool tma_eligible(const rb_ctx *ctx, const double *p, i64 ld, i64 stride, i64 ba
     return true;
 }
 
+// Split-K plan.  When the tiles do not fill whole waves of the chip and K is deep, the split count minimises a makespan
+// estimate in k steps: rounds(s) * item cost, where an item costs k/s steps + ~2 fixed (descriptor, epilogue, partial
+// store), rounds = ceil(items / SMs) is the number of items the busiest SM takes, and ragged edge tiles weigh what they
+// were measured to cost (the kernel works at 16 x 16 block granularity; the dynamic scheduler back-fills cheap items)
+// -- e.g. 105 tiles x 1013 steps: s = 7 -> 5 rounds of 147 steps instead of one of 1015; a 264^2 SYRK (3 full + 3 thin
+// tiles): s = 48, not the s = 24 that fills one round with half-empty SMs.  Partials are reduced in a fixed order:
+// results do not depend on the schedule.  Pure host arithmetic (exported as rb_gemm_plan_splits for the CPU tests).
+i64 plan_splits(i64 m, i64 n, i64 k, i64 batch, int tri, int num_sms)
+{
+    const i64 tiles_m = rb_cdiv(m, BM), tiles_n = rb_cdiv(n, BN);
+    const i64 tiles_per_batch = tri ? tiles_m * (tiles_m + 1) / 2 : tiles_m * tiles_n;
+    const i64 tiles = tiles_per_batch * batch;
+    const i64 ksteps = rb_cdiv(k, BK);
+    i64 splits = 1;
+    if (tiles <= 0 || num_sms <= 0 || !(tiles < 4 * (i64)num_sms && ksteps >= 8)) return 1;
+    const i64 me = m - (tiles_m - 1) * BM, ne = n - (tiles_n - 1) * BN; // extents of the last tile row / column
+    const int mbe = (int)((me + 15) >> 4), nbe = (int)((ne + 15) >> 4);
+    const double wm_edge = mbe >= 5 ? 1.0 : mbe >= 3 ? 0.5 : mbe == 2 ? 0.25 : 0.125; // <= 2 block rows per warp row
+    const double wn_edge = nbe / 8.0;
+    double eff = 0.0, max_w = 0.0;
+    for (i64 tn = 0; tn < tiles_n; ++tn)
+        for (i64 tm = 0; tm < tiles_m; ++tm) {
+            if ((tri == 1 && tm > tn) || (tri == 2 && tm < tn)) continue;
+            double w = (tm == tiles_m - 1 ? wm_edge : 1.0) * (tn == tiles_n - 1 ? wn_edge : 1.0);
+            if (w < 0.22) w = 0.22; // measured floor of a 1-block-wide tile
+            eff += w;
+            if (w > max_w) max_w = w;
+        }
+    const double avg_w = eff / (double)tiles_per_batch;
+    i64 smax = ksteps / 4;
+    if (smax > 64) smax = 64;
+    const i64 part_elems = batch * n * ((m + 1) & ~(i64)1);
+    while (smax > 1 && smax * part_elems * 8 > ((i64)1 << 30)) --smax; // partial workspace <= 1 GB
+    double best_cost = -1.0;
+    for (i64 s = 1; s <= smax; ++s) {
+        const i64 rounds = rb_cdiv(tiles * s, num_sms);
+        const double busiest = rounds == 1 ? max_w : (double)rounds * avg_w;
+        // + the partial round trip through HBM (s writes + s reads of every tile, ~1/200 step per tile each)
+        const double cost = busiest * (double)(rb_cdiv(ksteps, s) + 2) + (s > 1 ? (double)(2 * s * tiles) / 200.0 : 0.0);
+        if (best_cost < 0.0 || cost < best_cost) { best_cost = cost; splits = s; }
+    }
+    // what the kernel will actually run: k per split is a whole number of 32-deep steps
+    const i64 kper = rb_cdiv(ksteps, splits) * BK;
+    return rb_cdiv(k, kper);
+}
+
 template <bool A_K, bool B_K>
 int launch_tma(rb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p, int grid)
 {
@@ -680,6 +726,12 @@ int launch_tma(rb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, cons
 }
 
 } // namespace
+
+extern "C" int64_t rb_gemm_plan_splits(int64_t m, int64_t n, int64_t k, int64_t batch, int tri, int num_sms)
+{
+    if (m <= 0 || n <= 0 || k <= 0 || batch <= 0) return 1;
+    return plan_splits(m, n, k, batch, tri, num_sms);
+}
 
 int rb_gemm_core(rb_ctx *ctx, bool ta, bool tb, i64 m, i64 n, i64 k, double alpha, const double *a, i64 lda,
                  i64 stride_a, const double *b, i64 ldb, i64 stride_b, double beta, double *c, i64 ldc, i64 stride_c,
@@ -751,43 +803,8 @@ int rb_gemm_core(rb_ctx *ctx, bool ta, bool tb, i64 m, i64 n, i64 k, double alph
         p.tiles_m = rb_cdiv(m, BM); p.tiles_n = rb_cdiv(n, BN);
         p.tiles_per_batch = tri ? p.tiles_m * (p.tiles_m + 1) / 2 : p.tiles_m * p.tiles_n;
         i64 tiles = p.tiles_per_batch * batch;
-        // split-K when the tiles do not fill whole waves of the chip and K is deep.  The split count minimises a
-        // makespan estimate in k steps: rounds(s) * item cost, where an item costs k/s steps + ~2 fixed (descriptor,
-        // epilogue, partial store), rounds = ceil(items / SMs) is the number of items the busiest SM takes, and ragged
-        // edge tiles weigh what they were measured to cost (the kernel works at 16 x 16 block granularity; the
-        // dynamic scheduler back-fills cheap items) -- e.g. 105 tiles x 1013 steps: s = 7 -> 5 rounds of 147 steps
-        // instead of one of 1015; a 264^2 SYRK (3 full + 3 thin tiles): s = 49, not the s = 24 that fills one round
-        // with half-empty SMs.  Partials are reduced in a fixed order: results do not depend on the schedule.
-        i64 splits = 1;
-        i64 ksteps = rb_cdiv(k, BK);
-        if (tiles < 4 * (i64)ctx->num_sms && ksteps >= 8) {
-            const i64 me = m - (p.tiles_m - 1) * BM, ne = n - (p.tiles_n - 1) * BN; // extents of the last tile row / column
-            const int mbe = (int)((me + 15) >> 4), nbe = (int)((ne + 15) >> 4);
-            const double wm_edge = mbe >= 5 ? 1.0 : mbe >= 3 ? 0.5 : mbe == 2 ? 0.25 : 0.125; // <= 2 block rows per warp row
-            const double wn_edge = nbe / 8.0;
-            double eff = 0.0, max_w = 0.0;
-            for (i64 tn = 0; tn < p.tiles_n; ++tn)
-                for (i64 tm = 0; tm < p.tiles_m; ++tm) {
-                    if ((tri == 1 && tm > tn) || (tri == 2 && tm < tn)) continue;
-                    double w = (tm == p.tiles_m - 1 ? wm_edge : 1.0) * (tn == p.tiles_n - 1 ? wn_edge : 1.0);
-                    if (w < 0.22) w = 0.22; // measured floor of a 1-block-wide tile
-                    eff += w;
-                    if (w > max_w) max_w = w;
-                }
-            const double avg_w = eff / (double)p.tiles_per_batch;
-            i64 smax = ksteps / 4;
-            if (smax > 64) smax = 64;
-            const i64 part_elems = batch * n * ((m + 1) & ~(i64)1);
-            while (smax > 1 && smax * part_elems * 8 > ((i64)1 << 30)) --smax; // partial workspace <= 1 GB
-            double best_cost = -1.0;
-            for (i64 s = 1; s <= smax; ++s) {
-                const i64 rounds = rb_cdiv(tiles * s, ctx->num_sms);
-                const double busiest = rounds == 1 ? max_w : (double)rounds * avg_w;
-                // + the partial round trip through HBM (s writes + s reads of every tile, ~1/200 step per tile each)
-                const double cost = busiest * (double)(rb_cdiv(ksteps, s) + 2) + (s > 1 ? (double)(2 * s * tiles) / 200.0 : 0.0);
-                if (best_cost < 0.0 || cost < best_cost) { best_cost = cost; splits = s; }
-            }
-        }
+        const i64 ksteps = rb_cdiv(k, BK);
+        i64 splits = plan_splits(m, n, k, batch, tri, ctx->num_sms);
         i64 kper = rb_cdiv(ksteps, splits) * BK;
         splits = rb_cdiv(k, kper);
         p.splits = splits; p.kper = kper;

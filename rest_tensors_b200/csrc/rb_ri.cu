@@ -71,6 +71,13 @@ static i64 pick_chunk(i64 nx, i64 bytes_per_slab, i64 budget, bool tile_m)
     return best < nx ? best : nx;
 }
 
+// host-only planner entry for the CPU tests (no device is touched)
+extern "C" int64_t rb_ri_plan_chunk(int64_t nx, int64_t bytes_per_slab, int64_t budget_bytes, int tile_m)
+{
+    if (nx <= 0) return 0;
+    return pick_chunk(nx, bytes_per_slab, budget_bytes, tile_m != 0);
+}
+
 // ---- odd nb / unaligned tensors ------------------------------------------------------------------------------
 // TMA needs 16-byte aligned bases and row pitches, i.e. an even leading dimension.  Basis-set sizes are arbitrary, so
 // for odd nb (or an 8-byte-aligned tensor) every P-chunk is first copied into zero-padded slabs [nbp, nbp], nbp = nb

@@ -191,3 +191,40 @@ def test_shard_range_partitions_exactly():
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
     assert shard_range(4800, 3, 8) == (1800, 2400)
+
+
+def test_split_k_planner(rt):
+    """Host-side split-K plan of the GEMM (pure arithmetic, no GPU): the cases DESIGN.md quotes and the invariants."""
+    plan = rt.lib.rb_gemm_plan_splits
+    sms = 148
+    assert plan(600 * 1700, 600, 600, 1, 0, sms) == 1            # ao2mo GEMM 1, config C: ~40 000 tiles, no split
+    assert plan(16200, 16200, 1700, 1, 1, sms) == 1              # (ia|jb) diagonal block: 8128 tiles
+    assert plan(1700, 1700, 32400, 1, 1, sms) == 7               # RPA-type contraction: 105 tiles x 1013 steps -> 5 rounds
+    assert plan(264, 264, 21 * 720, 1, 1, sms) in (48, 49)       # config B SYRK: 3 full + 3 thin tiles -> two rounds
+    s_c = plan(600, 600, 60 * 1700, 1, 1, sms)                   # config C SYRK: 15 tiles x 3188 steps
+    assert 20 <= s_c <= 40
+    assert plan(128, 128, 64, 1, 0, sms) == 1                    # shallow K: never split
+    assert plan(128, 128, 32 * 8, 1, 0, sms) == 2                # 8 steps: at most ksteps / 4 splits
+    for (m, n, k, batch, tri) in [(100, 100, 10 ** 6, 1, 0), (513, 257, 4099, 3, 0), (2049, 2049, 2049, 1, 2), (64, 8, 10 ** 5, 7, 0)]:
+        s = plan(m, n, k, batch, tri, sms)
+        ksteps = -(-k // 32)
+        assert 1 <= s <= 64 and s <= max(1, ksteps // 4 + 1)
+        kper = -(-ksteps // s) * 32
+        assert (s - 1) * kper < k                                # every split owns at least one k
+        assert s * batch * n * ((m + 1) & ~1) * 8 <= (1 << 30) or s == 1   # partial workspace stays under 1 GB
+    assert plan(0, 5, 5, 1, 0, sms) == 1 and plan(5, 5, 5, 0, 0, sms) == 1
+
+
+def test_p_chunk_planner(rt):
+    """P-chunk planner of the RI contractions: whole range when it fits, multiples of 8 otherwise, cheapest GEMM tiling."""
+    chunk = rt.lib.rb_ri_plan_chunk
+    slab = 1800 * 1800 * 8                                       # config D: W needs nb * nl doubles per slab
+    assert chunk(600, slab, 16 << 30, 1) == 600                  # 15.6 GB fits the 16 GB cap: one chunk, flat GEMM 2
+    pc = chunk(600, slab, 8 << 30, 1)                            # two chunks: 312 + 288 beats 304 + 296 (DESIGN section 3)
+    assert pc == 312
+    for nx, per, budget, tile in [(1700, 600 * 600 * 8, 1 << 30, 1), (4800, slab, 3 << 30, 0), (17, 1 << 20, 1 << 20, 1), (9, 1, 1, 0)]:
+        pc = chunk(nx, per, budget, tile)
+        assert 1 <= pc <= nx
+        assert pc == nx or pc % 8 == 0
+        assert pc == nx or pc * per <= max(budget, 8 * per)      # within the budget (at least 8 slabs are always taken)
+    assert chunk(0, 8, 8, 0) == 0
