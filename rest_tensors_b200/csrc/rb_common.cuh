@@ -57,6 +57,7 @@ struct rb_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaStream_t aux_stream = nullptr;   // copy stream of the peer pipeline (rb_ri_mo_pq_peers), created on first use
     cudaEvent_t aux_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}; // [0] fork, [1..2] pulled, [3..4] buffer free
+    void *eig_cache = nullptr;           // instantiated Jacobi sweep graphs (rb_eig.cu), freed by rb_eig_cache_free
     unsigned long long *sched = nullptr; // GEMM tile-scheduler slots (64 x 2 words on the device), zero between launches
     unsigned sched_next = 0;             // slot of the next GEMM launch (round-robin)
 };
@@ -99,6 +100,9 @@ int rb_scale_or_zero(rb_ctx *ctx, double *y, i64 n, i64 inc, double beta);
 
 // rb_ri.cu: upper triangle of k (+)= sum_P (A_P ct)(A_P ct)^T over nx slabs (beta 0 overwrite / 1 accumulate)
 int rb_ri_k_upper(rb_ctx *ctx, const double *ri3ao, const double *ct, i64 no, double *k, i64 nb, i64 nx, double beta);
+
+// rb_eig.cu: drop the cached sweep graphs of a context (called by rb_ctx_destroy)
+void rb_eig_cache_free(rb_ctx *ctx);
 
 // Default (process-wide) context for the host-pointer entry points.
 rb_ctx *rb_default_ctx(void);

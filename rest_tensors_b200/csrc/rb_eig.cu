@@ -19,6 +19,7 @@
 #include <cooperative_groups.h>
 #include <algorithm>
 #include <cmath>
+#include <memory>
 #include <numeric>
 #include <vector>
 
@@ -378,6 +379,47 @@ bool build_sweep_graph(rb_ctx *ctx, SweepGraph &sg, bool psd, double *g, double 
     return true;
 }
 
+// Building and instantiating the n-1 node chain costs milliseconds of host time (more when the host cores are busy), and an
+// SCF loop diagonalises matrices of one size over and over in the same workspace: the instantiated graphs are kept per
+// context, keyed by everything the kernel nodes captured (shape, mode, buffers, tolerance); at most 4, least recently
+// used replaced.
+struct EigGraphEntry {
+    i64 n = 0;
+    bool psd = false;
+    double *g = nullptr, *v = nullptr;
+    double tol = 0.0;
+    unsigned long long *rot = nullptr;
+    unsigned stamp = 0;
+    SweepGraph sg;
+};
+struct EigCache {
+    std::vector<std::unique_ptr<EigGraphEntry>> entries;
+    unsigned clock = 0;
+};
+
+SweepGraph *get_sweep_graph(rb_ctx *ctx, bool psd, double *g, double *v, i64 n, i64 n_even, double tol, unsigned long long *rot)
+{
+    if (!ctx->eig_cache) ctx->eig_cache = new EigCache();
+    EigCache *cache = (EigCache *)ctx->eig_cache;
+    ++cache->clock;
+    for (auto &e : cache->entries)
+        if (e->n == n && e->psd == psd && e->g == g && e->v == v && e->tol == tol && e->rot == rot) {
+            e->stamp = cache->clock;
+            return &e->sg;
+        }
+    std::unique_ptr<EigGraphEntry> ent(new EigGraphEntry());
+    if (!build_sweep_graph(ctx, ent->sg, psd, g, v, n, n_even, tol, rot)) return nullptr;
+    ent->n = n; ent->psd = psd; ent->g = g; ent->v = v; ent->tol = tol; ent->rot = rot; ent->stamp = cache->clock;
+    if (cache->entries.size() >= 4) {
+        size_t old = 0;
+        for (size_t i = 1; i < cache->entries.size(); ++i) if (cache->entries[i]->stamp < cache->entries[old]->stamp) old = i;
+        cudaStreamSynchronize(ctx->stream); // the evicted graph may still be running
+        cache->entries.erase(cache->entries.begin() + (long)old);
+    }
+    cache->entries.push_back(std::move(ent));
+    return &cache->entries.back()->sg;
+}
+
 // Workspace of one solve, in doubles: G, V, W (n^2 each) + lam, stat (n each) + perm (n int64) + the rotation counter.
 i64 eig_work_elems(i64 n) { return 3 * n * n + 3 * n + 8; }
 
@@ -424,10 +466,10 @@ int jacobi_eig(rb_ctx *ctx, i64 n, const double *s, bool psd, double *work, std:
     }
     // One sweep = n-1 dependent launches of a few microseconds each: issued one by one the host's launch cost (~5 us)
     // bounds the sweep, so the sweep is built once as a CUDA graph (a chain of kernel nodes, one per round) and replayed.
-    SweepGraph graph;
-    bool use_graph = !converged && n_even - 1 >= 16 && build_sweep_graph(ctx, graph, psd, g, v, n, n_even, tol, rot);
+    SweepGraph *graph = (!converged && n_even - 1 >= 16) ? get_sweep_graph(ctx, psd, g, v, n, n_even, tol, rot) : nullptr;
+    bool use_graph = graph != nullptr;
     for (; sweeps < EIG_MAX_SWEEPS && !converged; ++sweeps) {
-        if (use_graph && cudaGraphLaunch(graph.exec, ctx->stream) != cudaSuccess) { // e.g. a stream that takes no graphs
+        if (use_graph && cudaGraphLaunch(graph->exec, ctx->stream) != cudaSuccess) { // e.g. a stream that takes no graphs
             cudaGetLastError();
             use_graph = false;
         }
@@ -608,4 +650,11 @@ extern "C" int rb_matrix_power(rb_ctx *ctx, int n_, const double *a, int64_t lda
     RB_CUDA(cudaStreamSynchronize(ctx->stream));
     RB_TRY(rb_gemm_core(ctx, false, true, n, n, n, 1.0, vs, n, 0, vs, n, 0, 0.0, out, ldo, 0, 1, 1));
     return rb_symmetrize(ctx, out, n, ldo, true);
+}
+
+void rb_eig_cache_free(rb_ctx *ctx)
+{
+    if (!ctx || !ctx->eig_cache) return;
+    delete (EigCache *)ctx->eig_cache;
+    ctx->eig_cache = nullptr;
 }
