@@ -33,7 +33,7 @@
  *
  * PARITY PINNING.  Pinned by the reference's own asserted doc-test vectors (tests/golden/reference_vectors.json):
  *   general_dgemm_f / _dgemm sub-block GEMM (GV1-GV3), pack order (GV4), unpack+mirror (GV5),
- *   MatrixFull::transpose (GV7).
+ *   MatrixFull::transpose (GV7), _dsyev (GV8).
  * PARITY UNPINNED (the reference holds no assertion, fixture or golden vector for them and cannot be
  * built here -- no cargo/rustc/gfortran): ri_ao2mo_f / ao2mo_v01, copy_mm/mr/rm/rr, the four RIFull
  * transposes, rifull_to_matfull_symm, the axpy family, special_dgemm_f_01, and d_P / J / K (not in the

@@ -1,7 +1,7 @@
 """Writes tests/golden/reference_vectors.json.
 
 The reference (Rust + Fortran + un-vendored OpenBLAS) cannot be built or imported in this image, so these
-vectors are TRANSCRIBED from the `assert_eq!` expectations of the reference's own doc-tests (GV1-GV7), with the
+vectors are TRANSCRIBED from the `assert_eq!` expectations of the reference's own doc-tests (GV1-GV8), with the
 reference file:line of each; GV9/GV10 are derived by hand from the reference's bench / print-only test inputs
 (the reference asserts nothing for them) and are flagged "derived".  Run from the repo root:
     python tests/golden/make_reference_vectors.py
@@ -62,6 +62,17 @@ V = {
         "pinned_by_reference": True,
         "data": [float(x) for x in range(1, 13)], "size": [3, 4],
         "transposed_column_2": [3.0, 6.0, 9.0, 12.0],
+    },
+    "GV8": {
+        "source": "src/matrix/matrix_blas_lapack.rs:285-317 _dsyev doc-test: MatrixUpper 1..6 -> full 3x3; eigenvectors and "
+                  "eigenvalues asserted with sum of squared differences < 10E-7 (jobz 'V' and 'N')",
+        "pinned_by_reference": True,
+        "packed": [float(x) for x in range(1, 7)], "n": 3,
+        "eigenvectors": [-0.6827362941552275, -0.38559063640162244, 0.6206375864887483,
+                         0.6202872696512856, -0.7547821848190948, 0.21341873532627673,
+                         -0.3861539275363389, -0.5306823104260265, -0.7544941548144386],
+        "eigenvalues": [-1.5066326307865059, -0.05739624271478554, 11.564028873501286],
+        "tolerance_sum_sq": 1e-6,
     },
     "GV9": {
         "source": "benches/bench_tensors.rs:5-9: RIFull::new([10,10,20],2.0).ao2mo_v02(MatrixFull::new([10,10],1.0)); "

@@ -38,6 +38,26 @@ def _align(z, zref):
     return z * s
 
 
+def test_golden_dsyev_doc_test(rt, golden):
+    """GV8: the reference's own _dsyev doc-test (matrix_blas_lapack.rs:285-317) through the drop-in names, with the
+    reference's tolerance (sum of squared differences < 10E-7).  Eigenvalues as asserted there; eigenvectors column by
+    column up to the sign LAPACK happens to return (ours: largest component positive)."""
+    g = golden["GV8"]
+    matr_b = rt.MatrixUpper.from_vec(6, np.array(g["packed"])).to_matrixfull()
+    vec, w, ndim = rt._dsyev(matr_b, "V")
+    assert ndim == 3
+    assert np.sum((w - np.array(g["eigenvalues"])) ** 2) < g["tolerance_sum_sq"]
+    assert np.max(np.abs(w - np.array(g["eigenvalues"]))) < 1e-13
+    z = vec.data.reshape((3, 3), order="F"); zr = np.array(g["eigenvectors"]).reshape((3, 3), order="F")
+    diff = sum(min(np.sum((z[:, c] - zr[:, c]) ** 2), np.sum((z[:, c] + zr[:, c]) ** 2)) for c in range(3))
+    assert diff < g["tolerance_sum_sq"] and diff < 1e-24
+    vec0, w0, _ = rt._dsyev(matr_b, "N")
+    assert vec0 is None and np.sum((w0 - np.array(g["eigenvalues"])) ** 2) < g["tolerance_sum_sq"]
+    # the packed form of the same matrix through lapack_dspevx
+    z2, w2, found = rt.MatrixUpper.from_vec(6, np.array(g["packed"])).lapack_dspevx()
+    assert found == 3 and np.max(np.abs(w2 - np.array(g["eigenvalues"]))) < 1e-13
+
+
 @pytest.mark.parametrize("n", [1, 2, 3, 16, 17, 64, 257, 600])
 def test_dsyev_vs_lapack(rt, oracle_blas, n):
     a = _sym(oracle_blas, n, 71)

@@ -188,3 +188,16 @@ def test_oracle_lapack_wrappers_vs_numpy(oracle_blas):
     x, kept = oracle_blas.power(flat(b), n, -0.5, 1e-10)
     xm = x.reshape((n, n), order="F")
     assert kept == n and np.max(np.abs(xm @ b @ xm - np.eye(n))) <= 1e-12
+
+
+def test_oracle_dsyev_reproduces_the_reference_doc_test(oracle_blas, golden):
+    """GV8 (matrix_blas_lapack.rs:285-317): the reference's own asserted eigenpairs, with the reference's own tolerance
+    (sum of squared differences < 10E-7) -- and the oracle's LAPACK even reproduces the signs to 1e-12."""
+    g = golden["GV8"]
+    full = oracle_blas.to_matrixfull(np.array(g["packed"]))
+    vec, w = oracle_blas.dsyev(full, g["n"], "V")
+    assert np.sum((w - np.array(g["eigenvalues"])) ** 2) < g["tolerance_sum_sq"]
+    assert np.sum((vec - np.array(g["eigenvectors"])) ** 2) < g["tolerance_sum_sq"]
+    assert np.max(np.abs(vec - np.array(g["eigenvectors"]))) < 1e-12
+    none, w2 = oracle_blas.dsyev(full, g["n"], "N")
+    assert none is None and np.sum((w2 - np.array(g["eigenvalues"])) ** 2) < g["tolerance_sum_sq"]
