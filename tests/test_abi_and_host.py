@@ -228,3 +228,42 @@ def test_p_chunk_planner(rt):
         assert pc == nx or pc % 8 == 0
         assert pc == nx or pc * per <= max(budget, 8 * per)      # within the budget (at least 8 slabs are always taken)
     assert chunk(0, 8, 8, 0) == 0
+
+
+def test_argument_errors_surface_before_any_device_call(rt):
+    """Shape / range validation of the C ABI and of the host mirror happens before the first CUDA call, so the error
+    behaviour (status RB_ERR_INVALID + message; the Rust wrappers panic on the same conditions) is checkable without a GPU."""
+    lib, RB_ERR_INVALID = rt.lib, 1
+    buf = np.zeros(64)
+    p = buf.ctypes.data
+    # host-pointer entry points: bad boxes / dimensions
+    assert lib.rb_host_ri_iajb(4, p, 2, 2, 0, 3, 0, 2, p, 2, 2, 0, 2, 0, 2, p) == RB_ERR_INVALID       # l range outside
+    assert b"box" in lib.rb_last_error()
+    assert lib.rb_host_ri_mo_pq(p, 4, 2, 2, 0, 2, 1, 2, None, p) == RB_ERR_INVALID                      # r range outside
+    assert lib.rb_host_dspgvx(3, p, p, 4, p, p) == RB_ERR_INVALID                                       # num_orb > n
+    assert lib.rb_host_dsyev(b"X", 3, p, p, p) == RB_ERR_INVALID                                        # bad jobz
+    assert lib.rb_host_dgemm(b"Q", b"N", 2, 2, 2, 1.0, p, 2, p, 2, 0.0, p, 2) == RB_ERR_INVALID         # bad trans
+    assert lib.rb_host_dsyrk(b"U", b"N", 3, 2, 1.0, p, 2, 0.0, p, 3) == RB_ERR_INVALID                  # lda too small
+    # device-pointer entry points reject a NULL context first
+    assert lib.rb_ri_iajb(None, 4, p, 4, 2, 2, 0, 2, 0, 2, p, 4, 2, 2, 0, 2, 0, 2, 0.0, p, 4) == RB_ERR_INVALID
+    assert lib.rb_dsyev(None, b"V", b"L", 3, p, 3, p, p, 3) == RB_ERR_INVALID
+    assert lib.rb_special_dgemm_01_peers(None, 0, 1, None, 4, None, None, p, 4, 1.0, 0.0, p) == RB_ERR_INVALID
+    # empty problems are not errors and touch nothing
+    assert lib.rb_host_ri_iajb(4, p, 2, 2, 0, 0, 0, 2, p, 2, 2, 0, 2, 0, 2, p) == 0
+    assert lib.rb_host_dsyev(b"V", 0, p, p, p) == 0 and lib.rb_host_power(0, p, -0.5, 1e-10, p, None) == 0
+    # host mirror: the reference's panics
+    t = rt.RIFull.new([4, 2, 3], 1.0)
+    with pytest.raises(rt.RestB200Error):
+        t.ri_iajb((0, 3), (0, 3), (0, 2), (0, 3))
+    with pytest.raises(rt.RestB200Error):
+        t.ri_iajb((0, 2), (0, 3), (0, 2), (0, 3), other=rt.RIFull.new([5, 2, 3], 1.0))
+    with pytest.raises(rt.RestB200Error):
+        t.ri_mo_pq((0, 2), (0, 3), np.ones(5))
+    with pytest.raises(rt.RestB200Error):
+        rt._dsyev(rt.MatrixFull.new([2, 3], 0.0), "V")
+    assert rt._power(rt.MatrixFull.new([2, 3], 0.0), -0.5, 1e-10) is None
+    assert rt.MatrixFull.new([2, 3], 0.0).lapack_dsyev() is None
+    with pytest.raises(rt.RestB200Error):
+        rt._dspgvx(rt.MatrixUpper.new(6, 0.0), rt.MatrixUpper.new(10, 0.0), 2)
+    with pytest.raises(rt.RestB200Error):
+        rt._dspgvx(rt.MatrixUpper.new(6, 0.0), rt.MatrixUpper.new(6, 0.0), 4)
