@@ -463,9 +463,12 @@ def run_ours(args):
     cpu_baseline = None
     if world == 1 and not args.no_cpu:
         cpu = CpuPath(nb, no)
-        slabs = cpu.calibrate(target_s=6.0, max_slabs=nx)
-        cpu.step()
-        t0 = time.perf_counter(); cpu.step(); cdt = time.perf_counter() - t0
+        slabs = cpu.calibrate(target_s=4.0, max_slabs=nx)
+        cpu.step()                                  # warm-up 1, median of 3
+        cts = []
+        for _ in range(3):
+            t0 = time.perf_counter(); cpu.step(); cts.append(time.perf_counter() - t0)
+        cdt = sorted(cts)[1]
         cpu_baseline = {"value": sum(flops(nb, slabs, no).values()) / cdt / 1e9, "unit": UNIT, "cores": cpu.threads,
                         "kind": "port", "sample": cpu.describe(slabs, nx)}
         # the same algorithm on ONE host thread (SURVEY 8d asks for both), on a ~3 s sample
