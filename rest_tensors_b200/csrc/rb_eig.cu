@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(EIG_THREADS) rb_eig_colstat_kernel(const doubl
 
 // One round of the tournament: CTA k orthogonalises the column pair (i, j) of round `round`.
 template <bool ACCUM_V, bool CACHE>
-__global__ void __launch_bounds__(EIG_THREADS) rb_jacobi_round_kernel(double *__restrict__ g, double *__restrict__ v, i64 n,
+__global__ void __launch_bounds__(EIG_THREADS, 8) rb_jacobi_round_kernel(double *__restrict__ g, double *__restrict__ v, i64 n,
                                                                      i64 n_even, i64 round, double tol,
                                                                      unsigned long long *__restrict__ rotations)
 {
@@ -325,11 +325,34 @@ int grid_for(rb_ctx *ctx, i64 total, int per_block)
     return (int)blocks;
 }
 
+// A round is a single dependent step, so its duration is (waves of CTAs) x (one CTA's latency chain): the shared-memory
+// column cache is used only when it does not cost a wave.  Resident CTAs per SM: 8 by threads and registers (launch bounds:
+// 32 registers); with the cache also by shared memory (2 n doubles + 1 KB reserved each, maximum carve-out requested).
+// n = 1800 (900 pairs): 7 x 148 = 1036 slots hold the round in one wave, where the 6 CTAs per SM of the first build (40
+// registers; ncu: 1.01 waves) ran a second, nearly empty one.
+bool eig_use_cache(rb_ctx *ctx, i64 n, i64 n_even)
+{
+    if (n > EIG_CACHE_MAX_N) return false;
+    static bool carve_set[64] = {false};
+    const int dev = ctx->device & 63;
+    if (!carve_set[dev]) {
+        cudaFuncSetAttribute(rb_jacobi_round_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(rb_jacobi_round_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaGetLastError();
+        carve_set[dev] = true;
+    }
+    const i64 pairs = n_even / 2;
+    i64 occ_cache = (i64)(227 * 1024) / (2 * n * 8 + 1024);
+    if (occ_cache > 8) occ_cache = 8;
+    if (occ_cache < 1) occ_cache = 1;
+    return rb_cdiv(pairs, occ_cache * ctx->num_sms) <= rb_cdiv(pairs, (i64)8 * ctx->num_sms);
+}
+
 template <bool ACCUM_V>
 int launch_round(rb_ctx *ctx, double *g, double *v, i64 n, i64 n_even, i64 round, double tol, unsigned long long *rot)
 {
     const unsigned blocks = (unsigned)(n_even / 2);
-    if (n <= EIG_CACHE_MAX_N)
+    if (eig_use_cache(ctx, n, n_even))
         rb_jacobi_round_kernel<ACCUM_V, true><<<blocks, EIG_THREADS, (size_t)(2 * n * 8), ctx->stream>>>(g, v, n, n_even, round, tol, rot);
     else
         rb_jacobi_round_kernel<ACCUM_V, false><<<blocks, EIG_THREADS, 0, ctx->stream>>>(g, v, n, n_even, round, tol, rot);
@@ -357,7 +380,7 @@ bool build_sweep_graph(rb_ctx *ctx, SweepGraph &sg, bool psd, double *g, double 
     mp.dst = rot; mp.value = 0; mp.elementSize = 4; mp.width = 2; mp.height = 1; mp.pitch = 8;
     cudaGraphNode_t prev = nullptr;
     if (cudaGraphAddMemsetNode(&prev, sg.graph, nullptr, 0, &mp) != cudaSuccess) { cudaGetLastError(); return false; }
-    const bool cache = n <= EIG_CACHE_MAX_N;
+    const bool cache = eig_use_cache(ctx, n, n_even);
     void *fn = psd ? (cache ? (void *)rb_jacobi_round_kernel<true, true> : (void *)rb_jacobi_round_kernel<true, false>)
                    : (cache ? (void *)rb_jacobi_round_kernel<false, true> : (void *)rb_jacobi_round_kernel<false, false>);
     for (i64 round = 0; round < n_even - 1; ++round) {
