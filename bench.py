@@ -145,7 +145,7 @@ def run_reference(args):
         "config": {"workload": desc, "nb": nb, "slabs_per_rank": nx, "nocc": no,
                    "note": "reference algorithm (oracle port of restmatr.f90 + OpenBLAS) on the host cores; each step is a "
                            "bounded sample of the per-rank workload, throughput is per-slab so it scales linearly"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu.threads, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu.threads, **host_cpu_model(), "kind": "port",
                          "sample": cpu.describe(slabs, nx)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -193,6 +193,19 @@ class ClockSampler:
                 reasons.append(name)
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": reasons,
                 "power_w_max": max(float(r[3]) for r in rows), "samples": len(rows)}
+
+
+def host_cpu_model():
+    """CPU model string and logical CPU count of the box (SURVEY 8d asks for both next to the CPU baseline)"""
+    model = None
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.lower().startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except Exception:
+        pass
+    return {"cpu_model": model, "nproc": os.cpu_count()}
 
 
 def host_mem_available_bytes():
@@ -470,7 +483,7 @@ def run_ours(args):
             t0 = time.perf_counter(); cpu.step(); cts.append(time.perf_counter() - t0)
         cdt = sorted(cts)[1]
         cpu_baseline = {"value": sum(flops(nb, slabs, no).values()) / cdt / 1e9, "unit": UNIT, "cores": cpu.threads,
-                        "kind": "port", "sample": cpu.describe(slabs, nx)}
+                        "kind": "port", "sample": cpu.describe(slabs, nx), **host_cpu_model()}
         # the same algorithm on ONE host thread (SURVEY 8d asks for both), on a ~3 s sample
         if cpu.have_blas and cpu.threads > 1:
             all_threads = cpu.threads
