@@ -3,17 +3,25 @@
 
 A "step" is one pass of the hot path over one rank's P-shard of a synthetic RI tensor:
     ao2mo (square C, reference semantics: 4*nb^3*nx flop)  +  d_P  +  J  +  K  (+ ONE all-reduce each for J, K when N > 1)
-Workload at N=1: BASELINE config C (nb=600, naux=1700, nocc=60; ri3ao 4.9 GB) -- the largest configuration of
-BASELINE.json:configs that fits one GPU together with its square ri3mo and host staging (config D's square ri3mo
-is 124 GB + 124 GB).  N > 1 is weak scaling: every rank holds `nx` slabs (global naux = nx * N, P-sharded exactly
-like shard_range()).  `--config D` selects the north-star shard (nb=1800, 600 slabs/rank = naux 4800 on 8 GPUs).
+`value` at N=1: BASELINE config C (nb=600, naux=1700, nocc=60; ri3ao 4.9 GB) -- the largest configuration of
+BASELINE.json:configs that fits one GPU together with its square ri3mo and host staging.  For N > 1 `value` is weak
+scaling of that workload (every rank holds 1700 slabs, global naux = 1700 * N, P-sharded exactly like shard_range()), so
+that the line stays comparable across N.  The same JSON line also carries, device-timed with the same rules:
+    step_occ_vir  the north star's step: occ-vir ao2mo (C_occ^T (mu nu|P) C_vir) + d_P + J + K on the same shards
+    strong_C      (N > 1) config C's 1700 slabs split over the N ranks, incl. both all-reduces (BASELINE: "1-8 B200")
+    config_D      (N = 8) the north-star target: nb=1800, naux=4800, nocc=180 P-sharded over 8 GPUs, with its own roofline
+    parity        all-reduced J / K, d_P and every rank's ri3mo rows against the CPU oracle on a reduced-slab replica of
+                  the same shapes (the oracle is the checker here, never on the timed path)
+    small_configs (N = 1) configs A and B: device, e2e pinned, e2e pageable and the reference CPU path
 
     python bench.py --gpus N --steps K --warmup W              # our arm (one process per GPU under torchrun)
     python bench.py --impl reference --gpus N --steps K ...    # the reference algorithm on the host cores (rank 0 only)
 
 `value` is device-timed (CUDA events, barrier + synchronize on both sides, max over ranks) with inputs resident in
 HBM; `e2e` goes through the host-pointer C ABI (rb_host_ri_ao2mo_jk: pinned host ri3ao in, host ri3mo/J/K out, H2D
-and D2H inside the timed region).  Inputs (4.9 GB) are larger than L2 (126 MB), so no explicit L2 flush is needed.
+and D2H inside the timed region).  Inputs (4.9 GB) are larger than L2 (126 MB), so no explicit L2 flush is needed; the
+small configs (A: 32 MB) flush L2 between timed iterations.  The collectives are librest_b200's own (rb_allreduce_sum:
+NCCL bound inside the library, on the compute stream); torch.distributed only carries the rendezvous and host barriers.
 """
 from __future__ import annotations
 
@@ -29,7 +37,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-CONFIGS = {  # name: (nb, slabs per rank, nocc, description)
+CONFIGS = {  # name: (nb, slabs per rank in the weak-scaling `value`, nocc, description)
     "A": (100, 400, 20, "A: bench_tensors.rs scale nb=100 naux=400 nocc=20"),
     "B": (264, 720, 21, "B: benzene/def2-TZVP-sized nb=264 naux=720 nocc=21"),
     "C": (600, 1700, 60, "C: C20/cc-pVTZ-sized nb=600 naux=1700 nocc=60"),
@@ -58,21 +66,30 @@ def emit_json_line(obj):
     os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
 
 
-def flops(nb, nx, no):
-    """algorithmic flop of one step over nx slabs"""
+def flops(nb, nx, no, square=True):
+    """algorithmic flop of one step over nx slabs; square=False: occ-vir ao2mo, cheapest order"""
     return {
-        "ao2mo": 4.0 * nb ** 3 * nx,
+        "ao2mo": 4.0 * nb ** 3 * nx if square else (2.0 * no * nb * nb + 2.0 * no * nb * (nb - no)) * nx,
         "k": (2.0 * nb * nb * no + nb * (nb + 1.0) * no) * nx,
         "dp": 2.0 * nb * nb * nx,
         "j": 2.0 * nb * nb * nx,
     }
 
 
+def config_dict(name, world):
+    """The `config` object of the JSON line -- the SAME dict in both arms (the driver compares them key by key)."""
+    nb, nx, no, desc = CONFIGS[name]
+    return {"workload": desc, "nb": nb, "slabs_per_rank": nx, "naux_global": nx * world, "nocc": no,
+            "parallelism": f"P-shard x{world}; all-reduce(sum) of J and K only",
+            "ao2mo": "square C (reference ri_ao2mo_f semantics), 4*nb^3*nx flop",
+            "l2": "inputs (ri3ao %.1f GB/rank) larger than L2; no flush needed" % (nx * nb * nb * 8 / 1e9)}
+
+
 # --------------------------------------------------------------------------------------------------------------
-# reference CPU path (oracle port + OpenBLAS) -- used by --impl reference and by the cpu_baseline leg
+# reference CPU path (oracle port + OpenBLAS) -- used by --impl reference, the cpu_baseline leg and the parity checker
 # --------------------------------------------------------------------------------------------------------------
 class CpuPath:
-    def __init__(self, nb, no):
+    def __init__(self, nb, no, threads=None):
         import numpy as np
         from oracle.api import Oracle
         self.np = np
@@ -82,7 +99,7 @@ class CpuPath:
             self.cores = len(os.sched_getaffinity(0))
         except Exception:
             pass
-        self.have_blas = self.o.load_openblas(threads=self.cores)
+        self.have_blas = self.o.load_openblas(threads=threads or self.cores)
         self.threads = self.o.blas_threads() if self.have_blas else 1
         self.nb, self.no = nb, no
         c = self.o.fill_linear(nb * nb, 3, scale=nb ** -0.5)
@@ -93,9 +110,9 @@ class CpuPath:
         self.ri = None
         self.ns = 0
 
-    def set_sample(self, slabs):
+    def set_sample(self, slabs, p_lo=0):
         self.ns = int(slabs)
-        self.ri = self.o.fill_ri3ao_symm(self.nb, 0, self.ns)
+        self.ri = self.o.fill_ri3ao_symm(self.nb, p_lo, p_lo + self.ns)
 
     def step(self):
         """reference algorithm on the sample: ri_ao2mo_f (restmatr.f90:158-194) + d_P/J (dgemv) + K (dgemm+dsyrk per slab)"""
@@ -127,6 +144,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     quiet_stdout()
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     nb, nx, no, desc = CONFIGS[args.config]
     cpu = CpuPath(nb, no)
     slabs = cpu.calibrate(target_s=3.0, max_slabs=nx)
@@ -142,9 +160,9 @@ def run_reference(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "impl": "reference",
-        "config": {"workload": desc, "nb": nb, "slabs_per_rank": nx, "nocc": no,
-                   "note": "reference algorithm (oracle port of restmatr.f90 + OpenBLAS) on the host cores; each step is a "
-                           "bounded sample of the per-rank workload, throughput is per-slab so it scales linearly"},
+        "config": config_dict(args.config, world),
+        "note": "reference algorithm (oracle port of restmatr.f90 + OpenBLAS) on the host cores; each step is a bounded "
+                "sample of the per-rank workload, throughput is per-slab so it scales linearly",
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu.threads, **host_cpu_model(), "kind": "port",
                          "sample": cpu.describe(slabs, nx)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -218,31 +236,190 @@ def host_mem_available_bytes():
     return None
 
 
-def run_e2e(args, torch, dist, lib, check, all_reduce_sum, world, dev, nb, nx, no, n2, sh, c, dm, ct, mo, k, total_flop, barrier):
-    """Same step through rb_host_ri_ao2mo_jk with pinned HOST buffers: every rank streams its whole shard up and its
-    ri3mo rows down.  Returns the `e2e` object; never raises (a host that cannot pin 2 x shard bytes per rank gets a
-    reduced-slab measurement, clearly labelled)."""
+# --------------------------------------------------------------------------------------------------------------
+# our arm: one rank's device-resident workload
+# --------------------------------------------------------------------------------------------------------------
+class Env:
+    """per-process plumbing shared by the legs"""
+
+    def __init__(self, torch, dist, ctx, rank, world, local):
+        self.torch, self.dist, self.ctx, self.rank, self.world, self.local = torch, dist, ctx, rank, world, local
+        self.dev = f"cuda:{local}"
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def ev(self):
+        return self.torch.cuda.Event(enable_timing=True)
+
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([float(x)], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+class Workload:
+    """ri3ao shard of `naux` global slabs in HBM + replicated C, C~, D + the output buffers of one step"""
+
+    def __init__(self, env, nb, naux, no, square_out=True):
+        from rest_tensors_b200.device import ShardedRI
+        ctx = env.ctx
+        self.env, self.nb, self.naux, self.no = env, nb, naux, no
+        self.sh = ShardedRI(ctx, nb, naux, env.rank, env.world).fill_synthetic()
+        self.nx = self.sh.nx
+        n2 = nb * nb
+        self.c = ctx.empty(n2); ctx.fill_linear(self.c, n2, 3, 0, nb ** -0.5)
+        self.ct = ctx.empty(nb * no); ctx.fill_linear(self.ct, nb * no, 3, 0, nb ** -0.5)
+        ctx.self_multiple(self.ct, 2.0 ** 0.5, nb * no)
+        self.dm = ctx.empty(n2)
+        ctx.dgemm("N", "T", nb, nb, no, 2.0, self.c, nb, self.c, nb, 0.0, self.dm, nb)   # D = 2 C_occ C_occ^T (our own GEMM)
+        self.mo = ctx.empty(max(1, self.nx) * n2) if square_out else None
+        self.ov = None
+        self.d = ctx.empty(max(1, self.nx)); self.j = ctx.empty(n2); self.k = ctx.empty(n2)
+
+    def step(self, square=True, marks=None):
+        sh, nb, no = self.sh, self.nb, self.no
+        if marks: marks[0].record()
+        if square:
+            sh.ao2mo(self.c, nb, self.c, nb, out=self.mo)
+        else:
+            if self.ov is None:
+                self.ov = self.env.ctx.empty(max(1, self.nx) * no * (nb - no))
+            sh.ao2mo(self.c[: nb * no], no, self.c[nb * no:], nb - no, out=self.ov)
+        if marks: marks[1].record()
+        sh.dp(self.dm, out=self.d)
+        if marks: marks[2].record()
+        sh.j(self.d, out=self.j, reduce=True)
+        if marks: marks[3].record()
+        sh.k(self.ct, no, out=self.k, reduce=True)
+        if marks: marks[4].record()
+
+    def measure(self, steps, warmup, square=True):
+        """W untimed steps, then exactly `steps` steps bracketed by barrier + synchronize; CUDA events on the launching
+        stream; max over ranks.  Returns ms per step, this rank's per-phase averages and the launches in the timed region."""
+        env = self.env
+        for _ in range(warmup):
+            self.step(square)
+        env.barrier()
+        launches0 = env.ctx.launches
+        e0, e1 = env.ev(), env.ev()
+        e0.record()
+        all_marks = []
+        for _ in range(steps):
+            marks = [env.ev() for _ in range(5)]
+            self.step(square, marks)
+            all_marks.append(marks)
+        e1.record()
+        env.barrier()
+        launches = env.ctx.launches - launches0
+        ms_step = env.max_over_ranks(e0.elapsed_time(e1)) / steps
+        seg = {}
+        for i, name in enumerate(["ao2mo", "dp", "j", "k"]):
+            seg[name] = sum(m[i].elapsed_time(m[i + 1]) for m in all_marks) / len(all_marks)
+        return ms_step, seg, launches
+
+    def total_flop(self, square=True):
+        """whole-job flop of one step (all ranks)"""
+        return sum(flops(self.nb, self.naux, self.no, square).values())
+
+
+def rates(nb, nx, no, seg, square=True):
+    f = flops(nb, nx, no, square)
+    return {"ao2mo_tflops": f["ao2mo"] / (seg["ao2mo"] * 1e-3) / 1e12, "k_tflops": f["k"] / (seg["k"] * 1e-3) / 1e12,
+            "dp_gbs": nx * nb * nb * 8 / (seg["dp"] * 1e-3) / 1e9, "j_gbs": nx * nb * nb * 8 / (seg["j"] * 1e-3) / 1e9}
+
+
+def allreduce_ms(env, n, reps=20):
+    """device time of one rb_allreduce_sum over n doubles (max over ranks)"""
+    if env.world == 1:
+        return 0.0
+    buf = env.ctx.empty(n); buf.zero_()
+    for _ in range(3):
+        env.ctx.allreduce_sum(buf)
+    env.barrier()
+    e0, e1 = env.ev(), env.ev()
+    e0.record()
+    for _ in range(reps):
+        env.ctx.allreduce_sum(buf)
+    e1.record()
+    env.barrier()
+    return env.max_over_ranks(e0.elapsed_time(e1)) / reps
+
+
+def parity_leg(env, nb, no, slabs_per_rank):
+    """Oracle parity of the multi-rank path on a reduced-slab replica of the same shapes: naux = slabs_per_rank * N slabs,
+    P-sharded like the real run, the same kernels and the same all-reduces.  Every rank checks its own ri3mo rows and d_P
+    piece against the oracle run on its own slabs (per-slab work is independent); rank 0 checks the all-reduced J and K
+    against the oracle over ALL slabs; all ranks must hold bitwise the same J and K.  Norm-wise relative errors."""
+    import numpy as np
+    torch = env.torch
+    naux = slabs_per_rank * env.world
+    w = Workload(env, nb, naux, no)
+    w.step(True)
+    torch.cuda.synchronize()
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(env.world)))
+    cpu = CpuPath(nb, no, threads=max(1, (os.cpu_count() or 1) // local_world))
+    o = cpu.o
+
+    def err(x, y):
+        den = float(np.max(np.abs(y)))
+        return float(np.max(np.abs(np.asarray(x) - y))) / den if den > 0 else 0.0
+
+    ri_local = o.fill_ri3ao_symm(nb, w.sh.p_lo, w.sh.p_hi)
+    assert np.array_equal(w.sh.data.cpu().numpy(), ri_local), "device generator != oracle generator"
+    e_mo = err(w.mo.cpu().numpy(), o.ri_ao2mo_f(cpu.c, ri_local, nb, nb, w.nx))
+    d_ref_local = o.ri_dp(ri_local, cpu.dm, nb, w.nx)
+    e_dp = err(w.d.cpu().numpy()[: w.nx], d_ref_local)
+    e_mo, e_dp = env.max_over_ranks(e_mo), env.max_over_ranks(e_dp)
+    # J / K: identical on every rank?  (sum of |x| and a position-weighted sum, compared as max - min over ranks)
+    j, k = w.j.cpu().numpy(), w.k.cpu().numpy()
+    sig = [float(np.sum(j)), float(np.sum(k)), float(np.dot(j, np.arange(j.size) % 97)), float(np.dot(k, np.arange(k.size) % 89))]
+    same = all(env.max_over_ranks(s) == -env.max_over_ranks(-s) for s in sig)
+    d_full = w.sh.gather_dp(w.d[: w.nx]) if env.world > 1 else w.d[: w.nx]
+    out = {"shape": {"nb": nb, "nocc": no, "naux": naux, "slabs_per_rank": slabs_per_rank}, "mo_all_ranks": e_mo,
+           "d_P_all_ranks": e_dp, "jk_identical_on_all_ranks": bool(same)}
+    if env.rank == 0:
+        ri = o.fill_ri3ao_symm(nb, 0, naux)
+        d_ref = o.ri_dp(ri, cpu.dm, nb, naux)
+        out["d_P_gathered"] = err(d_full.cpu().numpy(), d_ref)
+        out["J"] = err(j, o.ri_j(ri, d_ref, nb, naux))
+        out["K"] = err(k, o.ri_k(ri, cpu.ct, nb, no, naux))
+        out["bar"] = 1e-10
+        out["ok"] = bool(same and max(out["J"], out["K"], e_mo, e_dp, out["d_P_gathered"]) <= 1e-10)
+        out["checker"] = "oracle/rest_oracle.c + OpenBLAS (port of restmatr.f90:158-194 and the dgemv / dgemm+dsyrk composition)"
+    env.barrier()
+    return out
+
+
+def l2_flusher(env):
+    buf = env.torch.empty(256 << 20, dtype=env.torch.uint8, device=env.dev)
+    return lambda: buf.fill_(1)
+
+
+def e2e_leg(env, lib, check, w, total_flop, steps, pinned=True, no_numa=False):
+    """Same step through rb_host_ri_ao2mo_jk with HOST buffers: every rank streams its whole shard up and its ri3mo rows
+    down.  pinned=False: plain pageable memory (what a Rust Vec<f64> is).  Never raises."""
     import ctypes as C
-    if args.no_e2e:
-        return {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "skipped": "--no-e2e"}
-    # Host placement: pin this rank's host buffers next to its GPU's PCIe root (8 ranks streaming through the far
-    # socket share one inter-socket link otherwise).  Restored afterwards so the CPU baseline sees every core.
     saved_affinity = os.sched_getaffinity(0)
     node = C.c_int(-1)
-    if not args.no_numa:
-        check(lib.rb_bind_host_to_device_numa(int(dev.split(":")[1]), C.byref(node)), "rb_bind_host_to_device_numa")
+    if not no_numa:
+        check(lib.rb_bind_host_to_device_numa(env.local, C.byref(node)), "rb_bind_host_to_device_numa")
     try:
-        out = _run_e2e_bound(args, torch, dist, lib, check, all_reduce_sum, world, dev, nb, nx, no, n2, sh, c, dm, ct, mo, k,
-                             total_flop, barrier)
+        out = _e2e_bound(env, lib, check, w, total_flop, steps, pinned)
     finally:
         os.sched_setaffinity(0, saved_affinity)
     out["host_numa_node"] = int(node.value)
     return out
 
 
-def _run_e2e_bound(args, torch, dist, lib, check, all_reduce_sum, world, dev, nb, nx, no, n2, sh, c, dm, ct, mo, k, total_flop,
-                   barrier):
+def _e2e_bound(env, lib, check, w, total_flop, steps, pinned):
     import ctypes as C
+    torch, dist, world, dev = env.torch, env.dist, env.world, env.dev
+    nb, nx, no = w.nb, w.nx, w.no
+    n2 = nb * nb
     slabs = nx
     avail = host_mem_available_bytes()
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
@@ -250,16 +427,19 @@ def _run_e2e_bound(args, torch, dist, lib, check, all_reduce_sum, world, dev, nb
     note = None
     if avail is not None and need > 0.6 * avail:
         slabs = max(64, int(nx * 0.6 * avail / need) // 64 * 64)
-        note = f"host RAM allows pinning only {slabs} of {nx} slabs per rank; e2e measured on that sub-shard"
+        note = f"host RAM allows only {slabs} of {nx} slabs per rank; e2e measured on that sub-shard"
     alloc_err = None
     try:
-        ri_h = torch.empty(slabs * n2, dtype=torch.float64, pin_memory=True)
-        ri_h.copy_(sh.data[: slabs * n2])
-        mo_h = torch.empty(slabs * n2, dtype=torch.float64, pin_memory=True)
-        c_h, dm_h, ct_h = c.cpu().pin_memory(), dm.cpu().pin_memory(), ct.cpu().pin_memory()
-        d_h = torch.empty(slabs, dtype=torch.float64, pin_memory=True)
-        j_h = torch.empty(n2, dtype=torch.float64, pin_memory=True)
-        k_h = torch.empty(n2, dtype=torch.float64, pin_memory=True)
+        mk = (lambda n: torch.empty(n, dtype=torch.float64, pin_memory=True)) if pinned else \
+             (lambda n: torch.empty(n, dtype=torch.float64))
+        ri_h = mk(slabs * n2)
+        ri_h.copy_(w.sh.data[: slabs * n2])
+        mo_h = mk(slabs * n2)
+        if not pinned:
+            mo_h.zero_()    # touch the pages: the reference's vec![0.0; len] does the same before the FFI call
+        c_h, dm_h, ct_h = mk(n2), mk(n2), mk(nb * no)
+        c_h.copy_(w.c); dm_h.copy_(w.dm); ct_h.copy_(w.ct)
+        d_h, j_h, k_h = mk(slabs), mk(n2), mk(n2)
         torch.cuda.synchronize()
     except Exception as exc:  # noqa: BLE001
         alloc_err = f"{type(exc).__name__}: {exc}"[:300]
@@ -268,36 +448,38 @@ def _run_e2e_bound(args, torch, dist, lib, check, all_reduce_sum, world, dev, nb
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)   # all ranks take the same branch
     if float(flag.item()) < 1.0:
         return {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                "error": alloc_err or "another rank could not pin its host buffers"}
+                "error": alloc_err or "another rank could not allocate its host buffers"}
     try:
         P = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+        jk = torch.empty(2 * n2, dtype=torch.float64, device=dev) if world > 1 else None
 
         def e2e_step():
             check(lib.rb_host_ri_ao2mo_jk(P(c_h), nb, P(c_h), nb, P(ri_h), P(mo_h), nb, slabs, P(dm_h), P(ct_h), no, P(d_h),
                                           P(j_h), P(k_h)), "rb_host_ri_ao2mo_jk")
             if world > 1:  # complete J and K across ranks (host results -> NVLink all-reduce -> host)
-                jk = torch.cat([j_h, k_h]).to(dev, non_blocking=True)
-                all_reduce_sum(jk, world)
-                jk_h = jk.cpu()
-                j_h.copy_(jk_h[:n2]); k_h.copy_(jk_h[n2:])
+                jk[:n2].copy_(j_h, non_blocking=True); jk[n2:].copy_(k_h, non_blocking=True)
+                env.ctx.allreduce_sum(jk)
+                j_h.copy_(jk[:n2]); k_h.copy_(jk[n2:])
+                torch.cuda.synchronize()
 
-        steps = max(2, min(args.steps, 5))
         e2e_step()
         # parity spot check against the device-resident results of the same inputs (before J/K get all-reduced again)
-        ok = bool(torch.allclose(mo_h[: 4096], mo.view(-1)[: 4096].cpu(), rtol=1e-12, atol=1e-14)) if slabs == nx else None
-        barrier()
+        ok = None
+        if slabs == nx and w.mo is not None:
+            idx = torch.arange(0, slabs * n2, max(1, slabs * n2 // 65536))
+            ok = bool(torch.allclose(mo_h[idx], w.mo[idx.to(dev)].cpu(), rtol=1e-12, atol=1e-14))
+        env.barrier()
         t0 = time.perf_counter()
         for _ in range(steps):
             e2e_step()
-        barrier()
-        dt = torch.tensor([(time.perf_counter() - t0) / steps], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        env.barrier()
+        dt = env.max_over_ranks((time.perf_counter() - t0) / steps)
         flop = total_flop * slabs / nx
-        out = {"value": flop / float(dt.item()) / 1e9, "unit": UNIT,
+        out = {"value": flop / dt / 1e9, "unit": UNIT,
                "h2d_bytes_per_step": (slabs * n2 + 2 * n2 + nb * no) * 8, "d2h_bytes_per_step": (slabs * n2 + 2 * n2 + slabs) * 8,
-               "ms_per_step": float(dt.item()) * 1e3,
-               "api": "rb_host_ri_ao2mo_jk (host-pointer C ABI; pinned host buffers; 3-stream H2D|compute|D2H pipeline)",
+               "ms_per_step": dt * 1e3,
+               "api": "rb_host_ri_ao2mo_jk (host-pointer C ABI; %s host buffers; 3-stream H2D|compute|D2H pipeline)"
+                      % ("pinned" if pinned else "pageable"),
                "steps": steps, "matches_device_path": ok}
         if note:
             out["note"] = note
@@ -307,18 +489,50 @@ def _run_e2e_bound(args, torch, dist, lib, check, all_reduce_sum, world, dev, nb
                 "error": f"{type(exc).__name__}: {exc}"[:300]}
 
 
-# --------------------------------------------------------------------------------------------------------------
-# our arm
-# --------------------------------------------------------------------------------------------------------------
+def small_config_leg(env, lib, check, name):
+    """Configs A / B on one GPU: device-resident step, e2e through the host-pointer ABI with pinned
+    and with pageable buffers, and the reference CPU path on the FULL configuration, all in GFLOP/s of the same step."""
+    nb, nx, no, desc = CONFIGS[name]
+    torch = env.torch
+    w = Workload(env, nb, nx, no)
+    flop = w.total_flop(True)
+    flush = l2_flusher(env) if nx * nb * nb * 8 < (256 << 20) else (lambda: None)
+    for _ in range(3):
+        w.step(True)
+    times = []
+    for _ in range(10):
+        flush()
+        e0, e1 = env.ev(), env.ev()
+        e0.record(); w.step(True); e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    ms = sorted(times)[len(times) // 2]
+    out = {"workload": desc, "device": {"ms": ms, "gflops": flop / (ms * 1e-3) / 1e9,
+                                        "l2": "flushed between iterations" if nx * nb * nb * 8 < (256 << 20) else "inputs > L2"}}
+    for pinned in (True, False):
+        r = _e2e_bound(env, lib, check, w, flop, 5, pinned)
+        out["e2e_pinned" if pinned else "e2e_pageable"] = {"ms": r.get("ms_per_step"), "gflops": r.get("value"),
+                                                            "matches_device_path": r.get("matches_device_path"),
+                                                            **({"error": r["error"]} if "error" in r else {})}
+    cpu = CpuPath(nb, no)
+    cpu.set_sample(nx)
+    cpu.step()
+    cts = []
+    for _ in range(3):
+        t0 = time.perf_counter(); cpu.step(); cts.append(time.perf_counter() - t0)
+    cdt = sorted(cts)[1]
+    out["cpu_reference"] = {"ms": cdt * 1e3, "gflops": flop / cdt / 1e9, "cores": cpu.threads, "sample": "full configuration"}
+    return out
+
+
 def run_ours(args):
     quiet_stdout()
-    import ctypes as C
-    import numpy as np
+    import ctypes as C  # noqa: F401
     import torch
     import torch.distributed as dist
     from rest_tensors_b200 import lib
     from rest_tensors_b200._lib import check
-    from rest_tensors_b200.device import Context, ShardedRI, all_reduce_sum
+    from rest_tensors_b200.device import Context
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -329,39 +543,14 @@ def run_ours(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{local}"))
-    dev = f"cuda:{local}"
+    ctx = Context(local)
+    env = Env(torch, dist, ctx, rank, world, local)
     nb, nx, no, desc = CONFIGS[args.config]
     naux = nx * world
-    ctx = Context(local)
-    sh = ShardedRI(ctx, nb, naux, rank, world).fill_synthetic()
-    assert sh.nx == nx
+    w = Workload(env, nb, naux, no)
+    assert w.nx == nx
     n2 = nb * nb
-    c = ctx.empty(n2); ctx.fill_linear(c, n2, 3, 0, nb ** -0.5)
-    ct = ctx.empty(nb * no); ctx.fill_linear(ct, nb * no, 3, 0, nb ** -0.5); ctx.self_multiple(ct, 2.0 ** 0.5, nb * no)
-    dm = ctx.empty(n2)
-    ctx.dgemm("N", "T", nb, nb, no, 2.0, c, nb, c, nb, 0.0, dm, nb)       # D = 2 C_occ C_occ^T (our own GEMM)
-    mo = ctx.empty(nx * n2); d = ctx.empty(nx); j = ctx.empty(n2); k = ctx.empty(n2)
     f = flops(nb, nx, no)
-    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
-    seg = {"ao2mo": [], "dp": [], "j": [], "k": []}
-
-    def step(record=False):
-        marks = [ev() for _ in range(5)] if record else None
-        if record: marks[0].record()
-        sh.ao2mo(c, nb, c, nb, out=mo)
-        if record: marks[1].record()
-        sh.dp(dm, out=d)
-        if record: marks[2].record()
-        sh.j(d, out=j, reduce=True)
-        if record: marks[3].record()
-        sh.k(ct, no, out=k, reduce=True)
-        if record: marks[4].record()
-        return marks
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     # roofline denominators, measured live before the timed region
     dmma_peak = max(ctx.fp64_peak_probe(0, 100000)[0] for _ in range(2))
@@ -373,102 +562,107 @@ def run_ours(args):
     hbm_peak, hbm_src = (peaks["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (of measured)") if "hbm_gbs" in peaks else \
         (6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)")
 
-    for _ in range(max(args.warmup, 3) if args.warmup >= 0 else 3):
-        step()
-    barrier()
+    # ---- the timed region of `value` ----
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        w.step(True)
+    env.barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.2)
-    launches0 = ctx.launches
-    barrier()
     t_wall0 = time.perf_counter()
-    e0, e1 = ev(), ev()
-    e0.record()
-    all_marks = [step(record=True) for _ in range(args.steps)]
-    e1.record()
-    barrier()
+    ms_step, avg, launches = w.measure(args.steps, 0, True)
     t_wall1 = time.perf_counter()
-    launches = ctx.launches - launches0
-    ms_total = e0.elapsed_time(e1)
-    tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ms_step = float(tmax.item()) / args.steps
-    for m in all_marks:
-        for i, name in enumerate(["ao2mo", "dp", "j", "k"]):
-            seg[name].append(m[i].elapsed_time(m[i + 1]))
-    avg = {kname: sum(v) / len(v) for kname, v in seg.items()}
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
-    total_flop = sum(f.values()) * world
+    total_flop = w.total_flop(True)
     value = total_flop / (ms_step * 1e-3) / 1e9
+    nccl_ver = ctx.nccl_version() if world > 1 else None
 
-    # ---- extra (outside the timed region, not part of `value`): the north star's occ-vir form of ao2mo,
-    #      C_occ^T (mu nu|P) C_vir, on the same shard; flop = (2 no nb^2 + 2 no nb nv) nx ----
-    nv = nb - no
-    ov = ctx.empty(nx * no * nv)
-    ov_ms = []
-    for it in range(0 if args.no_extras else 4):
-        a0, a1 = ev(), ev()
-        a0.record(); sh.ao2mo(c[: nb * no], no, c[nb * no:], nv, out=ov); a1.record()
-        torch.cuda.synchronize()
-        if it:
-            ov_ms.append(a0.elapsed_time(a1))
-    ov_flop = (2.0 * no * nb * nb + 2.0 * no * nb * nv) * nx
-    occ_vir = None if args.no_extras else {
-        "ms": min(ov_ms), "tflops_per_gpu": ov_flop / (min(ov_ms) * 1e-3) / 1e12,
-        "note": "ao2mo with C_left = C_occ [nb,nocc], C_right = C_vir [nb,nb-nocc]; best of 3, per rank"}
-    # ---- extra: the step after ao2mo -- (ia|jb) blocks straight from the occ-vir ri3mo above:
-    #      diagonal block pair (i-block == j-block; SYRK, M(M+1)K flop) and an off-diagonal pair (GEMM, 2MNK flop);
-    #      the i-block is as many occupied orbitals as keep the [M, M] block under 6 GB ----
+    # ---- step_occ_vir: the north star's step (occ-vir ao2mo + d_P + J + K incl. all-reduces), same shards ----
+    step_occ_vir = None
+    if not args.no_extras:
+        ov_ms, ov_seg, _ = w.measure(max(3, min(args.steps, 5)), 2, False)
+        ov_flop = w.total_flop(False)
+        step_occ_vir = {"ms_per_step": ov_ms, "value": ov_flop / (ov_ms * 1e-3) / 1e9, "unit": UNIT,
+                        "frac_of_dmma_peak": ov_flop / (ov_ms * 1e-3) / 1e12 / (dmma_peak * world),
+                        "breakdown_ms": {kk: round(v, 4) for kk, v in ov_seg.items()},
+                        "breakdown_rate": rates(nb, nx, no, ov_seg, False),
+                        "note": "C_left = C_occ [nb,nocc], C_right = C_vir [nb,nb-nocc]; flop = (2 no nb^2 + 2 no nb nv) nx + K + d_P + J"}
+
+    # ---- strong scaling of config C: 1700 slabs over the N ranks (BASELINE: 'n_aux=1700, 1-8 B200') ----
+    strong = None
+    if world > 1 and args.config == "C" and not args.no_extras:
+        ws_ = Workload(env, nb, nx, no)
+        s_ms, s_seg, s_launches = ws_.measure(max(args.steps, 10), 3, True)
+        ar = allreduce_ms(env, n2)
+        sf = ws_.total_flop(True)
+        t1 = ms_step   # this run's weak step = the same 1700 slabs on ONE GPU (plus two all-reduces)
+        crit = max(s_seg, key=s_seg.get)
+        strong = {"slabs_global": nx, "slabs_this_rank": ws_.nx, "ms_per_step": s_ms, "value": sf / (s_ms * 1e-3) / 1e9,
+                  "unit": UNIT, "speedup_vs_1gpu_same_run": t1 / s_ms, "efficiency": t1 / s_ms / world,
+                  "frac_of_dmma_peak": sf / (s_ms * 1e-3) / 1e12 / (dmma_peak * world),
+                  "breakdown_ms_rank0": {kk: round(v, 4) for kk, v in s_seg.items()},
+                  "breakdown_rate_rank0": rates(nb, ws_.nx, no, s_seg, True),
+                  "allreduce_ms_each": ar, "allreduce_bytes": n2 * 8, "gpu_launches_per_step": s_launches / max(args.steps, 10),
+                  "largest_phase": crit,
+                  "note": "1-GPU reference time = this run's weak step (1700 slabs per rank); j and k phases include their all-reduce"}
+        del ws_
+
+    # ---- parity of the multi-rank path against the oracle (reduced-slab replica, same shapes) ----
+    parity = {}
+    if not args.no_parity:
+        try:
+            parity["C_shape"] = parity_leg(env, nb, no, 16)
+        except Exception as exc:  # noqa: BLE001
+            parity["C_shape"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
+    # ---- extras on the occ-vir ri3mo of this rank (the step after ao2mo) ----
     iajb = None
-    try:
-        if args.no_extras:
-            raise RuntimeError("skipped (--no-extras)")
-        li = max(1, min(no // 2 if no >= 2 else 1, int(((6 << 30) / 8) ** 0.5) // max(nv, 1)))
-        if (6 << 30) / 8 >= float(no * nv) ** 2:
-            li = no
-        m_blk = li * nv
-        g = ctx.empty(m_blk * m_blk)
-        res = {}
-        pairs = [("diag", (0, li, 0, nv), (0, li, 0, nv), float(m_blk) * (m_blk + 1) * nx)]
-        if 2 * li <= no:
-            pairs.append(("offdiag", (0, li, 0, nv), (li, li, 0, nv), 2.0 * m_blk * m_blk * nx))
-        for name, ba, bb, fl in pairs:
-            best = None
-            for it in range(3):
-                a0, a1 = ev(), ev()
-                a0.record(); sh.iajb(ov, no, nv, ba, bb, out=g, reduce=False); a1.record()
-                torch.cuda.synchronize()
-                if it:
-                    best = a0.elapsed_time(a1) if best is None else min(best, a0.elapsed_time(a1))
-            res[name] = {"ms": best, "tflops_per_gpu": fl / (best * 1e-3) / 1e12}
-        # RPA-type consumer on the same tensor: Pi[P,Q] = sum_ia w_ia R_ia^P R_ia^Q (upper triangle + mirror, np(np+1)K flop)
-        wts = ctx.empty(no * nv); ctx.fill_linear(wts, no * nv, 9, 0, 1.0)
-        pi = ctx.empty(nx * nx)
-        best = None
-        for it in range(3):
-            a0, a1 = ev(), ev()
-            a0.record(); ctx.ri_mo_pq(ov, nx, nx, ov, nx, nx, no, nv, (0, no, 0, nv), wts, 0.0, pi, nx); a1.record()
-            torch.cuda.synchronize()
-            if it:
-                best = a0.elapsed_time(a1) if best is None else min(best, a0.elapsed_time(a1))
-        res["mo_pq_weighted"] = {"ms": best, "tflops_per_gpu": float(nx) * (nx + 1) * no * nv / (best * 1e-3) / 1e12,
-                                 "m": nx, "k": no * nv}
-        del pi, wts
-        iajb = {"occ_block": li, "rows": m_blk, "k": nx, **res,
-                "note": "rb_ri_iajb on this rank's rows of the occ-vir ri3mo (partial sum; all-reduce not timed); best of 2"}
-        del g
-    except Exception as exc:  # noqa: BLE001
-        iajb = {"error": f"{type(exc).__name__}: {exc}"[:200]}
-    del ov
+    if not args.no_extras:
+        iajb = consumers_leg(env, w)
 
-    # ---- e2e through the host-pointer C ABI (pinned host buffers; H2D + D2H inside the timed region) ----
-    e2e = run_e2e(args, torch, dist, lib, check, all_reduce_sum, world, dev, nb, nx, no, n2, sh, c, dm, ct, mo, k, total_flop,
-                  barrier)
+    # ---- e2e through the host-pointer C ABI (H2D + D2H inside the timed region) ----
+    if args.no_e2e:
+        e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "skipped": "--no-e2e"}
+        e2e_pageable = None
+    else:
+        e2e = e2e_leg(env, lib, check, w, total_flop, max(2, min(args.steps, 5)), True, args.no_numa)
+        e2e_pageable = None
+        if world == 1:
+            check(lib.rb_host_trim(), "rb_host_trim")
+            e2e_pageable = e2e_leg(env, lib, check, w, total_flop, 3, False, args.no_numa)
+        check(lib.rb_host_trim(), "rb_host_trim")
+
+    # ---- config D (north star) on 8 GPUs: nb=1800, naux=4800, nocc=180, 600 slabs per rank ----
+    config_d = None
+    if (world == 8 or args.config_d_leg) and args.config == "C" and not args.no_extras:
+        del w
+        torch.cuda.empty_cache()
+        try:
+            config_d = config_d_leg(env, dmma_peak, hbm_peak, args)
+        except Exception as exc:  # noqa: BLE001
+            config_d = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        if not args.no_parity:
+            try:
+                parity["D_shape"] = parity_leg(env, 1800, 180, 4)
+            except Exception as exc:  # noqa: BLE001
+                parity["D_shape"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
+    # ---- configs A and B on one GPU ----
+    small = None
+    if world == 1 and args.config == "C" and not args.no_extras and not args.no_e2e:
+        small = {}
+        for name in ("A", "B"):
+            try:
+                small[name] = small_config_leg(env, lib, check, name)
+            except Exception as exc:  # noqa: BLE001
+                small[name] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        check(lib.rb_host_trim(), "rb_host_trim")
 
     if rank != 0:
         if world > 1:
+            ctx.comm_destroy()
             dist.destroy_process_group()
         return 0
 
@@ -494,38 +688,44 @@ def run_ours(args):
             cpu_baseline["value_single_thread"] = sum(flops(nb, s1, no).values()) / c1 / 1e9
             cpu_baseline["single_thread_sample_slabs"] = s1
 
-    traffic = traffic_dp = None
+    traffic = traffic_dp = traffic_src = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
-        traffic, traffic_dp = tj.get(args.config), tj.get(args.config + "_dp")
+        traffic, traffic_dp, traffic_src = tj.get(args.config), tj.get(args.config + "_dp"), tj.get("source")
     except Exception:
         pass
     gemm_launch_ms = avg["ao2mo"] / 2.0                      # ao2mo = 2 launches of the TMA+DMMA GEMM kernel
     achieved = (f["ao2mo"] / 2.0) / (gemm_launch_ms * 1e-3) / 1e12
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": desc, "nb": nb, "slabs_per_rank": nx, "naux_global": naux, "nocc": no,
-                   "parallelism": f"P-shard x{world}; all-reduce(sum) of J and K only",
-                   "ao2mo": "square C (reference ri_ao2mo_f semantics), 4*nb^3*nx flop",
-                   "l2": "inputs (ri3ao %.1f GB/rank) larger than L2; no flush needed" % (nx * n2 * 8 / 1e9)},
+        "config": config_dict(args.config, world),
         "breakdown_ms": {kname: round(v, 4) for kname, v in avg.items()},
-        "breakdown_rate": {"ao2mo_tflops": f["ao2mo"] / (avg["ao2mo"] * 1e-3) / 1e12,
-                           "k_tflops": f["k"] / (avg["k"] * 1e-3) / 1e12,
-                           "dp_gbs": nx * n2 * 8 / (avg["dp"] * 1e-3) / 1e9, "j_gbs": nx * n2 * 8 / (avg["j"] * 1e-3) / 1e9},
+        "breakdown_rate": rates(nb, nx, no, avg, True),
         "roofline": {"bound": "tensor", "kernel": "rb_gemm_tma_kernel<A_K=1,B_K=1> (ao2mo GEMMs; DMMA.8x8x4 fed by TMA)",
                      "achieved": achieved, "peak": dmma_peak, "unit": "TFLOP/s", "frac": achieved / dmma_peak,
                      "peak_source": "live register-resident DMMA.8x8x4 probe on this GPU (MEASURED_PEAKS.json holds only "
-                                    "bf16/HBM; nominal B200 FP64 tensor 37-40 TFLOP/s)",
-                     "flop_per_launch": f["ao2mo"] / 2.0, "launch_ms": gemm_launch_ms, "traffic": traffic},
+                                    "bf16/HBM; nominal B200 FP64 tensor 37-40 TFLOP/s; probe SASS + ncu pipe utilisation: "
+                                    "profiles/r02_fp64_probe.md)",
+                     "flop_per_launch": f["ao2mo"] / 2.0, "launch_ms": gemm_launch_ms, "traffic": traffic,
+                     "traffic_source": traffic_src or "profiles/roofline_traffic.json (an ncu --set full capture of this "
+                                                      "command, NOT re-measured by this run)"},
         "roofline_hbm": {"bound": "hbm", "kernel": "rb_gemv_t_vec_kernel (d_P) / rb_gemv_n_kernel (J)",
                          "achieved": nx * n2 * 8 / (avg["dp"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                          "frac": nx * n2 * 8 / (avg["dp"] * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
                          "j_achieved": nx * n2 * 8 / (avg["j"] * 1e-3) / 1e9, "traffic": traffic_dp},
         "e2e": e2e,
-        "ao2mo_occ_vir": occ_vir,
+        "e2e_pageable": e2e_pageable,
+        "step_occ_vir": step_occ_vir,
+        "strong_C": strong,
+        "config_D": config_d,
+        "parity": parity,
+        "small_configs": small,
         "iajb_occ_vir": iajb,
+        "collectives": None if world == 1 else {"api": "rb_allreduce_sum / rb_ri_j_allreduce / rb_ri_k_allreduce (librest_b200, NCCL "
+                                                       "bound at run time, compute stream)", "nccl_version": nccl_ver[0],
+                                                "nccl_lib": nccl_ver[1]},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
@@ -533,8 +733,89 @@ def run_ours(args):
         line["cpu_baseline"] = cpu_baseline
     emit_json_line(line)
     if world > 1:
+        ctx.comm_destroy()
         dist.destroy_process_group()
     return 0
+
+
+def config_d_leg(env, dmma_peak, hbm_peak, args):
+    """North-star configuration: C60/cc-pVTZ-sized ri3ao (nb=1800, naux=4800, nocc=180; 124 GB) P-sharded over the ranks;
+    square ao2mo + d_P + J + K with both all-reduces, device-timed like `value`; plus the occ-vir step."""
+    nb, _, no, desc = CONFIGS["D"]
+    naux = 4800
+    w = Workload(env, nb, naux, no)
+    steps = 3
+    ms, seg, launches = w.measure(steps, 2, True)
+    tf = w.total_flop(True)
+    f = flops(nb, w.nx, no)
+    achieved = f["ao2mo"] / (seg["ao2mo"] * 1e-3) / 1e12
+    out = {"workload": desc, "naux_global": naux, "slabs_this_rank": w.nx, "steps": steps, "warmup": 2,
+           "ms_per_step": ms, "value": tf / (ms * 1e-3) / 1e9, "unit": UNIT,
+           "frac_of_dmma_peak": tf / (ms * 1e-3) / 1e12 / (dmma_peak * env.world),
+           "target": ">= 0.60 of FP64 tensor peak on 8 x B200 (BASELINE.json north_star)",
+           "breakdown_ms_rank0": {kk: round(v, 4) for kk, v in seg.items()},
+           "breakdown_rate_rank0": rates(nb, w.nx, no, seg, True),
+           "roofline": {"bound": "tensor", "kernel": "rb_gemm_tma_kernel<1,1> (ao2mo GEMMs)", "achieved": achieved,
+                        "peak": dmma_peak, "unit": "TFLOP/s", "frac": achieved / dmma_peak,
+                        "flop_per_launch": f["ao2mo"] / 2.0, "launch_ms": seg["ao2mo"] / 2.0},
+           "roofline_hbm": {"bound": "hbm", "achieved": w.nx * nb * nb * 8 / (seg["dp"] * 1e-3) / 1e9, "peak": hbm_peak,
+                            "unit": "GB/s", "frac": w.nx * nb * nb * 8 / (seg["dp"] * 1e-3) / 1e9 / hbm_peak},
+           "allreduce_ms_each": allreduce_ms(env, nb * nb), "allreduce_bytes": nb * nb * 8,
+           "gpu_launches_per_step": launches / steps}
+    w.mo = None
+    env.torch.cuda.empty_cache()
+    ov_ms, ov_seg, _ = w.measure(steps, 1, False)
+    ovf = w.total_flop(False)
+    out["step_occ_vir"] = {"ms_per_step": ov_ms, "value": ovf / (ov_ms * 1e-3) / 1e9, "unit": UNIT,
+                           "frac_of_dmma_peak": ovf / (ov_ms * 1e-3) / 1e12 / (dmma_peak * env.world),
+                           "breakdown_ms_rank0": {kk: round(v, 4) for kk, v in ov_seg.items()},
+                           "breakdown_rate_rank0": rates(nb, w.nx, no, ov_seg, False)}
+    return out
+
+
+def consumers_leg(env, w):
+    """(ia|jb) blocks and the RPA-type contraction straight from this rank's occ-vir ri3mo (outside any timed region)"""
+    torch, ctx, sh = env.torch, env.ctx, w.sh
+    nb, nx, no = w.nb, w.nx, w.no
+    nv = nb - no
+    try:
+        if w.ov is None:
+            w.step(False)
+        ov = w.ov
+        li = max(1, min(no // 2 if no >= 2 else 1, int(((6 << 30) / 8) ** 0.5) // max(nv, 1)))
+        if (6 << 30) / 8 >= float(no * nv) ** 2:
+            li = no
+        m_blk = li * nv
+        g = ctx.empty(m_blk * m_blk)
+        res = {}
+        pairs = [("diag", (0, li, 0, nv), (0, li, 0, nv), float(m_blk) * (m_blk + 1) * nx)]
+        if 2 * li <= no:
+            pairs.append(("offdiag", (0, li, 0, nv), (li, li, 0, nv), 2.0 * m_blk * m_blk * nx))
+        for name, ba, bb, fl in pairs:
+            best = None
+            for it in range(3):
+                a0, a1 = env.ev(), env.ev()
+                a0.record(); sh.iajb(ov, no, nv, ba, bb, out=g, reduce=False); a1.record()
+                torch.cuda.synchronize()
+                if it:
+                    best = a0.elapsed_time(a1) if best is None else min(best, a0.elapsed_time(a1))
+            res[name] = {"ms": best, "tflops_per_gpu": fl / (best * 1e-3) / 1e12}
+        # RPA-type consumer on the same tensor: Pi[P,Q] = sum_ia w_ia R_ia^P R_ia^Q (upper triangle + mirror, np(np+1)K flop)
+        wts = ctx.empty(no * nv); ctx.fill_linear(wts, no * nv, 9, 0, 1.0)
+        pi = ctx.empty(nx * nx)
+        best = None
+        for it in range(3):
+            a0, a1 = env.ev(), env.ev()
+            a0.record(); ctx.ri_mo_pq(ov, nx, nx, ov, nx, nx, no, nv, (0, no, 0, nv), wts, 0.0, pi, nx); a1.record()
+            torch.cuda.synchronize()
+            if it:
+                best = a0.elapsed_time(a1) if best is None else min(best, a0.elapsed_time(a1))
+        res["mo_pq_weighted"] = {"ms": best, "tflops_per_gpu": float(nx) * (nx + 1) * no * nv / (best * 1e-3) / 1e12,
+                                 "m": nx, "k": no * nv}
+        return {"occ_block": li, "rows": m_blk, "k": nx, **res,
+                "note": "rb_ri_iajb on this rank's rows of the occ-vir ri3mo (partial sum; all-reduce not timed); best of 2"}
+    except Exception as exc:  # noqa: BLE001
+        return {"error": f"{type(exc).__name__}: {exc}"[:200]}
 
 
 def main():
@@ -546,9 +827,12 @@ def main():
     ap.add_argument("--config", default="C", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-numa", action="store_true", help="e2e leg: do not bind the rank to its GPU's NUMA node")
-    ap.add_argument("--no-extras", action="store_true", help="skip the untimed extras (occ-vir ao2mo, ri3mo consumers): "
-                    "the ncu launch list then holds the timed step's kernels only")
-    ap.add_argument("--no-e2e", action="store_true", help="skip the host-pointer e2e leg (e.g. config D: 2 x 15.5 GB pinned per rank)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra legs (occ-vir step, strong scaling, config D, "
+                    "small configs, ri3mo consumers): the ncu launch list then holds the timed step's kernels only")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-pointer e2e legs")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity leg")
+    ap.add_argument("--config-d-leg", action="store_true", help="run the config D leg at this N too (needs naux 4800 / N "
+                    "slabs of nb=1800 plus the square ri3mo per GPU: N >= 2)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -247,6 +247,34 @@ int rb_ri_mo_pq_peers(rb_ctx *ctx, int rank, int world, const double *const *pan
 int rb_special_dgemm_01_peers(rb_ctx *ctx, int rank, int world, const double *const *shards, int64_t xy, const int *np,
                               const int64_t *p_off, const double *b, int64_t ldb, double alpha, double beta, double *out);
 
+/* ---- collectives of the P-sharded path -----------------------------------------------------------------
+ * The reference has no communication layer; the partition is its iter_auxbas(P_lo..P_hi) (src/ri.rs:190-198) and the only
+ * exchanges are ONE all-reduce(sum, f64) each for J and K plus an all-gather of d_P.  They are NCCL calls (NVLink 5 /
+ * NVSwitch) on the context's stream.  NCCL is bound at run time: $REST_B200_NCCL_LIB, else a libnccl.so.2 the process
+ * already carries (PyTorch's), else the loader's search path; RB_ERR_UNSUPPORTED if none is found.
+ *   one process (or thread) per GPU : rank 0 calls rb_comm_unique_id and hands the 128 bytes to every rank by the host's
+ *                                     own means (pipe, file, MPI, a torch store); every rank calls rb_comm_init_rank.
+ *   one process, n contexts         : rb_comm_init_all; bracket each step's per-context collective calls with
+ *                                     rb_comm_group_start / rb_comm_group_end (NCCL group semantics).
+ * A context without a communicator is a world of one: the collectives are no-ops and the *_allreduce forms equal the
+ * plain ones.  rb_ctx_destroy destroys the communicator. */
+int rb_comm_nccl_version(int *version_out, char *path_out, int path_len);
+int rb_comm_unique_id(unsigned char id[128]);
+int rb_comm_init_rank(rb_ctx *ctx, int rank, int world, const unsigned char id[128]);
+int rb_comm_init_all(rb_ctx *const *ctxs, int n);
+int rb_comm_destroy(rb_ctx *ctx);
+int rb_comm_rank(rb_ctx *ctx);
+int rb_comm_world(rb_ctx *ctx);
+int rb_comm_group_start(void);
+int rb_comm_group_end(void);
+/* in-place sum over the ranks, asynchronous on the context's stream */
+int rb_allreduce_sum(rb_ctx *ctx, double *buf, int64_t n);
+/* full[0..naux) on every rank from the per-rank pieces local[floor(r*naux/G) .. floor((r+1)*naux/G)) (d_P) */
+int rb_allgather_shards(rb_ctx *ctx, const double *local, double *full, int64_t naux);
+/* rb_ri_j / rb_ri_k followed by the all-reduce: J and K complete on every rank */
+int rb_ri_j_allreduce(rb_ctx *ctx, const double *ri3ao, const double *d, double *j, int nb, int nx);
+int rb_ri_k_allreduce(rb_ctx *ctx, const double *ri3ao, const double *ct, int no, double *k, int nb, int nx);
+
 /* einsum helpers (matrix_blas_lapack.rs:1273-1387, matrix/einsum.rs) on device buffers:
  * "ij,j->ij" and "i,j->ij" are one multiply per element (bit-exact), "ip,ip->p" is a column dot (1e-10). */
 int rb_einsum_ij_j(rb_ctx *ctx, const double *a, int64_t lda, const double *b, double *out, int64_t ldo, int64_t ni,

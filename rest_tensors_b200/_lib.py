@@ -150,6 +150,20 @@ SIGNATURES = {
     "rb_pcie_probe": (C.c_int, [c_vp, C.c_int, c_i64, c_i64, C.c_int, c_dp]),
     "rb_bind_host_to_device_numa": (C.c_int, [C.c_int, c_ip]),
     "rb_host_trim": (C.c_int, []),
+    # collectives (NCCL bound at run time)
+    "rb_comm_nccl_version": (C.c_int, [c_ip, C.c_char_p, C.c_int]),
+    "rb_comm_unique_id": (C.c_int, [c_vp]),
+    "rb_comm_init_rank": (C.c_int, [c_vp, C.c_int, C.c_int, c_vp]),
+    "rb_comm_init_all": (C.c_int, [C.POINTER(c_vp), C.c_int]),
+    "rb_comm_destroy": (C.c_int, [c_vp]),
+    "rb_comm_rank": (C.c_int, [c_vp]),
+    "rb_comm_world": (C.c_int, [c_vp]),
+    "rb_comm_group_start": (C.c_int, []),
+    "rb_comm_group_end": (C.c_int, []),
+    "rb_allreduce_sum": (C.c_int, [c_vp, c_vp, c_i64]),
+    "rb_allgather_shards": (C.c_int, [c_vp, c_vp, c_vp, c_i64]),
+    "rb_ri_j_allreduce": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int]),
+    "rb_ri_k_allreduce": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, c_vp, C.c_int, C.c_int]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

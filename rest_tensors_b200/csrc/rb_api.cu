@@ -69,6 +69,7 @@ extern "C" int rb_ctx_destroy(rb_ctx *ctx)
     if (!ctx) return RB_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    rb_comm_destroy(ctx);
     rb_eig_cache_free(ctx);
     for (int s = 0; s < 4; ++s) if (ctx->ws[s]) cudaFree(ctx->ws[s]);
     if (ctx->sched) cudaFree(ctx->sched);

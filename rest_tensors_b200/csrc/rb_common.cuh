@@ -60,6 +60,8 @@ struct rb_ctx {
     void *eig_cache = nullptr;           // instantiated Jacobi sweep graphs (rb_eig.cu), freed by rb_eig_cache_free
     unsigned long long *sched = nullptr; // GEMM tile-scheduler slots (64 x 2 words on the device), zero between launches
     unsigned sched_next = 0;             // slot of the next GEMM launch (round-robin)
+    void *comm = nullptr;                // NCCL communicator (rb_comm.cu), NULL = a world of one
+    int comm_rank = 0, comm_world = 1;
 };
 
 // Grow-only device workspace (synchronises the stream before freeing the old block).

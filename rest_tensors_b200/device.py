@@ -7,7 +7,10 @@ called through the C ABI with raw device pointers.
 Sharding: the auxiliary index P is the slowest index of ri3ao[nb, nb, naux], so rank r of G owns the
 contiguous block P in [floor(r*naux/G), floor((r+1)*naux/G)) -- exactly the reference's ``iter_auxbas(range)``
 (src/ri.rs:190-198).  ao2mo and d_P need no communication; J and K are partial sums over the local slabs and
-are completed by ONE all-reduce(sum, f64) each over NVLink (torch.distributed, backend nccl; gloo on CPU tests).
+are completed by ONE all-reduce(sum, f64) each over NVLink.  The collectives live behind the C ABI (rb_comm_* /
+rb_allreduce_sum / rb_ri_j_allreduce / rb_ri_k_allreduce: NCCL bound by librest_b200 itself, on the context's stream), so
+a Rust host gets the same multi-GPU path; torch.distributed only carries the 128-byte NCCL unique id and the host barriers
+here.  CPU tensors (the gloo host-logic tests) go through torch.distributed.
 """
 from __future__ import annotations
 
@@ -77,6 +80,48 @@ class Context:
 
     def set_gemm_path(self, path: int) -> None:
         check(lib.rb_ctx_set_gemm_path(self.h, path), "rb_ctx_set_gemm_path")
+
+    # -- collectives (NCCL inside librest_b200) --
+    @property
+    def comm_world(self) -> int:
+        return int(lib.rb_comm_world(self.h))
+
+    @property
+    def comm_rank(self) -> int:
+        return int(lib.rb_comm_rank(self.h))
+
+    def comm_init(self, rank: int, world: int) -> None:
+        """Give this context a communicator over `world` ranks (one process per GPU).  Rank 0 draws the NCCL unique id
+        inside the library; the 128 bytes reach the other ranks through the torch.distributed process group (any
+        out-of-band channel would do: a Rust host uses a file or a pipe)."""
+        if world <= 1 or self.comm_world == world:
+            return
+        import torch.distributed as dist
+        ident = (C.c_ubyte * 128)()
+        if rank == 0:
+            check(lib.rb_comm_unique_id(ident), "rb_comm_unique_id")
+        box = [bytes(ident)]
+        dist.broadcast_object_list(box, src=0)
+        ident = (C.c_ubyte * 128).from_buffer_copy(box[0])
+        check(lib.rb_comm_init_rank(self.h, rank, world, ident), "rb_comm_init_rank")
+
+    def comm_destroy(self) -> None:
+        check(lib.rb_comm_destroy(self.h), "rb_comm_destroy")
+
+    def allreduce_sum(self, t: torch.Tensor) -> None:
+        check(lib.rb_allreduce_sum(self.h, _p(t), t.numel()), "rb_allreduce_sum")
+
+    def allgather_shards(self, local: torch.Tensor, naux: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if out is None:
+            out = self.empty(naux)
+        check(lib.rb_allgather_shards(self.h, _p(local), _p(out), naux), "rb_allgather_shards")
+        return out
+
+    def nccl_version(self):
+        v = C.c_int(0)
+        path = C.create_string_buffer(256)
+        check(lib.rb_comm_nccl_version(C.byref(v), path, 256), "rb_comm_nccl_version")
+        return int(v.value), path.value.decode()
 
     # -- BLAS --
     def dgemm(self, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc) -> None:
@@ -203,7 +248,9 @@ class ShardedRI:
     """One rank's P-shard of ri3ao[nb, nb, naux], resident in HBM across calls (the SCF loop re-uses it)."""
 
     def __init__(self, ctx: Context, nb: int, naux: int, rank: int = 0, world: int = 1,
-                 data: Optional[torch.Tensor] = None):
+                 data: Optional[torch.Tensor] = None, comm: bool = True):
+        """comm=False: do not set up a communicator here (a single process that drives several contexts calls
+        rb_comm_init_all itself and brackets the collectives with rb_comm_group_start / _end)"""
         self.ctx, self.nb, self.naux, self.rank, self.world = ctx, int(nb), int(naux), int(rank), int(world)
         self.p_lo, self.p_hi = shard_range(self.naux, self.rank, self.world)
         self.nx = self.p_hi - self.p_lo
@@ -213,6 +260,8 @@ class ShardedRI:
         elif data.numel() < n:
             raise ValueError("ShardedRI: buffer smaller than the local shard")
         self.data = data
+        if comm and ctx is not None and self.world > 1 and data.is_cuda:
+            ctx.comm_init(self.rank, self.world)
 
     def fill_synthetic(self, seed: int = 1, scale: float = 1.0) -> "ShardedRI":
         self.ctx.fill_ri3ao_symm(self.data, self.nb, self.p_lo, self.p_hi, seed, scale)
@@ -238,18 +287,24 @@ class ShardedRI:
     def j(self, d_local: torch.Tensor, out: Optional[torch.Tensor] = None, reduce: bool = True) -> torch.Tensor:
         if out is None:
             out = self.ctx.empty(self.nb * self.nb)
-        self.ctx.ri_j(self.data, d_local, out, self.nb, self.nx)
-        if reduce:
-            all_reduce_sum(out, self.world)
+        if reduce and self.world > 1:   # partial sum + NCCL all-reduce on the same stream, one C-ABI call
+            check(lib.rb_ri_j_allreduce(self.ctx.h, _p(self.data), _p(d_local), _p(out), self.nb, self.nx), "rb_ri_j_allreduce")
+        else:
+            self.ctx.ri_j(self.data, d_local, out, self.nb, self.nx)
         return out
 
     def k(self, ct: torch.Tensor, no: int, out: Optional[torch.Tensor] = None, reduce: bool = True) -> torch.Tensor:
         if out is None:
             out = self.ctx.empty(self.nb * self.nb)
-        self.ctx.ri_k(self.data, ct, no, out, self.nb, self.nx)
-        if reduce:
-            all_reduce_sum(out, self.world)
+        if reduce and self.world > 1:
+            check(lib.rb_ri_k_allreduce(self.ctx.h, _p(self.data), _p(ct), no, _p(out), self.nb, self.nx), "rb_ri_k_allreduce")
+        else:
+            self.ctx.ri_k(self.data, ct, no, out, self.nb, self.nx)
         return out
+
+    def gather_dp(self, d_local: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """full d[0..naux) on every rank (rb_allgather_shards)"""
+        return self.ctx.allgather_shards(d_local, self.naux, out)
 
     def iajb(self, mo: torch.Tensor, nl: int, nr: int, box_a, box_b, mo_b: Optional[torch.Tensor] = None,
              nl_b: Optional[int] = None, nr_b: Optional[int] = None, out: Optional[torch.Tensor] = None,
@@ -263,7 +318,7 @@ class ShardedRI:
             out = self.ctx.empty(m * n)
         self.ctx.ri_iajb(self.nx, mo, self.nx, nl, nr, box_a, mo_b, self.nx, nl_b, nr_b, box_b, 0.0, out, m)
         if reduce:
-            all_reduce_sum(out, self.world)
+            all_reduce_sum(out, self.world, self.ctx)
         return out
 
     def mo_pq(self, mo: torch.Tensor, nl: int, nr: int, box, w: Optional[torch.Tensor] = None,
@@ -426,16 +481,25 @@ class PeerBlocks(PeerViews):
         self.local = 0
 
 
-def all_reduce_sum(t: torch.Tensor, world: int) -> None:
-    """The only collective on the path: sum of the per-rank J / K partials (NCCL over NVLink on GPUs)."""
-    if world > 1:
-        import torch.distributed as dist
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+def all_reduce_sum(t: torch.Tensor, world: int, ctx: Optional[Context] = None) -> None:
+    """The only collective on the path: sum of the per-rank J / K partials.  Device tensors with a context that holds a
+    communicator: rb_allreduce_sum (NCCL inside librest_b200, on the context's stream).  CPU tensors (gloo host-logic
+    tier) or no context: torch.distributed."""
+    if world <= 1:
+        return
+    if ctx is not None and t.is_cuda and ctx.comm_world == world:
+        ctx.allreduce_sum(t)
+        return
+    import torch.distributed as dist
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
 
 
-def gather_dp(d_local: torch.Tensor, naux: int, p_lo: int, world: int) -> torch.Tensor:
-    """Full d[0..naux) on every rank (38 KB at naux=4800): each rank drops its piece into a zero vector and the
-    pieces are summed -- shards may differ in length by one, which all_gather does not accept on every backend."""
+def gather_dp(d_local: torch.Tensor, naux: int, p_lo: int, world: int, ctx: Optional[Context] = None) -> torch.Tensor:
+    """Full d[0..naux) on every rank (38 KB at naux=4800).  With a communicator: rb_allgather_shards.  Otherwise each rank
+    drops its piece into a zero vector and the pieces are summed -- shards may differ in length by one, which all_gather
+    does not accept on every backend."""
+    if ctx is not None and d_local.is_cuda and ctx.comm_world == world and world > 1:
+        return ctx.allgather_shards(d_local, naux)
     full = torch.zeros(int(naux), dtype=d_local.dtype, device=d_local.device)
     full[p_lo:p_lo + d_local.numel()] = d_local
     all_reduce_sum(full, world)

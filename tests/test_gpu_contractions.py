@@ -545,6 +545,39 @@ def test_config_c_full_size_parity_vs_oracle(ctx, oracle_blas):
     assert_close_1e10(sh.k(_dev(ctx, ct), no, reduce=False).cpu().numpy(), oracle_blas.ri_k(ri, ct, nb, no, nx), "config C K")
 
 
+def test_config_d_shapes_subset_parity_vs_oracle(ctx, oracle_blas):
+    """Config D's shapes (nb=1800, nocc=180) against the oracle on a subset of the north-star shard: per-slab work is
+    independent, so slabs [1234, 1234+12) of the naux=4800 tensor exercise the same tiles / chunk pitches as the full
+    600-slab shard (18 ragged k8 blocks, 15 tile columns, N = nocc = 180).  Square and occ-vir ao2mo, d_P, J, K: 1e-10."""
+    import os
+    from rest_tensors_b200.device import ShardedRI
+    nb, no, p_lo, ns = 1800, 180, 1234, 12
+    oracle_blas.set_threads(len(os.sched_getaffinity(0)))
+    ri = oracle_blas.fill_ri3ao_symm(nb, p_lo, p_lo + ns)
+    c = oracle_blas.fill_linear(nb * nb, 3, scale=nb ** -0.5)
+    cm = c.reshape((nb, nb), order="F")
+    dm = np.ascontiguousarray((2.0 * cm[:, :no] @ cm[:, :no].T).reshape(-1, order="F"))
+    ct = np.ascontiguousarray((cm[:, :no] * np.sqrt(2.0)).reshape(-1, order="F"))
+    sh = ShardedRI(ctx, nb, ns)
+    ctx.fill_ri3ao_symm(sh.data, nb, p_lo, p_lo + ns, 1, 1.0)
+    assert np.array_equal(sh.data.cpu().numpy(), ri), "device generator != oracle generator at config D offsets"
+    cd = _dev(ctx, c)
+    got = sh.ao2mo(cd, nb, cd, nb).cpu().numpy()
+    ref = oracle_blas.ri_ao2mo_f(c, ri, nb, nb, ns)
+    assert_close_1e10(got, ref, "config D shapes: square ao2mo")
+    nv = nb - no
+    ov = sh.ao2mo(cd[: nb * no], no, cd[nb * no:], nv).cpu().numpy()
+    ov_ref = oracle_blas.ri_ao2mo_rect(np.ascontiguousarray(c[: nb * no]), no, np.ascontiguousarray(c[nb * no:]), nv, ri, nb, ns)
+    assert_close_1e10(ov, ov_ref, "config D shapes: occ-vir ao2mo")
+    # the occ-vir block is the [occ, vir] sub-block of the square transform
+    assert_close_1e10(ov, ref.reshape((ns, nb, nb), order="F")[:, :no, no:].reshape(-1, order="F"), "occ-vir vs square block")
+    d_ref = oracle_blas.ri_dp(ri, dm, nb, ns)
+    d = sh.dp(_dev(ctx, dm))
+    assert_close_1e10(d.cpu().numpy(), d_ref, "config D shapes: d_P")
+    assert_close_1e10(sh.j(d, reduce=False).cpu().numpy(), oracle_blas.ri_j(ri, d_ref, nb, ns), "config D shapes: J")
+    assert_close_1e10(sh.k(_dev(ctx, ct), no, reduce=False).cpu().numpy(), oracle_blas.ri_k(ri, ct, nb, no, ns), "config D shapes: K")
+
+
 # ---------------------------------------------------------------- d_P, J, K ----
 @pytest.mark.parametrize("nb,nx,no,symm", [(10, 20, 3, True), (100, 400, 20, True), (37, 11, 5, False), (64, 300, 64, False),
                                            (264, 720, 21, True)])

@@ -1,5 +1,7 @@
 """Multi-GPU parity (needs >= 2 GPUs; skipped otherwise): each rank holds its P-shard of a synthetic ri3ao in HBM, runs
-the CUDA kernels on it, and ONE NCCL all-reduce(sum) each completes J and K.  Checked against the unsharded CPU oracle."""
+the CUDA kernels on it, and ONE all-reduce(sum) each completes J and K -- through the C ABI's own collectives
+(rb_comm_init_rank / rb_ri_j_allreduce / rb_ri_k_allreduce / rb_allgather_shards: NCCL bound inside librest_b200).
+Checked against the unsharded CPU oracle."""
 import os
 import sys
 
@@ -35,7 +37,11 @@ def _worker(rank, world, port, nb, naux, no, ret):
         j = sh.j(d_local)                  # partial + all-reduce
         k = sh.k(dev(ct), no)              # partial + all-reduce
         mo_local = sh.ao2mo(cd, nb, cd, nb)
-        d_full = gather_dp(d_local, naux, sh.p_lo, world)
+        assert ctx.comm_world == world and ctx.comm_rank == rank      # the communicator lives inside librest_b200
+        d_full = gather_dp(d_local, naux, sh.p_lo, world, ctx)        # rb_allgather_shards
+        assert torch.equal(d_full, sh.gather_dp(d_local))
+        j2 = sh.j(d_local, reduce=False); ctx.allreduce_sum(j2)       # partial + explicit rb_allreduce_sum == fused call
+        assert torch.equal(j, j2)
         # consumers of ri3mo: (ia|jb) block (partial + all-reduce) and the RPA-type block row (all-gather of row blocks)
         box_a, box_b = (0, no, no, nb - no), (1, no - 1, no, nb - no)
         g = sh.iajb(mo_local, nb, nb, box_a, box_b)
@@ -146,3 +152,52 @@ def test_one_process_peer_operand():
         c0.dgemm("N", "T", m, n, k, 1.0, a, m, b_remote, n, 0.0, o2, m)
         torch.cuda.synchronize(0)
         assert torch.equal(o1, o2)
+
+
+def test_one_process_comm_init_all():
+    """rb_comm_init_all: ONE host process drives two contexts (what a Rust host with a context per GPU does); the J
+    partials of the two P-shards are completed by rb_allreduce_sum inside rb_comm_group_start / _end."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sys.path.insert(0, ROOT)
+    import ctypes as C
+    from oracle.api import Oracle
+    from rest_tensors_b200.device import Context, ShardedRI
+    from rest_tensors_b200._lib import lib, check
+    o = Oracle(); o.load_openblas()
+    nb, naux, no = 48, 70, 5
+    ctxs = [Context(0), Context(1)]
+    hs = (C.c_void_p * 2)(ctxs[0].h, ctxs[1].h)
+    check(lib.rb_comm_init_all(hs, 2), "rb_comm_init_all")
+    assert [c.comm_world for c in ctxs] == [2, 2] and [c.comm_rank for c in ctxs] == [0, 1]
+    c = o.fill_linear(nb * nb, 3, scale=nb ** -0.5)
+    cm = c.reshape((nb, nb), order="F")
+    dm = np.ascontiguousarray((2.0 * cm[:, :no] @ cm[:, :no].T).reshape(-1, order="F"))
+    js, ds = [], []
+    for r in range(2):
+        with torch.cuda.device(r):
+            ctxs[r].bind_stream()
+            sh = ShardedRI(ctxs[r], nb, naux, r, 2, comm=False).fill_synthetic()   # no torch.distributed anywhere
+            d = sh.dp(torch.from_numpy(dm).to(f"cuda:{r}"))
+            js.append(sh.j(d, reduce=False)); ds.append(d[: sh.nx])
+    check(lib.rb_comm_group_start(), "rb_comm_group_start")
+    for r in range(2):
+        ctxs[r].allreduce_sum(js[r])
+    check(lib.rb_comm_group_end(), "rb_comm_group_end")
+    fulls = [ctxs[r].empty(naux) for r in range(2)]
+    check(lib.rb_comm_group_start(), "rb_comm_group_start")
+    for r in range(2):
+        with torch.cuda.device(r):
+            ctxs[r].allgather_shards(ds[r], naux, fulls[r])
+    check(lib.rb_comm_group_end(), "rb_comm_group_end")
+    for r in range(2):
+        torch.cuda.synchronize(r)
+    ri = o.fill_ri3ao_symm(nb, 0, naux)
+    d_ref = o.ri_dp(ri, dm, nb, naux)
+    j_ref = o.ri_j(ri, d_ref, nb, naux)
+    for r in range(2):
+        assert float(np.max(np.abs(js[r].cpu().numpy() - j_ref)) / np.max(np.abs(j_ref))) <= 1e-10
+        assert float(np.max(np.abs(fulls[r].cpu().numpy() - d_ref)) / np.max(np.abs(d_ref))) <= 1e-10
+    assert torch.equal(js[0].cpu(), js[1].cpu())
+    for c_ in ctxs:
+        c_.comm_destroy()

@@ -86,6 +86,25 @@ def test_ao2mo_two_restatements_agree(oracle, oracle_blas):
     assert np.array_equal(oracle.ri_ao2mo_rect(c, nb, c, nb, ri, nb, nx), a)
 
 
+def test_ao2mo_against_einsum(oracle, oracle_blas):
+    """Third, independent statement of ri_ao2mo_f (restmatr.f90:158-194): ri3mo[P,a,b] = sum_mu,nu C[mu,a] A[mu,nu,P] C[nu,b]
+    written as ONE numpy.einsum -- no slab loop, no dgemm call order, no scatter.  Both oracle builds (netlib-style loops
+    and OpenBLAS) and the rectangular generalisation must agree with it; symmetric and non-symmetric slabs."""
+    for nb, nx, symm in [(17, 6, True), (23, 7, False), (40, 3, True)]:
+        ri = oracle.fill_ri3ao_symm(nb, 0, nx) if symm else oracle.fill_linear(nb * nb * nx, 2)
+        c = oracle.fill_linear(nb * nb, 3, scale=nb ** -0.5)
+        A = ri.reshape((nb, nb, nx), order="F")
+        Cm = c.reshape((nb, nb), order="F")
+        ref = np.einsum("ma,mnp,nb->pab", Cm, A, Cm, optimize=False).reshape(-1, order="F")
+        assert_close_1e10(oracle.ri_ao2mo_f(c, ri, nb, nb, nx), ref, "ri_ao2mo_f vs einsum")
+        assert_close_1e10(oracle_blas.ri_ao2mo_f(c, ri, nb, nb, nx), ref, "ri_ao2mo_f(OpenBLAS) vs einsum")
+        assert_close_1e10(oracle.ao2mo_v01(c, ri, nb, nb, nx), ref, "ao2mo_v01 vs einsum")
+        no = 5
+        cl, cr = np.ascontiguousarray(c[: nb * no]), np.ascontiguousarray(c[nb * no:])
+        ref_ov = np.einsum("ma,mnp,nb->pab", Cm[:, :no], A, Cm[:, no:], optimize=False).reshape(-1, order="F")
+        assert_close_1e10(oracle_blas.ri_ao2mo_rect(cl, no, cr, nb - no, ri, nb, nx), ref_ov, "ri_ao2mo_rect vs einsum")
+
+
 def test_jk_against_einsum(oracle):
     nb, nx, no = 11, 5, 3
     ri = oracle.fill_ri3ao_symm(nb, 0, nx)
