@@ -122,6 +122,7 @@ int rb_ws_reserve(rb_ctx *ctx, int slot, i64 bytes, void **out)
         if (e != cudaSuccess) {
             cudaGetLastError();
             rb_set_error("workspace allocation of %lld bytes failed: %s", (long long)bytes, cudaGetErrorString(e));
+            ctx->ws_budget = 0; // the cached budget is stale (the application took HBM since): re-query on the next plan
             return RB_ERR_NOMEM;
         }
         ctx->ws_bytes[slot] = bytes;

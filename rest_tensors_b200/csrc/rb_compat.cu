@@ -333,6 +333,10 @@ struct Pipe {
     cudaEvent_t in_done[2] = {nullptr, nullptr}, comp_done[2] = {nullptr, nullptr}, out_done[2] = {nullptr, nullptr};
     ~Pipe()
     {
+        // an early return (e.g. a failed workspace allocation mid-pipeline) may leave copies in flight on the side streams
+        // that read / write the stage and pinned blocks HostOp is about to hand back: drain them first
+        if (s_in) cudaStreamSynchronize(s_in);
+        if (s_out) cudaStreamSynchronize(s_out);
         for (int i = 0; i < 2; ++i) {
             if (in_done[i]) cudaEventDestroy(in_done[i]);
             if (comp_done[i]) cudaEventDestroy(comp_done[i]);

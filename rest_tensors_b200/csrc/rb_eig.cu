@@ -26,7 +26,7 @@
 namespace {
 
 constexpr int EIG_THREADS = 256;
-constexpr int EIG_CACHE_MAX_N = 3072; // both columns of a pair cached in 48 KB of shared memory up to this n
+constexpr int EIG_CACHE_MAX_N = 3060; // both columns of a pair (2 n doubles) + 192 B of static reduction scratch within the 48 KB non-opt-in limit
 constexpr int EIG_MAX_SWEEPS = 60;
 
 // g = symmetric expansion of one triangle of a (+ shift on the diagonal); v = identity (if v != NULL)
@@ -450,10 +450,11 @@ i64 eig_work_elems(i64 n) { return 3 * n * n + 3 * n + 8; }
 // rotations (accurate small eigenvalues of positive semi-definite input); else Gershgorin shift and normalised columns.
 // lam_host[n] ascending; z (device, ldz) receives the first ncols eigenvectors (NULL: none).  Synchronises the stream.
 int jacobi_eig(rb_ctx *ctx, i64 n, const double *s, bool psd, double *work, std::vector<double> &lam_host, double *z, i64 ldz,
-               i64 ncols, int *sweeps_out)
+               i64 ncols, int *sweeps_out, bool *psd_ok = nullptr)
 {
     lam_host.assign((size_t)n, 0.0);
     if (sweeps_out) *sweeps_out = 0;
+    if (psd_ok) *psd_ok = true;
     if (n == 0) return RB_OK;
     double *g = work, *v = g + n * n, *w = v + n * n, *lam = w + n * n, *stat = lam + n;
     i64 *perm = (i64 *)(stat + n);
@@ -531,12 +532,23 @@ int jacobi_eig(rb_ctx *ctx, i64 n, const double *s, bool psd, double *work, std:
     }
     RB_CUDA(cudaStreamSynchronize(ctx->stream));
     if (psd) {
-        double lo = 0.0, hi = 0.0;
-        for (double x : host) { lo = std::min(lo, x); hi = std::max(hi, std::fabs(x)); }
-        if (!(lo < -1e-10 * hi)) { // genuinely semi-definite (else the caller repeats the solve with the shift)
-            RB_CUDA(cudaMemcpyAsync(host.data(), stat, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
-            RB_CUDA(cudaStreamSynchronize(ctx->stream));
+        // Unshifted one-sided Jacobi diagonalises S^2: it only sees |lambda|, and the eigenvectors of +s / -s pairs may stay
+        // mixed (e.g. [[0,1],[1,0]]: the columns are orthogonal from the start).  The converged columns are accepted as
+        // eigenpairs of a semi-definite S only if EVERY Rayleigh quotient v_i^T S v_i agrees with its column norm |g_i|
+        // to rounding (both are lambda_i >= 0 then; a mixed or negative pair gives a quotient below its norm).  Otherwise
+        // the caller repeats the solve with the shift, which is valid for any symmetric matrix.
+        std::vector<double> norms((size_t)n);
+        RB_CUDA(cudaMemcpyAsync(norms.data(), stat, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        RB_CUDA(cudaStreamSynchronize(ctx->stream));
+        double hi = 0.0, mismatch = 0.0;
+        for (i64 i = 0; i < n; ++i) {
+            hi = std::max(hi, norms[(size_t)i]);
+            mismatch = std::max(mismatch, std::fabs(host[(size_t)i] - norms[(size_t)i]));
         }
+        const bool ok = mismatch <= 64.0 * (double)n * 2.220446049250313e-16 * hi;
+        if (psd_ok) *psd_ok = ok;
+        if (!ok) return RB_OK; // lam_host / z are not valid; see psd_ok
+        host = norms;          // |g_i| carries the relative accuracy of small eigenvalues
     }
     std::vector<i64> order((size_t)n);
     std::iota(order.begin(), order.end(), (i64)0);
@@ -551,14 +563,13 @@ int jacobi_eig(rb_ctx *ctx, i64 n, const double *s, bool psd, double *work, std:
     return RB_OK;
 }
 
-// positive semi-definite path with a fallback: if the Rayleigh quotients reveal an indefinite matrix, one-sided Jacobi
-// without a shift only sees |lambda|, so the solve is repeated with the shift
+// positive semi-definite path with a fallback: if the Rayleigh quotients do not confirm the column norms as eigenvalues
+// (indefinite input), the solve is repeated with the shift
 int jacobi_eig_psd(rb_ctx *ctx, i64 n, const double *s, double *work, std::vector<double> &lam, double *z, i64 ldz, i64 ncols)
 {
-    RB_TRY(jacobi_eig(ctx, n, s, true, work, lam, z, ldz, ncols, nullptr));
-    double lo = 0.0, hi = 0.0;
-    for (double x : lam) { lo = std::min(lo, x); hi = std::max(hi, std::fabs(x)); }
-    if (lo < -1e-10 * hi) RB_TRY(jacobi_eig(ctx, n, s, false, work, lam, z, ldz, ncols, nullptr));
+    bool ok = true;
+    RB_TRY(jacobi_eig(ctx, n, s, true, work, lam, z, ldz, ncols, nullptr, &ok));
+    if (!ok) RB_TRY(jacobi_eig(ctx, n, s, false, work, lam, z, ldz, ncols, nullptr));
     return RB_OK;
 }
 
@@ -624,7 +635,9 @@ extern "C" int rb_dspgv(rb_ctx *ctx, int n_, const double *ap, const double *bp,
     // B = U D U^T (positive definite); Us = U D^-1/2 makes Us^T B Us = I
     std::vector<double> d;
     RB_TRY(jacobi_eig_psd(ctx, n, b, work, d, us, n, n));
-    RB_REQUIRE(d[0] > 0.0, "rb_dspgv: the overlap matrix is not positive definite (smallest eigenvalue %.3e)", d[0]);
+    // positive definite to working precision (what the reference's LAPACK Cholesky inside dspgvx demands; it panics otherwise)
+    RB_REQUIRE(d[0] > 0.0 && d[0] > (double)n * 2.220446049250313e-16 * d[(size_t)n - 1],
+               "rb_dspgv: the overlap matrix is not positive definite (eigenvalues %.3e .. %.3e)", d[0], d[(size_t)n - 1]);
     std::vector<double> sc((size_t)n);
     for (i64 i = 0; i < n; ++i) sc[(size_t)i] = 1.0 / std::sqrt(d[(size_t)i]);
     RB_CUDA(cudaMemcpyAsync(scale, sc.data(), (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));

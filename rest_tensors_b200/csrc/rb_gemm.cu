@@ -41,6 +41,12 @@
 // that a second kernel reduces in a fixed order (deterministic, no FP64 atomics; the dynamic scheduler only changes
 // WHICH CTA computes a tile, never how).
 //
+// Diagonal tiles of a triangular product (SYRK and friends) are worked on as a LIST of 16 x 16 blocks: the 36 blocks on or
+// above the diagonal of the 8 x 8 block grid are dealt round-robin to the 8 warps (5 or 4 each, 9 per SM sub-partition),
+// so a diagonal tile costs 5/8 of a full tile instead of 8/8 for 36/64 of its work; when both operands are the same
+// matrix only one operand tile is loaded.  Batched products whose M is not a multiple of 128 pack their 16-row blocks
+// across batches ("packed M", see GemmParams).
+//
 // A second, generic kernel (plain loads, any alignment / leading dimension) covers operands TMA cannot describe.
 #include "rb_common.cuh"
 
@@ -73,6 +79,12 @@ struct GemmParams {
     i64 ldp;
     int a_batched, b_batched; // 0 => operand shared by all batches (TMA batch coordinate 0)
     unsigned long long *sched; // [0] next work item - gridDim.x, [1] CTAs done (both 0 between launches)
+    // packed M (batched, A MN-major, B shared by all batches): the M index runs over 16-row blocks of (batch, row block),
+    // 8 consecutive blocks make a tile, so a tile may straddle batches and only the last block of a batch is ragged
+    // (m = 600: 38 blocks per batch instead of 5 tiles = 40; m = 264: 17 instead of 24).
+    int pack_m;
+    i64 bpb, total_blocks;     // 16-row blocks per batch, batch * bpb
+    int same_ab;               // tri != 0 and A, B are the same matrix: diagonal tiles load one operand tile only
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------
@@ -202,6 +214,73 @@ __device__ __forceinline__ void consume_kb(double (&acc)[2][2][4][2][2], uint32_
                     for (int pb = 0; pb < 2; ++pb) dmma(acc[i][pa][j][pb], bf[j][pb][q], af[i][pa][q]); // D[n][m]: see header
 }
 
+// One k8 block for ONE 16 x 16 block of a warp's block list (diagonal tiles): accumulators live in slot S of the same
+// register array (block S <-> acc[S >> 2][.][S & 3][.]).  sa_blk / sb_blk already include the block's offset.
+template <bool A_K, bool B_K, int S>
+__device__ __forceinline__ void consume_list_block(double (&acc)[2][2][4][2][2], uint32_t sa_blk, uint32_t sb_blk,
+                                                   const uint32_t (&a_off)[2], const uint32_t (&b_off)[2], int kb)
+{
+    double af[2][2], bf[2][2]; // [tile e/o][mma 0/1]
+    if (A_K) {
+#pragma unroll
+        for (int pa = 0; pa < 2; ++pa) { double2 v = lds128(sa_blk + kb * (BM * 64) + a_off[pa]); af[pa][0] = v.x; af[pa][1] = v.y; }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) { double2 v = lds128(sa_blk + kb * (8 * 128) + a_off[q]); af[0][q] = v.x; af[1][q] = v.y; }
+    }
+    if (B_K) {
+#pragma unroll
+        for (int pb = 0; pb < 2; ++pb) { double2 v = lds128(sb_blk + kb * (BN * 64) + b_off[pb]); bf[pb][0] = v.x; bf[pb][1] = v.y; }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) { double2 v = lds128(sb_blk + kb * (8 * 128) + b_off[q]); bf[0][q] = v.x; bf[1][q] = v.y; }
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int pa = 0; pa < 2; ++pa)
+#pragma unroll
+            for (int pb = 0; pb < 2; ++pb) dmma(acc[S >> 2][pa][S & 3][pb], bf[pb][q], af[pa][q]);
+}
+
+template <bool A_K, bool B_K, int NB>
+__device__ __forceinline__ void consume_list_kb(double (&acc)[2][2][4][2][2], uint32_t sa, uint32_t sb, const uint32_t (&la)[5],
+                                                const uint32_t (&lb)[5], const uint32_t (&a_off)[2], const uint32_t (&b_off)[2],
+                                                int kb)
+{
+    consume_list_block<A_K, B_K, 0>(acc, sa + la[0], sb + lb[0], a_off, b_off, kb);
+    if (NB > 1) consume_list_block<A_K, B_K, 1>(acc, sa + la[1], sb + lb[1], a_off, b_off, kb);
+    if (NB > 2) consume_list_block<A_K, B_K, 2>(acc, sa + la[2], sb + lb[2], a_off, b_off, kb);
+    if (NB > 3) consume_list_block<A_K, B_K, 3>(acc, sa + la[3], sb + lb[3], a_off, b_off, kb);
+    if (NB > 4) consume_list_block<A_K, B_K, 4>(acc, sa + la[4], sb + lb[4], a_off, b_off, kb);
+}
+
+// k loop of a diagonal tile for a warp that owns NB (0..5) blocks of the tile's triangle.  b_from_a: both operands are
+// the same matrix and only the A tile was loaded; the column-block fragments are read from it.
+template <bool A_K, bool B_K, int NB>
+__device__ __forceinline__ void run_tile_list(double (&acc)[2][2][4][2][2], uint32_t smem_base, uint32_t bar_base, int &stage,
+                                              uint32_t &phase, const uint32_t (&la)[5], const uint32_t (&lb)[5],
+                                              const uint32_t (&a_off)[2], const uint32_t (&b_off)[2], int full_steps, int tail_kb,
+                                              int lane, bool b_from_a)
+{
+    for (int ks = 0; ks < full_steps + (tail_kb > 0 ? 1 : 0); ++ks) {
+        mbar_wait(bar_base + 8 * stage, phase);
+        if (NB > 0) {
+            const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = b_from_a ? sa : sa + A_TILE_BYTES;
+            if (ks < full_steps) {
+#pragma unroll
+                for (int kb = 0; kb < BK / 8; ++kb) consume_list_kb<A_K, B_K, (NB > 0 ? NB : 1)>(acc, sa, sb, la, lb, a_off, b_off, kb);
+            } else {
+#pragma unroll 1
+                for (int kb = 0; kb < tail_kb; ++kb) consume_list_kb<A_K, B_K, (NB > 0 ? NB : 1)>(acc, sa, sb, la, lb, a_off, b_off, kb);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_base + 8 * (STAGES + stage));
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+    }
+}
+
 // The whole k loop of one tile for a warp with NI x NJ blocks: `full_steps` 32-deep stages (fully unrolled body) and
 // one last stage of which only `tail_kb` k8 blocks hold data (K is consumed at k8 granularity, not padded to 32).
 // The (NI, NJ) dispatch sits outside this loop, so the hot loop has no per-stage branching.  NI == 0: the warp has
@@ -235,36 +314,69 @@ __device__ __forceinline__ void run_tile(double (&acc)[2][2][4][2][2], uint32_t 
     }
 }
 
-// Interior-tile epilogue of one warp.  pbase points at (row_t, col_t) of the warp's rectangle; a thread owns two
-// (A_K) or, across the e/o tiles, four (!A_K) consecutive rows of a column -> 16-byte stores.
+// Epilogue of one 16-row block of a warp (NJ column blocks), every element inside the matrix: pblk points at
+// (first row of the block + row_t, first column of the warp's rectangle + col_t); a thread owns two (A_K) or, across the
+// e/o tiles, four (!A_K) consecutive rows of a column -> 16-byte stores, no tests.
 template <bool A_K, bool B_K, bool SCALE>
-__device__ __forceinline__ void store_lean(const double (&acc)[2][2][4][2][2], double *pbase, i64 ldc, double alpha, int ni,
-                                           int nj)
+__device__ __forceinline__ void store_lean_row(const double (&acc)[2][2][4][2][2], const int i, double *pblk, i64 ldc,
+                                               double alpha, int nj)
 {
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        if (i >= ni) continue;
+    for (int j = 0; j < 4; ++j) {
+        if (j >= nj) continue;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (j >= nj) continue;
+        for (int pb = 0; pb < 2; ++pb) {
+            double *pc = pblk + (i64)(j * 16 + (B_K ? 8 * pb : pb)) * ldc;
 #pragma unroll
-            for (int pb = 0; pb < 2; ++pb) {
-                double *pc = pbase + i * 16 + (i64)(j * 16 + (B_K ? 8 * pb : pb)) * ldc;
+            for (int h = 0; h < 2; ++h) { // A_K: h = pa (rows +8); !A_K: h = cc (rows +2)
+                double2 o;
+                if (A_K) { o.x = acc[i][h][j][pb][0]; o.y = acc[i][h][j][pb][1]; }
+                else { o.x = acc[i][0][j][pb][h]; o.y = acc[i][1][j][pb][h]; }
+                if (SCALE) { o.x *= alpha; o.y *= alpha; }
+                *reinterpret_cast<double2 *>(pc + (A_K ? 8 * h : 2 * h)) = o;
+            }
+        }
+    }
+}
+
+// One 16 x 16 block with every test: matrix bounds (rows < m_lim, cols < n_lim), triangle (tri 1: row <= col, 2: row >=
+// col; rows / cols are indices in the matrix cb points at), beta.  (i, j) select the accumulators.
+template <bool A_K, bool B_K>
+__device__ __forceinline__ void store_block_checked(const double (&acc)[2][2][4][2][2], const int i, const int j, double *cb,
+                                                    i64 ldc, i64 row_blk, i64 col_blk, i64 m_lim, i64 n_lim, int tri,
+                                                    bool vec_ok, double alpha, double beta, int row_t, int col_t)
+{
 #pragma unroll
-                for (int h = 0; h < 2; ++h) { // A_K: h = pa (rows +8); !A_K: h = cc (rows +2)
-                    double2 o;
-                    if (A_K) { o.x = acc[i][h][j][pb][0]; o.y = acc[i][h][j][pb][1]; }
-                    else { o.x = acc[i][0][j][pb][h]; o.y = acc[i][1][j][pb][h]; }
-                    if (SCALE) { o.x *= alpha; o.y *= alpha; }
-                    *reinterpret_cast<double2 *>(pc + (A_K ? 8 * h : 2 * h)) = o;
+    for (int pb = 0; pb < 2; ++pb) {
+        const i64 col = col_blk + col_t + (B_K ? 8 * pb : pb);
+        if (col >= n_lim) continue;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) { // A_K: h = pa (rows +8); !A_K: h = cc (rows +2)
+            const double v0 = A_K ? acc[i][h][j][pb][0] : acc[i][0][j][pb][h];
+            const double v1 = A_K ? acc[i][h][j][pb][1] : acc[i][1][j][pb][h];
+            const i64 row0 = row_blk + row_t + (A_K ? 8 * h : 2 * h);
+            double *cp = cb + row0 + col * ldc;
+            bool ok0 = row0 < m_lim, ok1 = row0 + 1 < m_lim;
+            if (tri == 1) { ok0 = ok0 && row0 <= col; ok1 = ok1 && row0 + 1 <= col; }
+            else if (tri == 2) { ok0 = ok0 && row0 >= col; ok1 = ok1 && row0 + 1 >= col; }
+            if (ok0 && ok1 && vec_ok) {
+                double2 o;
+                if (beta == 0.0) { o.x = alpha * v0; o.y = alpha * v1; }
+                else {
+                    const double2 old = *reinterpret_cast<const double2 *>(cp);
+                    o.x = alpha * v0 + beta * old.x; o.y = alpha * v1 + beta * old.y;
                 }
+                *reinterpret_cast<double2 *>(cp) = o;
+            } else {
+                if (ok0) cp[0] = (beta == 0.0) ? alpha * v0 : alpha * v0 + beta * cp[0];
+                if (ok1) cp[1] = (beta == 0.0) ? alpha * v1 : alpha * v1 + beta * cp[1];
             }
         }
     }
 }
 
 // ---- the TMA + DMMA kernel --------------------------------------------------------------------------------------
-template <bool A_K, bool B_K>
+template <bool A_K, bool B_K, bool PACK>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 rb_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p)
 {
@@ -307,8 +419,10 @@ rb_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 // the tile (edge tiles are ragged; TMA zero-fills the rest) and the gm x gn warp grid that gives the
                 // busiest warp the fewest blocks with at most 2 x 4 per warp: 4 x 2 for full tiles, 8 x 1 / 1 x 8 /
                 // 2 x 4 for thin ones.  The cost of a tile is thus proportional to its valid blocks, not to 128 x 128.
-                const i64 mrem = p.m - tm * BM, nrem = p.n - tn * BN;
-                const int mb = mrem >= BM ? BM / 16 : (int)((mrem + 15) >> 4);
+                const i64 nrem = p.n - tn * BN;
+                int mb;
+                if (PACK) { const i64 left = p.total_blocks - tm * (BM / 16); mb = left >= BM / 16 ? BM / 16 : (int)left; }
+                else { const i64 mrem = p.m - tm * BM; mb = mrem >= BM ? BM / 16 : (int)((mrem + 15) >> 4); }
                 const int nbk = nrem >= BN ? BN / 16 : (int)((nrem + 15) >> 4);
                 int lgm = 2, rpg = 2, cpg = 4, best = 1 << 30;
 #pragma unroll
@@ -316,7 +430,16 @@ rb_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     const int r = (mb + (1 << lg) - 1) >> lg, c = (nbk + (8 >> lg) - 1) >> (3 - lg);
                     if (r <= 2 && c <= 4 && r * c < best) { best = r * c; lgm = lg; rpg = r; cpg = c; }
                 }
-                const uint32_t grid_code = (uint32_t)lgm | ((uint32_t)rpg << 4) | ((uint32_t)cpg << 8) | ((uint32_t)mb << 12) | ((uint32_t)nbk << 16);
+                // diagonal tile of a triangular product: block-list mode (see header); same operand on both sides -> the
+                // B tile is not loaded at all
+                const bool diag = p.tri != 0 && tm == tn;
+                const bool skip_b = diag && p.same_ab;
+                const uint32_t grid_code = (uint32_t)lgm | ((uint32_t)rpg << 4) | ((uint32_t)cpg << 8) | ((uint32_t)mb << 12) |
+                                           ((uint32_t)nbk << 16) | (diag ? (1u << 20) : 0u);
+                const uint32_t tx_bytes = (PACK ? (uint32_t)mb * (16 * BK * 8) : (uint32_t)A_TILE_BYTES) + (skip_b ? 0u : (uint32_t)B_TILE_BYTES);
+                // packed M: (batch, first row) of the tile's first 16-row block
+                int pk_b0 = 0, pk_r0 = 0;
+                if (PACK) { const i64 gb0 = tm * (BM / 16); pk_b0 = (int)(gb0 / p.bpb); pk_r0 = (int)(gb0 - (i64)pk_b0 * p.bpb); }
                 bool first = true;
                 for (i64 k0 = k_begin; k0 < k_end; k0 += BK) {
                     const uint32_t full = bar_base + 8 * stage, empty = bar_base + 8 * (STAGES + stage);
@@ -329,25 +452,34 @@ rb_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                                      "r"((uint32_t)(((k_end - k_begin) % BK + 7) >> 3)), "r"(grid_code), "r"(0u) : "memory");
                         first = false;
                     }
-                    mbar_expect_tx(full, STAGE_BYTES);
+                    mbar_expect_tx(full, tx_bytes);
                     const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_TILE_BYTES;
                     if (A_K) {
 #pragma unroll
                         for (int kb = 0; kb < BK / 8; ++kb)
                             tma_load_3d(sa + kb * (BM * 64), &tmA, full, (int)(k0 + kb * 8), (int)(tm * BM), ba);
+                    } else if (PACK) {
+                        int bb_ = pk_b0, rr_ = pk_r0;
+#pragma unroll
+                        for (int blk = 0; blk < BM / 16; ++blk) {
+                            if (blk < mb) tma_load_3d(sa + blk * (BK * 128), &tmA, full, rr_ * 16, (int)k0, bb_);
+                            if (++rr_ == (int)p.bpb) { rr_ = 0; ++bb_; }
+                        }
                     } else {
 #pragma unroll
                         for (int blk = 0; blk < BM / 16; ++blk)
                             tma_load_3d(sa + blk * (BK * 128), &tmA, full, (int)(tm * BM + blk * 16), (int)k0, ba);
                     }
-                    if (B_K) {
+                    if (!skip_b) {
+                        if (B_K) {
 #pragma unroll
-                        for (int kb = 0; kb < BK / 8; ++kb)
-                            tma_load_3d(sb + kb * (BN * 64), &tmB, full, (int)(k0 + kb * 8), (int)(tn * BN), bb);
-                    } else {
+                            for (int kb = 0; kb < BK / 8; ++kb)
+                                tma_load_3d(sb + kb * (BN * 64), &tmB, full, (int)(k0 + kb * 8), (int)(tn * BN), bb);
+                        } else {
 #pragma unroll
-                        for (int blk = 0; blk < BN / 16; ++blk)
-                            tma_load_3d(sb + blk * (BK * 128), &tmB, full, (int)(tn * BN + blk * 16), (int)k0, bb);
+                            for (int blk = 0; blk < BN / 16; ++blk)
+                                tma_load_3d(sb + blk * (BK * 128), &tmB, full, (int)(tn * BN + blk * 16), (int)k0, bb);
+                        }
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
@@ -413,14 +545,6 @@ rb_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const i64 tm = utm, tn = utn, bidx = ub, sp = usp;
         const int full_steps = (int)ufull, tail_kb = (int)utail;
         const int lgm = ucode & 15, rpg = (ucode >> 4) & 15, cpg = (ucode >> 8) & 15, mb = (ucode >> 12) & 15, nbk = (ucode >> 16) & 15;
-        const int gi = warp & ((1 << lgm) - 1), gj = warp >> lgm;
-        const int rb0 = gi * rpg, cb0 = gj * cpg;
-        int ni = mb - rb0; ni = ni < 0 ? 0 : (ni > rpg ? rpg : ni);
-        int nj = nbk - cb0; nj = nj < 0 ? 0 : (nj > cpg ? cpg : nj);
-        if (ni == 0 || nj == 0) { ni = 0; nj = 0; }
-        const uint32_t a_blk = (uint32_t)rb0 * (A_K ? (16 * 64) : (BK * 128));
-        const uint32_t b_blk = (uint32_t)cb0 * (B_K ? (16 * 64) : (BK * 128));
-
         double acc[2][2][4][2][2]; // [row block i][row tile e/o][col block j][col tile e/o][2]
 #pragma unroll
         for (int i = 0; i < 2; ++i)
@@ -430,6 +554,68 @@ rb_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 for (int j = 0; j < 4; ++j)
 #pragma unroll
                     for (int pb = 0; pb < 2; ++pb) { acc[i][pa][j][pb][0] = 0.0; acc[i][pa][j][pb][1] = 0.0; }
+
+        // output matrix of this item
+        double *cb;
+        i64 ldc, cstride;
+        double alpha, beta;
+        if (p.splits > 1) {
+            cstride = p.n * p.ldp;
+            cb = p.partial + (sp * p.batch + bidx) * cstride;
+            ldc = p.ldp; alpha = 1.0; beta = 0.0;
+        } else {
+            cstride = p.stride_c;
+            cb = p.c + bidx * cstride;
+            ldc = p.ldc; alpha = p.alpha; beta = p.beta;
+        }
+        const bool vec_ok = ((ldc & 1) == 0) && ((((uintptr_t)cb) & 15) == 0) && (!PACK || (cstride & 1) == 0);
+        const int tri = (p.splits > 1) ? 0 : p.tri;
+
+        if ((ucode >> 20) & 1u) {
+            // ---- diagonal tile of a triangular product: this warp's share of the mb(mb+1)/2 blocks on or above (tri 1)
+            //      / below (tri 2) the diagonal, dealt round-robin: block e = warp + 8 s, e = hi(hi+1)/2 + lo, lo <= hi ----
+            const int nblocks = mb * (mb + 1) / 2;
+            const int nown = warp < nblocks ? (nblocks - warp + 7) >> 3 : 0;
+            uint32_t la[5], lb[5];
+            int lrow[5], lcol[5];
+#pragma unroll
+            for (int s = 0; s < 5; ++s) {
+                int e = warp + 8 * s, hi = 0;
+                if (e >= nblocks) e = 0;
+                while ((hi + 1) * (hi + 2) / 2 <= e) ++hi;
+                const int lo = e - hi * (hi + 1) / 2;
+                lrow[s] = (p.tri == 1) ? lo : hi;
+                lcol[s] = (p.tri == 1) ? hi : lo;
+                la[s] = (uint32_t)lrow[s] * (A_K ? (16 * 64) : (BK * 128));
+                lb[s] = (uint32_t)lcol[s] * (B_K ? (16 * 64) : (BK * 128));
+            }
+            const bool b_from_a = p.same_ab != 0;
+#define RB_RUN_LIST(NB_) run_tile_list<A_K, B_K, NB_>(acc, smem_base, bar_base, stage, phase, la, lb, a_off, b_off, full_steps, tail_kb, lane, b_from_a)
+            switch (nown) { // warp-uniform
+            case 5: RB_RUN_LIST(5); break;
+            case 4: RB_RUN_LIST(4); break;
+            case 3: RB_RUN_LIST(3); break;
+            case 2: RB_RUN_LIST(2); break;
+            case 1: RB_RUN_LIST(1); break;
+            default: RB_RUN_LIST(0); break;
+            }
+#undef RB_RUN_LIST
+#pragma unroll
+            for (int s = 0; s < 5; ++s) {
+                if (s >= nown) continue;
+                store_block_checked<A_K, B_K>(acc, s >> 2, s & 3, cb, ldc, tm * BM + lrow[s] * 16, tn * BN + lcol[s] * 16, p.m, p.n,
+                                              lrow[s] == lcol[s] ? tri : 0, vec_ok, alpha, beta, row_t, col_t);
+            }
+            continue;
+        }
+
+        const int gi = warp & ((1 << lgm) - 1), gj = warp >> lgm;
+        const int rb0 = gi * rpg, cb0 = gj * cpg;
+        int ni = mb - rb0; ni = ni < 0 ? 0 : (ni > rpg ? rpg : ni);
+        int nj = nbk - cb0; nj = nj < 0 ? 0 : (nj > cpg ? cpg : nj);
+        if (ni == 0 || nj == 0) { ni = 0; nj = 0; }
+        const uint32_t a_blk = (uint32_t)rb0 * (A_K ? (16 * 64) : (BK * 128));
+        const uint32_t b_blk = (uint32_t)cb0 * (B_K ? (16 * 64) : (BK * 128));
 
 #define RB_RUN(NI_, NJ_) run_tile<A_K, B_K, NI_, NJ_>(acc, smem_base, bar_base, stage, phase, a_blk, b_blk, a_off, b_off, full_steps, tail_kb, lane)
         switch (ni * 8 + nj) { // warp-uniform
@@ -445,62 +631,33 @@ rb_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
 #undef RB_RUN
 
-        // ---- epilogue: thread owns rows (2g, 2g+1) of each 16-row block -> 16-byte stores along M ----
-        double *cb;
-        i64 ldc;
-        double alpha, beta;
-        if (p.splits > 1) {
-            cb = p.partial + (sp * p.batch + bidx) * p.n * p.ldp;
-            ldc = p.ldp; alpha = 1.0; beta = 0.0;
-        } else {
-            cb = p.c + bidx * p.stride_c;
-            ldc = p.ldc; alpha = p.alpha; beta = p.beta;
-        }
-        const bool vec_ok = ((ldc & 1) == 0) && ((((uintptr_t)cb) & 15) == 0);
-        const int tri = (p.splits > 1) ? 0 : p.tri;
-        // Lean path when every block of this warp lies inside the matrix (the common case): no bounds / triangle
-        // tests, 16-byte stores, one IMAD per store, no scaling when alpha == 1.  The epilogue is pure issue overhead
-        // for the DMMA pipe, so it is kept as short as possible.
-        if (vec_ok && tri == 0 && beta == 0.0 && tm * BM + (rb0 + ni) * 16 <= p.m && tn * BN + (cb0 + nj) * 16 <= p.n) {
-            double *pbase = cb + (tm * BM + rb0 * 16 + row_t) + (tn * BN + cb0 * 16 + col_t) * ldc;
-            if (alpha == 1.0) store_lean<A_K, B_K, false>(acc, pbase, ldc, alpha, ni, nj);
-            else store_lean<A_K, B_K, true>(acc, pbase, ldc, alpha, ni, nj);
-            continue;
-        }
-        // Edge tiles / triangles / beta != 0: full tests per row pair.
+        // ---- epilogue, one 16-row block at a time: a thread owns rows (2t, 2t+1) (+8) or (4t .. 4t+3) of each block ->
+        //      16-byte stores along M.  A block whose 16 rows and all of the warp's columns lie inside the matrix (the
+        //      common case) takes the lean path: no bounds / triangle tests, one IMAD per store, no scaling when alpha == 1.
+        //      The epilogue is pure issue overhead for the DMMA pipe, so it is kept as short as possible. ----
+        const i64 col_w = tn * BN + cb0 * 16;
+        const bool cols_in = col_w + nj * 16 <= p.n;
+        const bool lean_ok = vec_ok && tri == 0 && beta == 0.0 && cols_in;
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
             if (i >= ni) continue;
+            double *cm = cb;       // matrix that holds this row block
+            i64 row_blk;           // first row of the block inside it
+            if (PACK) {
+                const i64 gb = tm * (BM / 16) + rb0 + i, bq = gb / p.bpb;
+                cm = cb + bq * cstride;
+                row_blk = (gb - bq * p.bpb) * 16;
+            } else row_blk = tm * BM + (rb0 + i) * 16;
+            if (lean_ok && row_blk + 16 <= p.m) {
+                double *pblk = cm + (row_blk + row_t) + (col_w + col_t) * ldc;
+                if (alpha == 1.0) store_lean_row<A_K, B_K, false>(acc, i, pblk, ldc, alpha, nj);
+                else store_lean_row<A_K, B_K, true>(acc, i, pblk, ldc, alpha, nj);
+                continue;
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 if (j >= nj) continue;
-#pragma unroll
-                for (int pb = 0; pb < 2; ++pb) {
-                    const i64 col = tn * BN + (cb0 + j) * 16 + col_t + (B_K ? 8 * pb : pb);
-                    if (col >= p.n) continue;
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) { // A_K: h = pa (rows +8); !A_K: h = cc (rows +2)
-                        const double v0 = A_K ? acc[i][h][j][pb][0] : acc[i][0][j][pb][h];
-                        const double v1 = A_K ? acc[i][h][j][pb][1] : acc[i][1][j][pb][h];
-                        const i64 row0 = tm * BM + (rb0 + i) * 16 + row_t + (A_K ? 8 * h : 2 * h);
-                        double *cp = cb + row0 + col * ldc;
-                        bool ok0 = row0 < p.m, ok1 = row0 + 1 < p.m;
-                        if (tri == 1) { ok0 = ok0 && row0 <= col; ok1 = ok1 && row0 + 1 <= col; }
-                        else if (tri == 2) { ok0 = ok0 && row0 >= col; ok1 = ok1 && row0 + 1 >= col; }
-                        if (ok0 && ok1 && vec_ok) {
-                            double2 o;
-                            if (beta == 0.0) { o.x = alpha * v0; o.y = alpha * v1; }
-                            else {
-                                const double2 old = *reinterpret_cast<const double2 *>(cp);
-                                o.x = alpha * v0 + beta * old.x; o.y = alpha * v1 + beta * old.y;
-                            }
-                            *reinterpret_cast<double2 *>(cp) = o;
-                        } else {
-                            if (ok0) cp[0] = (beta == 0.0) ? alpha * v0 : alpha * v0 + beta * cp[0];
-                            if (ok1) cp[1] = (beta == 0.0) ? alpha * v1 : alpha * v1 + beta * cp[1];
-                        }
-                    }
-                }
+                store_block_checked<A_K, B_K>(acc, i, j, cm, ldc, row_blk, col_w + j * 16, p.m, p.n, tri, vec_ok, alpha, beta, row_t, col_t);
             }
         }
     }
@@ -672,15 +829,24 @@ bool tma_eligible(const rb_ctx *ctx, const double *p, i64 ld, i64 stride, i64 ba
 // -- e.g. 105 tiles x 1013 steps: s = 7 -> 5 rounds of 147 steps instead of one of 1015; a 264^2 SYRK (3 full + 3 thin
 // tiles): s = 48, not the s = 24 that fills one round with half-empty SMs.  Partials are reduced in a fixed order:
 // results do not depend on the schedule.  Pure host arithmetic (exported as rb_gemm_plan_splits for the CPU tests).
-i64 plan_splits(i64 m, i64 n, i64 k, i64 batch, int tri, int num_sms)
+// packed: the batched product runs with packed M (16-row blocks of all batches enumerated together).
+bool pack_m_applies(bool a_k, bool a_batched, bool b_batched, i64 m, i64 batch, int tri)
 {
-    const i64 tiles_m = rb_cdiv(m, BM), tiles_n = rb_cdiv(n, BN);
+    // A MN-major (one TMA box per 16-row block anyway), B shared by all batches, and something to gain: ragged M
+    return !a_k && a_batched && !b_batched && batch > 1 && tri == 0 && (m % BM) != 0 && rb_cdiv(m, 16) < (1LL << 30);
+}
+
+i64 plan_splits(i64 m, i64 n, i64 k, i64 batch, int tri, int num_sms, bool packed = false)
+{
+    const i64 tiles_n = rb_cdiv(n, BN);
+    const i64 tiles_m = packed ? rb_cdiv(rb_cdiv(m, 16) * batch, BM / 16) : rb_cdiv(m, BM);
+    if (packed) batch = 1;
     const i64 tiles_per_batch = tri ? tiles_m * (tiles_m + 1) / 2 : tiles_m * tiles_n;
     const i64 tiles = tiles_per_batch * batch;
     const i64 ksteps = rb_cdiv(k, BK);
     i64 splits = 1;
     if (tiles <= 0 || num_sms <= 0 || !(tiles < 4 * (i64)num_sms && ksteps >= 8)) return 1;
-    const i64 me = m - (tiles_m - 1) * BM, ne = n - (tiles_n - 1) * BN; // extents of the last tile row / column
+    const i64 me = packed ? BM : m - (tiles_m - 1) * BM, ne = n - (tiles_n - 1) * BN; // extents of the last tile row / column
     const int mbe = (int)((me + 15) >> 4), nbe = (int)((ne + 15) >> 4);
     const double wm_edge = mbe >= 5 ? 1.0 : mbe >= 3 ? 0.5 : mbe == 2 ? 0.25 : 0.125; // <= 2 block rows per warp row
     const double wn_edge = nbe / 8.0;
@@ -689,6 +855,10 @@ i64 plan_splits(i64 m, i64 n, i64 k, i64 batch, int tri, int num_sms)
         for (i64 tm = 0; tm < tiles_m; ++tm) {
             if ((tri == 1 && tm > tn) || (tri == 2 && tm < tn)) continue;
             double w = (tm == tiles_m - 1 ? wm_edge : 1.0) * (tn == tiles_n - 1 ? wn_edge : 1.0);
+            if (tri && tm == tn) { // block-list mode: the busiest warp owns ceil(T / 8) of the T = mb(mb+1)/2 blocks
+                const int mb = tm == tiles_m - 1 ? mbe : 8;
+                w = (double)((mb * (mb + 1) / 2 + 7) / 8) / 8.0;
+            }
             if (w < 0.22) w = 0.22; // measured floor of a 1-block-wide tile
             eff += w;
             if (w > max_w) max_w = w;
@@ -711,16 +881,16 @@ i64 plan_splits(i64 m, i64 n, i64 k, i64 batch, int tri, int num_sms)
     return rb_cdiv(k, kper);
 }
 
-template <bool A_K, bool B_K>
+template <bool A_K, bool B_K, bool PACK>
 int launch_tma(rb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p, int grid)
 {
     static bool attr_set[64] = {false}; // the opt-in shared-memory size is a per-device function attribute
     const int dev = ctx->device & 63;
     if (!attr_set[dev]) {
-        RB_CUDA(cudaFuncSetAttribute(rb_gemm_tma_kernel<A_K, B_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        RB_CUDA(cudaFuncSetAttribute(rb_gemm_tma_kernel<A_K, B_K, PACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_set[dev] = true;
     }
-    rb_gemm_tma_kernel<A_K, B_K><<<grid, NUM_THREADS, SMEM_BYTES, ctx->stream>>>(tmA, tmB, p);
+    rb_gemm_tma_kernel<A_K, B_K, PACK><<<grid, NUM_THREADS, SMEM_BYTES, ctx->stream>>>(tmA, tmB, p);
     RB_LAUNCHED(ctx);
     return RB_OK;
 }
@@ -800,11 +970,14 @@ int rb_gemm_core(rb_ctx *ctx, bool ta, bool tb, i64 m, i64 n, i64 k, double alph
         RB_TRY(encode_map(ctx, &tmB, b, b_k, n, k, ldb, stride_b, b_batched ? batch : 1));
         GemmParams p;
         p.m = m; p.n = n; p.k = k; p.batch = batch;
-        p.tiles_m = rb_cdiv(m, BM); p.tiles_n = rb_cdiv(n, BN);
+        const bool packed = pack_m_applies(a_k, a_batched, b_batched, m, batch, tri);
+        p.pack_m = packed ? 1 : 0;
+        p.bpb = rb_cdiv(m, 16); p.total_blocks = p.bpb * batch;
+        p.tiles_m = packed ? rb_cdiv(p.total_blocks, BM / 16) : rb_cdiv(m, BM); p.tiles_n = rb_cdiv(n, BN);
         p.tiles_per_batch = tri ? p.tiles_m * (p.tiles_m + 1) / 2 : p.tiles_m * p.tiles_n;
-        i64 tiles = p.tiles_per_batch * batch;
+        i64 tiles = p.tiles_per_batch * (packed ? 1 : batch);
         const i64 ksteps = rb_cdiv(k, BK);
-        i64 splits = plan_splits(m, n, k, batch, tri, ctx->num_sms);
+        i64 splits = plan_splits(m, n, k, batch, tri, ctx->num_sms, packed);
         i64 kper = rb_cdiv(ksteps, splits) * BK;
         splits = rb_cdiv(k, kper);
         p.splits = splits; p.kper = kper;
@@ -812,6 +985,8 @@ int rb_gemm_core(rb_ctx *ctx, bool ta, bool tb, i64 m, i64 n, i64 k, double alph
         p.alpha = alpha; p.beta = beta; p.c = c; p.ldc = ldc; p.stride_c = stride_c; p.tri = tri;
         p.partial = nullptr; p.ldp = (m + 1) & ~(i64)1;
         p.a_batched = a_batched ? 1 : 0; p.b_batched = b_batched ? 1 : 0;
+        // same matrix on both sides of a triangular product (SYRK): diagonal tiles need one operand tile only
+        p.same_ab = (tri != 0 && a == b && lda == ldb && a_k == b_k && (batch <= 1 || stride_a == stride_b)) ? 1 : 0;
         // one of 64 self-re-arming scheduler slots per launch: launches of one context may overlap (the caller can
         // move the context between streams) without sharing a work counter
         p.sched = ctx->sched + 2 * (ctx->sched_next++ & 63);
@@ -821,10 +996,15 @@ int rb_gemm_core(rb_ctx *ctx, bool ta, bool tb, i64 m, i64 n, i64 k, double alph
             p.partial = (double *)ws;
         }
         int grid = (int)(p.total_items < ctx->num_sms ? p.total_items : ctx->num_sms);
-        if (a_k && b_k) RB_TRY((launch_tma<true, true>(ctx, tmA, tmB, p, grid)));
-        else if (a_k && !b_k) RB_TRY((launch_tma<true, false>(ctx, tmA, tmB, p, grid)));
-        else if (!a_k && b_k) RB_TRY((launch_tma<false, true>(ctx, tmA, tmB, p, grid)));
-        else RB_TRY((launch_tma<false, false>(ctx, tmA, tmB, p, grid)));
+        if (a_k && b_k) RB_TRY((launch_tma<true, true, false>(ctx, tmA, tmB, p, grid)));
+        else if (a_k && !b_k) RB_TRY((launch_tma<true, false, false>(ctx, tmA, tmB, p, grid)));
+        else if (!a_k && b_k) {
+            if (packed) RB_TRY((launch_tma<false, true, true>(ctx, tmA, tmB, p, grid)));
+            else RB_TRY((launch_tma<false, true, false>(ctx, tmA, tmB, p, grid)));
+        } else {
+            if (packed) RB_TRY((launch_tma<false, false, true>(ctx, tmA, tmB, p, grid)));
+            else RB_TRY((launch_tma<false, false, false>(ctx, tmA, tmB, p, grid)));
+        }
         if (splits > 1) {
             i64 total = m * n * batch;
             i64 blocks = rb_cdiv(total, 256);

@@ -173,9 +173,14 @@ extern "C" int rb_ri_ao2mo(rb_ctx *ctx, const double *c_left, int nl, const doub
     RB_REQUIRE(c_left && c_right && ri3ao, "rb_ri_ao2mo: NULL input");
     if (ri_needs_pad(nb, ri3ao) || (((uintptr_t)c_left | (uintptr_t)c_right) & 15))
         return ri_ao2mo_padded(ctx, c_left, nl, c_right, nr, ri3ao, out, nb, nx, out_ldp);
-    const i64 pc = pick_chunk(nx, nb * nl * 8, ws_budget_bytes(ctx), true);
+    i64 pc = pick_chunk(nx, nb * nl * 8, ws_budget_bytes(ctx), true);
     void *ws;
-    RB_TRY(rb_ws_reserve(ctx, 0, nb * pc * nl * 8, &ws));
+    int st = rb_ws_reserve(ctx, 0, nb * pc * nl * 8, &ws);
+    if (st == RB_ERR_NOMEM) { // the budget was stale (rb_ws_reserve reset it): plan again against what is free now
+        pc = pick_chunk(nx, nb * nl * 8, ws_budget_bytes(ctx), true);
+        st = rb_ws_reserve(ctx, 0, nb * pc * nl * 8, &ws);
+    }
+    RB_TRY(st);
     double *w = (double *)ws;
     for (i64 p0 = 0; p0 < nx; p0 += pc) {
         const i64 pn = (nx - p0 < pc) ? nx - p0 : pc;
@@ -245,10 +250,15 @@ int rb_ri_k_upper(rb_ctx *ctx, const double *ri3ao, const double *ct, i64 no, do
         RB_LAUNCHED(ctx);
         return RB_OK;
     }
-    const i64 pc = pick_chunk(nx, nb * no * 8, ws_budget_bytes(ctx), false);
+    i64 pc = pick_chunk(nx, nb * no * 8, ws_budget_bytes(ctx), false);
     RB_REQUIRE(no * pc <= 2147483647LL, "rb_ri_k: chunk too large");
     void *ws;
-    RB_TRY(rb_ws_reserve(ctx, 0, nb * no * pc * 8, &ws));
+    int st = rb_ws_reserve(ctx, 0, nb * no * pc * 8, &ws);
+    if (st == RB_ERR_NOMEM) { // stale budget: plan again against what is free now
+        pc = pick_chunk(nx, nb * no * 8, ws_budget_bytes(ctx), false);
+        st = rb_ws_reserve(ctx, 0, nb * no * pc * 8, &ws);
+    }
+    RB_TRY(st);
     double *y = (double *)ws;
     for (i64 p0 = 0; p0 < nx; p0 += pc) {
         const i64 pn = (nx - p0 < pc) ? nx - p0 : pc;

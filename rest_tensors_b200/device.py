@@ -261,7 +261,9 @@ class ShardedRI:
             raise ValueError("ShardedRI: buffer smaller than the local shard")
         self.data = data
         if comm and ctx is not None and self.world > 1 and data.is_cuda:
-            ctx.comm_init(self.rank, self.world)
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():   # one process per GPU; otherwise the host wires the comm itself
+                ctx.comm_init(self.rank, self.world)
 
     def fill_synthetic(self, seed: int = 1, scale: float = 1.0) -> "ShardedRI":
         self.ctx.fill_ri3ao_symm(self.data, self.nb, self.p_lo, self.p_hi, seed, scale)

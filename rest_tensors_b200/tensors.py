@@ -324,10 +324,6 @@ class MatrixFull:
     def self_multiple(self, a: float) -> None:
         self._axpy(2, None, a, 0.0)
 
-
-# ======================================================================================================
-# MatrixUpper
-# ======================================================================================================
     # -- eigen-solvers (matrix_blas_lapack.rs:775-797, 1004-1062): one-sided Jacobi on the GPU behind the LAPACK names --
     def lapack_dsyev(self):
         """(eigenvectors [n, n], eigenvalues ascending, n) or None for a non-square matrix"""
@@ -340,6 +336,9 @@ class MatrixFull:
         return _power(self, p, threshold)
 
 
+# ======================================================================================================
+# MatrixUpper
+# ======================================================================================================
 class MatrixUpper:
     """src/matrix/matrixupper.rs:231-234: ``size`` = n(n+1)/2 (the packed length), ``data``."""
 
@@ -414,10 +413,6 @@ class MatrixUpper:
     def __sub__(self, other: "MatrixUpper") -> "MatrixUpper":
         return self._zip(other, 4)
 
-
-# ======================================================================================================
-# RIFull
-# ======================================================================================================
     # -- packed eigen-solvers (matrix_blas_lapack.rs:1075-1147) --
     def lapack_dspevx(self):
         """(eigenvectors [n, n], eigenvalues ascending, n_found) of the packed-upper symmetric matrix"""
@@ -435,6 +430,9 @@ class MatrixUpper:
         return _dspgvx(self, ovlp, num_orb)
 
 
+# ======================================================================================================
+# RIFull
+# ======================================================================================================
 class RIFull:
     """src/ri.rs:18-24: rank-3 column-major tensor, linear index x + y*s0 + z*s0*s1."""
 

@@ -113,6 +113,70 @@ def test_dgemm_strided_batched_and_broadcast(ctx, oracle_blas):
     assert_close_1e10(cd.cpu().numpy(), c_ref, "batched NN with shared B")
 
 
+@pytest.mark.parametrize("ta", "NT")
+def test_dgemm_batched_packed_m_sweep(ctx, oracle_blas, ta):
+    """Batched products with a shared B whose M is not a multiple of 128 run with "packed M" when A is MN-major ('N'): the
+    16-row blocks of all batches are enumerated together, tiles straddle batches (m = 40: three batches per tile), only a
+    batch's last block is ragged.  Shapes around every boundary (m < 16, m = 16 q, q 16 + 1, > 128), shallow and deep k
+    (split-K partials of packed tiles), n with a ragged last column block, C with batch padding, beta != 0; 'T' runs
+    the unpacked path on the same data.  Bit-identical between a batched call and per-batch calls (same tiles' sums)."""
+    rng = np.random.default_rng(4242 + ord(ta))
+    shapes = [(40, 60, 64, 7), (600, 60, 600, 5), (264, 21, 264, 9), (17, 130, 40, 11), (8, 8, 8, 3), (129, 5, 2100, 4),
+              (250, 140, 6000, 2), (16, 64, 32, 20), (1800, 180, 96, 2)]
+    for m, n, k, batch in shapes:
+        lda = (m if ta == "N" else k) + 2 * int(rng.integers(0, 2))
+        cols_a = k if ta == "N" else m
+        sa = lda * cols_a + 2 * int(rng.integers(0, 3))
+        ldc = m + 2 * int(rng.integers(0, 2)); sc = ldc * n + 2 * int(rng.integers(0, 3))
+        alpha, beta = [(1.0, 0.0), (0.7, 1.0), (1.0, -0.5)][int(rng.integers(0, 3))]
+        a = rng.standard_normal(sa * batch); b = rng.standard_normal(k * n); c0 = rng.standard_normal(sc * batch)
+        c_ref = c0.copy()
+        for i in range(batch):
+            ci = c_ref[i * sc:(i + 1) * sc]
+            oracle_blas.dgemm(ta, "N", m, n, k, alpha, a[i * sa:(i + 1) * sa], lda, b, k, beta, ci, ldc)
+        cd = _dev(ctx, c0)
+        ad, bd = _dev(ctx, a), _dev(ctx, b)
+        ctx.dgemm_strided_batched(ta, "N", m, n, k, alpha, ad, lda, sa, bd, k, 0, beta, cd, ldc, sc, batch)
+        what = f"batched {ta}N m={m} n={n} k={k} batch={batch} lda={lda} ldc={ldc} alpha={alpha} beta={beta}"
+        got = cd.cpu().numpy()
+        view = lambda x: np.stack([x[i * sc:(i + 1) * sc][: ldc * n].reshape((ldc, n), order="F") for i in range(batch)])  # noqa: E731
+        assert_close_1e10(view(got)[:, :m], view(c_ref)[:, :m], what)
+        assert np.array_equal(view(got)[:, m:], view(c0)[:, m:]), what + " (padding rows touched)"
+        tails = lambda x: np.concatenate([x[i * sc + ldc * n:(i + 1) * sc] for i in range(batch)])  # noqa: E731
+        assert np.array_equal(tails(got), tails(c0)), what + " (batch padding touched)"
+
+
+def test_triangular_products_block_list_mode(ctx, oracle_blas):
+    """Diagonal tiles of a triangular product run in block-list mode (36 blocks dealt to 8 warps; one operand tile when A
+    and B are the same matrix).  SYRK n from one ragged block to several tiles, both triangles, both transposes, split-K,
+    beta != 0, plus a triangular product of two DIFFERENT matrices with a symmetric result (the weighted RPA form)."""
+    rng = np.random.default_rng(99)
+    for n in [1, 15, 16, 17, 100, 128, 129, 250, 264, 383, 600, 641]:
+        for trans in "NT":
+            for uplo in "UL":
+                k = int(rng.choice([24, 200, 5000]))
+                ra, ca = (n, k) if trans == "N" else (k, n)
+                lda = ra + (ra & 1); ldc = n + (n & 1)
+                beta = float(rng.choice([0.0, 1.0, -0.3]))
+                a = rng.standard_normal(lda * ca); c0 = rng.standard_normal(ldc * n)
+                c_ref = c0.copy()
+                oracle_blas.dsyrk(uplo, trans, n, k, 1.0, a, lda, beta, c_ref, ldc)
+                cd = _dev(ctx, c0)
+                ctx.dsyrk(uplo, trans, n, k, 1.0, _dev(ctx, a), lda, beta, cd, ldc)
+                got = cd.cpu().numpy().reshape((ldc, n), order="F"); ref = c_ref.reshape((ldc, n), order="F")
+                mask = (np.triu if uplo == "U" else np.tril)(np.ones((n, n), dtype=bool))
+                what = f"dsyrk {uplo}{trans} n={n} k={k} beta={beta}"
+                assert_close_1e10(got[:n][mask], ref[:n][mask], what)
+                assert np.array_equal(got[:n][~mask], c0.reshape((ldc, n), order="F")[:n][~mask]), what + " (other triangle)"
+    # weighted symmetric product through the RPA-type consumer: A = X diag(w) (a scaled copy), B = X -> two operands
+    nx, nl, nr = 300, 6, 40
+    mo = rng.standard_normal(nx * nl * nr); w = rng.standard_normal(nl * nr)
+    out = ctx.empty(nx * nx)
+    ctx.ri_mo_pq(_dev(ctx, mo), nx, nx, _dev(ctx, mo), nx, nx, nl, nr, (0, nl, 0, nr), _dev(ctx, w), 0.0, out, nx)
+    x = mo.reshape((nx, nl * nr), order="F")
+    assert_close_1e10(out.cpu().numpy().reshape((nx, nx), order="F"), (x * w) @ x.T, "weighted mo_pq (A != B, tri)")
+
+
 def test_host_dgemm_wrappers(rt, oracle_blas):
     m, n, k = 90, 41, 77
     a = oracle_blas.fill_linear(m * k, 28); b = oracle_blas.fill_linear(n * k, 29)

@@ -176,6 +176,28 @@ def test_power_drops_eigenvalues_below_the_threshold(rt, oracle_blas):
     assert_close_1e10(got.data, ref, "pseudo-inverse square root")
 
 
+def test_power_and_overlap_check_on_indefinite_input_with_symmetric_spectrum(rt, oracle_blas):
+    """Matrices whose spectrum is symmetric about zero ([[0, B], [B^T, 0]]: eigenvalues +-sigma_i) are the hard case of
+    the unshifted semi-definite fast path: one-sided Jacobi sees |lambda| only and the +s / -s eigenvectors can stay mixed
+    (for [[0,1],[1,0]] the columns are orthogonal from the start, every Rayleigh quotient is 0).  The result must be the
+    reference's: _power drops the negative eigenvalues (dsyev + threshold, matrix_blas_lapack.rs:2123-2185), and a
+    non-positive-definite overlap is rejected by _dspgvx (LAPACK's Cholesky panics there)."""
+    s2 = np.array([[0.0, 1.0], [1.0, 0.0]])
+    got = rt._power(rt.MatrixFull.from_vec([2, 2], _flat(s2)), 1.0, 1e-10)
+    assert_close_1e10(got.data, _flat(0.5 * np.ones((2, 2))), "_power([[0,1],[1,0]], p = 1)")
+    for n, m in [(6, 6), (40, 23), (130, 130)]:
+        b = oracle_blas.fill_linear(n * m, 81).reshape((n, m), order="F")
+        s = np.block([[np.zeros((n, n)), b], [b.T, np.zeros((m, m))]])
+        nn = n + m
+        ref, kept_ref = oracle_blas.power(_flat(s), nn, 0.5, 1e-10)
+        got = rt._power(rt.MatrixFull.from_vec([nn, nn], _flat(s)), 0.5, 1e-10)
+        assert kept_ref == min(n, m)
+        assert_close_1e10(got.data, ref, f"_power of the bipartite matrix {n}+{m}")
+        a = _sym(oracle_blas, nn, 82)
+        with pytest.raises(rt.RestB200Error, match="positive definite"):
+            rt._dspgvx(rt.MatrixUpper.from_vec(nn * (nn + 1) // 2, _pack(a)), rt.MatrixUpper.from_vec(nn * (nn + 1) // 2, _pack(s)), 2)
+
+
 def test_device_api_on_resident_buffers(ctx, oracle_blas):
     n = 96
     a = _sym(oracle_blas, n, 81)
