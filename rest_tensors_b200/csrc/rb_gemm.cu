@@ -85,6 +85,8 @@ struct GemmParams {
     int pack_m;
     i64 bpb, total_blocks;     // 16-row blocks per batch, batch * bpb
     int same_ab;               // tri != 0 and A, B are the same matrix: diagonal tiles load one operand tile only
+    int split_major;           // work items enumerate the tiles of one k-range before the next k-range (see decode_item)
+    i64 tiles_total;           // tiles_per_batch * batch (packed M: tiles_per_batch)
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------
@@ -140,8 +142,11 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b)
 // work item -> (batch, tm, tn, split)
 __device__ __forceinline__ void decode_item(const GemmParams &p, i64 item, i64 &b, i64 &tm, i64 &tn, i64 &sp)
 {
-    sp = item % p.splits;
-    i64 tile = item / p.splits;
+    // split-major: concurrently running CTAs work on the SAME k-range of different tiles, so the operand panels of that
+    // k-range are shared through L2 (a SYRK over a 490 MB operand reads it once instead of once per tile row / column)
+    i64 tile;
+    if (p.split_major) { sp = item / p.tiles_total; tile = item - sp * p.tiles_total; }
+    else { sp = item % p.splits; tile = item / p.splits; }
     b = tile / p.tiles_per_batch;
     i64 t = tile - b * p.tiles_per_batch;
     if (p.tri == 0) {
@@ -982,6 +987,9 @@ int rb_gemm_core(rb_ctx *ctx, bool ta, bool tb, i64 m, i64 n, i64 k, double alph
         splits = rb_cdiv(k, kper);
         p.splits = splits; p.kper = kper;
         p.total_items = tiles * splits;
+        p.tiles_total = tiles;
+        static const int split_order = [] { const char *e = getenv("REST_B200_SPLIT_ORDER"); return e ? atoi(e) : 1; }();
+        p.split_major = (splits > 1 && split_order) ? 1 : 0;
         p.alpha = alpha; p.beta = beta; p.c = c; p.ldc = ldc; p.stride_c = stride_c; p.tri = tri;
         p.partial = nullptr; p.ldp = (m + 1) & ~(i64)1;
         p.a_batched = a_batched ? 1 : 0; p.b_batched = b_batched ? 1 : 0;
