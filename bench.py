@@ -13,6 +13,8 @@ that the line stays comparable across N.  The same JSON line also carries, devic
     parity        all-reduced J / K, d_P and every rank's ri3mo rows against the CPU oracle on a reduced-slab replica of
                   the same shapes (the oracle is the checker here, never on the timed path)
     small_configs (N = 1) configs A and B: device, e2e pinned, e2e pageable and the reference CPU path
+    crossover     (N = 1) per-slab host-pointer BLAS / copy calls from 8 caller threads vs OpenBLAS, and the batched entry point
+    e2e_variants  (N = 1) the occ-vir form through the host ABI (10x fewer bytes back) and the resident-shard SCF iteration
 
     python bench.py --gpus N --steps K --warmup W              # our arm (one process per GPU under torchrun)
     python bench.py --impl reference --gpus N --steps K ...    # the reference algorithm on the host cores (rank 0 only)
@@ -489,6 +491,164 @@ def _e2e_bound(env, lib, check, w, total_flop, steps, pinned):
                 "error": f"{type(exc).__name__}: {exc}"[:300]}
 
 
+def e2e_variants_leg(env, lib, check, w, steps=3):
+    """Two more end-to-end forms of the same step at N = 1 (VERDICT r01 'cut e2e bytes'), both through the C ABI with pinned
+    host buffers and host<->device copies inside the timed region:
+      occ_vir      : rb_host_ri_ao2mo_jk with C_left = C_occ, C_right = C_vir (north-star form): ri3ao still streams up once,
+                     but the ri3mo that comes back is nocc*nvir/nb^2 of the square one;
+      scf_resident : ri3ao stays in HBM between SCF iterations (what REST's loop needs): per iteration D and C~ go up
+                     (rb_memcpy_h2d), d_P / J / K run on the resident shard, J and K come back (rb_memcpy_d2h)."""
+    import ctypes as C
+    torch, dev = env.torch, env.dev
+    nb, nx, no = w.nb, w.nx, w.no
+    n2, nv = nb * nb, nb - no
+    out = {}
+    try:
+        P = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+        mk = lambda n: torch.empty(n, dtype=torch.float64, pin_memory=True)  # noqa: E731
+        ri_h = mk(nx * n2); ri_h.copy_(w.sh.data[: nx * n2])
+        c_h, dm_h, ct_h = mk(n2), mk(n2), mk(nb * no)
+        c_h.copy_(w.c); dm_h.copy_(w.dm); ct_h.copy_(w.ct)
+        ov_h, d_h, j_h, k_h = mk(nx * no * nv), mk(nx), mk(n2), mk(n2)
+        torch.cuda.synchronize()
+        cocc = C.c_void_p(c_h.data_ptr()); cvir = C.c_void_p(c_h.data_ptr() + nb * no * 8)
+
+        def ov_step():
+            check(lib.rb_host_ri_ao2mo_jk(cocc, no, cvir, nv, P(ri_h), P(ov_h), nb, nx, P(dm_h), P(ct_h), no, P(d_h), P(j_h),
+                                          P(k_h)), "rb_host_ri_ao2mo_jk(occ-vir)")
+        ov_step()
+        w.step(False)
+        torch.cuda.synchronize()
+        idx = torch.arange(0, nx * no * nv, max(1, nx * no * nv // 65536))
+        ok = bool(torch.allclose(ov_h[idx], w.ov[idx.to(dev)].cpu(), rtol=1e-12, atol=1e-14)) and \
+            bool(torch.allclose(k_h, w.k.cpu(), rtol=1e-11, atol=1e-12))
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            ov_step()
+        dt = (time.perf_counter() - t0) / steps
+        flop = sum(flops(nb, nx, no, False).values())
+        out["occ_vir"] = {"ms_per_step": dt * 1e3, "value": flop / dt / 1e9, "unit": UNIT,
+                          "h2d_bytes_per_step": (nx * n2 + 2 * n2 + nb * no) * 8,
+                          "d2h_bytes_per_step": (nx * no * nv + 2 * n2 + nx) * 8, "matches_device_path": ok,
+                          "api": "rb_host_ri_ao2mo_jk(C_occ, C_vir) (host-pointer C ABI, pinned buffers)"}
+        del ri_h, ov_h
+        # resident shard: only D, C~ up and J, K down per iteration
+        ctx = env.ctx
+
+        def scf_step():
+            check(lib.rb_memcpy_h2d(ctx.h, P(w.dm), P(dm_h), C.c_int64(n2 * 8)), "rb_memcpy_h2d")
+            check(lib.rb_memcpy_h2d(ctx.h, P(w.ct), P(ct_h), C.c_int64(nb * no * 8)), "rb_memcpy_h2d")
+            w.sh.dp(w.dm, out=w.d)
+            w.sh.j(w.d, out=w.j, reduce=True)
+            w.sh.k(w.ct, no, out=w.k, reduce=True)
+            check(lib.rb_memcpy_d2h(ctx.h, P(j_h), P(w.j), C.c_int64(n2 * 8)), "rb_memcpy_d2h")
+            check(lib.rb_memcpy_d2h(ctx.h, P(k_h), P(w.k), C.c_int64(n2 * 8)), "rb_memcpy_d2h")
+            ctx.sync()
+        scf_step()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            scf_step()
+        dt = (time.perf_counter() - t0) / 10
+        f = flops(nb, nx, no, True)
+        flop = f["dp"] + f["j"] + f["k"]
+        out["scf_resident"] = {"ms_per_step": dt * 1e3, "value": flop / dt / 1e9, "unit": UNIT,
+                               "h2d_bytes_per_step": (n2 + nb * no) * 8, "d2h_bytes_per_step": 2 * n2 * 8,
+                               "api": "rb_memcpy_h2d(D, C~) + rb_ri_dp / rb_ri_j / rb_ri_k on the resident shard + rb_memcpy_d2h(J, K)",
+                               "note": "d_P + J + K only (the per-iteration work of an SCF loop); ri3ao uploaded once, outside"}
+    except Exception as exc:  # noqa: BLE001
+        out["error"] = f"{type(exc).__name__}: {exc}"[:300]
+    return out
+
+
+def crossover_leg(lib, check, threads=8, budget_s=1.0):
+    """Drop-in crossover: REST calls the BLAS wrappers PER SLAB from rayon worker threads (the reference's
+    par_iter_auxbas pattern, src/ri.rs:180-218).  For slab sizes nb = 100 / 264 / 600 this times, from `threads` concurrent
+    caller threads, the host-pointer entry points (upload -> kernel -> download under the library's per-device mutex)
+    against the same call on OpenBLAS with one BLAS thread per caller (the oracle is the CPU baseline here), and next to
+    them the BATCHED entry point that does the same per-slab work for a whole block of slabs in one call (rb_host_ri_k:
+    dgemm + dsyrk per slab).  Microseconds per call, wall clock / calls."""
+    import ctypes as C
+    import numpy as np
+    from oracle.api import Oracle
+    from rest_tensors_b200 import tensors as rt
+    o = Oracle()
+    if not o.load_openblas(threads=1):
+        return {"error": "no OpenBLAS for the CPU side"}
+    out = {"caller_threads": threads, "unit": "us per call (wall / calls, all caller threads running)",
+           "cpu": "OpenBLAS, 1 BLAS thread per caller thread; " + o.blas_config()[:60], "rows": []}
+
+    def timed(fn_per_thread, budget):
+        """every thread loops fn until the budget is spent; returns us per call"""
+        counts = [0] * threads
+        stop = time.perf_counter() + budget
+
+        def work(t):
+            fn = fn_per_thread(t)
+            fn()
+            n = 0
+            while time.perf_counter() < stop:
+                fn(); n += 1
+            counts[t] = n
+        ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+        t0 = time.perf_counter()
+        for th in ths: th.start()
+        for th in ths: th.join()
+        dt = time.perf_counter() - t0
+        return dt / max(1, sum(counts)) * 1e6
+
+    for nb, no in [(100, 20), (264, 21), (600, 60)]:
+        n2 = nb * nb
+        bufs = []
+        for t in range(threads):
+            a = o.fill_linear(n2, 100 + t); ct = o.fill_linear(nb * no, 200 + t, scale=nb ** -0.5)
+            bufs.append({"a": a, "ct": ct, "y": np.zeros(nb * no), "k": np.zeros(n2), "x": o.fill_linear(nb, 300 + t),
+                         "v": np.zeros(nb), "b": np.zeros(n2)})
+        P = lambda v: C.c_void_p(v.ctypes.data)  # noqa: E731
+        ops = {
+            "dgemm  Y = A_P C~ [nb,nb]x[nb,no]": (
+                lambda t: (lambda b=bufs[t]: check(lib.rb_host_dgemm(b"N", b"N", nb, no, nb, 1.0, P(b["a"]), nb, P(b["ct"]), nb, 0.0,
+                                                                     P(b["y"]), nb), "rb_host_dgemm")),
+                lambda t: (lambda b=bufs[t]: o.dgemm("N", "N", nb, no, nb, 1.0, b["a"], nb, b["ct"], nb, 0.0, b["y"], nb))),
+            "dsyrk  K += Y Y^T (n=nb, k=no)": (
+                lambda t: (lambda b=bufs[t]: check(lib.rb_host_dsyrk(b"U", b"N", nb, no, 1.0, P(b["y"]), nb, 1.0, P(b["k"]), nb),
+                                                   "rb_host_dsyrk")),
+                lambda t: (lambda b=bufs[t]: o.dsyrk("U", "N", nb, no, 1.0, b["y"], nb, 1.0, b["k"], nb))),
+            "dgemv  v = A_P x [nb,nb]": (
+                lambda t: (lambda b=bufs[t]: check(lib.rb_host_dgemv(b"N", nb, nb, 1.0, P(b["a"]), nb, P(b["x"]), 1, 0.0, P(b["v"]), 1),
+                                                   "rb_host_dgemv")),
+                lambda t: (lambda b=bufs[t]: o.dgemv("N", nb, nb, 1.0, b["a"], nb, b["x"], 1, 0.0, b["v"], 1))),
+            "copy_rr one slab [nb,nb,1]": (
+                lambda t: (lambda b=bufs[t]: rt.ri_copy_from_ri(b["a"], [nb, nb, 1], (0, nb), (0, nb), (0, 1), b["b"], [nb, nb, 1],
+                                                                (0, nb), (0, nb), (0, 1))),
+                lambda t: (lambda b=bufs[t]: o.copy_rr(nb, nb, 1, b["a"], nb, nb, 1, 0, 0, 0, b["b"], nb, nb, 1, 0, 0, 0))),
+        }
+        for name, (gpu, cpu) in ops.items():
+            g = timed(gpu, budget_s * 0.25)
+            c = timed(cpu, budget_s * 0.25)
+            out["rows"].append({"nb": nb, "no": no, "op": name, "gpu_us": round(g, 1), "cpu_us": round(c, 1),
+                                "gpu_over_cpu": round(g / c, 2)})
+        # the batched remedy: K over a block of slabs in ONE call vs the per-slab dgemm + dsyrk on the CPU
+        slabs = max(8, min(256, (64 << 20) // (n2 * 8)))
+        ri = o.fill_ri3ao_symm(nb, 0, slabs)
+        kk = np.zeros(n2)
+        check(lib.rb_host_ri_k(P(ri), P(bufs[0]["ct"]), no, P(kk), nb, slabs), "rb_host_ri_k")
+        t0 = time.perf_counter(); reps = 0
+        while time.perf_counter() - t0 < budget_s * 0.25:
+            check(lib.rb_host_ri_k(P(ri), P(bufs[0]["ct"]), no, P(kk), nb, slabs), "rb_host_ri_k"); reps += 1
+        g = (time.perf_counter() - t0) / reps / slabs * 1e6
+        o.set_threads(threads)
+        t0 = time.perf_counter(); reps = 0
+        while time.perf_counter() - t0 < budget_s * 0.25:
+            o.ri_k(ri, bufs[0]["ct"], nb, no, slabs); reps += 1
+        c = (time.perf_counter() - t0) / reps / slabs * 1e6
+        o.set_threads(1)
+        out["rows"].append({"nb": nb, "no": no, "op": f"BATCHED rb_host_ri_k over {slabs} slabs, per slab (dgemm + dsyrk); CPU: "
+                            f"same loop, {threads} BLAS threads", "gpu_us": round(g, 1), "cpu_us": round(c, 1),
+                            "gpu_over_cpu": round(g / c, 2)})
+    check(lib.rb_host_trim(), "rb_host_trim")
+    return out
+
+
 def small_config_leg(env, lib, check, name):
     """Configs A / B on one GPU: device-resident step, e2e through the host-pointer ABI with pinned
     and with pageable buffers, and the reference CPU path on the FULL configuration, all in GFLOP/s of the same step."""
@@ -623,6 +783,7 @@ def run_ours(args):
         iajb = consumers_leg(env, w)
 
     # ---- e2e through the host-pointer C ABI (H2D + D2H inside the timed region) ----
+    e2e_variants = None
     if args.no_e2e:
         e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "skipped": "--no-e2e"}
         e2e_pageable = None
@@ -632,6 +793,8 @@ def run_ours(args):
         if world == 1:
             check(lib.rb_host_trim(), "rb_host_trim")
             e2e_pageable = e2e_leg(env, lib, check, w, total_flop, 3, False, args.no_numa)
+            if not args.no_extras:
+                e2e_variants = e2e_variants_leg(env, lib, check, w)
         check(lib.rb_host_trim(), "rb_host_trim")
 
     # ---- config D (north star) on 8 GPUs: nb=1800, naux=4800, nocc=180, 600 slabs per rank ----
@@ -659,6 +822,12 @@ def run_ours(args):
             except Exception as exc:  # noqa: BLE001
                 small[name] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
         check(lib.rb_host_trim(), "rb_host_trim")
+    crossover = None
+    if world == 1 and args.config == "C" and not args.no_extras and not args.no_e2e and not args.no_cpu:
+        try:
+            crossover = crossover_leg(lib, check)
+        except Exception as exc:  # noqa: BLE001
+            crossover = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
     if rank != 0:
         if world > 1:
@@ -717,11 +886,13 @@ def run_ours(args):
                          "j_achieved": nx * n2 * 8 / (avg["j"] * 1e-3) / 1e9, "traffic": traffic_dp},
         "e2e": e2e,
         "e2e_pageable": e2e_pageable,
+        "e2e_variants": e2e_variants,
         "step_occ_vir": step_occ_vir,
         "strong_C": strong,
         "config_D": config_d,
         "parity": parity,
         "small_configs": small,
+        "crossover": crossover,
         "iajb_occ_vir": iajb,
         "collectives": None if world == 1 else {"api": "rb_allreduce_sum / rb_ri_j_allreduce / rb_ri_k_allreduce (librest_b200, NCCL "
                                                        "bound at run time, compute stream)", "nccl_version": nccl_ver[0],

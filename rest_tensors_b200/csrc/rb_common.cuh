@@ -52,6 +52,7 @@ struct rb_ctx {
     i64 ws_bytes[4] = {0, 0, 0, 0};
     i64 ws_budget = 0;             // cached workspace budget (bytes), 0 = not yet queried
     i64 launches = 0;
+    i64 tma_layout_launches = 0;   // launches of the bulk-tensor layout kernels (rb_layout_tma.cu)
     int gemm_path = 0;
     rb_encode_tiled_fn encode_tiled = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -60,9 +61,12 @@ struct rb_ctx {
     void *eig_cache = nullptr;           // instantiated Jacobi sweep graphs (rb_eig.cu), freed by rb_eig_cache_free
     unsigned long long *sched = nullptr; // GEMM tile-scheduler slots (64 x 2 words on the device), zero between launches
     unsigned sched_next = 0;             // slot of the next GEMM launch (round-robin)
+    unsigned *tile_counters = nullptr;   // fused split-K reduction: 4 regions of RB_TILE_COUNTER_REGION counters, zero between launches
     void *comm = nullptr;                // NCCL communicator (rb_comm.cu), NULL = a world of one
     int comm_rank = 0, comm_world = 1;
 };
+
+#define RB_TILE_COUNTER_REGION 32768 /* counters per region = 4096 tiles x 8 consumer warps */
 
 // Grow-only device workspace (synchronises the stream before freeing the old block).
 int rb_ws_reserve(rb_ctx *ctx, int slot, i64 bytes, void **out);
@@ -91,6 +95,10 @@ int rb_copy3d(rb_ctx *ctx, const double *src, i64 s0, i64 si, i64 sj, i64 sk, do
 // Batched tiled 2-D transpose: out[c + r*ors + b*obs] = in[r + c*ics + b*ibs]
 int rb_transpose_batched(rb_ctx *ctx, const double *in, i64 ics, i64 ibs, double *out, i64 ors, i64 obs, i64 nr,
                          i64 nc, i64 nbatch);
+// TMA forms (rb_layout_tma.cu); RB_TMA_NOT_ELIGIBLE (-1): operands TMA cannot describe, the caller runs the plain kernel
+#define RB_TMA_NOT_ELIGIBLE (-1)
+int rb_tma_copy3d(rb_ctx *ctx, const double *s, i64 sj, i64 sk, double *d, i64 dj, i64 dk, i64 ni, i64 nj, i64 nk);
+int rb_tma_transpose(rb_ctx *ctx, const double *in, i64 ics, i64 ibs, double *out, i64 ors, i64 obs, i64 nr, i64 nc, i64 nbatch);
 // GEMM core (rb_gemm.cu). tri: 0 = full, 1 = only tiles/elements with row<=col (upper), 2 = row>=col (lower)
 int rb_gemm_core(rb_ctx *ctx, bool ta, bool tb, i64 m, i64 n, i64 k, double alpha, const double *a, i64 lda,
                  i64 stride_a, const double *b, i64 ldb, i64 stride_b, double beta, double *c, i64 ldc,

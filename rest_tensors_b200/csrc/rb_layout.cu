@@ -253,6 +253,10 @@ int rb_copy3d(rb_ctx *ctx, const double *src, i64 s0, i64 si, i64 sj, i64 sk, do
     if (ni <= 0 || nj <= 0 || nk <= 0) return RB_OK;
     const double *s = src + s0;
     double *d = dst + d0;
+    if (si == 1 && di == 1) { // unit-stride runs on both sides: bulk-tensor copy when TMA can describe the operands
+        const int st = rb_tma_copy3d(ctx, s, sj, sk, d, dj, dk, ni, nj, nk);
+        if (st != RB_TMA_NOT_ELIGIBLE) return st;
+    }
     bool vec = si == 1 && di == 1 && (ni % 2 == 0) && (sj % 2 == 0) && (sk % 2 == 0) && (dj % 2 == 0) &&
                (dk % 2 == 0) && (((uintptr_t)s & 15) == 0) && (((uintptr_t)d & 15) == 0);
     const i64 niv = vec ? ni / 2 : ni;
@@ -404,6 +408,10 @@ int rb_transpose_batched(rb_ctx *ctx, const double *in, i64 ics, i64 ibs, double
                          i64 nc, i64 nbatch)
 {
     if (nr <= 0 || nc <= 0 || nbatch <= 0) return RB_OK;
+    {
+        const int st = rb_tma_transpose(ctx, in, ics, ibs, out, ors, obs, nr, nc, nbatch);
+        if (st != RB_TMA_NOT_ELIGIBLE) return st;
+    }
     i64 tiles_r = rb_cdiv(nr, TT), tiles_c = rb_cdiv(nc, TT);
     i64 total = tiles_r * tiles_c * nbatch;
     i64 blocks = total;

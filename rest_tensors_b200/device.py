@@ -78,6 +78,11 @@ class Context:
     def launches(self) -> int:
         return int(lib.rb_ctx_launch_count(self.h))
 
+    @property
+    def tma_layout_launches(self) -> int:
+        """launches of the bulk-tensor (TMA) copy / transpose / pack / unpack kernels so far"""
+        return int(lib.rb_ctx_tma_layout_count(self.h))
+
     def set_gemm_path(self, path: int) -> None:
         check(lib.rb_ctx_set_gemm_path(self.h, path), "rb_ctx_set_gemm_path")
 

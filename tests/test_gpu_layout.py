@@ -320,3 +320,63 @@ def test_host_entry_points_from_many_threads(rt, oracle_blas):
     for th in threads:
         th.join()
     assert not errors, errors
+
+
+# ---------------------------------------------------------------- bulk-tensor (TMA) forms, device buffers ----
+def _ri_transposed_view(x, i, j, k, which):
+    """torch view of what transpose `which` must produce (ri.rs:227-294), from the column-major [i, j, k] buffer x"""
+    t = x.view(k, j, i)                       # element (i, j, k) of the column-major tensor == t[k][j][i]
+    perm = [(0, 2, 1), (2, 0, 1), (2, 1, 0), (1, 0, 2)][which]   # jik, jki, kji, ikj (slowest output index first)
+    return t.permute(*perm).contiguous().view(-1)
+
+
+@pytest.mark.parametrize("shape", [(64, 64, 16), (256, 130, 6), (130, 258, 10), (66, 1000, 4), (1000, 66, 6), (600, 600, 8),
+                                   (2, 40000, 2), (40000, 2, 2)])
+def test_tma_ri_transposes_bit_exact(ctx, shape):
+    """Even extents and 16-byte aligned buffers take the bulk-tensor kernels (TMA load -> shared memory -> TMA store):
+    ragged tiles at every edge, thin tensors, all four permutations, compared bit for bit with torch's permute."""
+    i, j, k = shape
+    n = i * j * k
+    x = ctx.empty(n); ctx.fill_linear(x, n, 21, 0, 1.0)
+    u = ctx.empty(n)
+    before = ctx.tma_layout_launches
+    for which in range(4):
+        u.fill_(float("nan"))
+        ctx.ri_transpose(x, i, j, k, which, u)
+        assert torch.equal(u, _ri_transposed_view(x, i, j, k, which)), (shape, which)
+    assert ctx.tma_layout_launches == before + 4, "aligned transposes must run on the bulk-tensor path"
+
+
+@pytest.mark.parametrize("rows,cols", [(4000, 2000), (1002, 514), (64, 8192), (8192, 66), (600, 264)])
+def test_tma_matrix_transpose_bit_exact(ctx, rows, cols):
+    x = ctx.empty(rows * cols); ctx.fill_linear(x, rows * cols, 22, 0, 1.0)
+    u = ctx.empty(rows * cols); u.fill_(float("nan"))
+    before = ctx.tma_layout_launches
+    ctx.matrix_transpose(x, rows, cols, u)
+    assert torch.equal(u.view(rows, cols), x.view(cols, rows).t())
+    assert ctx.tma_layout_launches == before + 1
+
+
+def test_tma_sub_box_copies_bit_exact(ctx):
+    """copy_rr / copy_mm with even starts (16-byte aligned box corners): bulk-tensor copy; everything outside the box
+    must stay untouched.  Odd starts or extents of the same shapes fall back to the plain kernel and must agree too."""
+    fx, fy, fz, tx, ty, tz = 600, 520, 12, 640, 530, 14
+    f = ctx.empty(fx * fy * fz); ctx.fill_linear(f, f.numel(), 23, 0, 1.0)
+    for (xl, yl, zl, fs, ts, tma) in [(500, 500, 10, (50, 10, 1), (20, 4, 2), True), (600, 520, 12, (0, 0, 0), (0, 0, 0), True),
+                                      (2, 500, 12, (598, 3, 0), (0, 7, 1), False), (300, 1, 12, (0, 519, 0), (340, 0, 2), False),
+                                      (501, 500, 10, (50, 10, 1), (20, 4, 2), True), (500, 500, 10, (51, 10, 1), (20, 4, 2), False)]:
+        t = ctx.empty(tx * ty * tz); ctx.fill_linear(t, t.numel(), 24, 0, 1.0)
+        ref = t.clone()
+        ref.view(tz, ty, tx)[ts[2]:ts[2] + zl, ts[1]:ts[1] + yl, ts[0]:ts[0] + xl] = \
+            f.view(fz, fy, fx)[fs[2]:fs[2] + zl, fs[1]:fs[1] + yl, fs[0]:fs[0] + xl]
+        before = ctx.tma_layout_launches
+        ctx.copy_rr(xl, yl, zl, f, fx, fy, fz, fs[0], fs[1], fs[2], t, tx, ty, tz, ts[0], ts[1], ts[2])
+        assert torch.equal(t, ref), (xl, yl, zl, fs, ts)
+        assert (ctx.tma_layout_launches == before + 1) == tma, (xl, yl, zl, fs, ts)
+    n = 4000
+    a = ctx.empty(n * n); ctx.fill_linear(a, n * n, 25, 0, 1.0)
+    b = ctx.empty(n * n); b.zero_()
+    ctx.copy_mm(n - 100, n - 200, a, n, n, 100, 200, b, n, n, 0, 0)
+    ref = torch.zeros_like(b)
+    ref.view(n, n)[0:n - 200, 0:n - 100] = a.view(n, n)[200:n, 100:n]
+    assert torch.equal(b, ref)

@@ -1,11 +1,14 @@
 #!/bin/bash
 # round 2, K-build profile: eigen-solver fix check, K timings (split order A/B), ncu launch list with pipe/DRAM metrics, FP64 probe capture
 mkdir -p gpurun_out
-timeout -k 10 600 python -m pytest tests/test_gpu_eig.py tests/test_gpu_contractions.py -m gpu -q -x -p no:cacheprovider > gpurun_out/pytest_eig.log 2>&1
-echo "pytest rc=$?"; tail -4 gpurun_out/pytest_eig.log
-for so in 0 1; do
+timeout -k 10 900 python -m pytest tests/test_gpu_eig.py tests/test_gpu_contractions.py tests/test_gpu_layout.py -m gpu -q -p no:cacheprovider > gpurun_out/pytest_eig.log 2>&1
+echo "pytest rc=$?"; tail -12 gpurun_out/pytest_eig.log
+REST_B200_LAYOUT_TMA=0 timeout -k 10 300 python tools/hbm_probe.py gpurun_out/hbm_plain.json > gpurun_out/hbm_plain.log 2>&1; echo "hbm plain rc=$?"
+timeout -k 10 300 python tools/hbm_probe.py gpurun_out/hbm_tma.json > gpurun_out/hbm_tma.log 2>&1; echo "hbm tma rc=$?"; cat gpurun_out/hbm_plain.json gpurun_out/hbm_tma.json
+for combo in "0 0" "1 0" "1 1"; do
+  set -- $combo
   for cfg in "600 1700 60" "264 720 21" "1800 600 180" "100 400 20"; do
-    REST_B200_SPLIT_ORDER=$so timeout -k 10 300 python tools/prof_k.py $cfg 2>&1 | tail -1 | sed "s/^/split_order=$so /"
+    REST_B200_SPLIT_ORDER=$1 REST_B200_FUSED_SPLITK=$2 timeout -k 10 300 python tools/prof_k.py $cfg 2>&1 | tail -1 | sed "s/^/split_order=$1 fused=$2 /"
   done
 done | tee gpurun_out/k_timings.txt
 M=gpu__time_duration.sum,sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct,sm__warps_active.avg.pct_of_peak_sustained_active
