@@ -56,11 +56,14 @@ int rb_ctx_sync(rb_ctx *ctx);
 int rb_ctx_num_sms(rb_ctx *ctx);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 int64_t rb_ctx_launch_count(rb_ctx *ctx);
-/* ... of which launches of the bulk-tensor (TMA load -> shared memory -> TMA store) copy / transpose / pack / unpack kernels;
+/* ... of which launches of the bulk-tensor (TMA load -> shared memory -> TMA store) copy / transpose kernels;
  * the tests use it to prove that aligned operands take that path and not the plain-load fallback. */
 int64_t rb_ctx_tma_layout_count(rb_ctx *ctx);
 /* Select the GEMM implementation: 0 = auto (TMA+DMMA when alignment allows, else generic DMMA), 1 = force generic. */
 int rb_ctx_set_gemm_path(rb_ctx *ctx, int path);
+/* Select the copy / transpose implementation: 0 = 32-byte (LDG/STG.256) and plain-load kernels (default: measured faster),
+ * 1 = bulk-tensor kernels (TMA load -> shared memory -> TMA store) for operands TMA can describe. */
+int rb_ctx_set_layout_path(rb_ctx *ctx, int path);
 
 /* device memory helpers for hosts without their own allocator (Rust/C++ side) */
 int rb_dev_alloc(rb_ctx *ctx, int64_t bytes, void **out);

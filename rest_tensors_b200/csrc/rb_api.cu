@@ -54,13 +54,12 @@ extern "C" int rb_ctx_create(int device, rb_ctx **out)
     RB_CUDA(cudaEventCreate(&c->ev1));
     RB_CUDA(cudaMalloc((void **)&c->sched, 64 * 2 * sizeof(unsigned long long)));
     RB_CUDA(cudaMemset(c->sched, 0, 64 * 2 * sizeof(unsigned long long)));
-    RB_CUDA(cudaMalloc((void **)&c->tile_counters, 4 * RB_TILE_COUNTER_REGION * sizeof(unsigned)));
-    RB_CUDA(cudaMemset(c->tile_counters, 0, 4 * RB_TILE_COUNTER_REGION * sizeof(unsigned)));
     // cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link against libcuda).
     void *fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
     if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) c->encode_tiled = (rb_encode_tiled_fn)fn;
+    if (const char *lt = getenv("REST_B200_LAYOUT_TMA")) c->layout_path = atoi(lt) != 0 ? 1 : 0;
     else cudaGetLastError();
     *out = c;
     return RB_OK;
@@ -75,7 +74,6 @@ extern "C" int rb_ctx_destroy(rb_ctx *ctx)
     rb_eig_cache_free(ctx);
     for (int s = 0; s < 4; ++s) if (ctx->ws[s]) cudaFree(ctx->ws[s]);
     if (ctx->sched) cudaFree(ctx->sched);
-    if (ctx->tile_counters) cudaFree(ctx->tile_counters);
     for (int i = 0; i < 5; ++i) if (ctx->aux_ev[i]) cudaEventDestroy(ctx->aux_ev[i]);
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -109,6 +107,14 @@ extern "C" int rb_ctx_sync(rb_ctx *ctx)
 extern "C" int rb_ctx_num_sms(rb_ctx *ctx) { return ctx ? ctx->num_sms : 0; }
 extern "C" int64_t rb_ctx_launch_count(rb_ctx *ctx) { return ctx ? ctx->launches : 0; }
 extern "C" int64_t rb_ctx_tma_layout_count(rb_ctx *ctx) { return ctx ? ctx->tma_layout_launches : 0; }
+extern "C" int rb_ctx_set_layout_path(rb_ctx *ctx, int path)
+{
+    RB_REQUIRE(ctx, "rb_ctx_set_layout_path: ctx is NULL");
+    RB_REQUIRE(path == 0 || path == 1, "rb_ctx_set_layout_path: path must be 0 or 1");
+    ctx->layout_path = path;
+    return RB_OK;
+}
+
 extern "C" int rb_ctx_set_gemm_path(rb_ctx *ctx, int path)
 {
     RB_REQUIRE(ctx, "rb_ctx_set_gemm_path: ctx is NULL");

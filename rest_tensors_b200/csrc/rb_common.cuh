@@ -54,6 +54,7 @@ struct rb_ctx {
     i64 launches = 0;
     i64 tma_layout_launches = 0;   // launches of the bulk-tensor layout kernels (rb_layout_tma.cu)
     int gemm_path = 0;
+    int layout_path = 0;           // 0: 256-bit / plain-load layout kernels, 1: bulk-tensor (TMA) copy / transpose where eligible
     rb_encode_tiled_fn encode_tiled = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaStream_t aux_stream = nullptr;   // copy stream of the peer pipeline (rb_ri_mo_pq_peers), created on first use
@@ -61,12 +62,9 @@ struct rb_ctx {
     void *eig_cache = nullptr;           // instantiated Jacobi sweep graphs (rb_eig.cu), freed by rb_eig_cache_free
     unsigned long long *sched = nullptr; // GEMM tile-scheduler slots (64 x 2 words on the device), zero between launches
     unsigned sched_next = 0;             // slot of the next GEMM launch (round-robin)
-    unsigned *tile_counters = nullptr;   // fused split-K reduction: 4 regions of RB_TILE_COUNTER_REGION counters, zero between launches
     void *comm = nullptr;                // NCCL communicator (rb_comm.cu), NULL = a world of one
     int comm_rank = 0, comm_world = 1;
 };
-
-#define RB_TILE_COUNTER_REGION 32768 /* counters per region = 4096 tiles x 8 consumer warps */
 
 // Grow-only device workspace (synchronises the stream before freeing the old block).
 int rb_ws_reserve(rb_ctx *ctx, int slot, i64 bytes, void **out);
@@ -87,6 +85,25 @@ static inline bool rb_is_n(char c) { return c == 'N' || c == 'n'; }
 static inline bool rb_is_t(char c) { return c == 'T' || c == 't'; }
 static inline bool rb_is_u(char c) { return c == 'U' || c == 'u'; }
 static inline bool rb_is_l(char c) { return c == 'L' || c == 'l'; }
+
+// ---- 256-bit global accesses (sm_100: LDG.E.ENL2.256 / STG.E.ENL2.256) ------------------------------------------------
+// Measured on this pool's B200 (tools/micro/copy_bench.cu, profiles/r02_copy_microbench.md): a 1 read : 1 write SM kernel
+// moves 7.2 TB/s with 32-byte accesses, 8 of them in flight per thread and >= 16 CTAs per SM in the grid, against 6.3 TB/s
+// with 16-byte accesses and 6.5 TB/s for the driver's device-to-device memcpy.  Addresses must be 32-byte aligned.
+struct alignas(32) rb_d4 { double x, y, z, w; };
+#ifdef __CUDACC__
+__device__ __forceinline__ rb_d4 rb_ld256(const double *p)
+{
+    rb_d4 v;
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void rb_st256(double *p, const rb_d4 &v)
+{
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
+}
+#endif
+static inline bool rb_aligned32(const void *p) { return (((uintptr_t)p) & 31) == 0; }
 
 // ---- internal cross-TU entry points -------------------------------------------------------------------
 // Generic strided 3-D copy: dst[d0 + i*di + j*dj + k*dk] = src[s0 + i*si + j*sj + k*sk]

@@ -120,12 +120,12 @@ __global__ void __launch_bounds__(EIG_THREADS, 8) rb_jacobi_round_kernel(double 
     }
     block_sum3(a, b, c, red);
     if (!(fabs(c) > tol * (sqrt(a) * sqrt(b)))) return; // already orthogonal (also: zero column, NaN)
-    // A column negligible against the matrix (squared norm <= floor2 = (n eps |G|_F)^2, kept next to the rotation counter)
-    // belongs to the numerical null space of a rank-deficient matrix: what it holds is the rounding residue of earlier
-    // rotations, it shrinks by eps per sweep and never becomes orthogonal to the large columns in the RELATIVE sense of
-    // the test above (emulated: a 40+23 bipartite matrix rotates 391 such pairs per sweep for ever; 9 sweeps with the floor).
-    // It is zero to working precision and is left alone (the dgesvj treatment of negligible columns).  floor2 = 0 in the
-    // shifted (definite) mode.
+    // A column that has collapsed to nothing (squared norm <= floor2 = (eps^2 |G|_F)^2, kept next to the rotation counter)
+    // belongs to the null space of a rank-deficient matrix: what it holds is the rounding residue of earlier rotations, it
+    // shrinks by a factor eps per sweep and never becomes orthogonal to the large columns in the RELATIVE sense of the
+    // test above (emulated: a 40+23 bipartite matrix rotates 391 such pairs per sweep for ever; 11 sweeps with the floor).
+    // The floor sits 16 orders of magnitude below working precision, so every eigenvalue that means anything keeps its
+    // rotations.  floor2 = 0 in the shifted (definite) mode.
     const double floor2 = reinterpret_cast<const double *>(rotations)[1];
     if (a <= floor2 || b <= floor2) return;
     double cs, sn;
@@ -489,7 +489,7 @@ int jacobi_eig(rb_ctx *ctx, i64 n, const double *s, bool psd, double *work, std:
     }
     const i64 n_even = n + (n & 1);
     const double tol = std::sqrt((double)n) * 1.1102230246251565e-16;
-    // negligible-column floor of the unshifted mode (see rb_jacobi_round_kernel): (n eps |G|_F)^2, |G|_F is invariant under
+    // collapsed-column floor of the unshifted mode (see rb_jacobi_round_kernel): (eps^2 |G|_F)^2, |G|_F is invariant under
     // the rotations.  It lives in device memory (rot[1]) so that the cached sweep graphs stay valid from matrix to matrix.
     double floor2 = 0.0;
     if (psd) {
@@ -502,8 +502,8 @@ int jacobi_eig(rb_ctx *ctx, i64 n, const double *s, bool psd, double *work, std:
             if (!(x == x) || std::isinf(x)) { rb_set_error("eigen-solver: the matrix holds non-finite values"); return RB_ERR_INVALID; }
             fro2 += x * x;
         }
-        const double ne = (double)n * 2.220446049250313e-16;
-        floor2 = ne * ne * fro2;
+        const double e2 = 2.220446049250313e-16 * 2.220446049250313e-16;
+        floor2 = e2 * e2 * fro2;
     }
     RB_CUDA(cudaMemcpyAsync(rot + 1, &floor2, 8, cudaMemcpyHostToDevice, ctx->stream));
     RB_CUDA(cudaStreamSynchronize(ctx->stream)); // floor2 is a stack variable

@@ -58,7 +58,7 @@ constexpr int A_TILE_BYTES = BM * BK * 8;
 constexpr int B_TILE_BYTES = BN * BK * 8;
 constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
 constexpr int INFO_SLOTS = 8;  // tile-descriptor queue depth (> STAGES + 1: the producer is at most STAGES stages ahead)
-constexpr int INFO_INTS = 8;   // tm, tn, batch, split, full 32-deep stages, tail k8 blocks, warp-grid code, linear tile index
+constexpr int INFO_INTS = 8;   // tm, tn, batch, split, full 32-deep stages, tail k8 blocks, warp-grid code, unused
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 64 /*barriers*/ + INFO_SLOTS * INFO_INTS * 4;
 constexpr int NUM_CONSUMER_WARPS = 8;
 constexpr int NUM_THREADS = (NUM_CONSUMER_WARPS + 4) * 32; // 2 consumer warpgroups + 1 producer warpgroup
@@ -85,11 +85,6 @@ struct GemmParams {
     int pack_m;
     i64 bpb, total_blocks;     // 16-row blocks per batch, batch * bpb
     int same_ab;               // tri != 0 and A, B are the same matrix: diagonal tiles load one operand tile only
-    int split_major;           // work items enumerate the tiles of one k-range before the next k-range (see decode_item)
-    i64 tiles_total;           // tiles_per_batch * batch (packed M: tiles_per_batch)
-    // fused split-K reduction: every consumer warp counts the splits of its tile that have stored their partials; the warp
-    // that arrives last sums the partials of ITS blocks in split order (deterministic) and writes C -- no second kernel
-    unsigned *tile_counters;   // [tiles_total][8 warps], zero between launches (the last arrival re-arms), NULL = off
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------
@@ -143,12 +138,10 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b)
 }
 
 // work item -> (batch, tm, tn, split)
-__device__ __forceinline__ void decode_item(const GemmParams &p, i64 item, i64 &b, i64 &tm, i64 &tn, i64 &sp, i64 &tile)
+__device__ __forceinline__ void decode_item(const GemmParams &p, i64 item, i64 &b, i64 &tm, i64 &tn, i64 &sp)
 {
-    // split-major: concurrently running CTAs work on the SAME k-range of different tiles, so the operand panels of that
-    // k-range are shared through L2 (a SYRK over a 490 MB operand reads it once instead of once per tile row / column)
-    if (p.split_major) { sp = item / p.tiles_total; tile = item - sp * p.tiles_total; }
-    else { sp = item % p.splits; tile = item / p.splits; }
+    sp = item % p.splits;
+    i64 tile = item / p.splits;
     b = tile / p.tiles_per_batch;
     i64 t = tile - b * p.tiles_per_batch;
     if (p.tri == 0) {
@@ -382,90 +375,6 @@ __device__ __forceinline__ void store_block_checked(const double (&acc)[2][2][4]
     }
 }
 
-// acc(i, j) += the 16 x 16 block of a split-K partial, read with the addressing of store_block_checked (L1 bypassed: the
-// partials were written by other SMs).  Elements outside the matrix were never stored and are not read.
-template <bool A_K, bool B_K>
-__device__ __forceinline__ void load_block_add(double (&acc)[2][2][4][2][2], const int i, const int j, const double *cb, i64 ldc,
-                                               i64 row_blk, i64 col_blk, i64 m_lim, i64 n_lim, bool vec_ok, int row_t, int col_t)
-{
-#pragma unroll
-    for (int pb = 0; pb < 2; ++pb) {
-        const i64 col = col_blk + col_t + (B_K ? 8 * pb : pb);
-        if (col >= n_lim) continue;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const i64 row0 = row_blk + row_t + (A_K ? 8 * h : 2 * h);
-            const double *cp = cb + row0 + col * ldc;
-            double v0 = 0.0, v1 = 0.0;
-            if (row0 + 1 < m_lim && vec_ok) { const double2 v = __ldcg(reinterpret_cast<const double2 *>(cp)); v0 = v.x; v1 = v.y; }
-            else {
-                if (row0 < m_lim) v0 = __ldcg(cp);
-                if (row0 + 1 < m_lim) v1 = __ldcg(cp + 1);
-            }
-            if (A_K) { acc[i][h][j][pb][0] += v0; acc[i][h][j][pb][1] += v1; }
-            else { acc[i][0][j][pb][h] += v0; acc[i][1][j][pb][h] += v1; }
-        }
-    }
-}
-
-// Where a consumer warp's accumulators sit in the tile: a list of blocks (diagonal tiles of triangular products) or a
-// rectangle of ni x nj blocks starting at block (rb0, cb0).
-struct WarpTile {
-    bool diag;
-    int nown, lrow[5], lcol[5];
-    int ni, nj, rb0, cb0;
-};
-
-// Write (LOAD == false: alpha * acc + beta * C, honouring the triangle) or accumulate from (LOAD == true) the warp's part of
-// tile (tm, tn) of the matrix set cb (leading dimension ldc, batch stride cstride).
-template <bool A_K, bool B_K, bool PACK, bool LOAD>
-__device__ __forceinline__ void warp_tile_io(double (&acc)[2][2][4][2][2], const WarpTile &w, const GemmParams &p, double *cb,
-                                             i64 ldc, i64 cstride, double alpha, double beta, int tri, bool vec_ok, i64 tm,
-                                             i64 tn, int row_t, int col_t)
-{
-    if (w.diag) {
-#pragma unroll
-        for (int s = 0; s < 5; ++s) {
-            if (s >= w.nown) continue;
-            if (LOAD) load_block_add<A_K, B_K>(acc, s >> 2, s & 3, cb, ldc, tm * BM + w.lrow[s] * 16, tn * BN + w.lcol[s] * 16, p.m, p.n,
-                                               vec_ok, row_t, col_t);
-            else store_block_checked<A_K, B_K>(acc, s >> 2, s & 3, cb, ldc, tm * BM + w.lrow[s] * 16, tn * BN + w.lcol[s] * 16, p.m, p.n,
-                                               w.lrow[s] == w.lcol[s] ? tri : 0, vec_ok, alpha, beta, row_t, col_t);
-        }
-        return;
-    }
-    // one 16-row block at a time: a thread owns rows (2t, 2t+1) (+8) or (4t .. 4t+3) of each block -> 16-byte stores along M.
-    // A block whose 16 rows and all of the warp's columns lie inside the matrix (the common case) takes the lean path: no
-    // bounds / triangle tests, one IMAD per store, no scaling when alpha == 1.  The epilogue is pure issue overhead for the
-    // DMMA pipe, so it is kept as short as possible.
-    const i64 col_w = tn * BN + w.cb0 * 16;
-    const bool cols_in = col_w + w.nj * 16 <= p.n;
-    const bool lean_ok = !LOAD && vec_ok && tri == 0 && beta == 0.0 && cols_in;
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        if (i >= w.ni) continue;
-        double *cm = cb;       // matrix that holds this row block
-        i64 row_blk;           // first row of the block inside it
-        if (PACK) {
-            const i64 gb = tm * (BM / 16) + w.rb0 + i, bq = gb / p.bpb;
-            cm = cb + bq * cstride;
-            row_blk = (gb - bq * p.bpb) * 16;
-        } else row_blk = tm * BM + (w.rb0 + i) * 16;
-        if (lean_ok && row_blk + 16 <= p.m) {
-            double *pblk = cm + (row_blk + row_t) + (col_w + col_t) * ldc;
-            if (alpha == 1.0) store_lean_row<A_K, B_K, false>(acc, i, pblk, ldc, alpha, w.nj);
-            else store_lean_row<A_K, B_K, true>(acc, i, pblk, ldc, alpha, w.nj);
-            continue;
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (j >= w.nj) continue;
-            if (LOAD) load_block_add<A_K, B_K>(acc, i, j, cm, ldc, row_blk, col_w + j * 16, p.m, p.n, vec_ok, row_t, col_t);
-            else store_block_checked<A_K, B_K>(acc, i, j, cm, ldc, row_blk, col_w + j * 16, p.m, p.n, tri, vec_ok, alpha, beta, row_t, col_t);
-        }
-    }
-}
-
 // ---- the TMA + DMMA kernel --------------------------------------------------------------------------------------
 template <bool A_K, bool B_K, bool PACK>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -501,8 +410,8 @@ rb_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             i64 item = blockIdx.x;
             while (item < p.total_items) {
                 const i64 next = (i64)gridDim.x + (i64)atomicAdd(p.sched, 1ULL);
-                i64 b, tm, tn, sp, tile_lin;
-                decode_item(p, item, b, tm, tn, sp, tile_lin);
+                i64 b, tm, tn, sp;
+                decode_item(p, item, b, tm, tn, sp);
                 const i64 k_begin = sp * p.kper;
                 const i64 k_end = (k_begin + p.kper < p.k) ? k_begin + p.kper : p.k;
                 const int ba = p.a_batched ? (int)b : 0, bb = p.b_batched ? (int)b : 0;
@@ -540,7 +449,7 @@ rb_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(slot), "r"((uint32_t)tm), "r"((uint32_t)tn),
                                      "r"((uint32_t)b), "r"((uint32_t)sp) : "memory");
                         asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(slot + 16), "r"((uint32_t)((k_end - k_begin) / BK)),
-                                     "r"((uint32_t)(((k_end - k_begin) % BK + 7) >> 3)), "r"(grid_code), "r"((uint32_t)tile_lin) : "memory");
+                                     "r"((uint32_t)(((k_end - k_begin) % BK + 7) >> 3)), "r"(grid_code), "r"(0u) : "memory");
                         first = false;
                     }
                     mbar_expect_tx(full, tx_bytes);
@@ -646,32 +555,43 @@ rb_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
                     for (int pb = 0; pb < 2; ++pb) { acc[i][pa][j][pb][0] = 0.0; acc[i][pa][j][pb][1] = 0.0; }
 
-        WarpTile wt;
-        wt.diag = ((ucode >> 20) & 1u) != 0;
-        wt.nown = 0; wt.ni = 0; wt.nj = 0; wt.rb0 = 0; wt.cb0 = 0;
-#pragma unroll
-        for (int s = 0; s < 5; ++s) { wt.lrow[s] = 0; wt.lcol[s] = 0; }
+        // output matrix of this item
+        double *cb;
+        i64 ldc, cstride;
+        double alpha, beta;
+        if (p.splits > 1) {
+            cstride = p.n * p.ldp;
+            cb = p.partial + (sp * p.batch + bidx) * cstride;
+            ldc = p.ldp; alpha = 1.0; beta = 0.0;
+        } else {
+            cstride = p.stride_c;
+            cb = p.c + bidx * cstride;
+            ldc = p.ldc; alpha = p.alpha; beta = p.beta;
+        }
+        const bool vec_ok = ((ldc & 1) == 0) && ((((uintptr_t)cb) & 15) == 0) && (!PACK || (cstride & 1) == 0);
+        const int tri = (p.splits > 1) ? 0 : p.tri;
 
-        if (wt.diag) {
+        if ((ucode >> 20) & 1u) {
             // ---- diagonal tile of a triangular product: this warp's share of the mb(mb+1)/2 blocks on or above (tri 1)
             //      / below (tri 2) the diagonal, dealt round-robin: block e = warp + 8 s, e = hi(hi+1)/2 + lo, lo <= hi ----
             const int nblocks = mb * (mb + 1) / 2;
-            wt.nown = warp < nblocks ? (nblocks - warp + 7) >> 3 : 0;
+            const int nown = warp < nblocks ? (nblocks - warp + 7) >> 3 : 0;
             uint32_t la[5], lb[5];
+            int lrow[5], lcol[5];
 #pragma unroll
             for (int s = 0; s < 5; ++s) {
                 int e = warp + 8 * s, hi = 0;
                 if (e >= nblocks) e = 0;
                 while ((hi + 1) * (hi + 2) / 2 <= e) ++hi;
                 const int lo = e - hi * (hi + 1) / 2;
-                wt.lrow[s] = (p.tri == 1) ? lo : hi;
-                wt.lcol[s] = (p.tri == 1) ? hi : lo;
-                la[s] = (uint32_t)wt.lrow[s] * (A_K ? (16 * 64) : (BK * 128));
-                lb[s] = (uint32_t)wt.lcol[s] * (B_K ? (16 * 64) : (BK * 128));
+                lrow[s] = (p.tri == 1) ? lo : hi;
+                lcol[s] = (p.tri == 1) ? hi : lo;
+                la[s] = (uint32_t)lrow[s] * (A_K ? (16 * 64) : (BK * 128));
+                lb[s] = (uint32_t)lcol[s] * (B_K ? (16 * 64) : (BK * 128));
             }
             const bool b_from_a = p.same_ab != 0;
 #define RB_RUN_LIST(NB_) run_tile_list<A_K, B_K, NB_>(acc, smem_base, bar_base, stage, phase, la, lb, a_off, b_off, full_steps, tail_kb, lane, b_from_a)
-            switch (wt.nown) { // warp-uniform
+            switch (nown) { // warp-uniform
             case 5: RB_RUN_LIST(5); break;
             case 4: RB_RUN_LIST(4); break;
             case 3: RB_RUN_LIST(3); break;
@@ -680,65 +600,65 @@ rb_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             default: RB_RUN_LIST(0); break;
             }
 #undef RB_RUN_LIST
-        } else {
-            const int gi = warp & ((1 << lgm) - 1), gj = warp >> lgm;
-            wt.rb0 = gi * rpg; wt.cb0 = gj * cpg;
-            int ni = mb - wt.rb0; ni = ni < 0 ? 0 : (ni > rpg ? rpg : ni);
-            int nj = nbk - wt.cb0; nj = nj < 0 ? 0 : (nj > cpg ? cpg : nj);
-            if (ni == 0 || nj == 0) { ni = 0; nj = 0; }
-            wt.ni = ni; wt.nj = nj;
-            const uint32_t a_blk = (uint32_t)wt.rb0 * (A_K ? (16 * 64) : (BK * 128));
-            const uint32_t b_blk = (uint32_t)wt.cb0 * (B_K ? (16 * 64) : (BK * 128));
-#define RB_RUN(NI_, NJ_) run_tile<A_K, B_K, NI_, NJ_>(acc, smem_base, bar_base, stage, phase, a_blk, b_blk, a_off, b_off, full_steps, tail_kb, lane)
-            switch (ni * 8 + nj) { // warp-uniform
-            case 2 * 8 + 4: RB_RUN(2, 4); break;
-            case 2 * 8 + 3: RB_RUN(2, 3); break;
-            case 2 * 8 + 2: RB_RUN(2, 2); break;
-            case 2 * 8 + 1: RB_RUN(2, 1); break;
-            case 1 * 8 + 4: RB_RUN(1, 4); break;
-            case 1 * 8 + 3: RB_RUN(1, 3); break;
-            case 1 * 8 + 2: RB_RUN(1, 2); break;
-            case 1 * 8 + 1: RB_RUN(1, 1); break;
-            default: RB_RUN(0, 1); break; // this warp has no valid block in this tile
+#pragma unroll
+            for (int s = 0; s < 5; ++s) {
+                if (s >= nown) continue;
+                store_block_checked<A_K, B_K>(acc, s >> 2, s & 3, cb, ldc, tm * BM + lrow[s] * 16, tn * BN + lcol[s] * 16, p.m, p.n,
+                                              lrow[s] == lcol[s] ? tri : 0, vec_ok, alpha, beta, row_t, col_t);
             }
-#undef RB_RUN
+            continue;
         }
 
-        // ---- output ----
-        if (p.splits > 1) {
-            // this split's partial (whole blocks, no triangle): [split][batch][n][ldp]
-            const i64 pstride = p.n * p.ldp;
-            const bool pvec = !PACK || (pstride & 1) == 0; // ldp is even and the workspace 256-byte aligned
-            warp_tile_io<A_K, B_K, PACK, false>(acc, wt, p, p.partial + (sp * p.batch + bidx) * pstride, p.ldp, pstride, 1.0, 0.0, 0,
-                                                pvec, tm, tn, row_t, col_t);
-            if (p.tile_counters == nullptr) continue; // rb_splitk_reduce_kernel follows
-            // Fused reduction: the warp that stores the LAST partial of its blocks sums all of them in split order (the
-            // same warp index owns the same blocks in every split of a tile) and writes C.
-            __threadfence();
-            __syncwarp();
-            unsigned prev = 0;
-            unsigned *cnt = p.tile_counters + ((size_t)upad * NUM_CONSUMER_WARPS + warp);
-            if (lane == 0) prev = atomicAdd(cnt, 1u);
-            prev = __shfl_sync(0xffffffffu, prev, 0);
-            if (prev != (unsigned)p.splits - 1u) continue;
-            if (lane == 0) *cnt = 0u; // re-arm for the next launch
-            __threadfence();
-#pragma unroll
-            for (int i = 0; i < 2; ++i)
-#pragma unroll
-                for (int pa = 0; pa < 2; ++pa)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-#pragma unroll
-                        for (int pb = 0; pb < 2; ++pb) { acc[i][pa][j][pb][0] = 0.0; acc[i][pa][j][pb][1] = 0.0; }
-            for (i64 s2 = 0; s2 < p.splits; ++s2)
-                warp_tile_io<A_K, B_K, PACK, true>(acc, wt, p, p.partial + (s2 * p.batch + bidx) * pstride, p.ldp, pstride, 1.0, 0.0, 0,
-                                                   pvec, tm, tn, row_t, col_t);
+        const int gi = warp & ((1 << lgm) - 1), gj = warp >> lgm;
+        const int rb0 = gi * rpg, cb0 = gj * cpg;
+        int ni = mb - rb0; ni = ni < 0 ? 0 : (ni > rpg ? rpg : ni);
+        int nj = nbk - cb0; nj = nj < 0 ? 0 : (nj > cpg ? cpg : nj);
+        if (ni == 0 || nj == 0) { ni = 0; nj = 0; }
+        const uint32_t a_blk = (uint32_t)rb0 * (A_K ? (16 * 64) : (BK * 128));
+        const uint32_t b_blk = (uint32_t)cb0 * (B_K ? (16 * 64) : (BK * 128));
+
+#define RB_RUN(NI_, NJ_) run_tile<A_K, B_K, NI_, NJ_>(acc, smem_base, bar_base, stage, phase, a_blk, b_blk, a_off, b_off, full_steps, tail_kb, lane)
+        switch (ni * 8 + nj) { // warp-uniform
+        case 2 * 8 + 4: RB_RUN(2, 4); break;
+        case 2 * 8 + 3: RB_RUN(2, 3); break;
+        case 2 * 8 + 2: RB_RUN(2, 2); break;
+        case 2 * 8 + 1: RB_RUN(2, 1); break;
+        case 1 * 8 + 4: RB_RUN(1, 4); break;
+        case 1 * 8 + 3: RB_RUN(1, 3); break;
+        case 1 * 8 + 2: RB_RUN(1, 2); break;
+        case 1 * 8 + 1: RB_RUN(1, 1); break;
+        default: RB_RUN(0, 1); break; // this warp has no valid block in this tile
         }
-        {
-            double *cb = p.c + bidx * p.stride_c;
-            const bool vec_ok = ((p.ldc & 1) == 0) && ((((uintptr_t)cb) & 15) == 0) && (!PACK || (p.stride_c & 1) == 0);
-            warp_tile_io<A_K, B_K, PACK, false>(acc, wt, p, cb, p.ldc, p.stride_c, p.alpha, p.beta, p.tri, vec_ok, tm, tn, row_t, col_t);
+#undef RB_RUN
+
+        // ---- epilogue, one 16-row block at a time: a thread owns rows (2t, 2t+1) (+8) or (4t .. 4t+3) of each block ->
+        //      16-byte stores along M.  A block whose 16 rows and all of the warp's columns lie inside the matrix (the
+        //      common case) takes the lean path: no bounds / triangle tests, one IMAD per store, no scaling when alpha == 1.
+        //      The epilogue is pure issue overhead for the DMMA pipe, so it is kept as short as possible. ----
+        const i64 col_w = tn * BN + cb0 * 16;
+        const bool cols_in = col_w + nj * 16 <= p.n;
+        const bool lean_ok = vec_ok && tri == 0 && beta == 0.0 && cols_in;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            if (i >= ni) continue;
+            double *cm = cb;       // matrix that holds this row block
+            i64 row_blk;           // first row of the block inside it
+            if (PACK) {
+                const i64 gb = tm * (BM / 16) + rb0 + i, bq = gb / p.bpb;
+                cm = cb + bq * cstride;
+                row_blk = (gb - bq * p.bpb) * 16;
+            } else row_blk = tm * BM + (rb0 + i) * 16;
+            if (lean_ok && row_blk + 16 <= p.m) {
+                double *pblk = cm + (row_blk + row_t) + (col_w + col_t) * ldc;
+                if (alpha == 1.0) store_lean_row<A_K, B_K, false>(acc, i, pblk, ldc, alpha, nj);
+                else store_lean_row<A_K, B_K, true>(acc, i, pblk, ldc, alpha, nj);
+                continue;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (j >= nj) continue;
+                store_block_checked<A_K, B_K>(acc, i, j, cm, ldc, row_blk, col_w + j * 16, p.m, p.n, tri, vec_ok, alpha, beta, row_t, col_t);
+            }
         }
     }
 }
@@ -1062,9 +982,6 @@ int rb_gemm_core(rb_ctx *ctx, bool ta, bool tb, i64 m, i64 n, i64 k, double alph
         splits = rb_cdiv(k, kper);
         p.splits = splits; p.kper = kper;
         p.total_items = tiles * splits;
-        p.tiles_total = tiles;
-        static const int split_order = [] { const char *e = getenv("REST_B200_SPLIT_ORDER"); return e ? atoi(e) : 1; }();
-        p.split_major = (splits > 1 && split_order) ? 1 : 0;
         p.alpha = alpha; p.beta = beta; p.c = c; p.ldc = ldc; p.stride_c = stride_c; p.tri = tri;
         p.partial = nullptr; p.ldp = (m + 1) & ~(i64)1;
         p.a_batched = a_batched ? 1 : 0; p.b_batched = b_batched ? 1 : 0;
@@ -1073,15 +990,10 @@ int rb_gemm_core(rb_ctx *ctx, bool ta, bool tb, i64 m, i64 n, i64 k, double alph
         // one of 64 self-re-arming scheduler slots per launch: launches of one context may overlap (the caller can
         // move the context between streams) without sharing a work counter
         p.sched = ctx->sched + 2 * (ctx->sched_next++ & 63);
-        p.tile_counters = nullptr;
         if (splits > 1) {
             void *ws;
             RB_TRY(rb_ws_reserve(ctx, 1, splits * batch * n * p.ldp * 8, &ws));
             p.partial = (double *)ws;
-            // fused reduction: one of 4 counter regions per launch (launches of one context may overlap on different streams)
-            static const int fused = [] { const char *e = getenv("REST_B200_FUSED_SPLITK"); return e ? atoi(e) : 1; }();
-            if (fused && ctx->tile_counters && tiles * NUM_CONSUMER_WARPS <= RB_TILE_COUNTER_REGION)
-                p.tile_counters = ctx->tile_counters + (size_t)(ctx->sched_next & 3) * RB_TILE_COUNTER_REGION;
         }
         int grid = (int)(p.total_items < ctx->num_sms ? p.total_items : ctx->num_sms);
         if (a_k && b_k) RB_TRY((launch_tma<true, true, false>(ctx, tmA, tmB, p, grid)));
@@ -1093,7 +1005,7 @@ int rb_gemm_core(rb_ctx *ctx, bool ta, bool tb, i64 m, i64 n, i64 k, double alph
             if (packed) RB_TRY((launch_tma<false, false, true>(ctx, tmA, tmB, p, grid)));
             else RB_TRY((launch_tma<false, false, false>(ctx, tmA, tmB, p, grid)));
         }
-        if (splits > 1 && p.tile_counters == nullptr) {
+        if (splits > 1) {
             i64 total = m * n * batch;
             i64 blocks = rb_cdiv(total, 256);
             i64 cap = (i64)ctx->num_sms * 16;

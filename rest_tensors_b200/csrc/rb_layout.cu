@@ -42,10 +42,78 @@ __global__ void __launch_bounds__(256) rb_pack_upper_panel_kernel(const double *
     }
 }
 
+
+// 256-bit form (n % 4 == 0, 32-byte aligned `full`): one CTA per 64 x 64 tile on or above the diagonal.  The tile is read with
+// 32-byte loads along i (a thread takes a 4 x 4 micro-tile, 16 lanes cover 64 consecutive rows of a column) and parked in
+// shared memory; then each warp writes 8 of the 64 packed runs.  A run starts at the 8-byte offset j(j+1)/2 + i0, so it is
+// written as 16-byte pairs from whichever parity is aligned (plus one single double at each end): every store instruction
+// of a warp covers one contiguous run, which is what keeps the write path efficient (a first version that stored each
+// thread's 4 elements on its own -- 16 scattered sectors per instruction -- ran at 0.9x the 8-byte kernel it replaced).
+__global__ void __launch_bounds__(256) rb_pack_upper4_kernel(const double *__restrict__ full, double *__restrict__ packed, i64 n,
+                                                             i64 full_slab, i64 packed_slab, i64 pairs)
+{
+    __shared__ __align__(32) double tile[64][64]; // [column jj][row ii]
+    const i64 slab = blockIdx.x / pairs, p = blockIdx.x - slab * pairs;
+    i64 tj = (i64)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
+    while (tj * (tj + 1) / 2 > p) --tj;
+    while ((tj + 1) * (tj + 2) / 2 <= p) ++tj;
+    const i64 ti = p - tj * (tj + 1) / 2;
+    const double *f = full + slab * full_slab;
+    double *pk = packed + slab * packed_slab;
+    const i64 i0 = ti * 64, j0 = tj * 64;
+    {
+        const int lr = threadIdx.x & 15, lc = threadIdx.x >> 4;
+        const i64 i = i0 + 4 * lr;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const i64 j = j0 + 4 * lc + e;
+            if (i < n && j < n && i <= j) { // the quad holds at least one element on or above the diagonal
+                const rb_d4 v = rb_ld256(f + i + j * n);
+                double *t = &tile[4 * lc + e][4 * lr];
+                *reinterpret_cast<double2 *>(t) = make_double2(v.x, v.y);
+                *reinterpret_cast<double2 *>(t + 2) = make_double2(v.z, v.w);
+            }
+        }
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const int jj = warp * 8 + c;
+        const i64 j = j0 + jj;
+        if (j >= n) break;
+        i64 cnt = j - i0 + 1; // rows i0 .. min(i0 + 63, j) of column j
+        if (cnt > 64) cnt = 64;
+        double *dst = pk + j * (j + 1) / 2 + i0;
+        const double *src = tile[jj];
+        if ((((uintptr_t)dst) & 15) == 0) {
+            const int e = 2 * lane;
+            if (e + 1 < cnt) *reinterpret_cast<double2 *>(dst + e) = *reinterpret_cast<const double2 *>(src + e);
+            else if (e < cnt) dst[e] = src[e];
+        } else {
+            const int e = 2 * lane + 1; // pairs (1,2), (3,4), ... are the aligned ones; element 0 goes alone
+            if (lane == 0) dst[0] = src[0];
+            if (e + 1 < cnt) *reinterpret_cast<double2 *>(dst + e) = make_double2(src[e], src[e + 1]);
+            else if (e < cnt) dst[e] = src[e];
+        }
+    }
+}
+
 static int launch_pack(rb_ctx *ctx, const double *full, i64 n, i64 nslab, double *packed)
 {
     if (n == 0 || nslab == 0) return RB_OK;
     i64 np = n * (n + 1) / 2;
+    if ((n & 3) == 0 && rb_aligned32(full) && n >= 64) { // 256-bit loads; every slab starts 32-byte aligned (n^2 % 4 == 0)
+        const i64 nt = rb_cdiv(n, 64), pairs = nt * (nt + 1) / 2;
+        for (i64 z0 = 0; z0 < nslab;) {
+            i64 nz = nslab - z0;
+            if (nz * pairs > 2147483647LL) nz = 2147483647LL / pairs;
+            rb_pack_upper4_kernel<<<(unsigned)(nz * pairs), 256, 0, ctx->stream>>>(full + z0 * n * n, packed + z0 * np, n, n * n, np, pairs);
+            RB_LAUNCHED(ctx);
+            z0 += nz;
+        }
+        return RB_OK;
+    }
     for (i64 z0 = 0; z0 < nslab; z0 += 65535) {
         unsigned nz = (unsigned)((nslab - z0) < 65535 ? (nslab - z0) : 65535);
         if (n >= 512) {
@@ -150,6 +218,106 @@ __global__ void __launch_bounds__(256) rb_unpack_upper_kernel(const double *__re
     }
 }
 
+
+// ---- 32-byte exchange through shared memory (shared by the 256-bit unpack and transpose kernels) ---------------------
+// A 64 x 64 tile is 16 x 16 micro-tiles of 4 x 4; thread (lr, lc) = (tid & 15, tid >> 4) owns micro-tile rows 4 lr .. 4 lr + 3,
+// columns 4 lc .. 4 lc + 3.  After the register transpose it holds four 32-byte units u[e] = (column quad lc of TRANSPOSED
+// row R = 4 lr + e).  They go to slot [R][lc ^ lr] (and the two 16-byte halves of a unit swap places when bit 2 of lr and lc
+// differ), which makes the writes (16 lanes: same lc, all lr) and the reads (16 lanes: same R, all lc) both conflict-free.
+__device__ __forceinline__ void rb_xchg_write(double *sm, int lr, int lc, int e, const rb_d4 &u)
+{
+    const int R = 4 * lr + e, col = lc ^ lr, swap = ((lr >> 2) ^ (lc >> 2)) & 1;
+    double *slot = sm + (R * 16 + col) * 4;
+    *reinterpret_cast<double2 *>(slot + 2 * swap) = make_double2(u.x, u.y);
+    *reinterpret_cast<double2 *>(slot + 2 * (1 - swap)) = make_double2(u.z, u.w);
+}
+__device__ __forceinline__ rb_d4 rb_xchg_read(const double *sm, int R, int lc)
+{
+    const int lr = (R >> 2) & 15, col = lc ^ lr, swap = ((lr >> 2) ^ (lc >> 2)) & 1;
+    const double *slot = sm + (R * 16 + col) * 4;
+    const double2 a = *reinterpret_cast<const double2 *>(slot + 2 * swap);
+    const double2 b = *reinterpret_cast<const double2 *>(slot + 2 * (1 - swap));
+    rb_d4 u; u.x = a.x; u.y = a.y; u.z = b.x; u.w = b.y;
+    return u;
+}
+
+// four consecutive packed elements starting at an 8-byte aligned address: 16-byte loads where the parity allows
+__device__ __forceinline__ rb_d4 rb_load_run4(const double *src)
+{
+    rb_d4 v;
+    if ((((uintptr_t)src) & 15) == 0) {
+        const double2 a = *reinterpret_cast<const double2 *>(src), b = *reinterpret_cast<const double2 *>(src + 2);
+        v.x = a.x; v.y = a.y; v.z = b.x; v.w = b.y;
+    } else {
+        const double2 m = *reinterpret_cast<const double2 *>(src + 1);
+        v.x = src[0]; v.y = m.x; v.z = m.y; v.w = src[3];
+    }
+    return v;
+}
+
+// 256-bit unpack (n % 4 == 0, `full` 32-byte aligned): one CTA per 64 x 64 tile pair (ti <= tj).  A thread reads the packed
+// 4 x 4 micro-tile once, stores it to the upper position with four 32-byte stores (coalesced along i), transposes it in
+// registers and hands the 32-byte units through shared memory to the lanes that store the mirrored tile, coalesced along j.
+__global__ void __launch_bounds__(256) rb_unpack_upper4_kernel(const double *__restrict__ packed, double *__restrict__ full, i64 n)
+{
+    __shared__ __align__(32) double sm[64 * 64];
+    const i64 p = blockIdx.x;
+    i64 tj = (i64)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
+    while (tj * (tj + 1) / 2 > p) --tj;
+    while ((tj + 1) * (tj + 2) / 2 <= p) ++tj;
+    const i64 ti = p - tj * (tj + 1) / 2;
+    const bool diag = ti == tj;
+    const int lr = threadIdx.x & 15, lc = threadIdx.x >> 4;
+    const i64 i = ti * 64 + 4 * lr, j0 = tj * 64 + 4 * lc;
+    // diagonal tile: micro-tiles below the diagonal (lr > lc) are produced by the mirror of (lc, lr)
+    const bool mine = i < n && j0 < n && (!diag || lr <= lc);
+    rb_d4 v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { v[e].x = 0.0; v[e].y = 0.0; v[e].z = 0.0; v[e].w = 0.0; }
+    if (mine) {
+        if (!diag || lr < lc) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { const i64 j = j0 + e; v[e] = rb_load_run4(packed + j * (j + 1) / 2 + i); }
+        } else { // the 4 x 4 block on the diagonal: rows i .. j of column j, mirrored inside the registers
+            double m[4][4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const i64 j = j0 + e;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) m[e][k] = (k <= e) ? packed[j * (j + 1) / 2 + i + k] : 0.0;
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                v[e].x = m[e][0];
+                v[e].y = e >= 1 ? m[e][1] : m[1][e];
+                v[e].z = e >= 2 ? m[e][2] : m[2][e];
+                v[e].w = e >= 3 ? m[e][3] : m[3][e];
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) rb_st256(full + i + (j0 + e) * n, v[e]);
+    }
+    // mirrored tile: full[j0 .. j0+3 + (i + k) * n] = (v[0].k, v[1].k, v[2].k, v[3].k)
+    const bool give = mine && (!diag || lr < lc);
+    if (give) {
+        rb_d4 u;
+        u.x = v[0].x; u.y = v[1].x; u.z = v[2].x; u.w = v[3].x; rb_xchg_write(sm, lr, lc, 0, u);
+        u.x = v[0].y; u.y = v[1].y; u.z = v[2].y; u.w = v[3].y; rb_xchg_write(sm, lr, lc, 1, u);
+        u.x = v[0].z; u.y = v[1].z; u.z = v[2].z; u.w = v[3].z; rb_xchg_write(sm, lr, lc, 2, u);
+        u.x = v[0].w; u.y = v[1].w; u.z = v[2].w; u.w = v[3].w; rb_xchg_write(sm, lr, lc, 3, u);
+    }
+    __syncthreads();
+    const int qc = threadIdx.x & 15; // column quad (along j) this lane stores
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass) {
+        const int R = (threadIdx.x >> 4) + 16 * pass;   // row of the upper tile = column of the mirrored one
+        const i64 col = ti * 64 + R, row = tj * 64 + 4 * qc;
+        if (col >= n || row >= n) continue;
+        if (diag && !((R >> 2) < qc)) continue;        // only the slots strictly-upper micro-tiles wrote
+        rb_st256(full + row + col * n, rb_xchg_read(sm, R, qc));
+    }
+}
+
 extern "C" int rb_unpack_upper(rb_ctx *ctx, const double *packed, int64_t n, double *full)
 {
     RB_REQUIRE(ctx && n >= 0, "rb_unpack_upper: bad arguments");
@@ -159,7 +327,9 @@ extern "C" int rb_unpack_upper(rb_ctx *ctx, const double *packed, int64_t n, dou
     i64 nt = rb_cdiv(n, UT);
     i64 pairs = nt * (nt + 1) / 2;
     RB_REQUIRE(pairs < 2147483647LL, "rb_unpack_upper: n too large");
-    if ((n & 1) == 0 && (((uintptr_t)full) & 15) == 0)
+    if ((n & 3) == 0 && rb_aligned32(full) && n >= 64)
+        rb_unpack_upper4_kernel<<<(unsigned)pairs, 256, 0, ctx->stream>>>(packed, full, n);
+    else if ((n & 1) == 0 && (((uintptr_t)full) & 15) == 0)
         rb_unpack_upper_kernel<true><<<(unsigned)pairs, 256, 0, ctx->stream>>>(packed, full, n);
     else
         rb_unpack_upper_kernel<false><<<(unsigned)pairs, 256, 0, ctx->stream>>>(packed, full, n);
@@ -229,7 +399,15 @@ __global__ void __launch_bounds__(256) rb_copy3d_kernel(const double *__restrict
         const double *s = src + j * sj + k * sk;
         double *d = dst + j * dj + k * dk;
         i64 i = lane;
-        if (VEC == 2) {
+        if (VEC == 4) {
+            for (; i + 3 * lanes < niv; i += 4 * lanes) {
+                const rb_d4 v0 = rb_ld256(s + 4 * i), v1 = rb_ld256(s + 4 * (i + lanes)), v2 = rb_ld256(s + 4 * (i + 2 * lanes)),
+                            v3 = rb_ld256(s + 4 * (i + 3 * lanes));
+                rb_st256(d + 4 * i, v0); rb_st256(d + 4 * (i + lanes), v1); rb_st256(d + 4 * (i + 2 * lanes), v2);
+                rb_st256(d + 4 * (i + 3 * lanes), v3);
+            }
+            for (; i < niv; i += lanes) rb_st256(d + 4 * i, rb_ld256(s + 4 * i));
+        } else if (VEC == 2) {
             const double2 *s2 = reinterpret_cast<const double2 *>(s);
             double2 *d2 = reinterpret_cast<double2 *>(d);
             for (; i + 3 * lanes < niv; i += 4 * lanes) {
@@ -247,15 +425,67 @@ __global__ void __launch_bounds__(256) rb_copy3d_kernel(const double *__restrict
     }
 }
 
+// one contiguous run of niv 32-byte vectors: CTA c takes the 1024-vector chunks c, c + grid, ...; 8 loads in flight per thread
+__global__ void __launch_bounds__(256) rb_copy_flat4_kernel(const double *__restrict__ s, double *__restrict__ d, i64 niv, i64 chunks)
+{
+    for (i64 c = blockIdx.x; c < chunks; c += 2 * (i64)gridDim.x) {
+        const i64 a = c * 1024 + threadIdx.x, b = (c + gridDim.x) * 1024 + threadIdx.x;
+        const bool second = c + gridDim.x < chunks;
+        rb_d4 va[4], vb[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) if (a + u * 256 < niv) va[u] = rb_ld256(s + 4 * (a + u * 256));
+        if (second) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (b + u * 256 < niv) vb[u] = rb_ld256(s + 4 * (b + u * 256));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) if (a + u * 256 < niv) rb_st256(d + 4 * (a + u * 256), va[u]);
+        if (second) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (b + u * 256 < niv) rb_st256(d + 4 * (b + u * 256), vb[u]);
+        }
+    }
+}
+
 int rb_copy3d(rb_ctx *ctx, const double *src, i64 s0, i64 si, i64 sj, i64 sk, double *dst, i64 d0, i64 di, i64 dj,
               i64 dk, i64 ni, i64 nj, i64 nk)
 {
     if (ni <= 0 || nj <= 0 || nk <= 0) return RB_OK;
     const double *s = src + s0;
     double *d = dst + d0;
-    if (si == 1 && di == 1) { // unit-stride runs on both sides: bulk-tensor copy when TMA can describe the operands
+    if (si == 1 && di == 1) {
+        // rows that follow each other without a gap on both sides are one longer row (whole slabs, whole tensors)
+        if (sj == ni && dj == ni && nj > 1) { ni *= nj; nj = nk; sj = sk; dj = dk; nk = 1; sk = 0; dk = 0; }
+        if (sj == ni && dj == ni && nj > 1) { ni *= nj; nj = 1; }
+        // unit-stride runs on both sides: bulk-tensor copy when requested and TMA can describe the operands
         const int st = rb_tma_copy3d(ctx, s, sj, sk, d, dj, dk, ni, nj, nk);
         if (st != RB_TMA_NOT_ELIGIBLE) return st;
+    }
+    const bool vec4 = si == 1 && di == 1 && (ni % 4 == 0) && (sj % 4 == 0) && (sk % 4 == 0) && (dj % 4 == 0) && (dk % 4 == 0) &&
+                      rb_aligned32(s) && rb_aligned32(d);
+    if (vec4) {
+        const i64 niv = ni / 4;
+        int lg = 0;
+        while (lg < 8 && ((i64)2 << lg) * 4 <= niv) ++lg;
+        if (lg < 3 && niv >= 8) lg = 3;
+        const i64 rows = nj * nk, rows_per_cta = 256 >> lg;
+        // one row: split it over the CTAs (each takes whole 4-load passes of 256 lanes)
+        if (rows == 1 && niv >= 4096) {
+            const i64 per = 1024; // vectors per CTA pass (256 lanes x 4 loads)
+            i64 blocks = rb_cdiv(niv, per);
+            const i64 cap = (i64)ctx->num_sms * 32;
+            const i64 chunks = blocks;
+            if (blocks > cap) blocks = cap;
+            rb_copy_flat4_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(s, d, niv, chunks);
+            RB_LAUNCHED(ctx);
+            return RB_OK;
+        }
+        i64 blocks = rb_cdiv(rows, rows_per_cta);
+        const i64 cap = (i64)ctx->num_sms * 32;
+        if (blocks > cap) blocks = cap;
+        rb_copy3d_kernel<4><<<(unsigned)blocks, 256, 0, ctx->stream>>>(s, si, sj, sk, d, di, dj, dk, ni, nj, nk, lg);
+        RB_LAUNCHED(ctx);
+        return RB_OK;
     }
     bool vec = si == 1 && di == 1 && (ni % 2 == 0) && (sj % 2 == 0) && (sk % 2 == 0) && (dj % 2 == 0) &&
                (dk % 2 == 0) && (((uintptr_t)s & 15) == 0) && (((uintptr_t)d & 15) == 0);
@@ -404,6 +634,42 @@ __global__ void __launch_bounds__(256) rb_transpose_kernel(const double *__restr
     }
 }
 
+
+// 256-bit form (all extents and strides multiples of 4, 32-byte aligned bases): a thread loads a 4 x 4 micro-tile with four
+// 32-byte loads along r (16 lanes cover 64 consecutive r of one column), transposes it in registers, and the 32-byte units
+// change hands through shared memory (rb_xchg_*) so that the four 32-byte stores along c are coalesced as well.
+__global__ void __launch_bounds__(256) rb_transpose4_kernel(const double *__restrict__ in, i64 ics, i64 ibs, double *__restrict__ out,
+                                                            i64 ors, i64 obs, i64 nr, i64 nc, i64 tiles_r, i64 tiles_c, i64 total_tiles)
+{
+    __shared__ __align__(32) double sm[64 * 64];
+    const int lr = threadIdx.x & 15, lc = threadIdx.x >> 4;
+    for (i64 t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const i64 tr = t % tiles_r, rest = t / tiles_r;
+        const i64 tc = rest % tiles_c, b = rest / tiles_c;
+        const double *ib = in + b * ibs;
+        double *ob = out + b * obs;
+        const i64 r = tr * 64 + 4 * lr, c = tc * 64 + 4 * lc;
+        if (r < nr && c < nc) { // nr, nc are multiples of 4: a micro-tile is inside or outside as a whole
+            const rb_d4 v0 = rb_ld256(ib + r + c * ics), v1 = rb_ld256(ib + r + (c + 1) * ics), v2 = rb_ld256(ib + r + (c + 2) * ics),
+                        v3 = rb_ld256(ib + r + (c + 3) * ics);
+            rb_d4 u;
+            u.x = v0.x; u.y = v1.x; u.z = v2.x; u.w = v3.x; rb_xchg_write(sm, lr, lc, 0, u);
+            u.x = v0.y; u.y = v1.y; u.z = v2.y; u.w = v3.y; rb_xchg_write(sm, lr, lc, 1, u);
+            u.x = v0.z; u.y = v1.z; u.z = v2.z; u.w = v3.z; rb_xchg_write(sm, lr, lc, 2, u);
+            u.x = v0.w; u.y = v1.w; u.z = v2.w; u.w = v3.w; rb_xchg_write(sm, lr, lc, 3, u);
+        }
+        __syncthreads();
+        const int qc = threadIdx.x & 15;
+#pragma unroll
+        for (int pass = 0; pass < 4; ++pass) {
+            const int R = (threadIdx.x >> 4) + 16 * pass;
+            const i64 orow = tr * 64 + R, ocol = tc * 64 + 4 * qc; // out[ocol .. ocol+3 + orow * ors]
+            if (orow < nr && ocol < nc) rb_st256(ob + ocol + orow * ors, rb_xchg_read(sm, R, qc));
+        }
+        __syncthreads();
+    }
+}
+
 int rb_transpose_batched(rb_ctx *ctx, const double *in, i64 ics, i64 ibs, double *out, i64 ors, i64 obs, i64 nr,
                          i64 nc, i64 nbatch)
 {
@@ -414,6 +680,14 @@ int rb_transpose_batched(rb_ctx *ctx, const double *in, i64 ics, i64 ibs, double
     }
     i64 tiles_r = rb_cdiv(nr, TT), tiles_c = rb_cdiv(nc, TT);
     i64 total = tiles_r * tiles_c * nbatch;
+    if (((nr | nc | ics | ors) & 3) == 0 && (nbatch == 1 || ((ibs | obs) & 3) == 0) && rb_aligned32(in) && rb_aligned32(out)) {
+        i64 blocks = total;
+        const i64 cap4 = (i64)ctx->num_sms * 32;
+        if (blocks > cap4) blocks = cap4;
+        rb_transpose4_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(in, ics, ibs, out, ors, obs, nr, nc, tiles_r, tiles_c, total);
+        RB_LAUNCHED(ctx);
+        return RB_OK;
+    }
     i64 blocks = total;
     i64 cap = (i64)ctx->num_sms * 16;
     if (blocks > cap) blocks = cap;
@@ -475,11 +749,52 @@ __global__ void __launch_bounds__(256) rb_axpy_kernel(double *__restrict__ c, co
 }
 
 template <int OP>
+__device__ __forceinline__ double rb_axpy_op(double cv, double pv, double a, double b)
+{
+    if (OP == 0) return __dadd_rn(cv, __dmul_rn(pv, b));
+    if (OP == 1) return __dadd_rn(__dmul_rn(cv, a), __dmul_rn(pv, b));
+    if (OP == 2) return __dmul_rn(cv, a);
+    if (OP == 3) return __dadd_rn(cv, pv);
+    return __dsub_rn(cv, pv);
+}
+
+// 256-bit form: n4 vectors of 4 doubles (c, p 32-byte aligned), two vectors of each operand in flight per thread
+template <int OP>
+__global__ void __launch_bounds__(256) rb_axpy4_kernel(double *__restrict__ c, const double *__restrict__ p, double a, double b, i64 n4)
+{
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += 2 * stride) {
+        const bool two = i + stride < n4;
+        rb_d4 c0 = rb_ld256(c + 4 * i), c1, p0, p1;
+        if (OP != 2) p0 = rb_ld256(p + 4 * i);
+        if (two) { c1 = rb_ld256(c + 4 * (i + stride)); if (OP != 2) p1 = rb_ld256(p + 4 * (i + stride)); }
+        c0.x = rb_axpy_op<OP>(c0.x, p0.x, a, b); c0.y = rb_axpy_op<OP>(c0.y, p0.y, a, b);
+        c0.z = rb_axpy_op<OP>(c0.z, p0.z, a, b); c0.w = rb_axpy_op<OP>(c0.w, p0.w, a, b);
+        rb_st256(c + 4 * i, c0);
+        if (two) {
+            c1.x = rb_axpy_op<OP>(c1.x, p1.x, a, b); c1.y = rb_axpy_op<OP>(c1.y, p1.y, a, b);
+            c1.z = rb_axpy_op<OP>(c1.z, p1.z, a, b); c1.w = rb_axpy_op<OP>(c1.w, p1.w, a, b);
+            rb_st256(c + 4 * (i + stride), c1);
+        }
+    }
+}
+
+template <int OP>
 static int launch_axpy(rb_ctx *ctx, double *c, const double *p, double a, double b, i64 n)
 {
     RB_REQUIRE(ctx && n >= 0, "axpy: bad arguments");
     if (n == 0) return RB_OK;
     RB_CUDA(cudaSetDevice(ctx->device));
+    if (n >= 4096 && rb_aligned32(c) && (OP == 2 || rb_aligned32(p))) { // 256-bit body, scalar tail (< 4 elements)
+        const i64 n4 = n / 4;
+        i64 blocks4 = rb_cdiv(n4, 512);
+        const i64 cap4 = (i64)ctx->num_sms * 32;
+        if (blocks4 > cap4) blocks4 = cap4;
+        rb_axpy4_kernel<OP><<<(unsigned)blocks4, 256, 0, ctx->stream>>>(c, p, a, b, n4);
+        RB_LAUNCHED(ctx);
+        if (n4 * 4 == n) return RB_OK;
+        c += n4 * 4; if (OP != 2) p += n4 * 4; n -= n4 * 4;
+    }
     i64 blocks = rb_cdiv(n, 256);
     i64 cap = (i64)ctx->num_sms * 16;
     if (blocks > cap) blocks = cap;

@@ -13,6 +13,9 @@
 //               along c, contiguous per warp), one elected consumer stores that buffer with a single 64 x 64 box.
 // TMA needs 16-byte aligned bases and strides: operands with an odd leading dimension or an 8-byte-aligned base keep the
 // plain-load kernels of rb_layout.cu (the callers fall back when rb_tma_* returns RB_TMA_NOT_ELIGIBLE).
+// MEASURED (profiles/r02_hbm_kernels.md): these kernels move 5.0-5.7 TB/s, no more than the 16-byte plain-load kernels they
+// were meant to replace, while 32-byte LDG/STG kernels (rb_layout.cu) reach 6.5-7.2 TB/s; the bulk-tensor path is therefore
+// opt-in (rb_ctx_set_layout_path(ctx, 1) or REST_B200_LAYOUT_TMA=1) and kept for comparison and for its tests.
 #include "rb_common.cuh"
 
 namespace {
@@ -210,12 +213,6 @@ rb_tma_transpose_kernel(const __grid_constant__ CUtensorMap tmI, const __grid_co
     if (threadIdx.x == 0) bulk_wait_all();
 }
 
-bool layout_tma_enabled()
-{
-    static const int on = [] { const char *e = getenv("REST_B200_LAYOUT_TMA"); return e ? atoi(e) : 1; }();
-    return on != 0;
-}
-
 bool stride_ok(i64 s) { return s > 0 && (s & 1) == 0 && s * 8 < (1LL << 40); }
 
 // 3-D FP64 tensor map {d0 (unit stride), d1 @ s1, d2 @ s2}, s1 <= s2 (elements)
@@ -250,10 +247,13 @@ int encode_side(rb_ctx *ctx, CUtensorMap *tm, const double *basep, i64 ni, i64 n
 // dst[i + j*dj + k*dk] = src[i + j*sj + k*sk] (bases already offset).  RB_TMA_NOT_ELIGIBLE: the caller runs the plain kernel.
 int rb_tma_copy3d(rb_ctx *ctx, const double *s, i64 sj, i64 sk, double *d, i64 dj, i64 dk, i64 ni, i64 nj, i64 nk)
 {
-    if (!layout_tma_enabled() || !ctx->encode_tiled) return RB_TMA_NOT_ELIGIBLE;
+    if (ctx->layout_path != 1 || !ctx->encode_tiled) return RB_TMA_NOT_ELIGIBLE;
     if ((((uintptr_t)s) | ((uintptr_t)d)) & 15) return RB_TMA_NOT_ELIGIBLE;
     if (ni >= (1LL << 31) || nj >= (1LL << 31) || nk >= (1LL << 31)) return RB_TMA_NOT_ELIGIBLE;
     if (ni * nj * nk < (1LL << 16)) return RB_TMA_NOT_ELIGIBLE; // < 512 KB: one wave of the plain kernel is quicker to start
+    // Measured on B200: a bulk-tensor STORE clips the unit-stride extent at 16-byte granularity -- with an odd extent of
+    // doubles it also writes element [extent] (the zero the load filled in).  Loads clip exactly.
+    if (ni & 1) return RB_TMA_NOT_ELIGIBLE;
     // boxes of <= 4096 doubles: the i extent is cut into equal even pieces of <= 256, the j extent fills the box
     const i64 pieces_i = rb_cdiv(ni, 256);
     i64 bi = rb_cdiv(ni, pieces_i);
@@ -287,10 +287,11 @@ int rb_tma_copy3d(rb_ctx *ctx, const double *s, i64 sj, i64 sk, double *d, i64 d
 // out[c + r*ors + b*obs] = in[r + c*ics + b*ibs]
 int rb_tma_transpose(rb_ctx *ctx, const double *in, i64 ics, i64 ibs, double *out, i64 ors, i64 obs, i64 nr, i64 nc, i64 nbatch)
 {
-    if (!layout_tma_enabled() || !ctx->encode_tiled) return RB_TMA_NOT_ELIGIBLE;
+    if (ctx->layout_path != 1 || !ctx->encode_tiled) return RB_TMA_NOT_ELIGIBLE;
     if ((((uintptr_t)in) | ((uintptr_t)out)) & 15) return RB_TMA_NOT_ELIGIBLE;
     if (nr >= (1LL << 31) || nc >= (1LL << 31) || nbatch >= (1LL << 31)) return RB_TMA_NOT_ELIGIBLE;
     if (nr * nc * nbatch < (1LL << 16)) return RB_TMA_NOT_ELIGIBLE;
+    if (nc & 1) return RB_TMA_NOT_ELIGIBLE; // stores clip the unit-stride extent (nc on the output side) in 16-byte units
     TransposeSpace p;
     p.tiles_r = rb_cdiv(nr, TR); p.tiles_c = rb_cdiv(nc, TR);
     p.total = p.tiles_r * p.tiles_c * nbatch;

@@ -83,6 +83,10 @@ class Context:
         """launches of the bulk-tensor (TMA) copy / transpose / pack / unpack kernels so far"""
         return int(lib.rb_ctx_tma_layout_count(self.h))
 
+    def set_layout_path(self, path: int) -> None:
+        """0: 32-byte / plain-load copy and transpose kernels (default), 1: bulk-tensor (TMA) kernels where eligible"""
+        check(lib.rb_ctx_set_layout_path(self.h, path), "rb_ctx_set_layout_path")
+
     def set_gemm_path(self, path: int) -> None:
         check(lib.rb_ctx_set_gemm_path(self.h, path), "rb_ctx_set_gemm_path")
 

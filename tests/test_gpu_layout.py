@@ -332,47 +332,78 @@ def _ri_transposed_view(x, i, j, k, which):
 
 @pytest.mark.parametrize("shape", [(64, 64, 16), (256, 130, 6), (130, 258, 10), (66, 1000, 4), (1000, 66, 6), (600, 600, 8),
                                    (2, 40000, 2), (40000, 2, 2)])
-def test_tma_ri_transposes_bit_exact(ctx, shape):
-    """Even extents and 16-byte aligned buffers take the bulk-tensor kernels (TMA load -> shared memory -> TMA store):
-    ragged tiles at every edge, thin tensors, all four permutations, compared bit for bit with torch's permute."""
+@pytest.mark.parametrize("path", [0, 1])
+def test_tma_ri_transposes_bit_exact(ctx, shape, path):
+    """Even extents and aligned buffers: the 32-byte (LDG/STG.256) kernels (path 0, default) and the bulk-tensor kernels
+    (path 1: TMA load -> shared memory -> TMA store): ragged tiles at every edge, thin tensors, all four permutations,
+    compared bit for bit with torch's permute."""
     i, j, k = shape
     n = i * j * k
     x = ctx.empty(n); ctx.fill_linear(x, n, 21, 0, 1.0)
     u = ctx.empty(n)
-    before = ctx.tma_layout_launches
-    for which in range(4):
-        u.fill_(float("nan"))
-        ctx.ri_transpose(x, i, j, k, which, u)
-        assert torch.equal(u, _ri_transposed_view(x, i, j, k, which)), (shape, which)
-    assert ctx.tma_layout_launches == before + 4, "aligned transposes must run on the bulk-tensor path"
+    ctx.set_layout_path(path)
+    try:
+        before = ctx.tma_layout_launches
+        for which in range(4):
+            u.fill_(float("nan"))
+            ctx.ri_transpose(x, i, j, k, which, u)
+            assert torch.equal(u, _ri_transposed_view(x, i, j, k, which)), (shape, which, path)
+        assert ctx.tma_layout_launches == before + (4 if path else 0), "path 1 must run aligned transposes on the bulk-tensor kernels"
+    finally:
+        ctx.set_layout_path(0)
 
 
-@pytest.mark.parametrize("rows,cols", [(4000, 2000), (1002, 514), (64, 8192), (8192, 66), (600, 264)])
-def test_tma_matrix_transpose_bit_exact(ctx, rows, cols):
+@pytest.mark.parametrize("path", [0, 1])
+@pytest.mark.parametrize("rows,cols", [(4000, 2000), (1002, 514), (64, 8192), (8192, 66), (600, 264), (1004, 516), (68, 4100)])
+def test_tma_matrix_transpose_bit_exact(ctx, rows, cols, path):
     x = ctx.empty(rows * cols); ctx.fill_linear(x, rows * cols, 22, 0, 1.0)
     u = ctx.empty(rows * cols); u.fill_(float("nan"))
-    before = ctx.tma_layout_launches
-    ctx.matrix_transpose(x, rows, cols, u)
-    assert torch.equal(u.view(rows, cols), x.view(cols, rows).t())
-    assert ctx.tma_layout_launches == before + 1
+    ctx.set_layout_path(path)
+    try:
+        before = ctx.tma_layout_launches
+        ctx.matrix_transpose(x, rows, cols, u)
+        assert torch.equal(u.view(rows, cols), x.view(cols, rows).t())
+        assert ctx.tma_layout_launches == before + (1 if path else 0)
+    finally:
+        ctx.set_layout_path(0)
 
 
-def test_tma_sub_box_copies_bit_exact(ctx):
+@pytest.mark.parametrize("path", [0, 1])
+def test_tma_sub_box_copies_bit_exact(ctx, path):
     """copy_rr / copy_mm with even starts (16-byte aligned box corners): bulk-tensor copy; everything outside the box
-    must stay untouched.  Odd starts or extents of the same shapes fall back to the plain kernel and must agree too."""
+    must stay untouched.  Odd starts or an odd unit-stride extent (a bulk-tensor store clips that extent in 16-byte units:
+    it would overwrite the element just past an odd box) fall back to the plain kernel and must agree too."""
     fx, fy, fz, tx, ty, tz = 600, 520, 12, 640, 530, 14
     f = ctx.empty(fx * fy * fz); ctx.fill_linear(f, f.numel(), 23, 0, 1.0)
     for (xl, yl, zl, fs, ts, tma) in [(500, 500, 10, (50, 10, 1), (20, 4, 2), True), (600, 520, 12, (0, 0, 0), (0, 0, 0), True),
                                       (2, 500, 12, (598, 3, 0), (0, 7, 1), False), (300, 1, 12, (0, 519, 0), (340, 0, 2), False),
-                                      (501, 500, 10, (50, 10, 1), (20, 4, 2), True), (500, 500, 10, (51, 10, 1), (20, 4, 2), False)]:
+                                      (501, 500, 10, (50, 10, 1), (20, 4, 2), False), (500, 500, 10, (51, 10, 1), (20, 4, 2), False),
+                                      (500, 499, 9, (50, 11, 1), (20, 5, 2), True)]:
         t = ctx.empty(tx * ty * tz); ctx.fill_linear(t, t.numel(), 24, 0, 1.0)
         ref = t.clone()
         ref.view(tz, ty, tx)[ts[2]:ts[2] + zl, ts[1]:ts[1] + yl, ts[0]:ts[0] + xl] = \
             f.view(fz, fy, fx)[fs[2]:fs[2] + zl, fs[1]:fs[1] + yl, fs[0]:fs[0] + xl]
-        before = ctx.tma_layout_launches
-        ctx.copy_rr(xl, yl, zl, f, fx, fy, fz, fs[0], fs[1], fs[2], t, tx, ty, tz, ts[0], ts[1], ts[2])
-        assert torch.equal(t, ref), (xl, yl, zl, fs, ts)
-        assert (ctx.tma_layout_launches == before + 1) == tma, (xl, yl, zl, fs, ts)
+        ctx.set_layout_path(path)
+        try:
+            before = ctx.tma_layout_launches
+            ctx.copy_rr(xl, yl, zl, f, fx, fy, fz, fs[0], fs[1], fs[2], t, tx, ty, tz, ts[0], ts[1], ts[2])
+            assert torch.equal(t, ref), (xl, yl, zl, fs, ts, path)
+            assert (ctx.tma_layout_launches == before + 1) == (tma and path == 1), (xl, yl, zl, fs, ts)
+        finally:
+            ctx.set_layout_path(0)
+    # boxes whose corners and extents are multiples of 4 take the 32-byte kernels (path 0); whole slabs collapse into one run
+    for (xl, yl, zl, fs, ts) in [(496, 500, 10, (52, 10, 1), (20, 4, 2)), (600, 520, 3, (0, 0, 2), (0, 0, 0))]:
+        if (xl, yl) == (600, 520):
+            t = ctx.empty(fx * fy * 5); ctx.fill_linear(t, t.numel(), 24, 0, 1.0)
+            ref = t.clone(); ref.view(5, fy, fx)[0:3] = f.view(fz, fy, fx)[2:5]
+            ctx.copy_rr(xl, yl, zl, f, fx, fy, fz, 0, 0, 2, t, fx, fy, 5, 0, 0, 0)
+        else:
+            t = ctx.empty(tx * ty * tz); ctx.fill_linear(t, t.numel(), 24, 0, 1.0)
+            ref = t.clone()
+            ref.view(tz, ty, tx)[ts[2]:ts[2] + zl, ts[1]:ts[1] + yl, ts[0]:ts[0] + xl] = \
+                f.view(fz, fy, fx)[fs[2]:fs[2] + zl, fs[1]:fs[1] + yl, fs[0]:fs[0] + xl]
+            ctx.copy_rr(xl, yl, zl, f, fx, fy, fz, fs[0], fs[1], fs[2], t, tx, ty, tz, ts[0], ts[1], ts[2])
+        assert torch.equal(t, ref), (xl, yl, zl)
     n = 4000
     a = ctx.empty(n * n); ctx.fill_linear(a, n * n, 25, 0, 1.0)
     b = ctx.empty(n * n); b.zero_()
@@ -380,3 +411,50 @@ def test_tma_sub_box_copies_bit_exact(ctx):
     ref = torch.zeros_like(b)
     ref.view(n, n)[0:n - 200, 0:n - 100] = a.view(n, n)[200:n, 100:n]
     assert torch.equal(b, ref)
+
+
+@pytest.mark.parametrize("n", [64, 68, 128, 252, 600, 1000, 1028, 4000])
+def test_pack_unpack_256bit_kernels_bit_exact(ctx, n):
+    """n % 4 == 0 with 32-byte aligned buffers runs the LDG/STG.256 pack / unpack kernels: compare with an independent torch
+    construction of the packed <-> full maps (matrixupper.rs:330-373, matrixfull.rs:638-646), bit for bit, including
+    the mirrored triangle, ragged edge tiles (n % 64 != 0) and the 4 x 4 blocks on the diagonal."""
+    np_ = n * (n + 1) // 2
+    packed = ctx.empty(np_); ctx.fill_linear(packed, np_, 4, 0, 1.0)
+    full = ctx.empty(n * n); full.fill_(float("nan"))
+    ctx.unpack_upper(packed, n, full)
+    jj, ii = torch.meshgrid(torch.arange(n, device=packed.device), torch.arange(n, device=packed.device), indexing="ij")  # [col j][row i]
+    lo, hi = torch.minimum(ii, jj), torch.maximum(ii, jj)
+    want = packed[hi * (hi + 1) // 2 + lo]                   # full[i + j n] viewed as [j][i]
+    assert torch.equal(full.view(n, n), want)
+    back = ctx.empty(np_); back.fill_(float("nan"))
+    ctx.pack_upper(full, n, back)
+    assert torch.equal(back, packed)
+    # pack must read the upper triangle only: poison the strictly lower part
+    poisoned = full.clone().view(n, n)
+    poisoned[ii > jj] = float("nan")
+    ctx.pack_upper(poisoned.reshape(-1), n, back)
+    assert torch.equal(back, packed)
+
+
+def test_ri_pack_symm_256bit_bit_exact(ctx):
+    nao, naux = 128, 7
+    ri = ctx.empty(nao * nao * naux); ctx.fill_linear(ri, ri.numel(), 2, 0, 1.0)
+    out = ctx.empty(nao * (nao + 1) // 2 * naux); out.fill_(float("nan"))
+    ctx.ri_pack_symm(ri, nao, naux, out)
+    jj, ii = torch.meshgrid(torch.arange(nao, device=ri.device), torch.arange(nao, device=ri.device), indexing="ij")
+    sel = (ii <= jj)
+    for p in range(naux):
+        slab = ri.view(naux, nao, nao)[p]                    # [j][i]
+        assert torch.equal(out.view(naux, -1)[p], slab[sel])  # row-major walk of [j][i] with i <= j == packed order j(j+1)/2 + i
+
+
+def test_axpy_256bit_body_and_tail_bit_exact(ctx):
+    for n in (4096, 4099, 100003):
+        c = ctx.empty(n); p = ctx.empty(n)
+        ctx.fill_linear(c, n, 16, 0, 1.0); ctx.fill_linear(p, n, 17, 0, 1.0)
+        want = c + p * 0.37                                   # torch: separate multiply and add kernels -> unfused, like the reference
+        ctx.self_scaled_add(c, p, 0.37, n)
+        assert torch.equal(c, want), n
+        want = c * (-1.25) + p * (1.0 / 3.0)
+        ctx.self_general_add(c, p, -1.25, 1.0 / 3.0, n)
+        assert torch.equal(c, want), n

@@ -20,6 +20,26 @@ def best_ms(fn, reps=7, warm=2):
     return min(ts)
 
 
+def stream_ms(make_call, bytes_per_call, target=1 << 30):
+    """per-call time with the calls issued back to back over distinct buffer sets (>= 1 GB in total, so nothing is served
+    from L2) inside ONE event pair: the sustained rate of the kernel including its own launch gap, without the ~5 us an
+    event pair around a single launch adds"""
+    sets = int(max(2, min(64, -(-target // bytes_per_call))))
+    calls = [make_call() for _ in range(sets)]
+    best = None
+    for it in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for fn in calls:
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        if it:
+            t = e0.elapsed_time(e1) / sets
+            best = t if best is None else min(best, t)
+    return best
+
+
 def main():
     ctx = Context(0)
     out = {"hbm_copy_probe_gbs": round(ctx.hbm_copy_probe(4 << 30, 10), 1)}
@@ -35,6 +55,16 @@ def main():
         out[f"copy_mm_{n}_gbs"] = round(2 * n * n * 8 / best_ms(lambda: ctx.copy_mm(n, n, f, n, n, 0, 0, g, n, n, 0, 0)) / 1e6, 1)
         out[f"axpy_{n}_gbs"] = round(3 * n * n * 8 / best_ms(lambda: ctx.self_scaled_add(g, f, 0.5, n * n)) / 1e6, 1)
         del p, f, g
+
+        def mk(kind):
+            def make():
+                pp = ctx.empty(np_); ff = ctx.empty(n * n); gg = ctx.empty(n * n)
+                return {"unpack": lambda: ctx.unpack_upper(pp, n, ff), "pack": lambda: ctx.pack_upper(ff, n, pp),
+                        "transpose": lambda: ctx.matrix_transpose(ff, n, n, gg),
+                        "copy_mm": lambda: ctx.copy_mm(n, n, ff, n, n, 0, 0, gg, n, n, 0, 0)}[kind]
+            return make
+        for kind, nbytes in (("unpack", (np_ + n * n) * 8), ("pack", 2 * np_ * 8), ("transpose", 2 * n * n * 8), ("copy_mm", 2 * n * n * 8)):
+            out[f"{kind}_{n}_stream_gbs"] = round(nbytes / stream_ms(mk(kind), nbytes) / 1e6, 1)
     I, J, K = 600, 600, 400
     t = ctx.empty(I * J * K); u = ctx.empty(I * J * K); ctx.fill_linear(t, I * J * K, 5, 0, 1.0)
     for which, name in enumerate(["jik", "jki", "kji", "ikj"]):
