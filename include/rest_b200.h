@@ -289,6 +289,19 @@ int rb_einsum_ip_ip(rb_ctx *ctx, const double *a, int64_t lda, const double *b, 
                     int64_t np);
 int rb_einsum_i_j(rb_ctx *ctx, const double *a, const double *b, double *out, int64_t ni, int64_t nj);
 
+/* ERIFold4 (src/eri.rs:170-373): four-index integrals with both pairs folded, a column-major
+ * [size0 = npair_ij, size1 = npair_kl] matrix (leading dimension ld), packed pair index j(j+1)/2 + i, i <= j.  The chunk scatter
+ * moves a dense shell-quartet block buf[li, lj, lk, ll] (first index fastest) for i in i0..i0+li, ... into the folded tensor:
+ *   mode 0 = chunk_copy_from_local_erifull (eri.rs:266-305): elements with k <= l and i <= j
+ *   mode 1 = chunk_copy_from_a_full_vector (eri.rs:308-372): k <= l and (i0 < j0: every (i, j); i0 == j0: local ii <= jj;
+ *            i0 > j0: nothing)
+ * Bit-exact.  RB_ERR_INVALID when the block reaches outside the tensor (the reference panics on the slice). */
+int rb_erifold4_chunk_copy(rb_ctx *ctx, double *eri, int64_t size0, int64_t size1, int64_t ld, int i0, int li, int j0, int lj,
+                           int k0, int lk, int l0, int ll, const double *buf, int mode);
+/* the same on a HOST tensor (dense, ld = size0): only the window of rows the block touches crosses PCIe */
+int rb_host_erifold4_chunk_copy(double *eri, int64_t size0, int64_t size1, int i0, int li, int j0, int lj, int k0, int lk, int l0,
+                                int ll, const double *buf, int mode);
+
 /* Symmetric eigen-solvers (the reference's LAPACK wrappers _dsyev / lapack_dspevx / lapack_dspgvx /
  * _power, matrix_blas_lapack.rs:319-352, 599-652, 1004-1147, 2123-2185) as a parallel one-sided Jacobi method on device
  * buffers.  Eigenvalues ascending; eigenvectors in the columns of z, normalised, largest component positive (LAPACK

@@ -98,6 +98,10 @@ class Oracle:
         L.orc_power.argtypes = [_vp, _i, _d, _d, _vp, _vp]
         L.orc_ri_mo_pq.argtypes = [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]
         L.orc_ri_iajb.argtypes = [_i, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp]
+        L.orc_erifold4_chunk_copy_local.restype = _i
+        L.orc_erifold4_chunk_copy_local.argtypes = [_vp, _i64, _i64, _i64] + [_i64] * 8 + [_vp]
+        L.orc_erifold4_chunk_copy_full.restype = _i
+        L.orc_erifold4_chunk_copy_full.argtypes = [_vp, _i64, _i64] + [_i64] * 8 + [_vp]
         for name in ("orc_einsum_01", "orc_einsum_02", "orc_einsum_03"):
             getattr(L, name).argtypes = [_vp, _vp, _vp, _i64, _i64]
             getattr(L, name).restype = None
@@ -227,6 +231,17 @@ class Oracle:
         out = np.empty(ni * nj, dtype=np.float64)
         self.lib.orc_einsum_03(a.ctypes.data, b.ctypes.data, out.ctypes.data, ni, nj)
         return out
+
+    # -- ERIFold4 chunk copies (src/eri.rs:266-372); return False where the reference would panic --
+    def erifold4_chunk_copy_local(self, eri, size, dim, r, buf) -> bool:
+        (i0, i1), (j0, j1), (k0, k1), (l0, l1) = r
+        return self.lib.orc_erifold4_chunk_copy_local(eri.ctypes.data, size[0], size[1], dim, i0, i1 - i0, j0, j1 - j0, k0, k1 - k0,
+                                                      l0, l1 - l0, buf.ctypes.data) == 0
+
+    def erifold4_chunk_copy_full(self, eri, size, r, buf) -> bool:
+        (i0, i1), (j0, j1), (k0, k1), (l0, l1) = r
+        return self.lib.orc_erifold4_chunk_copy_full(eri.ctypes.data, size[0], size[1], i0, i1 - i0, j0, j1 - j0, k0, k1 - k0, l0,
+                                                     l1 - l0, buf.ctypes.data) == 0
 
     # -- BLAS --
     def dgemm(self, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc) -> None:

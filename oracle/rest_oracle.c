@@ -708,3 +708,64 @@ void orc_einsum_03(const double *a, const double *b, double *out, i64 ni, i64 nj
     for (i64 j = 0; j < nj; ++j)
         for (i64 i = 0; i < ni; ++i) out[i + j * ni] = a[i] * b[j];
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * ERIFold4 chunk copies (src/eri.rs:170-373).  The tensor is column-major [size0, size1] with the packed
+ * pair index (j+1)*j/2 + i (src/index.rs:227-233, the `_uncheck` form: no swap of i and j).
+ * Both follow the reference's loops run by run; they return 1 where the reference would panic (a slice that
+ * leaves the tensor), 0 otherwise.  PARITY UNPINNED: the reference has no test for ERIFold4.
+ * ---------------------------------------------------------------------------------------------- */
+/* chunk_copy_from_local_erifull (eri.rs:266-305): to-slices from get_slices_mut (eri.rs:227-263), from-slices from the
+ * dense local block; both enumerate l (outer), k, j (inner), skipping k > l and j < d1.start; run length
+ * d1.len if j >= d1.end else j - d1.start + 1.  `dim` only enters through len_d12 = dim(dim+1)/2 = the column stride. */
+int orc_erifold4_chunk_copy_local(double *eri, i64 size0, i64 size1, i64 dim, i64 i0, i64 li, i64 j0, i64 lj, i64 k0, i64 lk,
+                                  i64 l0, i64 ll, const double *buf)
+{
+    const i64 len_d12 = dim * (dim + 1) / 2;
+    const i64 ind1 = li, ind2 = ind1 * lj, ind3 = ind2 * lk;
+    for (i64 lx = 0; lx < ll; ++lx) {
+        const i64 l = l0 + lx;
+        for (i64 kx = 0; kx < lk; ++kx) {
+            const i64 k = k0 + kx;
+            if (k > l) continue;
+            for (i64 jx = 0; jx < lj; ++jx) {
+                const i64 j = j0 + jx;
+                if (j < i0) continue;
+                const i64 start = (l * (l + 1) / 2 + k) * len_d12 + j * (j + 1) / 2 + i0;
+                const i64 len = (j >= i0 + li) ? li : j - i0 + 1;
+                if (start + len > size0 * size1) return 1;
+                const double *src = buf + lx * ind3 + kx * ind2 + jx * ind1;
+                for (i64 e = 0; e < len; ++e) eri[start + e] = src[e];
+            }
+        }
+    }
+    return 0;
+}
+
+/* chunk_copy_from_a_full_vector (eri.rs:308-372), "algorithm 1" */
+int orc_erifold4_chunk_copy_full(double *eri, i64 size0, i64 size1, i64 i0, i64 li, i64 j0, i64 lj, i64 k0, i64 lk, i64 l0,
+                                 i64 ll, const double *buf)
+{
+    if (!(i0 < j0 || i0 == j0)) return 0; /* range[0].start > range[1].start: neither branch runs */
+    for (i64 lx = 0; lx < ll; ++lx) {
+        const i64 l = l0 + lx;
+        for (i64 kx = 0; kx < lk; ++kx) {
+            const i64 k = k0 + kx;
+            if (k > l) continue;
+            const i64 klpair = (l + 1) * l / 2 + k;
+            if (klpair >= size1) return 1;                         /* get_reducing_matrix_mut: index2d([0, klpair]).unwrap() */
+            double *col = eri + klpair * size0;                    /* MatrixUpperSliceMut of length indicing[1] = size0 */
+            const double *local_kl = buf + (kx + lx * lk) * li * lj;  /* mat_local.get_reducing_matrix(&[kk, ll]) */
+            i64 local_start = 0;
+            for (i64 jx = 0; jx < lj; ++jx) {
+                const i64 j = j0 + jx;
+                const i64 len = (i0 < j0) ? li : jx + 1;
+                const i64 tp = (j + 1) * j / 2 + i0;               /* index2d_uncheck([range[0].start, j]) */
+                if (tp >= size0 || tp + len > size0) return 1;
+                for (i64 e = 0; e < len; ++e) col[tp + e] = local_kl[local_start + e];
+                local_start += li;
+            }
+        }
+    }
+    return 0;
+}

@@ -8,7 +8,7 @@ Layout of the package (only what the hot path needs):
 """
 from ._lib import lib, RestB200Error, LIB_PATH, SIGNATURES  # noqa: F401
 from .tensors import (  # noqa: F401
-    RIFull, MatrixFull, MatrixUpper, MatrixFullSlice, MatrixFullSliceMut, MatrixUpperSlice, MatrixUpperStepBy,
+    RIFull, MatrixFull, MatrixUpper, MatrixFullSlice, MatrixFullSliceMut, MatrixUpperSlice, MatrixUpperStepBy, ERIFold4,
     map_upper_to_full, map_full_to_upper, general_check_shape,
     _dgemm, _dgemm_full, _dgemm_full_new, _dsyrk, _dsymm, _dgemv,
     _dgemm_nn, _dgemm_nn_serial, _dgemm_tn, _dgemm_tn_serial, _dgemm_tn_v02,
@@ -18,7 +18,7 @@ from .tensors import (  # noqa: F401
 )
 
 __all__ = [
-    "RIFull", "MatrixFull", "MatrixUpper", "MatrixFullSlice", "MatrixFullSliceMut", "MatrixUpperSlice", "MatrixUpperStepBy",
+    "RIFull", "MatrixFull", "MatrixUpper", "MatrixFullSlice", "MatrixFullSliceMut", "MatrixUpperSlice", "MatrixUpperStepBy", "ERIFold4",
     "map_upper_to_full", "map_full_to_upper", "general_check_shape", "RestB200Error",
     "_dgemm", "_dgemm_full", "_dgemm_full_new", "_dsyrk", "_dsymm", "_dgemv",
     "_dgemm_nn", "_dgemm_nn_serial", "_dgemm_tn", "_dgemm_tn_serial", "_dgemm_tn_v02",

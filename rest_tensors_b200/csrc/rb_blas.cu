@@ -147,9 +147,6 @@ constexpr int GT_ROWS_PER_IT = 1024; // 256 threads x 2 double2
 constexpr int GT_ITERS = 32;
 constexpr i64 GT_RCH = (i64)GT_ROWS_PER_IT * GT_ITERS;
 
-// W4: 32-byte loads (LDG.256; lda % 4 == 0, 32-byte aligned a and x): thread t owns rows base + 4t .. 4t+3 of every 1024-row step
-// instead of two row pairs -- same bytes in flight per thread, half the load instructions (measured: 6.85 -> see profiles).
-template <bool W4>
 __global__ void __launch_bounds__(256, 4) rb_gemv_t_vec_kernel(const double *__restrict__ a, i64 lda, i64 m, i64 n,
                                                                 const double *__restrict__ x, double *__restrict__ partial,
                                                                 i64 row_chunks, i64 col_groups)
@@ -170,26 +167,6 @@ __global__ void __launch_bounds__(256, 4) rb_gemv_t_vec_kernel(const double *__r
         }
         double acc[GT_COLS] = {0.0, 0.0, 0.0, 0.0};
         for (i64 base = r0; base < r1; base += GT_ROWS_PER_IT) {
-            if (W4) {
-                const i64 p0 = base + 4 * tid;
-                if (p0 + 3 < r1) {
-                    const rb_d4 xv = rb_ld256(x + p0);
-                    rb_d4 v[GT_COLS];
-#pragma unroll
-                    for (int g = 0; g < GT_COLS; ++g) v[g] = rb_ld256(col[g] + p0);
-#pragma unroll
-                    for (int g = 0; g < GT_COLS; ++g) acc[g] += (v[g].x * xv.x + v[g].y * xv.y) + (v[g].z * xv.z + v[g].w * xv.w);
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        if (p0 + e < r1) {
-                            const double xs = x[p0 + e];
-#pragma unroll
-                            for (int g = 0; g < GT_COLS; ++g) acc[g] += col[g][p0 + e] * xs;
-                        }
-                }
-                continue;
-            }
             const i64 p0 = base + 2 * tid, p1 = p0 + 512;
             if (p1 + 1 < r1) { // both pairs fully inside (the common case)
                 const double2 x0 = *reinterpret_cast<const double2 *>(x + p0);
@@ -297,7 +274,7 @@ __global__ void __launch_bounds__(256) rb_gemv_t_finish_kernel(const double *__r
 }
 
 // grid (row blocks, splits): thread owns RPT consecutive rows, loops over its column range; partial[split][m]
-template <int VEC>
+template <bool VEC>
 __global__ void __launch_bounds__(256) rb_gemv_n_kernel(const double *__restrict__ a, i64 lda, i64 m, i64 n,
                                                         const double *__restrict__ x, i64 incx, i64 cols_per_split,
                                                         double *__restrict__ partial, i64 pstride)
@@ -307,32 +284,7 @@ __global__ void __launch_bounds__(256) rb_gemv_n_kernel(const double *__restrict
     i64 j1 = j0 + cols_per_split;
     if (j1 > n) j1 = n;
     double *out = partial + split * pstride;
-    if (VEC == 4) { // four consecutive rows per thread, 32-byte loads (lda % 4 == 0, m % 4 == 0, 32-byte aligned a): per row the
-                    // same sums in the same order as the 16-byte form
-        const i64 i = ((i64)blockIdx.x * 256 + threadIdx.x) * 4;
-        if (i >= m) return;
-        const double *ap = a + i;
-        rb_d4 s0 = {0.0, 0.0, 0.0, 0.0}, s1 = s0, s2 = s0, s3 = s0;
-        i64 j = j0;
-        for (; j + 3 < j1; j += 4) {
-            const rb_d4 v0 = rb_ld256(ap + j * lda), v1 = rb_ld256(ap + (j + 1) * lda), v2 = rb_ld256(ap + (j + 2) * lda),
-                        v3 = rb_ld256(ap + (j + 3) * lda);
-            const double x0 = __ldg(x + j), x1 = __ldg(x + j + 1), x2 = __ldg(x + j + 2), x3 = __ldg(x + j + 3);
-            s0.x += v0.x * x0; s0.y += v0.y * x0; s0.z += v0.z * x0; s0.w += v0.w * x0;
-            s1.x += v1.x * x1; s1.y += v1.y * x1; s1.z += v1.z * x1; s1.w += v1.w * x1;
-            s2.x += v2.x * x2; s2.y += v2.y * x2; s2.z += v2.z * x2; s2.w += v2.w * x2;
-            s3.x += v3.x * x3; s3.y += v3.y * x3; s3.z += v3.z * x3; s3.w += v3.w * x3;
-        }
-        for (; j < j1; ++j) {
-            const rb_d4 v0 = rb_ld256(ap + j * lda);
-            const double x0 = __ldg(x + j);
-            s0.x += v0.x * x0; s0.y += v0.y * x0; s0.z += v0.z * x0; s0.w += v0.w * x0;
-        }
-        rb_d4 r;
-        r.x = (s0.x + s1.x) + (s2.x + s3.x); r.y = (s0.y + s1.y) + (s2.y + s3.y);
-        r.z = (s0.z + s1.z) + (s2.z + s3.z); r.w = (s0.w + s1.w) + (s2.w + s3.w);
-        rb_st256(out + i, r);
-    } else if (VEC == 2) {
+    if (VEC) {
         const i64 i = ((i64)blockIdx.x * 256 + threadIdx.x) * 2;
         if (i >= m) return;
         const bool pair = (i + 1 < m);
@@ -413,10 +365,7 @@ extern "C" int rb_dgemv(rb_ctx *ctx, char trans, int m_, int n_, double alpha, c
             i64 units = row_chunks * col_groups;
             i64 grid = (i64)ctx->num_sms * 4;
             if (grid > units) grid = units;
-            if ((lda & 3) == 0 && rb_aligned32(a) && rb_aligned32(xb))
-                rb_gemv_t_vec_kernel<true><<<(unsigned)grid, 256, 0, ctx->stream>>>(a, lda, m, n, xb, (double *)ws, row_chunks, col_groups);
-            else
-                rb_gemv_t_vec_kernel<false><<<(unsigned)grid, 256, 0, ctx->stream>>>(a, lda, m, n, xb, (double *)ws, row_chunks, col_groups);
+            rb_gemv_t_vec_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>(a, lda, m, n, xb, (double *)ws, row_chunks, col_groups);
             RB_LAUNCHED(ctx);
             rb_gemv_t_finish_kernel<<<(unsigned)rb_cdiv(n, 256), 256, 0, ctx->stream>>>((const double *)ws, row_chunks, n, alpha, beta, yb, incy);
             RB_LAUNCHED(ctx);
@@ -458,8 +407,7 @@ extern "C" int rb_dgemv(rb_ctx *ctx, char trans, int m_, int n_, double alpha, c
     }
     // 'N'
     bool vec = incx == 1 && ((lda & 1) == 0) && ((((uintptr_t)a) & 15) == 0);
-    const bool vec4 = vec && ((lda & 3) == 0) && ((m & 3) == 0) && rb_aligned32(a);
-    i64 row_blocks = vec4 ? rb_cdiv(m / 4, 256) : vec ? rb_cdiv(rb_cdiv(m, 2), 256) : rb_cdiv(m, 256);
+    i64 row_blocks = vec ? rb_cdiv(rb_cdiv(m, 2), 256) : rb_cdiv(m, 256);
     i64 splits = 1;
     i64 want = (i64)ctx->num_sms * 16; // measured: J at config C goes from 4.65 to >5.5 TB/s with 4 column splits
     if (row_blocks < want) splits = rb_cdiv(want, row_blocks);
@@ -470,12 +418,11 @@ extern "C" int rb_dgemv(rb_ctx *ctx, char trans, int m_, int n_, double alpha, c
     i64 cols_per_split = rb_cdiv(n, splits);
     splits = rb_cdiv(n, cols_per_split);
     void *ws;
-    const i64 pstride = (m + 3) & ~(i64)3;
+    const i64 pstride = (m + 1) & ~(i64)1;
     RB_TRY(rb_ws_reserve(ctx, 1, splits * pstride * 8, &ws));
     dim3 grid((unsigned)row_blocks, (unsigned)splits);
-    if (vec4) rb_gemv_n_kernel<4><<<grid, 256, 0, ctx->stream>>>(a, lda, m, n, xb, incx, cols_per_split, (double *)ws, pstride);
-    else if (vec) rb_gemv_n_kernel<2><<<grid, 256, 0, ctx->stream>>>(a, lda, m, n, xb, incx, cols_per_split, (double *)ws, pstride);
-    else rb_gemv_n_kernel<1><<<grid, 256, 0, ctx->stream>>>(a, lda, m, n, xb, incx, cols_per_split, (double *)ws, pstride);
+    if (vec) rb_gemv_n_kernel<true><<<grid, 256, 0, ctx->stream>>>(a, lda, m, n, xb, incx, cols_per_split, (double *)ws, pstride);
+    else rb_gemv_n_kernel<false><<<grid, 256, 0, ctx->stream>>>(a, lda, m, n, xb, incx, cols_per_split, (double *)ws, pstride);
     RB_LAUNCHED(ctx);
     i64 blocks = rb_cdiv(m, 256);
     i64 cap = (i64)ctx->num_sms * 16;

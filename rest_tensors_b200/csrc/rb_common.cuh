@@ -128,6 +128,10 @@ int rb_scale_or_zero(rb_ctx *ctx, double *y, i64 n, i64 inc, double beta);
 // rb_ri.cu: upper triangle of k (+)= sum_P (A_P ct)(A_P ct)^T over nx slabs (beta 0 overwrite / 1 accumulate)
 int rb_ri_k_upper(rb_ctx *ctx, const double *ri3ao, const double *ct, i64 no, double *k, i64 nb, i64 nx, double beta);
 
+// rb_eri.cu: ERIFold4 chunk scatter without bounds checks (dst may be a virtual origin of a window)
+int rb_erifold4_scatter(rb_ctx *ctx, double *dst, i64 ld, const double *buf, i64 i0, i64 li, i64 j0, i64 lj, i64 k0, i64 lk, i64 l0,
+                        i64 ll, int mode);
+
 // rb_eig.cu: drop the cached sweep graphs of a context (called by rb_ctx_destroy)
 void rb_eig_cache_free(rb_ctx *ctx);
 

@@ -990,6 +990,51 @@ extern "C" int rb_host_einsum(int which, const double *a, const double *b, doubl
     return op.sync();
 }
 
+// ERIFold4 chunk scatter on a HOST tensor: the block only touches the rows [row_lo, row_hi] of the columns (k, l), k <= l, so
+// just that window of every touched column crosses PCIe (up, scatter on the device, back); the rest of the tensor stays put.
+extern "C" int rb_host_erifold4_chunk_copy(double *eri, int64_t size0, int64_t size1, int i0, int li, int j0, int lj, int k0, int lk,
+                                           int l0, int ll, const double *buf, int mode)
+{
+    RB_REQUIRE(mode == 0 || mode == 1, "rb_host_erifold4_chunk_copy: mode must be 0 or 1");
+    RB_REQUIRE(size0 >= 0 && size1 >= 0, "rb_host_erifold4_chunk_copy: bad tensor shape");
+    RB_REQUIRE(i0 >= 0 && j0 >= 0 && k0 >= 0 && l0 >= 0 && li >= 0 && lj >= 0 && lk >= 0 && ll >= 0,
+               "rb_host_erifold4_chunk_copy: negative range");
+    const i64 total = (i64)li * lj * lk * ll;
+    if (total == 0 || (mode == 1 && i0 > j0)) return RB_OK;
+    RB_REQUIRE(eri && buf, "rb_host_erifold4_chunk_copy: NULL buffer");
+    const i64 jlo = j0, jhi = (i64)j0 + lj - 1;
+    i64 ihi = (i64)i0 + li - 1;
+    if ((mode == 0 || i0 == j0) && ihi > jhi) ihi = jhi;
+    const i64 row_lo = jlo * (jlo + 1) / 2 + i0, row_hi = jhi * (jhi + 1) / 2 + ihi;
+    if (mode == 0 && i0 > jhi) return RB_OK; // no i <= j in the block
+    RB_REQUIRE(row_hi < size0, "rb_host_erifold4_chunk_copy: the block reaches outside the folded tensor (row %lld of %lld)",
+               (long long)row_hi, (long long)size0);
+    const i64 rows = row_hi - row_lo + 1;
+    HOST_CTX(op);
+    double *dbuf, *dwin;
+    RB_TRY(op.alloc(total, &dbuf));
+    RB_TRY(op.up(dbuf, buf, total));
+    // per l: the columns (k, l), k = k0 .. min(k0 + lk - 1, l), are consecutive: one pitched window [rows, nk]
+    for (i64 lx = 0; lx < ll; ++lx) {
+        const i64 l = (i64)l0 + lx;
+        i64 khi = (i64)k0 + lk - 1;
+        if (khi > l) khi = l;
+        if (khi < k0) continue;
+        const i64 nk = khi - k0 + 1, col0 = l * (l + 1) / 2 + k0;
+        RB_REQUIRE(col0 + nk <= size1, "rb_host_erifold4_chunk_copy: the block reaches outside the folded tensor (column %lld of %lld)",
+                   (long long)(col0 + nk - 1), (long long)size1);
+        RB_TRY(op.alloc(rows * nk, &dwin));
+        double *hwin = eri + col0 * size0 + row_lo;
+        RB_TRY(op.up2d(dwin, hwin, rows, nk, size0));
+        // the window is a [rows, nk] matrix whose element (row - row_lo, k - k0) is tensor element (row, (k, l)): scatter with the
+        // tensor's index arithmetic by pointing the kernel at a virtual origin
+        double *origin = dwin - (col0 * rows + row_lo);
+        RB_TRY(rb_erifold4_scatter(op.ctx, origin, rows, dbuf + lx * (i64)li * lj * lk, i0, li, j0, lj, k0, lk, l, 1, mode));
+        RB_TRY(op.down2d(hwin, size0, dwin, rows, nk));
+    }
+    return op.sync();
+}
+
 extern "C" int rb_host_ri_dp(const double *ri3ao, const double *dm, double *d, int nb, int nx)
 {
     RB_REQUIRE(nb >= 0 && nx >= 0, "rb_host_ri_dp: negative dimension");

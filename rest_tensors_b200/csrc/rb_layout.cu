@@ -43,77 +43,14 @@ __global__ void __launch_bounds__(256) rb_pack_upper_panel_kernel(const double *
 }
 
 
-// 256-bit form (n % 4 == 0, 32-byte aligned `full`): one CTA per 64 x 64 tile on or above the diagonal.  The tile is read with
-// 32-byte loads along i (a thread takes a 4 x 4 micro-tile, 16 lanes cover 64 consecutive rows of a column) and parked in
-// shared memory; then each warp writes 8 of the 64 packed runs.  A run starts at the 8-byte offset j(j+1)/2 + i0, so it is
-// written as 16-byte pairs from whichever parity is aligned (plus one single double at each end): every store instruction
-// of a warp covers one contiguous run, which is what keeps the write path efficient (a first version that stored each
-// thread's 4 elements on its own -- 16 scattered sectors per instruction -- ran at 0.9x the 8-byte kernel it replaced).
-__global__ void __launch_bounds__(256) rb_pack_upper4_kernel(const double *__restrict__ full, double *__restrict__ packed, i64 n,
-                                                             i64 full_slab, i64 packed_slab, i64 pairs)
-{
-    __shared__ __align__(32) double tile[64][64]; // [column jj][row ii]
-    const i64 slab = blockIdx.x / pairs, p = blockIdx.x - slab * pairs;
-    i64 tj = (i64)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
-    while (tj * (tj + 1) / 2 > p) --tj;
-    while ((tj + 1) * (tj + 2) / 2 <= p) ++tj;
-    const i64 ti = p - tj * (tj + 1) / 2;
-    const double *f = full + slab * full_slab;
-    double *pk = packed + slab * packed_slab;
-    const i64 i0 = ti * 64, j0 = tj * 64;
-    {
-        const int lr = threadIdx.x & 15, lc = threadIdx.x >> 4;
-        const i64 i = i0 + 4 * lr;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const i64 j = j0 + 4 * lc + e;
-            if (i < n && j < n && i <= j) { // the quad holds at least one element on or above the diagonal
-                const rb_d4 v = rb_ld256(f + i + j * n);
-                double *t = &tile[4 * lc + e][4 * lr];
-                *reinterpret_cast<double2 *>(t) = make_double2(v.x, v.y);
-                *reinterpret_cast<double2 *>(t + 2) = make_double2(v.z, v.w);
-            }
-        }
-    }
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const int jj = warp * 8 + c;
-        const i64 j = j0 + jj;
-        if (j >= n) break;
-        i64 cnt = j - i0 + 1; // rows i0 .. min(i0 + 63, j) of column j
-        if (cnt > 64) cnt = 64;
-        double *dst = pk + j * (j + 1) / 2 + i0;
-        const double *src = tile[jj];
-        if ((((uintptr_t)dst) & 15) == 0) {
-            const int e = 2 * lane;
-            if (e + 1 < cnt) *reinterpret_cast<double2 *>(dst + e) = *reinterpret_cast<const double2 *>(src + e);
-            else if (e < cnt) dst[e] = src[e];
-        } else {
-            const int e = 2 * lane + 1; // pairs (1,2), (3,4), ... are the aligned ones; element 0 goes alone
-            if (lane == 0) dst[0] = src[0];
-            if (e + 1 < cnt) *reinterpret_cast<double2 *>(dst + e) = make_double2(src[e], src[e + 1]);
-            else if (e < cnt) dst[e] = src[e];
-        }
-    }
-}
-
 static int launch_pack(rb_ctx *ctx, const double *full, i64 n, i64 nslab, double *packed)
 {
     if (n == 0 || nslab == 0) return RB_OK;
     i64 np = n * (n + 1) / 2;
-    if ((n & 3) == 0 && rb_aligned32(full) && n >= 64) { // 256-bit loads; every slab starts 32-byte aligned (n^2 % 4 == 0)
-        const i64 nt = rb_cdiv(n, 64), pairs = nt * (nt + 1) / 2;
-        for (i64 z0 = 0; z0 < nslab;) {
-            i64 nz = nslab - z0;
-            if (nz * pairs > 2147483647LL) nz = 2147483647LL / pairs;
-            rb_pack_upper4_kernel<<<(unsigned)(nz * pairs), 256, 0, ctx->stream>>>(full + z0 * n * n, packed + z0 * np, n, n * n, np, pairs);
-            RB_LAUNCHED(ctx);
-            z0 += nz;
-        }
-        return RB_OK;
-    }
+    // (Two 256-bit variants were measured and dropped, profiles/r02_hbm_kernels.md: 32-byte loads with each thread storing its own
+    //  4 elements -- 16 scattered sectors per store instruction -- and 32-byte loads staged through shared memory with one 512-byte
+    //  run per store instruction reached 5.3 / 4.9 TB/s at n = 8000 against 5.9 TB/s for the kernels below, whose 8-byte accesses
+    //  are fully coalesced on both sides; the packed runs start at arbitrary 8-byte offsets, so wider stores buy nothing.)
     for (i64 z0 = 0; z0 < nslab; z0 += 65535) {
         unsigned nz = (unsigned)((nslab - z0) < 65535 ? (nslab - z0) : 65535);
         if (n >= 512) {
@@ -425,26 +362,21 @@ __global__ void __launch_bounds__(256) rb_copy3d_kernel(const double *__restrict
     }
 }
 
-// one contiguous run of niv 32-byte vectors: CTA c takes the 1024-vector chunks c, c + grid, ...; 8 loads in flight per thread
-__global__ void __launch_bounds__(256) rb_copy_flat4_kernel(const double *__restrict__ s, double *__restrict__ d, i64 niv, i64 chunks)
+// one contiguous run of niv 32-byte vectors: grid-stride with 8 loads in flight per thread, each a whole grid apart -- the
+// access pattern of the fastest variant of tools/micro/copy_bench.cu (7.2-7.6 TB/s with >= 16 CTAs per SM in the grid; taking
+// contiguous 32 KB chunks per CTA instead measured 6.6 TB/s on the same buffers)
+__global__ void __launch_bounds__(256) rb_copy_flat4_kernel(const double *__restrict__ s, double *__restrict__ d, i64 niv)
 {
-    for (i64 c = blockIdx.x; c < chunks; c += 2 * (i64)gridDim.x) {
-        const i64 a = c * 1024 + threadIdx.x, b = (c + gridDim.x) * 1024 + threadIdx.x;
-        const bool second = c + gridDim.x < chunks;
-        rb_d4 va[4], vb[4];
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 7 * stride < niv; i += 8 * stride) {
+        rb_d4 v[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) if (a + u * 256 < niv) va[u] = rb_ld256(s + 4 * (a + u * 256));
-        if (second) {
+        for (int u = 0; u < 8; ++u) v[u] = rb_ld256(s + 4 * (i + u * stride));
 #pragma unroll
-            for (int u = 0; u < 4; ++u) if (b + u * 256 < niv) vb[u] = rb_ld256(s + 4 * (b + u * 256));
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) if (a + u * 256 < niv) rb_st256(d + 4 * (a + u * 256), va[u]);
-        if (second) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) if (b + u * 256 < niv) rb_st256(d + 4 * (b + u * 256), vb[u]);
-        }
+        for (int u = 0; u < 8; ++u) rb_st256(d + 4 * (i + u * stride), v[u]);
     }
+    for (; i < niv; i += stride) rb_st256(d + 4 * i, rb_ld256(s + 4 * i));
 }
 
 int rb_copy3d(rb_ctx *ctx, const double *src, i64 s0, i64 si, i64 sj, i64 sk, double *dst, i64 d0, i64 di, i64 dj,
@@ -471,12 +403,10 @@ int rb_copy3d(rb_ctx *ctx, const double *src, i64 s0, i64 si, i64 sj, i64 sk, do
         const i64 rows = nj * nk, rows_per_cta = 256 >> lg;
         // one row: split it over the CTAs (each takes whole 4-load passes of 256 lanes)
         if (rows == 1 && niv >= 4096) {
-            const i64 per = 1024; // vectors per CTA pass (256 lanes x 4 loads)
-            i64 blocks = rb_cdiv(niv, per);
+            i64 blocks = rb_cdiv(niv, 256 * 8);
             const i64 cap = (i64)ctx->num_sms * 32;
-            const i64 chunks = blocks;
             if (blocks > cap) blocks = cap;
-            rb_copy_flat4_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(s, d, niv, chunks);
+            rb_copy_flat4_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(s, d, niv);
             RB_LAUNCHED(ctx);
             return RB_OK;
         }

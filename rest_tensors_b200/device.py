@@ -214,6 +214,12 @@ class Context:
         check(lib.rb_copy_rr(self.h, xl, yl, zl, _p(f), fx, fy, fz, fxs, fys, fzs, _p(t), tx, ty, tz, txs, tys, tzs),
               "rb_copy_rr")
 
+    def erifold4_chunk_copy(self, eri, size0, size1, ld, ranges, buf, mode) -> None:
+        """ERIFold4 chunk scatter on device buffers (src/eri.rs:266-372); ranges = ((i0, i1), (j0, j1), (k0, k1), (l0, l1))"""
+        (i0, i1), (j0, j1), (k0, k1), (l0, l1) = ranges
+        check(lib.rb_erifold4_chunk_copy(self.h, _p(eri), size0, size1, ld, i0, i1 - i0, j0, j1 - j0, k0, k1 - k0, l0, l1 - l0,
+                                         _p(buf), mode), "rb_erifold4_chunk_copy")
+
     def ri_transpose(self, inp, i, j, k, which, out) -> None:
         check(lib.rb_ri_transpose(self.h, _p(inp), i, j, k, which, _p(out)), "rb_ri_transpose")
 

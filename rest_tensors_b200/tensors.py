@@ -6,7 +6,7 @@ behaviour as the reference's Rust structs, so that the parity tests read like th
     RIFull        src/ri.rs:18-433
     MatrixFull    src/matrix/mod.rs:472-480, src/matrix/matrixfull.rs
     MatrixUpper   src/matrix/matrixupper.rs:231-420, src/index.rs:209-233
-    MatrixFullSlice(Mut), MatrixUpperSlice, MatrixUpperStepBy, map_upper_to_full, map_full_to_upper
+    MatrixFullSlice(Mut), MatrixUpperSlice, ERIFold4, MatrixUpperStepBy, map_upper_to_full, map_full_to_upper
     _dgemm, _dgemm_full, _dgemm_full_new, _dsyrk, _dsymm, _dgemv, general_check_shape,
     _dgemm_nn(_serial), _dgemm_tn(_serial), _dgemm_tn_v02            src/matrix/matrix_blas_lapack.rs
     ri_ao2mo_f, general_dgemm_f, special_dgemm_f_01, matr_copy, ...   src/external_libs/mod.rs
@@ -738,6 +738,68 @@ class MatrixUpperSlice:
         src = np.ascontiguousarray(self.data)
         check(lib.rb_host_to_matrixfull(_ptr(src), self.size, _ptr(out.data)), "MatrixUpperSlice::to_matrixfull")
         return out
+
+
+class ERIFold4:
+    """src/eri.rs:170-373: (ij|kl) with both index pairs folded -- a column-major [npair_ij, npair_kl] tensor,
+    ``indicing = [1, size[0]]``, packed pair index ``j(j+1)/2 + i``.  The chunk scatters run on the GPU (csrc/rb_eri.cu)."""
+
+    def __init__(self, size, data: np.ndarray):
+        self.size = [int(size[0]), int(size[1])]
+        self.indicing = [1, self.size[0]]
+        self.data = data
+
+    @staticmethod
+    def new(size, new_default: float) -> "ERIFold4":
+        return ERIFold4(size, np.full(int(size[0]) * int(size[1]), float(new_default), dtype=np.float64))
+
+    @staticmethod
+    def from_vec_unchecked(size, new_vec) -> "ERIFold4":
+        return ERIFold4(size, _f64(new_vec))
+
+    @staticmethod
+    def from_vec(size, new_vec) -> Optional["ERIFold4"]:
+        """eri.rs:204-218: panics when the vector is shorter than the tensor, warns (and keeps it) when it is longer"""
+        t = ERIFold4.from_vec_unchecked(size, new_vec)
+        ln = t.indicing[1] * t.size[1]
+        if ln > t.data.size:
+            raise ValueError("Error: inconsistency happens when formating a tensor from a given vector, (length from size, "
+                             f"length of new vector) = ({ln},{t.data.size})")
+        if ln < t.data.size:
+            print(f"Waring: the vector size ({t.data.size}) is larger for the size of the new tensor ({ln})")
+        return t
+
+    def get_reducing_matrix(self, i_reduced: int) -> "MatrixUpperSlice":
+        """eri.rs:229-236 (and the `_mut` form 219-227): column i_reduced as a packed-upper view (zero copy)"""
+        if not 0 <= i_reduced < self.size[1]:
+            raise IndexError("ERIFold4::get_reducing_matrix: index2d([0, i_reduced]) is None")
+        p0 = i_reduced * self.indicing[1]
+        v = MatrixUpperSlice(self.data[p0:p0 + self.indicing[1]])
+        v.size = self.size[0]
+        return v
+
+    get_reducing_matrix_mut = get_reducing_matrix
+
+    def _scatter(self, ranges, buf, mode: int, what: str) -> None:
+        (i0, i1), (j0, j1), (k0, k1), (l0, l1) = [(int(r[0]), int(r[1])) for r in ranges]
+        need = (i1 - i0) * (j1 - j0) * (k1 - k0) * (l1 - l0)
+        b = _f64(buf)
+        if b.size < need:
+            raise ValueError(f"{what}: the local block holds {b.size} elements, the ranges describe {need}")
+        check(lib.rb_host_erifold4_chunk_copy(_ptr(self.data), self.size[0], self.size[1], i0, i1 - i0, j0, j1 - j0, k0, k1 - k0,
+                                              l0, l1 - l0, _ptr(b), mode), what)
+
+    def chunk_copy_from_local_erifull(self, dim: int, d1: Range, d2: Range, d3: Range, d4: Range, buf) -> None:
+        """eri.rs:266-305: dense local block [|d1|, |d2|, |d3|, |d4|] -> the elements with k <= l and i <= j.  `dim` is the number
+        of basis functions: dim(dim+1)/2 must be the column length (the reference computes slice starts with it)."""
+        if dim * (dim + 1) // 2 != self.size[0]:
+            raise ValueError("chunk_copy_from_local_erifull: dim(dim+1)/2 differs from the column length of the tensor")
+        self._scatter((d1, d2, d3, d4), buf, 0, "ERIFold4::chunk_copy_from_local_erifull")
+
+    def chunk_copy_from_a_full_vector(self, ranges, buf) -> None:
+        """eri.rs:308-372: the libcint shell-quartet scatter (ranges[0].start < ranges[1].start: whole (i, j) block;
+        equal starts: the local upper triangle; otherwise nothing)"""
+        self._scatter(ranges, buf, 1, "ERIFold4::chunk_copy_from_a_full_vector")
 
 
 class MatrixUpperStepBy:

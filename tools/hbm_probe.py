@@ -65,6 +65,12 @@ def main():
             return make
         for kind, nbytes in (("unpack", (np_ + n * n) * 8), ("pack", 2 * np_ * 8), ("transpose", 2 * n * n * 8), ("copy_mm", 2 * n * n * 8)):
             out[f"{kind}_{n}_stream_gbs"] = round(nbytes / stream_ms(mk(kind), nbytes) / 1e6, 1)
+    # the flat 256-bit copy on the micro-benchmark's footprint (1 GiB in, 1 GiB out): separates kernel structure from size effects
+    nn = 11584
+    big = ctx.empty(nn * nn); big2 = ctx.empty(nn * nn)
+    out["copy_flat_1GiB_gbs"] = round(2 * nn * nn * 8 / best_ms(lambda: ctx.copy_mm(nn, nn, big, nn, nn, 0, 0, big2, nn, nn, 0, 0)) / 1e6, 1)
+    out["transpose_1GiB_gbs"] = round(2 * nn * nn * 8 / best_ms(lambda: ctx.matrix_transpose(big, nn, nn, big2)) / 1e6, 1)
+    del big, big2
     I, J, K = 600, 600, 400
     t = ctx.empty(I * J * K); u = ctx.empty(I * J * K); ctx.fill_linear(t, I * J * K, 5, 0, 1.0)
     for which, name in enumerate(["jik", "jki", "kji", "ikj"]):
