@@ -368,15 +368,13 @@ __global__ void __launch_bounds__(256) rb_copy3d_kernel(const double *__restrict
 __global__ void __launch_bounds__(256) rb_copy_flat4_kernel(const double *__restrict__ s, double *__restrict__ d, i64 niv)
 {
     const i64 stride = (i64)gridDim.x * blockDim.x;
-    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    for (; i + 7 * stride < niv; i += 8 * stride) {
-        rb_d4 v[8];
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < niv; i += 8 * stride) {
+        rb_d4 v[8]; // the last pass is predicated, not serialised: its loads are in flight together as well
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = rb_ld256(s + 4 * (i + u * stride));
+        for (int u = 0; u < 8; ++u) if (i + u * stride < niv) v[u] = rb_ld256(s + 4 * (i + u * stride));
 #pragma unroll
-        for (int u = 0; u < 8; ++u) rb_st256(d + 4 * (i + u * stride), v[u]);
+        for (int u = 0; u < 8; ++u) if (i + u * stride < niv) rb_st256(d + 4 * (i + u * stride), v[u]);
     }
-    for (; i < niv; i += stride) rb_st256(d + 4 * i, rb_ld256(s + 4 * i));
 }
 
 int rb_copy3d(rb_ctx *ctx, const double *src, i64 s0, i64 si, i64 sj, i64 sk, double *dst, i64 d0, i64 di, i64 dj,

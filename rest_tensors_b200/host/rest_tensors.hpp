@@ -58,6 +58,30 @@ struct MatrixFull {
         return m;
     }
     bool check_shape(const MatrixFull &o) const { return size == o.size; }
+    // matrixfull.rs:242-253: same data, new shape (the element count must agree)
+    void reshape(std::array<size_t, 2> new_size)
+    {
+        if (new_size[0] * new_size[1] != data.size()) throw std::runtime_error("Error: the reshaped matrix has a different number of elements");
+        size = new_size;
+        indicing = {1, new_size[0]};
+    }
+    inline RIFull to_rifull(size_t i, size_t j, size_t k) const; // matrixfull.rs:674-686
+    // matrixfull.rs:1398-1406 / matrix_blas_lapack.rs:739-774: self = alpha op(a) op(b) + beta self, NO shape check (like the reference)
+    void lapack_dgemm(const MatrixFull &a, const MatrixFull &b, char opa, char opb, double alpha, double beta)
+    {
+        const size_t m = size[0], n = size[1], k = (opa == 'N' || opa == 'n') ? a.size[1] : a.size[0];
+        rb_check(rb_host_dgemm(opa, opb, (int)m, (int)n, (int)k, alpha, a.data.data(), (int)std::max<size_t>(a.size[0], 1),
+                               b.data.data(), (int)std::max<size_t>(b.size[0], 1), beta, data.data(), (int)std::max<size_t>(m, 1)),
+                 "lapack_dgemm");
+    }
+    // matrix_blas_lapack.rs:714-730 (MatrixFullSlice::ddot): a * b as a new matrix, None on an inner-dimension mismatch
+    std::optional<MatrixFull> ddot(const MatrixFull &b) const
+    {
+        if (size[1] != b.size[0]) return std::nullopt;
+        MatrixFull c = make({size[0], b.size[1]}, 0.0);
+        c.lapack_dgemm(*this, b, 'N', 'N', 1.0, 1.0); // beta = 1 on a zeroed C, as the reference does
+        return c;
+    }
 
     MatrixFull transpose() const // matrixfull.rs:579-596
     {
@@ -207,6 +231,32 @@ struct RIFull {
         size_t chunk = size[0] * size[1];
         return {data.data() + chunk * r.first, data.data() + chunk * r.second};
     }
+    // ri.rs:102-115: columns `cols` of slab p (start pointer, element count) -- a zero-copy view
+    std::pair<const double *, size_t> get_reducing_matrix_columns(Range cols, size_t p) const
+    {
+        return {data.data() + p * indicing[2] + size[0] * cols.first, size[0] * rlen(cols)};
+    }
+    // ri.rs:117-128: the flattened x-runs of a sub-box, z outer / y inner: (pointer, length) per run, zero copy
+    std::vector<std::pair<const double *, size_t>> get_slices(Range x, Range y, Range z) const
+    {
+        std::vector<std::pair<const double *, size_t>> runs;
+        runs.reserve(rlen(y) * rlen(z));
+        for (size_t zz = z.first; zz < z.second; ++zz)
+            for (size_t yy = y.first; yy < y.second; ++yy)
+                runs.emplace_back(data.data() + x.first + yy * indicing[1] + zz * indicing[2], rlen(x));
+        return runs;
+    }
+    // ri.rs:309-326: metadata-only reshapes (the reference clones the data; so does this)
+    MatrixFull rifull_to_matfull_ij_k() const { return MatrixFull::from_vec({size[0] * size[1], size[2]}, data); }
+    MatrixFull rifull_to_matfull_i_jk() const { return MatrixFull::from_vec({size[0], size[1] * size[2]}, data); }
+    // north-star occ-vir form: out[P, a, b] = sum C_L[mu, a] A[mu, nu, P] C_R[nu, b]
+    RIFull ao2mo_rect(const MatrixFull &c_left, const MatrixFull &c_right) const
+    {
+        RIFull mo = make({size[2], c_left.size[1], c_right.size[1]}, 0.0);
+        rb_check(rb_host_ri_ao2mo(c_left.data.data(), (int)c_left.size[1], c_right.data.data(), (int)c_right.size[1], data.data(),
+                                  mo.data.data(), (int)size[0], (int)size[2]), "ao2mo_rect");
+        return mo;
+    }
     // ri.rs:356-408
     RIFull ao2mo(const MatrixFull &eigenvector) const { return ao2mo_v02(eigenvector); }
     RIFull ao2mo_v02(const MatrixFull &eigenvector) const
@@ -311,6 +361,55 @@ struct RIFull {
     }
 };
 
+inline RIFull MatrixFull::to_rifull(size_t i, size_t j, size_t k) const
+{
+    if (i * j * k != data.size()) throw std::runtime_error("Error: the RIFull shape does not hold the matrix elements");
+    RIFull r = RIFull::from_vec({i, j, k}, data);
+    r.indicing = {1, i, j}; // the reference's quirk (matrixfull.rs:681-685): [1, i, j], not [1, i, i*j]
+    return r;
+}
+
+// ERIFold4 (eri.rs:170-373): (ij|kl) with both pairs folded, column-major [npair, npair]
+struct ERIFold4 {
+    std::array<size_t, 2> size{0, 0};
+    std::array<size_t, 2> indicing{0, 0};
+    std::vector<double> data;
+    static ERIFold4 make(std::array<size_t, 2> size, double v)
+    {
+        ERIFold4 t;
+        t.size = size; t.indicing = {1, size[0]};
+        t.data.assign(size[0] * size[1], v);
+        return t;
+    }
+    // eri.rs:308-372 (mode 1) / 266-305 (mode 0)
+    void chunk_copy_from_a_full_vector(const std::array<Range, 4> &r, const std::vector<double> &buf) { scatter(r, buf, 1); }
+    void chunk_copy_from_local_erifull(size_t dim, Range d1, Range d2, Range d3, Range d4, const std::vector<double> &buf)
+    {
+        if (dim * (dim + 1) / 2 != size[0]) throw std::runtime_error("chunk_copy_from_local_erifull: dim does not match the tensor");
+        scatter({d1, d2, d3, d4}, buf, 0);
+    }
+
+  private:
+    void scatter(const std::array<Range, 4> &r, const std::vector<double> &buf, int mode)
+    {
+        if (buf.size() < rlen(r[0]) * rlen(r[1]) * rlen(r[2]) * rlen(r[3])) throw std::runtime_error("ERIFold4: the local block is too short");
+        rb_check(rb_host_erifold4_chunk_copy(data.data(), (int64_t)size[0], (int64_t)size[1], (int)r[0].first, (int)rlen(r[0]),
+                                             (int)r[1].first, (int)rlen(r[1]), (int)r[2].first, (int)rlen(r[2]), (int)r[3].first,
+                                             (int)rlen(r[3]), buf.data(), mode), "ERIFold4 chunk copy");
+    }
+};
+
+// matrix_blas_lapack.rs:256-278: allocates C with the op-dependent shape
+inline MatrixFull _dgemm_full_new(const MatrixFull &a, char opa, const MatrixFull &b, char opb, double alpha, double beta);
+// matrix_blas_lapack.rs:354-378: no checks, like the reference
+inline void _dsymm(const MatrixFull &a, const MatrixFull &b, MatrixFull &c, char side, char uplo, double alpha, double beta)
+{
+    const size_t m = c.size[0], n = c.size[1];
+    const size_t lda = (side == 'L' || side == 'l') ? m : n;
+    rb_check(rb_host_dsymm(side, uplo, (int)m, (int)n, alpha, a.data.data(), (int)std::max<size_t>(lda, 1), b.data.data(),
+                           (int)std::max<size_t>(m, 1), beta, c.data.data(), (int)std::max<size_t>(m, 1)), "_dsymm");
+}
+
 // matrix_blas_lapack.rs:180-252
 inline void _dgemm_full(const MatrixFull &a, char opa, const MatrixFull &b, char opb, MatrixFull &c, double alpha, double beta)
 {
@@ -322,6 +421,13 @@ inline void _dgemm_full(const MatrixFull &a, char opa, const MatrixFull &b, char
     size_t ldb = opb == 'N' ? std::max<size_t>(k, 1) : std::max<size_t>(n, 1);
     rb_check(rb_host_dgemm(opa, opb, (int)m, (int)n, (int)k, alpha, a.data.data(), (int)lda, b.data.data(), (int)ldb, beta,
                            c.data.data(), (int)std::max<size_t>(m, 1)), "_dgemm_full");
+}
+inline MatrixFull _dgemm_full_new(const MatrixFull &a, char opa, const MatrixFull &b, char opb, double alpha, double beta)
+{
+    const size_t m = opa == 'N' ? a.size[0] : a.size[1], n = opb == 'N' ? b.size[1] : b.size[0];
+    MatrixFull c = MatrixFull::make({m, n}, 0.0);
+    _dgemm_full(a, opa, b, opb, c, alpha, beta);
+    return c;
 }
 // matrix_blas_lapack.rs:392-413
 inline void _dsyrk(const MatrixFull &a, MatrixFull &c, char uplo, char trans, double alpha, double beta)

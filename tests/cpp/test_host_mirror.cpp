@@ -138,6 +138,42 @@ int main()
         for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) dev = std::max(dev, std::fabs(u[(size_t)i + (size_t)j * n] - (i == j ? 1.0 : 0.0)));
         CHECK(dev < 1e-11 * n, "lapack_power(-0.5): X S X = I");
     }
+    // round-2 additions to the mirror: occ-vir ao2mo == sub-block of the square one, _dgemm_full_new / ddot / lapack_dgemm, views,
+    // metadata reshapes, ERIFold4 shell-quartet scatter
+    {
+        const int nb = 24, nx = 10, no = 5;
+        auto ri = RIFull::from_vec({(size_t)nb, (size_t)nb, (size_t)nx}, fill((size_t)nb * nb * nx, 31));
+        auto c = MatrixFull::from_vec({(size_t)nb, (size_t)nb}, fill((size_t)nb * nb, 32, 0.2));
+        auto sq = ri.ao2mo(c);
+        auto cl = MatrixFull::from_vec({(size_t)nb, (size_t)no}, std::vector<double>(c.data.begin(), c.data.begin() + nb * no));
+        auto cr = MatrixFull::from_vec({(size_t)nb, (size_t)(nb - no)}, std::vector<double>(c.data.begin() + nb * no, c.data.end()));
+        auto ov = ri.ao2mo_rect(cl, cr);
+        bool same = ov.size[0] == (size_t)nx && ov.size[1] == (size_t)no && ov.size[2] == (size_t)(nb - no);
+        for (int b = 0; b < nb - no && same; ++b)
+            for (int a = 0; a < no && same; ++a)
+                for (int p = 0; p < nx; ++p)
+                    same = same && std::fabs(ov.data[p + (size_t)nx * (a + (size_t)no * b)] - sq.data[p + (size_t)nx * (a + (size_t)nb * (b + no))]) <= 1e-12;
+        CHECK(same, "ao2mo_rect == occ-vir block of the square transform");
+        auto prod = _dgemm_full_new(c, 'T', c, 'N', 1.0, 0.0);
+        auto dd = c.transpose().ddot(c);
+        CHECK(dd.has_value() && rel_err(dd->data, prod.data) < 1e-13, "ddot == _dgemm_full_new");
+        CHECK(!c.ddot(MatrixFull::make({3, 3}, 1.0)).has_value(), "ddot shape mismatch -> None");
+        auto ijk = ri.rifull_to_matfull_ij_k();
+        CHECK(ijk.size[0] == (size_t)nb * nb && ijk.size[1] == (size_t)nx && ijk.data == ri.data, "rifull_to_matfull_ij_k");
+        auto back = ijk.to_rifull(nb, nb, nx);
+        CHECK(back.indicing[2] == (size_t)nb && back.data == ri.data, "to_rifull keeps the reference's indicing quirk");
+        auto runs = ri.get_slices({2, 7}, {1, 3}, {4, 6});
+        CHECK(runs.size() == 4 && runs[0].second == 5 && runs[1].first == ri.data.data() + 2 + 2 * nb + 4 * nb * nb, "get_slices run order");
+        const size_t dim = 7, npair = dim * (dim + 1) / 2;
+        auto g = fill(dim * dim * dim * dim, 33);
+        auto eri = ERIFold4::make({npair, npair}, -1.0);
+        std::array<Range, 4> whole = {Range{0, dim}, Range{0, dim}, Range{0, dim}, Range{0, dim}};
+        eri.chunk_copy_from_a_full_vector(whole, g);
+        bool ok4 = true;
+        for (size_t l = 0; l < dim; ++l) for (size_t k = 0; k <= l; ++k) for (size_t j = 0; j < dim; ++j) for (size_t i = 0; i <= j; ++i)
+            ok4 = ok4 && eri.data[(j * (j + 1) / 2 + i) + npair * (l * (l + 1) / 2 + k)] == g[i + dim * (j + dim * (k + dim * l))];
+        CHECK(ok4, "ERIFold4 chunk_copy_from_a_full_vector (whole tensor as one block)");
+    }
     // panics
     bool threw = false;
     try { RIFull::from_vec({3, 2, 2}, std::vector<double>(11)); } catch (const std::runtime_error &) { threw = true; }
