@@ -356,6 +356,15 @@ int rb_fill_ri3ao_symm(rb_ctx *ctx, double *a, int64_t nb, int64_t p_lo, int64_t
  *   rb_ri_plan_chunk    : P-chunk length of the RI contractions for nx slabs of bytes_per_slab workspace each under a
  *                         workspace budget (tile_m != 0: P is the M index of a GEMM tile, cheapest tiling wins) */
 int64_t rb_gemm_plan_splits(int64_t m, int64_t n, int64_t k, int64_t batch, int tri, int num_sms);
+/* 1 when the same product would run as stream-K (every CTA an equal share of the COST of the tile x k-step space, pieces summed in a
+ * fixed order) instead of a uniform split; costs_out (NULL or 4 doubles): estimated makespans of the uniform split and of stream-K
+ * in full-tile k steps, the CTA count and the largest piece count of the stream-K plan */
+int rb_gemm_plan_stream_k(int64_t m, int64_t n, int64_t k, int64_t batch, int tri, int num_sms, double *costs_out);
+/* the stream-K partition itself (for tests): CTA c works on the steps from (cta_tile[c], cta_step[c]) up to (cta_tile[c+1], cta_step[c+1]);
+ * tile t is covered by tile_pieces[t] consecutive CTAs starting with tile_first[t].  Arrays of >= 161 / 161 / 592 / 592 entries.
+ * Returns the CTA count, 0 when the shape does not qualify. */
+int rb_gemm_stream_k_tables(int64_t m, int64_t n, int64_t k, int64_t batch, int tri, int num_sms, unsigned *cta_step,
+                            unsigned short *cta_tile, unsigned char *tile_first, unsigned char *tile_pieces);
 int64_t rb_ri_plan_chunk(int64_t nx, int64_t bytes_per_slab, int64_t budget_bytes, int tile_m);
 
 /* FP64 pipe micro-benchmarks used by bench.py for the roofline denominator: returns achieved TFLOP/s of a

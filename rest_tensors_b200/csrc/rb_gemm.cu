@@ -49,6 +49,8 @@
 //
 // A second, generic kernel (plain loads, any alignment / leading dimension) covers operands TMA cannot describe.
 #include "rb_common.cuh"
+#include <cmath>
+#include <vector>
 
 namespace {
 
@@ -63,6 +65,16 @@ constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 64 /*ba
 constexpr int NUM_CONSUMER_WARPS = 8;
 constexpr int NUM_THREADS = (NUM_CONSUMER_WARPS + 4) * 32; // 2 consumer warpgroups + 1 producer warpgroup
 constexpr int GROUP_M = 8;
+
+// Stream-K tables (host-built, passed by value): CTA c works on the steps from (cta_tile[c], cta_step[c]) up to, not including,
+// (cta_tile[c+1], cta_step[c+1]) of the tile-major (tile, 32-deep k step) space; tile t is covered by tile_pieces[t] consecutive CTAs
+// starting with tile_first[t].
+constexpr int SK_MAX_TILES = 592, SK_MAX_CTAS = 160;
+struct SkTables {
+    unsigned cta_step[SK_MAX_CTAS + 1];
+    unsigned short cta_tile[SK_MAX_CTAS + 1];
+    unsigned char tile_first[SK_MAX_TILES], tile_pieces[SK_MAX_TILES];
+};
 
 struct GemmParams {
     i64 m, n, k;
@@ -85,6 +97,13 @@ struct GemmParams {
     int pack_m;
     i64 bpb, total_blocks;     // 16-row blocks per batch, batch * bpb
     int same_ab;               // tri != 0 and A, B are the same matrix: diagonal tiles load one operand tile only
+    // Stream-K: every CTA takes an equal share of the COST of the tile x k-step space (a step of a ragged or diagonal tile weighs what
+    // it was measured to cost); a tile that falls into one CTA is written straight to C, the others leave one partial per piece (piece
+    // index = CTA - first CTA of the tile) and rb_streamk_reduce_kernel sums them in piece order.  Static partition: no scheduler, every
+    // piece is reproducible.  `splits` holds the largest piece count (the partial buffer is [piece][batch][n][ldp] as for split-K).
+    int stream_k;
+    i64 sk_ksteps;             // 32-deep k steps per tile
+    SkTables sk;
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------
@@ -138,10 +157,8 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b)
 }
 
 // work item -> (batch, tm, tn, split)
-__device__ __forceinline__ void decode_item(const GemmParams &p, i64 item, i64 &b, i64 &tm, i64 &tn, i64 &sp)
+__device__ __forceinline__ void decode_tile(const GemmParams &p, i64 tile, i64 &b, i64 &tm, i64 &tn)
 {
-    sp = item % p.splits;
-    i64 tile = item / p.splits;
     b = tile / p.tiles_per_batch;
     i64 t = tile - b * p.tiles_per_batch;
     if (p.tri == 0) {
@@ -160,6 +177,11 @@ __device__ __forceinline__ void decode_item(const GemmParams &p, i64 item, i64 &
         i64 lo = t - hi * (hi + 1) / 2;
         if (p.tri == 1) { tm = lo; tn = hi; } else { tm = hi; tn = lo; }
     }
+}
+__device__ __forceinline__ void decode_item(const GemmParams &p, i64 item, i64 &b, i64 &tm, i64 &tn, i64 &sp)
+{
+    sp = item % p.splits;
+    decode_tile(p, item / p.splits, b, tm, tn);
 }
 
 // One k8 block (two DMMA k4 steps) for a warp that owns NI x NJ 16x16 blocks (compile-time, so that every DMMA is
@@ -408,12 +430,29 @@ rb_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             // cost -- ragged edges, triangles -- so a static round-robin leaves SMs idle at the end).  The next item is
             // fetched one tile ahead so that the atomic's latency never sits between two tiles.
             i64 item = blockIdx.x;
-            while (item < p.total_items) {
-                const i64 next = (i64)gridDim.x + (i64)atomicAdd(p.sched, 1ULL);
-                i64 b, tm, tn, sp;
-                decode_item(p, item, b, tm, tn, sp);
-                const i64 k_begin = sp * p.kper;
-                const i64 k_end = (k_begin + p.kper < p.k) ? k_begin + p.kper : p.k;
+            unsigned sk_t = 0, sk_s = 0, sk_t_end = 0, sk_s_end = 0; // stream-K: this CTA's range of (tile, step)
+            if (p.stream_k) {
+                sk_t = p.sk.cta_tile[blockIdx.x]; sk_s = p.sk.cta_step[blockIdx.x];
+                sk_t_end = p.sk.cta_tile[blockIdx.x + 1]; sk_s_end = p.sk.cta_step[blockIdx.x + 1];
+            }
+            while (p.stream_k ? (sk_t < sk_t_end || (sk_t == sk_t_end && sk_s < sk_s_end)) : item < p.total_items) {
+                i64 next = 0;
+                i64 b, tm, tn, sp, k_begin, k_end;
+                bool whole = false;
+                if (p.stream_k) {
+                    const i64 s1 = (sk_t == sk_t_end) ? (i64)sk_s_end : p.sk_ksteps;
+                    decode_tile(p, (i64)sk_t, b, tm, tn);
+                    k_begin = (i64)sk_s * BK;
+                    k_end = (s1 * BK < p.k) ? s1 * BK : p.k;
+                    sp = (i64)blockIdx.x - (i64)p.sk.tile_first[sk_t]; // piece index inside the tile
+                    whole = p.sk.tile_pieces[sk_t] == 1;
+                    ++sk_t; sk_s = 0;
+                } else {
+                    next = (i64)gridDim.x + (i64)atomicAdd(p.sched, 1ULL);
+                    decode_item(p, item, b, tm, tn, sp);
+                    k_begin = sp * p.kper;
+                    k_end = (k_begin + p.kper < p.k) ? k_begin + p.kper : p.k;
+                }
                 const int ba = p.a_batched ? (int)b : 0, bb = p.b_batched ? (int)b : 0;
                 // Tile descriptor for the consumers (they do no index arithmetic of their own).  Valid 16x16 blocks of
                 // the tile (edge tiles are ragged; TMA zero-fills the rest) and the gm x gn warp grid that gives the
@@ -435,7 +474,7 @@ rb_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 const bool diag = p.tri != 0 && tm == tn;
                 const bool skip_b = diag && p.same_ab;
                 const uint32_t grid_code = (uint32_t)lgm | ((uint32_t)rpg << 4) | ((uint32_t)cpg << 8) | ((uint32_t)mb << 12) |
-                                           ((uint32_t)nbk << 16) | (diag ? (1u << 20) : 0u);
+                                           ((uint32_t)nbk << 16) | (diag ? (1u << 20) : 0u) | (whole ? (1u << 21) : 0u);
                 const uint32_t tx_bytes = (PACK ? (uint32_t)mb * (16 * BK * 8) : (uint32_t)A_TILE_BYTES) + (skip_b ? 0u : (uint32_t)B_TILE_BYTES);
                 // packed M: (batch, first row) of the tile's first 16-row block
                 int pk_b0 = 0, pk_r0 = 0;
@@ -493,8 +532,8 @@ rb_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(slot + 16), "r"(0xffffffffu), "r"(0u), "r"(0u), "r"(0u) : "memory");
                 mbar_arrive(full);
             }
-            // the last CTA to run dry re-arms the scheduler for the next launch on this stream
-            if (atomicAdd(p.sched + 1, 1ULL) == (unsigned long long)gridDim.x - 1ULL) {
+            // the last CTA to run dry re-arms the scheduler for the next launch on this stream (stream-K never touched it)
+            if (!p.stream_k && atomicAdd(p.sched + 1, 1ULL) == (unsigned long long)gridDim.x - 1ULL) {
                 p.sched[0] = 0ULL;
                 p.sched[1] = 0ULL;
                 __threadfence();
@@ -559,7 +598,8 @@ rb_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         double *cb;
         i64 ldc, cstride;
         double alpha, beta;
-        if (p.splits > 1) {
+        const bool to_partial = p.splits > 1 && ((ucode >> 21) & 1u) == 0u; // stream-K: a tile owned by one CTA goes straight to C
+        if (to_partial) {
             cstride = p.n * p.ldp;
             cb = p.partial + (sp * p.batch + bidx) * cstride;
             ldc = p.ldp; alpha = 1.0; beta = 0.0;
@@ -569,7 +609,7 @@ rb_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             ldc = p.ldc; alpha = p.alpha; beta = p.beta;
         }
         const bool vec_ok = ((ldc & 1) == 0) && ((((uintptr_t)cb) & 15) == 0) && (!PACK || (cstride & 1) == 0);
-        const int tri = (p.splits > 1) ? 0 : p.tri;
+        const int tri = to_partial ? 0 : p.tri;
 
         if ((ucode >> 20) & 1u) {
             // ---- diagonal tile of a triangular product: this warp's share of the mb(mb+1)/2 blocks on or above (tri 1)
@@ -663,25 +703,50 @@ rb_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
 }
 
-// ---- split-K reduction (fixed order => deterministic) ------------------------------------------------------------
-__global__ void __launch_bounds__(256) rb_splitk_reduce_kernel(const double *__restrict__ partial, i64 ldp, i64 splits,
-                                                               i64 m, i64 n, i64 batch, double alpha, double beta,
-                                                               double *__restrict__ c, i64 ldc, i64 stride_c, int tri)
+// ---- reduction of the split-K / stream-K partials (fixed order => deterministic) -------------------------------------------
+// partial[piece][batch][n][ldp] -> C = alpha * sum_pieces + beta * C.  A thread owns two consecutive rows of a column (16-byte loads of
+// the partials, ldp is even; 8 pieces in flight, added in piece order).  SK: the piece count is per tile (SkTables) and tiles owned by
+// one CTA were written by the GEMM kernel itself and are skipped.  No integer divisions: (row pair, column, batch) come from the grid.
+template <bool SK>
+__global__ void __launch_bounds__(256) rb_partial_reduce_kernel(const double *__restrict__ partial, i64 ldp, int splits, i64 m, i64 n,
+                                                                i64 batch, double alpha, double beta, double *__restrict__ c, i64 ldc,
+                                                                i64 stride_c, int tri, int tiles_m, int tiles_n, int tiles_per_batch,
+                                                                const __grid_constant__ SkTables sk)
 {
-    i64 total = m * n * batch;
-    i64 stride = (i64)gridDim.x * blockDim.x;
-    i64 split_stride = batch * n * ldp;
-    for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
-        i64 i = e % m, r = e / m;
-        i64 j = r % n, b = r / n;
-        if (tri == 1 && i > j) continue;
-        if (tri == 2 && i < j) continue;
-        const double *pp = partial + (b * n + j) * ldp + i;
-        double s = 0.0;
-        for (i64 sp = 0; sp < splits; ++sp) s += pp[sp * split_stride];
-        double *cp = c + b * stride_c + i + j * ldc;
-        *cp = (beta == 0.0) ? alpha * s : alpha * s + beta * (*cp);
-    }
+    const i64 split_stride = batch * n * ldp;
+    for (i64 b = blockIdx.z; b < batch; b += gridDim.z)
+        for (i64 j = blockIdx.y; j < n; j += gridDim.y) {
+            const int tn = (int)(j >> 7);
+            for (i64 i = 2 * ((i64)blockIdx.x * blockDim.x + threadIdx.x); i < m; i += 2 * (i64)gridDim.x * blockDim.x) {
+                bool v0 = true, v1 = i + 1 < m;
+                if (tri == 1) { v0 = i <= j; v1 = v1 && i + 1 <= j; }
+                else if (tri == 2) { v0 = i >= j; v1 = v1 && i + 1 >= j; }
+                if (!v0 && !v1) continue;
+                int np = splits;
+                if (SK) {
+                    const int tm = (int)(i >> 7); // rows i, i + 1 share a tile (i is even)
+                    int t;
+                    if (tri == 0) {
+                        const int grp = tm / GROUP_M, first_m = grp * GROUP_M;
+                        const int gsz = tiles_m - first_m < GROUP_M ? tiles_m - first_m : GROUP_M;
+                        t = grp * GROUP_M * tiles_n + tn * gsz + (tm - first_m);
+                    } else if (tri == 1) t = tn * (tn + 1) / 2 + tm;
+                    else t = tm * (tm + 1) / 2 + tn;
+                    np = sk.tile_pieces[(int)b * tiles_per_batch + t];
+                    if (np == 1) continue;
+                }
+                const double *pp = partial + (b * n + j) * ldp + i;
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll 8
+                for (int q = 0; q < np; ++q) {
+                    const double2 v = *reinterpret_cast<const double2 *>(pp + (i64)q * split_stride);
+                    s0 += v.x; s1 += v.y;
+                }
+                double *cp = c + b * stride_c + i + j * ldc;
+                if (v0) cp[0] = (beta == 0.0) ? alpha * s0 : alpha * s0 + beta * cp[0];
+                if (v1) cp[1] = (beta == 0.0) ? alpha * s1 : alpha * s1 + beta * cp[1];
+            }
+        }
 }
 
 // ---- generic kernel: any alignment / leading dimension, plain loads -------------------------------------------------
@@ -881,6 +946,190 @@ i64 plan_splits(i64 m, i64 n, i64 k, i64 batch, int tri, int num_sms, bool packe
     return rb_cdiv(k, kper);
 }
 
+
+// ---- stream-K planning (host) ---------------------------------------------------------------------------------------------
+// Cost of one 32-deep k step of tile (tm, tn) in 1/64 of a full tile step -- the same weights the split-K model uses (ragged tiles
+// are worked on at 16 x 16 block granularity; diagonal tiles of triangular products as a list of their blocks; measured floor 0.22).
+int tile_weight64(i64 tm, i64 tn, i64 tiles_m, i64 tiles_n, i64 m, i64 n, int tri)
+{
+    const i64 me = m - (tiles_m - 1) * BM, ne = n - (tiles_n - 1) * BN;
+    const int mb = tm == tiles_m - 1 ? (int)((me + 15) >> 4) : 8, nb = tn == tiles_n - 1 ? (int)((ne + 15) >> 4) : 8;
+    double w;
+    if (tri && tm == tn) w = (double)((mb * (mb + 1) / 2 + 7) / 8) / 8.0;
+    else {
+        int best = 1 << 30; // blocks of the busiest warp under the best warp grid (<= 2 x 4 per warp)
+        for (int lg = 3; lg >= 0; --lg) {
+            const int r = (mb + (1 << lg) - 1) >> lg, c = (nb + (8 >> lg) - 1) >> (3 - lg);
+            if (r <= 2 && c <= 4 && r * c < best) best = r * c;
+        }
+        w = (double)best / 8.0;
+    }
+    if (w < 0.22) w = 0.22;
+    int wi = (int)(w * 64.0 + 0.5);
+    return wi > 64 ? 64 : wi;
+}
+
+// tile index (within a batch) -> (tm, tn): the host twin of decode_tile
+void host_decode_tile(i64 t, i64 tiles_m, i64 tiles_n, int tri, i64 &tm, i64 &tn)
+{
+    if (tri == 0) {
+        const i64 per_group = GROUP_M * tiles_n, grp = t / per_group, first_m = grp * GROUP_M;
+        const i64 gsz = tiles_m - first_m < GROUP_M ? tiles_m - first_m : GROUP_M, r = t - grp * per_group;
+        tm = first_m + r % gsz; tn = r / gsz;
+    } else {
+        i64 hi = (i64)((std::sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+        while (hi * (hi + 1) / 2 > t) --hi;
+        while ((hi + 1) * (hi + 2) / 2 <= t) ++hi;
+        const i64 lo = t - hi * (hi + 1) / 2;
+        if (tri == 1) { tm = lo; tn = hi; } else { tm = hi; tn = lo; }
+    }
+}
+
+struct GemmPlan {
+    i64 splits = 1;          // uniform split-K count (stream_k: the largest piece count)
+    bool stream_k = false;
+    int sk_grid = 0;
+    SkTables sk;
+    double cost_split = 0.0, cost_stream_k = 0.0; // estimated makespans in full-tile k steps (diagnostics / tests)
+};
+
+// Makespan of the uniform split under the kernel's dynamic scheduler (list scheduling in work-item order: the first G items are taken
+// statically, every CTA then draws the next item when it runs dry), in full-tile k steps.  The closed-form model of plan_splits picks
+// the split count; this is what it really costs, and what stream-K has to beat.
+double simulate_split_makespan(const std::vector<int> &w64, i64 tiles_per_batch, i64 batch, i64 splits, i64 ksteps, int g)
+{
+    const i64 steps = rb_cdiv(ksteps, splits);
+    std::vector<double> heap((size_t)g, 0.0); // min-heap of CTA finish times
+    auto sift = [&](size_t i) {
+        for (;;) {
+            size_t l = 2 * i + 1, r = l + 1, mn = i;
+            if (l < heap.size() && heap[l] < heap[mn]) mn = l;
+            if (r < heap.size() && heap[r] < heap[mn]) mn = r;
+            if (mn == i) return;
+            std::swap(heap[i], heap[mn]); i = mn;
+        }
+    };
+    double makespan = 0.0;
+    for (i64 b = 0; b < batch; ++b)
+        for (i64 t = 0; t < tiles_per_batch; ++t)
+            for (i64 sp = 0; sp < splits; ++sp) {
+                i64 st = ksteps - sp * steps; if (st > steps) st = steps; if (st <= 0) continue;
+                heap[0] += (double)w64[(size_t)t] / 64.0 * (double)(st + 2);
+                if (heap[0] > makespan) makespan = heap[0];
+                sift(0);
+            }
+    return makespan;
+}
+
+// Build the stream-K tables for `tiles` tiles of ksteps steps each on at most num_sms CTAs; false when the shape does not qualify.
+bool build_stream_k(GemmPlan &pl, const std::vector<int> &w64, i64 tiles_per_batch, i64 batch, i64 ksteps, int num_sms)
+{
+    const i64 tiles = tiles_per_batch * batch;
+    if (tiles > SK_MAX_TILES || num_sms > SK_MAX_CTAS || ksteps >= (1LL << 31)) return false;
+    i64 total = 0;
+    for (i64 t = 0; t < tiles_per_batch; ++t) total += (i64)w64[(size_t)t] * ksteps;
+    total *= batch;
+    i64 g = num_sms;
+    if (total / 64 < g) g = total / 64; // every CTA at least one full-tile step: no empty ranges
+    if (g < 1) return false;
+    // CTA c starts at the first step whose cost interval begins at or after floor(c total / g)
+    i64 t = 0, wt0 = 0; // current tile and the cost at its first step
+    for (i64 c = 0; c <= g; ++c) {
+        const i64 bc = c == g ? total : (i64)((__int128)c * total / g);
+        while (t < tiles && wt0 + (i64)w64[(size_t)(t % tiles_per_batch)] * ksteps <= bc) { wt0 += (i64)w64[(size_t)(t % tiles_per_batch)] * ksteps; ++t; }
+        i64 st = 0;
+        if (t < tiles) {
+            const i64 w = w64[(size_t)(t % tiles_per_batch)];
+            st = (bc - wt0 + w - 1) / w;
+            if (st >= ksteps) { wt0 += w * ksteps; ++t; st = 0; }
+        }
+        pl.sk.cta_tile[c] = (unsigned short)t; pl.sk.cta_step[c] = (unsigned)st;
+    }
+    if (pl.sk.cta_tile[0] != 0 || pl.sk.cta_step[0] != 0 || pl.sk.cta_tile[g] != tiles || pl.sk.cta_step[g] != 0) return false;
+    // pieces per tile; the busiest CTA
+    i64 pmax = 1;
+    double busiest = 0.0;
+    for (i64 u = 0; u < tiles; ++u) { pl.sk.tile_first[u] = 0; pl.sk.tile_pieces[u] = 0; }
+    for (i64 c = 0; c < g; ++c) {
+        i64 ct = pl.sk.cta_tile[c], cs = pl.sk.cta_step[c];
+        const i64 et = pl.sk.cta_tile[c + 1], es = pl.sk.cta_step[c + 1];
+        if (!(ct < et || (ct == et && cs < es))) return false; // an empty range would break the piece numbering
+        double cost = 0.0;
+        while (ct < et || (ct == et && cs < es)) {
+            const i64 s1 = ct == et ? es : ksteps;
+            if (pl.sk.tile_pieces[ct] == 0) pl.sk.tile_first[ct] = (unsigned char)c;
+            if (++pl.sk.tile_pieces[ct] == 0) return false; // > 255 pieces
+            cost += (double)w64[(size_t)(ct % tiles_per_batch)] / 64.0 * (double)(s1 - cs) + 1.5; // + fill / partial store per piece
+            ++ct; cs = 0;
+        }
+        if (cost > busiest) busiest = cost;
+    }
+    for (i64 u = 0; u < tiles; ++u) {
+        if (pl.sk.tile_pieces[u] == 0) return false;
+        if (pl.sk.tile_pieces[u] > pmax) pmax = pl.sk.tile_pieces[u];
+    }
+    pl.sk_grid = (int)g;
+    pl.splits = pmax;
+    pl.cost_stream_k = busiest + 1.5 + (double)(4 * (tiles < g ? tiles : g)) / 200.0 + 0.05 * (double)pmax; // + the fix-up pass (a chain of pmax loads per element)
+    return true;
+}
+
+// Decide between the uniform split (count `splits`, already chosen by plan_splits) and stream-K for one shape.
+void make_plan(GemmPlan &pl, i64 m, i64 n, i64 k, i64 batch, int tri, int num_sms, i64 splits, i64 tiles_m, i64 tiles_n, i64 tiles_per_batch)
+{
+    static const int sk_on = [] { const char *e = getenv("REST_B200_STREAMK"); return e ? atoi(e) : 1; }();
+    const i64 ksteps = rb_cdiv(k, BK);
+    std::vector<int> w64((size_t)tiles_per_batch);
+    for (i64 t = 0; t < tiles_per_batch; ++t) {
+        i64 tm, tn;
+        host_decode_tile(t, tiles_m, tiles_n, tri, tm, tn);
+        w64[(size_t)t] = tile_weight64(tm, tn, tiles_m, tiles_n, m, n, tri);
+    }
+    pl.splits = splits; pl.stream_k = false;
+    const i64 tiles = tiles_per_batch * batch, items = tiles * splits;
+    const int g = (int)(items < num_sms ? items : num_sms);
+    pl.cost_split = simulate_split_makespan(w64, tiles_per_batch, batch, splits, ksteps, g) +
+                    (splits > 1 ? 1.5 + (double)(2 * splits * tiles) / 200.0 + 0.05 * (double)splits : 0.0);
+    GemmPlan sk;
+    const i64 ldp = (m + 1) & ~(i64)1;
+    bool have_sk = false;
+    for (int div = 1; div <= 4 && sk_on; div *= 2) { // all SMs, or fewer CTAs with longer pieces when the fix-up chain would dominate
+        GemmPlan cand;
+        if (num_sms / div < 1 || !build_stream_k(cand, w64, tiles_per_batch, batch, ksteps, num_sms / div)) continue;
+        if (!have_sk || cand.cost_stream_k < sk.cost_stream_k) { sk = cand; have_sk = true; }
+    }
+    if (have_sk && sk.splits * batch * n * ldp * 8 <= ((i64)1 << 30)) {
+        pl.cost_stream_k = sk.cost_stream_k;
+        if (sk.cost_stream_k < 0.97 * pl.cost_split) {
+            const double cs = pl.cost_split;
+            pl = sk; pl.cost_split = cs; pl.stream_k = true;
+        }
+    }
+}
+
+struct PlanKey { i64 m, n, k, batch; int tri, num_sms; i64 splits; };
+const GemmPlan *cached_plan(i64 m, i64 n, i64 k, i64 batch, int tri, int num_sms, i64 splits, i64 tiles_m, i64 tiles_n, i64 tiles_per_batch)
+{
+    constexpr int SLOTS = 16;
+    static thread_local PlanKey keys[SLOTS];
+    static thread_local GemmPlan plans[SLOTS];
+    static thread_local unsigned stamp[SLOTS], clock_ = 0;
+    static thread_local bool used[SLOTS];
+    ++clock_;
+    int victim = 0;
+    for (int i = 0; i < SLOTS; ++i) {
+        if (used[i] && keys[i].m == m && keys[i].n == n && keys[i].k == k && keys[i].batch == batch && keys[i].tri == tri &&
+            keys[i].num_sms == num_sms && keys[i].splits == splits) { stamp[i] = clock_; return &plans[i]; }
+        if (!used[i]) victim = i;
+        else if (used[victim] && stamp[i] < stamp[victim]) victim = i;
+    }
+    plans[victim] = GemmPlan();
+    make_plan(plans[victim], m, n, k, batch, tri, num_sms, splits, tiles_m, tiles_n, tiles_per_batch);
+    keys[victim] = PlanKey{m, n, k, batch, tri, num_sms, splits};
+    used[victim] = true; stamp[victim] = clock_;
+    return &plans[victim];
+}
+
 template <bool A_K, bool B_K, bool PACK>
 int launch_tma(rb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p, int grid)
 {
@@ -901,6 +1150,45 @@ extern "C" int64_t rb_gemm_plan_splits(int64_t m, int64_t n, int64_t k, int64_t 
 {
     if (m <= 0 || n <= 0 || k <= 0 || batch <= 0) return 1;
     return plan_splits(m, n, k, batch, tri, num_sms);
+}
+
+// 1 when the (non-packed) product would run as stream-K; costs_out[0..1] (optional) = estimated makespans of the uniform split and of
+// stream-K in full-tile k steps, costs_out[2] = CTAs, costs_out[3] = largest piece count
+extern "C" int rb_gemm_plan_stream_k(int64_t m, int64_t n, int64_t k, int64_t batch, int tri, int num_sms, double *costs_out)
+{
+    if (costs_out) { costs_out[0] = costs_out[1] = costs_out[2] = costs_out[3] = 0.0; }
+    if (m <= 0 || n <= 0 || k <= 0 || batch <= 0 || num_sms <= 0) return 0;
+    if (tri && m != n) return 0;
+    const i64 tiles_m = rb_cdiv(m, BM), tiles_n = rb_cdiv(n, BN);
+    const i64 tiles_per_batch = tri ? tiles_m * (tiles_m + 1) / 2 : tiles_m * tiles_n, ksteps = rb_cdiv(k, BK);
+    if (!(tiles_per_batch * batch < 4 * (i64)num_sms && ksteps >= 8)) return 0;
+    i64 splits = plan_splits(m, n, k, batch, tri, num_sms);
+    splits = rb_cdiv(k, rb_cdiv(ksteps, splits) * BK);
+    GemmPlan pl;
+    make_plan(pl, m, n, k, batch, tri, num_sms, splits, tiles_m, tiles_n, tiles_per_batch);
+    if (costs_out) { costs_out[0] = pl.cost_split; costs_out[1] = pl.cost_stream_k; costs_out[2] = pl.sk_grid; costs_out[3] = (double)pl.splits; }
+    return pl.stream_k ? 1 : 0;
+}
+
+// the stream-K tables of a shape, for the CPU tests of the partition (returns the CTA count, 0 when the shape does not qualify)
+extern "C" int rb_gemm_stream_k_tables(int64_t m, int64_t n, int64_t k, int64_t batch, int tri, int num_sms, unsigned *cta_step,
+                                       unsigned short *cta_tile, unsigned char *tile_first, unsigned char *tile_pieces)
+{
+    if (m <= 0 || n <= 0 || k <= 0 || batch <= 0 || num_sms <= 0 || (tri && m != n)) return 0;
+    const i64 tiles_m = rb_cdiv(m, BM), tiles_n = rb_cdiv(n, BN);
+    const i64 tiles_per_batch = tri ? tiles_m * (tiles_m + 1) / 2 : tiles_m * tiles_n, ksteps = rb_cdiv(k, BK);
+    if (tiles_per_batch * batch > SK_MAX_TILES) return 0;
+    std::vector<int> w64((size_t)tiles_per_batch);
+    for (i64 t = 0; t < tiles_per_batch; ++t) {
+        i64 tm, tn;
+        host_decode_tile(t, tiles_m, tiles_n, tri, tm, tn);
+        w64[(size_t)t] = tile_weight64(tm, tn, tiles_m, tiles_n, m, n, tri);
+    }
+    GemmPlan pl;
+    if (!build_stream_k(pl, w64, tiles_per_batch, batch, ksteps, num_sms)) return 0;
+    for (int c = 0; c <= pl.sk_grid; ++c) { cta_step[c] = pl.sk.cta_step[c]; cta_tile[c] = pl.sk.cta_tile[c]; }
+    for (i64 t = 0; t < tiles_per_batch * batch; ++t) { tile_first[t] = pl.sk.tile_first[t]; tile_pieces[t] = pl.sk.tile_pieces[t]; }
+    return pl.sk_grid;
 }
 
 int rb_gemm_core(rb_ctx *ctx, bool ta, bool tb, i64 m, i64 n, i64 k, double alpha, const double *a, i64 lda,
@@ -968,7 +1256,7 @@ int rb_gemm_core(rb_ctx *ctx, bool ta, bool tb, i64 m, i64 n, i64 k, double alph
         const bool a_batched = batch > 1 && stride_a != 0, b_batched = batch > 1 && stride_b != 0;
         RB_TRY(encode_map(ctx, &tmA, a, a_k, m, k, lda, stride_a, a_batched ? batch : 1));
         RB_TRY(encode_map(ctx, &tmB, b, b_k, n, k, ldb, stride_b, b_batched ? batch : 1));
-        GemmParams p;
+        GemmParams p{};
         p.m = m; p.n = n; p.k = k; p.batch = batch;
         const bool packed = pack_m_applies(a_k, a_batched, b_batched, m, batch, tri);
         p.pack_m = packed ? 1 : 0;
@@ -980,6 +1268,18 @@ int rb_gemm_core(rb_ctx *ctx, bool ta, bool tb, i64 m, i64 n, i64 k, double alph
         i64 splits = plan_splits(m, n, k, batch, tri, ctx->num_sms, packed);
         i64 kper = rb_cdiv(ksteps, splits) * BK;
         splits = rb_cdiv(k, kper);
+        // stream-K instead of the uniform split where the tiles do not fill the chip (same trigger as split-K) and the simulated
+        // makespan says so; plans are cached per shape (an SCF loop repeats a handful of shapes)
+        p.stream_k = 0; p.sk_ksteps = ksteps;
+        int sk_grid = 0;
+        if (!packed && tiles < 4 * (i64)ctx->num_sms && ksteps >= 8) {
+            const GemmPlan *pl = cached_plan(m, n, k, batch, tri, ctx->num_sms, splits, p.tiles_m, p.tiles_n, p.tiles_per_batch);
+            if (pl && pl->stream_k) {
+                p.stream_k = 1; p.sk = pl->sk; sk_grid = pl->sk_grid;
+                splits = pl->splits; kper = ksteps * BK;
+            }
+        }
+        const bool stream_k = p.stream_k != 0;
         p.splits = splits; p.kper = kper;
         p.total_items = tiles * splits;
         p.alpha = alpha; p.beta = beta; p.c = c; p.ldc = ldc; p.stride_c = stride_c; p.tri = tri;
@@ -996,6 +1296,7 @@ int rb_gemm_core(rb_ctx *ctx, bool ta, bool tb, i64 m, i64 n, i64 k, double alph
             p.partial = (double *)ws;
         }
         int grid = (int)(p.total_items < ctx->num_sms ? p.total_items : ctx->num_sms);
+        if (stream_k) grid = sk_grid;
         if (a_k && b_k) RB_TRY((launch_tma<true, true, false>(ctx, tmA, tmB, p, grid)));
         else if (a_k && !b_k) RB_TRY((launch_tma<true, false, false>(ctx, tmA, tmB, p, grid)));
         else if (!a_k && b_k) {
@@ -1006,12 +1307,17 @@ int rb_gemm_core(rb_ctx *ctx, bool ta, bool tb, i64 m, i64 n, i64 k, double alph
             else RB_TRY((launch_tma<false, false, false>(ctx, tmA, tmB, p, grid)));
         }
         if (splits > 1) {
-            i64 total = m * n * batch;
-            i64 blocks = rb_cdiv(total, 256);
-            i64 cap = (i64)ctx->num_sms * 16;
-            if (blocks > cap) blocks = cap;
-            rb_splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(p.partial, p.ldp, splits, m, n, batch,
-                                                                              alpha, beta, c, ldc, stride_c, tri);
+            // (row pairs, columns, batches); the partial rows beyond m up to ldp are never read
+            i64 bx = rb_cdiv(rb_cdiv(m, 2), 256);
+            if (bx > 64) bx = 64;
+            const i64 by = n < 65535 ? n : 65535, bz = batch < 64 ? batch : 64;
+            dim3 rgrid((unsigned)bx, (unsigned)by, (unsigned)bz);
+            if (stream_k)
+                rb_partial_reduce_kernel<true><<<rgrid, 256, 0, ctx->stream>>>(p.partial, p.ldp, (int)splits, m, n, batch, alpha, beta, c, ldc, stride_c,
+                                                                              tri, (int)p.tiles_m, (int)p.tiles_n, (int)p.tiles_per_batch, p.sk);
+            else
+                rb_partial_reduce_kernel<false><<<rgrid, 256, 0, ctx->stream>>>(p.partial, p.ldp, (int)splits, m, n, batch, alpha, beta, c, ldc, stride_c,
+                                                                               tri, (int)p.tiles_m, (int)p.tiles_n, (int)p.tiles_per_batch, p.sk);
             RB_LAUNCHED(ctx);
         }
         return RB_OK;

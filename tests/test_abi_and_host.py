@@ -267,3 +267,48 @@ def test_argument_errors_surface_before_any_device_call(rt):
         rt._dspgvx(rt.MatrixUpper.new(6, 0.0), rt.MatrixUpper.new(10, 0.0), 2)
     with pytest.raises(rt.RestB200Error):
         rt._dspgvx(rt.MatrixUpper.new(6, 0.0), rt.MatrixUpper.new(6, 0.0), 4)
+
+
+def test_stream_k_partition_covers_every_step_once(rt):
+    """Host-side planner of the stream-K GEMM (pure arithmetic, no device call): for a spread of shapes the CTA ranges must tile
+    the (tile, k step) space exactly once and in order, no CTA may be empty, and a tile's pieces must be numbered 0 .. pieces-1 by
+    consecutive CTAs starting at tile_first (that numbering is what makes the fix-up sum deterministic)."""
+    import ctypes as C
+    import random
+    from rest_tensors_b200._lib import lib
+    random.seed(7)
+    shapes = [(500, 500, 500, 1, 0), (1000, 1000, 1000, 1, 1), (600, 600, 102000, 1, 1), (264, 264, 15120, 1, 0), (100, 100, 8000, 1, 1),
+              (300, 200, 5000, 3, 0), (129, 1030, 777, 1, 0), (1800, 1800, 54720, 1, 1), (2000, 2000, 2000, 1, 0)]
+    for _ in range(40):
+        tri = random.choice([0, 0, 1, 2])
+        m = random.randint(1, 2600)
+        n = m if tri else random.randint(1, 2600)
+        shapes.append((m, n, random.randint(256, 120000), random.choice([1, 1, 1, 2, 5]), tri))
+    checked = 0
+    for (m, n, k, batch, tri) in shapes:
+        for sms in (148, 132, 7):
+            step = (C.c_uint * 161)(); tile = (C.c_ushort * 161)(); first = (C.c_ubyte * 592)(); pieces = (C.c_ubyte * 592)()
+            g = lib.rb_gemm_stream_k_tables(m, n, k, batch, tri, sms, C.cast(step, C.c_void_p), C.cast(tile, C.c_void_p),
+                                            C.cast(first, C.c_void_p), C.cast(pieces, C.c_void_p))
+            if g == 0:
+                continue
+            checked += 1
+            tm, tn = -(-m // 128), -(-n // 128)
+            tiles = (tm * (tm + 1) // 2 if tri else tm * tn) * batch
+            ksteps = -(-k // 32)
+            assert 1 <= g <= sms
+            assert (tile[0], step[0]) == (0, 0) and (tile[g], step[g]) == (tiles, 0)
+            seen = [0] * tiles            # steps covered so far per tile
+            count = [0] * tiles
+            for c in range(g):
+                t, s = tile[c], step[c]
+                te, se = tile[c + 1], step[c + 1]
+                assert (t, s) < (te, se), "empty CTA range"
+                while (t, s) < (te, se):
+                    s1 = se if t == te else ksteps
+                    assert seen[t] == s, "steps of a tile must be taken in order, without gaps"
+                    assert c - first[t] == count[t], "piece index = CTA - tile_first must count 0, 1, 2, ..."
+                    seen[t] = s1; count[t] += 1
+                    t, s = t + 1, 0
+            assert seen == [ksteps] * tiles and count == list(pieces[:tiles])
+    assert checked >= 30

@@ -749,3 +749,48 @@ def test_split_k_products_repeat_bit_for_bit(ctx, n, k):
     ref = torch.triu(full[0].view(n, n).t())
     err = float((tri[0] - ref).abs().max() / ref.abs().max())
     assert err < 1e-12, f"SYRK triangle vs full product: {err:.3e}"
+
+
+@pytest.mark.parametrize("m,n,k,batch", [(500, 500, 500, 1), (1000, 1000, 1000, 1), (2000, 2000, 2000, 1), (600, 600, 102000, 1),
+                                         (264, 264, 15120, 1), (1800, 1800, 54720, 1), (300, 200, 5000, 3), (129, 1030, 777, 1),
+                                         (136, 136, 40000, 1)])
+def test_stream_k_products(ctx, m, n, k, batch):
+    """Shapes the planner runs as stream-K (every CTA an equal share of the tile x k-step space, pieces summed in piece order by
+    rb_streamk_reduce_kernel): GEMM in all four layouts with alpha / beta, SYRK, batched; against torch's FP64 matmul (cuBLAS, an
+    independent implementation) to 1e-11 of the largest element (k up to 1e5 terms per element), and bit for bit across repeated launches."""
+    from rest_tensors_b200._lib import lib
+    assert lib.rb_gemm_plan_stream_k(m, n, k, batch, 0, ctx.num_sms, None) == 1, "this shape is meant to exercise the stream-K path"
+    a = ctx.empty(batch * m * k); b = ctx.empty(batch * k * n); c0 = ctx.empty(batch * m * n)
+    ctx.fill_linear(a, a.numel(), 41, 0, 1.0); ctx.fill_linear(b, b.numel(), 42, 0, 1.0); ctx.fill_linear(c0, c0.numel(), 43, 0, 1.0)
+    for ta, tb in (("N", "N"), ("T", "N"), ("N", "T"), ("T", "T")):
+        if batch > 1 and (ta, tb) != ("N", "N"):
+            continue
+        lda = m if ta == "N" else k
+        ldb = k if tb == "N" else n
+        outs = []
+        for rep in range(2):
+            c = c0.clone()
+            if batch == 1:
+                ctx.dgemm(ta, tb, m, n, k, 0.7, a, lda, b, ldb, -0.3, c, m)
+            else:
+                ctx.dgemm_strided_batched(ta, tb, m, n, k, 0.7, a, lda, m * k, b, ldb, k * n, -0.3, c, m, m * n, batch)
+            outs.append(c)
+        assert torch.equal(outs[0], outs[1]), (ta, tb, "repeated launches differ")
+        for bi in range(batch):
+            am = a[bi * m * k:(bi + 1) * m * k].view(k, m).t() if ta == "N" else a.view(m, k)      # op(A) [m, k]
+            bm = b[bi * k * n:(bi + 1) * k * n].view(n, k).t() if tb == "N" else b.view(k, n)      # op(B) [k, n]
+            want = 0.7 * (am @ bm) - 0.3 * c0[bi * m * n:(bi + 1) * m * n].view(n, m).t()
+            got = outs[0][bi * m * n:(bi + 1) * m * n].view(n, m).t()
+            err = float((got - want).abs().max() / want.abs().max())
+            assert err < 1e-11, (ta, tb, bi, err)
+    if m == n and batch == 1:
+        for uplo in ("U", "L"):
+            c = c0.clone()
+            ctx.dsyrk(uplo, "N", n, k, 1.0, a, n, 0.5, c, n)
+            am = a.view(k, n).t()
+            want = am @ am.t() + 0.5 * c0.view(n, n).t()
+            got = c.view(n, n).t()
+            tri = torch.triu(torch.ones(n, n, dtype=torch.bool, device=c.device)) if uplo == "U" else \
+                torch.tril(torch.ones(n, n, dtype=torch.bool, device=c.device))
+            assert float((got - want)[tri].abs().max() / want.abs().max()) < 1e-11, uplo
+            assert torch.equal(got[~tri], c0.view(n, n).t()[~tri]), "the other triangle must stay untouched"

@@ -19,9 +19,11 @@ RUST_DIR = os.path.join(ROOT, "rust", "rest_tensors_b200", "src")
 
 # canonical scalar classes: (kind, bits)
 C_SCALAR = {"int": ("int", 32), "double": ("float", 64), "char": ("char", 8), "void": ("void", 0), "int64_t": ("int", 64),
-            "uint64_t": ("uint", 64), "unsigned char": ("uint", 8), "rb_ctx": ("opaque", 0)}
+            "uint64_t": ("uint", 64), "unsigned char": ("uint", 8), "unsigned": ("uint", 32), "unsigned short": ("uint", 16),
+            "rb_ctx": ("opaque", 0)}
 RUST_SCALAR = {"c_int": ("int", 32), "i32": ("int", 32), "c_double": ("float", 64), "f64": ("float", 64), "c_char": ("char", 8),
-               "c_void": ("void", 0), "i64": ("int", 64), "u64": ("uint", 64), "u8": ("uint", 8), "RbCtx": ("opaque", 0)}
+               "c_void": ("void", 0), "i64": ("int", 64), "u64": ("uint", 64), "u8": ("uint", 8), "u32": ("uint", 32), "u16": ("uint", 16),
+               "RbCtx": ("opaque", 0)}
 
 
 def canon_c(ctype: str):
