@@ -47,5 +47,32 @@ pp = ctx.empty(50 * 50)
 ctx.ri_mo_pq(mo3, 50, 50, mo3, 50, 50, 5, 8, (0, 5, 0, 8), None, 0.0, pp, 50)
 ctx.ri_mo_pq(mo3, 50, 50, mo3, 50, 50, 5, 8, (1, 3, 2, 5), wv, 0.0, pp, 50)
 ctx.ri_mo_pq(mo3, 50, 20, mo3[20:], 50, 30, 5, 8, (0, 5, 0, 8), wv, 1.0, pp, 50)
+# round 2: 32-byte layout kernels (multiples of 4, aligned), the bulk-tensor (TMA) path, stream-K products, ERIFold4 scatter
+n = 256; npk = n * (n + 1) // 2
+p = ctx.empty(npk); f = ctx.empty(n * n); g = ctx.empty(n * n); ctx.fill_linear(p, npk, 4, 0, 1.0)
+ctx.unpack_upper(p, n, f); ctx.pack_upper(f, n, p); ctx.matrix_transpose(f, n, n, g); ctx.copy_mm(n, n, f, n, n, 0, 0, g, n, n, 0, 0)
+assert torch.equal(f.view(n, n), f.view(n, n).t())
+t = ctx.empty(64 * 72 * 20); u = ctx.empty(64 * 72 * 20); ctx.fill_linear(t, t.numel(), 5, 0, 1.0)
+for path in (0, 1):
+    ctx.set_layout_path(path)
+    for w in range(4):
+        ctx.ri_transpose(t, 64, 72, 20, w, u)
+    ctx.copy_rr(32, 40, 10, t, 64, 72, 20, 4, 8, 2, u, 64, 72, 20, 8, 4, 6)
+ctx.set_layout_path(0)
+ctx.self_scaled_add(g, f, 0.5, n * n)
+for (m, nn, k, tri) in [(500, 500, 500, 0), (264, 264, 4000, 1), (129, 300, 777, 0)]:
+    a = ctx.empty(max(m, nn) * k); b = ctx.empty(max(m, nn) * k); c = ctx.empty(m * nn)
+    ctx.fill_linear(a, a.numel(), 8, 0, 1.0); ctx.fill_linear(b, b.numel(), 9, 0, 1.0); c.zero_()
+    if tri:
+        ctx.dsyrk("U", "N", m, k, 1.0, a, m, 0.0, c, m)
+    else:
+        ctx.dgemm("N", "N", m, nn, k, 1.0, a, m, b, k, 0.0, c, m)
+        ref = a[: m * k].view(k, m).t() @ b[: k * nn].view(nn, k).t()
+        assert float((c.view(nn, m).t() - ref).abs().max() / ref.abs().max()) < 1e-12
+dim = 12; npair = dim * (dim + 1) // 2
+eri = ctx.empty(npair * npair); eri.zero_()
+blk = ctx.empty(5 * 7 * 4 * 6); ctx.fill_linear(blk, blk.numel(), 10, 0, 1.0)
+ctx.erifold4_chunk_copy(eri, npair, npair, npair, ((0, 5), (5, 12), (2, 6), (6, 12)), blk, 1)
+ctx.erifold4_chunk_copy(eri, npair, npair, npair, ((0, 5), (0, 7), (0, 4), (0, 6)), blk, 0)
 torch.cuda.synchronize()
 print("sanitize target ok")
