@@ -9,3 +9,5 @@ timeout -k 10 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 
 echo "bench n8 rc=$?"; cut -c1-300 gpurun_out/bench_n8.json; tail -3 gpurun_out/bench_n8.err
 timeout -k 10 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29741 bench.py --gpus 4 --no-e2e > gpurun_out/bench_n4.json 2> gpurun_out/bench_n4.err
 echo "bench n4 rc=$?"; cut -c1-300 gpurun_out/bench_n4.json; tail -3 gpurun_out/bench_n4.err
+timeout -k 10 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29751 bench.py --gpus 2 --no-e2e > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err
+echo "bench n2 rc=$?"; cut -c1-300 gpurun_out/bench_n2.json; tail -3 gpurun_out/bench_n2.err
