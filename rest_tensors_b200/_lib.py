@@ -45,6 +45,8 @@ SIGNATURES = {
     "rb_ctx_launch_count": (c_i64, [c_vp]),
     "rb_ctx_tma_layout_count": (c_i64, [c_vp]),
     "rb_ctx_set_layout_path": (C.c_int, [c_vp, C.c_int]),
+    "rb_host_register": (C.c_int, [c_vp, c_i64]),
+    "rb_host_unregister": (C.c_int, [c_vp]),
     "rb_gemm_plan_stream_k": (C.c_int, [c_i64, c_i64, c_i64, c_i64, C.c_int, C.c_int, c_vp]),
     "rb_gemm_stream_k_tables": (C.c_int, [c_i64, c_i64, c_i64, c_i64, C.c_int, C.c_int, c_vp, c_vp, c_vp, c_vp]),
     "rb_erifold4_chunk_copy": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64] + [C.c_int] * 8 + [c_vp, C.c_int]),

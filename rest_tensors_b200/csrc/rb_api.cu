@@ -246,6 +246,20 @@ extern "C" int rb_host_free_pinned(void *p)
     if (p) RB_CUDA(cudaFreeHost(p));
     return RB_OK;
 }
+// Page-lock a buffer the CALLER owns (e.g. the Vec<f64> that holds ri3ao for the whole SCF run) so that the host-pointer entry
+// points stream it at the pinned rate instead of bouncing it; the caller must unregister it before freeing it.
+extern "C" int rb_host_register(void *p, int64_t bytes)
+{
+    RB_REQUIRE(p && bytes > 0, "rb_host_register: bad arguments");
+    RB_CUDA(cudaHostRegister(p, (size_t)bytes, cudaHostRegisterPortable));
+    return RB_OK;
+}
+extern "C" int rb_host_unregister(void *p)
+{
+    RB_REQUIRE(p, "rb_host_unregister: NULL pointer");
+    RB_CUDA(cudaHostUnregister(p));
+    return RB_OK;
+}
 extern "C" int rb_memcpy_h2d(rb_ctx *ctx, void *dst, const void *src, int64_t bytes)
 {
     RB_REQUIRE(ctx, "rb_memcpy_h2d: ctx is NULL");

@@ -794,3 +794,21 @@ def test_stream_k_products(ctx, m, n, k, batch):
                 torch.tril(torch.ones(n, n, dtype=torch.bool, device=c.device))
             assert float((got - want)[tri].abs().max() / want.abs().max()) < 1e-11, uplo
             assert torch.equal(got[~tri], c0.view(n, n).t()[~tri]), "the other triangle must stay untouched"
+
+
+def test_host_register_makes_a_caller_buffer_pinned(rt, oracle_blas):
+    """rb_host_register page-locks a caller-owned (numpy) buffer in place: the streaming pass must give the same bits as with
+    the pageable bounce, and the buffer must be released cleanly."""
+    import ctypes as C
+    from rest_tensors_b200._lib import lib, check
+    nb, nx = 48, 300
+    ri = oracle_blas.fill_ri3ao_symm(nb, 0, nx)
+    c = oracle_blas.fill_linear(nb * nb, 3, scale=nb ** -0.5)
+    ref = rt.RIFull.from_vec([nb, nb, nx], ri).ao2mo(rt.MatrixFull.from_vec([nb, nb], c)).data.copy()
+    check(lib.rb_host_register(C.c_void_p(ri.ctypes.data), ri.nbytes), "rb_host_register")
+    try:
+        got = rt.RIFull.from_vec([nb, nb, nx], ri).ao2mo(rt.MatrixFull.from_vec([nb, nb], c)).data
+        assert np.array_equal(got, ref)
+    finally:
+        check(lib.rb_host_unregister(C.c_void_p(ri.ctypes.data)), "rb_host_unregister")
+    assert lib.rb_host_unregister(C.c_void_p(ri.ctypes.data)) != 0      # a second release is an error, not a crash
