@@ -19,6 +19,7 @@ void rb_set_error(const char *fmt, ...);
         cudaError_t _e = (call);                                                                        \
         if (_e != cudaSuccess) {                                                                        \
             rb_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e));         \
+            (void)cudaGetLastError(); /* reported here: must not resurface in a later launch check */   \
             return RB_ERR_CUDA;                                                                         \
         }                                                                                               \
     } while (0)

@@ -812,3 +812,8 @@ def test_host_register_makes_a_caller_buffer_pinned(rt, oracle_blas):
     finally:
         check(lib.rb_host_unregister(C.c_void_p(ri.ctypes.data)), "rb_host_unregister")
     assert lib.rb_host_unregister(C.c_void_p(ri.ctypes.data)) != 0      # a second release is an error, not a crash
+    # ... and a reported CUDA error must not linger in the runtime: the next launch check has to see a clean state
+    again = rt.RIFull.from_vec([nb, nb, nx], ri).ao2mo(rt.MatrixFull.from_vec([nb, nb], c)).data
+    assert np.array_equal(again, ref)
+    vec, w, n3 = rt._dsyev(rt.MatrixFull.from_vec([3, 3], np.array([2.0, 1, 0, 1, 2, 1, 0, 1, 2])), "V")
+    assert n3 == 3 and abs(w[1] - 2.0) < 1e-13
