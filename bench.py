@@ -649,6 +649,59 @@ def crossover_leg(lib, check, threads=8, budget_s=1.0):
     return out
 
 
+def graph_replay_leg(env, w, flop, flush):
+    """The same device-resident step recorded once into a CUDA graph (rb_graph_begin / rb_graph_end) and replayed with one launch
+    per step, and the per-iteration part of an SCF loop (d_P + J + K) both ways: for the small configurations the launches are the
+    cost, not the kernels.  Runs on a side stream (the default stream cannot be captured) and re-binds the context afterwards."""
+    torch, ctx = env.torch, env.ctx
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    res = {}
+
+    def scf_iter():
+        w.sh.dp(w.dm, out=w.d); w.sh.j(w.d, out=w.j, reduce=True); w.sh.k(w.ct, w.no, out=w.k, reduce=True)
+
+    def timed(fn, reps=10):
+        ts = []
+        for _ in range(reps):
+            flush()
+            e0, e1 = env.ev(), env.ev()
+            e0.record(); fn(); e1.record()
+            side.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return sorted(ts)[len(ts) // 2]
+
+    with torch.cuda.stream(side):
+        ctx.bind_stream()
+        try:
+            w.step(True)
+            want = [t.clone() for t in (w.mo, w.d, w.j, w.k)]
+            with ctx.record() as rec_step:
+                w.step(True)
+            with ctx.record() as rec_iter:
+                scf_iter()
+            for t in (w.mo, w.d, w.j, w.k):
+                t.zero_()
+            for _ in range(3):
+                rec_step.graph.launch()
+            side.synchronize()
+            same = all(bool(torch.equal(a, b)) for a, b in zip((w.mo, w.d, w.j, w.k), want))
+            ms_direct = timed(lambda: w.step(True))
+            ms_graph = timed(rec_step.graph.launch)
+            it_direct = timed(scf_iter)
+            it_graph = timed(rec_iter.graph.launch)
+            res = {"ms": ms_graph, "gflops": flop / (ms_graph * 1e-3) / 1e9, "ms_call_by_call_same_stream": ms_direct,
+                   "kernels_per_replay": rec_step.graph.kernels, "bit_identical_to_call_by_call": same,
+                   "scf_iteration_dp_j_k": {"ms_call_by_call": it_direct, "ms_graph": it_graph,
+                                            "kernels_per_replay": rec_iter.graph.kernels},
+                   "api": "rb_graph_begin / rb_graph_end once, rb_graph_launch per step"}
+            rec_step.graph.close(); rec_iter.graph.close()
+        finally:
+            side.synchronize()
+    ctx.bind_stream()
+    return res
+
+
 def small_config_leg(env, lib, check, name):
     """Configs A / B on one GPU: device-resident step, e2e through the host-pointer ABI with pinned
     and with pageable buffers, and the reference CPU path on the FULL configuration, all in GFLOP/s of the same step."""
@@ -669,6 +722,10 @@ def small_config_leg(env, lib, check, name):
     ms = sorted(times)[len(times) // 2]
     out = {"workload": desc, "device": {"ms": ms, "gflops": flop / (ms * 1e-3) / 1e9,
                                         "l2": "flushed between iterations" if nx * nb * nb * 8 < (256 << 20) else "inputs > L2"}}
+    try:
+        out["device_graph"] = graph_replay_leg(env, w, flop, flush)
+    except Exception as exc:  # noqa: BLE001 -- the line must survive a refused recording
+        out["device_graph"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     for pinned in (True, False):
         r = _e2e_bound(env, lib, check, w, flop, 5, pinned)
         out["e2e_pinned" if pinned else "e2e_pageable"] = {"ms": r.get("ms_per_step"), "gflops": r.get("value"),

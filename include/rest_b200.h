@@ -61,6 +61,24 @@ int64_t rb_ctx_launch_count(rb_ctx *ctx);
 int64_t rb_ctx_tma_layout_count(rb_ctx *ctx);
 /* Select the GEMM implementation: 0 = auto (TMA+DMMA when alignment allows, else generic DMMA), 1 = force generic. */
 int rb_ctx_set_gemm_path(rb_ctx *ctx, int path);
+/* ---- CUDA-graph recording of a repeated call sequence ------------------------------------------------------------------------
+ * The reference's SCF loop (d_P, J, K once per iteration on the same tensors) repeats one call
+ * sequence on the same buffers.  Between rb_graph_begin and rb_graph_end the calls issued on `ctx` are recorded instead of run;
+ * rb_graph_launch replays the recording with ONE launch (pointers, shapes, scalars and the split-K / stream-K plans are baked in:
+ * refresh the CONTENTS of the input buffers between replays, e.g. with rb_memcpy_h2d, which can itself be part of the recording
+ * when the host buffer is pinned).  Rules: the context must run on a non-default stream (rb_ctx_use_own_stream / rb_ctx_set_stream);
+ * run the sequence once before recording (workspaces get their size on first use and cannot grow while recording:
+ * RB_ERR_UNSUPPORTED); calls that need the host inside (eigen-solvers, collectives, the peer pipelines, probes, rb_ctx_sync) are
+ * refused with RB_ERR_UNSUPPORTED while a recording is open.  A recording stays valid until rb_graph_free, also across later,
+ * larger calls on the same context. */
+int rb_graph_begin(rb_ctx *ctx);
+int rb_graph_end(rb_ctx *ctx, void **graph_out);
+int rb_graph_launch(rb_ctx *ctx, void *graph);
+int64_t rb_graph_kernel_count(void *graph);
+int rb_graph_free(rb_ctx *ctx, void *graph);
+/* Test hook: fill every internal workspace with the all-ones bit pattern (NaN as a double) on the context's stream, so that a kernel
+ * reading workspace memory nobody wrote in the same call yields NaN instead of silently reusing the previous call's data. */
+int rb_ctx_poison_workspaces(rb_ctx *ctx);
 /* Select the copy / transpose implementation: 0 = 32-byte (LDG/STG.256) and plain-load kernels (default: measured faster),
  * 1 = bulk-tensor kernels (TMA load -> shared memory -> TMA store) for operands TMA can describe. */
 int rb_ctx_set_layout_path(rb_ctx *ctx, int path);

@@ -52,6 +52,12 @@ SIGNATURES = {
     "rb_erifold4_chunk_copy": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64] + [C.c_int] * 8 + [c_vp, C.c_int]),
     "rb_host_erifold4_chunk_copy": (C.c_int, [c_vp, c_i64, c_i64] + [C.c_int] * 8 + [c_vp, C.c_int]),
     "rb_ctx_set_gemm_path": (C.c_int, [c_vp, C.c_int]),
+    "rb_ctx_poison_workspaces": (C.c_int, [c_vp]),
+    "rb_graph_begin": (C.c_int, [c_vp]),
+    "rb_graph_end": (C.c_int, [c_vp, C.POINTER(c_vp)]),
+    "rb_graph_launch": (C.c_int, [c_vp, c_vp]),
+    "rb_graph_kernel_count": (C.c_int64, [c_vp]),
+    "rb_graph_free": (C.c_int, [c_vp, c_vp]),
     "rb_dev_alloc": (C.c_int, [c_vp, c_i64, C.POINTER(c_vp)]),
     "rb_dev_free": (C.c_int, [c_vp, c_vp]),
     "rb_host_alloc_pinned": (C.c_int, [c_i64, C.POINTER(c_vp)]),

@@ -73,6 +73,7 @@ extern "C" int rb_ctx_destroy(rb_ctx *ctx)
     rb_comm_destroy(ctx);
     rb_eig_cache_free(ctx);
     for (int s = 0; s < 4; ++s) if (ctx->ws[s]) cudaFree(ctx->ws[s]);
+    for (void *p : ctx->ws_parked) cudaFree(p);
     if (ctx->sched) cudaFree(ctx->sched);
     for (int i = 0; i < 5; ++i) if (ctx->aux_ev[i]) cudaEventDestroy(ctx->aux_ev[i]);
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
@@ -86,6 +87,7 @@ extern "C" int rb_ctx_destroy(rb_ctx *ctx)
 extern "C" int rb_ctx_set_stream(rb_ctx *ctx, void *cuda_stream)
 {
     RB_REQUIRE(ctx, "rb_ctx_set_stream: ctx is NULL");
+    RB_NO_CAPTURE(ctx, "rb_ctx_set_stream");
     ctx->stream = (cudaStream_t)cuda_stream; // NULL is the legacy default stream (what torch uses by default)
     return RB_OK;
 }
@@ -93,6 +95,7 @@ extern "C" int rb_ctx_set_stream(rb_ctx *ctx, void *cuda_stream)
 extern "C" int rb_ctx_use_own_stream(rb_ctx *ctx)
 {
     RB_REQUIRE(ctx, "rb_ctx_use_own_stream: ctx is NULL");
+    RB_NO_CAPTURE(ctx, "rb_ctx_use_own_stream");
     ctx->stream = ctx->own_stream;
     return RB_OK;
 }
@@ -100,6 +103,7 @@ extern "C" int rb_ctx_use_own_stream(rb_ctx *ctx)
 extern "C" int rb_ctx_sync(rb_ctx *ctx)
 {
     RB_REQUIRE(ctx, "rb_ctx_sync: ctx is NULL");
+    RB_NO_CAPTURE(ctx, "rb_ctx_sync");
     RB_CUDA(cudaStreamSynchronize(ctx->stream));
     return RB_OK;
 }
@@ -125,9 +129,19 @@ extern "C" int rb_ctx_set_gemm_path(rb_ctx *ctx, int path)
 int rb_ws_reserve(rb_ctx *ctx, int slot, i64 bytes, void **out)
 {
     if (bytes > ctx->ws_bytes[slot]) {
+        if (ctx->capturing) {
+            rb_set_error("workspace %d would have to grow (%lld -> %lld bytes) while a graph is being recorded: run the call "
+                         "sequence once before rb_graph_begin so that the workspaces have their final size",
+                         slot, (long long)ctx->ws_bytes[slot], (long long)bytes);
+            return RB_ERR_UNSUPPORTED;
+        }
         RB_CUDA(cudaSetDevice(ctx->device));
         RB_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (ctx->ws[slot]) { RB_CUDA(cudaFree(ctx->ws[slot])); ctx->ws[slot] = nullptr; ctx->ws_bytes[slot] = 0; }
+        if (ctx->ws[slot]) {
+            if (ctx->live_graphs > 0) ctx->ws_parked.push_back(ctx->ws[slot]); // recordings hold its address: freed with the last of them
+            else RB_CUDA(cudaFree(ctx->ws[slot]));
+            ctx->ws[slot] = nullptr; ctx->ws_bytes[slot] = 0;
+        }
         cudaError_t e = cudaMalloc(&ctx->ws[slot], (size_t)bytes);
         if (e != cudaSuccess) {
             cudaGetLastError();
@@ -138,6 +152,105 @@ int rb_ws_reserve(rb_ctx *ctx, int slot, i64 bytes, void **out)
         ctx->ws_bytes[slot] = bytes;
     }
     *out = ctx->ws[slot];
+    return RB_OK;
+}
+
+// ---- CUDA-graph capture of a repeated call sequence --------------------------------------------------------------------------
+// An SCF iteration issues the same d_P / J / K (and, small systems, ao2mo) calls on the same buffers every time; for small systems the
+// cost is the launches, not the kernels (~14 us per GEMM call against < 1 us of DMMA time).  Between
+// rb_graph_begin and rb_graph_end the calls on this context are RECORDED (stream capture) instead of run; rb_graph_launch replays
+// the recording with one launch.  Everything a call computed on the host is baked in: pointers, shapes, scalars, tensor maps, the
+// split-K / stream-K plan, the workspace addresses.  The GEMM's dynamic tile scheduler re-arms itself on the device, so a
+// recording can be replayed any number of times.
+struct RbGraph {
+    cudaGraphExec_t exec;
+    i64 kernels; // kernel launches recorded (added to the context's launch count per replay)
+};
+
+extern "C" int rb_graph_begin(rb_ctx *ctx)
+{
+    RB_REQUIRE(ctx, "rb_graph_begin: ctx is NULL");
+    RB_REQUIRE(!ctx->capturing, "rb_graph_begin: a recording is already open on this context");
+    RB_REQUIRE(ctx->stream != nullptr && ctx->stream != cudaStreamLegacy && ctx->stream != cudaStreamPerThread,
+               "rb_graph_begin: the default stream cannot be captured -- rb_ctx_use_own_stream() or rb_ctx_set_stream(a stream you created)");
+    RB_CUDA(cudaSetDevice(ctx->device));
+    RB_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+    ctx->capturing = 1;
+    ctx->capture_launches0 = ctx->launches;
+    return RB_OK;
+}
+
+extern "C" int rb_graph_end(rb_ctx *ctx, void **graph_out)
+{
+    RB_REQUIRE(ctx && graph_out, "rb_graph_end: bad arguments");
+    RB_REQUIRE(ctx->capturing, "rb_graph_end: no recording is open on this context");
+    *graph_out = nullptr;
+    ctx->capturing = 0;
+    const i64 kernels = ctx->launches - ctx->capture_launches0;
+    ctx->launches = ctx->capture_launches0; // recorded, not run
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+    if (e != cudaSuccess || !g) {
+        (void)cudaGetLastError();
+        rb_set_error("rb_graph_end: the recording is invalid (%s): a call inside it needed the host (see its own error)",
+                     cudaGetErrorString(e));
+        if (g) cudaGraphDestroy(g);
+        return RB_ERR_CUDA;
+    }
+    cudaGraphExec_t ex = nullptr;
+    e = cudaGraphInstantiate(&ex, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        rb_set_error("rb_graph_end: cudaGraphInstantiate -> %s", cudaGetErrorString(e));
+        return RB_ERR_CUDA;
+    }
+    (void)cudaGraphUpload(ex, ctx->stream); // first replay then costs what the others do
+    (void)cudaGetLastError();
+    *graph_out = new RbGraph{ex, kernels};
+    ctx->live_graphs++;
+    return RB_OK;
+}
+
+extern "C" int rb_graph_launch(rb_ctx *ctx, void *graph)
+{
+    RB_REQUIRE(ctx && graph, "rb_graph_launch: bad arguments");
+    RB_REQUIRE(!ctx->capturing, "rb_graph_launch: a recording is open on this context");
+    RbGraph *g = (RbGraph *)graph;
+    RB_CUDA(cudaSetDevice(ctx->device));
+    RB_CUDA(cudaGraphLaunch(g->exec, ctx->stream));
+    ctx->launches += g->kernels;
+    return RB_OK;
+}
+
+extern "C" int64_t rb_graph_kernel_count(void *graph) { return graph ? ((RbGraph *)graph)->kernels : 0; }
+
+extern "C" int rb_graph_free(rb_ctx *ctx, void *graph)
+{
+    RB_REQUIRE(ctx, "rb_graph_free: ctx is NULL");
+    if (!graph) return RB_OK;
+    RbGraph *g = (RbGraph *)graph;
+    RB_CUDA(cudaSetDevice(ctx->device));
+    RB_CUDA(cudaStreamSynchronize(ctx->stream)); // a replay may still be running
+    cudaGraphExecDestroy(g->exec);
+    delete g;
+    if (--ctx->live_graphs <= 0) {
+        ctx->live_graphs = 0;
+        for (void *p : ctx->ws_parked) cudaFree(p);
+        ctx->ws_parked.clear();
+    }
+    return RB_OK;
+}
+
+// Test hook: fill every workspace with the all-ones bit pattern (a NaN as a double, -1 as an integer) on the context's stream.  A kernel
+// that reads workspace memory it (or an earlier kernel of the same call) did not write then shows up as NaN in the result instead of
+// passing on whatever the previous call left there (tests/test_gpu_contractions.py::test_partials_never_read_stale_workspace).
+extern "C" int rb_ctx_poison_workspaces(rb_ctx *ctx)
+{
+    RB_REQUIRE(ctx, "rb_ctx_poison_workspaces: ctx is NULL");
+    RB_CUDA(cudaSetDevice(ctx->device));
+    for (int s = 0; s < 4; ++s)
+        if (ctx->ws[s] && ctx->ws_bytes[s] > 0) RB_CUDA(cudaMemsetAsync(ctx->ws[s], 0xff, (size_t)ctx->ws_bytes[s], ctx->stream));
     return RB_OK;
 }
 
@@ -362,6 +475,7 @@ __global__ void __launch_bounds__(256) rb_fp64_probe_kernel(double *sink, int it
 extern "C" int rb_fp64_peak_probe(rb_ctx *ctx, int kind, int iters, double *tflops_out, double *ms_out)
 {
     RB_REQUIRE(ctx && tflops_out, "rb_fp64_peak_probe: bad arguments");
+    RB_NO_CAPTURE(ctx, "rb_fp64_peak_probe");
     RB_REQUIRE(kind == 0 || kind == 1, "rb_fp64_peak_probe: kind must be 0 (DMMA) or 1 (DFMA)");
     RB_CUDA(cudaSetDevice(ctx->device));
     void *sink;
@@ -401,6 +515,7 @@ __global__ void __launch_bounds__(256) rb_copy_probe_kernel(const double2 *__res
 extern "C" int rb_hbm_copy_probe(rb_ctx *ctx, int64_t bytes, int iters, double *gbs_out)
 {
     RB_REQUIRE(ctx && gbs_out && bytes >= 32 && iters > 0, "rb_hbm_copy_probe: bad arguments");
+    RB_NO_CAPTURE(ctx, "rb_hbm_copy_probe");
     RB_CUDA(cudaSetDevice(ctx->device));
     void *buf;
     i64 half = (bytes / 2) & ~(i64)15;
@@ -442,6 +557,7 @@ __global__ void __launch_bounds__(256) rb_zero_copy_store_kernel(const double2 *
 extern "C" int rb_pcie_probe(rb_ctx *ctx, int mode, int64_t bytes, int64_t width, int iters, double *gbs_out)
 {
     RB_REQUIRE(ctx && gbs_out && bytes >= 4096 && iters > 0 && mode >= 0 && mode <= 5, "rb_pcie_probe: bad arguments");
+    RB_NO_CAPTURE(ctx, "rb_pcie_probe");
     RB_CUDA(cudaSetDevice(ctx->device));
     if (width <= 0) width = 2048;
     bytes = (bytes / width) * width;

@@ -117,6 +117,7 @@ extern "C" int rb_comm_unique_id(unsigned char id[128])
 extern "C" int rb_comm_init_rank(rb_ctx *ctx, int rank, int world, const unsigned char id[128])
 {
     RB_REQUIRE(ctx && id, "rb_comm_init_rank: NULL argument");
+    RB_NO_CAPTURE(ctx, "rb_comm_init_rank");
     RB_REQUIRE(world >= 1 && rank >= 0 && rank < world, "rb_comm_init_rank: rank %d outside world %d", rank, world);
     RB_REQUIRE(!ctx->comm, "rb_comm_init_rank: the context already has a communicator");
     RB_TRY(nccl_load());
@@ -181,6 +182,7 @@ extern "C" int rb_comm_group_end(void)
 extern "C" int rb_allreduce_sum(rb_ctx *ctx, double *buf, int64_t n)
 {
     RB_REQUIRE(ctx, "rb_allreduce_sum: ctx is NULL");
+    RB_NO_CAPTURE(ctx, "rb_allreduce_sum");
     RB_REQUIRE(n >= 0, "rb_allreduce_sum: negative length");
     if (!ctx->comm || ctx->comm_world == 1 || n == 0) return RB_OK;
     RB_REQUIRE(buf, "rb_allreduce_sum: buf is NULL");
@@ -194,6 +196,7 @@ extern "C" int rb_allreduce_sum(rb_ctx *ctx, double *buf, int64_t n)
 extern "C" int rb_allgather_shards(rb_ctx *ctx, const double *local, double *full, int64_t naux)
 {
     RB_REQUIRE(ctx && naux >= 0, "rb_allgather_shards: bad arguments");
+    RB_NO_CAPTURE(ctx, "rb_allgather_shards");
     if (naux == 0) return RB_OK;
     RB_REQUIRE(full, "rb_allgather_shards: full is NULL");
     RB_CUDA(cudaSetDevice(ctx->device));

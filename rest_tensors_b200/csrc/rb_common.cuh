@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <mutex>
+#include <vector>
 #include "../../include/rest_b200.h"
 
 typedef int64_t i64;
@@ -65,7 +66,24 @@ struct rb_ctx {
     unsigned sched_next = 0;             // slot of the next GEMM launch (round-robin)
     void *comm = nullptr;                // NCCL communicator (rb_comm.cu), NULL = a world of one
     int comm_rank = 0, comm_world = 1;
+    // CUDA-graph capture of a call sequence (rb_graph_begin / rb_graph_end): while `capturing`, calls that need the host in the loop
+    // (workspace growth, eigen-solvers, collectives) are refused; while recordings are alive, a workspace block that has to grow is
+    // parked instead of freed (the recordings hold its address).
+    int capturing = 0;
+    int live_graphs = 0;
+    i64 capture_launches0 = 0;
+    std::vector<void *> ws_parked;
 };
+
+// For entry points that synchronise with the host or allocate: they cannot be recorded into a CUDA graph.
+#define RB_NO_CAPTURE(ctx, name)                                                                        \
+    do {                                                                                                \
+        if ((ctx)->capturing) {                                                                         \
+            rb_set_error("%s cannot be recorded into a graph (it needs the host inside the call): "     \
+                         "issue it outside rb_graph_begin / rb_graph_end", name);                       \
+            return RB_ERR_UNSUPPORTED;                                                                  \
+        }                                                                                               \
+    } while (0)
 
 // Grow-only device workspace (synchronises the stream before freeing the old block).
 int rb_ws_reserve(rb_ctx *ctx, int slot, i64 bytes, void **out);

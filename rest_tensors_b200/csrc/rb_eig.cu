@@ -605,6 +605,7 @@ extern "C" int rb_dsyev(rb_ctx *ctx, char jobz, char uplo, int n_, const double 
                         int64_t ldz)
 {
     RB_REQUIRE(ctx, "rb_dsyev: ctx is NULL");
+    RB_NO_CAPTURE(ctx, "rb_dsyev");
     RB_REQUIRE(jobz == 'V' || jobz == 'v' || jobz == 'N' || jobz == 'n', "rb_dsyev: jobz must be 'V' or 'N'");
     RB_REQUIRE(rb_is_u(uplo) || rb_is_l(uplo), "rb_dsyev: uplo must be 'U' or 'L'");
     RB_REQUIRE(n_ >= 0, "rb_dsyev: negative dimension");
@@ -628,6 +629,7 @@ extern "C" int rb_dsyev(rb_ctx *ctx, char jobz, char uplo, int n_, const double 
 extern "C" int rb_dspev(rb_ctx *ctx, int n_, const double *ap, double *w, double *z, int64_t ldz)
 {
     RB_REQUIRE(ctx, "rb_dspev: ctx is NULL");
+    RB_NO_CAPTURE(ctx, "rb_dspev");
     RB_REQUIRE(n_ >= 0, "rb_dspev: negative dimension");
     const i64 n = n_;
     if (n == 0) return RB_OK;
@@ -647,6 +649,7 @@ extern "C" int rb_dspev(rb_ctx *ctx, int n_, const double *ap, double *w, double
 extern "C" int rb_dspgv(rb_ctx *ctx, int n_, const double *ap, const double *bp, int m_, double *w, double *z, int64_t ldz)
 {
     RB_REQUIRE(ctx, "rb_dspgv: ctx is NULL");
+    RB_NO_CAPTURE(ctx, "rb_dspgv");
     RB_REQUIRE(n_ >= 0 && m_ >= 0 && m_ <= n_, "rb_dspgv: bad dimensions (n = %d, num_orb = %d)", n_, m_);
     const i64 n = n_, m = m_;
     if (n == 0 || m == 0) return RB_OK;
@@ -685,6 +688,7 @@ extern "C" int rb_matrix_power(rb_ctx *ctx, int n_, const double *a, int64_t lda
                                int64_t ldo, int *n_nonsingular)
 {
     RB_REQUIRE(ctx, "rb_matrix_power: ctx is NULL");
+    RB_NO_CAPTURE(ctx, "rb_matrix_power");
     RB_REQUIRE(n_ >= 0, "rb_matrix_power: negative dimension");
     const i64 n = n_;
     if (n_nonsingular) *n_nonsingular = 0;

@@ -737,10 +737,15 @@ __global__ void __launch_bounds__(256) rb_partial_reduce_kernel(const double *__
                 }
                 const double *pp = partial + (b * n + j) * ldp + i;
                 double s0 = 0.0, s1 = 0.0;
+                if (i + 1 < m) {
 #pragma unroll 8
-                for (int q = 0; q < np; ++q) {
-                    const double2 v = *reinterpret_cast<const double2 *>(pp + (i64)q * split_stride);
-                    s0 += v.x; s1 += v.y;
+                    for (int q = 0; q < np; ++q) {
+                        const double2 v = *reinterpret_cast<const double2 *>(pp + (i64)q * split_stride);
+                        s0 += v.x; s1 += v.y;
+                    }
+                } else { // last row of an odd m: the pad row of the partials was never written, do not touch it
+#pragma unroll 8
+                    for (int q = 0; q < np; ++q) s0 += pp[(i64)q * split_stride];
                 }
                 double *cp = c + b * stride_c + i + j * ldc;
                 if (v0) cp[0] = (beta == 0.0) ? alpha * s0 : alpha * s0 + beta * cp[0];
@@ -1307,7 +1312,7 @@ int rb_gemm_core(rb_ctx *ctx, bool ta, bool tb, i64 m, i64 n, i64 k, double alph
             else RB_TRY((launch_tma<false, false, false>(ctx, tmA, tmB, p, grid)));
         }
         if (splits > 1) {
-            // (row pairs, columns, batches); the partial rows beyond m up to ldp are never read
+            // (row pairs, columns, batches); the pad row of an odd m (ldp = m + 1) is never read
             i64 bx = rb_cdiv(rb_cdiv(m, 2), 256);
             if (bx > 64) bx = 64;
             const i64 by = n < 65535 ? n : 65535, bz = batch < 64 ? batch : 64;

@@ -290,7 +290,9 @@ __global__ void __launch_bounds__(256) rb_symmetrize_kernel(double *__restrict__
     for (int r = 0; r < 4; ++r) {
         int cc = ty + r * 8;
         i64 row = sr0 + tx, col = sc0 + cc;
-        tile[cc][tx] = (row < n && col < n) ? c[row + col * ldc] : 0.0;
+        // only the source triangle is read: the other half of a diagonal tile may never have been written (SYRK with beta == 0)
+        const bool in_src = from_upper ? (row <= col) : (row >= col);
+        tile[cc][tx] = (row < n && col < n && in_src) ? c[row + col * ldc] : 0.0;
     }
     __syncthreads();
 #pragma unroll

@@ -505,6 +505,7 @@ extern "C" int rb_ri_mo_pq_peers(rb_ctx *ctx, int rank, int world, const double 
                                  int64_t cols, const double *w, double *out, int64_t ldo, const int64_t *q_off)
 {
     RB_REQUIRE(ctx && panels && np && q_off, "rb_ri_mo_pq_peers: NULL argument");
+    RB_NO_CAPTURE(ctx, "rb_ri_mo_pq_peers");
     RB_REQUIRE(world >= 1 && rank >= 0 && rank < world && cols >= 0, "rb_ri_mo_pq_peers: bad rank / world / cols");
     const i64 m = np[rank];
     RB_REQUIRE(m >= 0 && ldo >= m, "rb_ri_mo_pq_peers: ldo (%lld) < local rows (%lld)", (long long)ldo, (long long)m);
@@ -574,6 +575,7 @@ extern "C" int rb_special_dgemm_01_peers(rb_ctx *ctx, int rank, int world, const
                                          double beta, double *out)
 {
     RB_REQUIRE(ctx && shards && np && p_off, "rb_special_dgemm_01_peers: NULL argument");
+    RB_NO_CAPTURE(ctx, "rb_special_dgemm_01_peers");
     RB_REQUIRE(world >= 1 && rank >= 0 && rank < world && xy >= 0, "rb_special_dgemm_01_peers: bad rank / world / rows");
     i64 naux = 0, np_max = 0;
     for (int s = 0; s < world; ++s) {

@@ -36,6 +36,50 @@ def _p(t) -> C.c_void_p:
     return C.c_void_p(t.data_ptr())
 
 
+class Graph:
+    """A recorded call sequence (rb_graph_end); launch() replays it on the context's stream."""
+
+    def __init__(self, ctx: "Context", handle):
+        self.ctx, self.h = ctx, handle
+
+    @property
+    def kernels(self) -> int:
+        return int(lib.rb_graph_kernel_count(self.h))
+
+    def launch(self) -> None:
+        check(lib.rb_graph_launch(self.ctx.h, self.h), "rb_graph_launch")
+
+    def close(self) -> None:
+        if self.h and self.ctx.h:
+            check(lib.rb_graph_free(self.ctx.h, self.h), "rb_graph_free")
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _Recording:
+    def __init__(self, ctx: "Context"):
+        self.ctx, self.graph = ctx, None
+
+    def __enter__(self):
+        check(lib.rb_graph_begin(self.ctx.h), "rb_graph_begin")
+        return self
+
+    def __exit__(self, exc_type, exc, tb):
+        h = C.c_void_p()
+        st = lib.rb_graph_end(self.ctx.h, C.byref(h))
+        if exc_type is None:
+            check(st, "rb_graph_end")
+            self.graph = Graph(self.ctx, h)
+        elif st == 0:
+            lib.rb_graph_free(self.ctx.h, h)
+        return False
+
+
 class Context:
     """One rb_ctx bound to a CUDA device; calls run on torch's current stream for that device."""
 
@@ -89,6 +133,21 @@ class Context:
 
     def set_gemm_path(self, path: int) -> None:
         check(lib.rb_ctx_set_gemm_path(self.h, path), "rb_ctx_set_gemm_path")
+
+    def use_own_stream(self) -> None:
+        """run this context's calls on the library's own (non-default) stream instead of torch's current one"""
+        check(lib.rb_ctx_use_own_stream(self.h), "rb_ctx_use_own_stream")
+
+    def record(self) -> "_Recording":
+        """`with ctx.record() as rec: <calls>` records the calls on this context into a CUDA graph (they do not run); afterwards
+        `rec.graph.launch()` replays them with one launch.  The context must be on a non-default stream (bind_stream() inside
+        `torch.cuda.stream(s)`, or use_own_stream()), the sequence must have run once before, and every buffer it touches --
+        outputs included -- must exist before recording (no torch allocation inside)."""
+        return _Recording(self)
+
+    def poison_workspaces(self):
+        """Test hook: every internal workspace := NaN pattern (a stale read then shows in the result)."""
+        check(lib.rb_ctx_poison_workspaces(self.h), "rb_ctx_poison_workspaces")
 
     # -- collectives (NCCL inside librest_b200) --
     @property

@@ -29,6 +29,33 @@ impl Drop for Context {
     fn drop(&mut self) { unsafe { rb_ctx_destroy(self.raw); } }
 }
 
+/// A recorded call sequence (CUDA graph): the d_P / J / K calls of one SCF iteration issued once between `Context::record`
+/// and `Recording::finish`, then replayed with one launch per iteration.  See include/rest_b200.h (rb_graph_begin) for the
+/// rules (non-default stream, one un-recorded pass first, no eigen-solver / collective inside).
+pub struct Graph<'a> { ctx: &'a Context, raw: *mut c_void }
+
+impl Context {
+    /// the library's own stream: the default stream cannot be captured
+    pub fn use_own_stream(&self) { unsafe { check(rb_ctx_use_own_stream(self.raw), "rb_ctx_use_own_stream"); } }
+    /// record the calls `f` issues on this context; they do not run
+    pub fn record<F: FnOnce()>(&self, f: F) -> Graph<'_> {
+        let mut raw: *mut c_void = ptr::null_mut();
+        unsafe { check(rb_graph_begin(self.raw), "rb_graph_begin"); }
+        f();
+        unsafe { check(rb_graph_end(self.raw, &mut raw), "rb_graph_end"); }
+        Graph { ctx: self, raw }
+    }
+}
+
+impl<'a> Graph<'a> {
+    pub fn launch(&self) { unsafe { check(rb_graph_launch(self.ctx.raw, self.raw), "rb_graph_launch"); } }
+    pub fn kernels(&self) -> i64 { unsafe { rb_graph_kernel_count(self.raw) } }
+}
+
+impl<'a> Drop for Graph<'a> {
+    fn drop(&mut self) { unsafe { rb_graph_free(self.ctx.raw, self.raw); } }
+}
+
 /// FP64 buffer in HBM owned by a context
 pub struct DeviceBuffer<'a> { pub ctx: &'a Context, pub ptr: *mut f64, pub len: usize }
 

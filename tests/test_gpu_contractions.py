@@ -817,3 +817,76 @@ def test_host_register_makes_a_caller_buffer_pinned(rt, oracle_blas):
     assert np.array_equal(again, ref)
     vec, w, n3 = rt._dsyev(rt.MatrixFull.from_vec([3, 3], np.array([2.0, 1, 0, 1, 2, 1, 0, 1, 2])), "V")
     assert n3 == 3 and abs(w[1] - 2.0) < 1e-13
+
+
+def test_partials_never_read_stale_workspace(ctx):
+    """Every kernel that sums workspace partials (split-K and stream-K GEMM / SYRK, the packed-M half-transform of the K build, GEMV
+    column chunks, ao2mo panels, the eigen-solver's scratch) must read only what the same call wrote: with every workspace poisoned
+    to NaN right before the call the result has to be finite and bit-identical to the unpoisoned run.  (A stale read is how a wrong
+    tile / piece bookkeeping shows up as run-to-run differences instead of a plain wrong answer.)"""
+    from rest_tensors_b200.device import ShardedRI
+    from rest_tensors_b200._lib import lib
+
+    def both(fn):
+        r0 = fn().clone()
+        ctx.poison_workspaces()
+        r1 = fn().clone()
+        assert bool(torch.isfinite(r1).all()), "result depends on workspace memory the call did not write"
+        assert torch.equal(r0, r1)
+
+    kinds = set()
+    for (m, n, k, batch) in [(500, 500, 500, 1), (264, 264, 15120, 1), (129, 1030, 777, 1), (300, 200, 5000, 3), (600, 600, 102000, 1),
+                             (1800, 1800, 19200, 1), (200, 130, 6000, 1), (1000, 72, 9000, 1), (40, 40, 20000, 1)]:
+        kinds.add(int(lib.rb_gemm_plan_stream_k(m, n, k, batch, 0, ctx.num_sms, None)))
+        a = ctx.empty(batch * m * k); b = ctx.empty(batch * k * n)
+        ctx.fill_linear(a, a.numel(), 51, 0, 1.0); ctx.fill_linear(b, b.numel(), 52, 0, 1.0)
+
+        def gemm(ta="N", tb="N"):
+            c = ctx.empty(batch * m * n); c.zero_()
+            if batch == 1:
+                ctx.dgemm(ta, tb, m, n, k, 1.0, a, m if ta == "N" else k, b, k if tb == "N" else n, 0.0, c, m)
+            else:
+                ctx.dgemm_strided_batched("N", "N", m, n, k, 1.0, a, m, m * k, b, k, k * n, 0.0, c, m, m * n, batch)
+            return c
+        both(gemm)
+        if batch == 1:
+            both(lambda: gemm("T", "T"))
+        if m == n and batch == 1:
+            for uplo in ("U", "L"):
+                def syrk():
+                    c = ctx.empty(n * n); c.zero_()
+                    ctx.dsyrk(uplo, "N", n, k, 1.0, a, n, 0.0, c, n)
+                    return c
+                both(syrk)
+    assert kinds == {0, 1}, "the shape list is meant to cover both the uniform split and stream-K"
+
+    for nb, nx, no in [(264, 720, 21), (600, 200, 60), (45, 77, 7)]:
+        sh = ShardedRI(ctx, nb, nx).fill_synthetic()
+        cm = ctx.empty(nb * nb); ctx.fill_linear(cm, nb * nb, 3, 0, nb ** -0.5)
+        cocc = cm[: nb * no].clone()
+        both(lambda: sh.k(cocc, no))
+        both(lambda: sh.ao2mo(cm, nb, cm, nb))
+        d = sh.dp(cm)
+        both(lambda: sh.dp(cm))
+        both(lambda: sh.j(d))
+
+    # GEMV column / row chunk partials (workspace slot 1) and the eigen-solver's scratch (slot 0)
+    for trans, (m, n) in [("T", (360000, 70)), ("N", (360000, 70)), ("N", (5000, 3)), ("T", (77, 1900))]:
+        a = ctx.empty(m * n); ctx.fill_linear(a, m * n, 53, 0, 1.0)
+        nx_, ny_ = (n, m) if trans == "N" else (m, n)
+        x = ctx.empty(nx_); ctx.fill_linear(x, nx_, 54, 0, 1.0)
+
+        def gemv():
+            y = ctx.empty(ny_); y.zero_()
+            ctx.dgemv(trans, m, n, 1.0, a, m, x, 1, 0.0, y, 1)
+            return y
+        both(gemv)
+    for n in (3, 65, 300):
+        s = ctx.empty(n * n); ctx.fill_linear(s, n * n, 55, 0, 1.0)
+        sym = (s.view(n, n) + s.view(n, n).t()).contiguous().view(-1)
+
+        def eig():
+            w = ctx.empty(n); z = ctx.empty(n * n)
+            ctx.dsyev("V", "U", n, sym.clone(), n, w, z, n)
+            return torch.cat([w, z])
+        both(eig)
