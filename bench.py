@@ -531,7 +531,41 @@ def e2e_variants_leg(env, lib, check, w, steps=3):
                           "h2d_bytes_per_step": (nx * n2 + 2 * n2 + nb * no) * 8,
                           "d2h_bytes_per_step": (nx * no * nv + 2 * n2 + nx) * 8, "matches_device_path": ok,
                           "api": "rb_host_ri_ao2mo_jk(C_occ, C_vir) (host-pointer C ABI, pinned buffers)"}
-        del ri_h, ov_h
+        del ov_h
+        # square C, but only the a <= b pairs of ri3mo travel back (-50 % D2H)
+        try:
+            npair = nb * (nb + 1) // 2
+            up_h = mk(nx * npair)
+
+            def up_step():
+                check(lib.rb_host_ri_ao2mo_jk_upper(P(c_h), nb, P(ri_h), P(up_h), nb, nx, P(dm_h), P(ct_h), no, P(d_h), P(j_h),
+                                                    P(k_h)), "rb_host_ri_ao2mo_jk_upper")
+            up_step()
+            w.step(True)
+            torch.cuda.synchronize()
+            # pair (a, b) of slab column P  <->  w.mo[P + nx * (a + nb * b)]
+            bs = torch.tensor([0, 1, nb // 3, nb // 2, nb - 1]); as_ = torch.tensor([0, 0, nb // 5, nb // 2, nb - 2])
+            ok_up = True
+            for a_, b_ in zip(as_.tolist(), bs.tolist()):
+                a_ = min(a_, b_)
+                got = up_h[nx * (b_ * (b_ + 1) // 2 + a_): nx * (b_ * (b_ + 1) // 2 + a_ + 1)]
+                ref = w.mo[nx * (a_ + nb * b_): nx * (a_ + nb * b_ + 1)].cpu()
+                ok_up = ok_up and bool(torch.equal(got, ref))
+            ok_up = ok_up and bool(torch.allclose(k_h, w.k.cpu(), rtol=1e-11, atol=1e-12))
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                up_step()
+            dt = (time.perf_counter() - t0) / steps
+            flop = sum(flops(nb, nx, no, True).values())
+            out["upper_packed"] = {"ms_per_step": dt * 1e3, "value": flop / dt / 1e9, "unit": UNIT,
+                                   "h2d_bytes_per_step": (nx * n2 + 2 * n2 + nb * no) * 8,
+                                   "d2h_bytes_per_step": (nx * npair + 2 * n2 + nx) * 8, "matches_device_path": ok_up,
+                                   "api": "rb_host_ri_ao2mo_jk_upper (square C; ri3mo[P, a<=b] only: the slabs are symmetric)",
+                                   "note": "value counts the flop of the square step (the device still forms the full ri3mo chunk)"}
+            del up_h
+        except Exception as exc:  # noqa: BLE001
+            out["upper_packed"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        del ri_h
         # resident shard: only D, C~ up and J, K down per iteration
         ctx = env.ctx
 

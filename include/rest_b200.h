@@ -186,6 +186,13 @@ int rb_host_ri_ao2mo(const double *c_left, int nl, const double *c_right, int nr
 int rb_host_ri_ao2mo_jk(const double *c_left, int nl, const double *c_right, int nr, const double *ri3ao,
                         double *ri3mo, int nb, int nx, const double *dm, const double *ct, int no, double *d, double *j,
                         double *k);
+/* Same pass with ONE coefficient matrix c [nb, nmo] on both sides, shipping only the a <= b part of the transformed tensor:
+ *   ri3mo_upper[P + nx * (b (b + 1) / 2 + a)] = ri3mo[P, a, b],  0 <= a <= b < nmo   (MatrixUpper's pair index, P fastest).
+ * The slabs of ri3ao are symmetric (RIFull built by the reference's 3-centre integral code), so ri3mo[P, a, b] == ri3mo[P, b, a] and
+ * nothing is lost, while the device -> host traffic of the pass halves (nmo (nmo + 1) / 2 instead of nmo^2 columns).  For slabs that
+ * are not symmetric the result is still exactly the a <= b entries of rb_host_ri_ao2mo_jk's output. */
+int rb_host_ri_ao2mo_jk_upper(const double *c, int nmo, const double *ri3ao, double *ri3mo_upper, int nb, int nx,
+                              const double *dm, const double *ct, int no, double *d, double *j, double *k);
 /* axpy family on host buffers (matrix/mod.rs:545-648, ri.rs:345-354, matrixupper.rs:395-420):
  * op 0: c += p*b   1: c = c*a + p*b   2: c *= a   3: c += p   4: c -= p   (unfused mul-then-add, bit-exact) */
 int rb_host_axpy(int op, double *c, const double *p, double a, double b, int64_t n);

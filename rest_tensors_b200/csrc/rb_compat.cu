@@ -360,10 +360,34 @@ struct Pipe {
 
 // One streaming pass over the host ri3ao: every P-chunk is uploaded ONCE and feeds ao2mo (if out != NULL) and the
 // d_P / J / K builds (if dm / ct != NULL); J and K accumulate across chunks on the device.
+// ri3mo[P, a, b] -> the a <= b part, P fastest: packed[P + pn * (b (b + 1) / 2 + a)].  For a fixed b the pairs (0..b, b) are one
+// contiguous run of (b + 1) * pn doubles on both sides, so this is nl plain copies (blockIdx.y = b); 32-byte accesses when pn % 4 == 0.
+__global__ void __launch_bounds__(256) rb_ri3mo_pack_pairs_kernel(const double *__restrict__ full, double *__restrict__ packed, i64 pn, i64 nl,
+                                                                 int vec4)
+{
+    const i64 b = blockIdx.y;
+    const i64 len = (b + 1) * pn;
+    const double *s = full + pn * nl * b;
+    double *d = packed + pn * (b * (b + 1) / 2);
+    const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x, nt = (i64)gridDim.x * blockDim.x;
+    if (vec4) {
+        const i64 n4 = len >> 2;
+        i64 i = t;
+        for (; i + nt < n4; i += 2 * nt) {
+            const rb_d4 v0 = rb_ld256(s + 4 * i), v1 = rb_ld256(s + 4 * (i + nt));
+            rb_st256(d + 4 * i, v0); rb_st256(d + 4 * (i + nt), v1);
+        }
+        for (; i < n4; i += nt) rb_st256(d + 4 * i, rb_ld256(s + 4 * i));
+    } else {
+        for (i64 i = t; i < len; i += nt) d[i] = s[i];
+    }
+}
+
 int host_ri_stream(const double *cl, int nl, const double *cr, int nr, const double *ri3ao, double *out, int nb_, int nx_,
-                   const double *dm, const double *ct, int no, double *d_out, double *j_out, double *k_out)
+                   const double *dm, const double *ct, int no, double *d_out, double *j_out, double *k_out, bool upper_out = false)
 {
     RB_REQUIRE(nl >= 0 && nr >= 0 && nb_ >= 0 && nx_ >= 0 && no >= 0, "ri stream: negative dimension");
+    RB_REQUIRE(!upper_out || (cl == cr && nl == nr), "ri stream: the packed (a <= b) output needs the same C on both sides");
     const i64 nb = nb_, nx = nx_;
     const bool do_mo = out != nullptr && nl > 0 && nr > 0;
     const bool do_j = dm != nullptr && (d_out != nullptr || j_out != nullptr);
@@ -379,10 +403,12 @@ int host_ri_stream(const double *cl, int nl, const double *cr, int nr, const dou
     if (const char *e = getenv("REST_B200_PC")) { i64 v = atoll(e); if (v >= 8) pc = v; }
     // (Measured on this pool, profiles/r01_e2e_variants.md: letting GEMM 2 store straight into mapped pinned host memory
     //  is slower -- 223 ms vs 130 ms per pass at config C -- than staging in HBM and draining with 2-D copies.)
+    // slab_out: columns of the device ri3mo chunk; ship_out: columns that travel to the host (the a <= b pairs when upper_out)
     const i64 slab_in = nb * nb, slab_out = do_mo ? (i64)nl * nr : 0;
-    while (pc > 8 && pc * (slab_in + slab_out) * 8 * 2 > ((i64)6 << 30)) pc >>= 1;
+    const i64 ship_out = (do_mo && upper_out) ? (i64)nl * (nl + 1) / 2 : slab_out;
+    while (pc > 8 && pc * (slab_in + slab_out + (upper_out ? ship_out : 0)) * 8 * 2 > ((i64)6 << 30)) pc >>= 1;
     if (pc > nx) pc = nx;
-    double *d_cl = nullptr, *d_cr = nullptr, *d_in[2], *d_mo[2] = {nullptr, nullptr};
+    double *d_cl = nullptr, *d_cr = nullptr, *d_in[2], *d_mo[2] = {nullptr, nullptr}, *d_pk[2] = {nullptr, nullptr};
     double *d_dm = nullptr, *d_ct = nullptr, *d_d = nullptr, *d_j = nullptr, *d_k = nullptr;
     const bool same_c = (cl == cr && nl == nr);
     if (do_mo) {
@@ -392,6 +418,7 @@ int host_ri_stream(const double *cl, int nl, const double *cr, int nr, const dou
     for (int i = 0; i < 2; ++i) {
         RB_TRY(op.alloc(pc * slab_in, &d_in[i]));
         if (do_mo) RB_TRY(op.alloc(pc * slab_out, &d_mo[i]));
+        if (do_mo && upper_out) RB_TRY(op.alloc(pc * ship_out, &d_pk[i]));
     }
     if (do_j) { RB_TRY(op.alloc(slab_in, &d_dm)); RB_TRY(op.alloc(nx, &d_d)); RB_TRY(op.alloc(slab_in, &d_j)); }
     if (do_k) { RB_TRY(op.alloc(nb * no, &d_ct)); RB_TRY(op.alloc(slab_in, &d_k)); }
@@ -435,7 +462,7 @@ int host_ri_stream(const double *cl, int nl, const double *cr, int nr, const dou
     if (in_pageable)
         for (int i = 0; i < 2; ++i) if (!(pin_in[i] = (double *)pin_take(pc * slab_in * 8))) in_pageable = false;
     if (out_pageable)
-        for (int i = 0; i < 2; ++i) if (!(pin_out[i] = (double *)pin_take(pc * slab_out * 8))) out_pageable = false;
+        for (int i = 0; i < 2; ++i) if (!(pin_out[i] = (double *)pin_take(pc * ship_out * 8))) out_pageable = false;
     // REST_B200_TRACE: per-chunk timeline (timing events; start of H2D, end of H2D / compute / D2H relative to t0)
     std::vector<cudaEvent_t> tl;
     cudaEvent_t tl0 = nullptr;
@@ -466,6 +493,16 @@ int host_ri_stream(const double *cl, int nl, const double *cr, int nr, const dou
         RB_CUDA(cudaStreamWaitEvent(ctx->stream, pipe.in_done[s], 0));
         if (step >= 2) RB_CUDA(cudaStreamWaitEvent(ctx->stream, pipe.out_done[s], 0));
         if (do_mo) RB_TRY(rb_ri_ao2mo(ctx, d_cl, nl, d_cr, nr, d_in[s], d_mo[s], nb_, (int)pn, pn));
+        const double *d_ship = d_mo[s];
+        if (do_mo && upper_out) {
+            const int vec4 = ((pn & 3) == 0 && rb_aligned32(d_mo[s]) && rb_aligned32(d_pk[s])) ? 1 : 0;
+            i64 bx = rb_cdiv(rb_cdiv((i64)nl * pn, vec4 ? 8 : 2), 256);
+            if (bx > 32) bx = 32;
+            if (bx < 1) bx = 1;
+            rb_ri3mo_pack_pairs_kernel<<<dim3((unsigned)bx, (unsigned)nl), 256, 0, ctx->stream>>>(d_mo[s], d_pk[s], pn, nl, vec4);
+            RB_LAUNCHED(ctx);
+            d_ship = d_pk[s];
+        }
         if (do_j && slab_in > 0) {
             RB_TRY(rb_ri_dp(ctx, d_in[s], d_dm, d_d + p0, nb_, (int)pn));
             RB_TRY(rb_dgemv(ctx, 'N', (int)slab_in, (int)pn, 1.0, d_in[s], slab_in, d_d + p0, 1, p0 == 0 ? 0.0 : 1.0, d_j, 1));
@@ -477,16 +514,16 @@ int host_ri_stream(const double *cl, int nl, const double *cr, int nr, const dou
             // D2H: rows of pn doubles into the P-fastest host tensor (pitch nx)
             RB_CUDA(cudaStreamWaitEvent(pipe.s_out, pipe.comp_done[s], 0));
             if (out_pageable) // dense copy into the pinned block; host threads scatter it one chunk later
-                RB_CUDA(cudaMemcpyAsync(pin_out[s], d_mo[s], (size_t)(pn * slab_out) * 8, cudaMemcpyDeviceToHost, pipe.s_out));
+                RB_CUDA(cudaMemcpyAsync(pin_out[s], d_ship, (size_t)(pn * ship_out) * 8, cudaMemcpyDeviceToHost, pipe.s_out));
             else
-                RB_CUDA(cudaMemcpy2DAsync(out + p0, (size_t)nx * 8, d_mo[s], (size_t)pn * 8, (size_t)pn * 8, (size_t)slab_out,
+                RB_CUDA(cudaMemcpy2DAsync(out + p0, (size_t)nx * 8, d_ship, (size_t)pn * 8, (size_t)pn * 8, (size_t)ship_out,
                                           cudaMemcpyDeviceToHost, pipe.s_out));
             RB_CUDA(cudaEventRecord(pipe.out_done[s], pipe.s_out));
             mark(pipe.s_out);
             if (out_pageable && ci >= 1) { // previous chunk: its D2H ran while this chunk was copied in and enqueued
                 const i64 pp = sizes[ci - 1];
                 RB_CUDA(cudaEventSynchronize(pipe.out_done[s ^ 1]));
-                host_copy_2d(out + (p0 - pp), nx, pin_out[s ^ 1], pp, pp, slab_out);
+                host_copy_2d(out + (p0 - pp), nx, pin_out[s ^ 1], pp, pp, ship_out);
             }
         }
     }
@@ -494,7 +531,7 @@ int host_ri_stream(const double *cl, int nl, const double *cr, int nr, const dou
         const i64 pp = sizes.back();
         const int s = (step - 1) & 1;
         RB_CUDA(cudaEventSynchronize(pipe.out_done[s]));
-        host_copy_2d(out + (nx - pp), nx, pin_out[s], pp, pp, slab_out);
+        host_copy_2d(out + (nx - pp), nx, pin_out[s], pp, pp, ship_out);
     }
     const double t_enq = now_ms();
     if (do_k && slab_in > 0) RB_TRY(rb_symmetrize(ctx, d_k, nb, nb, true));
@@ -771,6 +808,12 @@ extern "C" int rb_host_ri_ao2mo_jk(const double *c_left, int nl, const double *c
                                    double *j, double *k)
 {
     return host_ri_stream(c_left, nl, c_right, nr, ri3ao, ri3mo, nb, nx, dm, ct, no, d, j, k);
+}
+
+extern "C" int rb_host_ri_ao2mo_jk_upper(const double *c, int nmo, const double *ri3ao, double *ri3mo_upper, int nb, int nx,
+                                         const double *dm, const double *ct, int no, double *d, double *j, double *k)
+{
+    return host_ri_stream(c, nmo, c, nmo, ri3ao, ri3mo_upper, nb, nx, dm, ct, no, d, j, k, true);
 }
 
 extern "C" int rb_host_dgemm(char ta, char tb, int m, int n, int k, double alpha, const double *a, int lda,

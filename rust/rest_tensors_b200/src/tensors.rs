@@ -148,6 +148,20 @@ impl RIFull {
         }
         (mo, d, j, k)
     }
+    /// ao2mo_jk shipping only the a <= b part of ri3mo: upper[P + nx * (b(b+1)/2 + a)] (MatrixUpper's pair index per P); for the
+    /// symmetric slabs of an RI tensor that is the whole result at half the device -> host traffic
+    pub fn ao2mo_jk_upper(&self, c: &MatrixFull, dm: &MatrixFull, ct: &MatrixFull) -> (Vec<f64>, Vec<f64>, MatrixFull, MatrixFull) {
+        let (nb, ns, nx) = (self.size[0], c.size[1], self.size[2]);
+        let mut upper = vec![0.0f64; nx * (ns * (ns + 1) / 2)];
+        let mut d = vec![0.0f64; nx];
+        let (mut j, mut k) = (MatrixFull::new([nb, nb], 0.0), MatrixFull::new([nb, nb], 0.0));
+        unsafe {
+            check(rb_host_ri_ao2mo_jk_upper(c.data.as_ptr(), ci(ns), self.data.as_ptr(), upper.as_mut_ptr(), ci(nb), ci(nx),
+                                            dm.data.as_ptr(), ct.data.as_ptr(), ci(ct.size[1]), d.as_mut_ptr(),
+                                            j.data.as_mut_ptr(), k.data.as_mut_ptr()), "ao2mo_jk_upper");
+        }
+        (upper, d, j, k)
+    }
     /// src/ri.rs:227-294; which = 0 jik, 1 jki, 2 kji, 3 ikj
     pub fn transpose(&self, which: usize) -> RIFull {
         let [i, j, k] = self.size;

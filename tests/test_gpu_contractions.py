@@ -699,6 +699,37 @@ def test_fused_streaming_step(rt, oracle_blas):
     assert_close_1e10(k.data, oracle_blas.ri_k(ri, ct, nb, no, nx), "fused K")
 
 
+@pytest.mark.parametrize("nb,ns,nx,no,pinned,symm", [(40, 40, 600, 6, False, True), (33, 21, 301, 5, False, True),
+                                                         (64, 64, 520, 9, True, True), (24, 24, 50, 4, False, False)])
+def test_fused_streaming_step_upper_output(rt, oracle_blas, nb, ns, nx, no, pinned, symm):
+    """ao2mo_jk_upper ships only the a <= b pairs of ri3mo (MatrixUpper's pair index per P, P fastest): bit for bit the a <= b
+    entries of the full pass, equal to the oracle's ri_ao2mo_f, with d_P / J / K unchanged; odd chunk sizes (nx = 301: scalar
+    pack kernel), several chunks, a rectangular coefficient block (ns < nb), pageable and page-locked host buffers."""
+    import ctypes as C
+    from rest_tensors_b200._lib import lib, check
+    ri, c_full, dm, ct = _inputs(oracle_blas, nb, nx, no, symm)
+    c = np.ascontiguousarray(c_full[: nb * ns])
+    if pinned:
+        check(lib.rb_host_register(C.c_void_p(ri.ctypes.data), ri.nbytes), "rb_host_register")
+    try:
+        rif = rt.RIFull.from_vec([nb, nb, nx], ri)
+        args = (rt.MatrixFull.from_vec([nb, ns], c), rt.MatrixFull.from_vec([nb, nb], dm), rt.MatrixFull.from_vec([nb, no], ct))
+        upper, d, j, k = rif.ao2mo_jk_upper(*args)
+        mo, d2, j2, k2 = rif.ao2mo_jk(*args)
+    finally:
+        if pinned:
+            check(lib.rb_host_unregister(C.c_void_p(ri.ctypes.data)), "rb_host_unregister")
+    full = mo.data.reshape((nx, ns, ns), order="F")
+    up = upper.reshape((nx, ns * (ns + 1) // 2), order="F")
+    for b in range(ns):
+        for a in range(b + 1):
+            assert np.array_equal(up[:, b * (b + 1) // 2 + a], full[:, a, b]), (a, b)
+    assert np.array_equal(d, d2) and np.array_equal(j.data, j2.data) and np.array_equal(k.data, k2.data)
+    w3 = np.asarray(oracle_blas.ri_ao2mo_rect(c, ns, c, ns, ri, nb, nx)).reshape((nx, ns, ns), order="F")
+    ref_up = np.stack([w3[:, a, b] for b in range(ns) for a in range(b + 1)], axis=1)
+    assert_close_1e10(up.ravel(order="F"), ref_up.ravel(order="F"), "upper ao2mo vs oracle")
+
+
 # ---------------------------------------------------------------- special_dgemm_f_01 ----
 def test_special_dgemm_f_01(rt, oracle_blas):
     X, Y, Z = 12, 7, 10
