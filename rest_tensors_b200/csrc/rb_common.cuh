@@ -107,7 +107,7 @@ static inline bool rb_is_l(char c) { return c == 'L' || c == 'l'; }
 
 // ---- 256-bit global accesses (sm_100: LDG.E.ENL2.256 / STG.E.ENL2.256) ------------------------------------------------
 // Measured on this pool's B200 (tools/micro/copy_bench.cu, profiles/r02_copy_microbench.md): a 1 read : 1 write SM kernel
-// moves 7.2 TB/s with 32-byte accesses, 8 of them in flight per thread and >= 16 CTAs per SM in the grid, against 6.3 TB/s
+// moves 6.6-6.7 TB/s with 32-byte accesses, 8 of them in flight per thread and >= 16 CTAs per SM in the grid, against 6.3 TB/s
 // with 16-byte accesses and 6.5 TB/s for the driver's device-to-device memcpy.  Addresses must be 32-byte aligned.
 struct alignas(32) rb_d4 { double x, y, z, w; };
 #ifdef __CUDACC__

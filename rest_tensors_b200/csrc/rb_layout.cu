@@ -365,8 +365,8 @@ __global__ void __launch_bounds__(256) rb_copy3d_kernel(const double *__restrict
 }
 
 // one contiguous run of niv 32-byte vectors: grid-stride with 8 loads in flight per thread, each a whole grid apart -- the
-// access pattern of the fastest variant of tools/micro/copy_bench.cu (7.2-7.6 TB/s with >= 16 CTAs per SM in the grid; taking
-// contiguous 32 KB chunks per CTA instead measured 6.6 TB/s on the same buffers)
+// access pattern of the fastest variant of tools/micro/copy_bench.cu (6.6-6.7 TB/s with >= 16 CTAs per SM in the grid; taking
+// contiguous chunks per CTA instead is no faster)
 __global__ void __launch_bounds__(256) rb_copy_flat4_kernel(const double *__restrict__ s, double *__restrict__ d, i64 niv)
 {
     const i64 stride = (i64)gridDim.x * blockDim.x;

@@ -14,7 +14,7 @@
 // TMA needs 16-byte aligned bases and strides: operands with an odd leading dimension or an 8-byte-aligned base keep the
 // plain-load kernels of rb_layout.cu (the callers fall back when rb_tma_* returns RB_TMA_NOT_ELIGIBLE).
 // MEASURED (profiles/r02_hbm_kernels.md): these kernels move 5.0-5.7 TB/s, no more than the 16-byte plain-load kernels they
-// were meant to replace, while 32-byte LDG/STG kernels (rb_layout.cu) reach 6.5-7.2 TB/s; the bulk-tensor path is therefore
+// were meant to replace, while 32-byte LDG/STG kernels (rb_layout.cu) reach 6.2-6.6 TB/s; the bulk-tensor path is therefore
 // opt-in (rb_ctx_set_layout_path(ctx, 1) or REST_B200_LAYOUT_TMA=1) and kept for comparison and for its tests.
 #include "rb_common.cuh"
 

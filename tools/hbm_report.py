@@ -10,7 +10,7 @@ except Exception:
     pass
 out = ["# Round 2 — HBM-bound kernels (tools/hbm_probe.py, one B200, CUDA events, inputs > L2)\n",
        f"Denominator: MEASURED_PEAKS.json `hbm_gbs` = {peak} GB/s (the driver's torch `copy_` = cudaMemcpyAsync D2D). `tools/micro/copy_bench.cu` shows that this is",
-       "not the ceiling of the part: SM kernels with 32-byte accesses reach 7.2-7.6 TB/s for mixed and 8.2 TB/s for read-only traffic (`r02_copy_microbench.md`),",
+       "close to the ceiling of the part for SM kernels as well: 32-byte grid-stride kernels reach 6.6-6.7 TB/s for a copy, 6.5 for a 1 read : 2 write mix, 7.0 read-only (`r02_copy_microbench.md`; its first version reported 7.2-8.2 TB/s from loops that dropped their tail),",
        "so fractions above 1.0 are possible.\n",
        "Two timings per kernel: **single call** = one launch inside one CUDA-event pair, best of 7 (includes the ~5 us an event pair adds around one launch:",
        "3 % at n = 8000, 12 % at n = 4000); **stream** = the call issued back to back over >= 1 GB of distinct buffer sets inside ONE event pair (the sustained",

@@ -67,13 +67,17 @@ struct alignas(32) d4 { double a, b, c, e; };
 template <int U, bool EF>
 __global__ void __launch_bounds__(256) k_stride32(const d4 *__restrict__ s, d4 *__restrict__ d, size_t n)
 {
+    // (Until round 2's last session this loop had no tail: `i + (U - 1) * stride < n` dropped the last, partial pass -- up to 15 % of the
+    //  buffer with 32 CTAs per SM -- and every "7.2 - 8.2 TB/s" figure taken from it was inflated by that share.  The last pass is
+    //  predicated now, as in the library's rb_copy_flat4_kernel.)
     size_t stride = (size_t)gridDim.x * blockDim.x;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (; i + (U - 1) * stride < n; i += U * stride) {
+    for (; i < n; i += U * stride) {
         d4 v[U];
 #pragma unroll
         for (int u = 0; u < U; ++u)
         {
+            if (i + u * stride >= n) continue;
             unsigned long long a, b, c, e;
             if (EF) asm volatile("ld.global.L1::no_allocate.L2::evict_first.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(e) : "l"(s + i + u * stride));
             else asm volatile("ld.global.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(e) : "l"(s + i + u * stride));
@@ -82,6 +86,7 @@ __global__ void __launch_bounds__(256) k_stride32(const d4 *__restrict__ s, d4 *
 #pragma unroll
         for (int u = 0; u < U; ++u)
         {
+            if (i + u * stride >= n) continue;
             if (EF) asm volatile("st.global.L1::no_allocate.L2::evict_first.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(d + i + u * stride), "l"(__double_as_longlong(v[u].a)), "l"(__double_as_longlong(v[u].b)), "l"(__double_as_longlong(v[u].c)), "l"(__double_as_longlong(v[u].e)) : "memory");
             else asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(d + i + u * stride), "l"(__double_as_longlong(v[u].a)), "l"(__double_as_longlong(v[u].b)), "l"(__double_as_longlong(v[u].c)), "l"(__double_as_longlong(v[u].e)) : "memory");
         }
@@ -96,20 +101,25 @@ __global__ void __launch_bounds__(256) k_mix32(const d4 *__restrict__ s, const d
     size_t stride = (size_t)gridDim.x * blockDim.x;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     double acc = 0.0;
-    for (; i + (U - 1) * stride < n; i += U * stride) {
+    for (; i < n; i += U * stride) { // last pass predicated (see k_stride32)
         d4 v[U], w[U];
+#define IN(u) (i + (u) * stride < n)
         if (MODE != 0) {
 #pragma unroll
-            for (int u = 0; u < U; ++u)
-                asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[u].a), "=d"(v[u].b), "=d"(v[u].c), "=d"(v[u].e) : "l"(s + i + u * stride));
+            for (int u = 0; u < U; ++u) {
+                v[u].a = 0.0; v[u].b = 0.0; v[u].c = 0.0; v[u].e = 0.0;
+                if (IN(u)) asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[u].a), "=d"(v[u].b), "=d"(v[u].c), "=d"(v[u].e) : "l"(s + i + u * stride));
+            }
         } else {
 #pragma unroll
             for (int u = 0; u < U; ++u) { v[u].a = 1.0; v[u].b = 2.0; v[u].c = 3.0; v[u].e = (double)i; }
         }
         if (MODE == 2) {
 #pragma unroll
-            for (int u = 0; u < U; ++u)
-                asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(w[u].a), "=d"(w[u].b), "=d"(w[u].c), "=d"(w[u].e) : "l"(s2 + i + u * stride));
+            for (int u = 0; u < U; ++u) {
+                w[u].a = 0.0; w[u].b = 0.0; w[u].c = 0.0; w[u].e = 0.0;
+                if (IN(u)) asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(w[u].a), "=d"(w[u].b), "=d"(w[u].c), "=d"(w[u].e) : "l"(s2 + i + u * stride));
+            }
 #pragma unroll
             for (int u = 0; u < U; ++u) { v[u].a += w[u].a; v[u].b += w[u].b; v[u].c += w[u].c; v[u].e += w[u].e; }
         }
@@ -120,12 +130,13 @@ __global__ void __launch_bounds__(256) k_mix32(const d4 *__restrict__ s, const d
         }
 #pragma unroll
         for (int u = 0; u < U; ++u)
-            asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(d + i + u * stride), "d"(v[u].a), "d"(v[u].b), "d"(v[u].c), "d"(v[u].e) : "memory");
+            if (IN(u)) asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(d + i + u * stride), "d"(v[u].a), "d"(v[u].b), "d"(v[u].c), "d"(v[u].e) : "memory");
         if (MODE == 1) {
 #pragma unroll
             for (int u = 0; u < U; ++u)
-                asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(d2 + i + u * stride), "d"(v[u].a), "d"(v[u].b), "d"(v[u].c), "d"(v[u].e) : "memory");
+                if (IN(u)) asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(d2 + i + u * stride), "d"(v[u].a), "d"(v[u].b), "d"(v[u].c), "d"(v[u].e) : "memory");
         }
+#undef IN
     }
     if (MODE == 3 && acc == 12345.678) *sink = acc;
 }
