@@ -156,6 +156,9 @@ __global__ void __launch_bounds__(256) rb_unpack_upper_kernel(const double *__re
 }
 
 
+// (Occupancy: these kernels run 4 CTAs per SM -- 58-62 registers, 32 KB of exchange buffer.  Compiling them for 5 or 6 CTAs per SM
+//  (`__launch_bounds__(256, 5 / 6)`: 48 / 40 registers, a few spilled bytes) with the maximum shared-memory carve-out was measured at
+//  4.1-4.9 TB/s against 5.8-6.3 (tools/gpu_batch_r02ac.sh): the smaller L1 hurts the 32-byte streams more than the extra CTAs help.)
 // ---- 32-byte exchange through shared memory (shared by the 256-bit unpack and transpose kernels) ---------------------
 // A 64 x 64 tile is 16 x 16 micro-tiles of 4 x 4; thread (lr, lc) = (tid & 15, tid >> 4) owns micro-tile rows 4 lr .. 4 lr + 3,
 // columns 4 lc .. 4 lc + 3.  After the register transpose it holds four 32-byte units u[e] = (column quad lc of TRANSPOSED
