@@ -562,6 +562,29 @@ def e2e_variants_leg(env, lib, check, w, steps=3):
                                    "d2h_bytes_per_step": (nx * npair + 2 * n2 + nx) * 8, "matches_device_path": ok_up,
                                    "api": "rb_host_ri_ao2mo_jk_upper (square C; ri3mo[P, a<=b] only: the slabs are symmetric)",
                                    "note": "value counts the flop of the square step (the device still forms the full ri3mo chunk)"}
+            # ... and only mu <= nu of every (symmetric) slab travels up: about half the bytes in both directions
+            try:
+                def sy_step():
+                    check(lib.rb_host_ri_ao2mo_jk_symm(P(c_h), nb, P(ri_h), P(up_h), nb, nx, P(dm_h), P(ct_h), no, P(d_h), P(j_h),
+                                                       P(k_h)), "rb_host_ri_ao2mo_jk_symm")
+                ref_up = up_h.clone(); ref_k = k_h.clone(); ref_j = j_h.clone()
+                up_h.zero_()
+                sy_step()
+                ok_sy = bool(torch.equal(up_h, ref_up)) and bool(torch.equal(k_h, ref_k)) and bool(torch.equal(j_h, ref_j))
+                del ref_up
+                t0 = time.perf_counter()
+                for _ in range(steps):
+                    sy_step()
+                dt = (time.perf_counter() - t0) / steps
+                up_bytes = sum((min(c0 + 32, nb)) * min(32, nb - c0) for c0 in range(0, nb, 32)) * nx * 8
+                out["symmetric_in_upper_out"] = {"ms_per_step": dt * 1e3, "value": flop / dt / 1e9, "unit": UNIT,
+                                                 "h2d_bytes_per_step": up_bytes + (2 * n2 + nb * no) * 8,
+                                                 "d2h_bytes_per_step": (nx * npair + 2 * n2 + nx) * 8,
+                                                 "bit_identical_to_upper_packed": ok_sy,
+                                                 "api": "rb_host_ri_ao2mo_jk_symm (caller guarantees symmetric slabs: mu <= nu up, a <= b down)",
+                                                 "note": "value counts the flop of the square step"}
+            except Exception as exc:  # noqa: BLE001
+                out["symmetric_in_upper_out"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
             del up_h
         except Exception as exc:  # noqa: BLE001
             out["upper_packed"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}

@@ -193,6 +193,12 @@ int rb_host_ri_ao2mo_jk(const double *c_left, int nl, const double *c_right, int
  * are not symmetric the result is still exactly the a <= b entries of rb_host_ri_ao2mo_jk's output. */
 int rb_host_ri_ao2mo_jk_upper(const double *c, int nmo, const double *ri3ao, double *ri3mo_upper, int nb, int nx,
                               const double *dm, const double *ct, int no, double *d, double *j, double *k);
+/* As rb_host_ri_ao2mo_jk_upper, for callers that GUARANTEE symmetric slabs (ri3ao[mu, nu, P] == ri3ao[nu, mu, P], what the reference's
+ * 3-centre integrals are): only the mu <= nu part of every slab is uploaded (pitched 3-D copies of 32-column trapezoids, 52-55 % of the
+ * bytes) and mirrored in HBM, so the pass moves about half the bytes in BOTH directions.  The strict lower triangle of the host slabs is
+ * never read.  ri3mo_upper may be NULL (d_P / J / K only). */
+int rb_host_ri_ao2mo_jk_symm(const double *c, int nmo, const double *ri3ao, double *ri3mo_upper, int nb, int nx,
+                             const double *dm, const double *ct, int no, double *d, double *j, double *k);
 /* axpy family on host buffers (matrix/mod.rs:545-648, ri.rs:345-354, matrixupper.rs:395-420):
  * op 0: c += p*b   1: c = c*a + p*b   2: c *= a   3: c += p   4: c -= p   (unfused mul-then-add, bit-exact) */
 int rb_host_axpy(int op, double *c, const double *p, double a, double b, int64_t n);

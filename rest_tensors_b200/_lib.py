@@ -98,6 +98,7 @@ SIGNATURES = {
     "rb_host_ri_ao2mo_jk": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int, c_vp, c_vp, C.c_int, C.c_int, c_vp, c_vp, C.c_int,
                                       c_vp, c_vp, c_vp]),
     "rb_host_ri_ao2mo_jk_upper": (C.c_int, [c_vp, C.c_int, c_vp, c_vp, C.c_int, C.c_int, c_vp, c_vp, C.c_int, c_vp, c_vp, c_vp]),
+    "rb_host_ri_ao2mo_jk_symm": (C.c_int, [c_vp, C.c_int, c_vp, c_vp, C.c_int, C.c_int, c_vp, c_vp, C.c_int, c_vp, c_vp, c_vp]),
     "rb_host_axpy": (C.c_int, [C.c_int, c_vp, c_vp, C.c_double, C.c_double, c_i64]),
     "rb_host_ri_dp": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, C.c_int]),
     "rb_host_ri_j": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, C.c_int]),

@@ -383,8 +383,36 @@ __global__ void __launch_bounds__(256) rb_ri3mo_pack_pairs_kernel(const double *
     }
 }
 
+// Slabs uploaded as upper trapezoids only (symm_in): every slab of the chunk gets its strict lower triangle from its upper one.
+// 32 x 32 tiles through shared memory, blockIdx.y = slab; both sides coalesced.
+__global__ void __launch_bounds__(256) rb_mirror_upper_slabs_kernel(double *__restrict__ a, i64 n, i64 slab)
+{
+    __shared__ double tile[32][33];
+    i64 p = blockIdx.x;
+    i64 tj = (i64)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
+    while (tj * (tj + 1) / 2 > p) --tj;
+    while ((tj + 1) * (tj + 2) / 2 <= p) ++tj;
+    const i64 ti = p - tj * (tj + 1) / 2; // ti <= tj: source tile rows ti, cols tj
+    double *c = a + (i64)blockIdx.y * slab;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int cc = ty + r * 8;
+        const i64 row = ti * 32 + tx, col = tj * 32 + cc;
+        tile[cc][tx] = (row < n && col < n && row <= col) ? c[row + col * n] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int cc = ty + r * 8;
+        const i64 row = tj * 32 + tx, col = ti * 32 + cc; // transposed position
+        if (row < n && col < n && row > col) c[row + col * n] = tile[tx][cc];
+    }
+}
+
 int host_ri_stream(const double *cl, int nl, const double *cr, int nr, const double *ri3ao, double *out, int nb_, int nx_,
-                   const double *dm, const double *ct, int no, double *d_out, double *j_out, double *k_out, bool upper_out = false)
+                   const double *dm, const double *ct, int no, double *d_out, double *j_out, double *k_out, bool upper_out = false,
+                   bool symm_in = false)
 {
     RB_REQUIRE(nl >= 0 && nr >= 0 && nb_ >= 0 && nx_ >= 0 && no >= 0, "ri stream: negative dimension");
     RB_REQUIRE(!upper_out || (cl == cr && nl == nr), "ri stream: the packed (a <= b) output needs the same C on both sides");
@@ -485,13 +513,32 @@ int host_ri_stream(const double *cl, int nl, const double *cr, int nr, const dou
             h_src = pin_in[s];
         }
         mark(pipe.s_in);
-        if (nb > 0)
+        if (nb > 0 && !symm_in)
             RB_CUDA(cudaMemcpyAsync(d_in[s], h_src, (size_t)(pn * slab_in) * 8, cudaMemcpyHostToDevice, pipe.s_in));
+        if (nb > 0 && symm_in) {
+            // rows 0 .. c0 + cw - 1 of the columns c0 .. c0 + cw - 1 of EVERY slab of the chunk: one pitched 3-D copy per block of
+            // 32 columns (row pitch nb, slice pitch nb^2) -- 52-55 % of the bytes of the full slabs, ~19 copies per chunk at nb = 600
+            const i64 CB = 32;
+            for (i64 c0 = 0; c0 < nb; c0 += CB) {
+                const i64 cw = nb - c0 < CB ? nb - c0 : CB, rows = c0 + cw;
+                cudaMemcpy3DParms q = {};
+                q.srcPtr = make_cudaPitchedPtr((void *)(h_src + c0 * nb), (size_t)nb * 8, (size_t)nb * 8, (size_t)nb);
+                q.dstPtr = make_cudaPitchedPtr((void *)(d_in[s] + c0 * nb), (size_t)nb * 8, (size_t)nb * 8, (size_t)nb);
+                q.extent = make_cudaExtent((size_t)rows * 8, (size_t)cw, (size_t)pn);
+                q.kind = cudaMemcpyHostToDevice;
+                RB_CUDA(cudaMemcpy3DAsync(&q, pipe.s_in));
+            }
+        }
         RB_CUDA(cudaEventRecord(pipe.in_done[s], pipe.s_in));
         mark(pipe.s_in);
         // compute needs the chunk in HBM and the previous D2H out of d_out[s]
         RB_CUDA(cudaStreamWaitEvent(ctx->stream, pipe.in_done[s], 0));
         if (step >= 2) RB_CUDA(cudaStreamWaitEvent(ctx->stream, pipe.out_done[s], 0));
+        if (symm_in && nb > 1) {
+            const i64 nt = rb_cdiv(nb, 32);
+            rb_mirror_upper_slabs_kernel<<<dim3((unsigned)(nt * (nt + 1) / 2), (unsigned)pn), 256, 0, ctx->stream>>>(d_in[s], nb, slab_in);
+            RB_LAUNCHED(ctx);
+        }
         if (do_mo) RB_TRY(rb_ri_ao2mo(ctx, d_cl, nl, d_cr, nr, d_in[s], d_mo[s], nb_, (int)pn, pn));
         const double *d_ship = d_mo[s];
         if (do_mo && upper_out) {
@@ -814,6 +861,12 @@ extern "C" int rb_host_ri_ao2mo_jk_upper(const double *c, int nmo, const double 
                                          const double *dm, const double *ct, int no, double *d, double *j, double *k)
 {
     return host_ri_stream(c, nmo, c, nmo, ri3ao, ri3mo_upper, nb, nx, dm, ct, no, d, j, k, true);
+}
+
+extern "C" int rb_host_ri_ao2mo_jk_symm(const double *c, int nmo, const double *ri3ao, double *ri3mo_upper, int nb, int nx,
+                                        const double *dm, const double *ct, int no, double *d, double *j, double *k)
+{
+    return host_ri_stream(c, nmo, c, nmo, ri3ao, ri3mo_upper, nb, nx, dm, ct, no, d, j, k, true, true);
 }
 
 extern "C" int rb_host_dgemm(char ta, char tb, int m, int n, int k, double alpha, const double *a, int lda,

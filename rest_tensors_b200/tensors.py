@@ -598,17 +598,20 @@ class RIFull:
                                       _ptr(k.data)), "ao2mo_jk")
         return ri3mo, d, j, k
 
-    def ao2mo_jk_upper(self, eigenvector: MatrixFull, dm: MatrixFull, ct: MatrixFull):
+    def ao2mo_jk_upper(self, eigenvector: MatrixFull, dm: MatrixFull, ct: MatrixFull, symmetric_slabs: bool = False):
         """ao2mo_jk shipping only the a <= b part of ri3mo: returns (upper, d, J, K) with upper a float64 array [nx, ns(ns+1)/2],
         upper[P + nx * (b(b+1)/2 + a)] = ri3mo[P, a, b] (MatrixUpper's pair index per P).  Symmetric slabs make ri3mo symmetric in
-        (a, b), so this is the whole tensor at half the device -> host traffic (rb_host_ri_ao2mo_jk_upper)."""
+        (a, b), so this is the whole tensor at half the device -> host traffic (rb_host_ri_ao2mo_jk_upper).  symmetric_slabs=True is
+        the caller's guarantee that self[mu, nu, P] == self[nu, mu, P]: then only mu <= nu is uploaded as well
+        (rb_host_ri_ao2mo_jk_symm; the strict lower triangles are never read)."""
         nb, ns, nx, no = eigenvector.size[0], eigenvector.size[1], self.size[2], ct.size[1]
         upper = np.zeros(nx * (ns * (ns + 1) // 2), dtype=np.float64)
         d = np.zeros(nx, dtype=np.float64)
         j = MatrixFull.new([nb, nb], 0.0)
         k = MatrixFull.new([nb, nb], 0.0)
-        check(lib.rb_host_ri_ao2mo_jk_upper(_ptr(eigenvector.data), ns, _ptr(self.data), _ptr(upper), nb, nx, _ptr(dm.data),
-                                            _ptr(ct.data), no, _ptr(d), _ptr(j.data), _ptr(k.data)), "ao2mo_jk_upper")
+        fn = lib.rb_host_ri_ao2mo_jk_symm if symmetric_slabs else lib.rb_host_ri_ao2mo_jk_upper
+        check(fn(_ptr(eigenvector.data), ns, _ptr(self.data), _ptr(upper), nb, nx, _ptr(dm.data), _ptr(ct.data), no, _ptr(d),
+                 _ptr(j.data), _ptr(k.data)), "ao2mo_jk_upper")
         return upper, d, j, k
 
     # -- slab copies (ri.rs:410-433) --

@@ -150,15 +150,23 @@ impl RIFull {
     }
     /// ao2mo_jk shipping only the a <= b part of ri3mo: upper[P + nx * (b(b+1)/2 + a)] (MatrixUpper's pair index per P); for the
     /// symmetric slabs of an RI tensor that is the whole result at half the device -> host traffic
-    pub fn ao2mo_jk_upper(&self, c: &MatrixFull, dm: &MatrixFull, ct: &MatrixFull) -> (Vec<f64>, Vec<f64>, MatrixFull, MatrixFull) {
+    /// `symmetric_slabs`: the caller guarantees self[mu, nu, P] == self[nu, mu, P]; only mu <= nu is uploaded then
+    pub fn ao2mo_jk_upper(&self, c: &MatrixFull, dm: &MatrixFull, ct: &MatrixFull, symmetric_slabs: bool) -> (Vec<f64>, Vec<f64>, MatrixFull, MatrixFull) {
         let (nb, ns, nx) = (self.size[0], c.size[1], self.size[2]);
         let mut upper = vec![0.0f64; nx * (ns * (ns + 1) / 2)];
         let mut d = vec![0.0f64; nx];
         let (mut j, mut k) = (MatrixFull::new([nb, nb], 0.0), MatrixFull::new([nb, nb], 0.0));
         unsafe {
-            check(rb_host_ri_ao2mo_jk_upper(c.data.as_ptr(), ci(ns), self.data.as_ptr(), upper.as_mut_ptr(), ci(nb), ci(nx),
-                                            dm.data.as_ptr(), ct.data.as_ptr(), ci(ct.size[1]), d.as_mut_ptr(),
-                                            j.data.as_mut_ptr(), k.data.as_mut_ptr()), "ao2mo_jk_upper");
+            let st = if symmetric_slabs {
+                rb_host_ri_ao2mo_jk_symm(c.data.as_ptr(), ci(ns), self.data.as_ptr(), upper.as_mut_ptr(), ci(nb), ci(nx),
+                                         dm.data.as_ptr(), ct.data.as_ptr(), ci(ct.size[1]), d.as_mut_ptr(),
+                                         j.data.as_mut_ptr(), k.data.as_mut_ptr())
+            } else {
+                rb_host_ri_ao2mo_jk_upper(c.data.as_ptr(), ci(ns), self.data.as_ptr(), upper.as_mut_ptr(), ci(nb), ci(nx),
+                                          dm.data.as_ptr(), ct.data.as_ptr(), ci(ct.size[1]), d.as_mut_ptr(),
+                                          j.data.as_mut_ptr(), k.data.as_mut_ptr())
+            };
+            check(st, "ao2mo_jk_upper");
         }
         (upper, d, j, k)
     }

@@ -730,6 +730,33 @@ def test_fused_streaming_step_upper_output(rt, oracle_blas, nb, ns, nx, no, pinn
     assert_close_1e10(up.ravel(order="F"), ref_up.ravel(order="F"), "upper ao2mo vs oracle")
 
 
+@pytest.mark.parametrize("nb,ns,nx,no,pinned", [(40, 40, 600, 6, False), (33, 21, 301, 5, False), (64, 64, 520, 9, True), (100, 100, 40, 20, True),
+                                                    (1, 1, 5, 1, False)])
+def test_fused_streaming_step_symmetric_slabs(rt, oracle_blas, nb, ns, nx, no, pinned):
+    """rb_host_ri_ao2mo_jk_symm uploads only mu <= nu of every slab (32-column trapezoids, pitched 3-D copies) and mirrors on the device:
+    for symmetric slabs every output is bit for bit what the full upload gives, and the strict lower triangle of the host tensor is never
+    read -- it is filled with NaN here."""
+    import ctypes as C
+    from rest_tensors_b200._lib import lib, check
+    ri, c_full, dm, ct = _inputs(oracle_blas, nb, nx, no, True)
+    c = np.ascontiguousarray(c_full[: nb * ns])
+    args = (rt.MatrixFull.from_vec([nb, ns], c), rt.MatrixFull.from_vec([nb, nb], dm), rt.MatrixFull.from_vec([nb, no], ct))
+    upper, d, j, k = rt.RIFull.from_vec([nb, nb, nx], ri).ao2mo_jk_upper(*args)
+    holed = ri.copy().reshape((nb, nb, nx), order="F")
+    holed[np.tril_indices(nb, -1)] = np.nan
+    holed = np.ascontiguousarray(holed.ravel(order="F"))
+    if pinned:
+        check(lib.rb_host_register(C.c_void_p(holed.ctypes.data), holed.nbytes), "rb_host_register")
+    try:
+        upper2, d2, j2, k2 = rt.RIFull.from_vec([nb, nb, nx], holed).ao2mo_jk_upper(*args, symmetric_slabs=True)
+    finally:
+        if pinned:
+            check(lib.rb_host_unregister(C.c_void_p(holed.ctypes.data)), "rb_host_unregister")
+    assert np.array_equal(upper2, upper) and np.array_equal(d2, d)
+    assert np.array_equal(j2.data, j.data) and np.array_equal(k2.data, k.data)
+    assert_close_1e10(k2.data, oracle_blas.ri_k(ri, ct, nb, no, nx), "K from half-uploaded slabs")
+
+
 # ---------------------------------------------------------------- special_dgemm_f_01 ----
 def test_special_dgemm_f_01(rt, oracle_blas):
     X, Y, Z = 12, 7, 10
