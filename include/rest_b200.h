@@ -68,8 +68,9 @@ int rb_ctx_set_gemm_path(rb_ctx *ctx, int path);
  * refresh the CONTENTS of the input buffers between replays, e.g. with rb_memcpy_h2d, which can itself be part of the recording
  * when the host buffer is pinned).  Rules: the context must run on a non-default stream (rb_ctx_use_own_stream / rb_ctx_set_stream);
  * run the sequence once before recording (workspaces get their size on first use and cannot grow while recording:
- * RB_ERR_UNSUPPORTED); calls that need the host inside (eigen-solvers, collectives, the peer pipelines, probes, rb_ctx_sync) are
- * refused with RB_ERR_UNSUPPORTED while a recording is open.  A recording stays valid until rb_graph_free, also across later,
+ * RB_ERR_UNSUPPORTED); calls that need the host inside (eigen-solvers, the peer pipelines, probes, rb_ctx_sync) are refused with
+ * RB_ERR_UNSUPPORTED while a recording is open.  The NCCL collectives (rb_allreduce_sum, rb_ri_j/k_allreduce, rb_allgather_shards)
+ * CAN be recorded: every rank must record, and later replay, the same sequence.  A recording stays valid until rb_graph_free, also across later,
  * larger calls on the same context. */
 int rb_graph_begin(rb_ctx *ctx);
 int rb_graph_end(rb_ctx *ctx, void **graph_out);

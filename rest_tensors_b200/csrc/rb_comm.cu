@@ -178,11 +178,11 @@ extern "C" int rb_comm_group_end(void)
 }
 
 // In-place sum over the ranks of the context's communicator, asynchronous on the context's stream.  A context without a
-// communicator is a world of one: nothing to do.
+// communicator is a world of one: nothing to do.  Recordable (rb_graph_begin): NCCL captures its collectives into the graph; every
+// rank must then record and replay the same sequence.
 extern "C" int rb_allreduce_sum(rb_ctx *ctx, double *buf, int64_t n)
 {
     RB_REQUIRE(ctx, "rb_allreduce_sum: ctx is NULL");
-    RB_NO_CAPTURE(ctx, "rb_allreduce_sum");
     RB_REQUIRE(n >= 0, "rb_allreduce_sum: negative length");
     if (!ctx->comm || ctx->comm_world == 1 || n == 0) return RB_OK;
     RB_REQUIRE(buf, "rb_allreduce_sum: buf is NULL");
@@ -196,7 +196,6 @@ extern "C" int rb_allreduce_sum(rb_ctx *ctx, double *buf, int64_t n)
 extern "C" int rb_allgather_shards(rb_ctx *ctx, const double *local, double *full, int64_t naux)
 {
     RB_REQUIRE(ctx && naux >= 0, "rb_allgather_shards: bad arguments");
-    RB_NO_CAPTURE(ctx, "rb_allgather_shards");
     if (naux == 0) return RB_OK;
     RB_REQUIRE(full, "rb_allgather_shards: full is NULL");
     RB_CUDA(cudaSetDevice(ctx->device));

@@ -257,6 +257,26 @@ struct RIFull {
                                   mo.data.data(), (int)size[0], (int)size[2]), "ao2mo_rect");
         return mo;
     }
+    // One streaming pass: ao2mo + d_P + J + K with every P-chunk uploaded once (not in the reference, which makes the calls one by
+    // one).  `upper`: ri3mo comes back as its a <= b pairs, upper[P + nx * (b (b + 1) / 2 + a)]; `symmetric_slabs`: the caller
+    // guarantees (*this)[mu, nu, P] == (*this)[nu, mu, P] and only mu <= nu is uploaded.
+    struct StepResult { std::vector<double> ri3mo; std::vector<double> d; MatrixFull j, k; };
+    StepResult ao2mo_jk(const MatrixFull &c, const MatrixFull &dm, const MatrixFull &ct, bool upper = false,
+                        bool symmetric_slabs = false) const
+    {
+        const int nb = (int)c.size[0], ns = (int)c.size[1], nx = (int)size[2], no = (int)ct.size[1];
+        StepResult r{std::vector<double>((size_t)nx * (upper ? (size_t)ns * (ns + 1) / 2 : (size_t)ns * ns), 0.0),
+                     std::vector<double>((size_t)nx, 0.0), MatrixFull::make({(size_t)nb, (size_t)nb}, 0.0),
+                     MatrixFull::make({(size_t)nb, (size_t)nb}, 0.0)};
+        if (!upper)
+            rb_check(rb_host_ri_ao2mo_jk(c.data.data(), ns, c.data.data(), ns, data.data(), r.ri3mo.data(), nb, nx, dm.data.data(),
+                                         ct.data.data(), no, r.d.data(), r.j.data.data(), r.k.data.data()), "ao2mo_jk");
+        else
+            rb_check((symmetric_slabs ? rb_host_ri_ao2mo_jk_symm : rb_host_ri_ao2mo_jk_upper)(
+                         c.data.data(), ns, data.data(), r.ri3mo.data(), nb, nx, dm.data.data(), ct.data.data(), no, r.d.data(),
+                         r.j.data.data(), r.k.data.data()), "ao2mo_jk(upper)");
+        return r;
+    }
     // ri.rs:356-408
     RIFull ao2mo(const MatrixFull &eigenvector) const { return ao2mo_v02(eigenvector); }
     RIFull ao2mo_v02(const MatrixFull &eigenvector) const

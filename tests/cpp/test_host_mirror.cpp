@@ -154,6 +154,21 @@ int main()
                 for (int p = 0; p < nx; ++p)
                     same = same && std::fabs(ov.data[p + (size_t)nx * (a + (size_t)no * b)] - sq.data[p + (size_t)nx * (a + (size_t)nb * (b + no))]) <= 1e-12;
         CHECK(same, "ao2mo_rect == occ-vir block of the square transform");
+        {   // streaming pass: full, upper pairs, upper pairs from half-uploaded symmetric slabs
+            std::vector<double> sym(ri.data);
+            for (int p = 0; p < nx; ++p) for (int j = 0; j < nb; ++j) for (int i = j + 1; i < nb; ++i)
+                sym[i + (size_t)nb * (j + (size_t)nb * p)] = sym[j + (size_t)nb * (i + (size_t)nb * p)];
+            auto rs = RIFull::from_vec({(size_t)nb, (size_t)nb, (size_t)nx}, sym);
+            auto dmat = MatrixFull::from_vec({(size_t)nb, (size_t)nb}, fill((size_t)nb * nb, 34, 0.1));
+            auto full = rs.ao2mo_jk(c, dmat, cl), up = rs.ao2mo_jk(c, dmat, cl, true), sy = rs.ao2mo_jk(c, dmat, cl, true, true);
+            bool okp = up.ri3mo.size() == (size_t)nx * nb * (nb + 1) / 2;
+            for (int b = 0; b < nb && okp; ++b) for (int a = 0; a <= b && okp; ++a) for (int p = 0; p < nx; ++p)
+                okp = okp && up.ri3mo[p + (size_t)nx * ((size_t)b * (b + 1) / 2 + a)] == full.ri3mo[p + (size_t)nx * (a + (size_t)nb * b)];
+            CHECK(okp, "ao2mo_jk(upper) == a <= b pairs of the full pass");
+            CHECK(sy.ri3mo == up.ri3mo && sy.k.data == up.k.data && sy.j.data == up.j.data && sy.d == up.d,
+                  "ao2mo_jk(upper, symmetric_slabs) == ao2mo_jk(upper) bit for bit");
+            CHECK(rel_err(full.ri3mo, rs.ao2mo(c).data) < 1e-13, "ao2mo_jk ri3mo == ao2mo");
+        }
         auto prod = _dgemm_full_new(c, 'T', c, 'N', 1.0, 0.0);
         auto dd = c.transpose().ddot(c);
         CHECK(dd.has_value() && rel_err(dd->data, prod.data) < 1e-13, "ddot == _dgemm_full_new");

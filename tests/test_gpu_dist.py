@@ -79,6 +79,28 @@ def _worker(rank, world, port, nb, naux, no, ret):
         o.special_dgemm_f_01(t_ref, [nb, nb, naux], (0, nb), 0, (0, naux), bmat, [naux, naux], (0, naux), (0, naux), 1.0, 0.0)
         torch.cuda.synchronize()
         errs.append(err(sh.data.cpu().numpy(), t_ref[sh.p_lo * nb * nb: sh.p_hi * nb * nb]))
+        # one launch per SCF iteration at N > 1: d_P + J + K with both all-reduces recorded into a CUDA graph on every rank
+        side = torch.cuda.Stream()
+        torch.cuda.synchronize()
+        with torch.cuda.stream(side):
+            ctx.bind_stream()
+            dmd, ctd = dev(dm), dev(ct)
+            sh2 = ShardedRI(ctx, nb, naux, rank, world).fill_synthetic()      # sh.data was transformed above
+            dg, jg, kg = ctx.empty(sh2.nx), ctx.empty(nb * nb), ctx.empty(nb * nb)
+
+            def iteration():
+                sh2.dp(dmd, out=dg); sh2.j(dg, out=jg); sh2.k(ctd, no, out=kg)
+            iteration(); side.synchronize()
+            want_j, want_k = jg.clone(), kg.clone()
+            assert torch.equal(want_j, j) and torch.equal(want_k, k)
+            with ctx.record() as rec:
+                iteration()
+            for _ in range(3):
+                jg.zero_(); kg.zero_()
+                rec.graph.launch(); side.synchronize()
+                assert torch.equal(jg, want_j) and torch.equal(kg, want_k), "graph replay with all-reduces differs"
+            rec.graph.close()
+        ctx.bind_stream()
         ret.put((rank, max(errs)))
         dist.barrier()
     finally:

@@ -50,7 +50,8 @@ class Step:
 def side():
     """a fresh context on a non-default stream (the legacy default stream cannot be captured)"""
     from rest_tensors_b200.device import Context
-    s = torch.cuda.Stream()
+    torch.cuda.set_device(0)              # earlier multi-GPU tests may have left another device current
+    s = torch.cuda.Stream(device=0)
     with torch.cuda.stream(s):
         ctx = Context(0)
         yield ctx
@@ -135,6 +136,7 @@ def test_what_cannot_be_recorded_is_refused_loudly(side):
 
 def test_default_stream_is_refused(ctx):
     from rest_tensors_b200._lib import RestB200Error
+    torch.cuda.set_device(0)
     ctx.bind_stream()
     if torch.cuda.current_stream().cuda_stream != 0:
         pytest.skip("torch's current stream is not the default stream here")
