@@ -427,7 +427,9 @@ int host_ri_stream(const double *cl, int nl, const double *cr, int nr, const dou
     rb_ctx *ctx = op.ctx;
     // chunk of P slabs staged per pipeline step: large enough for full 128-row MMA tiles along P, small enough
     // to overlap the PCIe transfers with compute
-    i64 pc = 256;
+    // 256 slabs per chunk for long tensors; short ones (configs A / B: 400 / 720 slabs) get 96 so that the pipeline still has 4-8 chunks to
+    // overlap (measured, tools/e2e_small_probe.py: config A 1.41 -> 1.20 ms, config B 12.0 -> 10.1 ms per pass)
+    i64 pc = nx > 1024 ? 256 : 96;
     if (const char *e = getenv("REST_B200_PC")) { i64 v = atoll(e); if (v >= 8) pc = v; }
     // (Measured on this pool, profiles/r01_e2e_variants.md: letting GEMM 2 store straight into mapped pinned host memory
     //  is slower -- 223 ms vs 130 ms per pass at config C -- than staging in HBM and draining with 2-D copies.)
