@@ -248,6 +248,14 @@ int rb_ri_ao2mo(rb_ctx *ctx, const double *c_left, int nl, const double *c_right
 int rb_ri_dp(rb_ctx *ctx, const double *ri3ao, const double *dm, double *d, int nb, int nx);
 /* j[mu,nu] = sum_P ri3ao[mu,nu,P]*d[P]  (this rank's partial sum; all-reduce across ranks) */
 int rb_ri_j(rb_ctx *ctx, const double *ri3ao, const double *d, double *j, int nb, int nx);
+/* d_P and J from ONE read of ri3ao (the reference makes two passes, ri.rs + _dgemv 'T' / 'N'): one persistent cooperative kernel, every
+ * CTA owns a fixed ij range in all slabs (its D and J entries stay in registers), the slabs stream through a shared-memory ring of 1-D
+ * bulk copies, the per-slab dot products are combined across CTAs in a fixed order (deterministic, no FP64 atomics) and J is updated
+ * from the copy still in shared memory.  Same results as rb_ri_dp followed by rb_ri_j up to the summation order inside d_P (1e-15).
+ * The single-pass kernel is OPT-IN (REST_B200_DPJ_FUSED=1): it halves the HBM traffic but is latency-bound and measured slower than the
+ * two GEMV passes (2.0 vs 1.46 ms at config C), so by default -- and for shapes its ring cannot hold (nb > ~1100) or odd nb -- this call
+ * is rb_ri_dp followed by rb_ri_j. */
+int rb_ri_dp_j(rb_ctx *ctx, const double *ri3ao, const double *dm, double *d, double *j, int nb, int nx);
 /* k = sum_P (A_P ct)(A_P ct)^T, ct [nb,no]; full symmetric nb x nb (both triangles written); partial per rank */
 int rb_ri_k(rb_ctx *ctx, const double *ri3ao, const double *ct, int no, double *k, int nb, int nx);
 /* in-place slab x matrix of restmatr.f90:111-154 on device buffers */

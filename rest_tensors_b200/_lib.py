@@ -118,6 +118,7 @@ SIGNATURES = {
     "rb_ri_ao2mo": (C.c_int, [c_vp, c_vp, C.c_int, c_vp, C.c_int, c_vp, c_vp, C.c_int, C.c_int, c_i64]),
     "rb_ri_dp": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int]),
     "rb_ri_j": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int]),
+    "rb_ri_dp_j": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int]),
     "rb_ri_k": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, c_vp, C.c_int, C.c_int]),
     "rb_ri_iajb": (C.c_int, [c_vp, C.c_int, c_vp, c_i64] + [C.c_int] * 6 + [c_vp, c_i64] + [C.c_int] * 6
                    + [C.c_double, c_vp, c_i64]),

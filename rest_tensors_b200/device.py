@@ -219,6 +219,10 @@ class Context:
     def ri_j(self, ri3ao, d, j, nb, nx) -> None:
         check(lib.rb_ri_j(self.h, _p(ri3ao), _p(d), _p(j), nb, nx), "rb_ri_j")
 
+    def ri_dp_j(self, ri3ao, dm, d, j, nb, nx) -> None:
+        """d_P and J from one read of ri3ao (rb_ri_dp_j: persistent cooperative kernel; falls back to the two GEMVs where it cannot run)"""
+        check(lib.rb_ri_dp_j(self.h, _p(ri3ao), _p(dm), _p(d), _p(j), nb, nx), "rb_ri_dp_j")
+
     def ri_k(self, ri3ao, ct, no, k, nb, nx) -> None:
         check(lib.rb_ri_k(self.h, _p(ri3ao), _p(ct), no, _p(k), nb, nx), "rb_ri_k")
 
@@ -368,6 +372,18 @@ class ShardedRI:
         else:
             self.ctx.ri_j(self.data, d_local, out, self.nb, self.nx)
         return out
+
+    def dp_j(self, dm: torch.Tensor, out_d: Optional[torch.Tensor] = None, out_j: Optional[torch.Tensor] = None,
+             reduce: bool = True):
+        """(d[P_lo..P_hi), J) from ONE pass over the shard; J is all-reduced over the ranks when reduce (rb_allreduce_sum)"""
+        if out_d is None:
+            out_d = self.ctx.empty(self.nx)
+        if out_j is None:
+            out_j = self.ctx.empty(self.nb * self.nb)
+        self.ctx.ri_dp_j(self.data, dm, out_d, out_j, self.nb, self.nx)
+        if reduce and self.world > 1:
+            self.ctx.allreduce_sum(out_j)
+        return out_d, out_j
 
     def k(self, ct: torch.Tensor, no: int, out: Optional[torch.Tensor] = None, reduce: bool = True) -> torch.Tensor:
         if out is None:
