@@ -608,7 +608,38 @@ def e2e_variants_leg(env, lib, check, w, steps=3):
         dt = (time.perf_counter() - t0) / 10
         f = flops(nb, nx, no, True)
         flop = f["dp"] + f["j"] + f["k"]
-        out["scf_resident"] = {"ms_per_step": dt * 1e3, "value": flop / dt / 1e9, "unit": UNIT,
+        # the same iteration with d_P and J from ONE read of the shard (rb_ri_dp_j: persistent cooperative kernel)
+        def scf_step_1pass():
+            check(lib.rb_memcpy_h2d(ctx.h, P(w.dm), P(dm_h), C.c_int64(n2 * 8)), "rb_memcpy_h2d")
+            check(lib.rb_memcpy_h2d(ctx.h, P(w.ct), P(ct_h), C.c_int64(nb * no * 8)), "rb_memcpy_h2d")
+            w.sh.dp_j(w.dm, out_d=w.d, out_j=w.j, reduce=True)
+            w.sh.k(w.ct, no, out=w.k, reduce=True)
+            check(lib.rb_memcpy_d2h(ctx.h, P(j_h), P(w.j), C.c_int64(n2 * 8)), "rb_memcpy_d2h")
+            check(lib.rb_memcpy_d2h(ctx.h, P(k_h), P(w.k), C.c_int64(n2 * 8)), "rb_memcpy_d2h")
+            ctx.sync()
+        one_pass = None
+        try:
+            j_two = j_h.clone()
+            scf_step_1pass()
+            rel = float((j_h - j_two).abs().max() / j_two.abs().max())
+            t1 = time.perf_counter()
+            for _ in range(10):
+                scf_step_1pass()
+            dt1 = (time.perf_counter() - t1) / 10
+            ev0, ev1, ev2 = env.ev(), env.ev(), env.ev()
+            ev0.record()
+            for _ in range(5):
+                w.sh.dp(w.dm, out=w.d); w.sh.j(w.d, out=w.j, reduce=False)
+            ev1.record()
+            for _ in range(5):
+                w.sh.dp_j(w.dm, out_d=w.d, out_j=w.j, reduce=False)
+            ev2.record(); torch.cuda.synchronize()
+            one_pass = {"ms_per_step": dt1 * 1e3, "value": flop / dt1 / 1e9, "j_rel_diff_vs_two_passes": rel,
+                        "dp_plus_j_two_passes_ms": ev0.elapsed_time(ev1) / 5, "dp_j_single_pass_ms": ev1.elapsed_time(ev2) / 5,
+                        "api": "rb_ri_dp_j (d_P and J from one read of the shard) + rb_ri_k"}
+        except Exception as exc:  # noqa: BLE001
+            one_pass = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        out["scf_resident"] = {"ms_per_step": dt * 1e3, "value": flop / dt / 1e9, "unit": UNIT, "single_pass_dp_j": one_pass,
                                "h2d_bytes_per_step": (n2 + nb * no) * 8, "d2h_bytes_per_step": 2 * n2 * 8,
                                "api": "rb_memcpy_h2d(D, C~) + rb_ri_dp / rb_ri_j / rb_ri_k on the resident shard + rb_memcpy_d2h(J, K)",
                                "note": "d_P + J + K only (the per-iteration work of an SCF loop); ri3ao uploaded once, outside"}

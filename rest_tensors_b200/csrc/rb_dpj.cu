@@ -17,14 +17,20 @@
 //     hides behind the dot products; they are added in CTA order -> d_P (bitwise the same in every CTA), then
 //     J[ij] += d_P * A[ij,P] from the copy that is STILL in shared memory, and the ring slot goes back to the loader.
 // HBM traffic: nb^2 * nx * 8 bytes once (plus kilobytes of partials) instead of twice.  Deterministic: fixed thread / warp / CTA order.
-// Shapes the ring cannot hold (nb > ~1100), odd nb^2 alignment or tiny problems fall back to the two GEMV kernels.
+// 16 compute warps + 2 exchange warps per CTA: the exchange warps publish the CTA's partial dots and gather everybody's, one block ahead
+// of the compute warps, so the grid-wide exchange is off the critical path.  What bounds the kernel is shared memory: loads in flight
+// (2.4 us of latency x 44 GB/s per SM = 106 KB) + the block being worked on + the blocks waiting for their d_P have to fit 200 KB, which
+// leaves two blocks in flight -> 4.1 TB/s of the single read = 1.2-1.3x the two passes for nb = 600-900.
+// Shapes the ring cannot hold (nb > ~1100), odd nb^2 alignment, short runs (nb < ~550) or small tensors use the two GEMV kernels.
 #include "rb_common.cuh"
 
 namespace {
 
-constexpr int DPJ_THREADS = 256;
-constexpr int DPJ_WARPS = DPJ_THREADS / 32;
-constexpr int DPJ_MAX_S = 32;
+constexpr int DPJ_THREADS = 512;
+constexpr int DPJ_WARPS = DPJ_THREADS / 32;   // compute warps
+constexpr int DPJ_XWARPS = 2;                  // exchange warps (publish the CTA's partial dots, gather everybody's -> d_P)
+constexpr int DPJ_BLOCK = DPJ_THREADS + 32 * DPJ_XWARPS;
+constexpr int DPJ_MAX_S = 8;
 constexpr int DPJ_MAX_RING = 10;
 constexpr i64 DPJ_RING_BYTES = 200 * 1024;
 
@@ -47,6 +53,12 @@ __device__ __forceinline__ uint32_t dpj_smem_u32(const void *p) { return (uint32
 __device__ __forceinline__ void dpj_cp16(uint32_t dst, const void *src)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ double2 dpj_lds128(uint32_t addr)
+{
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
 }
 __device__ __forceinline__ void dpj_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void dpj_wait_pending(int n) // wait until at most n of this thread's newest groups are still in flight
@@ -80,170 +92,215 @@ __device__ __forceinline__ double dpj_warp_sum(double v) // fixed butterfly: eve
     return v;
 }
 
-// K = double2 per thread that cover the CTA's run (L <= K * 512)
-template <int K>
-__global__ void __launch_bounds__(DPJ_THREADS, 1) rb_ri_dp_j_kernel(const DpjParams p)
+// K = 16-byte units per thread that cover the CTA's run (L <= K * 2 * DPJ_THREADS), ST = slabs per block (compile time: the ST dot
+// products and their butterflies are interleaved, not chained).
+template <int K, int ST>
+__global__ void __launch_bounds__(DPJ_BLOCK, 1) rb_ri_dp_j_kernel(const DpjParams p)
 {
     extern __shared__ __align__(128) unsigned char dpj_smem[];
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-    const i64 G = gridDim.x, cta = blockIdx.x;
-    const i64 e0 = cta * p.L;
+    const int Gi = (int)gridDim.x, cta = (int)blockIdx.x;
+    const i64 e0 = (i64)cta * p.L;
     const int len = (int)(p.slab - e0 < p.L ? (p.slab - e0 > 0 ? p.slab - e0 : 0) : p.L); // multiple of 4 (slab and L are)
-    const bool has = len > 0;
     double *ring = reinterpret_cast<double *>(dpj_smem);
-    const i64 ring_elems = (i64)p.R * p.S * p.L;
-    double *red = ring + ring_elems;                                                    // [S][DPJ_WARPS]
-    double *dsm = red + DPJ_MAX_S * DPJ_WARPS;                                          // [S]
+    const int R = p.R, LAG = p.LAG, nblocks = (int)p.nblocks;
+    const uint32_t run_bytes = (uint32_t)p.L * 8u, block_bytes = run_bytes * ST;
+    double *red = ring + (size_t)R * ST * p.L;       // [2][ST][DPJ_WARPS]  (by iteration parity)
+    double *dsm = red + 2 * ST * DPJ_WARPS;          // [2][ST]             (by block parity)
+    const uint32_t ring_s = dpj_smem_u32(ring);
 
-    // Every thread copies exactly the 16-byte units it reads back itself (unit t + k * 256 of each run), so the ring needs no barrier of
-    // its own: a thread waits for its own commit groups.  One group per block, committed by every thread whether or not it copied.
-    auto issue = [&](int b, int slot) {
-        const int s_n = (int)(p.nx - (i64)b * p.S < p.S ? p.nx - (i64)b * p.S : p.S);
-        for (int s = 0; s < s_n; ++s) {
-            const double *src = p.a + ((i64)b * p.S + s) * p.slab + e0;
-            const uint32_t dst = dpj_smem_u32(ring + (size_t)(slot * p.S + s) * p.L);
+    // the ring starts as zeros: slabs past the end of the last block are read (with weight zero) like any other
+    for (uint32_t o = (uint32_t)t * 16u; o < (uint32_t)R * block_bytes; o += DPJ_BLOCK * 16u)
+        *reinterpret_cast<double2 *>(dpj_smem + o) = make_double2(0.0, 0.0);
+    __syncthreads();
+
+    constexpr int GV = 5; // partials per lane: up to 160 CTAs
+    if (warp >= DPJ_WARPS) {
+        // ===================== exchange warps: off the compute warps' critical path =====================
+        // iteration `it`: (a) when the compute warps have left their partial dots of block `it` in red[it & 1] (named barrier 1), add
+        // them over the warps and publish the CTA's value; (b) gather block g = it - LAG + 1 from all CTAs -> dsm[g & 1], which the
+        // compute warps use in the NEXT iteration.  The gather's loads are issued first, so their L2 round trip overlaps (a).
+        const int xw = warp - DPJ_WARPS;
+        double gv[GV];
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const int q = 2 * (t + k * DPJ_THREADS);
-                if (q < len) dpj_cp16(dst + (uint32_t)q * 8u, src + q);
+        for (int i = 0; i < GV; ++i) gv[i] = 0.0;
+        for (int it = 0; it < nblocks + LAG; ++it) {
+            const int g = it - LAG + 1;
+            const bool g_ok = g >= 0 && g < nblocks;
+            const int s_ng = g_ok ? (int)(p.nx - (i64)g * ST < ST ? p.nx - (i64)g * ST : ST) : 0;
+            if (p.debug != 1 && xw < s_ng) {
+                const double *row = p.partial + (size_t)(g * ST + xw) * Gi;
+#pragma unroll
+                for (int i = 0; i < GV; ++i) gv[i] = (lane + 32 * i < Gi) ? dpj_ld_gpu(row + lane + 32 * i) : 0.0;
             }
+            if (it < nblocks) {
+                asm volatile("bar.sync 1, %0;" ::"n"(DPJ_BLOCK) : "memory");
+                const int s_n = (int)(p.nx - (i64)it * ST < ST ? p.nx - (i64)it * ST : ST);
+                for (int s = xw; s < s_n; s += DPJ_XWARPS) {
+                    double v = lane < DPJ_WARPS ? red[((it & 1) * ST + s) * DPJ_WARPS + lane] : 0.0;
+                    v = dpj_warp_sum(v); // fixed butterfly over the 16 compute warps
+                    if (lane == 0) dpj_st_gpu(p.partial + (size_t)(it * ST + s) * Gi + cta, v);
+                }
+            }
+            for (int s = xw; s < ST; s += DPJ_XWARPS) {
+                double v = 0.0; // slabs past the end of the last block get weight zero
+                if (s < s_ng) {
+                    if (p.debug == 1) v = 1.0;
+                    else {
+                        const double *row = p.partial + (size_t)(g * ST + s) * Gi;
+                        if (s != xw) {
+#pragma unroll
+                            for (int i = 0; i < GV; ++i) gv[i] = (lane + 32 * i < Gi) ? dpj_ld_gpu(row + lane + 32 * i) : 0.0;
+                        }
+                        const long long t0 = clock64();
+                        for (;;) { // a sentinel = that CTA has not published yet
+                            bool missing = false;
+#pragma unroll
+                            for (int i = 0; i < GV; ++i)
+                                if (__double_as_longlong(gv[i]) == DPJ_SENTINEL) { gv[i] = dpj_ld_gpu(row + lane + 32 * i); missing = true; }
+                            if (!__any_sync(0xffffffffu, missing)) break;
+                            if (clock64() - t0 > 8000000000LL) __trap(); // a lost CTA must not hang the device: fail loudly instead
+                        }
+#pragma unroll
+                        for (int i = 0; i < GV; ++i) v += gv[i]; // lane: CTAs lane, lane + 32, ... in order; then the fixed butterfly
+                        v = dpj_warp_sum(v);
+                        if (lane == 0 && cta == 0) p.d[g * ST + s] = v;
+                    }
+                }
+                if (g_ok && lane == 0) dsm[(g & 1) * ST + s] = v;
+            }
+            asm volatile("bar.sync 0;" ::: "memory");
         }
-        dpj_commit();
-    };
-    for (int b = 0; b < p.R; ++b) { // prologue: R groups (empty ones past the end keep the group arithmetic uniform)
-        if (b < (int)p.nblocks) issue(b, b);
-        else dpj_commit();
+        return;
     }
 
+    // ===================== compute warps =====================
+    // Per-thread geometry: unit k of this thread is doubles [q_k, q_k + 2) of the run.  Units past the end of the run alias the thread's
+    // first unit with weight zero, so the loops below carry no predicates; a thread without any unit sits the arithmetic out.
+    const bool tv = 2 * t < len;
+    uint32_t off[K];
+    bool ok[K];
     double2 dreg[K], jreg[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const int q = 2 * (t + k * DPJ_THREADS);
-        dreg[k] = (q < len) ? *reinterpret_cast<const double2 *>(p.dm + e0 + q) : make_double2(0.0, 0.0);
+        ok[k] = q < len;
+        off[k] = (uint32_t)(ok[k] ? q : 2 * t) * 8u;
+        dreg[k] = ok[k] ? *reinterpret_cast<const double2 *>(p.dm + e0 + q) : make_double2(0.0, 0.0);
         jreg[k] = make_double2(0.0, 0.0);
     }
 
-    constexpr int GV = 8; // partials per lane held in flight: up to 256 CTAs
-    // loop state kept incrementally (no 64-bit divisions in the loop): ring slot / barrier parity of stage 1, ring slot of stage 2,
-    // slabs left at the start of the block of each stage
-    const int S = p.S, R = p.R, nblocks = (int)p.nblocks, LAG = p.LAG, Gi = (int)G;
-    int slot1 = 0, slot2 = 0, left1 = (int)p.nx, left2 = (int)p.nx;
-    double gv[GV]; // this warp's share of the partials of the block stage 2 handles NEXT iteration (in flight across one iteration)
+    // Every thread copies exactly the 16-byte units it reads back itself, so the ring needs no barrier of its own: a thread waits for
+    // its own commit groups.  One group per block, committed by every thread whether or not it copied.
+    const double *src_next = p.a + e0; // first slab of the next block to be issued
+    int left_issue = (int)p.nx;
+    auto issue = [&](int slot) {
+        const uint32_t dst = ring_s + (uint32_t)slot * block_bytes;
 #pragma unroll
-    for (int i = 0; i < GV; ++i) gv[i] = 0.0;
+        for (int s = 0; s < ST; ++s) {
+            if (s < left_issue) {
+#pragma unroll
+                for (int k = 0; k < K; ++k)
+                    if (ok[k]) dpj_cp16(dst + s * run_bytes + off[k], src_next + (i64)s * p.slab + (off[k] >> 3));
+            }
+        }
+        dpj_commit();
+        src_next += (i64)ST * p.slab;
+        left_issue -= ST;
+    };
+    for (int b = 0; b < R; ++b) { // prologue: R groups (empty ones past the end keep the group arithmetic uniform)
+        if (b < nblocks) issue(b);
+        else dpj_commit();
+    }
+
+    int slot1 = 0, slot2 = 0;
     for (int it = 0; it < nblocks + LAG; ++it) {
         const int bb = it - LAG;
-        const int s_n2 = bb >= 0 ? (left2 < S ? left2 : S) : 0;
-        // ---- stage 2, first half: d_P of block bb from the partials.  Warp w gathers slabs w, w + 8, ...; the loads of the first one
-        //      were issued an iteration ago, so the L2 round trip is normally over (a sentinel = not published yet: poll).
-        for (int s = warp; s < s_n2; s += DPJ_WARPS) {
-            if (p.debug == 1) { if (lane == 0) { dsm[s] = 1.0; if (cta == 0) p.d[bb * S + s] = 1.0; } continue; }
-            const double *row = p.partial + (size_t)(bb * S + s) * Gi;
-            if (s != warp) {
-#pragma unroll
-                for (int i = 0; i < GV; ++i) gv[i] = (lane + 32 * i < Gi) ? dpj_ld_gpu(row + lane + 32 * i) : 0.0;
-            }
-            const long long t0 = clock64();
-            for (;;) {
-                bool missing = false;
-#pragma unroll
-                for (int i = 0; i < GV; ++i)
-                    if (__double_as_longlong(gv[i]) == DPJ_SENTINEL) { gv[i] = dpj_ld_gpu(row + lane + 32 * i); missing = true; }
-                if (!__any_sync(0xffffffffu, missing)) break;
-                if (clock64() - t0 > 8000000000LL) __trap(); // a lost CTA must not hang the device: fail loudly instead
-            }
-            double v = 0.0;
-#pragma unroll
-            for (int i = 0; i < GV; ++i) v += gv[i]; // lane: CTAs lane, lane + 32, ... in order; then the fixed butterfly
-            v = dpj_warp_sum(v);
-            if (lane == 0) {
-                dsm[s] = v;
-                if (cta == 0) p.d[bb * S + s] = v;
-            }
-        }
-        // ... and ask L2 for the partials of block bb + 1 now; they are looked at in the next iteration
-        if (p.debug != 1 && bb + 1 >= 0 && bb + 1 < nblocks && warp < (left2 - s_n2 < S ? left2 - s_n2 : S)) {
-            const double *row = p.partial + (size_t)((bb + 1) * S + warp) * Gi;
-#pragma unroll
-            for (int i = 0; i < GV; ++i) gv[i] = (lane + 32 * i < Gi) ? dpj_ld_gpu(row + lane + 32 * i) : 0.0;
-        }
-        int slot_a = 0, s_n = 0;
-        if (it < nblocks) { // ---- stage 1: partial dots of block `it`
-            slot_a = slot1;
-            s_n = left1 < S ? left1 : S;
+        if (it < nblocks) { // ---- stage 1: the ST partial dots of block `it`, interleaved
             // groups committed so far: R + max(0, it - LAG); block `it` is group `it`
             dpj_wait_pending(it >= LAG ? R - LAG - 1 : R - it - 1);
-            left1 -= S;
+            const uint32_t base = ring_s + (uint32_t)slot1 * block_bytes;
             if (++slot1 == R) slot1 = 0;
-            for (int s = 0; s < s_n; ++s) {
-                const double *run = ring + (size_t)(slot_a * S + s) * p.L;
-                double acc = 0.0;
+            double acc[ST];
+#pragma unroll
+            for (int s = 0; s < ST; ++s) acc[s] = 0.0;
+            if (tv) {
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
-                    const int q = 2 * (t + k * DPJ_THREADS);
-                    if (q < len) {
-                        const double2 v = *reinterpret_cast<const double2 *>(run + q);
-                        acc += dreg[k].x * v.x;
-                        acc += dreg[k].y * v.y;
+#pragma unroll
+                    for (int s = 0; s < ST; ++s) {
+                        const double2 v = dpj_lds128(base + s * run_bytes + off[k]);
+                        acc[s] += dreg[k].x * v.x;
+                        acc[s] += dreg[k].y * v.y;
                     }
                 }
-                acc = dpj_warp_sum(acc);
-                if (lane == 0) red[s * DPJ_WARPS + warp] = acc;
             }
-        }
-        __syncthreads(); // red (stage 1) and dsm (stage 2) are complete
-        if (t < s_n) {
-            double v = 0.0;
 #pragma unroll
-            for (int w = 0; w < DPJ_WARPS; ++w) v += red[t * DPJ_WARPS + w];
-            dpj_st_gpu(p.partial + (size_t)(it * S + t) * Gi + cta, v);
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int s = 0; s < ST; ++s) acc[s] += __shfl_xor_sync(0xffffffffu, acc[s], o);
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int s = 0; s < ST; ++s) red[((it & 1) * ST + s) * DPJ_WARPS + warp] = acc[s];
+            }
+            asm volatile("bar.arrive 1, %0;" ::"n"(DPJ_BLOCK) : "memory"); // hand red[it & 1] to the exchange warps, do not wait
         }
-        if (bb >= 0) { // ---- stage 2, second half: J += d_P * A from the copy still in the ring
+        if (bb >= 0) { // ---- stage 2: J += d_P * A from the copy still in the ring (d_P gathered during the previous iteration)
+            const uint32_t base = ring_s + (uint32_t)slot2 * block_bytes;
             const int slot = slot2;
-            left2 -= S;
             if (++slot2 == R) slot2 = 0;
-            if (has) {
+            if (tv) {
+                double ds[ST];
+#pragma unroll
+                for (int s = 0; s < ST; ++s) ds[s] = dsm[(bb & 1) * ST + s];
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
-                    const int q = 2 * (t + k * DPJ_THREADS);
-                    if (q < len) {
-                        for (int s = 0; s < s_n2; ++s) {
-                            const double2 v = *reinterpret_cast<const double2 *>(ring + (size_t)(slot * S + s) * p.L + q);
-                            const double ds = dsm[s];
-                            jreg[k].x += ds * v.x;
-                            jreg[k].y += ds * v.y;
-                        }
+#pragma unroll
+                    for (int s = 0; s < ST; ++s) {
+                        const double2 v = dpj_lds128(base + s * run_bytes + off[k]);
+                        jreg[k].x += ds[s] * v.x;
+                        jreg[k].y += ds[s] * v.y;
                     }
                 }
             }
             // the slot is private per thread (each thread reads only what it copied), so it can be refilled right away
-            if (bb + R < nblocks) issue(bb + R, slot);
+            if (bb + R < nblocks) issue(slot);
             else dpj_commit();
-            __syncthreads(); // every thread is done with dsm and with red
-        } else {
-            __syncthreads(); // red is reused by the next iteration's stage 1
         }
+        asm volatile("bar.sync 0;" ::: "memory"); // dsm of the next block is complete; red[it & 1] may be rewritten two iterations on
     }
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-        const int q = 2 * (t + k * DPJ_THREADS);
-        if (q < len) *reinterpret_cast<double2 *>(p.j + e0 + q) = jreg[k];
-    }
+    for (int k = 0; k < K; ++k)
+        if (ok[k]) *reinterpret_cast<double2 *>(p.j + e0 + (off[k] >> 3)) = jreg[k];
 }
 
-template <int K>
+template <int K, int ST>
 int dpj_launch(rb_ctx *ctx, const DpjParams &p, size_t smem)
 {
     static int configured_for = -1; // per process and device: the attribute belongs to the function on that device
     if (configured_for != ctx->device) {
-        RB_CUDA(cudaFuncSetAttribute(rb_ri_dp_j_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(DPJ_RING_BYTES + 8192)));
+        RB_CUDA(cudaFuncSetAttribute(rb_ri_dp_j_kernel<K, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(DPJ_RING_BYTES + 8192)));
         configured_for = ctx->device;
     }
     void *args[] = {(void *)&p};
-    RB_CUDA(cudaLaunchCooperativeKernel((const void *)rb_ri_dp_j_kernel<K>, dim3((unsigned)ctx->num_sms), dim3(DPJ_THREADS), args, smem,
+    RB_CUDA(cudaLaunchCooperativeKernel((const void *)rb_ri_dp_j_kernel<K, ST>, dim3((unsigned)ctx->num_sms), dim3(DPJ_BLOCK), args, smem,
                                         ctx->stream));
     RB_LAUNCHED(ctx);
     return RB_OK;
+}
+
+template <int ST>
+int dpj_dispatch_k(rb_ctx *ctx, const DpjParams &p, size_t smem, int kk)
+{
+    switch (kk) {
+    case 1: return dpj_launch<1, ST>(ctx, p, smem);
+    case 2: return dpj_launch<2, ST>(ctx, p, smem);
+    case 3: return dpj_launch<3, ST>(ctx, p, smem);
+    case 4: return dpj_launch<4, ST>(ctx, p, smem);
+    case 5: case 6: return dpj_launch<6, ST>(ctx, p, smem);
+    default: return dpj_launch<8, ST>(ctx, p, smem);
+    }
 }
 
 } // namespace
@@ -258,26 +315,25 @@ extern "C" int rb_ri_dp_j(rb_ctx *ctx, const double *ri3ao, const double *dm, do
     const i64 slab = (i64)nb * nb;
     const i64 G = ctx->num_sms;
     bool fused = slab >= 4 && nx >= 1 && G <= 256 && (slab & 3) == 0 && ((((uintptr_t)ri3ao) | ((uintptr_t)dm) | ((uintptr_t)j)) & 15) == 0;
-    // Opt-in: measured at config C (tools/prof_dpj.py, profiles/r02_dpj_fused.md) the single pass takes 2.0 ms against 1.46 ms for the two
-    // GEMV passes -- DRAM traffic is halved as designed (4.90 GB), but with one 256-thread CTA per SM the loop is bound by its own
-    // instruction latency (ncu: no memory stalls; 4 600 cycles per 2-slab block), not by HBM.
-    {
-        const char *e = getenv("REST_B200_DPJ_FUSED");
-        fused = fused && e && atoi(e) != 0;
-    }
+    // REST_B200_DPJ_FUSED: 0 = never, 1 = wherever the kernel can run; unset = where it was measured to win (below)
+    int mode = -1;
+    if (const char *e = getenv("REST_B200_DPJ_FUSED")) { if (*e) mode = atoi(e) != 0 ? 1 : 0; }
+    if (mode == 0) fused = false;
     i64 L = 0, S = 0, R = 0;
     int kk = 0;
     if (fused) {
         L = (rb_cdiv(slab, G) + 3) & ~(i64)3;
         kk = (int)rb_cdiv(L, 2 * DPJ_THREADS);
-        S = rb_cdiv((i64)20 * 1024, L * 8); // a block should be worth ~0.4 us of the SM's share of HBM bandwidth
-        if (S > DPJ_MAX_S) S = DPJ_MAX_S;
+        S = rb_cdiv((i64)32 * 1024, L * 8); // a block should be worth ~0.7 us of the SM's share of HBM bandwidth
         if (const char *e = getenv("REST_B200_DPJ_S")) { const i64 v = atoll(e); if (v >= 1 && v <= DPJ_MAX_S) S = v; }
-        if (S > nx) S = nx;
-        if (S < 1) S = 1;
+        S = S >= 8 ? 8 : (S >= 4 ? 4 : (S >= 2 ? 2 : 1));
+        while (S > 1 && DPJ_RING_BYTES / (S * L * 8) < 4) S >>= 1;
         R = DPJ_RING_BYTES / (S * L * 8);
         if (R > DPJ_MAX_RING) R = DPJ_MAX_RING;
-        if (kk > 16 || R < 4) fused = false;
+        if (kk > 8 || R < 4 || G > 160) fused = false;
+        // Measured (profiles/r02_dpj_fused.md): 1.22x / 1.16x / 1.32x faster than the two passes at nb = 600 / 800 / 900, but slower when
+        // a CTA's run of a slab is short (nb = 264: 3.8 KB per run, many tiny blocks: the exchange latency of every block shows).
+        if (mode < 0 && (L * 8 < 16 * 1024 || (i64)nx * slab * 8 < ((i64)256 << 20))) fused = false;
     }
     if (!fused) {
         RB_TRY(rb_ri_dp(ctx, ri3ao, dm, d, nb, nx));
@@ -285,7 +341,9 @@ extern "C" int rb_ri_dp_j(rb_ctx *ctx, const double *ri3ao, const double *dm, do
     }
     DpjParams p;
     p.a = ri3ao; p.slab = slab; p.nx = nx; p.dm = dm; p.d = d; p.j = j;
-    p.L = L; p.S = (int)S; p.R = (int)R; p.LAG = (int)(R / 2);
+    // LAG: blocks a slab waits in the ring for its d_P.  The ring also has to keep ~2 blocks of loads in flight, so LAG = R - 2 is the
+    // most slack the shared memory of an SM allows (R = 5 at nb = 600: LAG 3 -> 1.20 ms, 2 -> 1.37 ms, 1 -> 4.4 ms).
+    p.L = L; p.S = (int)S; p.R = (int)R; p.LAG = (int)(R - 2);
     if (const char *e = getenv("REST_B200_DPJ_LAG")) { const int v = atoi(e); if (v >= 1 && v < p.R) p.LAG = v; }
     p.nblocks = rb_cdiv((i64)nx, S);
     p.debug = 0;
@@ -295,17 +353,11 @@ extern "C" int rb_ri_dp_j(rb_ctx *ctx, const double *ri3ao, const double *dm, do
     RB_TRY(rb_ws_reserve(ctx, 1, partial_bytes, &ws));
     p.partial = (double *)ws;
     RB_CUDA(cudaMemsetAsync(p.partial, 0xff, (size_t)partial_bytes, ctx->stream)); // sentinel = "not published yet"
-    const size_t smem = (size_t)(R * S * L * 8) + 128 + (size_t)(DPJ_MAX_S * DPJ_WARPS + DPJ_MAX_S) * 8;
-    switch (kk) {
-    case 1: return dpj_launch<1>(ctx, p, smem);
-    case 2: return dpj_launch<2>(ctx, p, smem);
-    case 3: return dpj_launch<3>(ctx, p, smem);
-    case 4: return dpj_launch<4>(ctx, p, smem);
-    case 5: return dpj_launch<5>(ctx, p, smem);
-    case 6: return dpj_launch<6>(ctx, p, smem);
-    case 7: case 8: return dpj_launch<8>(ctx, p, smem);
-    case 9: case 10: return dpj_launch<10>(ctx, p, smem);
-    case 11: case 12: return dpj_launch<12>(ctx, p, smem);
-    default: return dpj_launch<16>(ctx, p, smem);
+    const size_t smem = (size_t)(R * S * L * 8) + (size_t)(2 * DPJ_MAX_S * DPJ_WARPS + 2 * DPJ_MAX_S) * 8 + 64;
+    switch (S) {
+    case 1: return dpj_dispatch_k<1>(ctx, p, smem, kk);
+    case 2: return dpj_dispatch_k<2>(ctx, p, smem, kk);
+    case 4: return dpj_dispatch_k<4>(ctx, p, smem, kk);
+    default: return dpj_dispatch_k<8>(ctx, p, smem, kk);
     }
 }

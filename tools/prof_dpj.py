@@ -2,6 +2,8 @@
 import sys
 import torch
 sys.path.insert(0, ".")
+import os
+os.environ["REST_B200_DPJ_FUSED"] = "1"
 from rest_tensors_b200.device import Context, ShardedRI  # noqa: E402
 ctx = Context(0)
 for nb, nx in [(600, 1700), (264, 720), (100, 400), (800, 600), (900, 400)]:
