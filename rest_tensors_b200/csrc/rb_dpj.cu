@@ -115,16 +115,21 @@ __global__ void __launch_bounds__(DPJ_BLOCK, 1) rb_ri_dp_j_kernel(const DpjParam
     __syncthreads();
 
     constexpr int GV = 5; // partials per lane: up to 160 CTAs
-    if (warp >= DPJ_WARPS) {
-        // ===================== exchange warps: off the compute warps' critical path =====================
-        // iteration `it`: (a) when the compute warps have left their partial dots of block `it` in red[it & 1] (named barrier 1), add
+    const bool xrole = warp >= DPJ_WARPS;
+    // ===================== exchange warps: off the compute warps' critical path =====================
+    // (both roles run ONE loop and meet in the same __syncthreads() at the end of every iteration)
+    {
+        // iteration `it`: (a) when the compute warps have left their partial dots of block `it` in red[it & 1] (named barrier 1; barrier 2, all 576 threads,
+        // closes every iteration -- named barriers with explicit counts, because the two roles meet from different instructions), add
         // them over the warps and publish the CTA's value; (b) gather block g = it - LAG + 1 from all CTAs -> dsm[g & 1], which the
         // compute warps use in the NEXT iteration.  The gather's loads are issued first, so their L2 round trip overlaps (a).
-        const int xw = warp - DPJ_WARPS;
-        double gv[GV];
+    }
+    const int xw = warp - DPJ_WARPS;
+    double gv[GV];
 #pragma unroll
-        for (int i = 0; i < GV; ++i) gv[i] = 0.0;
-        for (int it = 0; it < nblocks + LAG; ++it) {
+    for (int i = 0; i < GV; ++i) gv[i] = 0.0;
+    auto exchange_iteration = [&](int it) {
+        {
             const int g = it - LAG + 1;
             const bool g_ok = g >= 0 && g < nblocks;
             const int s_ng = g_ok ? (int)(p.nx - (i64)g * ST < ST ? p.nx - (i64)g * ST : ST) : 0;
@@ -134,6 +139,7 @@ __global__ void __launch_bounds__(DPJ_BLOCK, 1) rb_ri_dp_j_kernel(const DpjParam
                 for (int i = 0; i < GV; ++i) gv[i] = (lane + 32 * i < Gi) ? dpj_ld_gpu(row + lane + 32 * i) : 0.0;
             }
             if (it < nblocks) {
+                __syncwarp();
                 asm volatile("bar.sync 1, %0;" ::"n"(DPJ_BLOCK) : "memory");
                 const int s_n = (int)(p.nx - (i64)it * ST < ST ? p.nx - (i64)it * ST : ST);
                 for (int s = xw; s < s_n; s += DPJ_XWARPS) {
@@ -169,22 +175,20 @@ __global__ void __launch_bounds__(DPJ_BLOCK, 1) rb_ri_dp_j_kernel(const DpjParam
                 }
                 if (g_ok && lane == 0) dsm[(g & 1) * ST + s] = v;
             }
-            asm volatile("bar.sync 0;" ::: "memory");
         }
-        return;
-    }
+    };
 
     // ===================== compute warps =====================
     // Per-thread geometry: unit k of this thread is doubles [q_k, q_k + 2) of the run.  Units past the end of the run alias the thread's
     // first unit with weight zero, so the loops below carry no predicates; a thread without any unit sits the arithmetic out.
-    const bool tv = 2 * t < len;
+    const bool tv = !xrole && 2 * t < len;
     uint32_t off[K];
     bool ok[K];
     double2 dreg[K], jreg[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const int q = 2 * (t + k * DPJ_THREADS);
-        ok[k] = q < len;
+        ok[k] = !xrole && q < len;
         off[k] = (uint32_t)(ok[k] ? q : 2 * t) * 8u;
         dreg[k] = ok[k] ? *reinterpret_cast<const double2 *>(p.dm + e0 + q) : make_double2(0.0, 0.0);
         jreg[k] = make_double2(0.0, 0.0);
@@ -208,13 +212,17 @@ __global__ void __launch_bounds__(DPJ_BLOCK, 1) rb_ri_dp_j_kernel(const DpjParam
         src_next += (i64)ST * p.slab;
         left_issue -= ST;
     };
-    for (int b = 0; b < R; ++b) { // prologue: R groups (empty ones past the end keep the group arithmetic uniform)
-        if (b < nblocks) issue(b);
-        else dpj_commit();
-    }
+    if (!xrole)
+        for (int b = 0; b < R; ++b) { // prologue: R groups (empty ones past the end keep the group arithmetic uniform)
+            if (b < nblocks) issue(b);
+            else dpj_commit();
+        }
 
     int slot1 = 0, slot2 = 0;
     for (int it = 0; it < nblocks + LAG; ++it) {
+        if (xrole) {
+            exchange_iteration(it);
+        } else {
         const int bb = it - LAG;
         if (it < nblocks) { // ---- stage 1: the ST partial dots of block `it`, interleaved
             // groups committed so far: R + max(0, it - LAG); block `it` is group `it`
@@ -244,6 +252,7 @@ __global__ void __launch_bounds__(DPJ_BLOCK, 1) rb_ri_dp_j_kernel(const DpjParam
 #pragma unroll
                 for (int s = 0; s < ST; ++s) red[((it & 1) * ST + s) * DPJ_WARPS + warp] = acc[s];
             }
+            __syncwarp(); // lane 0 has stored: arrive as a whole warp
             asm volatile("bar.arrive 1, %0;" ::"n"(DPJ_BLOCK) : "memory"); // hand red[it & 1] to the exchange warps, do not wait
         }
         if (bb >= 0) { // ---- stage 2: J += d_P * A from the copy still in the ring (d_P gathered during the previous iteration)
@@ -268,8 +277,10 @@ __global__ void __launch_bounds__(DPJ_BLOCK, 1) rb_ri_dp_j_kernel(const DpjParam
             if (bb + R < nblocks) issue(slot);
             else dpj_commit();
         }
-        asm volatile("bar.sync 0;" ::: "memory"); // dsm of the next block is complete; red[it & 1] may be rewritten two iterations on
+        } // compute role
+        __syncthreads(); // both roles: dsm of the next block is complete; red[it & 1] may be rewritten two iterations on
     }
+    if (xrole) return;
 #pragma unroll
     for (int k = 0; k < K; ++k)
         if (ok[k]) *reinterpret_cast<double2 *>(p.j + e0 + (off[k] >> 3)) = jreg[k];

@@ -74,5 +74,16 @@ eri = ctx.empty(npair * npair); eri.zero_()
 blk = ctx.empty(5 * 7 * 4 * 6); ctx.fill_linear(blk, blk.numel(), 10, 0, 1.0)
 ctx.erifold4_chunk_copy(eri, npair, npair, npair, ((0, 5), (5, 12), (2, 6), (6, 12)), blk, 1)
 ctx.erifold4_chunk_copy(eri, npair, npair, npair, ((0, 5), (0, 7), (0, 4), (0, 6)), blk, 0)
+# d_P + J from one read (persistent cooperative kernel: LDGSTS ring, named-barrier hand-off to the exchange warps, sentinel-valued exchange)
+import os  # noqa: E402
+os.environ["REST_B200_DPJ_FUSED"] = "1"
+for nb2, nx2 in [(40, 70), (128, 33), (264, 40)]:
+    sh2 = ShardedRI(ctx, nb2, nx2).fill_synthetic()
+    dm2 = ctx.empty(nb2 * nb2); ctx.fill_linear(dm2, nb2 * nb2, 4, 0, 1.0 / nb2)
+    d_ref = sh2.dp(dm2); j_ref = sh2.j(d_ref, reduce=False)
+    d1, j1 = sh2.dp_j(dm2, reduce=False)
+    assert float((d1 - d_ref).abs().max()) <= 1e-13 * float(d_ref.abs().max())
+    assert float((j1 - j_ref).abs().max()) <= 1e-13 * float(j_ref.abs().max())
+del os.environ["REST_B200_DPJ_FUSED"]
 torch.cuda.synchronize()
 print("sanitize target ok")
