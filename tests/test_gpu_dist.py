@@ -79,6 +79,14 @@ def _worker(rank, world, port, nb, naux, no, ret):
         o.special_dgemm_f_01(t_ref, [nb, nb, naux], (0, nb), 0, (0, naux), bmat, [naux, naux], (0, naux), (0, naux), 1.0, 0.0)
         torch.cuda.synchronize()
         errs.append(err(sh.data.cpu().numpy(), t_ref[sh.p_lo * nb * nb: sh.p_hi * nb * nb]))
+        # d_P and J from one read of the shard (rb_ri_dp_j), J completed by the same all-reduce
+        os.environ["REST_B200_DPJ_FUSED"] = "1"
+        sh3 = ShardedRI(ctx, nb, naux, rank, world).fill_synthetic()
+        d1p, j1p = sh3.dp_j(dev(dm))
+        del os.environ["REST_B200_DPJ_FUSED"]
+        torch.cuda.synchronize()
+        errs.append(err(j1p.cpu().numpy(), o.ri_j(ri, d_ref, nb, naux)))
+        errs.append(err(gather_dp(d1p, naux, sh3.p_lo, world, ctx).cpu().numpy(), d_ref))
         # one launch per SCF iteration at N > 1: d_P + J + K with both all-reduces recorded into a CUDA graph on every rank
         side = torch.cuda.Stream()
         torch.cuda.synchronize()

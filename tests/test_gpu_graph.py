@@ -175,3 +175,25 @@ def test_host_copies_can_be_part_of_the_recording(side):
         rec.graph.launch(); torch.cuda.current_stream().synchronize()
         assert torch.equal(hj, wj) and torch.equal(hk, wk), it
     rec.graph.close()
+
+
+def test_single_pass_dp_j_can_be_recorded(side, monkeypatch):
+    """rb_ri_dp_j's cooperative launch (and the sentinel fill of its exchange array) inside a recording: replay == direct call"""
+    monkeypatch.setenv("REST_B200_DPJ_FUSED", "1")
+    ctx = side
+    st = Step(ctx, 128, 60, 8)
+    d2, j2 = ctx.empty(60), ctx.empty(128 * 128)
+
+    def seq():
+        st.sh.dp_j(st.dm, out_d=d2, out_j=j2, reduce=False)
+        st.sh.k(st.ct, st.no, out=st.k)
+    seq()
+    want = [d2.clone(), j2.clone(), st.k.clone()]
+    with ctx.record() as rec:
+        seq()
+    for _ in range(3):
+        d2.zero_(); j2.zero_(); st.k.zero_()
+        rec.graph.launch()
+        torch.cuda.current_stream().synchronize()
+        assert torch.equal(d2, want[0]) and torch.equal(j2, want[1]) and torch.equal(st.k, want[2])
+    rec.graph.close()
