@@ -115,6 +115,13 @@ impl<'a> ShardedRI<'a> {
     pub fn j(&self, d_local: &DeviceBuffer, j: &DeviceBuffer) {
         unsafe { check(rb_ri_j_allreduce(self.ctx.raw, self.data.ptr, d_local.ptr, j.ptr, self.nb as c_int, self.nx()), "rb_ri_j_allreduce"); }
     }
+    /// d[P_lo..P_hi) and J (complete on every rank) from ONE read of the shard where that is faster, else the two passes
+    pub fn dp_j(&self, dm: &DeviceBuffer, d_local: &DeviceBuffer, j: &DeviceBuffer) {
+        unsafe {
+            check(rb_ri_dp_j(self.ctx.raw, self.data.ptr, dm.ptr, d_local.ptr, j.ptr, self.nb as c_int, self.nx()), "rb_ri_dp_j");
+            check(rb_allreduce_sum(self.ctx.raw, j.ptr, (self.nb * self.nb) as i64), "rb_allreduce_sum");
+        }
+    }
     /// K complete on every rank
     pub fn k(&self, ct: &DeviceBuffer, no: usize, k: &DeviceBuffer) {
         unsafe { check(rb_ri_k_allreduce(self.ctx.raw, self.data.ptr, ct.ptr, no as c_int, k.ptr, self.nb as c_int, self.nx()), "rb_ri_k_allreduce"); }
