@@ -52,3 +52,14 @@ def test_library_links_no_math_library():
     out = subprocess.check_output(["ldd", so], text=True)
     for lib in ("cublas", "cusolver", "cutlass", "nccl", "openblas", "lapack"):
         assert lib not in out.lower(), f"librest_b200.so must not link {lib} (NCCL is bound at run time with dlopen)"
+
+
+def test_single_pass_dp_j_kernel_is_what_the_design_says():
+    """rb_dpj.o: 16-byte LDGSTS (global -> shared without registers) tracked by commit groups, GPU-scope (L1-bypassing) loads / stores for
+    the sentinel-valued exchange, a non-blocking named-barrier arrive for the hand-off to the exchange warps, and no atomics."""
+    s = _sass("rb_dpj.o")
+    assert _count(s, r"\bLDGSTS\.E\.BYPASS\.128\b") >= 100
+    assert _count(s, r"\bLDGDEPBAR\b") >= 24 and _count(s, r"\bDEPBAR\.LE\b") >= 24
+    assert _count(s, r"\bLDG\.E\.64\.STRONG\.GPU\b") >= 24 and _count(s, r"\bSTG\.E\.64\.STRONG\.GPU\b") >= 24
+    assert _count(s, r"\bBAR\.ARV\b") >= 24
+    assert _count(s, r"\bATOM[A-Z.]*\b|\bRED\.[A-Z.]*\b") == 0
