@@ -46,6 +46,7 @@ struct DpjParams {
     int debug;          // 1: tools/prof_dpj_sweep.py only -- skip the cross-CTA gather (WRONG results; isolates the cost of the exchange)
 };
 
+constexpr int DPJ_NOT_RESIDENT = -77; // internal status of dpj_launch: cooperative launch impossible here
 constexpr long long DPJ_SENTINEL = -1LL; // all ones: a NaN payload that FMA / add never produce
 
 __device__ __forceinline__ uint32_t dpj_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -295,8 +296,15 @@ int dpj_launch(rb_ctx *ctx, const DpjParams &p, size_t smem)
         configured_for = ctx->device;
     }
     void *args[] = {(void *)&p};
-    RB_CUDA(cudaLaunchCooperativeKernel((const void *)rb_ri_dp_j_kernel<K, ST>, dim3((unsigned)ctx->num_sms), dim3(DPJ_BLOCK), args, smem,
-                                        ctx->stream));
+    const cudaError_t e = cudaLaunchCooperativeKernel((const void *)rb_ri_dp_j_kernel<K, ST>, dim3((unsigned)ctx->num_sms), dim3(DPJ_BLOCK),
+                                                      args, smem, ctx->stream);
+    if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorNotSupported) {
+        // not every SM is available to this process (MPS share, MIG slice, ...): the grid-wide exchange needs all CTAs resident, so
+        // the caller runs the two GEMV passes instead (still on the GPU)
+        (void)cudaGetLastError();
+        return DPJ_NOT_RESIDENT;
+    }
+    RB_CUDA(e);
     RB_LAUNCHED(ctx);
     return RB_OK;
 }
@@ -365,10 +373,16 @@ extern "C" int rb_ri_dp_j(rb_ctx *ctx, const double *ri3ao, const double *dm, do
     p.partial = (double *)ws;
     RB_CUDA(cudaMemsetAsync(p.partial, 0xff, (size_t)partial_bytes, ctx->stream)); // sentinel = "not published yet"
     const size_t smem = (size_t)(R * S * L * 8) + (size_t)(2 * DPJ_MAX_S * DPJ_WARPS + 2 * DPJ_MAX_S) * 8 + 64;
+    int st;
     switch (S) {
-    case 1: return dpj_dispatch_k<1>(ctx, p, smem, kk);
-    case 2: return dpj_dispatch_k<2>(ctx, p, smem, kk);
-    case 4: return dpj_dispatch_k<4>(ctx, p, smem, kk);
-    default: return dpj_dispatch_k<8>(ctx, p, smem, kk);
+    case 1: st = dpj_dispatch_k<1>(ctx, p, smem, kk); break;
+    case 2: st = dpj_dispatch_k<2>(ctx, p, smem, kk); break;
+    case 4: st = dpj_dispatch_k<4>(ctx, p, smem, kk); break;
+    default: st = dpj_dispatch_k<8>(ctx, p, smem, kk); break;
     }
+    if (st == DPJ_NOT_RESIDENT) {
+        RB_TRY(rb_ri_dp(ctx, ri3ao, dm, d, nb, nx));
+        return rb_ri_j(ctx, ri3ao, d, j, nb, nx);
+    }
+    return st;
 }
