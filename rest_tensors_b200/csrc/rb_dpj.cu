@@ -20,7 +20,7 @@
 // 16 compute warps + 2 exchange warps per CTA: the exchange warps publish the CTA's partial dots and gather everybody's, one block ahead
 // of the compute warps, so the grid-wide exchange is off the critical path.  What bounds the kernel is shared memory: loads in flight
 // (2.4 us of latency x 44 GB/s per SM = 106 KB) + the block being worked on + the blocks waiting for their d_P have to fit 200 KB, which
-// leaves two blocks in flight -> 4.1 TB/s of the single read = 1.2-1.3x the two passes for nb = 600-900.
+// leaves one to two blocks in flight -> 4.85 TB/s of the single read = 1.34-1.46x the two passes for nb = 600-900.
 // Shapes the ring cannot hold (nb > ~1100), odd nb^2 alignment, short runs (nb < ~550) or small tensors use the two GEMV kernels.
 #include "rb_common.cuh"
 
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(DPJ_BLOCK, 1) rb_ri_dp_j_kernel(const DpjParam
     constexpr int GV = 5; // partials per lane: up to 160 CTAs
     const bool xrole = warp >= DPJ_WARPS;
     // ===================== exchange warps: off the compute warps' critical path =====================
-    // (both roles run ONE loop and meet in the same __syncthreads() at the end of every iteration)
+    // (both roles run ONE loop; they are coupled by two named barriers, see the end of the loop)
     {
         // iteration `it`: (a) when the compute warps have left their partial dots of block `it` in red[it & 1] (named barrier 1; barrier 2, all 576 threads,
         // closes every iteration -- named barriers with explicit counts, because the two roles meet from different instructions), add
@@ -139,9 +139,9 @@ __global__ void __launch_bounds__(DPJ_BLOCK, 1) rb_ri_dp_j_kernel(const DpjParam
 #pragma unroll
                 for (int i = 0; i < GV; ++i) gv[i] = (lane + 32 * i < Gi) ? dpj_ld_gpu(row + lane + 32 * i) : 0.0;
             }
+            __syncwarp();
+            asm volatile("bar.sync 1, %0;" ::"n"(DPJ_BLOCK) : "memory"); // every iteration, so that neither role runs a barrier phase ahead
             if (it < nblocks) {
-                __syncwarp();
-                asm volatile("bar.sync 1, %0;" ::"n"(DPJ_BLOCK) : "memory");
                 const int s_n = (int)(p.nx - (i64)it * ST < ST ? p.nx - (i64)it * ST : ST);
                 for (int s = xw; s < s_n; s += DPJ_XWARPS) {
                     double v = lane < DPJ_WARPS ? red[((it & 1) * ST + s) * DPJ_WARPS + lane] : 0.0;
@@ -175,6 +175,10 @@ __global__ void __launch_bounds__(DPJ_BLOCK, 1) rb_ri_dp_j_kernel(const DpjParam
                     }
                 }
                 if (g_ok && lane == 0) dsm[(g & 1) * ST + s] = v;
+            }
+            if (it + 1 < nblocks + LAG) { // this iteration's dsm is complete: the compute warps wait for it in their NEXT iteration
+                __syncwarp();
+                asm volatile("bar.arrive 3, %0;" ::"n"(DPJ_BLOCK) : "memory");
             }
         }
     };
@@ -253,9 +257,13 @@ __global__ void __launch_bounds__(DPJ_BLOCK, 1) rb_ri_dp_j_kernel(const DpjParam
 #pragma unroll
                 for (int s = 0; s < ST; ++s) red[((it & 1) * ST + s) * DPJ_WARPS + warp] = acc[s];
             }
-            __syncwarp(); // lane 0 has stored: arrive as a whole warp
-            asm volatile("bar.arrive 1, %0;" ::"n"(DPJ_BLOCK) : "memory"); // hand red[it & 1] to the exchange warps, do not wait
         }
+        // Hand-shake with the exchange warps, in this order: first wait until they are done with the PREVIOUS iteration (normally long
+        // ago: they had this iteration's stage 1 and the last stage 2 to do it), only then hand them red[it & 1] -- so that no barrier ever
+        // receives the arrivals of two iterations.
+        __syncwarp();
+        if (it >= 1) asm volatile("bar.sync 3, %0;" ::"n"(DPJ_BLOCK) : "memory");
+        asm volatile("bar.arrive 1, %0;" ::"n"(DPJ_BLOCK) : "memory");
         if (bb >= 0) { // ---- stage 2: J += d_P * A from the copy still in the ring (d_P gathered during the previous iteration)
             const uint32_t base = ring_s + (uint32_t)slot2 * block_bytes;
             const int slot = slot2;
@@ -279,7 +287,11 @@ __global__ void __launch_bounds__(DPJ_BLOCK, 1) rb_ri_dp_j_kernel(const DpjParam
             else dpj_commit();
         }
         } // compute role
-        __syncthreads(); // both roles: dsm of the next block is complete; red[it & 1] may be rewritten two iterations on
+        // No block-wide barrier per iteration: the two roles are coupled by the named barriers alone -- 1: red[it & 1] ready (compute
+        // arrives, exchange waits), 3: exchange iteration done (exchange arrives, compute waits in its next iteration, before arriving
+        // on 1 again).  red[it & 1] is rewritten in stage 1 of iteration it + 2, after the compute warps passed barrier 3 in iteration
+        // it + 1, i.e. after the exchange warps finished iteration it; dsm[g & 1] is rewritten in exchange iteration it + 2, which starts
+        // behind barrier 1 of it + 2, i.e. after the compute warps' stage 2 of iteration it + 1 that read it.
     }
     if (xrole) return;
 #pragma unroll
@@ -350,7 +362,7 @@ extern "C" int rb_ri_dp_j(rb_ctx *ctx, const double *ri3ao, const double *dm, do
         R = DPJ_RING_BYTES / (S * L * 8);
         if (R > DPJ_MAX_RING) R = DPJ_MAX_RING;
         if (kk > 8 || R < 4 || G > 160) fused = false;
-        // Measured (profiles/r02_dpj_fused.md): 1.22x / 1.16x / 1.32x faster than the two passes at nb = 600 / 800 / 900, but slower when
+        // Measured (profiles/r02_dpj_fused.md): 1.45x / 1.34x / 1.46x faster than the two passes at nb = 600 / 800 / 900, but slower when
         // a CTA's run of a slab is short (nb = 264: 3.8 KB per run, many tiny blocks: the exchange latency of every block shows).
         if (mode < 0 && (L * 8 < 16 * 1024 || (i64)nx * slab * 8 < ((i64)256 << 20))) fused = false;
     }

@@ -9,7 +9,7 @@ nb, nx = 600, 1700
 sh = ShardedRI(ctx, nb, nx).fill_synthetic()
 dm = ctx.empty(nb * nb); ctx.fill_linear(dm, nb * nb, 4, 0, 1.0 / nb)
 d = ctx.empty(nx); j = ctx.empty(nb * nb)
-for S, LAG, dbg in [(1, 5, 0), (1, 5, 1), (1, 3, 0), (2, 2, 0), (2, 2, 1), (2, 1, 0), (2, 3, 0)]:
+for S, LAG, dbg in [(2, 3, 0), (2, 2, 0), (2, 3, 1), (1, 3, 0), (1, 4, 0), (1, 5, 0), (1, 6, 0), (1, 7, 0)]:
     os.environ["REST_B200_DPJ_S"] = str(S); os.environ["REST_B200_DPJ_LAG"] = str(LAG); os.environ["REST_B200_DPJ_DEBUG"] = str(dbg)
     for _ in range(2):
         sh.dp_j(dm, out_d=d, out_j=j, reduce=False)
