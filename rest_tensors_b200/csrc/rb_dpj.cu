@@ -373,7 +373,7 @@ extern "C" int rb_ri_dp_j(rb_ctx *ctx, const double *ri3ao, const double *dm, do
     DpjParams p;
     p.a = ri3ao; p.slab = slab; p.nx = nx; p.dm = dm; p.d = d; p.j = j;
     // LAG: blocks a slab waits in the ring for its d_P.  The ring also has to keep ~2 blocks of loads in flight, so LAG = R - 2 is the
-    // most slack the shared memory of an SM allows (R = 5 at nb = 600: LAG 3 -> 1.20 ms, 2 -> 1.37 ms, 1 -> 4.4 ms).
+    // most slack the shared memory of an SM allows (R = 5 at nb = 600: LAG 3 -> 1.00 ms, 2 -> 1.13 ms).
     p.L = L; p.S = (int)S; p.R = (int)R; p.LAG = (int)(R - 2);
     if (const char *e = getenv("REST_B200_DPJ_LAG")) { const int v = atoi(e); if (v >= 1 && v < p.R) p.LAG = v; }
     p.nblocks = rb_cdiv((i64)nx, S);
