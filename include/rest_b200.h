@@ -252,7 +252,7 @@ int rb_ri_j(rb_ctx *ctx, const double *ri3ao, const double *d, double *j, int nb
  * CTA owns a fixed ij range in all slabs (its D and J entries stay in registers), the slabs stream through a shared-memory ring of 1-D
  * bulk copies, the per-slab dot products are combined across CTAs in a fixed order (deterministic, no FP64 atomics) and J is updated
  * from the copy still in shared memory.  Same results as rb_ri_dp followed by rb_ri_j up to the summation order inside d_P (1e-15).
- * The single-pass kernel runs where it was measured to win (nb ~ 550 .. 1100, tensors >= 256 MB: 1.01 vs 1.46 ms at config C, 0.57 vs
+ * The single-pass kernel runs where it was measured to win (nb ~ 550 .. 950, tensors >= 256 MB: 1.01 vs 1.46 ms at config C, 0.57 vs
  * 0.84 ms at nb = 900); elsewhere (short runs, nb > ~1100, odd nb) this call is rb_ri_dp followed by rb_ri_j.  REST_B200_DPJ_FUSED=0 / 1
  * forces the two passes / the single pass wherever it can run. */
 int rb_ri_dp_j(rb_ctx *ctx, const double *ri3ao, const double *dm, double *d, double *j, int nb, int nx);

@@ -32,7 +32,7 @@ constexpr int DPJ_XWARPS = 2;                  // exchange warps (publish the CT
 constexpr int DPJ_BLOCK = DPJ_THREADS + 32 * DPJ_XWARPS;
 constexpr int DPJ_MAX_S = 8;
 constexpr int DPJ_MAX_RING = 10;
-constexpr i64 DPJ_RING_BYTES = 200 * 1024;
+constexpr i64 DPJ_RING_BYTES = 220 * 1024;
 
 struct DpjParams {
     const double *a;
@@ -304,7 +304,7 @@ int dpj_launch(rb_ctx *ctx, const DpjParams &p, size_t smem)
 {
     static int configured_for = -1; // per process and device: the attribute belongs to the function on that device
     if (configured_for != ctx->device) {
-        RB_CUDA(cudaFuncSetAttribute(rb_ri_dp_j_kernel<K, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(DPJ_RING_BYTES + 8192)));
+        RB_CUDA(cudaFuncSetAttribute(rb_ri_dp_j_kernel<K, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(DPJ_RING_BYTES + 4096)));
         configured_for = ctx->device;
     }
     void *args[] = {(void *)&p};
@@ -362,9 +362,10 @@ extern "C" int rb_ri_dp_j(rb_ctx *ctx, const double *ri3ao, const double *dm, do
         R = DPJ_RING_BYTES / (S * L * 8);
         if (R > DPJ_MAX_RING) R = DPJ_MAX_RING;
         if (kk > 8 || R < 4 || G > 160) fused = false;
-        // Measured (profiles/r02_dpj_fused.md): 1.45x / 1.34x / 1.46x faster than the two passes at nb = 600 / 800 / 900, but slower when
+        // Measured (profiles/r02_dpj_fused.md): 1.42x / 1.70x / 1.29x / 1.60x faster than the two passes at nb = 600 / 700 / 800 / 900, but slower when
         // a CTA's run of a slab is short (nb = 264: 3.8 KB per run, many tiny blocks: the exchange latency of every block shows).
-        if (mode < 0 && (L * 8 < 16 * 1024 || (i64)nx * slab * 8 < ((i64)256 << 20))) fused = false;
+        // ... and nb ~ 1000 (54 KB runs: a ring of 4 one-slab blocks) measured 0.99x: no gain, so the two passes stay there as well.
+        if (mode < 0 && (L * 8 < 16 * 1024 || L * 8 > 48 * 1024 || (i64)nx * slab * 8 < ((i64)256 << 20))) fused = false;
     }
     if (!fused) {
         RB_TRY(rb_ri_dp(ctx, ri3ao, dm, d, nb, nx));
@@ -374,7 +375,7 @@ extern "C" int rb_ri_dp_j(rb_ctx *ctx, const double *ri3ao, const double *dm, do
     p.a = ri3ao; p.slab = slab; p.nx = nx; p.dm = dm; p.d = d; p.j = j;
     // LAG: blocks a slab waits in the ring for its d_P.  The ring also has to keep ~2 blocks of loads in flight, so LAG = R - 2 is the
     // most slack the shared memory of an SM allows (R = 5 at nb = 600: LAG 3 -> 1.00 ms, 2 -> 1.13 ms).
-    p.L = L; p.S = (int)S; p.R = (int)R; p.LAG = (int)(R - 2);
+    p.L = L; p.S = (int)S; p.R = (int)R; p.LAG = (int)(R - 2 < 3 ? R - 2 : 3);
     if (const char *e = getenv("REST_B200_DPJ_LAG")) { const int v = atoi(e); if (v >= 1 && v < p.R) p.LAG = v; }
     p.nblocks = rb_cdiv((i64)nx, S);
     p.debug = 0;

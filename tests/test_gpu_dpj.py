@@ -23,10 +23,10 @@ def _setup(ctx, nb, nx, seed=7):
 
 
 @pytest.mark.parametrize("nb,nx", [(100, 400), (264, 720), (600, 300), (40, 70), (10, 3), (2, 1), (64, 1), (128, 33), (800, 40), (900, 24),
-                                   (45, 77), (1000, 12), (36, 2000)])
+                                   (45, 77), (1000, 12), (1200, 6), (36, 2000)])
 def test_fused_dp_j_matches_two_passes(ctx, nb, nx):
     """same d_P and J as the two GEMV passes to summation-order accuracy (1e-13 of the largest element), bit-identical across
-    repeated launches and with every workspace poisoned in between; odd nb and nb >= 1000 take the fallback and are then identical."""
+    repeated launches and with every workspace poisoned in between; odd nb and nb > 1100 take the fallback and are then identical."""
     sh, dm = _setup(ctx, nb, nx)
     d_ref = sh.dp(dm); j_ref = sh.j(d_ref, reduce=False)
     d1, j1 = sh.dp_j(dm, reduce=False)
@@ -37,7 +37,7 @@ def test_fused_dp_j_matches_two_passes(ctx, nb, nx):
     sd, sj = float(d_ref.abs().max()), float(j_ref.abs().max())
     assert float((d1 - d_ref).abs().max()) <= 1e-13 * sd, float((d1 - d_ref).abs().max()) / sd
     assert float((j1 - j_ref).abs().max()) <= 1e-13 * sj, float((j1 - j_ref).abs().max()) / sj
-    if nb % 2 == 1 or nb >= 1000:
+    if nb % 2 == 1 or nb > 1100:
         assert torch.equal(d1, d_ref) and torch.equal(j1, j_ref)
 
 

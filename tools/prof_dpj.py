@@ -6,7 +6,7 @@ import os
 os.environ["REST_B200_DPJ_FUSED"] = "1"
 from rest_tensors_b200.device import Context, ShardedRI  # noqa: E402
 ctx = Context(0)
-for nb, nx in [(600, 1700), (264, 720), (100, 400), (800, 600), (900, 400)]:
+for nb, nx in [(600, 1700), (700, 800), (800, 600), (900, 400), (1000, 400), (264, 720)]:
     sh = ShardedRI(ctx, nb, nx).fill_synthetic()
     dm = ctx.empty(nb * nb); ctx.fill_linear(dm, nb * nb, 4, 0, 1.0 / nb)
     d = ctx.empty(nx); j = ctx.empty(nb * nb)
